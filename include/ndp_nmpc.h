@@ -1,0 +1,164 @@
+/*
+ * ndp_nmpc.h -- C ABI of the B200-native batched NMPC engine (libndp_nmpc_b200.so).
+ *
+ * Drop-in boundary for the per-step hot loop of Li-Jinjie/ndp_nmpc_qd.  The reference
+ * reaches its solver through acados_template's ctypes binding of a generated shared
+ * library (AcadosOcpSolver, constructed at
+ * ndp_nmpc/scripts/nmpc_ctl/nmpc_body_rate_ctl.py:84); the entry points below are what
+ * that binding would bind instead.  Each one cites the reference call it replaces.
+ *
+ * Conventions
+ *   - plain C, no torch / C++ types.  All `dev` pointers are DEVICE pointers borrowed from
+ *     the caller (e.g. tensor.data_ptr()); the library never frees caller memory and owns
+ *     its iterate / workspace.  `stream` is a cudaStream_t passed as void* (NULL = default).
+ *   - element type of every `dev` array is the engine precision chosen at ndp_create
+ *     (float for NDP_F32, double for NDP_F64) unless stated otherwise.
+ *   - every function returns 0 on success, <0 on API misuse (NDP_E_*), >0 = cudaError_t.
+ *     ndp_last_error() gives a message.  Per-problem solver status uses acados' codes
+ *     (0 success, 1 NaN, 2 max iter, 3 min step, 4 QP failure), as tested by
+ *     nmpc_body_rate_ctl.py:109-110.
+ *   - a handle is not re-entrant; calls on one handle are ordered on the given stream, so a
+ *     ndp_get issued while a solve is in flight returns a consistent snapshot (the
+ *     reference's viz thread reads solver.get(i,"x") concurrently, nmpc_node.py:233-237).
+ *   - batched layout: [B][stage][component], contiguous per problem.
+ */
+#ifndef NDP_NMPC_H
+#define NDP_NMPC_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NDP_NX 10 /* state  (p, v, qw qx qy qz)   nmpc_body_rate_ctl.py:120-130 */
+#define NDP_NU 4  /* input  (wx, wy, wz, c)       nmpc_body_rate_ctl.py:139-144 */
+#define NDP_NY 14 /* cost output y = [x-part; u]  nmpc_body_rate_ctl.py:168-180 */
+#define NDP_NP 8  /* parameter slot: q_r(4), f(3), pad   ndp_nmpc_body_rate_ctl.py:197 */
+#define NDP_N_MAX 128
+
+enum ndp_precision { NDP_F32 = 0, NDP_F64 = 1 };
+
+/* fields of ndp_set / ndp_get -- the strings of AcadosOcpSolver.set/get used by the
+ * reference ("x","u","yref","p": nmpc_body_rate_ctl.py:89-104; get "x": nmpc_node.py:237) */
+enum ndp_field {
+    NDP_FIELD_X = 0,    /* [10]  iterate state, stages 0..N     */
+    NDP_FIELD_U = 1,    /* [4]   iterate input, stages 0..N-1   */
+    NDP_FIELD_YREF = 2, /* [14]  stages 0..N-1; [10] at stage N */
+    NDP_FIELD_P = 3     /* [np]  np = 4 (q_r) or 7 (q_r, f)     */
+};
+
+enum ndp_error {
+    NDP_OK = 0,
+    NDP_E_ARG = -1,    /* bad argument (null pointer, unknown field, stage out of range) */
+    NDP_E_CONFIG = -2, /* unsupported configuration */
+    NDP_E_ALLOC = -3,
+    NDP_E_STATE = -4
+};
+
+/* Mirrors the constants the reference's controller reads from params/nmpc_params.py:9-35
+ * and params/fhnp_params.py:9-19 when it builds the AcadosOcp (nmpc_body_rate_ctl.py:36-80). */
+typedef struct ndp_config {
+    int32_t N;          /* shooting intervals (N_node)                   */
+    int32_t precision;  /* enum ndp_precision                            */
+    int32_t batch;      /* number of independent problems in the handle  */
+    int32_t np;         /* 4 = NMPCBodyRateController, 7 = NDPNMPCBodyRateController */
+    double T;           /* horizon length [s] (T_horizon); h = T / N     */
+    double mass;        /* [kg]                                          */
+    double gravity;     /* [m/s^2]                                       */
+    double Q[NDP_NX];   /* diag of Q   (W = blkdiag(Q,R), W_e = Q)       */
+    double R[NDP_NU];   /* diag of R                                     */
+    double u_min[NDP_NU], u_max[NDP_NU]; /* lbu/ubu, stages 0..N-1       */
+    double v_min[3], v_max[3];           /* lbx/ubx on idx 3,4,5, stages 1..N-1 */
+    int32_t ipm_max_iter; /* acados qp_solver_iter_max (50)              */
+    int32_t polish_max;   /* active-set refinement rounds after the IPM  */
+    double ipm_tol_mu;    /* IPM complementarity target (<=0: precision default) */
+} ndp_config;
+
+typedef struct ndp_handle ndp_handle;
+
+/* Fill cfg with the reference's constants (N=20, T=2, weights, bounds, mass, gravity). */
+void ndp_default_config(ndp_config* cfg);
+
+/* AcadosOcpSolver(ocp, json_file, build) -- nmpc_body_rate_ctl.py:84.  Allocates the iterate
+ * (zero-initialised like acados), reference/parameter storage and workspace on the current
+ * CUDA device. */
+int ndp_create(const ndp_config* cfg, ndp_handle** out);
+int ndp_destroy(ndp_handle* h);
+
+/* solver.set(stage, field, value) -- nmpc_body_rate_ctl.py:89-91,97-104.
+ * stage >= 0: dev -> [B][dim] with row stride ld (elements), one stage for all problems.
+ * stage == -1: dev -> [B][n_stages][dim] contiguous, all stages at once. */
+int ndp_set(ndp_handle* h, int field, int stage, const void* dev, int64_t ld, void* stream);
+
+/* solver.get(stage, field) -- nmpc_node.py:235-237 (same addressing as ndp_set). */
+int ndp_get(ndp_handle* h, int field, int stage, void* dev, int64_t ld, void* stream);
+
+/* controller.reset(xr, ur) -- nmpc_body_rate_ctl.py:86-91: iterate <- (xr[B][N+1][10], ur[B][N][4]). */
+int ndp_reset(ndp_handle* h, const void* xr_dev, const void* ur_dev, void* stream);
+
+/* The 42 solver.set calls of controller.update() in one launch --
+ * nmpc_body_rate_ctl.py:95-104 / ndp_nmpc_body_rate_ctl.py:93-104:
+ * yref_k = [xr_k; ur_k], p_k = [xr_k[6:10]; f_k].  f_dev may be NULL (zeros / np == 4). */
+int ndp_set_reference(ndp_handle* h, const void* xr_dev, const void* ur_dev, const void* f_dev, void* stream);
+
+/* u0 = solver.solve_for_x0(x0) -- nmpc_body_rate_ctl.py:107: one SQP_RTI step for every problem
+ * (x0 constraint, linearise, QP, full step).  x0_dev [B][10], u0_dev [B][4] (may be NULL). */
+int ndp_solve(ndp_handle* h, const void* x0_dev, void* u0_dev, void* stream);
+
+/* solver.status -- nmpc_body_rate_ctl.py:109.  status_dev: int32 [B]. */
+int ndp_status(ndp_handle* h, int32_t* status_dev, void* stream);
+
+/* Per-problem solve statistics: int32 [B][4] = {Riccati factorisations, IPM iterations,
+ * active-set rounds, active bounds at the solution}. */
+int ndp_stats(ndp_handle* h, int32_t* stats_dev, void* stream);
+
+/* Number of kernel launches issued on behalf of this handle so far. */
+int64_t ndp_launch_count(const ndp_handle* h);
+
+const char* ndp_last_error(void);
+
+/* ---- batched RK4 integrator with forward sensitivities (standalone entry point) ----
+ * acados ERK sim with sens_forw (integrator_type="ERK", nmpc_body_rate_ctl.py:76).
+ * x[M][10], u[M][4], f[M][3] (may be NULL) -> xn[M][10], AB[M][10][14] = [S_x S_u] row-major. */
+int ndp_rk4_sens(int precision, int64_t M, double h, double mass, double gravity, const void* x_dev,
+                 const void* u_dev, const void* f_dev, void* xn_dev, void* AB_dev, void* stream);
+
+/* ---- downwash MLP (6-128-64-128-3, ReLU) ----
+ * DownwashNN.__init__/update -- dnwash_nn_est/downwash_nn.py:10-29, net: nn_net.py:7-18. */
+typedef struct ndp_mlp ndp_mlp;
+
+/* Weights are HOST pointers, row-major [out][in] fp32 as in the torch state_dict
+ * ("0.weight" [128][6], "2.weight" [64][128], "4.weight" [128][64], "6.weight" [3][128]). */
+int ndp_mlp_create(const float* W1, const float* b1, const float* W2, const float* b2, const float* W3,
+                   const float* b3, const float* W4, const float* b4, ndp_mlp** out);
+int ndp_mlp_destroy(ndp_mlp* m);
+
+/* Fused feature construction + MLP for P (ego, neighbour) pairs:
+ *   f[p][k][:] = gate_p * MLP( (other[p][k] - ego[p][k])[0:6] ),  k = 0..n_nodes-1
+ * ego/other: [P][n_nodes][10] in `precision`; gate_xy (may be NULL = always on): [P][2] ego
+ * odometry x,y -- the force is zeroed when the neighbour's node-0 horizontal distance to it is
+ * >= r_horiz (ndp_nmpc_leader_node.py:65-76, params/downwash_params.py:10).
+ * out: [P][n_nodes][3] in `precision`.  accumulate != 0 adds into out (sum over neighbours).
+ * path: 0 = auto, 1 = CUDA-core fp32 kernel, 2 = tcgen05 tensor-core kernel. */
+int ndp_mlp_forward_pairs(ndp_mlp* m, int precision, int64_t P, int32_t n_nodes, const void* ego_dev,
+                          const void* other_dev, const void* gate_xy_dev, double r_horiz, void* out_dev,
+                          int accumulate, int path, void* stream);
+
+/* Plain rows: in [M][6] fp32 -> out [M][3] fp32 (the nn.Sequential itself). */
+int ndp_mlp_forward_rows(ndp_mlp* m, int64_t M, const float* in_dev, float* out_dev, int path, void* stream);
+
+/* Swarm: all-pairs gated sum.  traj [n_all][n_nodes][6] fp32 (positions+velocities of every quad's
+ * reference horizon, e.g. the all-gathered tensor), egos are rows [ego_begin, ego_begin+n_ego).
+ * odom_xy [n_ego][2] (may be NULL: use the ego's own node 0).  out [n_ego][n_nodes][3] in `precision`:
+ *   f_i = sum over j != i with |xy_j(node 0) - xy_i| < r_horiz of MLP(traj_j - traj_i). */
+int ndp_mlp_forward_swarm(ndp_mlp* m, int precision, int64_t n_all, int64_t ego_begin, int64_t n_ego,
+                          int32_t n_nodes, const float* traj_dev, const float* odom_xy_dev, double r_horiz,
+                          void* out_dev, int path, void* stream);
+
+int64_t ndp_mlp_launch_count(const ndp_mlp* m);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NDP_NMPC_H */

@@ -1,0 +1,91 @@
+"""ctypes binding of libndp_nmpc_b200.so (the C ABI declared in include/ndp_nmpc.h).
+
+There is no CPU fallback: if the shared library is missing this raises, and every compute
+entry point launches CUDA kernels.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_C", "libndp_nmpc_b200.so")
+
+NDP_F32, NDP_F64 = 0, 1
+FIELD_X, FIELD_U, FIELD_YREF, FIELD_P = 0, 1, 2, 3
+FIELDS = {"x": FIELD_X, "u": FIELD_U, "yref": FIELD_YREF, "p": FIELD_P}
+
+# every symbol include/ndp_nmpc.h declares
+EXPORTS = [
+    "ndp_default_config", "ndp_create", "ndp_destroy", "ndp_set", "ndp_get", "ndp_reset", "ndp_set_reference",
+    "ndp_solve", "ndp_status", "ndp_stats", "ndp_launch_count", "ndp_last_error", "ndp_rk4_sens",
+    "ndp_mlp_create", "ndp_mlp_destroy", "ndp_mlp_forward_pairs", "ndp_mlp_forward_rows", "ndp_mlp_forward_swarm",
+    "ndp_mlp_launch_count",
+]
+
+
+class NdpConfig(C.Structure):
+    _fields_ = [
+        ("N", C.c_int32), ("precision", C.c_int32), ("batch", C.c_int32), ("np", C.c_int32),
+        ("T", C.c_double), ("mass", C.c_double), ("gravity", C.c_double),
+        ("Q", C.c_double * 10), ("R", C.c_double * 4),
+        ("u_min", C.c_double * 4), ("u_max", C.c_double * 4),
+        ("v_min", C.c_double * 3), ("v_max", C.c_double * 3),
+        ("ipm_max_iter", C.c_int32), ("polish_max", C.c_int32), ("ipm_tol_mu", C.c_double),
+    ]
+
+
+class NdpError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the CUDA library; raise loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NdpError(
+            f"{LIB_PATH} is missing: build it with `python -m ndp_nmpc_qd_b200.build` "
+            "(or __graft_entry__.build()); there is no CPU fallback"
+        )
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, i64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
+    lib.ndp_default_config.argtypes = [C.POINTER(NdpConfig)]
+    lib.ndp_default_config.restype = None
+    lib.ndp_create.argtypes = [C.POINTER(NdpConfig), C.POINTER(vp)]
+    lib.ndp_destroy.argtypes = [vp]
+    lib.ndp_set.argtypes = [vp, i32, i32, vp, i64, vp]
+    lib.ndp_get.argtypes = [vp, i32, i32, vp, i64, vp]
+    lib.ndp_reset.argtypes = [vp, vp, vp, vp]
+    lib.ndp_set_reference.argtypes = [vp, vp, vp, vp, vp]
+    lib.ndp_solve.argtypes = [vp, vp, vp, vp]
+    lib.ndp_status.argtypes = [vp, vp, vp]
+    lib.ndp_stats.argtypes = [vp, vp, vp]
+    lib.ndp_launch_count.argtypes = [vp]
+    lib.ndp_launch_count.restype = i64
+    lib.ndp_last_error.restype = C.c_char_p
+    lib.ndp_rk4_sens.argtypes = [i32, i64, dbl, dbl, dbl, vp, vp, vp, vp, vp, vp]
+    fp = C.POINTER(C.c_float)
+    lib.ndp_mlp_create.argtypes = [fp] * 8 + [C.POINTER(vp)]
+    lib.ndp_mlp_destroy.argtypes = [vp]
+    lib.ndp_mlp_forward_pairs.argtypes = [vp, i32, i64, i32, vp, vp, vp, dbl, vp, i32, i32, vp]
+    lib.ndp_mlp_forward_rows.argtypes = [vp, i64, vp, vp, i32, vp]
+    lib.ndp_mlp_forward_swarm.argtypes = [vp, i32, i64, i64, i64, i32, vp, vp, dbl, vp, i32, vp]
+    lib.ndp_mlp_launch_count.argtypes = [vp]
+    lib.ndp_mlp_launch_count.restype = i64
+    for name in ("ndp_create", "ndp_destroy", "ndp_set", "ndp_get", "ndp_reset", "ndp_set_reference", "ndp_solve",
+                 "ndp_status", "ndp_stats", "ndp_rk4_sens", "ndp_mlp_create", "ndp_mlp_destroy",
+                 "ndp_mlp_forward_pairs", "ndp_mlp_forward_rows", "ndp_mlp_forward_swarm"):
+        getattr(lib, name).restype = C.c_int
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().ndp_last_error()
+        raise NdpError(f"{what} failed (code {rc}): {msg.decode() if msg else ''}")

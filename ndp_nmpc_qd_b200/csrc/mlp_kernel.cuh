@@ -1,0 +1,293 @@
+// Downwash MLP 6-128-64-128-3 (ReLU), fused with relative-feature construction and gating.
+// Reference: dnwash_nn_est/nn_net.py:7-18 (architecture), downwash_nn.py:21-29 (features =
+// (other - ego)[:, 0:6] cast to fp32), ndp_nmpc_leader_node.py:60-76 (1 m horizontal gate).
+//
+// This file holds the CUDA-core fp32 path (exact fp32 FMA arithmetic; used for small row counts
+// such as the batch-1 drop-in call and as the numerics anchor for the tensor-core path in
+// mlp_tc_kernel.cuh).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ndp {
+
+constexpr int MLP_IN = 6, MLP_H1 = 128, MLP_H2 = 64, MLP_H3 = 128, MLP_OUT = 3;
+// packed fp32 parameter block (floats): W1[128][6] b1[128] W2[64][128] b2[64] W3[128][64] b3[128] W4[3][128] b4[3](+1 pad)
+constexpr int MLP_OW1 = 0;
+constexpr int MLP_OB1 = MLP_OW1 + MLP_H1 * MLP_IN;
+constexpr int MLP_OW2 = MLP_OB1 + MLP_H1;
+constexpr int MLP_OB2 = MLP_OW2 + MLP_H2 * MLP_H1;
+constexpr int MLP_OW3 = MLP_OB2 + MLP_H2;
+constexpr int MLP_OB3 = MLP_OW3 + MLP_H3 * MLP_H2;
+constexpr int MLP_OW4 = MLP_OB3 + MLP_H3;
+constexpr int MLP_OB4 = MLP_OW4 + MLP_OUT * MLP_H3;
+constexpr int MLP_NPARAM = MLP_OB4 + 4;  // 17 860 floats
+
+// How rows are produced / consumed.
+struct MlpIo {
+    // mode 0: rows given directly, in[M][6] fp32
+    // mode 1: pairs, ego/other [P][n_nodes][10] (float or double), optional gate
+    // mode 2: pair list over a shared trajectory tensor traj[n_all][n_nodes][6] fp32
+    int mode;
+    int precision;  // element type of ego/other/out for mode 1, of out for mode 2 (0 f32, 1 f64)
+    int n_nodes;
+    int accumulate;
+    long long M;  // total rows
+    const float* in;
+    const void* ego;
+    const void* other;
+    const void* gate_xy;
+    double r2;
+    const float* traj;
+    const int2* pairs;  // (ego_global, other_global)
+    void* out;          // mode 0: float [M][3]; mode 1: precision [P][n_nodes][3]; mode 2: float [n_pairs][n_nodes][3]
+};
+
+// feature row + gate for row index `row`
+__device__ __forceinline__ bool mlp_fetch_row(const MlpIo& io, long long row, float (&x)[6]) {
+    if (io.mode == 0) {
+#pragma unroll
+        for (int i = 0; i < 6; i++) x[i] = io.in[row * 6 + i];
+        return true;
+    } else if (io.mode == 1) {
+        const long long p = row / io.n_nodes;
+        bool on = true;
+        if (io.precision == 1) {
+            const double* e = (const double*)io.ego + row * 10;
+            const double* o = (const double*)io.other + row * 10;
+#pragma unroll
+            for (int i = 0; i < 6; i++) x[i] = (float)(o[i] - e[i]);
+            if (io.gate_xy) {
+                const double* o0 = (const double*)io.other + p * io.n_nodes * 10;
+                const double* g = (const double*)io.gate_xy + p * 2;
+                const double dx = o0[0] - g[0], dy = o0[1] - g[1];
+                on = dx * dx + dy * dy < io.r2;
+            }
+        } else {
+            const float* e = (const float*)io.ego + row * 10;
+            const float* o = (const float*)io.other + row * 10;
+#pragma unroll
+            for (int i = 0; i < 6; i++) x[i] = o[i] - e[i];
+            if (io.gate_xy) {
+                const float* o0 = (const float*)io.other + p * io.n_nodes * 10;
+                const float* g = (const float*)io.gate_xy + p * 2;
+                const float dx = o0[0] - g[0], dy = o0[1] - g[1];
+                on = dx * dx + dy * dy < (float)io.r2;
+            }
+        }
+        return on;
+    } else {
+        const long long p = row / io.n_nodes;
+        const int k = (int)(row - p * io.n_nodes);
+        const int2 pr = io.pairs[p];
+        const float* e = io.traj + ((long long)pr.x * io.n_nodes + k) * 6;
+        const float* o = io.traj + ((long long)pr.y * io.n_nodes + k) * 6;
+#pragma unroll
+        for (int i = 0; i < 6; i++) x[i] = o[i] - e[i];
+        return true;
+    }
+}
+
+__device__ __forceinline__ void mlp_store_row(const MlpIo& io, long long row, bool on, float f0, float f1, float f2) {
+    if (!on) { f0 = 0.f; f1 = 0.f; f2 = 0.f; }
+    if (io.mode == 1 && io.precision == 1) {
+        double* o = (double*)io.out + row * 3;
+        if (io.accumulate) { o[0] += f0; o[1] += f1; o[2] += f2; }
+        else { o[0] = f0; o[1] = f1; o[2] = f2; }
+    } else {
+        float* o = (float*)io.out + row * 3;
+        if (io.accumulate) { o[0] += f0; o[1] += f1; o[2] += f2; }
+        else { o[0] = f0; o[1] = f1; o[2] = f2; }
+    }
+}
+
+// CUDA-core fp32 kernel: CTA = 256 threads, tile = 64 rows, weights + activations in shared memory.
+constexpr int MLPF_ROWS = 64;
+constexpr int MLPF_THREADS = 256;
+constexpr int MLPF_LD1 = MLP_H1 + 4;  // padded activation strides (floats)
+constexpr int MLPF_LD2 = MLP_H2 + 4;
+constexpr size_t MLPF_SMEM = (size_t)(MLP_NPARAM + MLPF_ROWS * MLPF_LD1 + MLPF_ROWS * MLPF_LD2 + MLPF_ROWS * 8) * sizeof(float);
+
+__global__ void __launch_bounds__(MLPF_THREADS, 1) mlp_fp32_kernel(const float* __restrict__ params, const MlpIo io) {
+    extern __shared__ __align__(16) float smf[];
+    float* sw = smf;                             // parameters
+    float* sA = sw + MLP_NPARAM;                 // h1 / h3  [64][132]
+    float* sB = sA + MLPF_ROWS * MLPF_LD1;       // h2       [64][68]
+    float* sF = sB + MLPF_ROWS * MLPF_LD2;       // features [64][8] (6 + gate + pad)
+    const int t = threadIdx.x;
+    for (int i = t; i < MLP_NPARAM; i += MLPF_THREADS) sw[i] = params[i];
+    const long long n_tiles = (io.M + MLPF_ROWS - 1) / MLPF_ROWS;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const long long row0 = tile * MLPF_ROWS;
+        __syncthreads();
+        if (t < MLPF_ROWS) {
+            float x[6] = {0, 0, 0, 0, 0, 0};
+            bool on = false;
+            if (row0 + t < io.M) on = mlp_fetch_row(io, row0 + t, x);
+#pragma unroll
+            for (int i = 0; i < 6; i++) sF[t * 8 + i] = x[i];
+            sF[t * 8 + 6] = on ? 1.f : 0.f;
+        }
+        __syncthreads();
+        // layer 1: 64 x 128, thread -> (row r = t/4, 32 neurons n = (t%4) + 4*i)
+        {
+            const int r = t >> 2, nb = t & 3;
+            float x[6];
+#pragma unroll
+            for (int i = 0; i < 6; i++) x[i] = sF[r * 8 + i];
+#pragma unroll 8
+            for (int i = 0; i < 32; i++) {
+                const int n = nb + 4 * i;
+                float acc = sw[MLP_OB1 + n];
+#pragma unroll
+                for (int q = 0; q < 6; q++) acc = fmaf(sw[MLP_OW1 + n * 6 + q], x[q], acc);
+                sA[r * MLPF_LD1 + n] = fmaxf(acc, 0.f);
+            }
+        }
+        __syncthreads();
+        // layer 2: 64 x 64, K = 128.  thread -> rows r0..r0+3 (r0 = 4*(t/16)), neurons n = (t%16) + 16*c
+        {
+            const int r0 = (t >> 4) * 4, nb = t & 15;
+            float acc[4][4];
+#pragma unroll
+            for (int c = 0; c < 4; c++)
+#pragma unroll
+                for (int r = 0; r < 4; r++) acc[r][c] = sw[MLP_OB2 + nb + 16 * c];
+            for (int k = 0; k < MLP_H1; k += 4) {
+                float4 a[4], w[4];
+#pragma unroll
+                for (int r = 0; r < 4; r++) a[r] = *reinterpret_cast<const float4*>(sA + (r0 + r) * MLPF_LD1 + k);
+#pragma unroll
+                for (int c = 0; c < 4; c++) w[c] = *reinterpret_cast<const float4*>(sw + MLP_OW2 + (nb + 16 * c) * MLP_H1 + k);
+#pragma unroll
+                for (int r = 0; r < 4; r++)
+#pragma unroll
+                    for (int c = 0; c < 4; c++) {
+                        acc[r][c] = fmaf(a[r].x, w[c].x, acc[r][c]);
+                        acc[r][c] = fmaf(a[r].y, w[c].y, acc[r][c]);
+                        acc[r][c] = fmaf(a[r].z, w[c].z, acc[r][c]);
+                        acc[r][c] = fmaf(a[r].w, w[c].w, acc[r][c]);
+                    }
+            }
+#pragma unroll
+            for (int r = 0; r < 4; r++)
+#pragma unroll
+                for (int c = 0; c < 4; c++) sB[(r0 + r) * MLPF_LD2 + nb + 16 * c] = fmaxf(acc[r][c], 0.f);
+        }
+        __syncthreads();
+        // layer 3: 64 x 128, K = 64.  thread -> rows r0..r0+3, neurons n = (t%16) + 16*c, c < 8
+        {
+            const int r0 = (t >> 4) * 4, nb = t & 15;
+            float acc[4][8];
+#pragma unroll
+            for (int c = 0; c < 8; c++)
+#pragma unroll
+                for (int r = 0; r < 4; r++) acc[r][c] = sw[MLP_OB3 + nb + 16 * c];
+            for (int k = 0; k < MLP_H2; k += 4) {
+                float4 a[4];
+#pragma unroll
+                for (int r = 0; r < 4; r++) a[r] = *reinterpret_cast<const float4*>(sB + (r0 + r) * MLPF_LD2 + k);
+#pragma unroll
+                for (int c = 0; c < 8; c++) {
+                    const float4 w = *reinterpret_cast<const float4*>(sw + MLP_OW3 + (nb + 16 * c) * MLP_H2 + k);
+#pragma unroll
+                    for (int r = 0; r < 4; r++) {
+                        acc[r][c] = fmaf(a[r].x, w.x, acc[r][c]);
+                        acc[r][c] = fmaf(a[r].y, w.y, acc[r][c]);
+                        acc[r][c] = fmaf(a[r].z, w.z, acc[r][c]);
+                        acc[r][c] = fmaf(a[r].w, w.w, acc[r][c]);
+                    }
+                }
+            }
+            __syncthreads();  // everyone is done reading h1 (layer 2 finished before the previous barrier)
+#pragma unroll
+            for (int r = 0; r < 4; r++)
+#pragma unroll
+                for (int c = 0; c < 8; c++) sA[(r0 + r) * MLPF_LD1 + nb + 16 * c] = fmaxf(acc[r][c], 0.f);
+        }
+        __syncthreads();
+        // layer 4: 64 x 3, K = 128.  thread t < 192 -> (row t/3, output t%3)
+        if (t < MLPF_ROWS * 3) {
+            const int r = t / 3, o = t - 3 * r;
+            float acc = sw[MLP_OB4 + o];
+            for (int k = 0; k < MLP_H3; k += 4) {
+                const float4 a = *reinterpret_cast<const float4*>(sA + r * MLPF_LD1 + k);
+                const float4 w = *reinterpret_cast<const float4*>(sw + MLP_OW4 + o * MLP_H3 + k);
+                acc = fmaf(a.x, w.x, acc);
+                acc = fmaf(a.y, w.y, acc);
+                acc = fmaf(a.z, w.z, acc);
+                acc = fmaf(a.w, w.w, acc);
+            }
+            sB[r * 4 + o] = acc;  // h2 is dead; reuse as the output tile
+        }
+        __syncthreads();
+        if (t < MLPF_ROWS && row0 + t < io.M)
+            mlp_store_row(io, row0 + t, sF[t * 8 + 6] != 0.f, sB[t * 4 + 0], sB[t * 4 + 1], sB[t * 4 + 2]);
+    }
+}
+
+// ---- swarm support: neighbour lists and ordered reduction ----
+// count / fill gated neighbours of each ego (deterministic order: ascending j)
+__global__ void swarm_count_kernel(const float* __restrict__ traj, const float* __restrict__ odom_xy, int n_all, int ego_begin,
+                                   int n_ego, int n_nodes, float r2, int* __restrict__ counts) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_ego) return;
+    const int gi = ego_begin + i;
+    const float ex = odom_xy ? odom_xy[i * 2] : traj[(long long)gi * n_nodes * 6];
+    const float ey = odom_xy ? odom_xy[i * 2 + 1] : traj[(long long)gi * n_nodes * 6 + 1];
+    int cnt = 0;
+    for (int j = 0; j < n_all; j++) {
+        if (j == gi) continue;
+        const float dx = traj[(long long)j * n_nodes * 6] - ex, dy = traj[(long long)j * n_nodes * 6 + 1] - ey;
+        cnt += (dx * dx + dy * dy < r2);
+    }
+    counts[i] = cnt;
+}
+__global__ void swarm_fill_kernel(const float* __restrict__ traj, const float* __restrict__ odom_xy, int n_all, int ego_begin,
+                                  int n_ego, int n_nodes, float r2, const int* __restrict__ offsets, int2* __restrict__ pairs) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_ego) return;
+    const int gi = ego_begin + i;
+    const float ex = odom_xy ? odom_xy[i * 2] : traj[(long long)gi * n_nodes * 6];
+    const float ey = odom_xy ? odom_xy[i * 2 + 1] : traj[(long long)gi * n_nodes * 6 + 1];
+    int o = offsets[i];
+    for (int j = 0; j < n_all; j++) {
+        if (j == gi) continue;
+        const float dx = traj[(long long)j * n_nodes * 6] - ex, dy = traj[(long long)j * n_nodes * 6 + 1] - ey;
+        if (dx * dx + dy * dy < r2) pairs[o++] = make_int2(gi, j);
+    }
+}
+// exclusive scan of counts[n] -> offsets[n+1] (single CTA; n <= a few 10^5)
+__global__ void swarm_scan_kernel(const int* __restrict__ counts, int n, int* __restrict__ offsets) {
+    __shared__ int part[1024];
+    const int t = threadIdx.x;
+    const int per = (n + blockDim.x - 1) / blockDim.x;
+    const int b = t * per, e = min(n, b + per);
+    int s = 0;
+    for (int i = b; i < e; i++) s += counts[i];
+    part[t] = s;
+    __syncthreads();
+    if (t == 0) {
+        int run = 0;
+        for (int i = 0; i < (int)blockDim.x; i++) { const int v = part[i]; part[i] = run; run += v; }
+        offsets[n] = run;
+    }
+    __syncthreads();
+    int run = part[t];
+    for (int i = b; i < e; i++) { offsets[i] = run; run += counts[i]; }
+}
+// f[i][k][:] = sum over the ego's pair segment, in list order
+template <typename TO>
+__global__ void swarm_reduce_kernel(const float* __restrict__ fpair, const int* __restrict__ offsets, int n_ego, int n_nodes,
+                                    TO* __restrict__ out) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)n_ego * n_nodes * 3;
+    if (idx >= total) return;
+    const int i = (int)(idx / (n_nodes * 3));
+    const int rem = (int)(idx - (long long)i * n_nodes * 3);
+    float acc = 0.f;
+    for (int p = offsets[i]; p < offsets[i + 1]; p++) acc += fpair[(long long)p * n_nodes * 3 + rem];
+    out[idx] = (TO)acc;
+}
+
+}  // namespace ndp

@@ -1,0 +1,522 @@
+// C ABI of libndp_nmpc_b200.so (see include/ndp_nmpc.h for the contract and the reference
+// call each entry point replaces).  No CPU fallback: every compute entry point launches a
+// hand-written sm_100a kernel and reports CUDA errors to the caller.
+#include "../../include/ndp_nmpc.h"
+
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+
+#include "mlp_kernel.cuh"
+#include "mlp_tc_kernel.cuh"
+#include "rti_kernel.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const char* msg) {
+    g_err = msg;
+    return code;
+}
+int cuda_fail(cudaError_t e, const char* where) {
+    g_err = std::string(where) + ": " + cudaGetErrorString(e);
+    return (int)e;
+}
+#define CU(call)                                        \
+    do {                                                \
+        cudaError_t e_ = (call);                        \
+        if (e_ != cudaSuccess) return cuda_fail(e_, #call); \
+    } while (0)
+
+}  // namespace
+
+struct ndp_handle {
+    ndp_config cfg;
+    int elt;  // bytes per element
+    void *X, *U, *yref, *par, *ws;
+    int32_t *status, *stats;
+    long long ws_stride;
+    int slots, grid;
+    size_t smem;
+    std::atomic<long long> launches;
+    std::mutex mu;
+};
+
+namespace ndp {
+
+// strided copy between a caller array [B][dim] (row stride ld) and one stage of an internal
+// [B][n_stages][sdim] tensor (offset off inside the stage slot).
+template <typename T, bool kToInternal>
+__global__ void stage_copy_kernel(T* __restrict__ internal, T* __restrict__ ext, int B, int n_stages, int sdim, int stage, int off,
+                                  int dim, long long ld) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)B * dim) return;
+    const int b = (int)(idx / dim), i = (int)(idx - (long long)b * dim);
+    T* pi = internal + ((long long)b * n_stages + stage) * sdim + off + i;
+    T* pe = ext + (long long)b * ld + i;
+    if (kToInternal) *pi = *pe;
+    else *pe = *pi;
+}
+
+// all stages: ext [B][n_stages][dim] contiguous  <->  internal [B][n_int][sdim] (first n_stages used)
+template <typename T, bool kToInternal>
+__global__ void all_copy_kernel(T* __restrict__ internal, T* __restrict__ ext, int B, int n_int, int sdim, int off, int n_stages,
+                                int dim, int dim_last) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long per = (long long)(n_stages - 1) * dim + dim_last;
+    if (idx >= (long long)B * per) return;
+    const int b = (int)(idx / per);
+    const long long r = idx - (long long)b * per;
+    const int k = (int)min((long long)(n_stages - 1), r / dim);
+    const int i = (int)(r - (long long)k * dim);
+    T* pi = internal + ((long long)b * n_int + k) * sdim + off + i;
+    T* pe = ext + idx;
+    if (kToInternal) *pi = *pe;
+    else *pe = *pi;
+}
+
+// yref_k = [xr_k; ur_k], p_k = [xr_k[6:10]; f_k]  (controller.update, nmpc_body_rate_ctl.py:95-104)
+template <typename T>
+__global__ void pack_reference_kernel(const T* __restrict__ xr, const T* __restrict__ ur, const T* __restrict__ f, T* __restrict__ yref,
+                                      T* __restrict__ par, int B, int N) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)B * (N + 1)) return;
+    const int b = (int)(idx / (N + 1)), k = (int)(idx - (long long)b * (N + 1));
+    const T* x = xr + idx * NX;
+    T* y = yref + idx * NYS;
+    T* p = par + idx * NPS;
+#pragma unroll
+    for (int i = 0; i < NX; i++) y[i] = x[i];
+#pragma unroll
+    for (int m = 0; m < NU; m++) y[NX + m] = (k < N) ? ur[((long long)b * N + k) * NU + m] : T(0);
+#pragma unroll
+    for (int i = 0; i < 4; i++) p[i] = x[6 + i];
+#pragma unroll
+    for (int i = 0; i < 3; i++) p[4 + i] = f ? f[idx * 3 + i] : T(0);
+    p[7] = T(0);
+}
+
+// standalone batched RK4 + forward sensitivities: 16 lanes per interval, lane j -> column j
+template <typename T>
+__global__ void rk4_sens_kernel(RtiCfg<T> c, long long M, const T* __restrict__ x, const T* __restrict__ u, const T* __restrict__ f,
+                                T* __restrict__ xn, T* __restrict__ AB) {
+    __shared__ T sx[RTI_PPC][16];
+    const int lane = threadIdx.x & 15, grp = threadIdx.x >> 4;
+    const unsigned mask = 0xFFFFu << (threadIdx.x & 16);
+    for (long long m = (long long)blockIdx.x * RTI_PPC + grp; m < M; m += (long long)gridDim.x * RTI_PPC) {
+        if (lane < 10) sx[grp][lane] = x[m * NX + lane];
+        else if (lane < 14) sx[grp][lane] = u[m * NU + lane - 10];
+        __syncwarp(mask);
+        T xa[10], sa[10];
+        const T f0 = f ? f[m * 3] * c.inv_mass : T(0), f1 = f ? f[m * 3 + 1] * c.inv_mass : T(0), f2 = f ? f[m * 3 + 2] * c.inv_mass : T(0);
+        rk4_column<T>(c, lane, &sx[grp][0], &sx[grp][10], f0, f1, f2, xa, sa);
+        if (lane < 14) {
+#pragma unroll
+            for (int r = 0; r < 10; r++) AB[(m * 10 + r) * 14 + lane] = sa[r];
+        } else if (lane == 14) {
+#pragma unroll
+            for (int r = 0; r < 10; r++) xn[m * 10 + r] = xa[r];
+        }
+        __syncwarp(mask);
+    }
+}
+
+template <typename T>
+RtiCfg<T> make_cfg(const ndp_config& g) {
+    RtiCfg<T> c;
+    c.N = g.N;
+    c.ipm_max_iter = g.ipm_max_iter;
+    c.polish_max = g.polish_max;
+    c.h = (T)(g.T / g.N);
+    c.inv_mass = (T)(1.0 / g.mass);
+    c.g = (T)g.gravity;
+    for (int i = 0; i < 10; i++) c.Q[i] = (T)g.Q[i];
+    for (int i = 0; i < 4; i++) { c.R[i] = (T)g.R[i]; c.umin[i] = (T)g.u_min[i]; c.umax[i] = (T)g.u_max[i]; }
+    for (int i = 0; i < 3; i++) { c.vmin[i] = (T)g.v_min[i]; c.vmax[i] = (T)g.v_max[i]; }
+    const bool f32 = sizeof(T) == 4;
+    c.tol_mu = (T)(g.ipm_tol_mu > 0 ? g.ipm_tol_mu : (f32 ? 1e-4 : 1e-9));
+    c.mu0 = (T)10.0;
+    c.t_floor = (T)0.1;
+    c.big = (T)(f32 ? 1e9 : 1e12);
+    return c;
+}
+
+template <typename T>
+int launch_solve(ndp_handle* h, const void* x0, void* u0, cudaStream_t st) {
+    RtiCfg<T> c = make_cfg<T>(h->cfg);
+    RtiArgs<T> a;
+    a.x0 = (const T*)x0;
+    a.yref = (const T*)h->yref;
+    a.par = (const T*)h->par;
+    a.X = (T*)h->X;
+    a.U = (T*)h->U;
+    a.u0 = (T*)u0;
+    a.status = h->status;
+    a.stats = h->stats;
+    a.ws = (T*)h->ws;
+    a.ws_stride = h->ws_stride;
+    a.B = h->cfg.batch;
+    rti_step_kernel<T><<<h->grid, RTI_THREADS, h->smem, st>>>(c, a);
+    h->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace ndp
+
+using namespace ndp;
+
+static int field_geom(const ndp_handle* h, int field, void** base, int* n_int, int* sdim, int* dim, int* dim_last, int* n_stages) {
+    const int N = h->cfg.N;
+    switch (field) {
+        case NDP_FIELD_X: *base = h->X; *n_int = N + 1; *sdim = NX; *dim = NX; *dim_last = NX; *n_stages = N + 1; return 0;
+        case NDP_FIELD_U: *base = h->U; *n_int = N; *sdim = NU; *dim = NU; *dim_last = NU; *n_stages = N; return 0;
+        case NDP_FIELD_YREF: *base = h->yref; *n_int = N + 1; *sdim = NYS; *dim = NYS; *dim_last = NX; *n_stages = N + 1; return 0;
+        case NDP_FIELD_P: *base = h->par; *n_int = N + 1; *sdim = NPS; *dim = h->cfg.np; *dim_last = h->cfg.np; *n_stages = N + 1; return 0;
+    }
+    return -1;
+}
+
+template <bool kToInternal>
+static int set_get(ndp_handle* h, int field, int stage, void* dev, int64_t ld, void* stream) {
+    if (!h || !dev) return fail(NDP_E_ARG, "ndp_set/get: null argument");
+    void* base; int n_int, sdim, dim, dim_last, n_stages;
+    if (field_geom(h, field, &base, &n_int, &sdim, &dim, &dim_last, &n_stages)) return fail(NDP_E_ARG, "ndp_set/get: unknown field");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int B = h->cfg.batch;
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (stage >= 0) {
+        if (stage >= n_stages) return fail(NDP_E_ARG, "ndp_set/get: stage out of range");
+        const int d = (stage == n_stages - 1) ? dim_last : dim;
+        if (ld < d) ld = d;
+        const long long tot = (long long)B * d;
+        const int blk = 128, grd = (int)((tot + blk - 1) / blk);
+        if (h->elt == 4) stage_copy_kernel<float, kToInternal><<<grd, blk, 0, st>>>((float*)base, (float*)dev, B, n_int, sdim, stage, 0, d, ld);
+        else stage_copy_kernel<double, kToInternal><<<grd, blk, 0, st>>>((double*)base, (double*)dev, B, n_int, sdim, stage, 0, d, ld);
+    } else {
+        const long long tot = (long long)B * ((long long)(n_stages - 1) * dim + dim_last);
+        const int blk = 256, grd = (int)((tot + blk - 1) / blk);
+        if (h->elt == 4) all_copy_kernel<float, kToInternal><<<grd, blk, 0, st>>>((float*)base, (float*)dev, B, n_int, sdim, 0, n_stages, dim, dim_last);
+        else all_copy_kernel<double, kToInternal><<<grd, blk, 0, st>>>((double*)base, (double*)dev, B, n_int, sdim, 0, n_stages, dim, dim_last);
+    }
+    h->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+extern "C" {
+
+const char* ndp_last_error(void) { return g_err.c_str(); }
+
+void ndp_default_config(ndp_config* c) {
+    // params/nmpc_params.py:9-35, params/fhnp_params.py:9-19
+    std::memset(c, 0, sizeof(*c));
+    c->N = 20;
+    c->precision = NDP_F32;
+    c->batch = 1;
+    c->np = 4;
+    c->T = 2.0;
+    c->mass = 1.4844;
+    c->gravity = 9.81;
+    const double Q[10] = {300, 300, 400, 10, 10, 10, 0, 10, 10, 100};
+    const double R[4] = {10, 10, 10, 5};
+    for (int i = 0; i < 10; i++) c->Q[i] = Q[i];
+    for (int i = 0; i < 4; i++) c->R[i] = R[i];
+    for (int i = 0; i < 3; i++) { c->u_min[i] = -6; c->u_max[i] = 6; c->v_min[i] = -20; c->v_max[i] = 20; }
+    c->u_min[3] = 0;
+    c->u_max[3] = 9.81 / 0.36;
+    c->ipm_max_iter = 50;
+    c->polish_max = 6;
+    c->ipm_tol_mu = 0.0;
+}
+
+int ndp_create(const ndp_config* cfg, ndp_handle** out) {
+    if (!cfg || !out) return fail(NDP_E_ARG, "ndp_create: null argument");
+    if (cfg->N < 1 || cfg->N > NDP_N_MAX) return fail(NDP_E_CONFIG, "ndp_create: N out of range [1,128]");
+    if (cfg->batch < 1) return fail(NDP_E_CONFIG, "ndp_create: batch < 1");
+    if (cfg->np != 4 && cfg->np != 7) return fail(NDP_E_CONFIG, "ndp_create: np must be 4 or 7");
+    if (cfg->precision != NDP_F32 && cfg->precision != NDP_F64) return fail(NDP_E_CONFIG, "ndp_create: bad precision");
+    int dev = 0, n_sm = 0;
+    CU(cudaGetDevice(&dev));
+    CU(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    ndp_handle* h = new ndp_handle();
+    h->cfg = *cfg;
+    h->elt = cfg->precision == NDP_F64 ? 8 : 4;
+    h->launches = 0;
+    const int N = cfg->N, B = cfg->batch;
+    const SmemLayout L(N);
+    const WsLayout WL(N);
+    h->smem = (size_t)L.total * RTI_PPC * h->elt;
+    if (h->smem > 227 * 1024) { delete h; return fail(NDP_E_CONFIG, "ndp_create: horizon too long for shared memory"); }
+    cudaError_t e = (h->elt == 4)
+                        ? cudaFuncSetAttribute(rti_step_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem)
+                        : cudaFuncSetAttribute(rti_step_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem);
+    if (e != cudaSuccess) { delete h; return cuda_fail(e, "cudaFuncSetAttribute(rti_step_kernel)"); }
+    int occ = 0;
+    e = (h->elt == 4) ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rti_step_kernel<float>, RTI_THREADS, h->smem)
+                      : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rti_step_kernel<double>, RTI_THREADS, h->smem);
+    if (e != cudaSuccess || occ < 1) { delete h; return e != cudaSuccess ? cuda_fail(e, "occupancy") : fail(NDP_E_CONFIG, "kernel does not fit"); }
+    const int need = (B + RTI_PPC - 1) / RTI_PPC;
+    const int cap = n_sm * occ;  // persistent: at most one resident wave, grid-stride over problems
+    h->grid = need < cap ? need : cap;
+    h->slots = h->grid * RTI_PPC;
+    h->ws_stride = WL.total;
+    const size_t eb = (size_t)h->elt;
+    h->X = h->U = h->yref = h->par = h->ws = nullptr;
+    h->status = h->stats = nullptr;
+    bool ok = cudaMalloc(&h->X, (size_t)B * (N + 1) * NX * eb) == cudaSuccess && cudaMalloc(&h->U, (size_t)B * N * NU * eb) == cudaSuccess &&
+              cudaMalloc(&h->yref, (size_t)B * (N + 1) * NYS * eb) == cudaSuccess &&
+              cudaMalloc(&h->par, (size_t)B * (N + 1) * NPS * eb) == cudaSuccess &&
+              cudaMalloc(&h->ws, (size_t)h->slots * h->ws_stride * eb) == cudaSuccess &&
+              cudaMalloc(&h->status, (size_t)B * sizeof(int32_t)) == cudaSuccess &&
+              cudaMalloc(&h->stats, (size_t)B * 4 * sizeof(int32_t)) == cudaSuccess;
+    if (!ok) { ndp_destroy(h); return fail(NDP_E_ALLOC, "ndp_create: cudaMalloc failed"); }
+    // acados initialises the iterate, yref and p to zeros
+    cudaMemset(h->X, 0, (size_t)B * (N + 1) * NX * eb);
+    cudaMemset(h->U, 0, (size_t)B * N * NU * eb);
+    cudaMemset(h->yref, 0, (size_t)B * (N + 1) * NYS * eb);
+    cudaMemset(h->par, 0, (size_t)B * (N + 1) * NPS * eb);
+    cudaMemset(h->ws, 0, (size_t)h->slots * h->ws_stride * eb);
+    cudaMemset(h->status, 0, (size_t)B * sizeof(int32_t));
+    cudaMemset(h->stats, 0, (size_t)B * 4 * sizeof(int32_t));
+    CU(cudaDeviceSynchronize());
+    *out = h;
+    return 0;
+}
+
+int ndp_destroy(ndp_handle* h) {
+    if (!h) return 0;
+    cudaFree(h->X); cudaFree(h->U); cudaFree(h->yref); cudaFree(h->par); cudaFree(h->ws);
+    cudaFree(h->status); cudaFree(h->stats);
+    delete h;
+    return 0;
+}
+
+int ndp_set(ndp_handle* h, int field, int stage, const void* dev, int64_t ld, void* stream) {
+    return set_get<true>(h, field, stage, const_cast<void*>(dev), ld, stream);
+}
+int ndp_get(ndp_handle* h, int field, int stage, void* dev, int64_t ld, void* stream) {
+    return set_get<false>(h, field, stage, dev, ld, stream);
+}
+
+int ndp_reset(ndp_handle* h, const void* xr, const void* ur, void* stream) {
+    if (!h || !xr || !ur) return fail(NDP_E_ARG, "ndp_reset: null argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    const size_t eb = (size_t)h->elt;
+    const int N = h->cfg.N, B = h->cfg.batch;
+    CU(cudaMemcpyAsync(h->X, xr, (size_t)B * (N + 1) * NX * eb, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    CU(cudaMemcpyAsync(h->U, ur, (size_t)B * N * NU * eb, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return 0;
+}
+
+int ndp_set_reference(ndp_handle* h, const void* xr, const void* ur, const void* f, void* stream) {
+    if (!h || !xr || !ur) return fail(NDP_E_ARG, "ndp_set_reference: null argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    const int N = h->cfg.N, B = h->cfg.batch;
+    const long long tot = (long long)B * (N + 1);
+    const int blk = 128, grd = (int)((tot + blk - 1) / blk);
+    if (h->elt == 4)
+        pack_reference_kernel<float><<<grd, blk, 0, (cudaStream_t)stream>>>((const float*)xr, (const float*)ur, (const float*)f, (float*)h->yref, (float*)h->par, B, N);
+    else
+        pack_reference_kernel<double><<<grd, blk, 0, (cudaStream_t)stream>>>((const double*)xr, (const double*)ur, (const double*)f, (double*)h->yref, (double*)h->par, B, N);
+    h->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int ndp_solve(ndp_handle* h, const void* x0, void* u0, void* stream) {
+    if (!h || !x0) return fail(NDP_E_ARG, "ndp_solve: null argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    return h->elt == 4 ? launch_solve<float>(h, x0, u0, (cudaStream_t)stream) : launch_solve<double>(h, x0, u0, (cudaStream_t)stream);
+}
+
+int ndp_status(ndp_handle* h, int32_t* status_dev, void* stream) {
+    if (!h || !status_dev) return fail(NDP_E_ARG, "ndp_status: null argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    CU(cudaMemcpyAsync(status_dev, h->status, (size_t)h->cfg.batch * sizeof(int32_t), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return 0;
+}
+
+int ndp_stats(ndp_handle* h, int32_t* stats_dev, void* stream) {
+    if (!h || !stats_dev) return fail(NDP_E_ARG, "ndp_stats: null argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    CU(cudaMemcpyAsync(stats_dev, h->stats, (size_t)h->cfg.batch * 4 * sizeof(int32_t), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return 0;
+}
+
+int64_t ndp_launch_count(const ndp_handle* h) { return h ? (int64_t)h->launches.load() : 0; }
+
+int ndp_rk4_sens(int precision, int64_t M, double hh, double mass, double gravity, const void* x, const void* u, const void* f, void* xn,
+                 void* AB, void* stream) {
+    if (!x || !u || !xn || !AB || M < 0) return fail(NDP_E_ARG, "ndp_rk4_sens: bad argument");
+    if (M == 0) return 0;
+    ndp_config g;
+    ndp_default_config(&g);
+    g.N = 1; g.T = hh; g.mass = mass; g.gravity = gravity;
+    long long need = (M + RTI_PPC - 1) / RTI_PPC;
+    const int grd = (int)(need < 148 * 16 ? need : 148 * 16);
+    if (precision == NDP_F32)
+        rk4_sens_kernel<float><<<grd, RTI_THREADS, 0, (cudaStream_t)stream>>>(make_cfg<float>(g), M, (const float*)x, (const float*)u, (const float*)f, (float*)xn, (float*)AB);
+    else if (precision == NDP_F64)
+        rk4_sens_kernel<double><<<grd, RTI_THREADS, 0, (cudaStream_t)stream>>>(make_cfg<double>(g), M, (const double*)x, (const double*)u, (const double*)f, (double*)xn, (double*)AB);
+    else
+        return fail(NDP_E_ARG, "ndp_rk4_sens: bad precision");
+    CU(cudaGetLastError());
+    return 0;
+}
+
+}  // extern "C"
+
+// ======================= downwash MLP =======================
+struct ndp_mlp {
+    float* params;     // packed fp32 parameters (mlp_kernel.cuh layout)
+    void* tc_weights;  // tensor-core operand images (mlp_tc_kernel.cuh)
+    int n_sm;
+    // swarm scratch (grown on demand)
+    int* counts; int* offsets; int2* pairs; float* fpair;
+    long long cap_ego, cap_pairs, cap_rows;
+    std::atomic<long long> launches;
+    std::mutex mu;
+};
+
+namespace ndp {
+
+static int mlp_run(ndp_mlp* m, MlpIo io, int path, cudaStream_t st) {
+    if (io.M <= 0) return 0;
+    if (path == 0) path = (io.M >= MLPT_MIN_ROWS) ? 2 : 1;
+    if (path == 2) {
+        int rc = mlp_tc_launch(m->params, m->tc_weights, io, m->n_sm, st);
+        if (rc) return cuda_fail((cudaError_t)rc, "mlp_tc_kernel launch");
+    } else if (path == 1) {
+        const long long tiles = (io.M + MLPF_ROWS - 1) / MLPF_ROWS;
+        const int grd = (int)(tiles < m->n_sm ? tiles : m->n_sm);
+        mlp_fp32_kernel<<<grd, MLPF_THREADS, MLPF_SMEM, st>>>(m->params, io);
+        CU(cudaGetLastError());
+    } else {
+        return fail(NDP_E_ARG, "ndp_mlp: unknown path");
+    }
+    m->launches++;
+    return 0;
+}
+
+}  // namespace ndp
+
+extern "C" {
+
+int ndp_mlp_create(const float* W1, const float* b1, const float* W2, const float* b2, const float* W3, const float* b3, const float* W4,
+                   const float* b4, ndp_mlp** out) {
+    if (!W1 || !b1 || !W2 || !b2 || !W3 || !b3 || !W4 || !b4 || !out) return fail(NDP_E_ARG, "ndp_mlp_create: null argument");
+    float* host = new float[MLP_NPARAM]();
+    std::memcpy(host + MLP_OW1, W1, sizeof(float) * MLP_H1 * MLP_IN);
+    std::memcpy(host + MLP_OB1, b1, sizeof(float) * MLP_H1);
+    std::memcpy(host + MLP_OW2, W2, sizeof(float) * MLP_H2 * MLP_H1);
+    std::memcpy(host + MLP_OB2, b2, sizeof(float) * MLP_H2);
+    std::memcpy(host + MLP_OW3, W3, sizeof(float) * MLP_H3 * MLP_H2);
+    std::memcpy(host + MLP_OB3, b3, sizeof(float) * MLP_H3);
+    std::memcpy(host + MLP_OW4, W4, sizeof(float) * MLP_OUT * MLP_H3);
+    std::memcpy(host + MLP_OB4, b4, sizeof(float) * MLP_OUT);
+    ndp_mlp* m = new ndp_mlp();
+    m->launches = 0;
+    m->counts = m->offsets = nullptr; m->pairs = nullptr; m->fpair = nullptr;
+    m->cap_ego = m->cap_pairs = m->cap_rows = 0;
+    m->params = nullptr; m->tc_weights = nullptr;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&m->n_sm, cudaDevAttrMultiProcessorCount, dev);
+    cudaError_t e = cudaMalloc(&m->params, sizeof(float) * MLP_NPARAM);
+    if (e == cudaSuccess) e = cudaMemcpy(m->params, host, sizeof(float) * MLP_NPARAM, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = (cudaError_t)mlp_tc_prepare(host, &m->tc_weights);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_fp32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MLPF_SMEM);
+    delete[] host;
+    if (e != cudaSuccess) { ndp_mlp_destroy(m); return cuda_fail(e, "ndp_mlp_create"); }
+    *out = m;
+    return 0;
+}
+
+int ndp_mlp_destroy(ndp_mlp* m) {
+    if (!m) return 0;
+    cudaFree(m->params); cudaFree(m->tc_weights);
+    cudaFree(m->counts); cudaFree(m->offsets); cudaFree(m->pairs); cudaFree(m->fpair);
+    delete m;
+    return 0;
+}
+
+int ndp_mlp_forward_rows(ndp_mlp* m, int64_t M, const float* in, float* out, int path, void* stream) {
+    if (!m || !in || !out || M < 0) return fail(NDP_E_ARG, "ndp_mlp_forward_rows: bad argument");
+    std::lock_guard<std::mutex> lk(m->mu);
+    MlpIo io{};
+    io.mode = 0; io.M = M; io.in = in; io.out = out; io.n_nodes = 1;
+    return mlp_run(m, io, path, (cudaStream_t)stream);
+}
+
+int ndp_mlp_forward_pairs(ndp_mlp* m, int precision, int64_t P, int32_t n_nodes, const void* ego, const void* other, const void* gate_xy,
+                          double r_horiz, void* out, int accumulate, int path, void* stream) {
+    if (!m || !ego || !other || !out || P < 0 || n_nodes < 1) return fail(NDP_E_ARG, "ndp_mlp_forward_pairs: bad argument");
+    if (precision != NDP_F32 && precision != NDP_F64) return fail(NDP_E_ARG, "ndp_mlp_forward_pairs: bad precision");
+    std::lock_guard<std::mutex> lk(m->mu);
+    MlpIo io{};
+    io.mode = 1; io.precision = precision; io.n_nodes = n_nodes; io.accumulate = accumulate;
+    io.M = (long long)P * n_nodes; io.ego = ego; io.other = other; io.gate_xy = gate_xy; io.r2 = r_horiz * r_horiz; io.out = out;
+    return mlp_run(m, io, path, (cudaStream_t)stream);
+}
+
+int ndp_mlp_forward_swarm(ndp_mlp* m, int precision, int64_t n_all, int64_t ego_begin, int64_t n_ego, int32_t n_nodes, const float* traj,
+                          const float* odom_xy, double r_horiz, void* out, int path, void* stream) {
+    if (!m || !traj || !out || n_all < 1 || n_ego < 0 || ego_begin < 0 || ego_begin + n_ego > n_all || n_nodes < 1)
+        return fail(NDP_E_ARG, "ndp_mlp_forward_swarm: bad argument");
+    if (precision != NDP_F32 && precision != NDP_F64) return fail(NDP_E_ARG, "ndp_mlp_forward_swarm: bad precision");
+    if (n_ego == 0) return 0;
+    std::lock_guard<std::mutex> lk(m->mu);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_ego > m->cap_ego) {
+        cudaFree(m->counts); cudaFree(m->offsets);
+        CU(cudaMalloc(&m->counts, sizeof(int) * n_ego));
+        CU(cudaMalloc(&m->offsets, sizeof(int) * (n_ego + 1)));
+        m->cap_ego = n_ego;
+    }
+    const float r2 = (float)(r_horiz * r_horiz);
+    const int blk = 128, grd = (int)((n_ego + blk - 1) / blk);
+    swarm_count_kernel<<<grd, blk, 0, st>>>(traj, odom_xy, (int)n_all, (int)ego_begin, (int)n_ego, n_nodes, r2, m->counts);
+    swarm_scan_kernel<<<1, 1024, 0, st>>>(m->counts, (int)n_ego, m->offsets);
+    m->launches += 2;
+    int n_pairs = 0;
+    // the pair count sizes the next launches: one 4-byte read-back per swarm step
+    CU(cudaMemcpyAsync(&n_pairs, m->offsets + n_ego, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (n_pairs > m->cap_pairs) {
+        cudaFree(m->pairs); cudaFree(m->fpair);
+        const long long cap = (long long)n_pairs * 5 / 4 + 1024;
+        CU(cudaMalloc(&m->pairs, sizeof(int2) * cap));
+        CU(cudaMalloc(&m->fpair, sizeof(float) * cap * n_nodes * 3));
+        m->cap_pairs = cap;
+        m->cap_rows = cap * n_nodes;
+    } else if ((long long)n_pairs * n_nodes > m->cap_rows) {
+        cudaFree(m->fpair);
+        CU(cudaMalloc(&m->fpair, sizeof(float) * m->cap_pairs * n_nodes * 3));
+        m->cap_rows = m->cap_pairs * n_nodes;
+    }
+    if (n_pairs > 0) {
+        swarm_fill_kernel<<<grd, blk, 0, st>>>(traj, odom_xy, (int)n_all, (int)ego_begin, (int)n_ego, n_nodes, r2, m->offsets, m->pairs);
+        m->launches++;
+        MlpIo io{};
+        io.mode = 2; io.precision = NDP_F32; io.n_nodes = n_nodes; io.M = (long long)n_pairs * n_nodes;
+        io.traj = traj; io.pairs = m->pairs; io.out = m->fpair;
+        int rc = mlp_run(m, io, path, st);
+        if (rc) return rc;
+    }
+    const long long tot = (long long)n_ego * n_nodes * 3;
+    const int g2 = (int)((tot + 255) / 256);
+    if (precision == NDP_F64) swarm_reduce_kernel<double><<<g2, 256, 0, st>>>(m->fpair, m->offsets, (int)n_ego, n_nodes, (double*)out);
+    else swarm_reduce_kernel<float><<<g2, 256, 0, st>>>(m->fpair, m->offsets, (int)n_ego, n_nodes, (float*)out);
+    m->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int64_t ndp_mlp_launch_count(const ndp_mlp* m) { return m ? (int64_t)m->launches.load() : 0; }
+
+}  // extern "C"

@@ -1,0 +1,779 @@
+// Fused SQP-RTI step kernel for the quadrotor body-rate OCP (sm_100a).
+//
+// One 16-lane group (half a warp) owns one problem.  Lane j < 14 owns COLUMN j of every
+// 14-wide stage matrix ([A_k B_k], P+[A B], the 14x14 stage Hessian), lane 14 owns the
+// affine "column" (b_k -> stage gradient), lane 15 idles.  With that mapping
+//   * the RK4 forward-sensitivity column j of interval k is integrated by lane j and lands
+//     in the registers where the Riccati step needs it (reference: acados ERK + sens_forw,
+//     integrator_type="ERK" nmpc_body_rate_ctl.py:76; dynamics ndp_nmpc_body_rate_ctl.py:151-162),
+//   * P+ [A B], [A B]' P+ [A B], the 4x4 Cholesky solve and the Schur complement are all
+//     column-local; cross-lane traffic is broadcast reads of small shared-memory tiles plus
+//     ten shuffles for the 4x4 input block,
+//   * the gradient recursion rides along as lane 14 with the same instruction stream.
+// The QP is solved exactly: unconstrained Riccati sweep first (if the step satisfies all box
+// bounds it IS the QP solution); otherwise a Mehrotra predictor-corrector IPM on the same
+// Riccati kernel (HPIPM's algorithm, qp_solver="PARTIAL_CONDENSING_HPIPM" with cond_N = N,
+// nmpc_body_rate_ctl.py:71-79) followed by primal-dual active-set rounds that remove the
+// barrier floor (needed for fp32).  Cost: NONLINEAR_LS Gauss-Newton blocks in closed form
+// (nmpc_body_rate_ctl.py:48-53,163-180), bounds :56-61, iterate protocol :86-112.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ndp {
+
+constexpr int NX = 10, NU = 4, NZ = 14, GL = 16;
+constexpr int NYS = 14;  // yref stride per stage
+constexpr int NPS = 8;   // parameter stride per stage
+constexpr int RTI_THREADS = 128;
+constexpr int RTI_PPC = RTI_THREADS / GL;  // problems per CTA
+
+template <typename T>
+struct RtiCfg {
+    int N, ipm_max_iter, polish_max;
+    T h, inv_mass, g;
+    T Q[10], R[4], umin[4], umax[4], vmin[3], vmax[3];
+    T tol_mu, mu0, t_floor, big;
+};
+
+template <typename T>
+struct RtiArgs {
+    const T* x0;    // [B][10]
+    const T* yref;  // [B][N+1][14]
+    const T* par;   // [B][N+1][8]   q_r(4) f(3) pad
+    T* X;           // [B][N+1][10]  iterate, in/out
+    T* U;           // [B][N][4]
+    T* u0;          // [B][4] or null
+    int32_t* status;  // [B]
+    int32_t* stats;   // [B][4]
+    T* ws;            // [slots][ws_stride]
+    long long ws_stride;
+    int B;
+};
+
+// ---- per-problem shared memory layout (elements of T) ----
+struct SmemLayout {
+    int oX, oU, oY, oPar, oDz, oP, op, oAB, oHux, total;
+    __host__ __device__ explicit SmemLayout(int N) {
+        int o = 0;
+        oX = o; o += (N + 1) * NX;
+        oU = o; o += N * NU;
+        oY = o; o += (N + 1) * NYS;
+        oPar = o; o += (N + 1) * NPS;
+        o = (o + 3) & ~3;
+        oDz = o; o += (N + 1) * 16;   // QP step [k][lane]
+        oP = o; o += 10 * 12;         // P+ rows, stride 12
+        op = o; o += 12;              // p+
+        oAB = o; o += 10 * 12;        // nontrivial [A B] columns 6..13 and b, stride 12
+        oHux = o; o += 10 * 4;        // Hux transposed [i][m]
+        total = (o + 3) & ~3;
+    }
+};
+
+// ---- per-slot global workspace layout (elements of T) ----
+struct WsLayout {
+    long long oAB, oRec, oKt, oBarD, oBarG, oIpm, oZc, oHrow, total;
+    __host__ __device__ explicit WsLayout(int N) {
+        long long o = 0;
+        oAB = o; o += (long long)N * 80;    // [k][r][8]   columns 6..13 of [A B]
+        oRec = o; o += (long long)N * 16;   // [k]: b[10], kappa[4], pad
+        oKt = o; o += (long long)N * 40;    // [k][j][4]   K transposed
+        oBarD = o; o += (long long)(N + 1) * 16;
+        oBarG = o; o += (long long)(N + 1) * 16;
+        oIpm = o; o += (long long)7 * N * 16;  // LL LU TL TU CL CU ACT, each [k][lane]
+        oZc = o; o += (long long)(N + 1) * 16;
+        oHrow = o; o += (long long)N * 4 * 16;  // [k][m][16]: row m of [Hux Guu], [14] = gradient
+        total = (o + 3) & ~3LL;
+    }
+};
+
+template <typename T> struct Vec4;
+template <> struct Vec4<float> {
+    static __device__ __forceinline__ void ld(const float* p, float& a, float& b, float& c, float& d) {
+        float4 v = *reinterpret_cast<const float4*>(p);
+        a = v.x; b = v.y; c = v.z; d = v.w;
+    }
+    static __device__ __forceinline__ void st(float* p, float a, float b, float c, float d) {
+        *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
+    }
+};
+template <> struct Vec4<double> {
+    static __device__ __forceinline__ void ld(const double* p, double& a, double& b, double& c, double& d) {
+        double2 v = *reinterpret_cast<const double2*>(p);
+        double2 w = *reinterpret_cast<const double2*>(p + 2);
+        a = v.x; b = v.y; c = w.x; d = w.y;
+    }
+    static __device__ __forceinline__ void st(double* p, double a, double b, double c, double d) {
+        *reinterpret_cast<double2*>(p) = make_double2(a, b);
+        *reinterpret_cast<double2*>(p + 2) = make_double2(c, d);
+    }
+};
+
+template <typename T> __device__ __forceinline__ T tsqrt(T x);
+template <> __device__ __forceinline__ float tsqrt<float>(float x) { return sqrtf(x); }
+template <> __device__ __forceinline__ double tsqrt<double>(double x) { return sqrt(x); }
+
+template <typename T>
+__device__ __forceinline__ T grp_sum(T v, unsigned mask) {
+#pragma unroll
+    for (int o = 8; o >= 1; o >>= 1) v += __shfl_xor_sync(mask, v, o, GL);
+    return v;
+}
+template <typename T>
+__device__ __forceinline__ T grp_min(T v, unsigned mask) {
+#pragma unroll
+    for (int o = 8; o >= 1; o >>= 1) {
+        T w = __shfl_xor_sync(mask, v, o, GL);
+        v = w < v ? w : v;
+    }
+    return v;
+}
+
+// One RK4 step of the state (every lane, redundantly) and of this lane's sensitivity column.
+// x[10], u[4] in shared memory; fm = f / mass.  Column j: initial e_j for j < 10, forcing
+// B_c[:, j-10] for j = 10..13, nothing for j >= 14.
+template <typename T>
+__device__ __forceinline__ void rk4_column(const RtiCfg<T>& c, int j, const T* __restrict__ x, const T* __restrict__ u,
+                                           T fm0, T fm1, T fm2, T (&xa)[10], T (&sa)[10]) {
+    const T h = c.h;
+    const T wx = u[0], wy = u[1], wz = u[2], cc = u[3];
+    const T ew0 = (j == 10) ? T(1) : T(0), ew1 = (j == 11) ? T(1) : T(0), ew2 = (j == 12) ? T(1) : T(0);
+    const T ec = (j == 13) ? T(1) : T(0);
+    T x0[10], s0[10], kx[10], ks[10];
+#pragma unroll
+    for (int i = 0; i < 10; i++) {
+        x0[i] = x[i];
+        s0[i] = (j == i) ? T(1) : T(0);
+        xa[i] = x0[i];
+        sa[i] = s0[i];
+        kx[i] = T(0);
+        ks[i] = T(0);
+    }
+#pragma unroll
+    for (int st = 0; st < 4; st++) {
+        const T a = (st == 0) ? T(0) : ((st == 3) ? h : h * T(0.5));
+        const T vx = x0[3] + a * kx[3], vy = x0[4] + a * kx[4], vz = x0[5] + a * kx[5];
+        const T qw = x0[6] + a * kx[6], qx = x0[7] + a * kx[7], qy = x0[8] + a * kx[8], qz = x0[9] + a * kx[9];
+        const T s3 = s0[3] + a * ks[3], s4 = s0[4] + a * ks[4], s5 = s0[5] + a * ks[5];
+        const T s6 = s0[6] + a * ks[6], s7 = s0[7] + a * ks[7], s8 = s0[8] + a * ks[8], s9 = s0[9] + a * ks[9];
+        const T r13 = T(2) * (qx * qz + qw * qy), r23 = T(2) * (qy * qz - qw * qx);
+        const T r33 = T(1) - T(2) * qx * qx - T(2) * qy * qy;
+        kx[0] = vx; kx[1] = vy; kx[2] = vz;
+        kx[3] = r13 * cc + fm0;
+        kx[4] = r23 * cc + fm1;
+        kx[5] = r33 * cc - c.g + fm2;
+        kx[6] = T(0.5) * (-wx * qx - wy * qy - wz * qz);
+        kx[7] = T(0.5) * (wx * qw + wz * qy - wy * qz);
+        kx[8] = T(0.5) * (wy * qw - wz * qx + wx * qz);
+        kx[9] = T(0.5) * (wz * qw + wy * qx - wx * qy);
+        const T c2 = T(2) * cc;
+        ks[0] = s3; ks[1] = s4; ks[2] = s5;
+        ks[3] = c2 * (qy * s6 + qz * s7 + qw * s8 + qx * s9) + ec * r13;
+        ks[4] = c2 * (-qx * s6 - qw * s7 + qz * s8 + qy * s9) + ec * r23;
+        ks[5] = -T(2) * c2 * (qx * s7 + qy * s8) + ec * r33;
+        ks[6] = T(0.5) * (-wx * s7 - wy * s8 - wz * s9 - qx * ew0 - qy * ew1 - qz * ew2);
+        ks[7] = T(0.5) * (wx * s6 + wz * s8 - wy * s9 + qw * ew0 - qz * ew1 + qy * ew2);
+        ks[8] = T(0.5) * (wy * s6 - wz * s7 + wx * s9 + qz * ew0 + qw * ew1 - qx * ew2);
+        ks[9] = T(0.5) * (wz * s6 + wy * s7 - wx * s8 - qy * ew0 + qx * ew1 + qw * ew2);
+        const T bw = (st == 0 || st == 3) ? h * T(1.0 / 6.0) : h * T(1.0 / 3.0);
+#pragma unroll
+        for (int i = 0; i < 10; i++) {
+            xa[i] += bw * kx[i];
+            sa[i] += bw * ks[i];
+        }
+    }
+}
+
+// Gauss-Newton cost blocks in column form: lane j < 14 gets column j of the stage Hessian,
+// lane 14 the gradient (yref quaternion part may differ from q_r).
+template <typename T>
+__device__ __forceinline__ void add_cost(T (&H)[14], const RtiCfg<T>& c, int j, int k, bool terminal, const T* __restrict__ sX,
+                                         const T* __restrict__ sU, const T* __restrict__ sY, const T* __restrict__ sPar) {
+    const T s = terminal ? T(1) : c.h;
+    const T* xk = sX + k * NX;
+    const T* yr = sY + k * NYS;
+    const T* pr = sPar + k * NPS;
+    const bool g = (j == 14);
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        const T yi = (j == i) ? T(1) : (g ? xk[i] - yr[i] : T(0));
+        H[i] += s * c.Q[i] * yi;
+    }
+    const T w = pr[0], x = pr[1], y = pr[2], z = pr[3];
+    T yq[4];
+#pragma unroll
+    for (int n = 0; n < 4; n++) yq[n] = (j == 6 + n) ? T(1) : (g ? xk[6 + n] : T(0));
+    const T d1 = g ? pr[1] - yr[7] : T(0), d2 = g ? pr[2] - yr[8] : T(0), d3 = g ? pr[3] - yr[9] : T(0);
+    const T v1 = c.Q[7] * (-x * yq[0] + w * yq[1] - z * yq[2] + y * yq[3] + d1);
+    const T v2 = c.Q[8] * (-y * yq[0] + z * yq[1] + w * yq[2] - x * yq[3] + d2);
+    const T v3 = c.Q[9] * (-z * yq[0] - y * yq[1] + x * yq[2] + w * yq[3] + d3);
+    H[6] += s * (-x * v1 - y * v2 - z * v3);
+    H[7] += s * (w * v1 + z * v2 - y * v3);
+    H[8] += s * (-z * v1 + w * v2 + x * v3);
+    H[9] += s * (y * v1 - x * v2 + w * v3);
+    if (!terminal) {
+#pragma unroll
+        for (int m = 0; m < 4; m++) {
+            const T yu = (j == 10 + m) ? T(1) : (g ? sU[k * NU + m] - yr[10 + m] : T(0));
+            H[10 + m] += s * c.R[m] * yu;
+        }
+    }
+}
+
+// Terminal stage: P_N = W_e (+ barrier), p_N = gradient.
+template <typename T, bool kBar>
+__device__ __forceinline__ void backward_terminal(const RtiCfg<T>& c, int j, unsigned mask, T* sm, const SmemLayout& L, const T* ws,
+                                                  const WsLayout& WL) {
+    const int N = c.N;
+    T H[14];
+#pragma unroll
+    for (int i = 0; i < 14; i++) H[i] = T(0);
+    add_cost<T>(H, c, j, N, true, sm + L.oX, sm + L.oU, sm + L.oY, sm + L.oPar);
+    (void)ws; (void)WL;  // no bounds at the terminal node (acados lbx/ubx: intermediate nodes only)
+    __syncwarp(mask);
+    if (j < 10) {
+#pragma unroll
+        for (int i = 0; i < 10; i++) sm[L.oP + i * 12 + j] = H[i];
+    } else if (j == 14) {
+#pragma unroll
+        for (int i = 0; i < 10; i++) sm[L.op + i] = H[i];
+    }
+    __syncwarp(mask);
+}
+
+// One backward Riccati stage.  kLin: integrate the sensitivity column (and store it) instead of
+// loading it; kBar: add the barrier / active-set diagonal and gradient; kRows: store the rows of
+// [Hux Guu | g_u] needed by the active-set multiplier test.  Returns false on a non-positive pivot.
+template <typename T, bool kLin, bool kBar, bool kRows>
+__device__ __forceinline__ bool backward_stage(const RtiCfg<T>& c, int k, int j, unsigned mask, T* sm, const SmemLayout& L, T* ws,
+                                               const WsLayout& WL) {
+    const T* sX = sm + L.oX;
+    const T* sU = sm + L.oU;
+    const T* sPar = sm + L.oPar;
+    T* sP = sm + L.oP;
+    T* sp = sm + L.op;
+    T* sAB = sm + L.oAB;
+    T* sHux = sm + L.oHux;
+    T col[10];
+    if (kLin) {
+        T xa[10], sa[10];
+        const T* pr = sPar + k * NPS;
+        rk4_column<T>(c, j, sX + k * NX, sU + k * NU, pr[4] * c.inv_mass, pr[5] * c.inv_mass, pr[6] * c.inv_mass, xa, sa);
+#pragma unroll
+        for (int r = 0; r < 10; r++) col[r] = (j == 14) ? xa[r] - sX[(k + 1) * NX + r] : sa[r];
+        if (j >= 6 && j < 14) {
+#pragma unroll
+            for (int r = 0; r < 10; r++) ws[WL.oAB + k * 80 + r * 8 + (j - 6)] = col[r];
+        } else if (j == 14) {
+#pragma unroll
+            for (int r = 0; r < 10; r++) ws[WL.oRec + k * 16 + r] = col[r];
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < 10; r++) col[r] = (j == r) ? T(1) : T(0);
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+            if (j == r + 3) col[r] = c.h;  // dp/dv0 = h I exactly
+        if (j >= 6 && j < 14) {
+#pragma unroll
+            for (int r = 0; r < 10; r++) col[r] = ws[WL.oAB + k * 80 + r * 8 + (j - 6)];
+        } else if (j == 14) {
+#pragma unroll
+            for (int r = 0; r < 10; r++) col[r] = ws[WL.oRec + k * 16 + r];
+        }
+    }
+    // W = P+ col (+ p+ on the gradient lane)
+    T W[10];
+#pragma unroll
+    for (int i = 0; i < 10; i++) {
+        T p0, p1, p2, p3, p4, p5, p6, p7, p8, p9, pa, pb;
+        Vec4<T>::ld(sP + i * 12, p0, p1, p2, p3);
+        Vec4<T>::ld(sP + i * 12 + 4, p4, p5, p6, p7);
+        Vec4<T>::ld(sP + i * 12 + 8, p8, p9, pa, pb);
+        T acc = (j == 14) ? sp[i] : T(0);
+        acc += p0 * col[0]; acc += p1 * col[1]; acc += p2 * col[2]; acc += p3 * col[3]; acc += p4 * col[4];
+        acc += p5 * col[5]; acc += p6 * col[6]; acc += p7 * col[7]; acc += p8 * col[8]; acc += p9 * col[9];
+        W[i] = acc;
+    }
+    // publish the nontrivial columns (6..13) and b (col 8 of the tile)
+    if (j >= 6 && j < 15) {
+#pragma unroll
+        for (int r = 0; r < 10; r++) sAB[r * 12 + (j - 6)] = col[r];
+    }
+    __syncwarp(mask);
+    // H[:,j] = [A B]' W  (columns 0..5 of [A B] are [I; 0; 0] and [hI; I; 0])
+    T H[14];
+    H[0] = W[0]; H[1] = W[1]; H[2] = W[2];
+    H[3] = c.h * W[0] + W[3];
+    H[4] = c.h * W[1] + W[4];
+    H[5] = c.h * W[2] + W[5];
+#pragma unroll
+    for (int i = 6; i < 14; i++) H[i] = T(0);
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        T a0, a1, a2, a3, a4, a5, a6, a7;
+        Vec4<T>::ld(sAB + r * 12, a0, a1, a2, a3);
+        Vec4<T>::ld(sAB + r * 12 + 4, a4, a5, a6, a7);
+        H[6] += a0 * W[r]; H[7] += a1 * W[r]; H[8] += a2 * W[r]; H[9] += a3 * W[r];
+        H[10] += a4 * W[r]; H[11] += a5 * W[r]; H[12] += a6 * W[r]; H[13] += a7 * W[r];
+    }
+    add_cost<T>(H, c, j, k, false, sX, sU, sm + L.oY, sPar);
+    if (kRows) {
+        // rows of the un-penalised [Hux Guu] (by symmetry: column 10+m) and g_u, for the multiplier test
+        if (j >= 10 && j < 14) {
+#pragma unroll
+            for (int i = 0; i < 14; i++) ws[WL.oHrow + (k * 4 + (j - 10)) * 16 + i] = H[i];
+        } else if (j == 14) {
+#pragma unroll
+            for (int m = 0; m < 4; m++) ws[WL.oHrow + (k * 4 + m) * 16 + 14] = H[10 + m];
+        }
+    }
+    if (kBar) {
+        if (j < 14) {
+            const T d = ws[WL.oBarD + k * 16 + j];
+#pragma unroll
+            for (int i = 0; i < 14; i++) H[i] += (j == i) ? d : T(0);
+        } else if (j == 14) {
+#pragma unroll
+            for (int i = 0; i < 14; i++) H[i] += ws[WL.oBarG + k * 16 + i];
+        }
+    }
+    // 4x4 input block G = Huu from lanes 10..13, Cholesky, solve for this lane's column
+    const T g00 = __shfl_sync(mask, H[10], 10, GL), g10 = __shfl_sync(mask, H[11], 10, GL);
+    const T g20 = __shfl_sync(mask, H[12], 10, GL), g30 = __shfl_sync(mask, H[13], 10, GL);
+    const T g11 = __shfl_sync(mask, H[11], 11, GL), g21 = __shfl_sync(mask, H[12], 11, GL);
+    const T g31 = __shfl_sync(mask, H[13], 11, GL), g22 = __shfl_sync(mask, H[12], 12, GL);
+    const T g32 = __shfl_sync(mask, H[13], 12, GL), g33 = __shfl_sync(mask, H[13], 13, GL);
+    const T l00 = tsqrt(g00), i00 = T(1) / l00;
+    const T l10 = g10 * i00, l20 = g20 * i00, l30 = g30 * i00;
+    const T e1 = g11 - l10 * l10;
+    const T l11 = tsqrt(e1), i11 = T(1) / l11;
+    const T l21 = (g21 - l20 * l10) * i11, l31 = (g31 - l30 * l10) * i11;
+    const T e2 = g22 - l20 * l20 - l21 * l21;
+    const T l22 = tsqrt(e2), i22 = T(1) / l22;
+    const T l32 = (g32 - l30 * l20 - l31 * l21) * i22;
+    const T e3 = g33 - l30 * l30 - l31 * l31 - l32 * l32;
+    const T l33 = tsqrt(e3), i33 = T(1) / l33;
+    const bool ok = (g00 > T(0)) && (e1 > T(0)) && (e2 > T(0)) && (e3 > T(0));
+    const T y0 = H[10] * i00;
+    const T y1 = (H[11] - l10 * y0) * i11;
+    const T y2 = (H[12] - l20 * y0 - l21 * y1) * i22;
+    const T y3 = (H[13] - l30 * y0 - l31 * y1 - l32 * y2) * i33;
+    const T x3 = y3 * i33;
+    const T x2 = (y2 - l32 * x3) * i22;
+    const T x1 = (y1 - l21 * x2 - l31 * x3) * i11;
+    const T x0 = (y0 - l10 * x1 - l20 * x2 - l30 * x3) * i00;
+    const T K0 = -x0, K1 = -x1, K2 = -x2, K3 = -x3;  // K[:,j] (j < 10) or kappa (j == 14)
+    if (j < 10) Vec4<T>::st(sHux + j * 4, H[10], H[11], H[12], H[13]);
+    __syncwarp(mask);
+    T Pn[10];
+#pragma unroll
+    for (int i = 0; i < 10; i++) {
+        T h0, h1, h2, h3;
+        Vec4<T>::ld(sHux + i * 4, h0, h1, h2, h3);
+        Pn[i] = H[i] + h0 * K0 + h1 * K1 + h2 * K2 + h3 * K3;
+    }
+    if (j < 10) {
+#pragma unroll
+        for (int i = 0; i < 10; i++) sP[i * 12 + j] = Pn[i];
+        Vec4<T>::st(ws + WL.oKt + k * 40 + j * 4, K0, K1, K2, K3);
+    } else if (j == 14) {
+#pragma unroll
+        for (int i = 0; i < 10; i++) sp[i] = Pn[i];
+        ws[WL.oRec + k * 16 + 10] = K0;
+        ws[WL.oRec + k * 16 + 11] = K1;
+        ws[WL.oRec + k * 16 + 12] = K2;
+        ws[WL.oRec + k * 16 + 13] = K3;
+    }
+    __syncwarp(mask);
+    return ok;
+}
+
+template <typename T, bool kLin, bool kBar, bool kRows>
+__device__ __forceinline__ bool backward_sweep(const RtiCfg<T>& c, int j, unsigned mask, T* sm, const SmemLayout& L, T* ws,
+                                               const WsLayout& WL) {
+    backward_terminal<T, kBar>(c, j, mask, sm, L, ws, WL);
+    bool ok = true;
+    for (int k = c.N - 1; k >= 0; k--) ok &= backward_stage<T, kLin, kBar, kRows>(c, k, j, mask, sm, L, ws, WL);
+    return __all_sync(mask, ok);
+}
+
+// Forward substitution: lane i < 10 carries dx_k[i], lanes 10..13 compute du_k[m].
+// Writes the step to sDz[k][lane].
+template <typename T>
+__device__ __forceinline__ void forward_sweep(const RtiCfg<T>& c, int lane, unsigned mask, T dx0, T* sm, const SmemLayout& L,
+                                              const T* ws, const WsLayout& WL) {
+    const int N = c.N;
+    T* sDz = sm + L.oDz;
+    const bool isx = lane < 10, isu = (lane >= 10 && lane < 14);
+    T z = isx ? dx0 : T(0);
+    T cf[11], nf[11];
+    auto load = [&](int k, T(&f)[11]) {
+#pragma unroll
+        for (int i = 0; i < 11; i++) f[i] = T(0);
+        if (isx) {
+            Vec4<T>::ld(ws + WL.oAB + k * 80 + lane * 8, f[0], f[1], f[2], f[3]);
+            Vec4<T>::ld(ws + WL.oAB + k * 80 + lane * 8 + 4, f[4], f[5], f[6], f[7]);
+            f[8] = ws[WL.oRec + k * 16 + lane];
+        } else if (isu) {
+#pragma unroll
+            for (int jj = 0; jj < 10; jj++) f[jj] = ws[WL.oKt + k * 40 + jj * 4 + (lane - 10)];
+            f[10] = ws[WL.oRec + k * 16 + lane];
+        }
+    };
+    load(0, cf);
+    for (int k = 0; k < N; k++) {
+        if (k + 1 < N) load(k + 1, nf);
+        T xj[10];
+#pragma unroll
+        for (int jj = 0; jj < 10; jj++) xj[jj] = __shfl_sync(mask, z, jj, GL);
+        const T zv = __shfl_sync(mask, z, (lane + 3) & 15, GL);
+        T du = cf[10];
+#pragma unroll
+        for (int jj = 0; jj < 10; jj++) du += cf[jj] * xj[jj];
+        T um[4];
+#pragma unroll
+        for (int m = 0; m < 4; m++) um[m] = __shfl_sync(mask, du, 10 + m, GL);
+        T xn = cf[8] + ((lane < 3) ? z + c.h * zv : ((lane < 6) ? z : T(0)));
+        xn += cf[0] * xj[6] + cf[1] * xj[7] + cf[2] * xj[8] + cf[3] * xj[9];
+        xn += cf[4] * um[0] + cf[5] * um[1] + cf[6] * um[2] + cf[7] * um[3];
+        if (lane < 14) sDz[k * 16 + lane] = isx ? z : du;
+        z = xn;
+#pragma unroll
+        for (int i = 0; i < 11; i++) cf[i] = nf[i];
+    }
+    if (isx) sDz[N * 16 + lane] = z;
+    __syncwarp(mask);
+}
+
+enum { IPM_LL = 0, IPM_LU, IPM_TL, IPM_TU, IPM_CL, IPM_CU, IPM_ACT };
+
+template <typename T>
+__global__ void __launch_bounds__(RTI_THREADS, (sizeof(T) == 4) ? 4 : 2) rti_step_kernel(const RtiCfg<T> c, const RtiArgs<T> a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int N = c.N;
+    const SmemLayout L(N);
+    const WsLayout WL(N);
+    const int lane = threadIdx.x & 15;
+    const int grp = threadIdx.x >> 4;
+    const unsigned mask = 0xFFFFu << (threadIdx.x & 16);
+    T* sm = reinterpret_cast<T*>(smem_raw) + (size_t)grp * L.total;
+    T* ws = a.ws + (size_t)(blockIdx.x * RTI_PPC + grp) * a.ws_stride;
+    T* sX = sm + L.oX;
+    T* sU = sm + L.oU;
+    T* sDz = sm + L.oDz;
+
+    // per-lane box of the variable this lane owns (lanes 3..5: v, lanes 10..13: u)
+    T lo = T(-1e30), hi = T(1e30);
+#pragma unroll
+    for (int m = 0; m < 3; m++)
+        if (lane == 3 + m) { lo = c.vmin[m]; hi = c.vmax[m]; }
+#pragma unroll
+    for (int m = 0; m < 4; m++)
+        if (lane == 10 + m) { lo = c.umin[m]; hi = c.umax[m]; }
+    const bool isx = lane < 10, isu = (lane >= 10 && lane < 14), isv = (lane >= 3 && lane < 6);
+
+    for (int prob = blockIdx.x * RTI_PPC + grp; prob < a.B; prob += gridDim.x * RTI_PPC) {
+        // ---- stage the problem record in shared memory ----
+        {
+            const T* gX = a.X + (size_t)prob * (N + 1) * NX;
+            const T* gU = a.U + (size_t)prob * N * NU;
+            const T* gY = a.yref + (size_t)prob * (N + 1) * NYS;
+            const T* gP = a.par + (size_t)prob * (N + 1) * NPS;
+            for (int i = lane; i < (N + 1) * NX; i += GL) sX[i] = gX[i];
+            for (int i = lane; i < N * NU; i += GL) sU[i] = gU[i];
+            for (int i = lane; i < (N + 1) * NYS; i += GL) sm[L.oY + i] = gY[i];
+            for (int i = lane; i < (N + 1) * NPS; i += GL) sm[L.oPar + i] = gP[i];
+        }
+        const T dx0 = isx ? a.x0[(size_t)prob * NX + lane] - a.X[(size_t)prob * (N + 1) * NX + lane] : T(0);
+        __syncwarp(mask);
+
+        int status = 0, n_fact = 0, n_ipm = 0, n_pol = 0;
+        // iterate value of the variable this lane owns at stage k
+        auto iter_at = [&](int k) -> T { return isx ? sX[k * NX + lane] : (isu ? sU[k * NU + (lane - 10)] : T(0)); };
+        auto has_box = [&](int k) -> bool { return (isu && k < N) || (isv && k >= 1 && k < N); };
+
+        // ---- preparation + unconstrained feedback ----
+        bool ok = backward_sweep<T, true, false, false>(c, lane, mask, sm, L, ws, WL);
+        n_fact++;
+        forward_sweep<T>(c, lane, mask, dx0, sm, L, ws, WL);
+        bool viol = false;
+        for (int k = 0; k < N; k++)
+            if (has_box(k)) {
+                const T v = iter_at(k) + sDz[k * 16 + lane];
+                viol |= !(v >= lo && v <= hi);
+            }
+        viol = __any_sync(mask, viol);
+        if (!ok) status = 4;
+
+        if (ok && viol) {
+            // ================= Mehrotra IPM on the Riccati kernel =================
+            T* wI = ws + WL.oIpm;
+            T* wZ = ws + WL.oZc;
+            T* bD = ws + WL.oBarD;
+            T* bG = ws + WL.oBarG;
+            const int FS = N * 16;  // field stride
+            for (int k = 0; k <= N; k++) {
+                bD[k * 16 + lane] = T(0);
+                bG[k * 16 + lane] = T(0);
+                wZ[k * 16 + lane] = (k == 0 && isx) ? dx0 : T(0);
+            }
+            int nb_l = 0;
+            for (int k = 0; k < N; k++)
+                if (has_box(k)) {
+                    const T it_v = iter_at(k);
+                    const T lb = lo - it_v, ub = hi - it_v;
+                    const T tl = fmax(-lb, c.t_floor), tu = fmax(ub, c.t_floor);
+                    wI[IPM_TL * FS + k * 16 + lane] = tl;
+                    wI[IPM_TU * FS + k * 16 + lane] = tu;
+                    wI[IPM_LL * FS + k * 16 + lane] = c.mu0 / tl;
+                    wI[IPM_LU * FS + k * 16 + lane] = c.mu0 / tu;
+                    nb_l++;
+                }
+            const T inv_m = T(1) / (T(2) * grp_sum<T>((T)nb_l, mask));
+            __syncwarp(mask);
+            T res_lin = T(1), mu_prev = T(1e30), mu = T(0);
+            bool ipm_ok = false, any_x_act = false;
+            int it = 0;
+            for (it = 0; it <= c.ipm_max_iter; it++) {
+                // complementarity, affine barrier terms
+                T mu_l = T(0);
+                bool xa_l = false;
+                for (int k = 0; k < N; k++)
+                    if (has_box(k)) {
+                        const int e = k * 16 + lane;
+                        const T it_v = iter_at(k);
+                        const T lb = lo - it_v, ub = hi - it_v;
+                        const T tl = wI[IPM_TL * FS + e], tu = wI[IPM_TU * FS + e];
+                        const T ll = wI[IPM_LL * FS + e], lu = wI[IPM_LU * FS + e];
+                        mu_l += ll * tl + lu * tu;
+                        const T gl = ll / tl, gu = lu / tu;
+                        bD[e] = gl + gu;
+                        bG[e] = (-gu * ub + lu) - (gl * lb + ll);
+                        if (isv) xa_l |= (tl < ll) || (tu < lu);
+                    }
+                mu = grp_sum<T>(mu_l, mask) * inv_m;
+                any_x_act = __any_sync(mask, xa_l);
+                const T tol = any_x_act ? c.tol_mu * T(0.01) : c.tol_mu;
+                if (it > 0 && res_lin == T(0) && mu < tol) { ipm_ok = true; break; }
+                if (it > 3 && res_lin == T(0) && mu > T(0.9) * mu_prev && mu < T(1e-2)) { ipm_ok = true; break; }
+                if (!(mu == mu)) { status = 4; break; }  // NaN
+                if (it == c.ipm_max_iter) break;
+                mu_prev = mu;
+                __syncwarp(mask);
+                // ---- predictor ----
+                if (!backward_sweep<T, false, true, false>(c, lane, mask, sm, L, ws, WL)) { status = 4; break; }
+                n_fact++;
+                forward_sweep<T>(c, lane, mask, dx0, sm, L, ws, WL);
+                T amax = T(1e30);
+                for (int k = 0; k < N; k++)
+                    if (has_box(k)) {
+                        const int e = k * 16 + lane;
+                        const T it_v = iter_at(k);
+                        const T lb = lo - it_v, ub = hi - it_v;
+                        const T zn = sDz[e];
+                        const T tl = wI[IPM_TL * FS + e], tu = wI[IPM_TU * FS + e];
+                        const T ll = wI[IPM_LL * FS + e], lu = wI[IPM_LU * FS + e];
+                        const T dtl = (zn - lb) - tl, dtu = (ub - zn) - tu;
+                        const T dll = -(ll / tl) * dtl - ll, dlu = -(lu / tu) * dtu - lu;
+                        wI[IPM_CL * FS + e] = dll * dtl;
+                        wI[IPM_CU * FS + e] = dlu * dtu;
+                        if (dtl < T(0)) amax = fmin(amax, -tl / dtl);
+                        if (dtu < T(0)) amax = fmin(amax, -tu / dtu);
+                        if (dll < T(0)) amax = fmin(amax, -ll / dll);
+                        if (dlu < T(0)) amax = fmin(amax, -lu / dlu);
+                    }
+                const T a_aff = fmin(grp_min<T>(amax, mask), T(1));
+                T mua_l = T(0);
+                for (int k = 0; k < N; k++)
+                    if (has_box(k)) {
+                        const int e = k * 16 + lane;
+                        const T it_v = iter_at(k);
+                        const T lb = lo - it_v, ub = hi - it_v;
+                        const T zn = sDz[e];
+                        const T tl = wI[IPM_TL * FS + e], tu = wI[IPM_TU * FS + e];
+                        const T ll = wI[IPM_LL * FS + e], lu = wI[IPM_LU * FS + e];
+                        const T dtl = (zn - lb) - tl, dtu = (ub - zn) - tu;
+                        const T dll = -(ll / tl) * dtl - ll, dlu = -(lu / tu) * dtu - lu;
+                        mua_l += (ll + a_aff * dll) * (tl + a_aff * dtl) + (lu + a_aff * dlu) * (tu + a_aff * dtu);
+                    }
+                const T mu_aff = grp_sum<T>(mua_l, mask) * inv_m;
+                const T sg = mu_aff / mu;
+                const T sigma_mu = sg * sg * sg * mu;
+                // ---- corrector ----
+                for (int k = 0; k < N; k++)
+                    if (has_box(k)) {
+                        const int e = k * 16 + lane;
+                        const T it_v = iter_at(k);
+                        const T lb = lo - it_v, ub = hi - it_v;
+                        const T tl = wI[IPM_TL * FS + e], tu = wI[IPM_TU * FS + e];
+                        const T ll = wI[IPM_LL * FS + e], lu = wI[IPM_LU * FS + e];
+                        const T gl = ll / tl, gu = lu / tu;
+                        const T cl = wI[IPM_CL * FS + e], cu = wI[IPM_CU * FS + e];
+                        bG[e] = ((sigma_mu - cu) / tu - gu * ub + lu) - ((sigma_mu - cl) / tl + gl * lb + ll);
+                    }
+                __syncwarp(mask);
+                if (!backward_sweep<T, false, true, false>(c, lane, mask, sm, L, ws, WL)) { status = 4; break; }
+                n_fact++;
+                forward_sweep<T>(c, lane, mask, dx0, sm, L, ws, WL);
+                amax = T(1e30);
+                for (int k = 0; k < N; k++)
+                    if (has_box(k)) {
+                        const int e = k * 16 + lane;
+                        const T it_v = iter_at(k);
+                        const T lb = lo - it_v, ub = hi - it_v;
+                        const T zn = sDz[e];
+                        const T tl = wI[IPM_TL * FS + e], tu = wI[IPM_TU * FS + e];
+                        const T ll = wI[IPM_LL * FS + e], lu = wI[IPM_LU * FS + e];
+                        const T cl = wI[IPM_CL * FS + e], cu = wI[IPM_CU * FS + e];
+                        const T dtl = (zn - lb) - tl, dtu = (ub - zn) - tu;
+                        const T dll = (sigma_mu - cl) / tl - (ll / tl) * dtl - ll;
+                        const T dlu = (sigma_mu - cu) / tu - (lu / tu) * dtu - lu;
+                        if (dtl < T(0)) amax = fmin(amax, -tl / dtl);
+                        if (dtu < T(0)) amax = fmin(amax, -tu / dtu);
+                        if (dll < T(0)) amax = fmin(amax, -ll / dll);
+                        if (dlu < T(0)) amax = fmin(amax, -lu / dlu);
+                    }
+                const T alpha = fmin(T(1), T(0.995) * grp_min<T>(amax, mask));
+                for (int k = 0; k < N; k++)
+                    if (has_box(k)) {
+                        const int e = k * 16 + lane;
+                        const T it_v = iter_at(k);
+                        const T lb = lo - it_v, ub = hi - it_v;
+                        const T zn = sDz[e];
+                        const T tl = wI[IPM_TL * FS + e], tu = wI[IPM_TU * FS + e];
+                        const T ll = wI[IPM_LL * FS + e], lu = wI[IPM_LU * FS + e];
+                        const T cl = wI[IPM_CL * FS + e], cu = wI[IPM_CU * FS + e];
+                        const T dtl = (zn - lb) - tl, dtu = (ub - zn) - tu;
+                        const T dll = (sigma_mu - cl) / tl - (ll / tl) * dtl - ll;
+                        const T dlu = (sigma_mu - cu) / tu - (lu / tu) * dtu - lu;
+                        wI[IPM_TL * FS + e] = tl + alpha * dtl;
+                        wI[IPM_TU * FS + e] = tu + alpha * dtu;
+                        wI[IPM_LL * FS + e] = ll + alpha * dll;
+                        wI[IPM_LU * FS + e] = lu + alpha * dlu;
+                    }
+                if (lane < 14)
+                    for (int k = 0; k <= N; k++) {
+                        if (k == N && !isx) break;
+                        const int e = k * 16 + lane;
+                        wZ[e] += alpha * (sDz[e] - wZ[e]);
+                    }
+                res_lin *= (T(1) - alpha);
+                n_ipm++;
+                __syncwarp(mask);
+            }
+            // ================= active-set refinement =================
+            bool pol_ok = false;
+            if (status == 0 && c.polish_max > 0) {
+                for (int k = 0; k < N; k++)
+                    if (has_box(k)) {
+                        const int e = k * 16 + lane;
+                        const T tl = wI[IPM_TL * FS + e], tu = wI[IPM_TU * FS + e];
+                        const T ll = wI[IPM_LL * FS + e], lu = wI[IPM_LU * FS + e];
+                        wI[IPM_ACT * FS + e] = (tl < ll) ? T(1) : ((tu < lu) ? T(2) : T(0));
+                    }
+                for (int round = 0; round < c.polish_max; round++) {
+                    for (int k = 0; k < N; k++)
+                        if (has_box(k)) {
+                            const int e = k * 16 + lane;
+                            const T it_v = iter_at(k);
+                            const T lb = lo - it_v, ub = hi - it_v;
+                            if (isu) {
+                                const T act = wI[IPM_ACT * FS + e];
+                                bD[e] = (act != T(0)) ? c.big : T(0);
+                                bG[e] = (act != T(0)) ? -c.big * (act == T(1) ? lb : ub) : T(0);
+                            } else {
+                                const T tl = wI[IPM_TL * FS + e], tu = wI[IPM_TU * FS + e];
+                                const T ll = wI[IPM_LL * FS + e], lu = wI[IPM_LU * FS + e];
+                                const T gl = ll / tl, gu = lu / tu;
+                                bD[e] = gl + gu;
+                                bG[e] = (-gu * ub + lu) - (gl * lb + ll);
+                            }
+                        }
+                    __syncwarp(mask);
+                    if (!backward_sweep<T, false, true, true>(c, lane, mask, sm, L, ws, WL)) break;
+                    n_fact++;
+                    n_pol++;
+                    forward_sweep<T>(c, lane, mask, dx0, sm, L, ws, WL);
+                    bool changed = false;
+                    if (isu)
+                        for (int k = 0; k < N; k++) {
+                            const int e = k * 16 + lane;
+                            const T it_v = iter_at(k);
+                            const T lb = lo - it_v, ub = hi - it_v;
+                            const T act = wI[IPM_ACT * FS + e];
+                            if (act != T(0)) {
+                                const T* hr = ws + WL.oHrow + (k * 4 + (lane - 10)) * 16;
+                                T gq = hr[14];
+#pragma unroll
+                                for (int i = 0; i < 14; i++) gq += hr[i] * sDz[k * 16 + i];
+                                const T lam = (act == T(2)) ? -gq : gq;
+                                if (lam < T(0)) { wI[IPM_ACT * FS + e] = T(0); changed = true; }
+                            } else {
+                                const T zn = sDz[e];
+                                if (zn > ub) { wI[IPM_ACT * FS + e] = T(2); changed = true; }
+                                else if (zn < lb) { wI[IPM_ACT * FS + e] = T(1); changed = true; }
+                            }
+                        }
+                    changed = __any_sync(mask, changed);
+                    __syncwarp(mask);
+                    if (!changed) { pol_ok = true; break; }
+                }
+                if (pol_ok && isu) {
+                    // pinned inputs sit exactly on their bound
+                    for (int k = 0; k < N; k++) {
+                        const int e = k * 16 + lane;
+                        const T act = wI[IPM_ACT * FS + e];
+                        const T it_v = iter_at(k);
+                        if (act == T(1)) sDz[e] = lo - it_v;
+                        if (act == T(2)) sDz[e] = hi - it_v;
+                    }
+                }
+            }
+            if (!pol_ok) {
+                // fall back to the interior-point iterate
+                if (lane < 14)
+                    for (int k = 0; k <= N; k++) {
+                        if (k == N && !isx) break;
+                        sDz[k * 16 + lane] = wZ[k * 16 + lane];
+                    }
+                if (!ipm_ok && status == 0) status = 4;
+            }
+            __syncwarp(mask);
+        }
+
+        // ---- full step, write back ----
+        bool bad = false;
+        int nact_l = 0;
+        if (lane < 14)
+            for (int k = 0; k <= N; k++) {
+                if (k == N && !isx) break;
+                const T v = iter_at(k) + sDz[k * 16 + lane];
+                bad |= !(v == v) || (fabs(v) > T(1e30));
+                if (has_box(k)) nact_l += (v <= lo) + (v >= hi);
+                if (isx) sX[k * NX + lane] = v;
+                else sU[k * NU + (lane - 10)] = v;
+            }
+        bad = __any_sync(mask, bad);
+        const int nact = (int)grp_sum<float>((float)nact_l, mask);
+        if (bad) status = 1;
+        __syncwarp(mask);
+        {
+            T* gX = a.X + (size_t)prob * (N + 1) * NX;
+            T* gU = a.U + (size_t)prob * N * NU;
+            for (int i = lane; i < (N + 1) * NX; i += GL) gX[i] = sX[i];
+            for (int i = lane; i < N * NU; i += GL) gU[i] = sU[i];
+            if (a.u0 && lane < NU) a.u0[(size_t)prob * NU + lane] = sU[lane];
+            if (lane == 0) {
+                a.status[prob] = status;
+                a.stats[prob * 4 + 0] = n_fact;
+                a.stats[prob * 4 + 1] = n_ipm;
+                a.stats[prob * 4 + 2] = n_pol;
+                a.stats[prob * 4 + 3] = nact;
+            }
+        }
+        __syncwarp(mask);
+    }
+}
+
+}  // namespace ndp

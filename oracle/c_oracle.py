@@ -29,6 +29,7 @@ class OrcCfg(C.Structure):
         ("v_min", C.c_double * 3),
         ("v_max", C.c_double * 3),
         ("tol", C.c_double),
+        ("tol_mu", C.c_double),
         ("max_iter", C.c_int),
         ("mu0", C.c_double),
         ("t_floor", C.c_double),
@@ -44,7 +45,7 @@ def build(force: bool = False) -> str:
     return out
 
 
-def make_cfg(N=20, T=None, tol=1e-10, max_iter=50, u_min=None, u_max=None, v_min=None, v_max=None) -> OrcCfg:
+def make_cfg(N=20, T=None, tol=1e-10, tol_mu=None, max_iter=50, u_min=None, u_max=None, v_min=None, v_max=None) -> OrcCfg:
     """Constants of params/nmpc_params.py:9-35 and params/fhnp_params.py:9-19.
 
     th_pred = T/N is 0.1 s in the reference; for N != 20 the horizon is T = 0.1 N
@@ -61,6 +62,7 @@ def make_cfg(N=20, T=None, tol=1e-10, max_iter=50, u_min=None, u_max=None, v_min
     c.v_min[:] = list(v_min) if v_min is not None else [-20, -20, -20]
     c.v_max[:] = list(v_max) if v_max is not None else [20, 20, 20]
     c.tol, c.max_iter, c.mu0, c.t_floor = tol, max_iter, 10.0, 0.1
+    c.tol_mu = tol if tol_mu is None else tol_mu
     return c
 
 

@@ -21,6 +21,7 @@
  * -DORC_REAL=float gives an fp32 build used only to study rounding offline.
  */
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #ifdef _OPENMP
@@ -48,7 +49,8 @@ typedef struct {
     double R[NU];     /* diag input weights            nmpc_body_rate_ctl.py:49 */
     double u_min[NU], u_max[NU]; /* nmpc_body_rate_ctl.py:56-58 */
     double v_min[NBX], v_max[NBX]; /* nmpc_body_rate_ctl.py:59-61 */
-    double tol;       /* IPM residual / complementarity tolerance */
+    double tol;       /* IPM residual tolerance */
+    double tol_mu;    /* IPM complementarity tolerance */
     int max_iter;     /* acados qp_solver_iter_max default 50 */
     double mu0;       /* IPM cold start */
     double t_floor;   /* slack floor at cold start */
@@ -388,7 +390,7 @@ int orc_rti_step(const orc_cfg* c, const real* x0, const real* xr, const real* u
             res = fmax(res, fabs(tu[i] - (ub[i] - zb[i])));
         }
         mu /= (2 * nb);
-        if (it > 0 && res < tol && mu < tol && res_lin < tol) { status = 0; break; }
+        if (it > 0 && res < tol && mu < (real)c->tol_mu && res_lin < tol) { status = 0; break; }
         if (it == c->max_iter) break;
         real sigma_mu = 0;
         real alpha = 1;
@@ -451,6 +453,7 @@ int orc_rti_step(const orc_cfg* c, const real* x0, const real* xr, const real* u
         for (int k = 0; k < N; k++)
             for (int m = 0; m < NU; m++) du[k][m] += alpha * (dun[k][m] - du[k][m]);
         res_lin *= (1 - alpha);
+        if (getenv("ORC_TRACE")) fprintf(stderr, "it %d mu %.3e res %.3e alpha %.4f res_lin %.3e sigma_mu %.3e\n", it, (double)mu, (double)res, (double)alpha, (double)res_lin, (double)sigma_mu);
     }
 done:;
     int nact = 0;
