@@ -1,0 +1,83 @@
+"""GPU parity tests of the downwash MLP kernels vs the reference's torch module (golden vectors)
+and the numpy oracle.  Tolerance: 1e-5 N absolute on forces for the fp32 CUDA-core path
+(SURVEY.md 8d); the tensor-core path's tolerance is stated where it is tested."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden
+from oracle import mlp_numpy
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def nn(built_lib):
+    from ndp_nmpc_qd_b200.dnwash_nn_est import DownwashNN
+
+    return DownwashNN()
+
+
+def test_rows_vs_reference_module(nn):
+    g = golden("mlp_golden.npz")
+    x = torch.as_tensor(g["x"], device="cuda")
+    y = nn.forward_rows(x, path=nn.PATH_FP32).cpu().numpy()
+    assert np.abs(y - g["y32"]).max() < 1e-5
+    assert np.abs(y - g["y64"]).max() < 2e-5
+
+
+def test_rows_ragged_sizes(nn, mlp_weights):
+    rng = np.random.default_rng(0)
+    for M in (1, 21, 63, 64, 65, 1000, 20000):
+        x = (rng.normal(size=(M, 6)) * 1.5).astype(np.float32)
+        y = nn.forward_rows(torch.as_tensor(x, device="cuda"), path=nn.PATH_FP32).cpu().numpy()
+        ref = mlp_numpy.mlp_forward(mlp_weights, x, np.float64)
+        assert np.abs(y - ref).max() < 2e-5, M
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_pairs_fused_features_and_gate(nn, mlp_weights, dtype):
+    from ndp_nmpc_qd_b200 import workloads as wl
+
+    w = wl.independent_problems(300, seed=2, with_neighbour=True)
+    ego, other = w["xr"], w["other"].copy()
+    other[::3, :, 0] += 2.0  # every third neighbour is outside the 1 m gate
+    gate = ego[:, 0, 0:2] + 0.01
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=dtype, device="cuda")
+    f = nn.forward_pairs(t(ego), t(other), t(gate), path=nn.PATH_FP32).cpu().numpy()
+    e_, o_, g_ = (t(a).cpu().numpy().astype(np.float64) for a in (ego, other, gate))
+    ref = mlp_numpy.gated_pairs(mlp_weights, e_, o_, g_, 1.0)
+    assert np.abs(f - ref).max() < (3e-5 if dtype == torch.float32 else 2e-5)
+    assert np.all(f[::3] == 0) and np.abs(f[1::3]).max() > 0.1
+    # accumulate adds a second neighbour
+    f2 = nn.forward_pairs(t(ego), t(other), t(gate), out=t(ref.astype(np.float64)).clone(), accumulate=True, path=nn.PATH_FP32)
+    assert np.abs(f2.cpu().numpy() - 2 * ref).max() < 1e-4
+
+
+def test_swarm_all_pairs_vs_oracle(nn, mlp_weights):
+    """config 4 semantics on a 12 x 12 lattice: gated all-pairs sum, ego shard in the middle."""
+    rng = np.random.default_rng(3)
+    n_side, n_nodes = 12, 21
+    gx, gy = np.meshgrid(np.arange(n_side) * 0.8, np.arange(n_side) * 0.8, indexing="ij")
+    n_all = n_side * n_side
+    traj = np.zeros((n_all, n_nodes, 6), np.float32)
+    traj[:, :, 0] = gx.reshape(-1, 1) + 0.05 * np.arange(n_nodes)
+    traj[:, :, 1] = gy.reshape(-1, 1)
+    traj[:, :, 2] = rng.uniform(0.5, 3.5, size=(n_all, 1))
+    traj[:, :, 3:6] = 0.1 * rng.normal(size=(n_all, 1, 3))
+    t = torch.as_tensor(traj, device="cuda")
+    for ego_begin, n_ego in ((0, n_all), (40, 50)):
+        f = nn.forward_swarm(t, ego_begin, n_ego, path=nn.PATH_FP32).cpu().numpy()
+        ref = mlp_numpy.swarm_forces(mlp_weights, traj, ego_begin, n_ego)
+        assert np.abs(f - ref).max() < 1e-4
+        assert np.abs(ref).max() > 1.0
+    # a lone quad has no neighbours -> zeros
+    f = nn.forward_swarm(t[:1].contiguous(), 0, 1).cpu().numpy()
+    assert np.all(f == 0)
+
+
+def test_update_matches_reference_semantics(nn, mlp_weights):
+    g = golden("downwash_golden.npz")
+    f = nn.update(g["other"], g["ego"])
+    assert f.dtype == np.float32 and f.shape == (21, 3)
+    assert np.abs(f - g["f"]).max() < 1e-5

@@ -1,0 +1,209 @@
+"""GPU parity tests of the NMPC hot path: CUDA engine (through the C ABI) vs the fp64 CPU oracle.
+
+Tolerances (BASELINE.json north_star / SURVEY.md 8d): u0 and predicted trajectories within 1e-4
+relative for the fp32 build, 1e-9 for the fp64 build, measured as
+max_b ||a-b||_inf / max(||b||_inf, 1)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden, rel_err
+from oracle.c_oracle import make_cfg
+from ndp_nmpc_qd_b200 import workloads as wl
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"f32": 1e-4, "f64": 1e-9}
+
+
+def _dt(prec):
+    return torch.float32 if prec == "f32" else torch.float64
+
+
+def _engine(B, prec, N=20, np_=7, **kw):
+    from ndp_nmpc_qd_b200.solver import Engine
+
+    return Engine(batch=B, N=N, np_=np_, precision=prec, **kw)
+
+
+def _run_engine(e, w, fd=None, steps=1, x0_seq=None):
+    dt, dev = e.dtype, e.device
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=dt, device=dev)
+    xr, ur = t(w["xr"]), t(w["ur"])
+    e.reset(xr, ur)
+    e.set_reference(xr, ur, None if fd is None else t(fd))
+    u0 = None
+    for s in range(steps):
+        x0 = t(w["x0"] if x0_seq is None else x0_seq[s])
+        u0 = e.solve(x0)
+    torch.cuda.synchronize()
+    return (u0.cpu().numpy().astype(np.float64), e.get_all("x").cpu().numpy().astype(np.float64),
+            e.get_all("u").cpu().numpy().astype(np.float64), e.status().cpu().numpy(), e.stats().cpu().numpy())
+
+
+def _run_oracle(c_oracle, cfg, w, fd=None, steps=1, x0_seq=None):
+    X, U = w["xr"].copy(), w["ur"].copy()
+    r = None
+    for s in range(steps):
+        r = c_oracle.rti_batch(cfg, w["x0"] if x0_seq is None else x0_seq[s], w["xr"], w["ur"], fd, X, U)
+    return r["u0"], X, U, r["status"], r
+
+
+@pytest.mark.parametrize("prec", ["f32", "f64"])
+def test_rk4_sens_kernel_vs_oracle(built_lib, c_oracle, prec):
+    """(1) batched RK4 integrator with forward sensitivities."""
+    import ctypes as C
+
+    from ndp_nmpc_qd_b200 import _lib
+
+    lib = _lib.load()
+    rng = np.random.default_rng(0)
+    M = 1000
+    x = rng.normal(size=(M, 10)); x[:, 6:10] /= np.linalg.norm(x[:, 6:10], axis=1, keepdims=True)
+    u = np.concatenate([rng.normal(size=(M, 3)) * 2, 9.81 + 3 * rng.normal(size=(M, 1))], 1)
+    f = rng.normal(size=(M, 3)) * 2
+    x[0], u[0], f[0] = [0.1, -0.2, 0.3, 1.0, -2.0, 0.5, 0.9, 0.1, -0.2, 0.3], [1.2, -0.7, 0.4, 13.0], [0.3, -0.2, -4.0]
+    dt = _dt(prec)
+    tx, tu, tf = (torch.as_tensor(a, dtype=dt, device="cuda") for a in (x, u, f))
+    xn = torch.empty((M, 10), dtype=dt, device="cuda")
+    AB = torch.empty((M, 10, 14), dtype=dt, device="cuda")
+    p = lambda t: C.c_void_p(t.data_ptr())
+    rc = lib.ndp_rk4_sens(0 if prec == "f32" else 1, M, 0.1, 1.4844, 9.81, p(tx), p(tu), p(tf), p(xn), p(AB), None)
+    assert rc == 0
+    torch.cuda.synchronize()
+    cfg = make_cfg()
+    ref_x = np.zeros((M, 10)); ref_AB = np.zeros((M, 10, 14))
+    xi, ui, fi = (t.cpu().numpy().astype(np.float64) for t in (tx, tu, tf))
+    for m in range(M):
+        a, Sx, Su = c_oracle.rk4_sens(cfg, xi[m], ui[m], fi[m])
+        ref_x[m], ref_AB[m, :, :10], ref_AB[m, :, 10:] = a, Sx, Su
+    tol = 1e-6 if prec == "f32" else 1e-12
+    assert rel_err(xn.cpu().numpy(), ref_x) < tol
+    assert rel_err(AB.cpu().numpy(), ref_AB) < tol
+    if prec == "f64":  # SURVEY.md B.5 known answer
+        assert abs(xn[0, 3].item() - 0.646352242513726) < 1e-13
+
+
+@pytest.mark.parametrize("prec", ["f32", "f64"])
+def test_golden_problems(built_lib, prec):
+    """The committed dense-KKT solutions (tests/golden/rti_golden.npz), incl. up to 10 active bounds."""
+    g = golden("rti_golden.npz")
+    B = g["x0"].shape[0]
+    e = _engine(B, prec)
+    w = dict(x0=g["x0"], xr=g["xr"], ur=g["ur"])
+    u0, X, U, st, stats = _run_engine(e, w, g["fd"])
+    assert np.all(st == 0), st
+    assert rel_err(u0, g["u0"]) < TOL[prec]
+    assert rel_err(X, g["X"]) < TOL[prec] and rel_err(U, g["U"]) < TOL[prec]
+    assert stats[:4, 0].max() == 1  # nominal problems: one Riccati sweep, no IPM
+    assert stats[8:, 1].min() >= 1  # saturated problems went through the IPM
+
+
+@pytest.mark.parametrize("prec,scale", [("f32", 1.0), ("f64", 1.0), ("f32", 5.0), ("f64", 5.0), ("f32", 15.0), ("f64", 15.0)])
+def test_rti_step_vs_oracle(built_lib, c_oracle, prec, scale):
+    """(2) SQP-RTI linearisation + Riccati/IPM QP, config-3 distribution; scale 5 / 15 are the stress
+    variants that activate the input bounds."""
+    B = 512
+    w = wl.independent_problems(B, seed=21, scale=scale)
+    fd = np.random.default_rng(4).normal(size=(B, 21, 3))
+    e = _engine(B, prec)
+    u0, X, U, st, stats = _run_engine(e, w, fd)
+    ou0, oX, oU, ost, r = _run_oracle(c_oracle, make_cfg(), w, fd)
+    ok = (ost == 0)
+    assert ok.mean() > 0.99
+    assert np.all(st[ok] == 0), np.bincount(st[ok])
+    tol = TOL[prec] if prec == "f32" else (1e-9 if scale < 10 else 1e-7)
+    assert rel_err(u0[ok], ou0[ok]) < tol
+    assert rel_err(X[ok], oX[ok]) < tol and rel_err(U[ok], oU[ok]) < tol
+    if scale == 1.0:
+        assert stats[:, 0].max() == 1 and r["n_active"].max() == 0
+    if scale == 15.0:
+        assert (r["n_active"] > 0).mean() > 0.5
+
+
+@pytest.mark.parametrize("prec", ["f32", "f64"])
+def test_tightened_bounds(built_lib, c_oracle, prec):
+    """Forced saturation: omega_max = 1.5 rad/s, c_max = 15 m/s^2 (SURVEY.md 8d stress variant)."""
+    B = 256
+    kw = dict(u_min=[-1.5, -1.5, -1.5, 0.0], u_max=[1.5, 1.5, 1.5, 15.0])
+    w = wl.independent_problems(B, seed=31, scale=5.0)
+    e = _engine(B, prec, np_=4, **kw)
+    u0, X, U, st, stats = _run_engine(e, w)
+    ou0, oX, oU, ost, r = _run_oracle(c_oracle, make_cfg(**kw), w)
+    ok = ost == 0
+    assert ok.mean() > 0.99 and np.all(st[ok] == 0)
+    assert (r["n_active"] > 0).mean() > 0.8
+    tol = TOL[prec] if prec == "f32" else 1e-8
+    assert rel_err(u0[ok], ou0[ok]) < tol and rel_err(U[ok], oU[ok]) < tol and rel_err(X[ok], oX[ok]) < tol
+    assert np.all(U[ok][:, :, :3] <= 1.5 + 1e-6) and np.all(U[ok][:, :, :3] >= -1.5 - 1e-6)
+
+
+@pytest.mark.parametrize("prec", ["f32", "f64"])
+def test_warm_started_closed_loop(built_lib, c_oracle, prec):
+    """Iterate persists between calls without shifting (nmpc_body_rate_ctl.py:86-112): five RTI steps
+    with moving x0 stay on the oracle's trajectory."""
+    B = 64
+    w = wl.independent_problems(B, seed=41)
+    rng = np.random.default_rng(5)
+    x0_seq = [w["x0"] + 0.02 * s * rng.normal(size=w["x0"].shape) for s in range(5)]
+    e = _engine(B, prec, np_=4)
+    u0, X, U, st, _ = _run_engine(e, w, steps=5, x0_seq=x0_seq)
+    ou0, oX, oU, ost, _ = _run_oracle(c_oracle, make_cfg(), w, steps=5, x0_seq=x0_seq)
+    assert np.all(st == 0) and np.all(ost == 0)
+    assert rel_err(u0, ou0) < TOL[prec] and rel_err(X, oX) < TOL[prec]
+
+
+@pytest.mark.parametrize("N", [40, 80])
+def test_longer_horizons(built_lib, c_oracle, N):
+    """Config 5 horizons (th_pred stays 0.1 s)."""
+    B = 64
+    w = wl.independent_problems(B, N=N, seed=51, scale=3.0)
+    e = _engine(B, "f32", N=N, np_=4)
+    u0, X, U, st, _ = _run_engine(e, w)
+    ou0, oX, oU, ost, _ = _run_oracle(c_oracle, make_cfg(N=N), w)
+    ok = ost == 0
+    assert np.all(st[ok] == 0)
+    assert rel_err(u0[ok], ou0[ok]) < 1e-4 and rel_err(X[ok], oX[ok]) < 1e-4
+
+
+def test_ragged_and_tiny_batches(built_lib, c_oracle):
+    """Batch sizes that do not fill a CTA / a half-warp pair, and more problems than resident slots."""
+    for B in (1, 3, 9, 6001):
+        w = wl.independent_problems(B, seed=B)
+        e = _engine(B, "f32", np_=4)
+        u0, X, U, st, _ = _run_engine(e, w)
+        ou0, oX, oU, ost, _ = _run_oracle(c_oracle, make_cfg(), w)
+        assert np.all(st == 0)
+        assert rel_err(u0, ou0) < 1e-4 and rel_err(X, oX) < 1e-4
+
+
+def test_full_size_properties(built_lib):
+    """BASELINE config 3 at full size (B = 4096): size-independent properties.
+    (i) a problem whose x0 sits on a dynamically consistent iterate = reference returns ~zero step;
+    (ii) batch-permutation equivariance; (iii) solving twice from the same state is idempotent in
+    the sense that the second RTI step is a much smaller correction."""
+    B = 4096
+    w = wl.independent_problems(B, seed=0)
+    e = _engine(B, "f32", np_=4)
+    u0, X, U, st, _ = _run_engine(e, w)
+    assert np.all(st == 0)
+    perm = np.random.default_rng(0).permutation(B)
+    wp = {k: v[perm] for k, v in w.items()}
+    e2 = _engine(B, "f32", np_=4)
+    u0p, Xp, _, _, _ = _run_engine(e2, wp)
+    assert np.array_equal(u0p, u0[perm]) and np.array_equal(Xp, X[perm])
+    u0b, Xb, _, stb, _ = _run_engine(e, w, steps=2)
+    assert np.abs(Xb - X).max() < 0.25 * np.abs(X - w["xr"]).max()
+    assert np.all(np.isfinite(u0)) and np.all(U[:, :, 3] >= 0) and np.all(np.abs(U[:, :, :3]) <= 6 + 1e-5)
+
+
+def test_infeasible_qp_reports_status(built_lib):
+    """Velocity box tighter than the initial speed -> infeasible QP -> non-zero status, and the
+    drop-in controller raises the reference's exception (nmpc_body_rate_ctl.py:109-110)."""
+    from ndp_nmpc_qd_b200.nmpc_ctl import NMPCBodyRateController
+
+    ctl = NMPCBodyRateController(v_min=[-0.5] * 3, v_max=[0.5] * 3, ipm_max_iter=30)
+    xr, ur = wl.reference_horizon([2.75], name="eight_high_dyn")
+    ctl.reset(xr[0], ur[0])
+    with pytest.raises(Exception, match="acados acados_ocp_solver returned status"):
+        ctl.update(xr[0, 0], xr[0], ur[0])
