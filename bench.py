@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""Benchmark of the NMPC hot path (BASELINE.json metric: batched NMPC SQP-RTI solves/sec, N=20,
+with downwash MLP; p50 step latency).
+
+Workload (config 3 of BASELINE.json with the downwash MLP switched on): B independent single-quad
+NDP-NMPC problems per GPU (default 4096), each with one neighbour inside the 1 m gate.  One "step" =
+one pass of the hot path over the batch:
+    forces = downwash MLP(fused features (other - ego)[0:6], gate)      [kernel 1]
+    yref/p upload (the 42 solver.set calls of controller.update)        [kernel 2]
+    one SQP-RTI step (RK4+sens -> Gauss-Newton -> Riccati/IPM -> step)  [kernel 3]
+Problems are independent, so N GPUs run N shards with no data-path collective (weak scaling).
+
+  python bench.py [--gpus N --steps K --warmup W]          # this repo's CUDA engine
+  python bench.py --impl reference ...                     # CPU arm: the fp64 oracle port (acados is
+                                                           # not installable here), all host threads
+Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_HORIZON = 20
+NX, NU = 10, 4
+METRIC = "batched NMPC SQP-RTI solves/sec (N=20, w/ downwash MLP)"
+UNIT = "solves/s"
+
+
+def algorithmic_flop_per_solve(N: int, n_fact: float) -> float:
+    """F_solve = N*13186 + n_it*(N*4275 + 2*N*1352 + 30*n_b), n_b = 4N + 3(N-1);
+    n_it = Riccati factorisations actually performed (1 when no bound is active)."""
+    n_b = 4 * N + 3 * (N - 1)
+    return N * 13186.0 + n_fact * (N * 4275.0 + 2 * N * 1352.0 + 30.0 * n_b)
+
+
+def compulsory_bytes_per_solve(N: int, elt: int = 4) -> float:
+    """x0 + xr + ur + f + iterate read + iterate write (+ status)."""
+    return elt * (10 + 10 * (N + 1) + 4 * N + 3 * (N + 1) + 2 * (14 * N + 10)) + 4
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d["hbm_gbs"], bf16_tflops=d["bf16_tflops"], bf16_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    sm_max_mhz=d.get("sm_max_mhz", 1965.0), source="measured")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_sustained=1400.0, sm_max_mhz=1965.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); smax.append(float(r[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
+        return dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(smax)), reasons=sorted(reasons), samples=len(sm))
+
+
+def make_workload(B, seed, n_sets):
+    """n_sets consecutive control steps of B problems (phases advance by 0.02 s, x0 re-perturbed)."""
+    from ndp_nmpc_qd_b200 import workloads as wl
+
+    sets = []
+    base = wl.independent_problems(B, N=N_HORIZON, seed=seed, with_neighbour=True)
+    rng = np.random.default_rng(seed + 1)
+    for s in range(n_sets):
+        w = {k: v.copy() for k, v in base.items()}
+        w["x0"] = base["x0"] + 0.02 * rng.normal(size=base["x0"].shape) * np.array([1, 1, 1, 2, 2, 2, 0.2, 0.2, 0.2, 0.2])
+        w["x0"][:, 6:10] /= np.linalg.norm(w["x0"][:, 6:10], axis=1, keepdims=True)
+        sets.append(w)
+    return sets
+
+
+def cpu_oracle_rate(sets, seconds=12.0, threads=0):
+    """Time the fp64 oracle port (HPIPM-like tolerance) + numpy MLP on a bounded sample."""
+    from oracle import mlp_numpy
+    from oracle.c_oracle import COracle, make_cfg
+    from ndp_nmpc_qd_b200.dnwash_nn_est.downwash_nn import DEFAULT_WEIGHTS
+
+    co = COracle()
+    cfg = make_cfg(tol=1e-8, max_iter=50)
+    wts = mlp_numpy.load_npz(DEFAULT_WEIGHTS)
+    w = sets[0]
+    B = w["x0"].shape[0]
+    n = min(B, 256)
+
+    def run(n):
+        X, U = w["xr"][:n].copy(), w["ur"][:n].copy()
+        t0 = time.perf_counter()
+        f = mlp_numpy.gated_pairs(wts, w["xr"][:n], w["other"][:n], w["xr"][:n, 0, 0:2], 1.0, np.float32).astype(np.float64)
+        r = co.rti_batch(cfg, w["x0"][:n], w["xr"][:n], w["ur"][:n], f, X, U, nthreads=threads)
+        return time.perf_counter() - t0, r
+
+    run(n)  # warm up OpenMP
+    dt, r = run(n)
+    n2 = int(min(B, max(n, n / dt * seconds)))
+    dt, r = run(n2)
+    return dict(value=n2 / dt, unit=UNIT, cores=int(r["threads"]), kind="port",
+                sample=f"{n2} of the {B} problems of one step, fp64 C restatement of acados SQP_RTI+HPIPM (tol 1e-8) + numpy MLP, {dt:.1f} s",
+                n_iter_mean=float(r["n_iter"].mean())), n2, dt
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    sets = make_workload(args.batch, 0, 1)
+    times = []
+    info = None
+    per_step = max(2.0, min(20.0, 150.0 / max(1, args.steps + args.warmup)))
+    for s in range(args.warmup + args.steps):
+        info, n, dt = cpu_oracle_rate(sets, seconds=per_step)
+        if s >= args.warmup:
+            times.append((n, dt))
+    tot_n, tot_t = sum(n for n, _ in times), sum(t for _, t in times)
+    value = tot_n / tot_t
+    info["value"] = value
+    out = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+               ms_per_step=1e3 * tot_t / len(times), higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
+               data="synthetic", impl="reference",
+               config=dict(workload=f"config 3: {args.batch} independent single-quad NDP-NMPC problems per GPU, N=20, one gated neighbour each (downwash MLP on)",
+                           note="acados/HPIPM/CasADi are not installable here (un-vendored, no network); this arm is the fp64 CPU oracle port on all host threads; each step is a bounded sample"),
+               cpu_baseline=info, e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(out), flush=True)
+
+
+def run_native(args, rank, local_rank, world):
+    import torch
+
+    from ndp_nmpc_qd_b200.dnwash_nn_est import DownwashNN
+    from ndp_nmpc_qd_b200.solver import Engine
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    B, K, W = args.batch, args.steps, args.warmup
+    n_sets = 8
+    sets = make_workload(B, seed=1000 * rank, n_sets=n_sets)
+    dt = torch.float32
+    eng = Engine(batch=B, N=N_HORIZON, np_=7, precision="f32", device=dev)
+    nn = DownwashNN(device=dev)
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=dt, device=dev)
+    d_sets = [dict(x0=t(w["x0"]), xr=t(w["xr"]), ur=t(w["ur"]), other=t(w["other"]), gate=t(w["xr"][:, 0, 0:2])) for w in sets]
+    f_buf = torch.empty((B, N_HORIZON + 1, 3), dtype=dt, device=dev)
+    u0_buf = torch.empty((B, NU), dtype=dt, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    stream = torch.cuda.current_stream()
+
+    def step(d):
+        nn.forward_pairs(d["xr"], d["other"], d["gate"], out=f_buf)
+        eng.set_reference(d["xr"], d["ur"], f_buf)
+        eng.solve(d["x0"], u0_buf)
+
+    eng.reset(d_sets[0]["xr"], d_sets[0]["ur"])
+    for s in range(W):
+        step(d_sets[s % n_sets])
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    # ---------- device-resident timing (value) ----------
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(K)]
+    l0 = eng.launch_count + nn.launch_count
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    torch.cuda.synchronize()
+    for s in range(K):
+        d = d_sets[(W + s) % n_sets]
+        flush.zero_()  # evict L2 between timed iterations
+        ev[s][0].record()
+        nn.forward_pairs(d["xr"], d["other"], d["gate"], out=f_buf)
+        eng.set_reference(d["xr"], d["ur"], f_buf)
+        ev[s][1].record()
+        eng.solve(d["x0"], u0_buf)
+        ev[s][2].record()
+    torch.cuda.synchronize()
+    launches = eng.launch_count + nn.launch_count - l0
+    step_ms = np.array([e[0].elapsed_time(e[2]) for e in ev])
+    solve_ms = np.array([e[1].elapsed_time(e[2]) for e in ev])
+    mlp_ms = np.array([e[0].elapsed_time(e[1]) for e in ev])
+    total_ms = float(step_ms.sum())
+    stats = eng.stats().cpu().numpy()
+    status = eng.status().cpu().numpy()
+    # ---------- end-to-end timing through the host-facing call (e2e) ----------
+    n_in = B * (NX + (N_HORIZON + 1) * NX + N_HORIZON * NU + (N_HORIZON + 1) * NX + 2)
+    pin_in = [torch.empty(n_in, dtype=dt).pin_memory() for _ in range(n_sets)]
+    sizes = [B * NX, B * (N_HORIZON + 1) * NX, B * N_HORIZON * NU, B * (N_HORIZON + 1) * NX, B * 2]
+    shapes = [(B, NX), (B, N_HORIZON + 1, NX), (B, N_HORIZON, NU), (B, N_HORIZON + 1, NX), (B, 2)]
+    for p, w in zip(pin_in, sets):
+        o = 0
+        for n, key in zip(sizes, ("x0", "xr", "ur", "other", None)):
+            src = w[key] if key else w["xr"][:, 0, 0:2]
+            p[o:o + n] = torch.as_tensor(np.ascontiguousarray(src), dtype=dt).reshape(-1)
+            o += n
+    d_in = torch.empty(n_in, dtype=dt, device=dev)
+    views, o = [], 0
+    for n, shp in zip(sizes, shapes):
+        views.append(d_in[o:o + n].view(*shp)); o += n
+    pin_out = torch.empty((B, NU), dtype=dt).pin_memory()
+    pin_st = torch.empty((B,), dtype=torch.int32).pin_memory()
+    d_st = torch.empty((B,), dtype=torch.int32, device=dev)
+
+    def e2e_step(s):
+        d_in.copy_(pin_in[s % n_sets], non_blocking=True)
+        nn.forward_pairs(views[1], views[3], views[4], out=f_buf)
+        eng.set_reference(views[1], views[2], f_buf)
+        eng.solve(views[0], u0_buf)
+        eng.status(d_st)
+        pin_out.copy_(u0_buf, non_blocking=True)
+        pin_st.copy_(d_st, non_blocking=True)
+        stream.synchronize()
+        return float(pin_out[0, 3])
+
+    for s in range(W):
+        e2e_step(s)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2e_lat = []
+    e0.record()
+    for s in range(K):
+        t0 = time.perf_counter()
+        e2e_step(W + s)
+        e2e_lat.append(time.perf_counter() - t0)
+    e1.record()
+    torch.cuda.synchronize()
+    e2e_ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if sampler else None
+    # ---------- reduce over ranks: max time ----------
+    red = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(red, op=dist.ReduceOp.MAX)
+        dist.barrier()
+    total_ms, e2e_ms = float(red[0]), float(red[1])
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    peaks = measured_peaks()
+    n_fact = float(stats[:, 0].mean())
+    flop = algorithmic_flop_per_solve(N_HORIZON, n_fact)
+    fp32_peak = 148 * 128 * 2 * peaks["sm_max_mhz"] * 1e6 / 1e12  # TFLOP/s, CUDA-core FMA pipe
+    solve_s = float(solve_ms.mean()) * 1e-3
+    ach_tf = flop * B / solve_s / 1e12
+    traffic = None
+    prof = os.path.join(ROOT, "profiles", "ncu_rti_summary.json")
+    if os.path.exists(prof):
+        try:
+            traffic = json.load(open(prof)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    out = dict(
+        metric=METRIC, value=world * B * K / (total_ms * 1e-3), unit=UNIT, n_gpus=world, steps=K, warmup=W,
+        ms_per_step=total_ms / K, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+        config=dict(workload=f"config 3: {B} independent single-quad NDP-NMPC problems per GPU, N=20, one gated neighbour each (downwash MLP on)",
+                    batch_per_gpu=B, horizon=N_HORIZON, l2="flushed between timed iterations (256 MiB memset outside the event pair)",
+                    inputs="8 pre-generated control steps cycled; iterate warm-started, no shift",
+                    parallelism=f"{world} independent shards, no collective"),
+        clocks=clocks,
+        e2e=dict(value=world * B * K / (e2e_ms * 1e-3), unit=UNIT, h2d_bytes_per_step=int(n_in * 4), d2h_bytes_per_step=int(B * NU * 4 + B * 4),
+                 ms_per_step=e2e_ms / K, p50_step_ms=float(np.median(e2e_lat) * 1e3)),
+        gpu_launches=int(launches),
+        roofline=dict(bound="fp32", kernel="rti_step_kernel<float>", achieved=ach_tf, peak=fp32_peak, unit="TFLOP/s", frac=ach_tf / fp32_peak,
+                      traffic=traffic, flop_per_solve=flop, n_fact_mean=n_fact, kernel_ms=float(solve_ms.mean()),
+                      peak_source=f"148 SM x 128 FMA x 2 x {peaks['sm_max_mhz']:.0f} MHz ({peaks['source']} sm_max_mhz)",
+                      hbm=dict(achieved=compulsory_bytes_per_solve(N_HORIZON) * B / solve_s / 1e9, peak=peaks["hbm_gbs"], unit="GB/s",
+                               frac=compulsory_bytes_per_solve(N_HORIZON) * B / solve_s / 1e9 / peaks["hbm_gbs"], bytes_per_solve=compulsory_bytes_per_solve(N_HORIZON))),
+        mlp=dict(kernel_ms=float(mlp_ms.mean()), rows=B * (N_HORIZON + 1), note="MLP + reference upload kernels (events 0-1)"),
+        p50_step_ms=float(np.median(step_ms)), p99_step_ms=float(np.quantile(step_ms, 0.99)),
+        solver=dict(status_nonzero=int((status != 0).sum()), ipm_iters_mean=float(stats[:, 1].mean()), active_bounds_mean=float(stats[:, 3].mean())),
+    )
+    if world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_oracle_rate(sets, seconds=12.0)[0]
+    if world == 1 and not args.no_latency:
+        out["latency_b1"] = batch1_latency(dev)
+    print(json.dumps(out), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def batch1_latency(dev):
+    """p50 of controller.update() through the drop-in Python surface at batch 1 (configs 1/2)."""
+    from ndp_nmpc_qd_b200 import workloads as wl
+    from ndp_nmpc_qd_b200.dnwash_nn_est import DownwashNN
+    from ndp_nmpc_qd_b200.ndp_nmpc_ctl import NDPNMPCBodyRateController
+
+    ctl = NDPNMPCBodyRateController(device=dev)
+    nn = DownwashNN(device=dev)
+    xr, ur = wl.reference_horizon([1.0])
+    other = xr[0].copy(); other[:, 2] += 0.8
+    ctl.reset(xr[0], ur[0])
+    lat_u, lat_n = [], []
+    for i in range(220):
+        xr, ur = wl.reference_horizon([1.0 + 0.02 * i])
+        t0 = time.perf_counter()
+        f = nn.update(other, xr[0])
+        t1 = time.perf_counter()
+        ctl.update(xr[0, 0], xr[0], ur[0], f)
+        t2 = time.perf_counter()
+        if i >= 20:
+            lat_n.append(t1 - t0); lat_u.append(t2 - t1)
+    return dict(update_p50_us=float(np.median(lat_u) * 1e6), update_p99_us=float(np.quantile(lat_u, 0.99) * 1e6),
+                downwash_update_p50_us=float(np.median(lat_n) * 1e6), note="NDPNMPCBodyRateController.update / DownwashNN.update, host numpy in -> out")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--batch", type=int, default=4096, help="problems per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-latency", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world == 1 and args.gpus > 1:
+        # launched without torchrun: re-exec under it
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
+               "--master-port", str(29500 + os.getpid() % 1000), os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    run_native(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

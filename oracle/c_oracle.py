@@ -45,9 +45,12 @@ def build(force: bool = False) -> str:
     return out
 
 
-def make_cfg(N=20, T=None, tol=1e-10, tol_mu=None, max_iter=50, u_min=None, u_max=None, v_min=None, v_max=None) -> OrcCfg:
+def make_cfg(N=20, T=None, tol=1e-13, tol_mu=None, max_iter=100, u_min=None, u_max=None, v_min=None, v_max=None) -> OrcCfg:
     """Constants of params/nmpc_params.py:9-35 and params/fhnp_params.py:9-19.
 
+    tol / max_iter default to a much tighter solve than HPIPM's own (res 1e-8, 50 iterations): the
+    parity target is the exact solution of the QP, which an IPM stopped at mu ~ 1e-10 misses by up
+    to ~3e-7 on weakly active bounds.  Use make_cfg(tol=1e-8, max_iter=50) to time HPIPM-like work.
     th_pred = T/N is 0.1 s in the reference; for N != 20 the horizon is T = 0.1 N
     (th_pred must stay a multiple of ts_nmpc).
     """

@@ -86,7 +86,7 @@ def rti():
         w = wl.independent_problems(4, seed=seed, scale=scale)
         fd = np.random.default_rng(seed).normal(size=(4, 21, 3)) * (scale > 1)
         for b in range(4):
-            d = on.rti_step(w["x0"][b], w["xr"][b], w["ur"][b], fd[b], w["xr"][b].copy(), w["ur"][b].copy(), p)
+            d = on.rti_step(w["x0"][b], w["xr"][b], w["ur"][b], fd[b], w["xr"][b].copy(), w["ur"][b].copy(), p, tol=1e-12)
             assert d["status"] == 0
             for k, v in (("x0", w["x0"][b]), ("xr", w["xr"][b]), ("ur", w["ur"][b]), ("fd", fd[b]), ("u0", d["u0"]), ("X", d["X"]),
                          ("U", d["U"]), ("n_active", d["n_active"]), ("scale", scale)):
