@@ -40,7 +40,7 @@ struct ndp_handle {
     void *X, *U, *yref, *par, *ws;
     int32_t *status, *stats;
     long long ws_stride;
-    int slots, grid;
+    int slots, grid, ppc;
     size_t smem;
     std::atomic<long long> launches;
     std::mutex mu;
@@ -139,6 +139,8 @@ RtiCfg<T> make_cfg(const ndp_config& g) {
     for (int i = 0; i < 3; i++) { c.vmin[i] = (T)g.v_min[i]; c.vmax[i] = (T)g.v_max[i]; }
     const bool f32 = sizeof(T) == 4;
     c.tol_mu = (T)(g.ipm_tol_mu > 0 ? g.ipm_tol_mu : (f32 ? 1e-4 : 1e-9));
+    c.tol_res = (T)(f32 ? 1e-6 : 1e-11);  // contraction of the linear residuals (prod of 1 - alpha)
+    c.t_min = (T)1e-12;
     c.mu0 = (T)10.0;
     c.t_floor = (T)0.1;
     c.big = (T)(f32 ? 1e9 : 1e12);
@@ -160,7 +162,7 @@ int launch_solve(ndp_handle* h, const void* x0, void* u0, cudaStream_t st) {
     a.ws = (T*)h->ws;
     a.ws_stride = h->ws_stride;
     a.B = h->cfg.batch;
-    rti_step_kernel<T><<<h->grid, RTI_THREADS, h->smem, st>>>(c, a);
+    rti_step_kernel<T><<<h->grid, h->ppc * GL, h->smem, st>>>(c, a);
     h->launches++;
     CU(cudaGetLastError());
     return 0;
@@ -250,20 +252,22 @@ int ndp_create(const ndp_config* cfg, ndp_handle** out) {
     const int N = cfg->N, B = cfg->batch;
     const SmemLayout L(N);
     const WsLayout WL(N);
-    h->smem = (size_t)L.total * RTI_PPC * h->elt;
+    h->ppc = RTI_PPC;
+    while (h->ppc > 1 && (size_t)L.total * h->ppc * h->elt > 200 * 1024) h->ppc >>= 1;  // long horizons / fp64: fewer problems per CTA
+    h->smem = (size_t)L.total * h->ppc * h->elt;
     if (h->smem > 227 * 1024) { delete h; return fail(NDP_E_CONFIG, "ndp_create: horizon too long for shared memory"); }
     cudaError_t e = (h->elt == 4)
                         ? cudaFuncSetAttribute(rti_step_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem)
                         : cudaFuncSetAttribute(rti_step_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem);
     if (e != cudaSuccess) { delete h; return cuda_fail(e, "cudaFuncSetAttribute(rti_step_kernel)"); }
     int occ = 0;
-    e = (h->elt == 4) ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rti_step_kernel<float>, RTI_THREADS, h->smem)
-                      : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rti_step_kernel<double>, RTI_THREADS, h->smem);
+    e = (h->elt == 4) ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rti_step_kernel<float>, h->ppc * GL, h->smem)
+                      : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rti_step_kernel<double>, h->ppc * GL, h->smem);
     if (e != cudaSuccess || occ < 1) { delete h; return e != cudaSuccess ? cuda_fail(e, "occupancy") : fail(NDP_E_CONFIG, "kernel does not fit"); }
-    const int need = (B + RTI_PPC - 1) / RTI_PPC;
+    const int need = (B + h->ppc - 1) / h->ppc;
     const int cap = n_sm * occ;  // persistent: at most one resident wave, grid-stride over problems
     h->grid = need < cap ? need : cap;
-    h->slots = h->grid * RTI_PPC;
+    h->slots = h->grid * h->ppc;
     h->ws_stride = WL.total;
     const size_t eb = (size_t)h->elt;
     h->X = h->U = h->yref = h->par = h->ws = nullptr;

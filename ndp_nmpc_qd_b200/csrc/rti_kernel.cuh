@@ -33,7 +33,7 @@ struct RtiCfg {
     int N, ipm_max_iter, polish_max;
     T h, inv_mass, g;
     T Q[10], R[4], umin[4], umax[4], vmin[3], vmax[3];
-    T tol_mu, mu0, t_floor, big;
+    T tol_mu, tol_res, mu0, t_floor, t_min, big;
 };
 
 template <typename T>
@@ -374,8 +374,13 @@ __device__ __forceinline__ bool backward_stage(const RtiCfg<T>& c, int k, int j,
         Pn[i] = H[i] + h0 * K0 + h1 * K1 + h2 * K2 + h3 * K3;
     }
     if (j < 10) {
+        // keep P exactly symmetric (lower triangle mirrored): without this the antisymmetric rounding
+        // part is amplified by the recursion (1e-3 relative error at N = 80 in fp32)
 #pragma unroll
-        for (int i = 0; i < 10; i++) sP[i * 12 + j] = Pn[i];
+        for (int i = 0; i < 10; i++) {
+            if (i >= j) sP[i * 12 + j] = Pn[i];
+            if (i > j) sP[j * 12 + i] = Pn[i];
+        }
         Vec4<T>::st(ws + WL.oKt + k * 40 + j * 4, K0, K1, K2, K3);
     } else if (j == 14) {
 #pragma unroll
@@ -458,7 +463,8 @@ __global__ void __launch_bounds__(RTI_THREADS, (sizeof(T) == 4) ? 4 : 2) rti_ste
     const int grp = threadIdx.x >> 4;
     const unsigned mask = 0xFFFFu << (threadIdx.x & 16);
     T* sm = reinterpret_cast<T*>(smem_raw) + (size_t)grp * L.total;
-    T* ws = a.ws + (size_t)(blockIdx.x * RTI_PPC + grp) * a.ws_stride;
+    const int ppc = blockDim.x >> 4;  // problems per CTA (8 unless the horizon needs more shared memory)
+    T* ws = a.ws + (size_t)(blockIdx.x * ppc + grp) * a.ws_stride;
     T* sX = sm + L.oX;
     T* sU = sm + L.oU;
     T* sDz = sm + L.oDz;
@@ -473,7 +479,7 @@ __global__ void __launch_bounds__(RTI_THREADS, (sizeof(T) == 4) ? 4 : 2) rti_ste
         if (lane == 10 + m) { lo = c.umin[m]; hi = c.umax[m]; }
     const bool isx = lane < 10, isu = (lane >= 10 && lane < 14), isv = (lane >= 3 && lane < 6);
 
-    for (int prob = blockIdx.x * RTI_PPC + grp; prob < a.B; prob += gridDim.x * RTI_PPC) {
+    for (int prob = blockIdx.x * ppc + grp; prob < a.B; prob += gridDim.x * ppc) {
         // ---- stage the problem record in shared memory ----
         {
             const T* gX = a.X + (size_t)prob * (N + 1) * NX;
@@ -555,8 +561,8 @@ __global__ void __launch_bounds__(RTI_THREADS, (sizeof(T) == 4) ? 4 : 2) rti_ste
                 mu = grp_sum<T>(mu_l, mask) * inv_m;
                 any_x_act = __any_sync(mask, xa_l);
                 const T tol = any_x_act ? c.tol_mu * T(0.01) : c.tol_mu;
-                if (it > 0 && res_lin == T(0) && mu < tol) { ipm_ok = true; break; }
-                if (it > 3 && res_lin == T(0) && mu > T(0.9) * mu_prev && mu < T(1e-2)) { ipm_ok = true; break; }
+                if (it > 0 && res_lin <= c.tol_res && mu < tol) { ipm_ok = true; break; }
+                if (it > 3 && res_lin <= c.tol_res && mu > T(0.9) * mu_prev && mu < T(1e-2)) { ipm_ok = true; break; }
                 if (!(mu == mu)) { status = 4; break; }  // NaN
                 if (it == c.ipm_max_iter) break;
                 mu_prev = mu;
@@ -647,10 +653,10 @@ __global__ void __launch_bounds__(RTI_THREADS, (sizeof(T) == 4) ? 4 : 2) rti_ste
                         const T dtl = (zn - lb) - tl, dtu = (ub - zn) - tu;
                         const T dll = (sigma_mu - cl) / tl - (ll / tl) * dtl - ll;
                         const T dlu = (sigma_mu - cu) / tu - (lu / tu) * dtu - lu;
-                        wI[IPM_TL * FS + e] = tl + alpha * dtl;
-                        wI[IPM_TU * FS + e] = tu + alpha * dtu;
-                        wI[IPM_LL * FS + e] = ll + alpha * dll;
-                        wI[IPM_LU * FS + e] = lu + alpha * dlu;
+                        wI[IPM_TL * FS + e] = fmax(tl + alpha * dtl, c.t_min);
+                        wI[IPM_TU * FS + e] = fmax(tu + alpha * dtu, c.t_min);
+                        wI[IPM_LL * FS + e] = fmax(ll + alpha * dll, c.t_min);
+                        wI[IPM_LU * FS + e] = fmax(lu + alpha * dlu, c.t_min);
                     }
                 if (lane < 14)
                     for (int k = 0; k <= N; k++) {
@@ -683,11 +689,15 @@ __global__ void __launch_bounds__(RTI_THREADS, (sizeof(T) == 4) ? 4 : 2) rti_ste
                                 bD[e] = (act != T(0)) ? c.big : T(0);
                                 bG[e] = (act != T(0)) ? -c.big * (act == T(1) ? lb : ub) : T(0);
                             } else {
+                                // velocity boxes cannot be pinned inside the input-elimination Riccati: an
+                                // active one keeps its interior-point barrier term, an inactive one is dropped
+                                // (and checked for feasibility below)
+                                const T act = wI[IPM_ACT * FS + e];
                                 const T tl = wI[IPM_TL * FS + e], tu = wI[IPM_TU * FS + e];
                                 const T ll = wI[IPM_LL * FS + e], lu = wI[IPM_LU * FS + e];
                                 const T gl = ll / tl, gu = lu / tu;
-                                bD[e] = gl + gu;
-                                bG[e] = (-gu * ub + lu) - (gl * lb + ll);
+                                bD[e] = (act != T(0)) ? gl + gu : T(0);
+                                bG[e] = (act != T(0)) ? (-gu * ub + lu) - (gl * lb + ll) : T(0);
                             }
                         }
                     __syncwarp(mask);
@@ -695,7 +705,13 @@ __global__ void __launch_bounds__(RTI_THREADS, (sizeof(T) == 4) ? 4 : 2) rti_ste
                     n_fact++;
                     n_pol++;
                     forward_sweep<T>(c, lane, mask, dx0, sm, L, ws, WL);
-                    bool changed = false;
+                    bool changed = false, xviol = false;
+                    if (isv)
+                        for (int k = 1; k < N; k++) {
+                            const int e = k * 16 + lane;
+                            const T it_v = iter_at(k);
+                            if (wI[IPM_ACT * FS + e] == T(0)) xviol |= !(sDz[e] >= lo - it_v && sDz[e] <= hi - it_v);
+                        }
                     if (isu)
                         for (int k = 0; k < N; k++) {
                             const int e = k * 16 + lane;
@@ -716,7 +732,9 @@ __global__ void __launch_bounds__(RTI_THREADS, (sizeof(T) == 4) ? 4 : 2) rti_ste
                             }
                         }
                     changed = __any_sync(mask, changed);
+                    xviol = __any_sync(mask, xviol);
                     __syncwarp(mask);
+                    if (xviol) break;  // a dropped velocity box is violated: keep the interior-point iterate
                     if (!changed) { pol_ok = true; break; }
                 }
                 if (pol_ok && isu) {
