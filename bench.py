@@ -5,9 +5,9 @@ with downwash MLP; p50 step latency).
 Workload (config 3 of BASELINE.json with the downwash MLP switched on): B independent single-quad
 NDP-NMPC problems per GPU (default 4096), each with one neighbour inside the 1 m gate.  One "step" =
 one pass of the hot path over the batch:
-    forces = downwash MLP(fused features (other - ego)[0:6], gate)      [kernel 1]
-    yref/p upload (the 42 solver.set calls of controller.update)        [kernel 2]
-    one SQP-RTI step (RK4+sens -> Gauss-Newton -> Riccati/IPM -> step)  [kernel 3]
+    forces = downwash MLP(fused features (other - ego)[0:6], gate)      [kernel 1, tcgen05]
+    controller.update(): yref/p upload (the 42 solver.set calls) fused with one SQP-RTI step
+    (RK4+sens -> Gauss-Newton -> Riccati/IPM -> full step)              [kernel 2]
 Problems are independent, so N GPUs run N shards with no data-path collective (weak scaling).
 
   python bench.py [--gpus N --steps K --warmup W]          # this repo's CUDA engine
@@ -192,8 +192,7 @@ def run_native(args, rank, local_rank, world):
 
     def step(d):
         nn.forward_pairs(d["xr"], d["other"], d["gate"], out=f_buf)
-        eng.set_reference(d["xr"], d["ur"], f_buf)
-        eng.solve(d["x0"], u0_buf)
+        eng.update(d["x0"], d["xr"], d["ur"], f_buf, u0_buf)
 
     eng.reset(d_sets[0]["xr"], d_sets[0]["ur"])
     for s in range(W):
@@ -211,9 +210,8 @@ def run_native(args, rank, local_rank, world):
         flush.zero_()  # evict L2 between timed iterations
         ev[s][0].record()
         nn.forward_pairs(d["xr"], d["other"], d["gate"], out=f_buf)
-        eng.set_reference(d["xr"], d["ur"], f_buf)
         ev[s][1].record()
-        eng.solve(d["x0"], u0_buf)
+        eng.update(d["x0"], d["xr"], d["ur"], f_buf, u0_buf)
         ev[s][2].record()
     torch.cuda.synchronize()
     launches = eng.launch_count + nn.launch_count - l0
@@ -245,8 +243,7 @@ def run_native(args, rank, local_rank, world):
     def e2e_step(s):
         d_in.copy_(pin_in[s % n_sets], non_blocking=True)
         nn.forward_pairs(views[1], views[3], views[4], out=f_buf)
-        eng.set_reference(views[1], views[2], f_buf)
-        eng.solve(views[0], u0_buf)
+        eng.update(views[0], views[1], views[2], f_buf, u0_buf)
         eng.status(d_st)
         pin_out.copy_(u0_buf, non_blocking=True)
         pin_st.copy_(d_st, non_blocking=True)
@@ -308,7 +305,7 @@ def run_native(args, rank, local_rank, world):
                       peak_source=f"148 SM x 128 FMA x 2 x {peaks['sm_max_mhz']:.0f} MHz ({peaks['source']} sm_max_mhz)",
                       hbm=dict(achieved=compulsory_bytes_per_solve(N_HORIZON) * B / solve_s / 1e9, peak=peaks["hbm_gbs"], unit="GB/s",
                                frac=compulsory_bytes_per_solve(N_HORIZON) * B / solve_s / 1e9 / peaks["hbm_gbs"], bytes_per_solve=compulsory_bytes_per_solve(N_HORIZON))),
-        mlp=dict(kernel_ms=float(mlp_ms.mean()), rows=B * (N_HORIZON + 1), note="MLP + reference upload kernels (events 0-1)"),
+        mlp=dict(kernel_ms=float(mlp_ms.mean()), rows=B * (N_HORIZON + 1), note="fused feature + gate + MLP kernel (events 0-1)"),
         p50_step_ms=float(np.median(step_ms)), p99_step_ms=float(np.quantile(step_ms, 0.99)),
         solver=dict(status_nonzero=int((status != 0).sum()), ipm_iters_mean=float(stats[:, 1].mean()), active_bounds_mean=float(stats[:, 3].mean())),
     )

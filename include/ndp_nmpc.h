@@ -106,6 +106,11 @@ int ndp_set_reference(ndp_handle* h, const void* xr_dev, const void* ur_dev, con
  * (x0 constraint, linearise, QP, full step).  x0_dev [B][10], u0_dev [B][4] (may be NULL). */
 int ndp_solve(ndp_handle* h, const void* x0_dev, void* u0_dev, void* stream);
 
+/* controller.update(x0, xr, ur[, f]) in ONE launch -- nmpc_body_rate_ctl.py:93-112: the reference
+ * upload of ndp_set_reference fused into the solve (yref / p are stored as if set).  f_dev may be NULL. */
+int ndp_update(ndp_handle* h, const void* x0_dev, const void* xr_dev, const void* ur_dev, const void* f_dev,
+               void* u0_dev, void* stream);
+
 /* solver.status -- nmpc_body_rate_ctl.py:109.  status_dev: int32 [B]. */
 int ndp_status(ndp_handle* h, int32_t* status_dev, void* stream);
 

@@ -18,7 +18,7 @@ FIELDS = {"x": FIELD_X, "u": FIELD_U, "yref": FIELD_YREF, "p": FIELD_P}
 # every symbol include/ndp_nmpc.h declares
 EXPORTS = [
     "ndp_default_config", "ndp_create", "ndp_destroy", "ndp_set", "ndp_get", "ndp_reset", "ndp_set_reference",
-    "ndp_solve", "ndp_status", "ndp_stats", "ndp_launch_count", "ndp_last_error", "ndp_rk4_sens",
+    "ndp_solve", "ndp_update", "ndp_status", "ndp_stats", "ndp_launch_count", "ndp_last_error", "ndp_rk4_sens",
     "ndp_mlp_create", "ndp_mlp_destroy", "ndp_mlp_forward_pairs", "ndp_mlp_forward_rows", "ndp_mlp_forward_swarm",
     "ndp_mlp_launch_count",
 ]
@@ -63,6 +63,7 @@ def load() -> C.CDLL:
     lib.ndp_reset.argtypes = [vp, vp, vp, vp]
     lib.ndp_set_reference.argtypes = [vp, vp, vp, vp, vp]
     lib.ndp_solve.argtypes = [vp, vp, vp, vp]
+    lib.ndp_update.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     lib.ndp_status.argtypes = [vp, vp, vp]
     lib.ndp_stats.argtypes = [vp, vp, vp]
     lib.ndp_launch_count.argtypes = [vp]
@@ -77,7 +78,7 @@ def load() -> C.CDLL:
     lib.ndp_mlp_forward_swarm.argtypes = [vp, i32, i64, i64, i64, i32, vp, vp, dbl, vp, i32, vp]
     lib.ndp_mlp_launch_count.argtypes = [vp]
     lib.ndp_mlp_launch_count.restype = i64
-    for name in ("ndp_create", "ndp_destroy", "ndp_set", "ndp_get", "ndp_reset", "ndp_set_reference", "ndp_solve",
+    for name in ("ndp_create", "ndp_destroy", "ndp_set", "ndp_get", "ndp_reset", "ndp_set_reference", "ndp_solve", "ndp_update",
                  "ndp_status", "ndp_stats", "ndp_rk4_sens", "ndp_mlp_create", "ndp_mlp_destroy",
                  "ndp_mlp_forward_pairs", "ndp_mlp_forward_rows", "ndp_mlp_forward_swarm"):
         getattr(lib, name).restype = C.c_int

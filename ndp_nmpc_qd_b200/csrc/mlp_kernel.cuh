@@ -40,6 +40,7 @@ struct MlpIo {
     double r2;
     const float* traj;
     const int2* pairs;  // (ego_global, other_global)
+    int prof;           // debug: record phase timestamps of CTA 0 (mlp_tc_kernel)
     void* out;          // mode 0: float [M][3]; mode 1: precision [P][n_nodes][3]; mode 2: float [n_pairs][n_nodes][3]
 };
 

@@ -34,21 +34,27 @@ constexpr float MLPT_LO_INV = 1.f / 2048.f;
 constexpr int MLPT_W2_ELEMS = MLP_H2 * MLP_H1;
 constexpr int MLPT_W3_ELEMS = MLP_H3 * MLP_H2;
 constexpr int MLPT_WIMG_ELEMS = 2 * MLPT_W2_ELEMS + 2 * MLPT_W3_ELEMS;
-// fp32 side parameters staged in smem: W1[128][6] b1[128] b2[64] b3[128] W4[3][128] b4[4]
-constexpr int MLPT_PW1 = 0, MLPT_PB1 = 768, MLPT_PB2 = 896, MLPT_PB3 = 960, MLPT_PW4 = 1088, MLPT_PB4 = 1472, MLPT_PN = 1476;
+// fp32 side parameters (layers 1 and 4, biases): passed by value as a kernel argument, staged once per
+// CTA in shared memory and read with broadcast 128-bit loads (indexed constant-bank loads measured 4x slower)
+struct alignas(16) MlpSmall {
+    float W1[MLP_H1 * MLP_IN], b1[MLP_H1], b2[MLP_H2], b3[MLP_H3], W4[MLP_OUT * MLP_H3], b4[4];
+};
 
-// shared memory map (bytes)
+// shared memory map (bytes): weights once per CTA, one activation region per 128-thread group
+// (h2 hi/lo alias the front of the h1 region: h1 is dead once the layer-2 MMAs have committed)
+constexpr int MLPT_GROUPS = 2;
+constexpr int MLPT_CTA_THREADS = MLPT_GROUPS * MLPT_THREADS;
 constexpr int MLPT_S_W2H = 0;
 constexpr int MLPT_S_W2L = MLPT_S_W2H + MLPT_W2_ELEMS * 2;
 constexpr int MLPT_S_W3H = MLPT_S_W2L + MLPT_W2_ELEMS * 2;
 constexpr int MLPT_S_W3L = MLPT_S_W3H + MLPT_W3_ELEMS * 2;
-constexpr int MLPT_S_A1H = MLPT_S_W3L + MLPT_W3_ELEMS * 2;       // h1 hi [128 x 128]
-constexpr int MLPT_S_A1L = MLPT_S_A1H + MLPT_ROWS * MLP_H1 * 2;
-constexpr int MLPT_S_A2H = MLPT_S_A1L + MLPT_ROWS * MLP_H1 * 2;  // h2 hi [128 x 64]
-constexpr int MLPT_S_A2L = MLPT_S_A2H + MLPT_ROWS * MLP_H2 * 2;
-constexpr int MLPT_S_PAR = MLPT_S_A2L + MLPT_ROWS * MLP_H2 * 2;
-constexpr int MLPT_S_BAR = MLPT_S_PAR + MLPT_PN * 4;             // mbarrier (8 B) + tmem base (4 B)
-constexpr int MLPT_SMEM = MLPT_S_BAR + 16;
+constexpr int MLPT_S_ACT = MLPT_S_W3L + MLPT_W3_ELEMS * 2;
+constexpr int MLPT_ACT_BYTES = 2 * MLPT_ROWS * MLP_H1 * 2;       // h1 hi + lo [128 x 128] fp16
+constexpr int MLPT_A1H = 0, MLPT_A1L = MLPT_ROWS * MLP_H1 * 2;   // offsets inside a group's region
+constexpr int MLPT_A2H = 0, MLPT_A2L = MLPT_ROWS * MLP_H2 * 2;
+constexpr int MLPT_S_PAR = MLPT_S_ACT + MLPT_GROUPS * MLPT_ACT_BYTES;  // fp32 side parameters (MlpSmall image)
+constexpr int MLPT_S_BAR = MLPT_S_PAR + (int)sizeof(MlpSmall);         // 3 mbarriers (24 B) + tmem base (4 B)
+constexpr int MLPT_SMEM = MLPT_S_BAR + 48;
 
 // element offset of (row r, col k) inside a [R x K] K-major no-swizzle operand
 __host__ __device__ __forceinline__ int umma_off(int r, int k, int R) { return ((k >> 3) * (R >> 3) + (r >> 3)) * 64 + (r & 7) * 8 + (k & 7); }
@@ -69,6 +75,15 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
+}
+// one elected lane of a converged warp (lets ptxas keep the MMA operands on the uniform datapath)
+__device__ __forceinline__ uint32_t elect_one_sync() {
+    uint32_t pred = 0, laneid = 0;
+    asm volatile(
+        "{\n\t.reg .b32 %%rx;\n\t.reg .pred %%px;\n\telect.sync %%rx|%%px, %2;\n\t@%%px mov.s32 %1, 1;\n\tmov.s32 %0, %%rx;\n\t}\n"
+        : "+r"(laneid), "+r"(pred)
+        : "r"(0xFFFFFFFFu));
+    return pred;
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -113,36 +128,49 @@ __device__ __forceinline__ void split_store8(const float (&h)[8], __half* dst_hi
     *reinterpret_cast<uint4*>(dst_lo) = *reinterpret_cast<uint4*>(lo);
 }
 
-__global__ void __launch_bounds__(MLPT_THREADS, 1) mlp_tc_kernel(const float* __restrict__ params, const __half* __restrict__ wimg, const MlpIo io) {
-    extern __shared__ __align__(1024) unsigned char smt[];
-    __half* sW2h = reinterpret_cast<__half*>(smt + MLPT_S_W2H);
-    __half* sA1h = reinterpret_cast<__half*>(smt + MLPT_S_A1H);
-    __half* sA1l = reinterpret_cast<__half*>(smt + MLPT_S_A1L);
-    __half* sA2h = reinterpret_cast<__half*>(smt + MLPT_S_A2H);
-    __half* sA2l = reinterpret_cast<__half*>(smt + MLPT_S_A2L);
-    float* sPar = reinterpret_cast<float*>(smt + MLPT_S_PAR);
-    uint64_t* sBar = reinterpret_cast<uint64_t*>(smt + MLPT_S_BAR);
-    uint32_t* sTmem = reinterpret_cast<uint32_t*>(smt + MLPT_S_BAR + 8);
-    const int t = threadIdx.x, warp = t >> 5;
+__device__ long long g_mlpt_prof[128];
+#define MLPT_STAMP(i) do { const int i_ = (i); if (io.prof && blockIdx.x == 0 && threadIdx.x == 0 && i_ < 128) g_mlpt_prof[i_] = clock64(); } while (0)
 
-    // ---- one-time setup: weights -> smem, mbarrier, TMEM ----
+__device__ __forceinline__ void group_sync(int grp) { asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(MLPT_THREADS) : "memory"); }
+
+// CTA = 2 groups of 128 threads; each group owns a 128-row tile (thread <-> row <-> TMEM lane), its own
+// activation tiles, mbarrier and 256 TMEM columns, so one group's CUDA-core phases overlap the other's
+// MMAs and memory latency.  Features of the next tile are prefetched while the current one computes.
+__global__ void __launch_bounds__(MLPT_CTA_THREADS, 1) mlp_tc_kernel(const __grid_constant__ MlpSmall sp, const __half* __restrict__ wimg, const MlpIo io) {
+    extern __shared__ __align__(1024) unsigned char smt[];
+    uint64_t* sBar = reinterpret_cast<uint64_t*>(smt + MLPT_S_BAR);
+    uint32_t* sTmem = reinterpret_cast<uint32_t*>(smt + MLPT_S_BAR + 32);
+    const int grp = threadIdx.x >> 7, t = threadIdx.x & 127, warp = t >> 5;
+    unsigned char* act = smt + MLPT_S_ACT + grp * MLPT_ACT_BYTES;
+    __half* sA1h = reinterpret_cast<__half*>(act + MLPT_A1H);
+    __half* sA1l = reinterpret_cast<__half*>(act + MLPT_A1L);
+    __half* sA2h = reinterpret_cast<__half*>(act + MLPT_A2H);
+    __half* sA2l = reinterpret_cast<__half*>(act + MLPT_A2L);
+    const MlpSmall& sq = *reinterpret_cast<const MlpSmall*>(smt + MLPT_S_PAR);
     {
-        const uint4* src = reinterpret_cast<const uint4*>(wimg);
-        uint4* dst = reinterpret_cast<uint4*>(sW2h);
-        for (int i = t; i < MLPT_WIMG_ELEMS * 2 / 16; i += MLPT_THREADS) dst[i] = src[i];
-        for (int i = t; i < MLP_H1 * MLP_IN; i += MLPT_THREADS) sPar[MLPT_PW1 + i] = params[MLP_OW1 + i];
-        for (int i = t; i < MLP_H1; i += MLPT_THREADS) sPar[MLPT_PB1 + i] = params[MLP_OB1 + i];
-        for (int i = t; i < MLP_H2; i += MLPT_THREADS) sPar[MLPT_PB2 + i] = params[MLP_OB2 + i];
-        for (int i = t; i < MLP_H3; i += MLPT_THREADS) sPar[MLPT_PB3 + i] = params[MLP_OB3 + i];
-        for (int i = t; i < MLP_OUT * MLP_H3; i += MLPT_THREADS) sPar[MLPT_PW4 + i] = params[MLP_OW4 + i];
-        if (t < 4) sPar[MLPT_PB4 + t] = params[MLP_OB4 + t];
+        float* dstp = reinterpret_cast<float*>(smt + MLPT_S_PAR);
+        const float* srcp = reinterpret_cast<const float*>(&sp);
+        for (int i = threadIdx.x; i < (int)(sizeof(MlpSmall) / 4); i += MLPT_CTA_THREADS) dstp[i] = srcp[i];
     }
-    const uint32_t bar = smem_u32(sBar);
-    if (t == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(1) : "memory");
+
+    // ---- one-time setup: mbarriers, weights -> smem by TMA bulk copy (lands under the first tile's
+    //      layer-1 compute; only the tensor core reads them), TMEM ----
+    const uint32_t bar = smem_u32(sBar + grp), wbar = smem_u32(sBar + 2);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(sBar)), "r"(1) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(sBar + 1)), "r"(1) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(wbar), "r"(1) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        constexpr uint32_t kBytes = MLPT_WIMG_ELEMS * 2, kChunk = 16384;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(wbar), "r"(kBytes) : "memory");
+#pragma unroll
+        for (uint32_t o = 0; o < kBytes; o += kChunk)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             smem_u32(smt + MLPT_S_W2H) + o),
+                         "l"(reinterpret_cast<const unsigned char*>(wimg) + o), "r"(kChunk), "r"(wbar)
+                         : "memory");
     }
-    if (warp == 0) {
+    if (threadIdx.x < 32) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(sTmem)), "r"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -150,8 +178,9 @@ __global__ void __launch_bounds__(MLPT_THREADS, 1) mlp_tc_kernel(const float* __
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem = *sTmem;
-    const uint32_t tD1m = tmem + 0, tD1c = tmem + 64, tD2m = tmem + 128, tD2c = tmem + 256;
+    const uint32_t tmem = *sTmem + grp * 256;
+    // layer-2 accumulators alias the front of the layer-3 ones (dead by then)
+    const uint32_t tD1m = tmem + 0, tD1c = tmem + 64, tD2m = tmem + 0, tD2c = tmem + 128;
     const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;  // this warp's TMEM lane quarter
     const uint32_t aW2h = smem_u32(smt + MLPT_S_W2H), aW2l = smem_u32(smt + MLPT_S_W2L);
     const uint32_t aW3h = smem_u32(smt + MLPT_S_W3H), aW3l = smem_u32(smt + MLPT_S_W3L);
@@ -159,31 +188,61 @@ __global__ void __launch_bounds__(MLPT_THREADS, 1) mlp_tc_kernel(const float* __
     constexpr uint32_t ID1 = umma_idesc(128, MLP_H2), ID2 = umma_idesc(128, MLP_H3);
     uint32_t phase = 0;
 
+    int stamp = 0;
+    MLPT_STAMP(stamp++);
     const long long n_tiles = (io.M + MLPT_ROWS - 1) / MLPT_ROWS;
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const long long tile0 = (long long)blockIdx.x * MLPT_GROUPS + grp, tstride = (long long)gridDim.x * MLPT_GROUPS;
+    float xn[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    bool on_n = false;
+    if (tile0 < n_tiles && tile0 * MLPT_ROWS + t < io.M) on_n = mlp_fetch_row(io, tile0 * MLPT_ROWS + t, xn);
+    for (long long tile = tile0; tile < n_tiles; tile += tstride) {
         const long long row = tile * MLPT_ROWS + t;
-        float x[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        bool on = false;
-        if (row < io.M) on = mlp_fetch_row(io, row, x);
+        float x[6];
+#pragma unroll
+        for (int i = 0; i < 6; i++) x[i] = xn[i];
+        const bool on = on_n;
+        {   // prefetch the next tile's features; the loads complete under this tile's compute
+            const long long nrow = row + tstride * MLPT_ROWS;
+#pragma unroll
+            for (int i = 0; i < 6; i++) xn[i] = 0.f;
+            on_n = false;
+            if (tile + tstride < n_tiles && nrow < io.M) on_n = mlp_fetch_row(io, nrow, xn);
+        }
+        MLPT_STAMP(stamp++);
         // ---- layer 1 (CUDA cores, fp32) -> h1 hi/lo operand tiles ----
 #pragma unroll 2
         for (int kb = 0; kb < MLP_H1 / 8; kb++) {
-            float h[8];
+            float w[48], bb[8], h[8];
+            const float4* wp = reinterpret_cast<const float4*>(sq.W1 + kb * 48);
+            const float4* bp = reinterpret_cast<const float4*>(sq.b1 + kb * 8);
+#pragma unroll
+            for (int i = 0; i < 12; i++) {
+                const float4 v = wp[i];
+                w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+            }
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+                const float4 v = bp[i];
+                bb[4 * i] = v.x; bb[4 * i + 1] = v.y; bb[4 * i + 2] = v.z; bb[4 * i + 3] = v.w;
+            }
 #pragma unroll
             for (int i = 0; i < 8; i++) {
-                const int n = kb * 8 + i;
-                float acc = sPar[MLPT_PB1 + n];
+                float acc = bb[i];
 #pragma unroll
-                for (int q = 0; q < 6; q++) acc = fmaf(sPar[MLPT_PW1 + n * 6 + q], x[q], acc);
+                for (int q = 0; q < 6; q++) acc = fmaf(w[i * 6 + q], x[q], acc);
                 h[i] = fmaxf(acc, 0.f);
             }
             const int off = umma_off(t, kb * 8, MLPT_ROWS);
             split_store8(h, sA1h + off, sA1l + off);
         }
+        MLPT_STAMP(stamp++);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncthreads();
+        group_sync(grp);
+        MLPT_STAMP(stamp++);
         // ---- layer 2: D1[128 x 64] = h1[128 x 128] . W2^T  (tcgen05, K = 128 -> 8 k-steps x 3 MMAs) ----
-        if (t == 0) {
+        if (warp == 0) {
+          if (elect_one_sync()) {
+            mbar_wait(wbar, 0);  // weights have landed (returns immediately after the first tile)
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
             for (int ks = 0; ks < MLP_H1 / 16; ks++) {
@@ -196,12 +255,16 @@ __global__ void __launch_bounds__(MLPT_THREADS, 1) mlp_tc_kernel(const float* __
                 umma_f16(tD1c, dAl, dBh, ID1, 1);
             }
             umma_commit(bar);
+          }
+          __syncwarp();
         }
+        MLPT_STAMP(stamp++);
         mbar_wait(bar, phase);
         phase ^= 1;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        // ---- epilogue 1: h2 = relu(D1 + b2) -> hi/lo operand tiles ----
-#pragma unroll
+        MLPT_STAMP(stamp++);
+        // ---- epilogue 1: h2 = relu(D1 + b2) -> hi/lo operand tiles (over the dead h1 tiles) ----
+#pragma unroll 1
         for (int c0 = 0; c0 < MLP_H2; c0 += 32) {
             float m[32], cr[32];
             tmem_ld32(tD1m + lane_sel + c0, m);
@@ -212,17 +275,20 @@ __global__ void __launch_bounds__(MLPT_THREADS, 1) mlp_tc_kernel(const float* __
 #pragma unroll
                 for (int i = 0; i < 8; i++) {
                     const int n = c0 + kb * 8 + i;
-                    h[i] = fmaxf(m[kb * 8 + i] + cr[kb * 8 + i] * MLPT_LO_INV + sPar[MLPT_PB2 + n], 0.f);
+                    h[i] = fmaxf(m[kb * 8 + i] + cr[kb * 8 + i] * MLPT_LO_INV + sq.b2[n], 0.f);
                 }
                 const int off = umma_off(t, c0 + kb * 8, MLPT_ROWS);
                 split_store8(h, sA2h + off, sA2l + off);
             }
         }
+        MLPT_STAMP(stamp++);
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncthreads();
+        group_sync(grp);
+        MLPT_STAMP(stamp++);
         // ---- layer 3: D2[128 x 128] = h2[128 x 64] . W3^T  (K = 64 -> 4 k-steps x 3 MMAs) ----
-        if (t == 0) {
+        if (warp == 0) {
+          if (elect_one_sync()) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
             for (int ks = 0; ks < MLP_H2 / 16; ks++) {
@@ -235,31 +301,46 @@ __global__ void __launch_bounds__(MLPT_THREADS, 1) mlp_tc_kernel(const float* __
                 umma_f16(tD2c, dAl, dBh, ID2, 1);
             }
             umma_commit(bar);
+          }
+          __syncwarp();
         }
+        MLPT_STAMP(stamp++);
         mbar_wait(bar, phase);
         phase ^= 1;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        MLPT_STAMP(stamp++);
         // ---- epilogue 2: h3 = relu(D2 + b3); layer 4 (CUDA cores, fp32): out = W4 h3 + b4 ----
-        float o0 = sPar[MLPT_PB4 + 0], o1 = sPar[MLPT_PB4 + 1], o2 = sPar[MLPT_PB4 + 2];
-#pragma unroll
+        float o0 = sq.b4[0], o1 = sq.b4[1], o2 = sq.b4[2];
+#pragma unroll 1
         for (int c0 = 0; c0 < MLP_H3; c0 += 32) {
             float m[32], cr[32];
             tmem_ld32(tD2m + lane_sel + c0, m);
             tmem_ld32(tD2c + lane_sel + c0, cr);
 #pragma unroll
-            for (int i = 0; i < 32; i++) {
-                const int n = c0 + i;
-                const float h = fmaxf(m[i] + cr[i] * MLPT_LO_INV + sPar[MLPT_PB3 + n], 0.f);
-                o0 = fmaf(sPar[MLPT_PW4 + n], h, o0);
-                o1 = fmaf(sPar[MLPT_PW4 + MLP_H3 + n], h, o1);
-                o2 = fmaf(sPar[MLPT_PW4 + 2 * MLP_H3 + n], h, o2);
+            for (int i4 = 0; i4 < 8; i4++) {
+                const float4 b = *reinterpret_cast<const float4*>(sq.b3 + c0 + 4 * i4);
+                const float4 w0 = *reinterpret_cast<const float4*>(sq.W4 + c0 + 4 * i4);
+                const float4 w1 = *reinterpret_cast<const float4*>(sq.W4 + MLP_H3 + c0 + 4 * i4);
+                const float4 w2 = *reinterpret_cast<const float4*>(sq.W4 + 2 * MLP_H3 + c0 + 4 * i4);
+                const float h0 = fmaxf(m[4 * i4 + 0] + cr[4 * i4 + 0] * MLPT_LO_INV + b.x, 0.f);
+                const float h1 = fmaxf(m[4 * i4 + 1] + cr[4 * i4 + 1] * MLPT_LO_INV + b.y, 0.f);
+                const float h2 = fmaxf(m[4 * i4 + 2] + cr[4 * i4 + 2] * MLPT_LO_INV + b.z, 0.f);
+                const float h3 = fmaxf(m[4 * i4 + 3] + cr[4 * i4 + 3] * MLPT_LO_INV + b.w, 0.f);
+                o0 = fmaf(w0.x, h0, o0); o1 = fmaf(w1.x, h0, o1); o2 = fmaf(w2.x, h0, o2);
+                o0 = fmaf(w0.y, h1, o0); o1 = fmaf(w1.y, h1, o1); o2 = fmaf(w2.y, h1, o2);
+                o0 = fmaf(w0.z, h2, o0); o1 = fmaf(w1.z, h2, o1); o2 = fmaf(w2.z, h2, o2);
+                o0 = fmaf(w0.w, h3, o0); o1 = fmaf(w1.w, h3, o1); o2 = fmaf(w2.w, h3, o2);
             }
         }
+        MLPT_STAMP(stamp++);
         if (row < io.M) mlp_store_row(io, row, on, o0, o1, o2);
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();
+        group_sync(grp);
+        MLPT_STAMP(stamp++);
     }
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*sTmem), "r"(512) : "memory");
 }
 
 // host: build the fp16 hi/lo operand images of W2, W3 in UMMA layout and upload them
@@ -283,10 +364,20 @@ inline int mlp_tc_prepare(const float* host_params, void** out) {
     return (int)e;
 }
 
-inline int mlp_tc_launch(const float* params, const void* wimg, const MlpIo& io, int n_sm, cudaStream_t st) {
+inline void mlp_tc_small(const float* host_params, MlpSmall* sp) {
+    for (int i = 0; i < MLP_H1 * MLP_IN; i++) sp->W1[i] = host_params[MLP_OW1 + i];
+    for (int i = 0; i < MLP_H1; i++) sp->b1[i] = host_params[MLP_OB1 + i];
+    for (int i = 0; i < MLP_H2; i++) sp->b2[i] = host_params[MLP_OB2 + i];
+    for (int i = 0; i < MLP_H3; i++) sp->b3[i] = host_params[MLP_OB3 + i];
+    for (int i = 0; i < MLP_OUT * MLP_H3; i++) sp->W4[i] = host_params[MLP_OW4 + i];
+    for (int i = 0; i < 4; i++) sp->b4[i] = i < MLP_OUT ? host_params[MLP_OB4 + i] : 0.f;
+}
+
+inline int mlp_tc_launch(const MlpSmall& sp, const void* wimg, const MlpIo& io, int n_sm, cudaStream_t st) {
     const long long tiles = (io.M + MLPT_ROWS - 1) / MLPT_ROWS;
-    const int grd = (int)(tiles < n_sm ? tiles : n_sm);
-    mlp_tc_kernel<<<grd, MLPT_THREADS, MLPT_SMEM, st>>>(params, reinterpret_cast<const __half*>(wimg), io);
+    const long long ctas = (tiles + MLPT_GROUPS - 1) / MLPT_GROUPS;
+    const int grd = (int)(ctas < n_sm ? ctas : n_sm);
+    mlp_tc_kernel<<<grd, MLPT_CTA_THREADS, MLPT_SMEM, st>>>(sp, reinterpret_cast<const __half*>(wimg), io);
     return (int)cudaGetLastError();
 }
 

@@ -148,9 +148,15 @@ RtiCfg<T> make_cfg(const ndp_config& g) {
 }
 
 template <typename T>
-int launch_solve(ndp_handle* h, const void* x0, void* u0, cudaStream_t st) {
+int launch_solve(ndp_handle* h, const void* x0, void* u0, cudaStream_t st, const void* xr = nullptr, const void* ur = nullptr,
+                 const void* f = nullptr) {
     RtiCfg<T> c = make_cfg<T>(h->cfg);
     RtiArgs<T> a;
+    a.xr = (const T*)xr;
+    a.ur = (const T*)ur;
+    a.f = (const T*)f;
+    a.yref_w = (T*)h->yref;
+    a.par_w = (T*)h->par;
     a.x0 = (const T*)x0;
     a.yref = (const T*)h->yref;
     a.par = (const T*)h->par;
@@ -252,7 +258,7 @@ int ndp_create(const ndp_config* cfg, ndp_handle** out) {
     const int N = cfg->N, B = cfg->batch;
     const SmemLayout L(N);
     const WsLayout WL(N);
-    h->ppc = RTI_PPC;
+    h->ppc = 4;  // 64-thread CTAs: 4096 problems -> 1024 CTAs = 6.9 per SM (8-problem CTAs leave a 15 % imbalance)
     while (h->ppc > 1 && (size_t)L.total * h->ppc * h->elt > 200 * 1024) h->ppc >>= 1;  // long horizons / fp64: fewer problems per CTA
     h->smem = (size_t)L.total * h->ppc * h->elt;
     if (h->smem > 227 * 1024) { delete h; return fail(NDP_E_CONFIG, "ndp_create: horizon too long for shared memory"); }
@@ -338,6 +344,13 @@ int ndp_solve(ndp_handle* h, const void* x0, void* u0, void* stream) {
     return h->elt == 4 ? launch_solve<float>(h, x0, u0, (cudaStream_t)stream) : launch_solve<double>(h, x0, u0, (cudaStream_t)stream);
 }
 
+int ndp_update(ndp_handle* h, const void* x0, const void* xr, const void* ur, const void* f, void* u0, void* stream) {
+    if (!h || !x0 || !xr || !ur) return fail(NDP_E_ARG, "ndp_update: null argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    return h->elt == 4 ? launch_solve<float>(h, x0, u0, (cudaStream_t)stream, xr, ur, f)
+                       : launch_solve<double>(h, x0, u0, (cudaStream_t)stream, xr, ur, f);
+}
+
 int ndp_status(ndp_handle* h, int32_t* status_dev, void* stream) {
     if (!h || !status_dev) return fail(NDP_E_ARG, "ndp_status: null argument");
     std::lock_guard<std::mutex> lk(h->mu);
@@ -379,6 +392,7 @@ int ndp_rk4_sens(int precision, int64_t M, double hh, double mass, double gravit
 struct ndp_mlp {
     float* params;     // packed fp32 parameters (mlp_kernel.cuh layout)
     void* tc_weights;  // tensor-core operand images (mlp_tc_kernel.cuh)
+    ndp::MlpSmall small;  // fp32 side parameters passed by value to the tensor-core kernel
     int n_sm;
     // swarm scratch (grown on demand)
     int* counts; int* offsets; int2* pairs; float* fpair;
@@ -393,7 +407,7 @@ static int mlp_run(ndp_mlp* m, MlpIo io, int path, cudaStream_t st) {
     if (io.M <= 0) return 0;
     if (path == 0) path = (io.M >= MLPT_MIN_ROWS) ? 2 : 1;
     if (path == 2) {
-        int rc = mlp_tc_launch(m->params, m->tc_weights, io, m->n_sm, st);
+        int rc = mlp_tc_launch(m->small, m->tc_weights, io, m->n_sm, st);
         if (rc) return cuda_fail((cudaError_t)rc, "mlp_tc_kernel launch");
     } else if (path == 1) {
         const long long tiles = (io.M + MLPF_ROWS - 1) / MLPF_ROWS;
@@ -434,6 +448,7 @@ int ndp_mlp_create(const float* W1, const float* b1, const float* W2, const floa
     cudaError_t e = cudaMalloc(&m->params, sizeof(float) * MLP_NPARAM);
     if (e == cudaSuccess) e = cudaMemcpy(m->params, host, sizeof(float) * MLP_NPARAM, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = (cudaError_t)mlp_tc_prepare(host, &m->tc_weights);
+    mlp_tc_small(host, &m->small);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_fp32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MLPF_SMEM);
     delete[] host;
     if (e != cudaSuccess) { ndp_mlp_destroy(m); return cuda_fail(e, "ndp_mlp_create"); }
@@ -449,10 +464,17 @@ int ndp_mlp_destroy(ndp_mlp* m) {
     return 0;
 }
 
+// debug helper (not part of the public header): phase timestamps of the last profiled tensor-core launch
+int ndp_debug_mlp_prof(long long* host128) {
+    return (int)cudaMemcpyFromSymbol(host128, ndp::g_mlpt_prof, sizeof(long long) * 128);
+}
+
 int ndp_mlp_forward_rows(ndp_mlp* m, int64_t M, const float* in, float* out, int path, void* stream) {
     if (!m || !in || !out || M < 0) return fail(NDP_E_ARG, "ndp_mlp_forward_rows: bad argument");
     std::lock_guard<std::mutex> lk(m->mu);
     MlpIo io{};
+    io.prof = (path >= 100);
+    if (path >= 100) path -= 100;
     io.mode = 0; io.M = M; io.in = in; io.out = out; io.n_nodes = 1;
     return mlp_run(m, io, path, (cudaStream_t)stream);
 }

@@ -46,6 +46,13 @@ struct RtiArgs {
     T* u0;          // [B][4] or null
     int32_t* status;  // [B]
     int32_t* stats;   // [B][4]
+    // optional fused controller.update(): when xr != null the kernel builds yref / p from
+    // (xr[B][N+1][10], ur[B][N][4], f[B][N+1][3] or null) itself and stores them in yref_w / par_w
+    const T* xr;
+    const T* ur;
+    const T* f;
+    T* yref_w;
+    T* par_w;
     T* ws;            // [slots][ws_stride]
     long long ws_stride;
     int B;
@@ -109,9 +116,13 @@ template <> struct Vec4<double> {
     }
 };
 
-template <typename T> __device__ __forceinline__ T tsqrt(T x);
-template <> __device__ __forceinline__ float tsqrt<float>(float x) { return sqrtf(x); }
-template <> __device__ __forceinline__ double tsqrt<double>(double x) { return sqrt(x); }
+// reciprocal square root: MUFU.RSQ + one Newton step (fp32, ~1 ulp) / IEEE (fp64)
+template <typename T> __device__ __forceinline__ T trsqrt(T x);
+template <> __device__ __forceinline__ float trsqrt<float>(float x) {
+    const float y = rsqrtf(x);
+    return y * (1.5f - 0.5f * x * y * y);
+}
+template <> __device__ __forceinline__ double trsqrt<double>(double x) { return 1.0 / sqrt(x); }
 
 template <typename T>
 __device__ __forceinline__ T grp_sum(T v, unsigned mask) {
@@ -344,16 +355,16 @@ __device__ __forceinline__ bool backward_stage(const RtiCfg<T>& c, int k, int j,
     const T g11 = __shfl_sync(mask, H[11], 11, GL), g21 = __shfl_sync(mask, H[12], 11, GL);
     const T g31 = __shfl_sync(mask, H[13], 11, GL), g22 = __shfl_sync(mask, H[12], 12, GL);
     const T g32 = __shfl_sync(mask, H[13], 12, GL), g33 = __shfl_sync(mask, H[13], 13, GL);
-    const T l00 = tsqrt(g00), i00 = T(1) / l00;
+    const T i00 = trsqrt(g00);
     const T l10 = g10 * i00, l20 = g20 * i00, l30 = g30 * i00;
     const T e1 = g11 - l10 * l10;
-    const T l11 = tsqrt(e1), i11 = T(1) / l11;
+    const T i11 = trsqrt(e1);
     const T l21 = (g21 - l20 * l10) * i11, l31 = (g31 - l30 * l10) * i11;
     const T e2 = g22 - l20 * l20 - l21 * l21;
-    const T l22 = tsqrt(e2), i22 = T(1) / l22;
+    const T i22 = trsqrt(e2);
     const T l32 = (g32 - l30 * l20 - l31 * l21) * i22;
     const T e3 = g33 - l30 * l30 - l31 * l31 - l32 * l32;
-    const T l33 = tsqrt(e3), i33 = T(1) / l33;
+    const T i33 = trsqrt(e3);
     const bool ok = (g00 > T(0)) && (e1 > T(0)) && (e2 > T(0)) && (e3 > T(0));
     const T y0 = H[10] * i00;
     const T y1 = (H[11] - l10 * y0) * i11;
@@ -488,8 +499,30 @@ __global__ void __launch_bounds__(RTI_THREADS, (sizeof(T) == 4) ? 4 : 2) rti_ste
             const T* gP = a.par + (size_t)prob * (N + 1) * NPS;
             for (int i = lane; i < (N + 1) * NX; i += GL) sX[i] = gX[i];
             for (int i = lane; i < N * NU; i += GL) sU[i] = gU[i];
-            for (int i = lane; i < (N + 1) * NYS; i += GL) sm[L.oY + i] = gY[i];
-            for (int i = lane; i < (N + 1) * NPS; i += GL) sm[L.oPar + i] = gP[i];
+            if (a.xr == nullptr) {
+                for (int i = lane; i < (N + 1) * NYS; i += GL) sm[L.oY + i] = gY[i];
+                for (int i = lane; i < (N + 1) * NPS; i += GL) sm[L.oPar + i] = gP[i];
+            } else {
+                // yref_k = [xr_k; ur_k], p_k = [xr_k[6:10]; f_k]   (nmpc_body_rate_ctl.py:95-104)
+                const T* gxr = a.xr + (size_t)prob * (N + 1) * NX;
+                const T* gur = a.ur + (size_t)prob * N * NU;
+                for (int i = lane; i < (N + 1) * NX; i += GL) {
+                    const T v = gxr[i];
+                    const int k = i / NX, cix = i - k * NX;
+                    sm[L.oY + k * NYS + cix] = v;
+                    if (cix >= 6) sm[L.oPar + k * NPS + cix - 6] = v;
+                }
+                for (int i = lane; i < (N + 1) * NU; i += GL) {
+                    const int k = i >> 2, m = i & 3;
+                    sm[L.oY + k * NYS + NX + m] = (k < N) ? gur[i] : T(0);
+                    sm[L.oPar + k * NPS + 4 + m] = (m < 3 && a.f) ? a.f[((size_t)prob * (N + 1) + k) * 3 + m] : T(0);
+                }
+                __syncwarp(mask);
+                T* wY = a.yref_w + (size_t)prob * (N + 1) * NYS;
+                T* wP = a.par_w + (size_t)prob * (N + 1) * NPS;
+                for (int i = lane; i < (N + 1) * NYS; i += GL) wY[i] = sm[L.oY + i];
+                for (int i = lane; i < (N + 1) * NPS; i += GL) wP[i] = sm[L.oPar + i];
+            }
         }
         const T dx0 = isx ? a.x0[(size_t)prob * NX + lane] - a.X[(size_t)prob * (N + 1) * NX + lane] : T(0);
         __syncwarp(mask);

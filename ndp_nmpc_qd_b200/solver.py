@@ -137,6 +137,20 @@ class Engine:
         _lib.check(self.lib.ndp_solve(self._h, _ptr(x0), _ptr(u0), _stream_ptr(stream)), "ndp_solve")
         return u0
 
+    def update(self, x0: torch.Tensor, xr: torch.Tensor, ur: torch.Tensor, f: Optional[torch.Tensor] = None,
+               u0: Optional[torch.Tensor] = None, stream=None) -> torch.Tensor:
+        """controller.update() in one launch: reference upload fused into the RTI solve."""
+        self._chk(x0, (self.batch, NX))
+        self._chk(xr, (self.batch, self.N + 1, NX))
+        self._chk(ur, (self.batch, self.N, NU))
+        if f is not None:
+            self._chk(f, (self.batch, self.N + 1, 3))
+        if u0 is None:
+            u0 = torch.empty((self.batch, NU), dtype=self.dtype, device=self.device)
+        self._chk(u0, (self.batch, NU))
+        _lib.check(self.lib.ndp_update(self._h, _ptr(x0), _ptr(xr), _ptr(ur), _ptr(f), _ptr(u0), _stream_ptr(stream)), "ndp_update")
+        return u0
+
     def status(self, out: Optional[torch.Tensor] = None, stream=None) -> torch.Tensor:
         if out is None:
             out = torch.empty((self.batch,), dtype=torch.int32, device=self.device)
