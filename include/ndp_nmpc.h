@@ -150,6 +150,12 @@ int ndp_mlp_forward_pairs(ndp_mlp* m, int precision, int64_t P, int32_t n_nodes,
                           const void* other_dev, const void* gate_xy_dev, double r_horiz, void* out_dev,
                           int accumulate, int path, void* stream);
 
+/* Same with an explicit row stride of `other`: other_ld = 10 (full state rows, as above) or 6
+ * ([P][n_nodes][6]: only the position+velocity columns, the slice downwash_nn.py:24 reads). */
+int ndp_mlp_forward_pairs_ex(ndp_mlp* m, int precision, int64_t P, int32_t n_nodes, const void* ego_dev,
+                             const void* other_dev, int32_t other_ld, const void* gate_xy_dev, double r_horiz,
+                             void* out_dev, int accumulate, int path, void* stream);
+
 /* Plain rows: in [M][6] fp32 -> out [M][3] fp32 (the nn.Sequential itself). */
 int ndp_mlp_forward_rows(ndp_mlp* m, int64_t M, const float* in_dev, float* out_dev, int path, void* stream);
 
@@ -162,6 +168,29 @@ int ndp_mlp_forward_swarm(ndp_mlp* m, int precision, int64_t n_all, int64_t ego_
                           void* out_dev, int path, void* stream);
 
 int64_t ndp_mlp_launch_count(const ndp_mlp* m);
+
+/* ---- host-buffer step pipeline ----
+ * One control step for the whole batch straight from HOST memory: what the ROS node does per timer
+ * tick -- DownwashNN.update(other, ego_ref) (ndp_nmpc_leader_node.py:60-76, incl. its H2D/D2H,
+ * downwash_nn.py:22-28) followed by controller.update(x0, xr, ur, f) (nmpc_node.py:202-209,
+ * ndp_nmpc_body_rate_ctl.py:91-112) -- as ONE asynchronous submission: H2D copy of the step record,
+ * MLP + RTI kernels, D2H copy of (u0, status).  `depth` slots of pinned host memory are owned by the
+ * pipeline; the caller fills a slot's input arrays in place, submits it and later waits for it.
+ * Uploads, kernels and downloads of different slots overlap (three streams); solves stay ordered
+ * (the iterate is warm-started from the previous solve, nmpc_body_rate_ctl.py:86-112).
+ * mlp == NULL: plain NMPC (np = 4), no neighbour arrays.  r_horiz: params/downwash_params.py:10. */
+typedef struct ndp_pipeline ndp_pipeline;
+int ndp_pipeline_create(ndp_handle* h, ndp_mlp* mlp, double r_horiz, int depth, ndp_pipeline** out);
+int ndp_pipeline_destroy(ndp_pipeline* p);
+/* Pinned HOST arrays of a slot, engine precision: x0 [B][10], xr [B][N+1][10], ur [B][N][4],
+ * other [B][N+1][6] (neighbour horizon, position+velocity columns), gate_xy [B][2] (ego odometry x,y) -> u0 [B][4], status int32 [B].
+ * Any output pointer may be NULL; other / gate_xy are NULL without an MLP. */
+int ndp_pipeline_buffers(ndp_pipeline* p, int slot, void** x0, void** xr, void** ur, void** other,
+                         void** gate_xy, void** u0, int32_t** status);
+int ndp_pipeline_submit(ndp_pipeline* p, int slot); /* asynchronous */
+int ndp_pipeline_wait(ndp_pipeline* p, int slot);   /* blocks until the slot's u0 / status are in host memory */
+int ndp_pipeline_bytes(const ndp_pipeline* p, int64_t* h2d_bytes_per_step, int64_t* d2h_bytes_per_step);
+void* ndp_pipeline_stream(ndp_pipeline* p);         /* the compute stream (cudaStream_t) */
 
 #ifdef __cplusplus
 }

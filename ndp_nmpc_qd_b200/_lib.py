@@ -20,7 +20,9 @@ EXPORTS = [
     "ndp_default_config", "ndp_create", "ndp_destroy", "ndp_set", "ndp_get", "ndp_reset", "ndp_set_reference",
     "ndp_solve", "ndp_update", "ndp_status", "ndp_stats", "ndp_launch_count", "ndp_last_error", "ndp_rk4_sens",
     "ndp_mlp_create", "ndp_mlp_destroy", "ndp_mlp_forward_pairs", "ndp_mlp_forward_rows", "ndp_mlp_forward_swarm",
-    "ndp_mlp_launch_count",
+    "ndp_mlp_launch_count", "ndp_mlp_forward_pairs_ex",
+    "ndp_pipeline_create", "ndp_pipeline_destroy", "ndp_pipeline_buffers", "ndp_pipeline_submit", "ndp_pipeline_wait",
+    "ndp_pipeline_bytes", "ndp_pipeline_stream",
 ]
 
 
@@ -77,10 +79,21 @@ def load() -> C.CDLL:
     lib.ndp_mlp_forward_rows.argtypes = [vp, i64, vp, vp, i32, vp]
     lib.ndp_mlp_forward_swarm.argtypes = [vp, i32, i64, i64, i64, i32, vp, vp, dbl, vp, i32, vp]
     lib.ndp_mlp_launch_count.argtypes = [vp]
+    lib.ndp_mlp_forward_pairs_ex.argtypes = [vp, i32, i64, i32, vp, vp, i32, vp, dbl, vp, i32, i32, vp]
+    lib.ndp_pipeline_create.argtypes = [vp, vp, dbl, i32, C.POINTER(vp)]
+    lib.ndp_pipeline_destroy.argtypes = [vp]
+    lib.ndp_pipeline_buffers.argtypes = [vp, i32] + [C.POINTER(vp)] * 7
+    lib.ndp_pipeline_submit.argtypes = [vp, i32]
+    lib.ndp_pipeline_wait.argtypes = [vp, i32]
+    lib.ndp_pipeline_bytes.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]
+    lib.ndp_pipeline_stream.argtypes = [vp]
+    lib.ndp_pipeline_stream.restype = vp
     lib.ndp_mlp_launch_count.restype = i64
     for name in ("ndp_create", "ndp_destroy", "ndp_set", "ndp_get", "ndp_reset", "ndp_set_reference", "ndp_solve", "ndp_update",
                  "ndp_status", "ndp_stats", "ndp_rk4_sens", "ndp_mlp_create", "ndp_mlp_destroy",
-                 "ndp_mlp_forward_pairs", "ndp_mlp_forward_rows", "ndp_mlp_forward_swarm"):
+                 "ndp_mlp_forward_pairs", "ndp_mlp_forward_rows", "ndp_mlp_forward_swarm", "ndp_mlp_forward_pairs_ex",
+                 "ndp_pipeline_create", "ndp_pipeline_destroy", "ndp_pipeline_buffers", "ndp_pipeline_submit", "ndp_pipeline_wait",
+                 "ndp_pipeline_bytes"):
         getattr(lib, name).restype = C.c_int
     _lib = lib
     return lib

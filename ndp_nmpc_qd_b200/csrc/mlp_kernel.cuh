@@ -32,6 +32,7 @@ struct MlpIo {
     int precision;  // element type of ego/other/out for mode 1, of out for mode 2 (0 f32, 1 f64)
     int n_nodes;
     int accumulate;
+    int other_ld;  // mode 1: row stride of `other` (10 = full state rows, 6 = position+velocity only)
     long long M;  // total rows
     const float* in;
     const void* ego;
@@ -55,22 +56,22 @@ __device__ __forceinline__ bool mlp_fetch_row(const MlpIo& io, long long row, fl
         bool on = true;
         if (io.precision == 1) {
             const double* e = (const double*)io.ego + row * 10;
-            const double* o = (const double*)io.other + row * 10;
+            const double* o = (const double*)io.other + row * io.other_ld;
 #pragma unroll
             for (int i = 0; i < 6; i++) x[i] = (float)(o[i] - e[i]);
             if (io.gate_xy) {
-                const double* o0 = (const double*)io.other + p * io.n_nodes * 10;
+                const double* o0 = (const double*)io.other + p * io.n_nodes * io.other_ld;
                 const double* g = (const double*)io.gate_xy + p * 2;
                 const double dx = o0[0] - g[0], dy = o0[1] - g[1];
                 on = dx * dx + dy * dy < io.r2;
             }
         } else {
             const float* e = (const float*)io.ego + row * 10;
-            const float* o = (const float*)io.other + row * 10;
+            const float* o = (const float*)io.other + row * io.other_ld;
 #pragma unroll
             for (int i = 0; i < 6; i++) x[i] = o[i] - e[i];
             if (io.gate_xy) {
-                const float* o0 = (const float*)io.other + p * io.n_nodes * 10;
+                const float* o0 = (const float*)io.other + p * io.n_nodes * io.other_ld;
                 const float* g = (const float*)io.gate_xy + p * 2;
                 const float dx = o0[0] - g[0], dy = o0[1] - g[1];
                 on = dx * dx + dy * dy < (float)io.r2;

@@ -479,13 +479,21 @@ int ndp_mlp_forward_rows(ndp_mlp* m, int64_t M, const float* in, float* out, int
     return mlp_run(m, io, path, (cudaStream_t)stream);
 }
 
+int ndp_mlp_forward_pairs_ex(ndp_mlp* m, int precision, int64_t P, int32_t n_nodes, const void* ego, const void* other, int32_t other_ld,
+                             const void* gate_xy, double r_horiz, void* out, int accumulate, int path, void* stream);
+
 int ndp_mlp_forward_pairs(ndp_mlp* m, int precision, int64_t P, int32_t n_nodes, const void* ego, const void* other, const void* gate_xy,
                           double r_horiz, void* out, int accumulate, int path, void* stream) {
-    if (!m || !ego || !other || !out || P < 0 || n_nodes < 1) return fail(NDP_E_ARG, "ndp_mlp_forward_pairs: bad argument");
+    return ndp_mlp_forward_pairs_ex(m, precision, P, n_nodes, ego, other, 10, gate_xy, r_horiz, out, accumulate, path, stream);
+}
+
+int ndp_mlp_forward_pairs_ex(ndp_mlp* m, int precision, int64_t P, int32_t n_nodes, const void* ego, const void* other, int32_t other_ld,
+                             const void* gate_xy, double r_horiz, void* out, int accumulate, int path, void* stream) {
+    if (!m || !ego || !other || !out || P < 0 || n_nodes < 1 || other_ld < 6) return fail(NDP_E_ARG, "ndp_mlp_forward_pairs: bad argument");
     if (precision != NDP_F32 && precision != NDP_F64) return fail(NDP_E_ARG, "ndp_mlp_forward_pairs: bad precision");
     std::lock_guard<std::mutex> lk(m->mu);
     MlpIo io{};
-    io.mode = 1; io.precision = precision; io.n_nodes = n_nodes; io.accumulate = accumulate;
+    io.mode = 1; io.precision = precision; io.n_nodes = n_nodes; io.accumulate = accumulate; io.other_ld = other_ld;
     io.M = (long long)P * n_nodes; io.ego = ego; io.other = other; io.gate_xy = gate_xy; io.r2 = r_horiz * r_horiz; io.out = out;
     return mlp_run(m, io, path, (cudaStream_t)stream);
 }
@@ -544,5 +552,144 @@ int ndp_mlp_forward_swarm(ndp_mlp* m, int precision, int64_t n_all, int64_t ego_
 }
 
 int64_t ndp_mlp_launch_count(const ndp_mlp* m) { return m ? (int64_t)m->launches.load() : 0; }
+
+}  // extern "C"
+
+// ======================= host-buffer step pipeline =======================
+// controller.update() (+ DownwashNN.update()) for the whole batch straight from pinned HOST memory:
+// one H2D copy of the step's record, the MLP and RTI kernels, one D2H copy of (u0, status).  Copies
+// and kernels of consecutive steps run on three streams (copy-in / compute / copy-out) ordered by
+// events, so step i+1's upload overlaps step i's kernels; the iterate dependency between
+// consecutive solves is kept by the single compute stream.
+struct ndp_pipeline {
+    ndp_handle* h;
+    ndp_mlp* mlp;
+    int depth;
+    double r_horiz;
+    size_t o_x0, o_xr, o_ur, o_other, o_gate, in_bytes;  // byte offsets inside a slot's input record
+    size_t o_status, out_bytes;                          // output record: [u0 | status]
+    unsigned char *h_in, *h_out, *d_in, *d_out, *d_f;
+    size_t f_bytes;
+    cudaStream_t s_in, s_cmp, s_out;
+    cudaEvent_t *e_in, *e_cmp, *e_out;
+};
+
+extern "C" {
+
+int ndp_pipeline_create(ndp_handle* h, ndp_mlp* mlp, double r_horiz, int depth, ndp_pipeline** out) {
+    if (!h || !out || depth < 1 || depth > 64) return fail(NDP_E_ARG, "ndp_pipeline_create: bad argument");
+    if (mlp && h->cfg.np != 7) return fail(NDP_E_CONFIG, "ndp_pipeline_create: downwash forces need np = 7");
+    ndp_pipeline* p = new ndp_pipeline();
+    std::memset(p, 0, sizeof(*p));
+    p->h = h; p->mlp = mlp; p->depth = depth; p->r_horiz = r_horiz;
+    const size_t eb = (size_t)h->elt, B = (size_t)h->cfg.batch, N = (size_t)h->cfg.N;
+    size_t o = 0;
+    p->o_x0 = o; o += B * NX * eb;
+    p->o_xr = o; o += B * (N + 1) * NX * eb;
+    p->o_ur = o; o += B * N * NU * eb;
+    p->o_other = o; if (mlp) o += B * (N + 1) * 6 * eb;  // neighbour horizon: the 6 columns DownwashNN reads
+    p->o_gate = o; if (mlp) o += B * 2 * eb;
+    p->in_bytes = (o + 255) & ~(size_t)255;
+    p->o_status = B * NU * eb;
+    p->out_bytes = (p->o_status + B * sizeof(int32_t) + 255) & ~(size_t)255;
+    p->f_bytes = (B * (N + 1) * 3 * eb + 255) & ~(size_t)255;
+    bool ok = cudaHostAlloc((void**)&p->h_in, p->in_bytes * depth, cudaHostAllocDefault) == cudaSuccess &&
+              cudaHostAlloc((void**)&p->h_out, p->out_bytes * depth, cudaHostAllocDefault) == cudaSuccess &&
+              cudaMalloc((void**)&p->d_in, p->in_bytes * depth) == cudaSuccess && cudaMalloc((void**)&p->d_out, p->out_bytes * depth) == cudaSuccess &&
+              cudaMalloc((void**)&p->d_f, p->f_bytes * depth) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&p->s_in, cudaStreamNonBlocking) == cudaSuccess &&
+         cudaStreamCreateWithFlags(&p->s_cmp, cudaStreamNonBlocking) == cudaSuccess &&
+         cudaStreamCreateWithFlags(&p->s_out, cudaStreamNonBlocking) == cudaSuccess;
+    p->e_in = new cudaEvent_t[depth](); p->e_cmp = new cudaEvent_t[depth](); p->e_out = new cudaEvent_t[depth]();
+    for (int s = 0; ok && s < depth; s++)
+        ok = cudaEventCreateWithFlags(&p->e_in[s], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&p->e_cmp[s], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&p->e_out[s], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) { ndp_pipeline_destroy(p); return fail(NDP_E_ALLOC, "ndp_pipeline_create: allocation failed"); }
+    std::memset(p->h_in, 0, p->in_bytes * depth);
+    std::memset(p->h_out, 0, p->out_bytes * depth);
+    cudaMemset(p->d_f, 0, p->f_bytes * depth);
+    *out = p;
+    return 0;
+}
+
+int ndp_pipeline_destroy(ndp_pipeline* p) {
+    if (!p) return 0;
+    if (p->s_cmp) cudaStreamSynchronize(p->s_cmp);
+    if (p->s_out) cudaStreamSynchronize(p->s_out);
+    if (p->s_in) cudaStreamSynchronize(p->s_in);
+    for (int s = 0; s < p->depth; s++) {
+        if (p->e_in && p->e_in[s]) cudaEventDestroy(p->e_in[s]);
+        if (p->e_cmp && p->e_cmp[s]) cudaEventDestroy(p->e_cmp[s]);
+        if (p->e_out && p->e_out[s]) cudaEventDestroy(p->e_out[s]);
+    }
+    delete[] p->e_in; delete[] p->e_cmp; delete[] p->e_out;
+    if (p->s_in) cudaStreamDestroy(p->s_in);
+    if (p->s_cmp) cudaStreamDestroy(p->s_cmp);
+    if (p->s_out) cudaStreamDestroy(p->s_out);
+    cudaFreeHost(p->h_in); cudaFreeHost(p->h_out);
+    cudaFree(p->d_in); cudaFree(p->d_out); cudaFree(p->d_f);
+    delete p;
+    return 0;
+}
+
+int ndp_pipeline_buffers(ndp_pipeline* p, int slot, void** x0, void** xr, void** ur, void** other, void** gate_xy, void** u0, int32_t** status) {
+    if (!p || slot < 0 || slot >= p->depth) return fail(NDP_E_ARG, "ndp_pipeline_buffers: bad slot");
+    unsigned char* in = p->h_in + (size_t)slot * p->in_bytes;
+    unsigned char* ot = p->h_out + (size_t)slot * p->out_bytes;
+    if (x0) *x0 = in + p->o_x0;
+    if (xr) *xr = in + p->o_xr;
+    if (ur) *ur = in + p->o_ur;
+    if (other) *other = p->mlp ? in + p->o_other : nullptr;
+    if (gate_xy) *gate_xy = p->mlp ? in + p->o_gate : nullptr;
+    if (u0) *u0 = ot;
+    if (status) *status = reinterpret_cast<int32_t*>(ot + p->o_status);
+    return 0;
+}
+
+int ndp_pipeline_submit(ndp_pipeline* p, int slot) {
+    if (!p || slot < 0 || slot >= p->depth) return fail(NDP_E_ARG, "ndp_pipeline_submit: bad slot");
+    ndp_handle* h = p->h;
+    unsigned char* din = p->d_in + (size_t)slot * p->in_bytes;
+    unsigned char* dout = p->d_out + (size_t)slot * p->out_bytes;
+    unsigned char* df = p->d_f + (size_t)slot * p->f_bytes;
+    // copy-in: the slot's device record is free once the kernels of its previous use are done
+    CU(cudaStreamWaitEvent(p->s_in, p->e_cmp[slot], 0));
+    CU(cudaMemcpyAsync(din, p->h_in + (size_t)slot * p->in_bytes, p->o_gate + (p->mlp ? (size_t)h->cfg.batch * 2 * h->elt : 0), cudaMemcpyHostToDevice, p->s_in));
+    CU(cudaEventRecord(p->e_in[slot], p->s_in));
+    // compute
+    CU(cudaStreamWaitEvent(p->s_cmp, p->e_in[slot], 0));
+    CU(cudaStreamWaitEvent(p->s_cmp, p->e_out[slot], 0));
+    if (p->mlp) {
+        int rc = ndp_mlp_forward_pairs_ex(p->mlp, h->cfg.precision, h->cfg.batch, h->cfg.N + 1, din + p->o_xr, din + p->o_other, 6, din + p->o_gate,
+                                          p->r_horiz, df, 0, 0, p->s_cmp);
+        if (rc) return rc;
+    }
+    int rc = ndp_update(h, din + p->o_x0, din + p->o_xr, din + p->o_ur, p->mlp ? df : nullptr, dout, p->s_cmp);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(dout + p->o_status, h->status, (size_t)h->cfg.batch * sizeof(int32_t), cudaMemcpyDeviceToDevice, p->s_cmp));
+    CU(cudaEventRecord(p->e_cmp[slot], p->s_cmp));
+    // copy-out
+    CU(cudaStreamWaitEvent(p->s_out, p->e_cmp[slot], 0));
+    CU(cudaMemcpyAsync(p->h_out + (size_t)slot * p->out_bytes, dout, p->o_status + (size_t)h->cfg.batch * sizeof(int32_t), cudaMemcpyDeviceToHost, p->s_out));
+    CU(cudaEventRecord(p->e_out[slot], p->s_out));
+    return 0;
+}
+
+int ndp_pipeline_wait(ndp_pipeline* p, int slot) {
+    if (!p || slot < 0 || slot >= p->depth) return fail(NDP_E_ARG, "ndp_pipeline_wait: bad slot");
+    CU(cudaEventSynchronize(p->e_out[slot]));
+    return 0;
+}
+
+int ndp_pipeline_bytes(const ndp_pipeline* p, int64_t* h2d, int64_t* d2h) {
+    if (!p) return fail(NDP_E_ARG, "ndp_pipeline_bytes: null");
+    if (h2d) *h2d = (int64_t)(p->o_gate + (p->mlp ? (size_t)p->h->cfg.batch * 2 * p->h->elt : 0));
+    if (d2h) *d2h = (int64_t)(p->o_status + (size_t)p->h->cfg.batch * sizeof(int32_t));
+    return 0;
+}
+
+// compute stream of the pipeline (so device-side consumers can order work after a step)
+void* ndp_pipeline_stream(ndp_pipeline* p) { return p ? (void*)p->s_cmp : nullptr; }
 
 }  // extern "C"
