@@ -168,7 +168,13 @@ int launch_solve(ndp_handle* h, const void* x0, void* u0, cudaStream_t st, const
     a.ws = (T*)h->ws;
     a.ws_stride = h->ws_stride;
     a.B = h->cfg.batch;
-    rti_step_kernel<T><<<h->grid, h->ppc * GL, h->smem, st>>>(c, a);
+    const int thr = h->ppc * GL;
+    switch (h->cfg.N) {
+        case 20: rti_step_kernel<T, 20><<<h->grid, thr, h->smem, st>>>(c, a); break;
+        case 40: rti_step_kernel<T, 40><<<h->grid, thr, h->smem, st>>>(c, a); break;
+        case 80: rti_step_kernel<T, 80><<<h->grid, thr, h->smem, st>>>(c, a); break;
+        default: rti_step_kernel<T, 0><<<h->grid, thr, h->smem, st>>>(c, a); break;
+    }
     h->launches++;
     CU(cudaGetLastError());
     return 0;
@@ -177,6 +183,23 @@ int launch_solve(ndp_handle* h, const void* x0, void* u0, cudaStream_t st, const
 }  // namespace ndp
 
 using namespace ndp;
+
+static const void* rti_kernel_ptr(int elt, int N) {
+    if (elt == 4) {
+        switch (N) {
+            case 20: return (const void*)rti_step_kernel<float, 20>;
+            case 40: return (const void*)rti_step_kernel<float, 40>;
+            case 80: return (const void*)rti_step_kernel<float, 80>;
+            default: return (const void*)rti_step_kernel<float, 0>;
+        }
+    }
+    switch (N) {
+        case 20: return (const void*)rti_step_kernel<double, 20>;
+        case 40: return (const void*)rti_step_kernel<double, 40>;
+        case 80: return (const void*)rti_step_kernel<double, 80>;
+        default: return (const void*)rti_step_kernel<double, 0>;
+    }
+}
 
 static int field_geom(const ndp_handle* h, int field, void** base, int* n_int, int* sdim, int* dim, int* dim_last, int* n_stages) {
     const int N = h->cfg.N;
@@ -259,16 +282,14 @@ int ndp_create(const ndp_config* cfg, ndp_handle** out) {
     const SmemLayout L(N);
     const WsLayout WL(N);
     h->ppc = 4;  // 64-thread CTAs: 4096 problems -> 1024 CTAs = 6.9 per SM (8-problem CTAs leave a 15 % imbalance)
-    while (h->ppc > 1 && (size_t)L.total * h->ppc * h->elt > 200 * 1024) h->ppc >>= 1;  // long horizons / fp64: fewer problems per CTA
-    h->smem = (size_t)L.total * h->ppc * h->elt;
+    while (h->ppc > 1 && ((size_t)L.total * h->ppc + 10 * TLD) * h->elt > 200 * 1024) h->ppc >>= 1;  // long horizons / fp64: fewer problems per CTA
+    h->smem = ((size_t)L.total * h->ppc + 10 * TLD) * h->elt;
     if (h->smem > 227 * 1024) { delete h; return fail(NDP_E_CONFIG, "ndp_create: horizon too long for shared memory"); }
-    cudaError_t e = (h->elt == 4)
-                        ? cudaFuncSetAttribute(rti_step_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem)
-                        : cudaFuncSetAttribute(rti_step_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem);
+    const void* kfn = rti_kernel_ptr(h->elt, N);
+    cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem);
     if (e != cudaSuccess) { delete h; return cuda_fail(e, "cudaFuncSetAttribute(rti_step_kernel)"); }
     int occ = 0;
-    e = (h->elt == 4) ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rti_step_kernel<float>, h->ppc * GL, h->smem)
-                      : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rti_step_kernel<double>, h->ppc * GL, h->smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, h->ppc * GL, h->smem);
     if (e != cudaSuccess || occ < 1) { delete h; return e != cudaSuccess ? cuda_fail(e, "occupancy") : fail(NDP_E_CONFIG, "kernel does not fit"); }
     const int need = (B + h->ppc - 1) / h->ppc;
     const int cap = n_sm * occ;  // persistent: at most one resident wave, grid-stride over problems
@@ -346,6 +367,7 @@ int ndp_solve(ndp_handle* h, const void* x0, void* u0, void* stream) {
 
 int ndp_update(ndp_handle* h, const void* x0, const void* xr, const void* ur, const void* f, void* u0, void* stream) {
     if (!h || !x0 || !xr || !ur) return fail(NDP_E_ARG, "ndp_update: null argument");
+    if ((((uintptr_t)xr) | ((uintptr_t)ur)) & 7) return fail(NDP_E_ARG, "ndp_update: xr / ur must be 8-byte aligned");
     std::lock_guard<std::mutex> lk(h->mu);
     return h->elt == 4 ? launch_solve<float>(h, x0, u0, (cudaStream_t)stream, xr, ur, f)
                        : launch_solve<double>(h, x0, u0, (cudaStream_t)stream, xr, ur, f);

@@ -25,8 +25,9 @@ namespace ndp {
 constexpr int NX = 10, NU = 4, NZ = 14, GL = 16;
 constexpr int NYS = 14;  // yref stride per stage
 constexpr int NPS = 8;   // parameter stride per stage
+constexpr int TLD = 12;  // leading dimension of the [A B b] tiles and of the forward-sweep records
 constexpr int RTI_THREADS = 128;
-constexpr int RTI_PPC = RTI_THREADS / GL;  // problems per CTA
+constexpr int RTI_PPC = RTI_THREADS / GL;  // problems per CTA (upper bound)
 
 template <typename T>
 struct RtiCfg {
@@ -58,40 +59,31 @@ struct RtiArgs {
     int B;
 };
 
-// ---- per-problem shared memory layout (elements of T) ----
+__host__ __device__ constexpr int al4(int o) { return (o + 3) & ~3; }
+
+// ---- per-problem shared memory layout (elements of T; every region 4-element aligned) ----
 struct SmemLayout {
-    int oX, oU, oY, oPar, oDz, oP, op, oAB, oHux, total;
-    __host__ __device__ explicit SmemLayout(int N) {
-        int o = 0;
-        oX = o; o += (N + 1) * NX;
-        oU = o; o += N * NU;
-        oY = o; o += (N + 1) * NYS;
-        oPar = o; o += (N + 1) * NPS;
-        o = (o + 3) & ~3;
-        oDz = o; o += (N + 1) * 16;   // QP step [k][lane]
-        oP = o; o += 10 * 12;         // P+ rows, stride 12
-        op = o; o += 12;              // p+
-        oAB = o; o += 10 * 12;        // nontrivial [A B] columns 6..13 and b, stride 12
-        oHux = o; o += 10 * 4;        // Hux transposed [i][m]
-        total = (o + 3) & ~3;
-    }
+    int oX, oU, oY, oPar, oDz, oP, op, oT0, oT1, oHux, total;
+    __host__ __device__ constexpr explicit SmemLayout(int N)
+        : oX(0), oU(al4((N + 1) * NX)), oY(oU + N * NU), oPar(oY + al4((N + 1) * NYS)), oDz(oPar + (N + 1) * NPS),
+          oP(oDz + (N + 1) * 16),  // QP step [k][lane]
+          op(oP + 10 * 12),        // P+ rows, stride 12; then p+
+          oT0(op + 12),            // tile of stage k:   rows r = 0..9 of [A B](:,6..13) | b | pad3, stride TLD
+          oT1(oT0 + 10 * TLD),     // tile of stage k-1 (the integrator fills two stages per pass)
+          oHux(oT1 + 10 * TLD),    // Hux transposed [i][m]
+          total(oHux + 10 * 4) {}
 };
 
 // ---- per-slot global workspace layout (elements of T) ----
 struct WsLayout {
-    long long oAB, oRec, oKt, oBarD, oBarG, oIpm, oZc, oHrow, total;
-    __host__ __device__ explicit WsLayout(int N) {
-        long long o = 0;
-        oAB = o; o += (long long)N * 80;    // [k][r][8]   columns 6..13 of [A B]
-        oRec = o; o += (long long)N * 16;   // [k]: b[10], kappa[4], pad
-        oKt = o; o += (long long)N * 40;    // [k][j][4]   K transposed
-        oBarD = o; o += (long long)(N + 1) * 16;
-        oBarG = o; o += (long long)(N + 1) * 16;
-        oIpm = o; o += (long long)7 * N * 16;  // LL LU TL TU CL CU ACT, each [k][lane]
-        oZc = o; o += (long long)(N + 1) * 16;
-        oHrow = o; o += (long long)N * 4 * 16;  // [k][m][16]: row m of [Hux Guu], [14] = gradient
-        total = (o + 3) & ~3LL;
-    }
+    long long oRec, oBarD, oBarG, oIpm, oZc, oHrow, total;
+    __host__ __device__ constexpr explicit WsLayout(int N)
+        : oRec(0),                                   // [k][14][TLD]: rows 0..9 = tile rows (x-lane records of the
+                                                     // forward sweep), rows 10..13 = [K(m, 0..9) kappa_m pad]
+          oBarD(oRec + (long long)N * 14 * TLD), oBarG(oBarD + (long long)(N + 1) * 16), oIpm(oBarG + (long long)(N + 1) * 16),
+          oZc(oIpm + (long long)7 * N * 16),  // LL LU TL TU CL CU ACT, each [k][lane]
+          oHrow(oZc + (long long)(N + 1) * 16),  // [k][m][16]: row m of [Hux Guu], [14] = gradient
+          total(oHrow + (long long)N * 4 * 16) {}
 };
 
 template <typename T> struct Vec4;
@@ -147,9 +139,10 @@ template <typename T>
 __device__ __forceinline__ void rk4_column(const RtiCfg<T>& c, int j, const T* __restrict__ x, const T* __restrict__ u,
                                            T fm0, T fm1, T fm2, T (&xa)[10], T (&sa)[10]) {
     const T h = c.h;
-    const T wx = u[0], wy = u[1], wz = u[2], cc = u[3];
-    const T ew0 = (j == 10) ? T(1) : T(0), ew1 = (j == 11) ? T(1) : T(0), ew2 = (j == 12) ? T(1) : T(0);
+    const T hwx = T(0.5) * u[0], hwy = T(0.5) * u[1], hwz = T(0.5) * u[2], cc = u[3];
+    const T ew0 = (j == 10) ? T(0.5) : T(0), ew1 = (j == 11) ? T(0.5) : T(0), ew2 = (j == 12) ? T(0.5) : T(0);
     const T ec = (j == 13) ? T(1) : T(0);
+    const T c2 = T(2) * cc, c4n = T(-4) * cc, fg2 = fm2 - c.g;
     T x0[10], s0[10], kx[10], ks[10];
 #pragma unroll
     for (int i = 0; i < 10; i++) {
@@ -172,20 +165,19 @@ __device__ __forceinline__ void rk4_column(const RtiCfg<T>& c, int j, const T* _
         kx[0] = vx; kx[1] = vy; kx[2] = vz;
         kx[3] = r13 * cc + fm0;
         kx[4] = r23 * cc + fm1;
-        kx[5] = r33 * cc - c.g + fm2;
-        kx[6] = T(0.5) * (-wx * qx - wy * qy - wz * qz);
-        kx[7] = T(0.5) * (wx * qw + wz * qy - wy * qz);
-        kx[8] = T(0.5) * (wy * qw - wz * qx + wx * qz);
-        kx[9] = T(0.5) * (wz * qw + wy * qx - wx * qy);
-        const T c2 = T(2) * cc;
+        kx[5] = r33 * cc + fg2;
+        kx[6] = -hwx * qx - hwy * qy - hwz * qz;
+        kx[7] = hwx * qw + hwz * qy - hwy * qz;
+        kx[8] = hwy * qw - hwz * qx + hwx * qz;
+        kx[9] = hwz * qw + hwy * qx - hwx * qy;
         ks[0] = s3; ks[1] = s4; ks[2] = s5;
         ks[3] = c2 * (qy * s6 + qz * s7 + qw * s8 + qx * s9) + ec * r13;
         ks[4] = c2 * (-qx * s6 - qw * s7 + qz * s8 + qy * s9) + ec * r23;
-        ks[5] = -T(2) * c2 * (qx * s7 + qy * s8) + ec * r33;
-        ks[6] = T(0.5) * (-wx * s7 - wy * s8 - wz * s9 - qx * ew0 - qy * ew1 - qz * ew2);
-        ks[7] = T(0.5) * (wx * s6 + wz * s8 - wy * s9 + qw * ew0 - qz * ew1 + qy * ew2);
-        ks[8] = T(0.5) * (wy * s6 - wz * s7 + wx * s9 + qz * ew0 + qw * ew1 - qx * ew2);
-        ks[9] = T(0.5) * (wz * s6 + wy * s7 - wx * s8 - qy * ew0 + qx * ew1 + qw * ew2);
+        ks[5] = c4n * (qx * s7 + qy * s8) + ec * r33;
+        ks[6] = (-hwx * s7 - hwy * s8 - hwz * s9) + (-qx * ew0 - qy * ew1 - qz * ew2);
+        ks[7] = (hwx * s6 + hwz * s8 - hwy * s9) + (qw * ew0 - qz * ew1 + qy * ew2);
+        ks[8] = (hwy * s6 - hwz * s7 + hwx * s9) + (qz * ew0 + qw * ew1 - qx * ew2);
+        ks[9] = (hwz * s6 + hwy * s7 - hwx * s8) + (-qy * ew0 + qx * ew1 + qw * ew2);
         const T bw = (st == 0 || st == 3) ? h * T(1.0 / 6.0) : h * T(1.0 / 3.0);
 #pragma unroll
         for (int i = 0; i < 10; i++) {
@@ -231,16 +223,14 @@ __device__ __forceinline__ void add_cost(T (&H)[14], const RtiCfg<T>& c, int j, 
     }
 }
 
-// Terminal stage: P_N = W_e (+ barrier), p_N = gradient.
-template <typename T, bool kBar>
-__device__ __forceinline__ void backward_terminal(const RtiCfg<T>& c, int j, unsigned mask, T* sm, const SmemLayout& L, const T* ws,
-                                                  const WsLayout& WL) {
-    const int N = c.N;
+// Terminal stage: P_N = W_e, p_N = gradient (no bounds at the terminal node: acados lbx/ubx
+// apply to intermediate nodes only).
+template <typename T>
+__device__ __forceinline__ void backward_terminal(const RtiCfg<T>& c, int N, int j, unsigned mask, T* sm, const SmemLayout& L) {
     T H[14];
 #pragma unroll
     for (int i = 0; i < 14; i++) H[i] = T(0);
     add_cost<T>(H, c, j, N, true, sm + L.oX, sm + L.oU, sm + L.oY, sm + L.oPar);
-    (void)ws; (void)WL;  // no bounds at the terminal node (acados lbx/ubx: intermediate nodes only)
     __syncwarp(mask);
     if (j < 10) {
 #pragma unroll
@@ -252,47 +242,23 @@ __device__ __forceinline__ void backward_terminal(const RtiCfg<T>& c, int j, uns
     __syncwarp(mask);
 }
 
-// One backward Riccati stage.  kLin: integrate the sensitivity column (and store it) instead of
-// loading it; kBar: add the barrier / active-set diagonal and gradient; kRows: store the rows of
-// [Hux Guu | g_u] needed by the active-set multiplier test.  Returns false on a non-positive pivot.
-template <typename T, bool kLin, bool kBar, bool kRows>
+// One backward Riccati stage on the tile `sT` ([10][TLD]: columns 6..13 of [A_k B_k], then b_k), which
+// must be complete and visible.  colp = this lane's column inside the tile (or the constant tile of the
+// trivial columns 0..5: dx+/dp = [I;0;0], dx+/dv = [hI;I;0]).  kBar: add the barrier / active-set
+// diagonal and gradient; kRows: store the rows of [Hux Guu | g_u] needed by the active-set multiplier
+// test.  Returns false on a non-positive pivot.
+template <typename T, bool kBar, bool kRows>
 __device__ __forceinline__ bool backward_stage(const RtiCfg<T>& c, int k, int j, unsigned mask, T* sm, const SmemLayout& L, T* ws,
-                                               const WsLayout& WL) {
+                                               const WsLayout& WL, const T* __restrict__ sT, const T* __restrict__ colp) {
     const T* sX = sm + L.oX;
     const T* sU = sm + L.oU;
     const T* sPar = sm + L.oPar;
     T* sP = sm + L.oP;
     T* sp = sm + L.op;
-    T* sAB = sm + L.oAB;
     T* sHux = sm + L.oHux;
     T col[10];
-    if (kLin) {
-        T xa[10], sa[10];
-        const T* pr = sPar + k * NPS;
-        rk4_column<T>(c, j, sX + k * NX, sU + k * NU, pr[4] * c.inv_mass, pr[5] * c.inv_mass, pr[6] * c.inv_mass, xa, sa);
 #pragma unroll
-        for (int r = 0; r < 10; r++) col[r] = (j == 14) ? xa[r] - sX[(k + 1) * NX + r] : sa[r];
-        if (j >= 6 && j < 14) {
-#pragma unroll
-            for (int r = 0; r < 10; r++) ws[WL.oAB + k * 80 + r * 8 + (j - 6)] = col[r];
-        } else if (j == 14) {
-#pragma unroll
-            for (int r = 0; r < 10; r++) ws[WL.oRec + k * 16 + r] = col[r];
-        }
-    } else {
-#pragma unroll
-        for (int r = 0; r < 10; r++) col[r] = (j == r) ? T(1) : T(0);
-#pragma unroll
-        for (int r = 0; r < 3; r++)
-            if (j == r + 3) col[r] = c.h;  // dp/dv0 = h I exactly
-        if (j >= 6 && j < 14) {
-#pragma unroll
-            for (int r = 0; r < 10; r++) col[r] = ws[WL.oAB + k * 80 + r * 8 + (j - 6)];
-        } else if (j == 14) {
-#pragma unroll
-            for (int r = 0; r < 10; r++) col[r] = ws[WL.oRec + k * 16 + r];
-        }
-    }
+    for (int r = 0; r < 10; r++) col[r] = colp[r * TLD];
     // W = P+ col (+ p+ on the gradient lane)
     T W[10];
 #pragma unroll
@@ -306,12 +272,6 @@ __device__ __forceinline__ bool backward_stage(const RtiCfg<T>& c, int k, int j,
         acc += p5 * col[5]; acc += p6 * col[6]; acc += p7 * col[7]; acc += p8 * col[8]; acc += p9 * col[9];
         W[i] = acc;
     }
-    // publish the nontrivial columns (6..13) and b (col 8 of the tile)
-    if (j >= 6 && j < 15) {
-#pragma unroll
-        for (int r = 0; r < 10; r++) sAB[r * 12 + (j - 6)] = col[r];
-    }
-    __syncwarp(mask);
     // H[:,j] = [A B]' W  (columns 0..5 of [A B] are [I; 0; 0] and [hI; I; 0])
     T H[14];
     H[0] = W[0]; H[1] = W[1]; H[2] = W[2];
@@ -323,8 +283,8 @@ __device__ __forceinline__ bool backward_stage(const RtiCfg<T>& c, int k, int j,
 #pragma unroll
     for (int r = 0; r < 10; r++) {
         T a0, a1, a2, a3, a4, a5, a6, a7;
-        Vec4<T>::ld(sAB + r * 12, a0, a1, a2, a3);
-        Vec4<T>::ld(sAB + r * 12 + 4, a4, a5, a6, a7);
+        Vec4<T>::ld(sT + r * TLD, a0, a1, a2, a3);
+        Vec4<T>::ld(sT + r * TLD + 4, a4, a5, a6, a7);
         H[6] += a0 * W[r]; H[7] += a1 * W[r]; H[8] += a2 * W[r]; H[9] += a3 * W[r];
         H[10] += a4 * W[r]; H[11] += a5 * W[r]; H[12] += a6 * W[r]; H[13] += a7 * W[r];
     }
@@ -376,6 +336,11 @@ __device__ __forceinline__ bool backward_stage(const RtiCfg<T>& c, int k, int j,
     const T x0 = (y0 - l10 * x1 - l20 * x2 - l30 * x3) * i00;
     const T K0 = -x0, K1 = -x1, K2 = -x2, K3 = -x3;  // K[:,j] (j < 10) or kappa (j == 14)
     if (j < 10) Vec4<T>::st(sHux + j * 4, H[10], H[11], H[12], H[13]);
+    // feedback rows for the forward sweep: rec[k][10+m][j] = K(m, j), [10] = kappa_m
+    if (j < 10 || j == 14) {
+        T* kr = ws + WL.oRec + ((long long)k * 14 + 10) * TLD + ((j == 14) ? 10 : j);
+        kr[0] = K0; kr[TLD] = K1; kr[2 * TLD] = K2; kr[3 * TLD] = K3;
+    }
     __syncwarp(mask);
     T Pn[10];
 #pragma unroll
@@ -392,93 +357,232 @@ __device__ __forceinline__ bool backward_stage(const RtiCfg<T>& c, int k, int j,
             if (i >= j) sP[i * 12 + j] = Pn[i];
             if (i > j) sP[j * 12 + i] = Pn[i];
         }
-        Vec4<T>::st(ws + WL.oKt + k * 40 + j * 4, K0, K1, K2, K3);
     } else if (j == 14) {
 #pragma unroll
         for (int i = 0; i < 10; i++) sp[i] = Pn[i];
-        ws[WL.oRec + k * 16 + 10] = K0;
-        ws[WL.oRec + k * 16 + 11] = K1;
-        ws[WL.oRec + k * 16 + 12] = K2;
-        ws[WL.oRec + k * 16 + 13] = K3;
     }
     __syncwarp(mask);
     return ok;
 }
 
+// copy one finished tile ([10][TLD], 30 vectors of 4) to the workspace record of stage k
+template <typename T>
+__device__ __forceinline__ void tile_to_ws(const T* __restrict__ sT, T* __restrict__ rec, int lane) {
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+        const int idx = lane + q * GL;
+        if (idx < 30) {
+            T a, b, cc, d;
+            Vec4<T>::ld(sT + idx * 4, a, b, cc, d);
+            Vec4<T>::st(rec + idx * 4, a, b, cc, d);
+        }
+    }
+}
+
+// Backward sweep.  kLin: linearise on the fly -- the 16 lanes integrate the 8 non-trivial sensitivity
+// columns (q0, omega, c) of TWO intervals per pass (lanes 0-7: interval k, lanes 8-15: interval k-1; the
+// state is integrated redundantly by every lane, so x+ comes for free) straight into the two tiles,
+// which are also saved to the workspace for the forward sweep / later IPM sweeps.  !kLin: tiles are
+// re-loaded from the workspace, one stage ahead of their use.
 template <typename T, bool kLin, bool kBar, bool kRows>
-__device__ __forceinline__ bool backward_sweep(const RtiCfg<T>& c, int j, unsigned mask, T* sm, const SmemLayout& L, T* ws,
-                                               const WsLayout& WL) {
-    backward_terminal<T, kBar>(c, j, mask, sm, L, ws, WL);
+__device__ __forceinline__ bool backward_sweep(const RtiCfg<T>& c, int N, int j, unsigned mask, T* sm, const SmemLayout& L, T* ws,
+                                               const WsLayout& WL, const T* __restrict__ sTriv) {
+    backward_terminal<T>(c, N, j, mask, sm, L);
     bool ok = true;
-    for (int k = c.N - 1; k >= 0; k--) ok &= backward_stage<T, kLin, kBar, kRows>(c, k, j, mask, sm, L, ws, WL);
+    T* sT0 = sm + L.oT0;
+    T* sT1 = sm + L.oT1;
+    const int jc = (j >= 6 && j < 15) ? j - 6 : 9;  // lane 15 reads a zeroed pad column
+    const T* col0 = (j < 6) ? sTriv + j : sT0 + jc;
+    const T* col1 = (j < 6) ? sTriv + j : sT1 + jc;
+    if (kLin) {
+        const T* sX = sm + L.oX;
+        const T* sU = sm + L.oU;
+        const T* sPar = sm + L.oPar;
+        const int half = j >> 3, cj = j & 7;
+        for (int k = N - 1; k >= 0; k -= 2) {
+            const int kk = (k - half >= 0) ? k - half : 0;
+            {
+                T xa[10], sa[10];
+                const T* pr = sPar + kk * NPS;
+                rk4_column<T>(c, 6 + cj, sX + kk * NX, sU + kk * NU, pr[4] * c.inv_mass, pr[5] * c.inv_mass, pr[6] * c.inv_mass, xa, sa);
+                T* t = (half ? sT1 : sT0) + cj;
+#pragma unroll
+                for (int r = 0; r < 10; r++) t[r * TLD] = sa[r];
+                if (cj == 0) {
+#pragma unroll
+                    for (int r = 0; r < 10; r++) t[r * TLD + 8] = xa[r] - sX[(kk + 1) * NX + r];
+                }
+            }
+            __syncwarp(mask);
+            tile_to_ws<T>(sT0, ws + WL.oRec + (long long)k * 14 * TLD, j);
+            ok &= backward_stage<T, kBar, kRows>(c, k, j, mask, sm, L, ws, WL, sT0, col0);
+            if (k >= 1) {
+                tile_to_ws<T>(sT1, ws + WL.oRec + (long long)(k - 1) * 14 * TLD, j);
+                ok &= backward_stage<T, kBar, kRows>(c, k - 1, j, mask, sm, L, ws, WL, sT1, col1);
+            }
+        }
+    } else {
+        // tile of stage k lives in sT[(N-1-k) & 1]; the loads of stage k-1 are issued before stage k runs
+        T pre[2][4];
+        auto fetch = [&](int k) {
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                const int idx = j + q * GL;
+                if (idx < 30) Vec4<T>::ld(ws + WL.oRec + (long long)k * 14 * TLD + idx * 4, pre[q][0], pre[q][1], pre[q][2], pre[q][3]);
+            }
+        };
+        auto put = [&](T* t) {
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                const int idx = j + q * GL;
+                if (idx < 30) Vec4<T>::st(t + idx * 4, pre[q][0], pre[q][1], pre[q][2], pre[q][3]);
+            }
+        };
+        fetch(N - 1);
+        put(sT0);
+        __syncwarp(mask);
+        int par = 0;
+        for (int k = N - 1; k >= 0; k--) {
+            if (k >= 1) fetch(k - 1);
+            ok &= backward_stage<T, kBar, kRows>(c, k, j, mask, sm, L, ws, WL, par ? sT1 : sT0, par ? col1 : col0);
+            if (k >= 1) {
+                put(par ? sT0 : sT1);
+                __syncwarp(mask);
+            }
+            par ^= 1;
+        }
+    }
     return __all_sync(mask, ok);
 }
 
-// Forward substitution: lane i < 10 carries dx_k[i], lanes 10..13 compute du_k[m].
-// Writes the step to sDz[k][lane].
-template <typename T>
-__device__ __forceinline__ void forward_sweep(const RtiCfg<T>& c, int lane, unsigned mask, T dx0, T* sm, const SmemLayout& L,
-                                              const T* ws, const WsLayout& WL) {
-    const int N = c.N;
+// Forward substitution: lane i < 10 carries dx_k[i], lanes 10..13 compute du_k[m]; the stage records
+// (3 vectors per lane) are prefetched kPf stages ahead from the L2-resident workspace.
+// kFinal: the step is accepted on the fly -- the new iterate (X + dx, U + du) is written to global
+// memory as it is produced and the box test / NaN test / active count are fused in (flags returned
+// through viol / bad / nact); otherwise the step goes to sDz[k][lane] for the IPM.
+template <typename T, bool kFinal>
+__device__ __forceinline__ void forward_sweep(const RtiCfg<T>& c, int N, int lane, unsigned mask, T dx0, T* sm, const SmemLayout& L,
+                                              const T* ws, const WsLayout& WL, T lo, T hi, T* gX, T* gU, T* gu0, bool& viol, bool& bad,
+                                              int& nact) {
+    constexpr int kPf = 4;
     T* sDz = sm + L.oDz;
-    const bool isx = lane < 10, isu = (lane >= 10 && lane < 14);
+    const bool isx = lane < 10, isu = (lane >= 10 && lane < 14), isv = (lane >= 3 && lane < 6);
+    const T* rec = ws + WL.oRec + (long long)((lane < 14) ? lane : 13) * TLD;
+    // iterate value / destination of the variable this lane owns
+    const T* itp = isx ? sm + L.oX + lane : sm + L.oU + ((lane - 10) & 3);
+    T* gp = isx ? gX + lane : gU + ((lane - 10) & 3);
+    const int its = isx ? NX : NU;
     T z = isx ? dx0 : T(0);
-    T cf[11], nf[11];
-    auto load = [&](int k, T(&f)[11]) {
+    T buf[kPf][12];
 #pragma unroll
-        for (int i = 0; i < 11; i++) f[i] = T(0);
-        if (isx) {
-            Vec4<T>::ld(ws + WL.oAB + k * 80 + lane * 8, f[0], f[1], f[2], f[3]);
-            Vec4<T>::ld(ws + WL.oAB + k * 80 + lane * 8 + 4, f[4], f[5], f[6], f[7]);
-            f[8] = ws[WL.oRec + k * 16 + lane];
-        } else if (isu) {
-#pragma unroll
-            for (int jj = 0; jj < 10; jj++) f[jj] = ws[WL.oKt + k * 40 + jj * 4 + (lane - 10)];
-            f[10] = ws[WL.oRec + k * 16 + lane];
+    for (int u = 0; u < kPf; u++) {
+        if (u < N) {
+            const T* r = rec + (long long)u * 14 * TLD;
+            Vec4<T>::ld(r, buf[u][0], buf[u][1], buf[u][2], buf[u][3]);
+            Vec4<T>::ld(r + 4, buf[u][4], buf[u][5], buf[u][6], buf[u][7]);
+            Vec4<T>::ld(r + 8, buf[u][8], buf[u][9], buf[u][10], buf[u][11]);
         }
-    };
-    load(0, cf);
-    for (int k = 0; k < N; k++) {
-        if (k + 1 < N) load(k + 1, nf);
-        T xj[10];
-#pragma unroll
-        for (int jj = 0; jj < 10; jj++) xj[jj] = __shfl_sync(mask, z, jj, GL);
-        const T zv = __shfl_sync(mask, z, (lane + 3) & 15, GL);
-        T du = cf[10];
-#pragma unroll
-        for (int jj = 0; jj < 10; jj++) du += cf[jj] * xj[jj];
-        T um[4];
-#pragma unroll
-        for (int m = 0; m < 4; m++) um[m] = __shfl_sync(mask, du, 10 + m, GL);
-        T xn = cf[8] + ((lane < 3) ? z + c.h * zv : ((lane < 6) ? z : T(0)));
-        xn += cf[0] * xj[6] + cf[1] * xj[7] + cf[2] * xj[8] + cf[3] * xj[9];
-        xn += cf[4] * um[0] + cf[5] * um[1] + cf[6] * um[2] + cf[7] * um[3];
-        if (lane < 14) sDz[k * 16 + lane] = isx ? z : du;
-        z = xn;
-#pragma unroll
-        for (int i = 0; i < 11; i++) cf[i] = nf[i];
     }
-    if (isx) sDz[N * 16 + lane] = z;
+    bool v_l = false, b_l = false;
+    int n_l = 0;
+    for (int k0 = 0; k0 < N; k0 += kPf) {
+#pragma unroll
+        for (int u = 0; u < kPf; u++) {
+            const int k = k0 + u;
+            if (k < N) {
+                T (&cf)[12] = buf[u];
+                T xj[10];
+#pragma unroll
+                for (int jj = 0; jj < 10; jj++) xj[jj] = __shfl_sync(mask, z, jj, GL);
+                const T zv = __shfl_sync(mask, z, (lane + 3) & 15, GL);
+                T du = cf[10], du2 = T(0);
+#pragma unroll
+                for (int jj = 0; jj < 5; jj++) {
+                    du += cf[jj] * xj[jj];
+                    du2 += cf[5 + jj] * xj[5 + jj];
+                }
+                du += du2;
+                T um[4];
+#pragma unroll
+                for (int m = 0; m < 4; m++) um[m] = __shfl_sync(mask, du, 10 + m, GL);
+                T xn = cf[8] + ((lane < 3) ? z + c.h * zv : ((lane < 6) ? z : T(0)));
+                xn += cf[0] * xj[6] + cf[1] * xj[7] + cf[2] * xj[8] + cf[3] * xj[9];
+                xn += cf[4] * um[0] + cf[5] * um[1] + cf[6] * um[2] + cf[7] * um[3];
+                const T dz = isx ? z : du;
+                if (kFinal) {
+                    if (lane < 14) {
+                        const T v = itp[k * its] + dz;
+                        gp[k * its] = v;
+                        if (k == 0 && isu && gu0) gu0[lane - 10] = v;
+                        b_l |= !(fabs(v) <= T(1e30));
+                        if (isu || (isv && k >= 1)) {
+                            v_l |= !(v >= lo && v <= hi);
+                            n_l += (v <= lo) + (v >= hi);
+                        }
+                    }
+                } else {
+                    if (lane < 14) sDz[k * 16 + lane] = dz;
+                }
+                z = xn;
+                if (k + kPf < N) {
+                    const T* r = rec + (long long)(k + kPf) * 14 * TLD;
+                    Vec4<T>::ld(r, cf[0], cf[1], cf[2], cf[3]);
+                    Vec4<T>::ld(r + 4, cf[4], cf[5], cf[6], cf[7]);
+                    Vec4<T>::ld(r + 8, cf[8], cf[9], cf[10], cf[11]);
+                }
+            }
+        }
+    }
+    if (kFinal) {
+        if (isx) {
+            const T v = itp[N * its] + z;
+            gp[N * its] = v;
+            b_l |= !(fabs(v) <= T(1e30));
+        }
+        viol = __any_sync(mask, v_l);
+        bad = __any_sync(mask, b_l);
+        nact = n_l;
+    } else {
+        if (isx) sDz[N * 16 + lane] = z;
+    }
     __syncwarp(mask);
 }
 
+// 4/8/16-byte asynchronous global -> shared copies (LDGSTS): the whole problem record is requested
+// up front and lands while nothing else waits on it
+template <int kBytes>
+__device__ __forceinline__ void cp_async(void* smem_dst, const void* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(d), "l"(gsrc), "n"(kBytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 enum { IPM_LL = 0, IPM_LU, IPM_TL, IPM_TU, IPM_CL, IPM_CU, IPM_ACT };
 
-template <typename T>
-__global__ void __launch_bounds__(RTI_THREADS, (sizeof(T) == 4) ? 4 : 2) rti_step_kernel(const RtiCfg<T> c, const RtiArgs<T> a) {
+constexpr int RTI_CTA = 64;  // threads per CTA of the nominal launch (4 problems)
+
+template <typename T, int kN>
+__global__ void __maxnreg__((sizeof(T) == 4) ? 144 : 255) rti_step_kernel(const RtiCfg<T> c, const RtiArgs<T> a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int N = c.N;
+    const int N = (kN > 0) ? kN : c.N;
     const SmemLayout L(N);
     const WsLayout WL(N);
     const int lane = threadIdx.x & 15;
     const int grp = threadIdx.x >> 4;
     const unsigned mask = 0xFFFFu << (threadIdx.x & 16);
-    T* sm = reinterpret_cast<T*>(smem_raw) + (size_t)grp * L.total;
-    const int ppc = blockDim.x >> 4;  // problems per CTA (8 unless the horizon needs more shared memory)
+    const int ppc = blockDim.x >> 4;  // problems per CTA
+    T* sTriv = reinterpret_cast<T*>(smem_raw);  // [10][TLD] constant tile of the trivial columns 0..5, shared by the CTA
+    T* sm = sTriv + 10 * TLD + (size_t)grp * L.total;
     T* ws = a.ws + (size_t)(blockIdx.x * ppc + grp) * a.ws_stride;
     T* sX = sm + L.oX;
     T* sU = sm + L.oU;
     T* sDz = sm + L.oDz;
+    for (int i = threadIdx.x; i < 10 * TLD; i += blockDim.x) {
+        const int r = i / TLD, cc = i - r * TLD;
+        sTriv[i] = (cc < 6 && cc == r) ? T(1) : ((cc >= 3 && cc < 6 && cc - 3 == r) ? c.h : T(0));
+    }
+    for (int i = lane; i < 20 * TLD; i += GL) sm[L.oT0 + i] = T(0);
+    __syncthreads();
 
     // per-lane box of the variable this lane owns (lanes 3..5: v, lanes 10..13: u)
     T lo = T(-1e30), hi = T(1e30);
@@ -491,59 +595,94 @@ __global__ void __launch_bounds__(RTI_THREADS, (sizeof(T) == 4) ? 4 : 2) rti_ste
     const bool isx = lane < 10, isu = (lane >= 10 && lane < 14), isv = (lane >= 3 && lane < 6);
 
     for (int prob = blockIdx.x * ppc + grp; prob < a.B; prob += gridDim.x * ppc) {
-        // ---- stage the problem record in shared memory ----
+        T* gX = a.X + (size_t)prob * (N + 1) * NX;
+        T* gU = a.U + (size_t)prob * N * NU;
+        // ---- stage the problem record in shared memory (asynchronous copies, one wait) ----
         {
-            const T* gX = a.X + (size_t)prob * (N + 1) * NX;
-            const T* gU = a.U + (size_t)prob * N * NU;
-            const T* gY = a.yref + (size_t)prob * (N + 1) * NYS;
-            const T* gP = a.par + (size_t)prob * (N + 1) * NPS;
-            for (int i = lane; i < (N + 1) * NX; i += GL) sX[i] = gX[i];
-            for (int i = lane; i < N * NU; i += GL) sU[i] = gU[i];
+            constexpr int E2 = 8 / (int)sizeof(T);  // elements per 8-byte copy (records are 8-byte aligned)
+            if (E2 == 2) {
+                for (int i = lane; i < (N + 1) * NX / 2; i += GL) cp_async<8>(sX + 2 * i, gX + 2 * i);
+                for (int i = lane; i < N * NU / 2; i += GL) cp_async<8>(sU + 2 * i, gU + 2 * i);
+            } else {
+                for (int i = lane; i < (N + 1) * NX; i += GL) cp_async<8>(sX + i, gX + i);
+                for (int i = lane; i < N * NU; i += GL) cp_async<8>(sU + i, gU + i);
+            }
             if (a.xr == nullptr) {
-                for (int i = lane; i < (N + 1) * NYS; i += GL) sm[L.oY + i] = gY[i];
-                for (int i = lane; i < (N + 1) * NPS; i += GL) sm[L.oPar + i] = gP[i];
+                const T* gY = a.yref + (size_t)prob * (N + 1) * NYS;
+                const T* gP = a.par + (size_t)prob * (N + 1) * NPS;
+                if (E2 == 2) {
+                    for (int i = lane; i < (N + 1) * NYS / 2; i += GL) cp_async<8>(sm + L.oY + 2 * i, gY + 2 * i);
+                    for (int i = lane; i < (N + 1) * NPS / 2; i += GL) cp_async<8>(sm + L.oPar + 2 * i, gP + 2 * i);
+                } else {
+                    for (int i = lane; i < (N + 1) * NYS; i += GL) cp_async<8>(sm + L.oY + i, gY + i);
+                    for (int i = lane; i < (N + 1) * NPS; i += GL) cp_async<8>(sm + L.oPar + i, gP + i);
+                }
             } else {
                 // yref_k = [xr_k; ur_k], p_k = [xr_k[6:10]; f_k]   (nmpc_body_rate_ctl.py:95-104)
                 const T* gxr = a.xr + (size_t)prob * (N + 1) * NX;
                 const T* gur = a.ur + (size_t)prob * N * NU;
-                for (int i = lane; i < (N + 1) * NX; i += GL) {
-                    const T v = gxr[i];
-                    const int k = i / NX, cix = i - k * NX;
-                    sm[L.oY + k * NYS + cix] = v;
-                    if (cix >= 6) sm[L.oPar + k * NPS + cix - 6] = v;
+                for (int i = lane; i < (N + 1) * 5; i += GL) {  // element pairs (k, 2q), (k, 2q+1)
+                    const int k = i / 5, q = i - k * 5;
+                    if (E2 == 2) {
+                        cp_async<8>(sm + L.oY + k * NYS + 2 * q, gxr + k * NX + 2 * q);
+                        if (q >= 3) cp_async<8>(sm + L.oPar + k * NPS + 2 * q - 6, gxr + k * NX + 2 * q);
+                    } else {
+                        cp_async<8>(sm + L.oY + k * NYS + 2 * q, gxr + k * NX + 2 * q);
+                        cp_async<8>(sm + L.oY + k * NYS + 2 * q + 1, gxr + k * NX + 2 * q + 1);
+                        if (q >= 3) {
+                            cp_async<8>(sm + L.oPar + k * NPS + 2 * q - 6, gxr + k * NX + 2 * q);
+                            cp_async<8>(sm + L.oPar + k * NPS + 2 * q - 5, gxr + k * NX + 2 * q + 1);
+                        }
+                    }
                 }
-                for (int i = lane; i < (N + 1) * NU; i += GL) {
-                    const int k = i >> 2, m = i & 3;
-                    sm[L.oY + k * NYS + NX + m] = (k < N) ? gur[i] : T(0);
-                    sm[L.oPar + k * NPS + 4 + m] = (m < 3 && a.f) ? a.f[((size_t)prob * (N + 1) + k) * 3 + m] : T(0);
+                for (int i = lane; i < N * 2; i += GL) {
+                    const int k = i >> 1, q = i & 1;
+                    if (E2 == 2) {
+                        cp_async<8>(sm + L.oY + k * NYS + NX + 2 * q, gur + k * NU + 2 * q);
+                    } else {
+                        cp_async<8>(sm + L.oY + k * NYS + NX + 2 * q, gur + k * NU + 2 * q);
+                        cp_async<8>(sm + L.oY + k * NYS + NX + 2 * q + 1, gur + k * NU + 2 * q + 1);
+                    }
                 }
-                __syncwarp(mask);
-                T* wY = a.yref_w + (size_t)prob * (N + 1) * NYS;
-                T* wP = a.par_w + (size_t)prob * (N + 1) * NPS;
-                for (int i = lane; i < (N + 1) * NYS; i += GL) wY[i] = sm[L.oY + i];
-                for (int i = lane; i < (N + 1) * NPS; i += GL) wP[i] = sm[L.oPar + i];
+                if (lane < NU) sm[L.oY + N * NYS + NX + lane] = T(0);
+                if (a.f) {
+                    const T* gf = a.f + (size_t)prob * (N + 1) * 3;
+                    for (int i = lane; i < (N + 1) * 3; i += GL) {
+                        const int k = i / 3, m = i - k * 3;
+                        cp_async<(int)sizeof(T)>(sm + L.oPar + k * NPS + 4 + m, gf + i);
+                    }
+                    for (int k = lane; k <= N; k += GL) sm[L.oPar + k * NPS + 7] = T(0);
+                } else {
+                    for (int i = lane; i < (N + 1) * 4; i += GL) sm[L.oPar + (i >> 2) * NPS + 4 + (i & 3)] = T(0);
+                }
             }
         }
-        const T dx0 = isx ? a.x0[(size_t)prob * NX + lane] - a.X[(size_t)prob * (N + 1) * NX + lane] : T(0);
+        const T x0v = isx ? a.x0[(size_t)prob * NX + lane] : T(0);
+        cp_async_wait_all();
         __syncwarp(mask);
+        if (a.xr != nullptr) {
+            // persist yref / p as if set stage by stage (a later plain solve or get sees them)
+            T* wY = a.yref_w + (size_t)prob * (N + 1) * NYS;
+            T* wP = a.par_w + (size_t)prob * (N + 1) * NPS;
+            for (int i = lane; i < (N + 1) * NYS; i += GL) wY[i] = sm[L.oY + i];
+            for (int i = lane; i < (N + 1) * NPS; i += GL) wP[i] = sm[L.oPar + i];
+        }
+        const T dx0 = isx ? x0v - sX[lane] : T(0);
 
         int status = 0, n_fact = 0, n_ipm = 0, n_pol = 0;
         // iterate value of the variable this lane owns at stage k
         auto iter_at = [&](int k) -> T { return isx ? sX[k * NX + lane] : (isu ? sU[k * NU + (lane - 10)] : T(0)); };
         auto has_box = [&](int k) -> bool { return (isu && k < N) || (isv && k >= 1 && k < N); };
 
-        // ---- preparation + unconstrained feedback ----
-        bool ok = backward_sweep<T, true, false, false>(c, lane, mask, sm, L, ws, WL);
+        // ---- preparation + unconstrained feedback; the step is accepted on the fly ----
+        bool ok = backward_sweep<T, true, false, false>(c, N, lane, mask, sm, L, ws, WL, sTriv);
         n_fact++;
-        forward_sweep<T>(c, lane, mask, dx0, sm, L, ws, WL);
-        bool viol = false;
-        for (int k = 0; k < N; k++)
-            if (has_box(k)) {
-                const T v = iter_at(k) + sDz[k * 16 + lane];
-                viol |= !(v >= lo && v <= hi);
-            }
-        viol = __any_sync(mask, viol);
+        bool viol = false, bad = false;
+        int nact_l = 0;
+        forward_sweep<T, true>(c, N, lane, mask, dx0, sm, L, ws, WL, lo, hi, gX, gU, a.u0 ? a.u0 + (size_t)prob * NU : nullptr, viol, bad,
+                               nact_l);
         if (!ok) status = 4;
+        const bool nominal = ok && !viol;
 
         if (ok && viol) {
             // ================= Mehrotra IPM on the Riccati kernel =================
@@ -601,9 +740,9 @@ __global__ void __launch_bounds__(RTI_THREADS, (sizeof(T) == 4) ? 4 : 2) rti_ste
                 mu_prev = mu;
                 __syncwarp(mask);
                 // ---- predictor ----
-                if (!backward_sweep<T, false, true, false>(c, lane, mask, sm, L, ws, WL)) { status = 4; break; }
+                if (!backward_sweep<T, false, true, false>(c, N, lane, mask, sm, L, ws, WL, sTriv)) { status = 4; break; }
                 n_fact++;
-                forward_sweep<T>(c, lane, mask, dx0, sm, L, ws, WL);
+                forward_sweep<T, false>(c, N, lane, mask, dx0, sm, L, ws, WL, lo, hi, gX, gU, nullptr, viol, bad, nact_l);
                 T amax = T(1e30);
                 for (int k = 0; k < N; k++)
                     if (has_box(k)) {
@@ -652,9 +791,9 @@ __global__ void __launch_bounds__(RTI_THREADS, (sizeof(T) == 4) ? 4 : 2) rti_ste
                         bG[e] = ((sigma_mu - cu) / tu - gu * ub + lu) - ((sigma_mu - cl) / tl + gl * lb + ll);
                     }
                 __syncwarp(mask);
-                if (!backward_sweep<T, false, true, false>(c, lane, mask, sm, L, ws, WL)) { status = 4; break; }
+                if (!backward_sweep<T, false, true, false>(c, N, lane, mask, sm, L, ws, WL, sTriv)) { status = 4; break; }
                 n_fact++;
-                forward_sweep<T>(c, lane, mask, dx0, sm, L, ws, WL);
+                forward_sweep<T, false>(c, N, lane, mask, dx0, sm, L, ws, WL, lo, hi, gX, gU, nullptr, viol, bad, nact_l);
                 amax = T(1e30);
                 for (int k = 0; k < N; k++)
                     if (has_box(k)) {
@@ -734,10 +873,10 @@ __global__ void __launch_bounds__(RTI_THREADS, (sizeof(T) == 4) ? 4 : 2) rti_ste
                             }
                         }
                     __syncwarp(mask);
-                    if (!backward_sweep<T, false, true, true>(c, lane, mask, sm, L, ws, WL)) break;
+                    if (!backward_sweep<T, false, true, true>(c, N, lane, mask, sm, L, ws, WL, sTriv)) break;
                     n_fact++;
                     n_pol++;
-                    forward_sweep<T>(c, lane, mask, dx0, sm, L, ws, WL);
+                    forward_sweep<T, false>(c, N, lane, mask, dx0, sm, L, ws, WL, lo, hi, gX, gU, nullptr, viol, bad, nact_l);
                     bool changed = false, xviol = false;
                     if (isv)
                         for (int k = 1; k < N; k++) {
@@ -793,35 +932,39 @@ __global__ void __launch_bounds__(RTI_THREADS, (sizeof(T) == 4) ? 4 : 2) rti_ste
             __syncwarp(mask);
         }
 
-        // ---- full step, write back ----
-        bool bad = false;
-        int nact_l = 0;
-        if (lane < 14)
-            for (int k = 0; k <= N; k++) {
-                if (k == N && !isx) break;
-                const T v = iter_at(k) + sDz[k * 16 + lane];
-                bad |= !(v == v) || (fabs(v) > T(1e30));
-                if (has_box(k)) nact_l += (v <= lo) + (v >= hi);
-                if (isx) sX[k * NX + lane] = v;
-                else sU[k * NU + (lane - 10)] = v;
-            }
-        bad = __any_sync(mask, bad);
-        const int nact = (int)grp_sum<float>((float)nact_l, mask);
-        if (bad) status = 1;
-        __syncwarp(mask);
-        {
-            T* gX = a.X + (size_t)prob * (N + 1) * NX;
-            T* gU = a.U + (size_t)prob * N * NU;
+        // ---- write back ----
+        int nact;
+        if (nominal || !ok) {
+            // the forward sweep already stored the new iterate and u0
+            nact = (int)grp_sum<float>((float)nact_l, mask);
+            if (bad) status = 1;
+        } else {
+            // constrained step from the IPM / active-set rounds: full step, overwrite the tentative iterate
+            bool bad2 = false;
+            nact_l = 0;
+            if (lane < 14)
+                for (int k = 0; k <= N; k++) {
+                    if (k == N && !isx) break;
+                    const T v = iter_at(k) + sDz[k * 16 + lane];
+                    bad2 |= !(fabs(v) <= T(1e30));
+                    if (has_box(k)) nact_l += (v <= lo) + (v >= hi);
+                    if (isx) sX[k * NX + lane] = v;
+                    else sU[k * NU + (lane - 10)] = v;
+                }
+            bad2 = __any_sync(mask, bad2);
+            nact = (int)grp_sum<float>((float)nact_l, mask);
+            if (bad2) status = 1;
+            __syncwarp(mask);
             for (int i = lane; i < (N + 1) * NX; i += GL) gX[i] = sX[i];
             for (int i = lane; i < N * NU; i += GL) gU[i] = sU[i];
             if (a.u0 && lane < NU) a.u0[(size_t)prob * NU + lane] = sU[lane];
-            if (lane == 0) {
-                a.status[prob] = status;
-                a.stats[prob * 4 + 0] = n_fact;
-                a.stats[prob * 4 + 1] = n_ipm;
-                a.stats[prob * 4 + 2] = n_pol;
-                a.stats[prob * 4 + 3] = nact;
-            }
+        }
+        if (lane == 0) {
+            a.status[prob] = status;
+            a.stats[prob * 4 + 0] = n_fact;
+            a.stats[prob * 4 + 1] = n_ipm;
+            a.stats[prob * 4 + 2] = n_pol;
+            a.stats[prob * 4 + 3] = nact;
         }
         __syncwarp(mask);
     }
