@@ -134,8 +134,8 @@ RtiCfg<T> make_cfg(const ndp_config& g) {
     c.h = (T)(g.T / g.N);
     c.inv_mass = (T)(1.0 / g.mass);
     c.g = (T)g.gravity;
-    for (int i = 0; i < 10; i++) c.Q[i] = (T)g.Q[i];
-    for (int i = 0; i < 4; i++) { c.R[i] = (T)g.R[i]; c.umin[i] = (T)g.u_min[i]; c.umax[i] = (T)g.u_max[i]; }
+    for (int i = 0; i < 10; i++) { c.Q[i] = (T)g.Q[i]; c.hQ[i] = (T)(g.Q[i] * g.T / g.N); }
+    for (int i = 0; i < 4; i++) { c.R[i] = (T)g.R[i]; c.hR[i] = (T)(g.R[i] * g.T / g.N); c.umin[i] = (T)g.u_min[i]; c.umax[i] = (T)g.u_max[i]; }
     for (int i = 0; i < 3; i++) { c.vmin[i] = (T)g.v_min[i]; c.vmax[i] = (T)g.v_max[i]; }
     const bool f32 = sizeof(T) == 4;
     c.tol_mu = (T)(g.ipm_tol_mu > 0 ? g.ipm_tol_mu : (f32 ? 1e-4 : 1e-9));

@@ -23,7 +23,8 @@
 namespace ndp {
 
 constexpr int NX = 10, NU = 4, NZ = 14, GL = 16;
-constexpr int NYS = 14;  // yref stride per stage
+constexpr int NYS = 14;  // yref stride per stage (global)
+constexpr int SYS = 16;  // shared-memory stride of the per-stage cost record (residuals, see cost_records)
 constexpr int NPS = 8;   // parameter stride per stage
 constexpr int TLD = 12;  // leading dimension of the [A B b] tiles and of the forward-sweep records
 constexpr int RTI_THREADS = 128;
@@ -33,7 +34,7 @@ template <typename T>
 struct RtiCfg {
     int N, ipm_max_iter, polish_max;
     T h, inv_mass, g;
-    T Q[10], R[4], umin[4], umax[4], vmin[3], vmax[3];
+    T Q[10], R[4], hQ[10], hR[4], umin[4], umax[4], vmin[3], vmax[3];  // hQ = h Q, hR = h R (stage cost scaled by the interval)
     T tol_mu, tol_res, mu0, t_floor, t_min, big;
 };
 
@@ -65,13 +66,14 @@ __host__ __device__ constexpr int al4(int o) { return (o + 3) & ~3; }
 struct SmemLayout {
     int oX, oU, oY, oPar, oDz, oP, op, oT0, oT1, oHux, total;
     __host__ __device__ constexpr explicit SmemLayout(int N)
-        : oX(0), oU(al4((N + 1) * NX)), oY(oU + N * NU), oPar(oY + al4((N + 1) * NYS)), oDz(oPar + (N + 1) * NPS),
+        : oX(0), oU(al4((N + 1) * NX)), oY(oU + N * NU), oPar(oY + (N + 1) * SYS), oDz(oPar + (N + 1) * NPS),
           oP(oDz + (N + 1) * 16),  // QP step [k][lane]
           op(oP + 10 * 12),        // P+ rows, stride 12; then p+
           oT0(op + 12),            // tile of stage k:   rows r = 0..9 of [A B](:,6..13) | b | pad3, stride TLD
           oT1(oT0 + 10 * TLD),     // tile of stage k-1 (the integrator fills two stages per pass)
           oHux(oT1 + 10 * TLD),    // Hux transposed [i][m]
-          total(oHux + 10 * 4) {}
+          // problem stride = 16 (mod 32) words: the two problems of a warp then sit on disjoint bank halves
+          total(((oHux + 10 * 4 + 15) & ~31) + 16) {}
 };
 
 // ---- per-slot global workspace layout (elements of T) ----
@@ -187,38 +189,59 @@ __device__ __forceinline__ void rk4_column(const RtiCfg<T>& c, int j, const T* _
     }
 }
 
+// Per-stage cost record (shared memory, stride SYS), built once per problem from the iterate and yref/p:
+//   [0..5] x - yref (p, v)   [6] 0   [7..9] q_r(xyz) - yref_q(xyz)   [10..13] u - yref_u   [14..15] 0
+// so that the gradient lane reads its stage residual with four 128-bit loads.
+template <typename T>
+__device__ __forceinline__ void cost_records(int N, int lane, T* __restrict__ sY, const T* __restrict__ sX, const T* __restrict__ sU,
+                                             const T* __restrict__ sPar) {
+    for (int i = lane; i < (N + 1) * SYS; i += GL) {
+        const int k = i >> 4, e = i & 15;
+        const T y = sY[i];
+        T v = T(0);
+        if (e < 6) v = sX[k * NX + e] - y;
+        else if (e >= 7 && e < 10) v = sPar[k * NPS + e - 6] - y;
+        else if (e >= 10 && e < 14 && k < N) v = sU[k * NU + e - 10] - y;
+        sY[i] = v;
+    }
+}
+
 // Gauss-Newton cost blocks in column form: lane j < 14 gets column j of the stage Hessian,
 // lane 14 the gradient (yref quaternion part may differ from q_r).
 template <typename T>
 __device__ __forceinline__ void add_cost(T (&H)[14], const RtiCfg<T>& c, int j, int k, bool terminal, const T* __restrict__ sX,
-                                         const T* __restrict__ sU, const T* __restrict__ sY, const T* __restrict__ sPar) {
-    const T s = terminal ? T(1) : c.h;
+                                         const T* __restrict__ sR, const T* __restrict__ sPar) {
+    const T* wq = terminal ? c.Q : c.hQ;
     const T* xk = sX + k * NX;
-    const T* yr = sY + k * NYS;
-    const T* pr = sPar + k * NPS;
     const bool g = (j == 14);
+    T r[16];
+    Vec4<T>::ld(sR + k * SYS, r[0], r[1], r[2], r[3]);
+    Vec4<T>::ld(sR + k * SYS + 4, r[4], r[5], r[6], r[7]);
+    Vec4<T>::ld(sR + k * SYS + 8, r[8], r[9], r[10], r[11]);
+    Vec4<T>::ld(sR + k * SYS + 12, r[12], r[13], r[14], r[15]);
+    T w, x, y, z;
+    Vec4<T>::ld(sPar + k * NPS, w, x, y, z);
 #pragma unroll
     for (int i = 0; i < 6; i++) {
-        const T yi = (j == i) ? T(1) : (g ? xk[i] - yr[i] : T(0));
-        H[i] += s * c.Q[i] * yi;
+        const T yi = g ? r[i] : ((j == i) ? T(1) : T(0));
+        H[i] += wq[i] * yi;
     }
-    const T w = pr[0], x = pr[1], y = pr[2], z = pr[3];
     T yq[4];
 #pragma unroll
-    for (int n = 0; n < 4; n++) yq[n] = (j == 6 + n) ? T(1) : (g ? xk[6 + n] : T(0));
-    const T d1 = g ? pr[1] - yr[7] : T(0), d2 = g ? pr[2] - yr[8] : T(0), d3 = g ? pr[3] - yr[9] : T(0);
-    const T v1 = c.Q[7] * (-x * yq[0] + w * yq[1] - z * yq[2] + y * yq[3] + d1);
-    const T v2 = c.Q[8] * (-y * yq[0] + z * yq[1] + w * yq[2] - x * yq[3] + d2);
-    const T v3 = c.Q[9] * (-z * yq[0] - y * yq[1] + x * yq[2] + w * yq[3] + d3);
-    H[6] += s * (-x * v1 - y * v2 - z * v3);
-    H[7] += s * (w * v1 + z * v2 - y * v3);
-    H[8] += s * (-z * v1 + w * v2 + x * v3);
-    H[9] += s * (y * v1 - x * v2 + w * v3);
+    for (int n = 0; n < 4; n++) yq[n] = g ? xk[6 + n] : ((j == 6 + n) ? T(1) : T(0));
+    const T d1 = g ? r[7] : T(0), d2 = g ? r[8] : T(0), d3 = g ? r[9] : T(0);
+    const T v1 = wq[7] * (-x * yq[0] + w * yq[1] - z * yq[2] + y * yq[3] + d1);
+    const T v2 = wq[8] * (-y * yq[0] + z * yq[1] + w * yq[2] - x * yq[3] + d2);
+    const T v3 = wq[9] * (-z * yq[0] - y * yq[1] + x * yq[2] + w * yq[3] + d3);
+    H[6] += -x * v1 - y * v2 - z * v3;
+    H[7] += w * v1 + z * v2 - y * v3;
+    H[8] += -z * v1 + w * v2 + x * v3;
+    H[9] += y * v1 - x * v2 + w * v3;
     if (!terminal) {
 #pragma unroll
         for (int m = 0; m < 4; m++) {
-            const T yu = (j == 10 + m) ? T(1) : (g ? sU[k * NU + m] - yr[10 + m] : T(0));
-            H[10 + m] += s * c.R[m] * yu;
+            const T yu = g ? r[10 + m] : ((j == 10 + m) ? T(1) : T(0));
+            H[10 + m] += c.hR[m] * yu;
         }
     }
 }
@@ -230,7 +253,7 @@ __device__ __forceinline__ void backward_terminal(const RtiCfg<T>& c, int N, int
     T H[14];
 #pragma unroll
     for (int i = 0; i < 14; i++) H[i] = T(0);
-    add_cost<T>(H, c, j, N, true, sm + L.oX, sm + L.oU, sm + L.oY, sm + L.oPar);
+    add_cost<T>(H, c, j, N, true, sm + L.oX, sm + L.oY, sm + L.oPar);
     __syncwarp(mask);
     if (j < 10) {
 #pragma unroll
@@ -260,14 +283,17 @@ __device__ __forceinline__ bool backward_stage(const RtiCfg<T>& c, int k, int j,
 #pragma unroll
     for (int r = 0; r < 10; r++) col[r] = colp[r * TLD];
     // W = P+ col (+ p+ on the gradient lane)
-    T W[10];
+    T W[10], spv[12];
+    Vec4<T>::ld(sp, spv[0], spv[1], spv[2], spv[3]);
+    Vec4<T>::ld(sp + 4, spv[4], spv[5], spv[6], spv[7]);
+    Vec4<T>::ld(sp + 8, spv[8], spv[9], spv[10], spv[11]);
 #pragma unroll
     for (int i = 0; i < 10; i++) {
         T p0, p1, p2, p3, p4, p5, p6, p7, p8, p9, pa, pb;
         Vec4<T>::ld(sP + i * 12, p0, p1, p2, p3);
         Vec4<T>::ld(sP + i * 12 + 4, p4, p5, p6, p7);
         Vec4<T>::ld(sP + i * 12 + 8, p8, p9, pa, pb);
-        T acc = (j == 14) ? sp[i] : T(0);
+        T acc = (j == 14) ? spv[i] : T(0);
         acc += p0 * col[0]; acc += p1 * col[1]; acc += p2 * col[2]; acc += p3 * col[3]; acc += p4 * col[4];
         acc += p5 * col[5]; acc += p6 * col[6]; acc += p7 * col[7]; acc += p8 * col[8]; acc += p9 * col[9];
         W[i] = acc;
@@ -288,7 +314,7 @@ __device__ __forceinline__ bool backward_stage(const RtiCfg<T>& c, int k, int j,
         H[6] += a0 * W[r]; H[7] += a1 * W[r]; H[8] += a2 * W[r]; H[9] += a3 * W[r];
         H[10] += a4 * W[r]; H[11] += a5 * W[r]; H[12] += a6 * W[r]; H[13] += a7 * W[r];
     }
-    add_cost<T>(H, c, j, k, false, sX, sU, sm + L.oY, sPar);
+    add_cost<T>(H, c, j, k, false, sX, sm + L.oY, sPar);
     if (kRows) {
         // rows of the un-penalised [Hux Guu] (by symmetry: column 10+m) and g_u, for the multiplier test
         if (j >= 10 && j < 14) {
@@ -358,8 +384,9 @@ __device__ __forceinline__ bool backward_stage(const RtiCfg<T>& c, int k, int j,
             if (i > j) sP[j * 12 + i] = Pn[i];
         }
     } else if (j == 14) {
-#pragma unroll
-        for (int i = 0; i < 10; i++) sp[i] = Pn[i];
+        Vec4<T>::st(sp, Pn[0], Pn[1], Pn[2], Pn[3]);
+        Vec4<T>::st(sp + 4, Pn[4], Pn[5], Pn[6], Pn[7]);
+        Vec4<T>::st(sp + 8, Pn[8], Pn[9], T(0), T(0));
     }
     __syncwarp(mask);
     return ok;
@@ -408,10 +435,15 @@ __device__ __forceinline__ bool backward_sweep(const RtiCfg<T>& c, int N, int j,
                 T* t = (half ? sT1 : sT0) + cj;
 #pragma unroll
                 for (int r = 0; r < 10; r++) t[r * TLD] = sa[r];
-                if (cj == 0) {
+                // b = x+ - X_{k+1}: every lane holds x+; lane cj writes row cj, lanes 0/1 also rows 8/9
+                T b0 = xa[0];
 #pragma unroll
-                    for (int r = 0; r < 10; r++) t[r * TLD + 8] = xa[r] - sX[(kk + 1) * NX + r];
-                }
+                for (int r = 1; r < 8; r++) b0 = (cj == r) ? xa[r] : b0;
+                const T b1 = (cj == 0) ? xa[8] : xa[9];
+                T* tb = (half ? sT1 : sT0) + 8;
+                const T* xn = sX + (kk + 1) * NX;
+                tb[cj * TLD] = b0 - xn[cj];
+                if (cj < 2) tb[(8 + cj) * TLD] = b1 - xn[8 + cj];
             }
             __syncwarp(mask);
             tile_to_ws<T>(sT0, ws + WL.oRec + (long long)k * 14 * TLD, j);
@@ -485,12 +517,14 @@ __device__ __forceinline__ void forward_sweep(const RtiCfg<T>& c, int N, int lan
     }
     bool v_l = false, b_l = false;
     int n_l = 0;
+    T it_cur = kFinal ? itp[0] : T(0);
     for (int k0 = 0; k0 < N; k0 += kPf) {
 #pragma unroll
         for (int u = 0; u < kPf; u++) {
             const int k = k0 + u;
             if (k < N) {
                 T (&cf)[12] = buf[u];
+                const T it_nxt = (kFinal && (k + 1 < N || isx)) ? itp[(k + 1) * its] : T(0);
                 T xj[10];
 #pragma unroll
                 for (int jj = 0; jj < 10; jj++) xj[jj] = __shfl_sync(mask, z, jj, GL);
@@ -511,7 +545,7 @@ __device__ __forceinline__ void forward_sweep(const RtiCfg<T>& c, int N, int lan
                 const T dz = isx ? z : du;
                 if (kFinal) {
                     if (lane < 14) {
-                        const T v = itp[k * its] + dz;
+                        const T v = it_cur + dz;
                         gp[k * its] = v;
                         if (k == 0 && isu && gu0) gu0[lane - 10] = v;
                         b_l |= !(fabs(v) <= T(1e30));
@@ -524,6 +558,7 @@ __device__ __forceinline__ void forward_sweep(const RtiCfg<T>& c, int N, int lan
                     if (lane < 14) sDz[k * 16 + lane] = dz;
                 }
                 z = xn;
+                it_cur = it_nxt;
                 if (k + kPf < N) {
                     const T* r = rec + (long long)(k + kPf) * 14 * TLD;
                     Vec4<T>::ld(r, cf[0], cf[1], cf[2], cf[3]);
@@ -535,7 +570,7 @@ __device__ __forceinline__ void forward_sweep(const RtiCfg<T>& c, int N, int lan
     }
     if (kFinal) {
         if (isx) {
-            const T v = itp[N * its] + z;
+            const T v = it_cur + z;
             gp[N * its] = v;
             b_l |= !(fabs(v) <= T(1e30));
         }
@@ -562,7 +597,7 @@ enum { IPM_LL = 0, IPM_LU, IPM_TL, IPM_TU, IPM_CL, IPM_CU, IPM_ACT };
 constexpr int RTI_CTA = 64;  // threads per CTA of the nominal launch (4 problems)
 
 template <typename T, int kN>
-__global__ void __maxnreg__((sizeof(T) == 4) ? 144 : 255) rti_step_kernel(const RtiCfg<T> c, const RtiArgs<T> a) {
+__global__ void __launch_bounds__(RTI_CTA, (sizeof(T) == 4) ? 8 : 3) rti_step_kernel(const RtiCfg<T> c, const RtiArgs<T> a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int N = (kN > 0) ? kN : c.N;
     const SmemLayout L(N);
@@ -600,62 +635,44 @@ __global__ void __maxnreg__((sizeof(T) == 4) ? 144 : 255) rti_step_kernel(const 
         // ---- stage the problem record in shared memory (asynchronous copies, one wait) ----
         {
             constexpr int E2 = 8 / (int)sizeof(T);  // elements per 8-byte copy (records are 8-byte aligned)
-            if (E2 == 2) {
-                for (int i = lane; i < (N + 1) * NX / 2; i += GL) cp_async<8>(sX + 2 * i, gX + 2 * i);
-                for (int i = lane; i < N * NU / 2; i += GL) cp_async<8>(sU + 2 * i, gU + 2 * i);
-            } else {
-                for (int i = lane; i < (N + 1) * NX; i += GL) cp_async<8>(sX + i, gX + i);
-                for (int i = lane; i < N * NU; i += GL) cp_async<8>(sU + i, gU + i);
-            }
+            T* sY = sm + L.oY;
+            T* sPar = sm + L.oPar;
+            for (int i = lane; i < (N + 1) * NX / E2; i += GL) cp_async<8>(sX + E2 * i, gX + E2 * i);
+            for (int i = lane; i < N * NU / E2; i += GL) cp_async<8>(sU + E2 * i, gU + E2 * i);
             if (a.xr == nullptr) {
                 const T* gY = a.yref + (size_t)prob * (N + 1) * NYS;
                 const T* gP = a.par + (size_t)prob * (N + 1) * NPS;
-                if (E2 == 2) {
-                    for (int i = lane; i < (N + 1) * NYS / 2; i += GL) cp_async<8>(sm + L.oY + 2 * i, gY + 2 * i);
-                    for (int i = lane; i < (N + 1) * NPS / 2; i += GL) cp_async<8>(sm + L.oPar + 2 * i, gP + 2 * i);
-                } else {
-                    for (int i = lane; i < (N + 1) * NYS; i += GL) cp_async<8>(sm + L.oY + i, gY + i);
-                    for (int i = lane; i < (N + 1) * NPS; i += GL) cp_async<8>(sm + L.oPar + i, gP + i);
+                for (int i = lane; i < (N + 1) * (NYS / E2); i += GL) {
+                    const int k = i / (NYS / E2), q = i - k * (NYS / E2);
+                    cp_async<8>(sY + k * SYS + E2 * q, gY + k * NYS + E2 * q);
                 }
+                for (int i = lane; i < (N + 1) * NPS / E2; i += GL) cp_async<8>(sPar + E2 * i, gP + E2 * i);
             } else {
                 // yref_k = [xr_k; ur_k], p_k = [xr_k[6:10]; f_k]   (nmpc_body_rate_ctl.py:95-104)
                 const T* gxr = a.xr + (size_t)prob * (N + 1) * NX;
                 const T* gur = a.ur + (size_t)prob * N * NU;
-                for (int i = lane; i < (N + 1) * 5; i += GL) {  // element pairs (k, 2q), (k, 2q+1)
-                    const int k = i / 5, q = i - k * 5;
-                    if (E2 == 2) {
-                        cp_async<8>(sm + L.oY + k * NYS + 2 * q, gxr + k * NX + 2 * q);
-                        if (q >= 3) cp_async<8>(sm + L.oPar + k * NPS + 2 * q - 6, gxr + k * NX + 2 * q);
-                    } else {
-                        cp_async<8>(sm + L.oY + k * NYS + 2 * q, gxr + k * NX + 2 * q);
-                        cp_async<8>(sm + L.oY + k * NYS + 2 * q + 1, gxr + k * NX + 2 * q + 1);
-                        if (q >= 3) {
-                            cp_async<8>(sm + L.oPar + k * NPS + 2 * q - 6, gxr + k * NX + 2 * q);
-                            cp_async<8>(sm + L.oPar + k * NPS + 2 * q - 5, gxr + k * NX + 2 * q + 1);
-                        }
-                    }
+                for (int i = lane; i < (N + 1) * (NX / E2); i += GL) {
+                    const int k = i / (NX / E2), q = (i - k * (NX / E2)) * E2;
+                    cp_async<8>(sY + k * SYS + q, gxr + k * NX + q);
+                    if (q >= 6) cp_async<8>(sPar + k * NPS + q - 6, gxr + k * NX + q);
                 }
-                for (int i = lane; i < N * 2; i += GL) {
-                    const int k = i >> 1, q = i & 1;
-                    if (E2 == 2) {
-                        cp_async<8>(sm + L.oY + k * NYS + NX + 2 * q, gur + k * NU + 2 * q);
-                    } else {
-                        cp_async<8>(sm + L.oY + k * NYS + NX + 2 * q, gur + k * NU + 2 * q);
-                        cp_async<8>(sm + L.oY + k * NYS + NX + 2 * q + 1, gur + k * NU + 2 * q + 1);
-                    }
+                for (int i = lane; i < N * (NU / E2); i += GL) {
+                    const int k = i / (NU / E2), q = (i - k * (NU / E2)) * E2;
+                    cp_async<8>(sY + k * SYS + NX + q, gur + k * NU + q);
                 }
-                if (lane < NU) sm[L.oY + N * NYS + NX + lane] = T(0);
+                if (lane < NU) sY[N * SYS + NX + lane] = T(0);
                 if (a.f) {
                     const T* gf = a.f + (size_t)prob * (N + 1) * 3;
                     for (int i = lane; i < (N + 1) * 3; i += GL) {
                         const int k = i / 3, m = i - k * 3;
-                        cp_async<(int)sizeof(T)>(sm + L.oPar + k * NPS + 4 + m, gf + i);
+                        cp_async<(int)sizeof(T)>(sPar + k * NPS + 4 + m, gf + i);
                     }
-                    for (int k = lane; k <= N; k += GL) sm[L.oPar + k * NPS + 7] = T(0);
+                    for (int k = lane; k <= N; k += GL) sPar[k * NPS + 7] = T(0);
                 } else {
-                    for (int i = lane; i < (N + 1) * 4; i += GL) sm[L.oPar + (i >> 2) * NPS + 4 + (i & 3)] = T(0);
+                    for (int i = lane; i < (N + 1) * 4; i += GL) sPar[(i >> 2) * NPS + 4 + (i & 3)] = T(0);
                 }
             }
+            for (int i = lane; i < (N + 1) * 2; i += GL) sY[(i >> 1) * SYS + NYS + (i & 1)] = T(0);
         }
         const T x0v = isx ? a.x0[(size_t)prob * NX + lane] : T(0);
         cp_async_wait_all();
@@ -664,9 +681,15 @@ __global__ void __maxnreg__((sizeof(T) == 4) ? 144 : 255) rti_step_kernel(const 
             // persist yref / p as if set stage by stage (a later plain solve or get sees them)
             T* wY = a.yref_w + (size_t)prob * (N + 1) * NYS;
             T* wP = a.par_w + (size_t)prob * (N + 1) * NPS;
-            for (int i = lane; i < (N + 1) * NYS; i += GL) wY[i] = sm[L.oY + i];
+            for (int i = lane; i < (N + 1) * NYS; i += GL) {
+                const int k = i / NYS;
+                wY[i] = sm[L.oY + k * SYS + (i - k * NYS)];
+            }
             for (int i = lane; i < (N + 1) * NPS; i += GL) wP[i] = sm[L.oPar + i];
+            __syncwarp(mask);
         }
+        cost_records<T>(N, lane, sm + L.oY, sX, sU, sm + L.oPar);
+        __syncwarp(mask);
         const T dx0 = isx ? x0v - sX[lane] : T(0);
 
         int status = 0, n_fact = 0, n_ipm = 0, n_pol = 0;
