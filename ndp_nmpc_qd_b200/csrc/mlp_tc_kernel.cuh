@@ -26,11 +26,11 @@ namespace ndp {
 
 constexpr long long MLPT_MIN_ROWS = 2048;  // below this the fp32 CUDA-core kernel is used (latency path)
 constexpr int MLPT_ROWS = 128;
-constexpr int MLPT_THREADS = 128;
+constexpr int MLPT_THREADS = 256;  // per 128-row tile: two threads per row (each owns half of the columns)
 constexpr float MLPT_LO_SCALE = 2048.f;       // 2^11
 constexpr float MLPT_LO_INV = 1.f / 2048.f;
 
-// fp16 operand images (elements): W2 hi, W2 lo [64 x 128], W3 hi, W3 lo [128 x 64]
+// fp16 operand images (elements): [W2 hi; W2 lo] [128 x 128], [W3 hi; W3 lo] [256 x 64]
 constexpr int MLPT_W2_ELEMS = MLP_H2 * MLP_H1;
 constexpr int MLPT_W3_ELEMS = MLP_H3 * MLP_H2;
 constexpr int MLPT_WIMG_ELEMS = 2 * MLPT_W2_ELEMS + 2 * MLPT_W3_ELEMS;
@@ -53,7 +53,8 @@ constexpr int MLPT_ACT_BYTES = 2 * MLPT_ROWS * MLP_H1 * 2;       // h1 hi + lo [
 constexpr int MLPT_A1H = 0, MLPT_A1L = MLPT_ROWS * MLP_H1 * 2;   // offsets inside a group's region
 constexpr int MLPT_A2H = 0, MLPT_A2L = MLPT_ROWS * MLP_H2 * 2;
 constexpr int MLPT_S_PAR = MLPT_S_ACT + MLPT_GROUPS * MLPT_ACT_BYTES;  // fp32 side parameters (MlpSmall image)
-constexpr int MLPT_S_BAR = MLPT_S_PAR + (int)sizeof(MlpSmall);         // 3 mbarriers (24 B) + tmem base (4 B)
+constexpr int MLPT_S_OUT = MLPT_S_PAR + (int)sizeof(MlpSmall);         // layer-4 partial sums of the upper column half [groups][128][4] fp32
+constexpr int MLPT_S_BAR = MLPT_S_OUT + MLPT_GROUPS * MLPT_ROWS * 16;  // 3 mbarriers (24 B) + tmem base (4 B)
 constexpr int MLPT_SMEM = MLPT_S_BAR + 48;
 
 // element offset of (row r, col k) inside a [R x K] K-major no-swizzle operand
@@ -133,14 +134,17 @@ __device__ long long g_mlpt_prof[128];
 
 __device__ __forceinline__ void group_sync(int grp) { asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(MLPT_THREADS) : "memory"); }
 
-// CTA = 2 groups of 128 threads; each group owns a 128-row tile (thread <-> row <-> TMEM lane), its own
-// activation tiles, mbarrier and 256 TMEM columns, so one group's CUDA-core phases overlap the other's
-// MMAs and memory latency.  Features of the next tile are prefetched while the current one computes.
+// CTA = 2 groups of 256 threads; each group owns a 128-row tile, its own activation tiles, mbarrier and
+// 256 TMEM columns, so one group's CUDA-core phases overlap the other's MMAs and memory latency.  Inside
+// a group, threads t and t + 128 share row t (= TMEM lane t: warps w and w + 4 address the same lane
+// quarter) and each owns one half of the columns of every layer.  Features of the next tile are
+// prefetched while the current one computes.
 __global__ void __launch_bounds__(MLPT_CTA_THREADS, 1) mlp_tc_kernel(const __grid_constant__ MlpSmall sp, const __half* __restrict__ wimg, const MlpIo io) {
     extern __shared__ __align__(1024) unsigned char smt[];
     uint64_t* sBar = reinterpret_cast<uint64_t*>(smt + MLPT_S_BAR);
     uint32_t* sTmem = reinterpret_cast<uint32_t*>(smt + MLPT_S_BAR + 32);
-    const int grp = threadIdx.x >> 7, t = threadIdx.x & 127, warp = t >> 5;
+    const int grp = threadIdx.x / MLPT_THREADS, tg = threadIdx.x % MLPT_THREADS, t = tg & 127, hf = tg >> 7, warp = tg >> 5;
+    float4* sOut = reinterpret_cast<float4*>(smt + MLPT_S_OUT) + grp * MLPT_ROWS;
     unsigned char* act = smt + MLPT_S_ACT + grp * MLPT_ACT_BYTES;
     __half* sA1h = reinterpret_cast<__half*>(act + MLPT_A1H);
     __half* sA1l = reinterpret_cast<__half*>(act + MLPT_A1L);
@@ -181,11 +185,11 @@ __global__ void __launch_bounds__(MLPT_CTA_THREADS, 1) mlp_tc_kernel(const __gri
     const uint32_t tmem = *sTmem + grp * 256;
     // layer-2 accumulators alias the front of the layer-3 ones (dead by then)
     const uint32_t tD1m = tmem + 0, tD1c = tmem + 64, tD2m = tmem + 0, tD2c = tmem + 128;
-    const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;  // this warp's TMEM lane quarter
-    const uint32_t aW2h = smem_u32(smt + MLPT_S_W2H), aW2l = smem_u32(smt + MLPT_S_W2L);
-    const uint32_t aW3h = smem_u32(smt + MLPT_S_W3H), aW3l = smem_u32(smt + MLPT_S_W3L);
+    const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;  // this warp's TMEM lane quarter
+    const uint32_t aW2h = smem_u32(smt + MLPT_S_W2H), aW3h = smem_u32(smt + MLPT_S_W3H);
     const uint32_t aA1h = smem_u32(sA1h), aA1l = smem_u32(sA1l), aA2h = smem_u32(sA2h), aA2l = smem_u32(sA2l);
     constexpr uint32_t ID1 = umma_idesc(128, MLP_H2), ID2 = umma_idesc(128, MLP_H3);
+    constexpr uint32_t ID1C = umma_idesc(128, 2 * MLP_H2), ID2C = umma_idesc(128, 2 * MLP_H3);  // concatenated hi|lo operands
     uint32_t phase = 0;
 
     int stamp = 0;
@@ -211,7 +215,7 @@ __global__ void __launch_bounds__(MLPT_CTA_THREADS, 1) mlp_tc_kernel(const __gri
         MLPT_STAMP(stamp++);
         // ---- layer 1 (CUDA cores, fp32) -> h1 hi/lo operand tiles ----
 #pragma unroll 2
-        for (int kb = 0; kb < MLP_H1 / 8; kb++) {
+        for (int kb = hf * (MLP_H1 / 16); kb < (hf + 1) * (MLP_H1 / 16); kb++) {
             float w[48], bb[8], h[8];
             const float4* wp = reinterpret_cast<const float4*>(sq.W1 + kb * 48);
             const float4* bp = reinterpret_cast<const float4*>(sq.b1 + kb * 8);
@@ -247,12 +251,13 @@ __global__ void __launch_bounds__(MLPT_CTA_THREADS, 1) mlp_tc_kernel(const __gri
 #pragma unroll
             for (int ks = 0; ks < MLP_H1 / 16; ks++) {
                 const uint32_t ao = ks * 2 * (MLPT_ROWS / 8) * 128;  // two k-chunks per step
-                const uint32_t bo = ks * 2 * (MLP_H2 / 8) * 128;
+                const uint32_t bo = ks * 2 * (2 * MLP_H2 / 8) * 128;
                 const uint64_t dAh = umma_desc(aA1h + ao, (MLPT_ROWS / 8) * 128, 128), dAl = umma_desc(aA1l + ao, (MLPT_ROWS / 8) * 128, 128);
-                const uint64_t dBh = umma_desc(aW2h + bo, (MLP_H2 / 8) * 128, 128), dBl = umma_desc(aW2l + bo, (MLP_H2 / 8) * 128, 128);
-                umma_f16(tD1m, dAh, dBh, ID1, ks > 0);
-                umma_f16(tD1c, dAh, dBl, ID1, ks > 0);
-                umma_f16(tD1c, dAl, dBh, ID1, 1);
+                // B = [W2_hi; W2_lo] as one 128-row operand: one N=128 MMA fills the main (cols 0..63) and the
+                // first correction term (cols 64..127); the second correction term reuses the hi rows (N=64)
+                const uint64_t dB = umma_desc(aW2h + bo, (2 * MLP_H2 / 8) * 128, 128);
+                umma_f16(tD1m, dAh, dB, ID1C, ks > 0);
+                umma_f16(tD1c, dAl, dB, ID1, 1);
             }
             umma_commit(bar);
           }
@@ -264,8 +269,8 @@ __global__ void __launch_bounds__(MLPT_CTA_THREADS, 1) mlp_tc_kernel(const __gri
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         MLPT_STAMP(stamp++);
         // ---- epilogue 1: h2 = relu(D1 + b2) -> hi/lo operand tiles (over the dead h1 tiles) ----
-#pragma unroll 1
-        for (int c0 = 0; c0 < MLP_H2; c0 += 32) {
+        {
+            const int c0 = hf * 32;
             float m[32], cr[32];
             tmem_ld32(tD1m + lane_sel + c0, m);
             tmem_ld32(tD1c + lane_sel + c0, cr);
@@ -293,12 +298,11 @@ __global__ void __launch_bounds__(MLPT_CTA_THREADS, 1) mlp_tc_kernel(const __gri
 #pragma unroll
             for (int ks = 0; ks < MLP_H2 / 16; ks++) {
                 const uint32_t ao = ks * 2 * (MLPT_ROWS / 8) * 128;
-                const uint32_t bo = ks * 2 * (MLP_H3 / 8) * 128;
+                const uint32_t bo = ks * 2 * (2 * MLP_H3 / 8) * 128;
                 const uint64_t dAh = umma_desc(aA2h + ao, (MLPT_ROWS / 8) * 128, 128), dAl = umma_desc(aA2l + ao, (MLPT_ROWS / 8) * 128, 128);
-                const uint64_t dBh = umma_desc(aW3h + bo, (MLP_H3 / 8) * 128, 128), dBl = umma_desc(aW3l + bo, (MLP_H3 / 8) * 128, 128);
-                umma_f16(tD2m, dAh, dBh, ID2, ks > 0);
-                umma_f16(tD2c, dAh, dBl, ID2, ks > 0);
-                umma_f16(tD2c, dAl, dBh, ID2, 1);
+                const uint64_t dB = umma_desc(aW3h + bo, (2 * MLP_H3 / 8) * 128, 128);  // [W3_hi; W3_lo], 256 rows
+                umma_f16(tD2m, dAh, dB, ID2C, ks > 0);
+                umma_f16(tD2c, dAl, dB, ID2, 1);
             }
             umma_commit(bar);
           }
@@ -310,9 +314,9 @@ __global__ void __launch_bounds__(MLPT_CTA_THREADS, 1) mlp_tc_kernel(const __gri
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         MLPT_STAMP(stamp++);
         // ---- epilogue 2: h3 = relu(D2 + b3); layer 4 (CUDA cores, fp32): out = W4 h3 + b4 ----
-        float o0 = sq.b4[0], o1 = sq.b4[1], o2 = sq.b4[2];
+        float o0 = hf ? 0.f : sq.b4[0], o1 = hf ? 0.f : sq.b4[1], o2 = hf ? 0.f : sq.b4[2];
 #pragma unroll 1
-        for (int c0 = 0; c0 < MLP_H3; c0 += 32) {
+        for (int c0 = hf * 64; c0 < hf * 64 + 64; c0 += 32) {
             float m[32], cr[32];
             tmem_ld32(tD2m + lane_sel + c0, m);
             tmem_ld32(tD2c + lane_sel + c0, cr);
@@ -333,9 +337,13 @@ __global__ void __launch_bounds__(MLPT_CTA_THREADS, 1) mlp_tc_kernel(const __gri
             }
         }
         MLPT_STAMP(stamp++);
-        if (row < io.M) mlp_store_row(io, row, on, o0, o1, o2);
+        if (hf) sOut[t] = make_float4(o0, o1, o2, 0.f);
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         group_sync(grp);
+        if (!hf && row < io.M) {
+            const float4 p = sOut[t];
+            mlp_store_row(io, row, on, o0 + p.x, o1 + p.y, o2 + p.z);
+        }
         MLPT_STAMP(stamp++);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -346,17 +354,18 @@ __global__ void __launch_bounds__(MLPT_CTA_THREADS, 1) mlp_tc_kernel(const __gri
 // host: build the fp16 hi/lo operand images of W2, W3 in UMMA layout and upload them
 inline int mlp_tc_prepare(const float* host_params, void** out) {
     __half* img = new __half[MLPT_WIMG_ELEMS];
-    auto put = [&](const float* W, int R, int K, __half* hi, __half* lo) {
+    // each image is the concatenation [W_hi; W_lo] (2R rows) in UMMA K-major layout
+    auto put = [&](const float* W, int R, int K, __half* dst) {
         for (int r = 0; r < R; r++)
             for (int k = 0; k < K; k++) {
                 const float w = W[r * K + k];
                 const __half h = __float2half_rn(w);
-                hi[umma_off(r, k, R)] = h;
-                lo[umma_off(r, k, R)] = __float2half_rn((w - __half2float(h)) * MLPT_LO_SCALE);
+                dst[umma_off(r, k, 2 * R)] = h;
+                dst[umma_off(R + r, k, 2 * R)] = __float2half_rn((w - __half2float(h)) * MLPT_LO_SCALE);
             }
     };
-    put(host_params + MLP_OW2, MLP_H2, MLP_H1, img, img + MLPT_W2_ELEMS);
-    put(host_params + MLP_OW3, MLP_H3, MLP_H2, img + 2 * MLPT_W2_ELEMS, img + 2 * MLPT_W2_ELEMS + MLPT_W3_ELEMS);
+    put(host_params + MLP_OW2, MLP_H2, MLP_H1, img);
+    put(host_params + MLP_OW3, MLP_H3, MLP_H2, img + 2 * MLPT_W2_ELEMS);
     cudaError_t e = cudaMalloc(out, sizeof(__half) * MLPT_WIMG_ELEMS);
     if (e == cudaSuccess) e = cudaMemcpy(*out, img, sizeof(__half) * MLPT_WIMG_ELEMS, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MLPT_SMEM);

@@ -64,10 +64,11 @@ __host__ __device__ constexpr int al4(int o) { return (o + 3) & ~3; }
 
 // ---- per-problem shared memory layout (elements of T; every region 4-element aligned) ----
 struct SmemLayout {
-    int oX, oU, oY, oPar, oDz, oP, op, oT0, oT1, oHux, total;
+    int oX, oU, oPar, oY, oDz, oP, op, oT0, oT1, oHux, total;  // oY and oDz are adjacent: see forward_sweep
     __host__ __device__ constexpr explicit SmemLayout(int N)
-        : oX(0), oU(al4((N + 1) * NX)), oY(oU + N * NU), oPar(oY + (N + 1) * SYS), oDz(oPar + (N + 1) * NPS),
-          oP(oDz + (N + 1) * 16),  // QP step [k][lane]
+        : oX(0), oU(al4((N + 1) * NX)), oPar(oU + N * NU), oY(oPar + (N + 1) * NPS), oDz(oY + (N + 1) * SYS),
+          // QP step [k][lane]; sY | sDz also hosts the 4 x (14 x TLD) ring of the accepted forward sweep
+          oP(oY + (((N + 1) * (SYS + 16) > 4 * 14 * TLD) ? (N + 1) * (SYS + 16) : 4 * 14 * TLD)),
           op(oP + 10 * 12),        // P+ rows, stride 12; then p+
           oT0(op + 12),            // tile of stage k:   rows r = 0..9 of [A B](:,6..13) | b | pad3, stride TLD
           oT1(oT0 + 10 * TLD),     // tile of stage k-1 (the integrator fills two stages per pass)
@@ -487,88 +488,106 @@ __device__ __forceinline__ bool backward_sweep(const RtiCfg<T>& c, int N, int j,
     return __all_sync(mask, ok);
 }
 
-// Forward substitution: lane i < 10 carries dx_k[i], lanes 10..13 compute du_k[m]; the stage records
-// (3 vectors per lane) are prefetched kPf stages ahead from the L2-resident workspace.
-// kFinal: the step is accepted on the fly -- the new iterate (X + dx, U + du) is written to global
-// memory as it is produced and the box test / NaN test / active count are fused in (flags returned
-// through viol / bad / nact); otherwise the step goes to sDz[k][lane] for the IPM.
+// 4/8/16-byte asynchronous global -> shared copies (LDGSTS): the whole problem record is requested
+// up front and lands while nothing else waits on it
+template <int kBytes>
+__device__ __forceinline__ void cp_async(void* smem_dst, const void* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(d), "l"(gsrc), "n"(kBytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int kPending>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory"); }
+
+constexpr int FW_RING = 4;            // stages of forward-sweep records in flight
+constexpr int FW_REC = 14 * TLD;      // one stage: 14 lanes x TLD
+
+// Forward substitution: lane i < 10 carries dx_k[i], lanes 10..13 compute du_k[m].
+// kFinal (the accepted sweep of the nominal path): the stage records stream from the L2-resident
+// workspace through a FW_RING-deep shared-memory ring (cp.async groups; each lane copies and reads only
+// its own record, so no barrier is needed) laid over the cost records + sDz, which are dead by then; the
+// new iterate (X + dx, U + du) is written to global memory as it is produced and the box test / NaN
+// test / active count are fused in (returned through viol / bad / nact).
+// !kFinal (IPM sweeps): records are register-prefetched and the step goes to sDz[k][lane].
 template <typename T, bool kFinal>
 __device__ __forceinline__ void forward_sweep(const RtiCfg<T>& c, int N, int lane, unsigned mask, T dx0, T* sm, const SmemLayout& L,
                                               const T* ws, const WsLayout& WL, T lo, T hi, T* gX, T* gU, T* gu0, bool& viol, bool& bad,
                                               int& nact) {
-    constexpr int kPf = 4;
     T* sDz = sm + L.oDz;
     const bool isx = lane < 10, isu = (lane >= 10 && lane < 14), isv = (lane >= 3 && lane < 6);
     const T* rec = ws + WL.oRec + (long long)((lane < 14) ? lane : 13) * TLD;
-    // iterate value / destination of the variable this lane owns
-    const T* itp = isx ? sm + L.oX + lane : sm + L.oU + ((lane - 10) & 3);
-    T* gp = isx ? gX + lane : gU + ((lane - 10) & 3);
-    const int its = isx ? NX : NU;
     T z = isx ? dx0 : T(0);
-    T buf[kPf][12];
+    // one stage: consumes this lane's record cf, the iterate value it_cur (kFinal)
+    auto stage = [&](int k, const T (&cf)[12], T& du_out) {
+        T xj[10];
 #pragma unroll
-    for (int u = 0; u < kPf; u++) {
-        if (u < N) {
-            const T* r = rec + (long long)u * 14 * TLD;
-            Vec4<T>::ld(r, buf[u][0], buf[u][1], buf[u][2], buf[u][3]);
-            Vec4<T>::ld(r + 4, buf[u][4], buf[u][5], buf[u][6], buf[u][7]);
-            Vec4<T>::ld(r + 8, buf[u][8], buf[u][9], buf[u][10], buf[u][11]);
+        for (int jj = 0; jj < 10; jj++) xj[jj] = __shfl_sync(mask, z, jj, GL);
+        const T zv = __shfl_sync(mask, z, (lane + 3) & 15, GL);
+        T du = cf[10], du2 = T(0);
+#pragma unroll
+        for (int jj = 0; jj < 5; jj++) {
+            du += cf[jj] * xj[jj];
+            du2 += cf[5 + jj] * xj[5 + jj];
         }
-    }
-    bool v_l = false, b_l = false;
-    int n_l = 0;
-    T it_cur = kFinal ? itp[0] : T(0);
-    for (int k0 = 0; k0 < N; k0 += kPf) {
+        du += du2;
+        T um[4];
 #pragma unroll
-        for (int u = 0; u < kPf; u++) {
-            const int k = k0 + u;
-            if (k < N) {
-                T (&cf)[12] = buf[u];
-                const T it_nxt = (kFinal && (k + 1 < N || isx)) ? itp[(k + 1) * its] : T(0);
-                T xj[10];
+        for (int m = 0; m < 4; m++) um[m] = __shfl_sync(mask, du, 10 + m, GL);
+        T xn = cf[8] + ((lane < 3) ? z + c.h * zv : ((lane < 6) ? z : T(0)));
+        xn += cf[0] * xj[6] + cf[1] * xj[7] + cf[2] * xj[8] + cf[3] * xj[9];
+        xn += cf[4] * um[0] + cf[5] * um[1] + cf[6] * um[2] + cf[7] * um[3];
+        du_out = isx ? z : du;
+        z = xn;
+    };
+    if (kFinal) {
+        const T* itp = isx ? sm + L.oX + lane : sm + L.oU + ((lane - 10) & 3);
+        T* gp = isx ? gX + lane : gU + ((lane - 10) & 3);
+        const int its = isx ? NX : NU;
+        T* ring = sm + L.oY + ((lane < 14) ? lane : 13) * TLD;  // [FW_RING][14][TLD] over sY | sDz
+        auto issue = [&](int k) {
+            if (k < N && lane < 14) {
+                const T* r = rec + (long long)k * FW_REC;
+                T* d = ring + (k % FW_RING) * FW_REC;
 #pragma unroll
-                for (int jj = 0; jj < 10; jj++) xj[jj] = __shfl_sync(mask, z, jj, GL);
-                const T zv = __shfl_sync(mask, z, (lane + 3) & 15, GL);
-                T du = cf[10], du2 = T(0);
-#pragma unroll
-                for (int jj = 0; jj < 5; jj++) {
-                    du += cf[jj] * xj[jj];
-                    du2 += cf[5 + jj] * xj[5 + jj];
-                }
-                du += du2;
-                T um[4];
-#pragma unroll
-                for (int m = 0; m < 4; m++) um[m] = __shfl_sync(mask, du, 10 + m, GL);
-                T xn = cf[8] + ((lane < 3) ? z + c.h * zv : ((lane < 6) ? z : T(0)));
-                xn += cf[0] * xj[6] + cf[1] * xj[7] + cf[2] * xj[8] + cf[3] * xj[9];
-                xn += cf[4] * um[0] + cf[5] * um[1] + cf[6] * um[2] + cf[7] * um[3];
-                const T dz = isx ? z : du;
-                if (kFinal) {
-                    if (lane < 14) {
-                        const T v = it_cur + dz;
-                        gp[k * its] = v;
-                        if (k == 0 && isu && gu0) gu0[lane - 10] = v;
-                        b_l |= !(fabs(v) <= T(1e30));
-                        if (isu || (isv && k >= 1)) {
-                            v_l |= !(v >= lo && v <= hi);
-                            n_l += (v <= lo) + (v >= hi);
-                        }
-                    }
-                } else {
-                    if (lane < 14) sDz[k * 16 + lane] = dz;
-                }
-                z = xn;
-                it_cur = it_nxt;
-                if (k + kPf < N) {
-                    const T* r = rec + (long long)(k + kPf) * 14 * TLD;
-                    Vec4<T>::ld(r, cf[0], cf[1], cf[2], cf[3]);
-                    Vec4<T>::ld(r + 4, cf[4], cf[5], cf[6], cf[7]);
-                    Vec4<T>::ld(r + 8, cf[8], cf[9], cf[10], cf[11]);
+                for (int q = 0; q < 3; q++) {
+                    if (sizeof(T) == 4) cp_async<16>(d + 4 * q, r + 4 * q);
+                    else { cp_async<16>(d + 4 * q, r + 4 * q); cp_async<16>(d + 4 * q + 2, r + 4 * q + 2); }
                 }
             }
+            cp_async_commit();
+        };
+        __syncwarp(mask);  // every lane is done with the cost records
+#pragma unroll
+        for (int u = 0; u < FW_RING; u++) issue(u);
+        bool v_l = false, b_l = false;
+        int n_l = 0;
+        T it_cur = itp[0];
+        for (int k = 0; k < N; k++) {
+            const T it_nxt = (k + 1 < N || isx) ? itp[(k + 1) * its] : T(0);
+            cp_async_wait<FW_RING - 1>();
+            T cf[12];
+            const T* d = ring + (k % FW_RING) * FW_REC;
+            Vec4<T>::ld(d, cf[0], cf[1], cf[2], cf[3]);
+            Vec4<T>::ld(d + 4, cf[4], cf[5], cf[6], cf[7]);
+            Vec4<T>::ld(d + 8, cf[8], cf[9], cf[10], cf[11]);
+            issue(k + FW_RING);
+            T dz;
+            stage(k, cf, dz);
+            if (lane < 14) {
+                const T v = it_cur + dz;
+                gp[k * its] = v;
+                if (k == 0 && isu && gu0) gu0[lane - 10] = v;
+                b_l |= !(fabs(v) <= T(1e30));
+                if (isu || (isv && k >= 1)) {
+                    v_l |= !(v >= lo && v <= hi);
+                    n_l += (v <= lo) + (v >= hi);
+                }
+            }
+            it_cur = it_nxt;
         }
-    }
-    if (kFinal) {
+        cp_async_wait<0>();
         if (isx) {
             const T v = it_cur + z;
             gp[N * its] = v;
@@ -578,19 +597,38 @@ __device__ __forceinline__ void forward_sweep(const RtiCfg<T>& c, int N, int lan
         bad = __any_sync(mask, b_l);
         nact = n_l;
     } else {
+        constexpr int kPf = 2;
+        T buf[kPf][12];
+#pragma unroll
+        for (int u = 0; u < kPf; u++) {
+            if (u < N) {
+                const T* r = rec + (long long)u * FW_REC;
+                Vec4<T>::ld(r, buf[u][0], buf[u][1], buf[u][2], buf[u][3]);
+                Vec4<T>::ld(r + 4, buf[u][4], buf[u][5], buf[u][6], buf[u][7]);
+                Vec4<T>::ld(r + 8, buf[u][8], buf[u][9], buf[u][10], buf[u][11]);
+            }
+        }
+        for (int k0 = 0; k0 < N; k0 += kPf) {
+#pragma unroll
+            for (int u = 0; u < kPf; u++) {
+                const int k = k0 + u;
+                if (k < N) {
+                    T dz;
+                    stage(k, buf[u], dz);
+                    if (lane < 14) sDz[k * 16 + lane] = dz;
+                    if (k + kPf < N) {
+                        const T* r = rec + (long long)(k + kPf) * FW_REC;
+                        Vec4<T>::ld(r, buf[u][0], buf[u][1], buf[u][2], buf[u][3]);
+                        Vec4<T>::ld(r + 4, buf[u][4], buf[u][5], buf[u][6], buf[u][7]);
+                        Vec4<T>::ld(r + 8, buf[u][8], buf[u][9], buf[u][10], buf[u][11]);
+                    }
+                }
+            }
+        }
         if (isx) sDz[N * 16 + lane] = z;
     }
     __syncwarp(mask);
 }
-
-// 4/8/16-byte asynchronous global -> shared copies (LDGSTS): the whole problem record is requested
-// up front and lands while nothing else waits on it
-template <int kBytes>
-__device__ __forceinline__ void cp_async(void* smem_dst, const void* gsrc) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(d), "l"(gsrc), "n"(kBytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 enum { IPM_LL = 0, IPM_LU, IPM_TL, IPM_TU, IPM_CL, IPM_CU, IPM_ACT };
 
@@ -708,6 +746,17 @@ __global__ void __launch_bounds__(RTI_CTA, (sizeof(T) == 4) ? 8 : 3) rti_step_ke
         const bool nominal = ok && !viol;
 
         if (ok && viol) {
+            {   // the accepted-sweep ring overwrote the cost records: rebuild them from the stored yref
+                const T* gY = (a.xr != nullptr ? a.yref_w : a.yref) + (size_t)prob * (N + 1) * NYS;
+                T* sY = sm + L.oY;
+                for (int i = lane; i < (N + 1) * SYS; i += GL) {
+                    const int k = i >> 4, e = i & 15;
+                    sY[i] = (e < NYS) ? gY[k * NYS + e] : T(0);
+                }
+                __syncwarp(mask);
+                cost_records<T>(N, lane, sY, sX, sU, sm + L.oPar);
+                __syncwarp(mask);
+            }
             // ================= Mehrotra IPM on the Riccati kernel =================
             T* wI = ws + WL.oIpm;
             T* wZ = ws + WL.oZc;
