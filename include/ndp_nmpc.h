@@ -192,6 +192,31 @@ int ndp_pipeline_wait(ndp_pipeline* p, int slot);   /* blocks until the slot's u
 int ndp_pipeline_bytes(const ndp_pipeline* p, int64_t* h2d_bytes_per_step, int64_t* d2h_bytes_per_step);
 void* ndp_pipeline_stream(ndp_pipeline* p);         /* the compute stream (cudaStream_t) */
 
+/* ---- batched dop_sim quadrotor plant (closed-loop rollouts) ----
+ * dop_sim/scripts/quadrotor/mul_quadrotors.py:19-50 MulQuadrotors(num_agent, ts_sim, ts_control, float64,
+ * has_downwash, has_motor_model, has_battery).forward(ts_sim, ego_states[n,35,1], body_rate_cmd[n,4,1]).
+ * state_dev: double [n][35] (index map params/def_mul_states.py:10-31), updated IN PLACE like the
+ * reference; cmd_dev: double [n][4] = (roll, pitch, yaw rate [rad/s], throttle 0..1).
+ * group: the pairwise downwash (a_dynamics/qd_dynamics.py:161-198) couples agents of the same contiguous
+ * block of `group` agents (<= 0 or n: all pairs, the reference; smaller: independent Monte-Carlo scenarios). */
+typedef struct ndp_plant ndp_plant;
+int ndp_plant_create(int64_t n, double ts_sim, double ts_ctl, int has_downwash, int has_motor_model, int has_battery,
+                     int64_t group, ndp_plant** out);
+int ndp_plant_destroy(ndp_plant* p);
+int ndp_plant_reset(ndp_plant* p, void* stream); /* PID states, control / simulation clocks */
+/* MulQuadrotors.forward: autopilot when the control clock says so (every call while ctl_t > ts_ctl), then dynamics */
+int ndp_plant_forward(ndp_plant* p, double ts_sim, double* state_dev, const double* cmd_dev, void* stream);
+/* b_autopilot/atp_rate.py:60-112 AtpRate.forward (PID rate loops pid_control.py:36-65): stores the rotor commands */
+int ndp_plant_autopilot(ndp_plant* p, const double* state_dev, const double* cmd_dev, double all_sim_t, void* stream);
+/* a_dynamics/qd_dynamics.py:75-98 QdDynamics.forward with the stored rotor commands */
+int ndp_plant_dynamics(ndp_plant* p, double dt, double* state_dev, void* stream);
+/* pt_pub/pt_publisher.py:106-122 odom_2_nmpc_x: plant state -> NMPC x0 [n][10] = (p, v, qw, qx, qy, qz) in `precision` */
+int ndp_plant_nmpc_x0(int64_t n, const double* state_dev, int precision, void* x0_dev, void* stream);
+/* nmpc_node.py:273-283 nmpc_u_2_att_tgt: cmd = (u0[0:3], u0[3] * mass / k_throttle)  (thrust 0 if k_throttle == 0) */
+int ndp_plant_cmd_from_u0(int64_t n, int precision, const void* u0_dev, double mass, double k_throttle, double* cmd_dev,
+                          void* stream);
+int64_t ndp_plant_launch_count(const ndp_plant* p);
+
 #ifdef __cplusplus
 }
 #endif

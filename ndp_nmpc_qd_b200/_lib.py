@@ -23,6 +23,8 @@ EXPORTS = [
     "ndp_mlp_launch_count", "ndp_mlp_forward_pairs_ex",
     "ndp_pipeline_create", "ndp_pipeline_destroy", "ndp_pipeline_buffers", "ndp_pipeline_submit", "ndp_pipeline_wait",
     "ndp_pipeline_bytes", "ndp_pipeline_stream",
+    "ndp_plant_create", "ndp_plant_destroy", "ndp_plant_reset", "ndp_plant_forward", "ndp_plant_autopilot", "ndp_plant_dynamics",
+    "ndp_plant_nmpc_x0", "ndp_plant_cmd_from_u0", "ndp_plant_launch_count",
 ]
 
 
@@ -89,6 +91,19 @@ def load() -> C.CDLL:
     lib.ndp_pipeline_stream.argtypes = [vp]
     lib.ndp_pipeline_stream.restype = vp
     lib.ndp_mlp_launch_count.restype = i64
+    lib.ndp_plant_create.argtypes = [i64, dbl, dbl, i32, i32, i32, i64, C.POINTER(vp)]
+    lib.ndp_plant_destroy.argtypes = [vp]
+    lib.ndp_plant_reset.argtypes = [vp, vp]
+    lib.ndp_plant_forward.argtypes = [vp, dbl, vp, vp, vp]
+    lib.ndp_plant_autopilot.argtypes = [vp, vp, vp, dbl, vp]
+    lib.ndp_plant_dynamics.argtypes = [vp, dbl, vp, vp]
+    lib.ndp_plant_nmpc_x0.argtypes = [i64, vp, i32, vp, vp]
+    lib.ndp_plant_cmd_from_u0.argtypes = [i64, i32, vp, dbl, dbl, vp, vp]
+    lib.ndp_plant_launch_count.argtypes = [vp]
+    lib.ndp_plant_launch_count.restype = i64
+    for name in ("ndp_plant_create", "ndp_plant_destroy", "ndp_plant_reset", "ndp_plant_forward", "ndp_plant_autopilot",
+                 "ndp_plant_dynamics", "ndp_plant_nmpc_x0", "ndp_plant_cmd_from_u0"):
+        getattr(lib, name).restype = C.c_int
     for name in ("ndp_create", "ndp_destroy", "ndp_set", "ndp_get", "ndp_reset", "ndp_set_reference", "ndp_solve", "ndp_update",
                  "ndp_status", "ndp_stats", "ndp_rk4_sens", "ndp_mlp_create", "ndp_mlp_destroy",
                  "ndp_mlp_forward_pairs", "ndp_mlp_forward_rows", "ndp_mlp_forward_swarm", "ndp_mlp_forward_pairs_ex",

@@ -715,3 +715,144 @@ int ndp_pipeline_bytes(const ndp_pipeline* p, int64_t* h2d, int64_t* d2h) {
 void* ndp_pipeline_stream(ndp_pipeline* p) { return p ? (void*)p->s_cmp : nullptr; }
 
 }  // extern "C"
+
+// ======================= batched dop_sim plant =======================
+#include "plant_kernel.cuh"
+
+struct ndp_plant {
+    ndp::PlantCfg pc;
+    ndp::AutopilotCfg ac;
+    int has_battery;
+    double ts_ctl, ctl_t, all_sim_t;  // mul_quadrotors.py:33-36
+    double *pid, *delta, *pos;
+    std::atomic<long long> launches;
+    std::mutex mu;
+};
+
+extern "C" {
+
+int ndp_plant_create(int64_t n, double ts_sim, double ts_ctl, int has_downwash, int has_motor_model, int has_battery, int64_t group,
+                     ndp_plant** out) {
+    if (!out || n < 1 || ts_sim <= 0 || ts_ctl <= 0) return fail(NDP_E_ARG, "ndp_plant_create: bad argument");
+    if (group <= 0 || group > n) group = n;
+    ndp_plant* p = new ndp_plant();
+    p->launches = 0;
+    p->has_battery = has_battery;
+    p->ts_ctl = ts_ctl; p->ctl_t = 999.0; p->all_sim_t = 0.0;
+    // params/physical_param.py:34-95
+    const double l_frame = 0.1372, alpha = 45.0 * M_PI / 180.0, ixx = 0.0094, iyy = 0.0134, izz = 0.0145, ixz = 0.0;
+    const double k_q = 3.7611e-10 * 1e6, k_t = 2.8158e-08 * 1e6, ls = l_frame * sin(alpha), lc = l_frame * cos(alpha);
+    const double gam = ixx * izz - ixz * ixz;
+    ndp::PlantCfg& c = p->pc;
+    c.n = n; c.group = group; c.dt = ts_sim; c.motor_alpha = exp(-ts_sim / 0.0840);
+    c.has_downwash = has_downwash; c.has_motor = has_motor_model;
+    c.mass = 1.4844; c.gravity = 9.81; c.iyy = iyy;
+    c.g1 = (ixz * (ixx - iyy + izz)) / gam; c.g2 = (izz * (izz - iyy) + ixz * ixz) / gam; c.g3 = izz / gam; c.g4 = ixz / gam;
+    c.g5 = (izz - ixx) / iyy; c.g6 = ixz / iyy; c.g7 = ((ixx - iyy) * ixx + ixz * ixz) / gam; c.g8 = ixx / gam;
+    c.o_min = 2600.0 / 1000; c.o_max = 24000.0 / 1000; c.o_min_sat = (double)(float)c.o_min; c.o_max_sat = (double)(float)c.o_max;
+    c.k_t = k_t; c.kd_x = 0.26; c.kd_y = 0.28; c.kd_z = 0.42; c.k_h = 0.01;
+    c.dw_h = 1.5; c.dw_v = 4; c.rp = 0.0775; c.k_d1 = 4000; c.k_d2 = 0.65; c.k_d3 = -0.10;
+    c.half_pi_f32 = (double)(float)M_PI / 2;
+    const double G1[16] = {1, 1, 1, 1, -ls, ls, ls, -ls, -lc, lc, -lc, lc, -k_q / k_t, -k_q / k_t, k_q / k_t, k_q / k_t};
+    for (int i = 0; i < 16; i++) c.G1[i] = G1[i];
+    // params/control_param.py:17-57, atp_rate.py:22-57, pid_control.py:14-24
+    ndp::AutopilotCfg& a = p->ac;
+    a.n = n; a.ts_ctl = ts_ctl; a.voltage_cf = 1.0; a.k_th = 17.666; a.b_th = -1.206; a.k_t = k_t; a.u_limit = 999.0;
+    const double sigma = 0.05, tsf = ts_ctl / 0.02;
+    a.a1 = (2.0 * sigma - ts_ctl) / (2.0 * sigma + ts_ctl); a.a2 = 2.0 / (2.0 * sigma + ts_ctl);
+    const double kp[3] = {0.3, 0.3, 0.13};
+    for (int i = 0; i < 3; i++) { a.kp[i] = kp[i]; a.ki[i] = 0.01 / tsf; a.kd[i] = 0.005 * tsf; }
+    const double csc = 1 / (4 * l_frame * sin(alpha)), sec = 1 / (4 * l_frame * cos(alpha)), kk = k_t / (4 * k_q);
+    const double Gi[16] = {0.25, -csc, -sec, -kk, 0.25, csc, sec, -kk, 0.25, csc, -sec, kk, 0.25, -csc, sec, kk};
+    for (int i = 0; i < 16; i++) a.G1inv[i] = Gi[i];
+    p->pid = p->delta = p->pos = nullptr;
+    bool ok = cudaMalloc((void**)&p->pid, sizeof(double) * n * 9) == cudaSuccess && cudaMalloc((void**)&p->delta, sizeof(double) * n * 4) == cudaSuccess &&
+              cudaMalloc((void**)&p->pos, sizeof(double) * n * 3) == cudaSuccess;
+    if (!ok) { ndp_plant_destroy(p); return fail(NDP_E_ALLOC, "ndp_plant_create: cudaMalloc failed"); }
+    cudaMemset(p->pid, 0, sizeof(double) * n * 9);
+    cudaMemset(p->delta, 0, sizeof(double) * n * 4);
+    *out = p;
+    return 0;
+}
+
+int ndp_plant_destroy(ndp_plant* p) {
+    if (!p) return 0;
+    cudaFree(p->pid); cudaFree(p->delta); cudaFree(p->pos);
+    delete p;
+    return 0;
+}
+
+int ndp_plant_reset(ndp_plant* p, void* stream) {
+    if (!p) return fail(NDP_E_ARG, "ndp_plant_reset: null");
+    std::lock_guard<std::mutex> lk(p->mu);
+    p->ctl_t = 999.0; p->all_sim_t = 0.0;
+    CU(cudaMemsetAsync(p->pid, 0, sizeof(double) * p->pc.n * 9, (cudaStream_t)stream));
+    CU(cudaMemsetAsync(p->delta, 0, sizeof(double) * p->pc.n * 4, (cudaStream_t)stream));
+    return 0;
+}
+
+int ndp_plant_autopilot(ndp_plant* p, const double* state, const double* cmd, double all_sim_t, void* stream) {
+    if (!p || !state || !cmd) return fail(NDP_E_ARG, "ndp_plant_autopilot: null argument");
+    ndp::AutopilotCfg a = p->ac;
+    a.voltage_cf = p->has_battery ? (4.2 - all_sim_t / 705.0 * (4.2 - 3.6)) / 4.2 : 1.0;  // atp_rate.py:86-90
+    const int grd = (int)((a.n + 127) / 128);
+    ndp::plant_autopilot_kernel<<<grd, 128, 0, (cudaStream_t)stream>>>(a, state, cmd, p->pid, p->delta);
+    p->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int ndp_plant_dynamics(ndp_plant* p, double dt, double* state, void* stream) {
+    if (!p || !state) return fail(NDP_E_ARG, "ndp_plant_dynamics: null argument");
+    ndp::PlantCfg c = p->pc;
+    c.dt = dt;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (c.has_downwash) {
+        ndp::plant_snapshot_kernel<<<(int)((c.n + 255) / 256), 256, 0, st>>>(c.n, state, p->pos);
+        p->launches++;
+    }
+    const int grd = (int)((c.n + ndp::PL_THREADS - 1) / ndp::PL_THREADS);
+    ndp::plant_step_kernel<<<grd, ndp::PL_THREADS, 0, st>>>(c, state, p->delta, p->pos);
+    p->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int ndp_plant_forward(ndp_plant* p, double ts_sim, double* state, const double* cmd, void* stream) {
+    if (!p || !state || !cmd) return fail(NDP_E_ARG, "ndp_plant_forward: null argument");
+    std::lock_guard<std::mutex> lk(p->mu);
+    if (p->ctl_t > p->ts_ctl) {  // mul_quadrotors.py:41-43
+        int rc = ndp_plant_autopilot(p, state, cmd, p->all_sim_t, stream);
+        if (rc) return rc;
+        p->ctl_t = 0.0;
+    }
+    int rc = ndp_plant_dynamics(p, ts_sim, state, stream);
+    if (rc) return rc;
+    p->ctl_t += ts_sim;
+    p->all_sim_t += ts_sim;
+    return 0;
+}
+
+int ndp_plant_nmpc_x0(int64_t n, const double* state, int precision, void* x0, void* stream) {
+    if (!state || !x0 || n < 0) return fail(NDP_E_ARG, "ndp_plant_nmpc_x0: bad argument");
+    if (n == 0) return 0;
+    const int grd = (int)((n + 255) / 256);
+    if (precision == NDP_F32) ndp::plant_nmpc_x0_kernel<float><<<grd, 256, 0, (cudaStream_t)stream>>>(n, state, (float*)x0);
+    else ndp::plant_nmpc_x0_kernel<double><<<grd, 256, 0, (cudaStream_t)stream>>>(n, state, (double*)x0);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int ndp_plant_cmd_from_u0(int64_t n, int precision, const void* u0, double mass, double k_throttle, double* cmd, void* stream) {
+    if (!u0 || !cmd || n < 0) return fail(NDP_E_ARG, "ndp_plant_cmd_from_u0: bad argument");
+    if (n == 0) return 0;
+    const int grd = (int)((n + 255) / 256);
+    if (precision == NDP_F32) ndp::plant_cmd_from_u0_kernel<float><<<grd, 256, 0, (cudaStream_t)stream>>>(n, (const float*)u0, mass, k_throttle, cmd);
+    else ndp::plant_cmd_from_u0_kernel<double><<<grd, 256, 0, (cudaStream_t)stream>>>(n, (const double*)u0, mass, k_throttle, cmd);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int64_t ndp_plant_launch_count(const ndp_plant* p) { return p ? (int64_t)p->launches.load() : 0; }
+
+}  // extern "C"
