@@ -217,6 +217,25 @@ int ndp_plant_cmd_from_u0(int64_t n, int precision, const void* u0_dev, double m
                           void* stream);
 int64_t ndp_plant_launch_count(const ndp_plant* p);
 
+/* ---- batched NMPC reference generation ----
+ * ndp_nmpc/scripts/pt_pub/: NMPCRefPublisher.get_nmpc_pts (pt_publisher.py:78-103) = piecewise polynomial
+ * evaluation (base_pt_publisher.py:81-148) + diff_flatness (pt_publisher.py:188-248) + traj_full_pt_2_x_u
+ * (:124-147), for B problems at once and without leaving the device.
+ * create: HOST arrays holding n_traj TrajCoefficients messages (ndp_nmpc/msg/TrajCoefficients.msg):
+ *   seg_off [n_traj+1] (first segment index of each trajectory), t_cum: per trajectory n_seg+1 knot times,
+ *   concatenated; cx, cy, cz [total_seg][8], cyaw [total_seg][4] ascending powers of the normalised segment
+ *   time; final_pt [n_traj][3].
+ * horizon: xr[b][k] / ur[b][k] = reference at t0[b] + k * th_pred of trajectory traj_id[b] (NULL: 0), position
+ *   shifted by offset[b][0:3] (NULL: none; formation offsets, nmpc_follower_node.py:44-74).  t0 double [B],
+ *   xr [B][N+1][10], ur [B][N][4] in `precision`. */
+typedef struct ndp_refgen ndp_refgen;
+int ndp_refgen_create(int32_t n_traj, const int32_t* seg_off, const double* t_cum, const double* cx, const double* cy,
+                      const double* cz, const double* cyaw, const double* final_pt, ndp_refgen** out);
+int ndp_refgen_destroy(ndp_refgen* g);
+int ndp_refgen_horizon(ndp_refgen* g, int precision, int64_t B, const int32_t* traj_id_dev, const double* t0_dev, int32_t N,
+                       double th_pred, const double* offset_dev, void* xr_dev, void* ur_dev, void* stream);
+int64_t ndp_refgen_launch_count(const ndp_refgen* g);
+
 #ifdef __cplusplus
 }
 #endif

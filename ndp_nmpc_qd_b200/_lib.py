@@ -25,6 +25,7 @@ EXPORTS = [
     "ndp_pipeline_bytes", "ndp_pipeline_stream",
     "ndp_plant_create", "ndp_plant_destroy", "ndp_plant_reset", "ndp_plant_forward", "ndp_plant_autopilot", "ndp_plant_dynamics",
     "ndp_plant_nmpc_x0", "ndp_plant_cmd_from_u0", "ndp_plant_launch_count",
+    "ndp_refgen_create", "ndp_refgen_destroy", "ndp_refgen_horizon", "ndp_refgen_launch_count",
 ]
 
 
@@ -101,6 +102,14 @@ def load() -> C.CDLL:
     lib.ndp_plant_cmd_from_u0.argtypes = [i64, i32, vp, dbl, dbl, vp, vp]
     lib.ndp_plant_launch_count.argtypes = [vp]
     lib.ndp_plant_launch_count.restype = i64
+    ip, dp = C.POINTER(C.c_int32), C.POINTER(C.c_double)
+    lib.ndp_refgen_create.argtypes = [i32, ip, dp, dp, dp, dp, dp, dp, C.POINTER(vp)]
+    lib.ndp_refgen_destroy.argtypes = [vp]
+    lib.ndp_refgen_horizon.argtypes = [vp, i32, i64, vp, vp, i32, dbl, vp, vp, vp, vp]
+    lib.ndp_refgen_launch_count.argtypes = [vp]
+    lib.ndp_refgen_launch_count.restype = i64
+    for name in ("ndp_refgen_create", "ndp_refgen_destroy", "ndp_refgen_horizon"):
+        getattr(lib, name).restype = C.c_int
     for name in ("ndp_plant_create", "ndp_plant_destroy", "ndp_plant_reset", "ndp_plant_forward", "ndp_plant_autopilot",
                  "ndp_plant_dynamics", "ndp_plant_nmpc_x0", "ndp_plant_cmd_from_u0"):
         getattr(lib, name).restype = C.c_int

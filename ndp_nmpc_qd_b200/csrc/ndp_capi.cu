@@ -856,3 +856,76 @@ int ndp_plant_cmd_from_u0(int64_t n, int precision, const void* u0, double mass,
 int64_t ndp_plant_launch_count(const ndp_plant* p) { return p ? (int64_t)p->launches.load() : 0; }
 
 }  // extern "C"
+
+// ======================= batched reference generation =======================
+#include "refgen_kernel.cuh"
+
+struct ndp_refgen {
+    ndp::RefGenTable tb;
+    int* d_seg_off;
+    double *d_t_cum, *d_cxyz, *d_cyaw, *d_final;
+    std::atomic<long long> launches;
+};
+
+extern "C" {
+
+int ndp_refgen_create(int32_t n_traj, const int32_t* seg_off, const double* t_cum, const double* cx, const double* cy, const double* cz,
+                      const double* cyaw, const double* final_pt, ndp_refgen** out) {
+    if (!out || n_traj < 1 || !seg_off || !t_cum || !cx || !cy || !cz || !cyaw || !final_pt) return fail(NDP_E_ARG, "ndp_refgen_create: bad argument");
+    const int total = seg_off[n_traj];
+    if (total < n_traj) return fail(NDP_E_ARG, "ndp_refgen_create: every trajectory needs at least one segment");
+    ndp_refgen* g = new ndp_refgen();
+    g->launches = 0;
+    g->d_seg_off = nullptr; g->d_t_cum = g->d_cxyz = g->d_cyaw = g->d_final = nullptr;
+    double* cxyz = new double[(size_t)total * 24];
+    for (int s = 0; s < total; s++)
+        for (int j = 0; j < 8; j++) {
+            cxyz[(s * 3 + 0) * 8 + j] = cx[s * 8 + j];
+            cxyz[(s * 3 + 1) * 8 + j] = cy[s * 8 + j];
+            cxyz[(s * 3 + 2) * 8 + j] = cz[s * 8 + j];
+        }
+    bool ok = cudaMalloc((void**)&g->d_seg_off, sizeof(int) * (n_traj + 1)) == cudaSuccess &&
+              cudaMalloc((void**)&g->d_t_cum, sizeof(double) * (total + n_traj)) == cudaSuccess &&
+              cudaMalloc((void**)&g->d_cxyz, sizeof(double) * total * 24) == cudaSuccess &&
+              cudaMalloc((void**)&g->d_cyaw, sizeof(double) * total * 4) == cudaSuccess &&
+              cudaMalloc((void**)&g->d_final, sizeof(double) * n_traj * 3) == cudaSuccess;
+    ok = ok && cudaMemcpy(g->d_seg_off, seg_off, sizeof(int) * (n_traj + 1), cudaMemcpyHostToDevice) == cudaSuccess &&
+         cudaMemcpy(g->d_t_cum, t_cum, sizeof(double) * (total + n_traj), cudaMemcpyHostToDevice) == cudaSuccess &&
+         cudaMemcpy(g->d_cxyz, cxyz, sizeof(double) * total * 24, cudaMemcpyHostToDevice) == cudaSuccess &&
+         cudaMemcpy(g->d_cyaw, cyaw, sizeof(double) * total * 4, cudaMemcpyHostToDevice) == cudaSuccess &&
+         cudaMemcpy(g->d_final, final_pt, sizeof(double) * n_traj * 3, cudaMemcpyHostToDevice) == cudaSuccess;
+    delete[] cxyz;
+    if (!ok) { ndp_refgen_destroy(g); return fail(NDP_E_ALLOC, "ndp_refgen_create: allocation / upload failed"); }
+    g->tb.n_traj = n_traj; g->tb.seg_off = g->d_seg_off; g->tb.t_cum = g->d_t_cum; g->tb.cxyz = g->d_cxyz; g->tb.cyaw = g->d_cyaw;
+    g->tb.final_pt = g->d_final;
+    *out = g;
+    return 0;
+}
+
+int ndp_refgen_destroy(ndp_refgen* g) {
+    if (!g) return 0;
+    cudaFree(g->d_seg_off); cudaFree(g->d_t_cum); cudaFree(g->d_cxyz); cudaFree(g->d_cyaw); cudaFree(g->d_final);
+    delete g;
+    return 0;
+}
+
+int ndp_refgen_horizon(ndp_refgen* g, int precision, int64_t B, const int32_t* traj_id, const double* t0, int32_t N, double th_pred,
+                       const double* offset, void* xr, void* ur, void* stream) {
+    if (!g || B < 0 || N < 1 || th_pred <= 0) return fail(NDP_E_ARG, "ndp_refgen_horizon: bad argument");
+    if (precision != NDP_F32 && precision != NDP_F64) return fail(NDP_E_ARG, "ndp_refgen_horizon: bad precision");
+    if (B == 0) return 0;  // empty batch: nothing to do (pointers may be null)
+    if (!t0 || !xr || !ur) return fail(NDP_E_ARG, "ndp_refgen_horizon: null argument");
+    const long long tot = (long long)B * (N + 1);
+    const int grd = (int)((tot + 127) / 128);
+    if (precision == NDP_F32)
+        ndp::refgen_horizon_kernel<float><<<grd, 128, 0, (cudaStream_t)stream>>>(g->tb, B, traj_id, t0, N, th_pred, offset, 1.4844, 9.81, (float*)xr, (float*)ur);
+    else
+        ndp::refgen_horizon_kernel<double><<<grd, 128, 0, (cudaStream_t)stream>>>(g->tb, B, traj_id, t0, N, th_pred, offset, 1.4844, 9.81, (double*)xr, (double*)ur);
+    g->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int64_t ndp_refgen_launch_count(const ndp_refgen* g) { return g ? (int64_t)g->launches.load() : 0; }
+
+}  // extern "C"
