@@ -1,0 +1,82 @@
+"""Closed-loop batched rollouts entirely on the device (BASELINE.json config 5): for B independent
+scenarios, per 50 Hz control step
+    reference horizon (RefGen, pt_pub)  ->  controller.update (Engine: one SQP-RTI step, [+ downwash MLP])
+    ->  AttitudeTarget mapping (nmpc_node.py:273-283)  ->  plant steps (MulQuadrotors, dop_sim)  ->  odometry -> x0
+mirroring the ROS wiring nmpc_node.py <-> dop_qd_node.py without the host in
+the loop.  Everything is a kernel of libndp_nmpc_b200.so; torch only owns the buffers.
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from .dop_sim import MulQuadrotors
+from .params import nmpc_params as CP
+from .solver import Engine
+from .traj_gen.min_snap import Trajectory
+from .traj_gen.refgen import RefGen
+
+MASS, GRAVITY = 1.4844, 9.81
+# throttle that makes the plant hover: 4 (k_th thr + b_th) = m g (atp_rate.py:92, control_param.py:19-20);
+# k_throttle = m g / thr_hover is what the reference's HoverThrottleEstimator converges to
+THR_HOVER = (MASS * GRAVITY / 4 + 1.206) / 17.666
+K_THROTTLE = MASS * GRAVITY / THR_HOVER
+
+
+class ClosedLoop:
+    def __init__(self, trajectories: Sequence[Trajectory], traj_id: np.ndarray, t_start: np.ndarray, N: int = CP.N_node,
+                 precision: str = "f32", ts_sim: float = 0.01, ts_ctl_plant: float = 0.01, ts_nmpc: float = CP.ts_nmpc,
+                 offset: Optional[np.ndarray] = None, has_motor_model: bool = True, has_battery: bool = False,
+                 has_downwash: bool = False, group: int = 1, k_throttle: float = K_THROTTLE, device="cuda:0", **engine_overrides):
+        self.device = torch.device(device)
+        B = len(traj_id)
+        self.B, self.N, self.ts_sim, self.ts_nmpc = B, N, ts_sim, ts_nmpc
+        self.sim_per_ctl = int(round(ts_nmpc / ts_sim))
+        self.k_throttle = float(k_throttle)
+        self.dtype = torch.float32 if precision == "f32" else torch.float64
+        dev = self.device
+        self.refgen = RefGen(trajectories, device=dev)
+        self.engine = Engine(batch=B, N=N, np_=4, precision=precision, device=dev, **engine_overrides)
+        self.plant = MulQuadrotors(B, ts_sim, ts_ctl_plant, torch.float64, has_downwash, has_motor_model, has_battery, group=group, device=dev)
+        self.traj_id = torch.as_tensor(np.asarray(traj_id, dtype=np.int32), device=dev)
+        self.t = torch.as_tensor(np.asarray(t_start, dtype=np.float64), device=dev)
+        self.offset = None if offset is None else torch.as_tensor(np.asarray(offset, dtype=np.float64), device=dev).contiguous()
+        self.xr = torch.empty((B, N + 1, 10), dtype=self.dtype, device=dev)
+        self.ur = torch.empty((B, N, 4), dtype=self.dtype, device=dev)
+        self.x0 = torch.empty((B, 10), dtype=self.dtype, device=dev)
+        self.u0 = torch.empty((B, 4), dtype=self.dtype, device=dev)
+        self.cmd = torch.zeros((B, 4, 1), dtype=torch.float64, device=dev)
+        self.state = torch.zeros((B, 35, 1), dtype=torch.float64, device=dev)
+        self.reset_to_reference()
+
+    def reset_to_reference(self):
+        """plant on the reference at t (rotors at hover speed), iterate = reference horizon (controller.reset)."""
+        self.refgen.horizon(self.t, self.traj_id, self.N, CP.th_pred, self.offset, xr=self.xr, ur=self.ur)
+        s = self.state
+        s.zero_()
+        x = self.xr[:, 0].to(torch.float64)
+        s[:, 3:6, 0] = x[:, 0:3]; s[:, 13:16, 0] = x[:, 3:6]; s[:, 9:13, 0] = x[:, 6:10]
+        s[:, 31:35, 0] = float(np.sqrt(MASS * GRAVITY / 4 / (2.8158e-08 * 1e6)))  # hover rotor speed [kRPM]
+        self.plant.reset()
+        self.engine.reset(self.xr, self.ur)
+
+    def step(self):
+        """one control period: returns nothing; self.u0 / self.state hold the latest command and plant state."""
+        self.refgen.horizon(self.t, self.traj_id, self.N, CP.th_pred, self.offset, xr=self.xr, ur=self.ur)
+        self.plant.nmpc_x0(self.state, self.x0)
+        self.engine.update(self.x0, self.xr, self.ur, None, self.u0)
+        self.plant.cmd_from_u0(self.u0, self.cmd, MASS, self.k_throttle)
+        for _ in range(self.sim_per_ctl):
+            self.plant(self.ts_sim, self.state, self.cmd)
+        self.t.add_(self.ts_nmpc)
+
+    def position_error(self) -> torch.Tensor:
+        """|p - p_ref(t)| per scenario, against the reference at the current time."""
+        xr, _ = self.refgen.horizon(self.t, self.traj_id, 1, CP.th_pred, self.offset, dtype=torch.float64)
+        return (self.state[:, 3:6, 0] - xr[:, 0, 0:3]).norm(dim=1)
+
+    @property
+    def launch_count(self) -> int:
+        return self.engine.launch_count + self.plant.launch_count + self.refgen.launch_count
