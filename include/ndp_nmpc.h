@@ -167,6 +167,15 @@ int ndp_mlp_forward_swarm(ndp_mlp* m, int precision, int64_t n_all, int64_t ego_
                           int32_t n_nodes, const float* traj_dev, const float* odom_xy_dev, double r_horiz,
                           void* out_dev, int path, void* stream);
 
+/* Same, with the trajectory tensor split in n_parts (<= 16) equal contiguous parts of part_rows quads that may
+ * live on different GPUs: part_ptrs is a HOST array of device pointers, part r holding rows
+ * [r * part_rows, (r+1) * part_rows) -- the local shard and the peers' shards mapped over NVLink (symmetric
+ * memory).  The kernels read neighbour horizons directly from the owning GPU: the exchange of the coupled
+ * swarm is fused into the gated feature construction instead of a separate all-gather. */
+int ndp_mlp_forward_swarm_parts(ndp_mlp* m, int precision, int32_t n_parts, const float* const* part_ptrs, int64_t part_rows,
+                                int64_t n_all, int64_t ego_begin, int64_t n_ego, int32_t n_nodes, const float* odom_xy_dev,
+                                double r_horiz, void* out_dev, int path, void* stream);
+
 int64_t ndp_mlp_launch_count(const ndp_mlp* m);
 
 /* ---- host-buffer step pipeline ----

@@ -20,7 +20,7 @@ EXPORTS = [
     "ndp_default_config", "ndp_create", "ndp_destroy", "ndp_set", "ndp_get", "ndp_reset", "ndp_set_reference",
     "ndp_solve", "ndp_update", "ndp_status", "ndp_stats", "ndp_launch_count", "ndp_last_error", "ndp_rk4_sens",
     "ndp_mlp_create", "ndp_mlp_destroy", "ndp_mlp_forward_pairs", "ndp_mlp_forward_rows", "ndp_mlp_forward_swarm",
-    "ndp_mlp_launch_count", "ndp_mlp_forward_pairs_ex",
+    "ndp_mlp_launch_count", "ndp_mlp_forward_pairs_ex", "ndp_mlp_forward_swarm_parts",
     "ndp_pipeline_create", "ndp_pipeline_destroy", "ndp_pipeline_buffers", "ndp_pipeline_submit", "ndp_pipeline_wait",
     "ndp_pipeline_bytes", "ndp_pipeline_stream",
     "ndp_plant_create", "ndp_plant_destroy", "ndp_plant_reset", "ndp_plant_forward", "ndp_plant_autopilot", "ndp_plant_dynamics",
@@ -82,6 +82,8 @@ def load() -> C.CDLL:
     lib.ndp_mlp_forward_rows.argtypes = [vp, i64, vp, vp, i32, vp]
     lib.ndp_mlp_forward_swarm.argtypes = [vp, i32, i64, i64, i64, i32, vp, vp, dbl, vp, i32, vp]
     lib.ndp_mlp_launch_count.argtypes = [vp]
+    lib.ndp_mlp_forward_swarm_parts.argtypes = [vp, i32, i32, C.POINTER(vp), i64, i64, i64, i64, i32, vp, dbl, vp, i32, vp]
+    lib.ndp_mlp_forward_swarm_parts.restype = C.c_int
     lib.ndp_mlp_forward_pairs_ex.argtypes = [vp, i32, i64, i32, vp, vp, i32, vp, dbl, vp, i32, i32, vp]
     lib.ndp_pipeline_create.argtypes = [vp, vp, dbl, i32, C.POINTER(vp)]
     lib.ndp_pipeline_destroy.argtypes = [vp]

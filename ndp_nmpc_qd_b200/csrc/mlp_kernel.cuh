@@ -23,6 +23,19 @@ constexpr int MLP_OW4 = MLP_OB3 + MLP_H3;
 constexpr int MLP_OB4 = MLP_OW4 + MLP_OUT * MLP_H3;
 constexpr int MLP_NPARAM = MLP_OB4 + 4;  // 17 860 floats
 
+// The swarm's trajectory tensor traj[n_all][n_nodes][6] fp32, possibly split in equal contiguous parts that
+// live on different GPUs: p[r] is the base of rows [r * part_rows, (r + 1) * part_rows) -- local memory or a
+// peer GPU's buffer mapped over NVLink (symmetric memory), read directly by the kernels below.
+constexpr int MLP_MAX_PARTS = 16;
+struct TrajParts {
+    const float* p[MLP_MAX_PARTS];
+    int n_parts, part_rows;
+    __device__ __forceinline__ const float* row(int j, int n_nodes) const {
+        const int r = j / part_rows;
+        return p[r] + (long long)(j - r * part_rows) * n_nodes * 6;
+    }
+};
+
 // How rows are produced / consumed.
 struct MlpIo {
     // mode 0: rows given directly, in[M][6] fp32
@@ -39,7 +52,7 @@ struct MlpIo {
     const void* other;
     const void* gate_xy;
     double r2;
-    const float* traj;
+    TrajParts tp;
     const int2* pairs;  // (ego_global, other_global)
     int prof;           // debug: record phase timestamps of CTA 0 (mlp_tc_kernel)
     void* out;          // mode 0: float [M][3]; mode 1: precision [P][n_nodes][3]; mode 2: float [n_pairs][n_nodes][3]
@@ -82,8 +95,8 @@ __device__ __forceinline__ bool mlp_fetch_row(const MlpIo& io, long long row, fl
         const long long p = row / io.n_nodes;
         const int k = (int)(row - p * io.n_nodes);
         const int2 pr = io.pairs[p];
-        const float* e = io.traj + ((long long)pr.x * io.n_nodes + k) * 6;
-        const float* o = io.traj + ((long long)pr.y * io.n_nodes + k) * 6;
+        const float* e = io.tp.row(pr.x, io.n_nodes) + k * 6;
+        const float* o = io.tp.row(pr.y, io.n_nodes) + k * 6;
 #pragma unroll
         for (int i = 0; i < 6; i++) x[i] = o[i] - e[i];
         return true;
@@ -229,35 +242,44 @@ __global__ void __launch_bounds__(MLPF_THREADS, 1) mlp_fp32_kernel(const float* 
 }
 
 // ---- swarm support: neighbour lists and ordered reduction ----
-// count / fill gated neighbours of each ego (deterministic order: ascending j)
-__global__ void swarm_count_kernel(const float* __restrict__ traj, const float* __restrict__ odom_xy, int n_all, int ego_begin,
-                                   int n_ego, int n_nodes, float r2, int* __restrict__ counts) {
+// count / fill gated neighbours of each ego (deterministic order: ascending j).  The node-0 positions of
+// all quads stream through shared memory tiles, so every (possibly remote) position is read once per CTA.
+constexpr int SWARM_TILE = 1024;
+template <bool kFill>
+__global__ void swarm_neighbours_kernel(const TrajParts tp, const float* __restrict__ odom_xy, int n_all, int ego_begin, int n_ego, int n_nodes,
+                                        float r2, int* __restrict__ counts, const int* __restrict__ offsets, int2* __restrict__ pairs) {
+    __shared__ float2 sxy[SWARM_TILE];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_ego) return;
+    const bool act = i < n_ego;
     const int gi = ego_begin + i;
-    const float ex = odom_xy ? odom_xy[i * 2] : traj[(long long)gi * n_nodes * 6];
-    const float ey = odom_xy ? odom_xy[i * 2 + 1] : traj[(long long)gi * n_nodes * 6 + 1];
-    int cnt = 0;
-    for (int j = 0; j < n_all; j++) {
-        if (j == gi) continue;
-        const float dx = traj[(long long)j * n_nodes * 6] - ex, dy = traj[(long long)j * n_nodes * 6 + 1] - ey;
-        cnt += (dx * dx + dy * dy < r2);
+    float ex = 0.f, ey = 0.f;
+    if (act) {
+        const float* me = tp.row(gi, n_nodes);
+        ex = odom_xy ? odom_xy[i * 2] : me[0];
+        ey = odom_xy ? odom_xy[i * 2 + 1] : me[1];
     }
-    counts[i] = cnt;
-}
-__global__ void swarm_fill_kernel(const float* __restrict__ traj, const float* __restrict__ odom_xy, int n_all, int ego_begin,
-                                  int n_ego, int n_nodes, float r2, const int* __restrict__ offsets, int2* __restrict__ pairs) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_ego) return;
-    const int gi = ego_begin + i;
-    const float ex = odom_xy ? odom_xy[i * 2] : traj[(long long)gi * n_nodes * 6];
-    const float ey = odom_xy ? odom_xy[i * 2 + 1] : traj[(long long)gi * n_nodes * 6 + 1];
-    int o = offsets[i];
-    for (int j = 0; j < n_all; j++) {
-        if (j == gi) continue;
-        const float dx = traj[(long long)j * n_nodes * 6] - ex, dy = traj[(long long)j * n_nodes * 6 + 1] - ey;
-        if (dx * dx + dy * dy < r2) pairs[o++] = make_int2(gi, j);
+    int cnt = 0, o = (kFill && act) ? offsets[i] : 0;
+    for (int j0 = 0; j0 < n_all; j0 += SWARM_TILE) {
+        const int m = min(SWARM_TILE, n_all - j0);
+        __syncthreads();
+        for (int e = threadIdx.x; e < m; e += blockDim.x) {
+            const float* q = tp.row(j0 + e, n_nodes);
+            sxy[e] = make_float2(q[0], q[1]);
+        }
+        __syncthreads();
+        if (act) {
+            for (int e = 0; e < m; e++) {
+                const int j = j0 + e;
+                if (j == gi) continue;
+                const float dx = sxy[e].x - ex, dy = sxy[e].y - ey;
+                if (dx * dx + dy * dy < r2) {
+                    if (kFill) pairs[o++] = make_int2(gi, j);
+                    else cnt++;
+                }
+            }
+        }
     }
+    if (!kFill && act) counts[i] = cnt;
 }
 // exclusive scan of counts[n] -> offsets[n+1] (single CTA; n <= a few 10^5)
 __global__ void swarm_scan_kernel(const int* __restrict__ counts, int n, int* __restrict__ offsets) {

@@ -520,12 +520,20 @@ int ndp_mlp_forward_pairs_ex(ndp_mlp* m, int precision, int64_t P, int32_t n_nod
     return mlp_run(m, io, path, (cudaStream_t)stream);
 }
 
-int ndp_mlp_forward_swarm(ndp_mlp* m, int precision, int64_t n_all, int64_t ego_begin, int64_t n_ego, int32_t n_nodes, const float* traj,
-                          const float* odom_xy, double r_horiz, void* out, int path, void* stream) {
-    if (!m || !traj || !out || n_all < 1 || n_ego < 0 || ego_begin < 0 || ego_begin + n_ego > n_all || n_nodes < 1)
+int ndp_mlp_forward_swarm_parts(ndp_mlp* m, int precision, int32_t n_parts, const float* const* part_ptrs, int64_t part_rows, int64_t n_all,
+                                int64_t ego_begin, int64_t n_ego, int32_t n_nodes, const float* odom_xy, double r_horiz, void* out, int path,
+                                void* stream) {
+    if (!m || !part_ptrs || !out || n_parts < 1 || n_parts > MLP_MAX_PARTS || part_rows < 1 || n_all < 1 || n_all > (int64_t)n_parts * part_rows ||
+        n_ego < 0 || ego_begin < 0 || ego_begin + n_ego > n_all || n_nodes < 1)
         return fail(NDP_E_ARG, "ndp_mlp_forward_swarm: bad argument");
     if (precision != NDP_F32 && precision != NDP_F64) return fail(NDP_E_ARG, "ndp_mlp_forward_swarm: bad precision");
     if (n_ego == 0) return 0;
+    TrajParts tp{};
+    tp.n_parts = n_parts; tp.part_rows = (int)part_rows;
+    for (int r = 0; r < n_parts; r++) {
+        if (!part_ptrs[r]) return fail(NDP_E_ARG, "ndp_mlp_forward_swarm: null part pointer");
+        tp.p[r] = part_ptrs[r];
+    }
     std::lock_guard<std::mutex> lk(m->mu);
     cudaStream_t st = (cudaStream_t)stream;
     if (n_ego > m->cap_ego) {
@@ -536,7 +544,7 @@ int ndp_mlp_forward_swarm(ndp_mlp* m, int precision, int64_t n_all, int64_t ego_
     }
     const float r2 = (float)(r_horiz * r_horiz);
     const int blk = 128, grd = (int)((n_ego + blk - 1) / blk);
-    swarm_count_kernel<<<grd, blk, 0, st>>>(traj, odom_xy, (int)n_all, (int)ego_begin, (int)n_ego, n_nodes, r2, m->counts);
+    swarm_neighbours_kernel<false><<<grd, blk, 0, st>>>(tp, odom_xy, (int)n_all, (int)ego_begin, (int)n_ego, n_nodes, r2, m->counts, nullptr, nullptr);
     swarm_scan_kernel<<<1, 1024, 0, st>>>(m->counts, (int)n_ego, m->offsets);
     m->launches += 2;
     int n_pairs = 0;
@@ -556,11 +564,11 @@ int ndp_mlp_forward_swarm(ndp_mlp* m, int precision, int64_t n_all, int64_t ego_
         m->cap_rows = m->cap_pairs * n_nodes;
     }
     if (n_pairs > 0) {
-        swarm_fill_kernel<<<grd, blk, 0, st>>>(traj, odom_xy, (int)n_all, (int)ego_begin, (int)n_ego, n_nodes, r2, m->offsets, m->pairs);
+        swarm_neighbours_kernel<true><<<grd, blk, 0, st>>>(tp, odom_xy, (int)n_all, (int)ego_begin, (int)n_ego, n_nodes, r2, nullptr, m->offsets, m->pairs);
         m->launches++;
         MlpIo io{};
         io.mode = 2; io.precision = NDP_F32; io.n_nodes = n_nodes; io.M = (long long)n_pairs * n_nodes;
-        io.traj = traj; io.pairs = m->pairs; io.out = m->fpair;
+        io.tp = tp; io.pairs = m->pairs; io.out = m->fpair;
         int rc = mlp_run(m, io, path, st);
         if (rc) return rc;
     }
@@ -571,6 +579,13 @@ int ndp_mlp_forward_swarm(ndp_mlp* m, int precision, int64_t n_all, int64_t ego_
     m->launches++;
     CU(cudaGetLastError());
     return 0;
+}
+
+int ndp_mlp_forward_swarm(ndp_mlp* m, int precision, int64_t n_all, int64_t ego_begin, int64_t n_ego, int32_t n_nodes, const float* traj,
+                          const float* odom_xy, double r_horiz, void* out, int path, void* stream) {
+    if (!traj) return fail(NDP_E_ARG, "ndp_mlp_forward_swarm: bad argument");
+    const float* parts[1] = {traj};
+    return ndp_mlp_forward_swarm_parts(m, precision, 1, parts, n_all > 0 ? n_all : 1, n_all, ego_begin, n_ego, n_nodes, odom_xy, r_horiz, out, path, stream);
 }
 
 int64_t ndp_mlp_launch_count(const ndp_mlp* m) { return m ? (int64_t)m->launches.load() : 0; }

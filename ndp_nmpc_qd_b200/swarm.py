@@ -1,0 +1,99 @@
+"""Coupled swarm (BASELINE.json config 4): egos sharded over the ranks of one node, one exchange of reference
+horizons per RTI step for the downwash features, nothing else crosses GPUs.
+
+Reference semantics generalised: the reference's leader evaluates the MLP against ONE neighbour whose
+reference horizon arrives as a PredXU message (ndp_nmpc_leader_node.py:60-76, nmpc_node.py:116-133); here
+every ego sums the MLP force over all neighbours inside the 1 m horizontal gate.
+
+Two exchange modes, same results:
+  "p2p"        each rank writes its [n_local, N+1, 6] fp32 horizons into a symmetric-memory buffer; after one
+               device-side barrier the gating / MLP kernels read the peers' shards directly over NVLink
+               (ndp_mlp_forward_swarm_parts): the transfer is fused into the feature construction.
+  "allgather"  NCCL all_gather into a local [n_all, N+1, 6] buffer, then the same kernels on local memory
+               (the baseline the fused mode is measured against).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+from .dnwash_nn_est import DownwashNN
+from .params import downwash_params as DP
+from .solver import Engine
+
+
+def shard_bounds(n_all: int, world: int, rank: int):
+    """Equal contiguous shards (the last ranks may be padded): returns (part_rows, begin, end)."""
+    part = (n_all + world - 1) // world
+    b = min(n_all, rank * part)
+    return part, b, min(n_all, b + part)
+
+
+def pack_horizons(xr: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """[n, N+1, 10] state horizons -> [n, N+1, 6] fp32 positions + velocities (the columns DownwashNN reads)."""
+    out.copy_(xr[:, :, 0:6])
+    return out
+
+
+class SwarmStep:
+    def __init__(self, n_all: int, N: int = 20, precision: str = "f32", mode: str = "p2p", device=None, group=None):
+        import torch.distributed as dist
+
+        self.dist = dist
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.group = group
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.n_all, self.N = n_all, N
+        self.part, self.begin, self.end = shard_bounds(n_all, self.world, self.rank)
+        self.n_local = self.end - self.begin
+        self.mode = mode if self.world > 1 else "local"
+        self.dtype = torch.float32 if precision == "f32" else torch.float64
+        self.engine = Engine(batch=max(self.n_local, 1), N=N, np_=7, precision=precision, device=self.device)
+        self.nn = DownwashNN(device=self.device)
+        self.f = torch.zeros((max(self.n_local, 1), N + 1, 3), dtype=self.dtype, device=self.device)
+        self.step_no = 0
+        shape = (2, self.part, N + 1, 6)  # double-buffered by step parity: one barrier per step is enough
+        if self.mode == "p2p":
+            import torch.distributed._symmetric_memory as symm
+
+            self.buf = symm.empty(shape, dtype=torch.float32, device=self.device)
+            self.hdl = symm.rendezvous(self.buf, dist.group.WORLD if group is None else group)
+            esz = self.part * (N + 1) * 6 * 4
+            self._ptrs = [[int(p) + par * esz for p in self.hdl.buffer_ptrs] for par in (0, 1)]
+        else:
+            self.buf = torch.zeros(shape, dtype=torch.float32, device=self.device)
+            self.gathered = torch.zeros((self.world * self.part, N + 1, 6), dtype=torch.float32, device=self.device)
+        self.buf.zero_()
+
+    def forces(self, xr_local: torch.Tensor, odom_xy: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """xr_local [n_local, N+1, 10]: this rank's reference horizons.  Returns f [n_local, N+1, 3]."""
+        par = self.step_no & 1
+        self.step_no += 1
+        mine = self.buf[par]
+        if self.n_local:
+            pack_horizons(xr_local, mine[: self.n_local])
+        if self.mode == "p2p":
+            self.hdl.barrier(channel=par)  # every shard of this parity is written; peers are done with its previous use
+            parts, part_rows = self._ptrs[par], self.part
+        elif self.mode == "allgather":
+            self.dist.all_gather_into_tensor(self.gathered, mine, group=self.group)
+            parts, part_rows = [self.gathered.data_ptr()], self.world * self.part
+        else:
+            parts, part_rows = [mine.data_ptr()], self.part
+        if self.n_local:
+            ptrs = (C.c_void_p * len(parts))(*parts)
+            _lib.check(self.nn.lib.ndp_mlp_forward_swarm_parts(
+                self.nn._h, _lib.NDP_F32 if self.dtype == torch.float32 else _lib.NDP_F64, len(parts), ptrs, part_rows, self.n_all,
+                self.begin, self.n_local, self.N + 1, None if odom_xy is None else C.c_void_p(odom_xy.data_ptr()), float(DP.r_horiz),
+                C.c_void_p(self.f.data_ptr()), 0, C.c_void_p(torch.cuda.current_stream().cuda_stream)), "ndp_mlp_forward_swarm_parts")
+        return self.f
+
+    def step(self, x0: torch.Tensor, xr: torch.Tensor, ur: torch.Tensor, odom_xy: Optional[torch.Tensor] = None,
+             u0: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """one RTI step of the local egos: exchange + gated all-pairs MLP + NDP-NMPC update."""
+        f = self.forces(xr, odom_xy)
+        return self.engine.update(x0, xr, ur, f, u0)

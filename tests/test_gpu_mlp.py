@@ -133,3 +133,29 @@ def test_tc_swarm(nn, mlp_weights):
     f = nn.forward_swarm(torch.as_tensor(traj, device="cuda"), 0, n_all, path=nn.PATH_TENSOR).cpu().numpy()
     ref = mlp_numpy.swarm_forces(mlp_weights, traj, 0, n_all)
     assert np.abs(f - ref).max() < 2e-4  # sum over up to 4 neighbours
+
+
+def test_swarm_parts_equal_single_buffer(nn, mlp_weights):
+    """the multi-part entry point (peer shards in the multi-GPU run; here 4 slices of local memory, the last
+    one ragged) gives exactly the single-buffer result and matches the oracle."""
+    import ctypes as C
+
+    from ndp_nmpc_qd_b200 import _lib
+
+    rng = np.random.default_rng(5)
+    n_all, n, part = 150, 21, 40
+    traj = (rng.normal(size=(n_all, n, 6)) * np.array([1.2, 1.2, 1.0, 0.5, 0.5, 0.5])).astype(np.float32)
+    t = torch.as_tensor(traj, device="cuda")
+    padded = torch.zeros((4 * part, n, 6), dtype=torch.float32, device="cuda")
+    padded[:n_all] = t
+    chunks = [padded[r * part:(r + 1) * part].clone() for r in range(4)]  # four separate allocations
+    ptrs = (C.c_void_p * 4)(*[c.data_ptr() for c in chunks])
+    for ego_begin, n_ego in [(0, n_all), (40, 40), (120, 30)]:
+        out = torch.empty((n_ego, n, 3), dtype=torch.float32, device="cuda")
+        _lib.check(nn.lib.ndp_mlp_forward_swarm_parts(nn._h, _lib.NDP_F32, 4, ptrs, part, n_all, ego_begin, n_ego, n, None, 1.0,
+                                                      C.c_void_p(out.data_ptr()), nn.PATH_FP32, None), "parts")
+        single = nn.forward_swarm(t, ego_begin, n_ego, path=nn.PATH_FP32)
+        torch.cuda.synchronize()
+        assert torch.equal(out, single)
+        ref = mlp_numpy.swarm_forces(mlp_weights, traj, ego_begin, n_ego)
+        assert np.abs(out.cpu().numpy() - ref).max() < 5e-5

@@ -1,0 +1,113 @@
+"""Coupled swarm on several GPUs of one node (BASELINE.json config 4): correctness of the fused peer-memory
+exchange against the NCCL all-gather baseline and the CPU oracle, and step timings of both.
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node=N --master-addr 127.0.0.1 tools/swarm_multi_gpu.py [--quads 1024]"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+from ndp_nmpc_qd_b200 import traj_gen  # noqa: E402
+from ndp_nmpc_qd_b200.swarm import SwarmStep  # noqa: E402
+from ndp_nmpc_qd_b200.traj_gen.refgen import RefGen  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--quads", type=int, default=1024)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--check", action="store_true")
+    ap.add_argument("--breakdown", action="store_true")
+    a = ap.parse_args()
+    rank, world, lr = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(lr)
+    dev = torch.device("cuda", lr)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n_all = a.quads
+    # 32 x 32 lattice, 0.8 m pitch, altitude U(0.5, 3.5), phase-shifted eight_low
+    side = int(np.ceil(np.sqrt(n_all)))
+    rng = np.random.default_rng(0)
+    off = np.stack([(np.arange(n_all) % side) * 0.8, (np.arange(n_all) // side) * 0.8, rng.uniform(0.0, 3.0, n_all)], 1)
+    t0 = rng.uniform(0, 20.0, n_all)
+    tr = traj_gen.plan_named("eight_low")
+    rg = RefGen([tr], device=dev)
+    res = {}
+    f_by_mode = {}
+    for mode in (["p2p", "allgather"] if world > 1 else ["local"]):
+        sw = SwarmStep(n_all, mode=mode, device=dev)
+        b, e = sw.begin, sw.end
+        t_loc = torch.as_tensor(t0[b:e], device=dev)
+        off_loc = torch.as_tensor(off[b:e], device=dev).contiguous()
+        xr, ur = rg.horizon(t_loc, None, 20, 0.1, off_loc)
+        x0 = xr[:, 0].contiguous()
+        sw.engine.reset(xr, ur)
+        u0 = torch.empty((e - b, 4), dtype=torch.float32, device=dev)
+        for _ in range(5):
+            sw.step(x0, xr, ur, None, u0)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(a.steps):
+            t_loc.add_(0.02)
+            rg.horizon(t_loc, None, 20, 0.1, off_loc, xr=xr, ur=ur)
+            sw.step(x0, xr, ur, None, u0)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        res[mode] = dict(ms_per_step=float(ms) / a.steps, quad_steps_per_s=n_all * a.steps / (float(ms) * 1e-3))
+        f_by_mode[mode] = sw.f[: e - b].clone()
+        if a.breakdown:
+            import time
+
+            def timed(fn, n=30):
+                torch.cuda.synchronize()
+                if world > 1:
+                    dist.barrier()
+                t_ = time.perf_counter()
+                for _ in range(n):
+                    fn()
+                torch.cuda.synchronize()
+                return (time.perf_counter() - t_) / n * 1e6
+
+            bd = dict(refgen_us=timed(lambda: rg.horizon(t_loc, None, 20, 0.1, off_loc, xr=xr, ur=ur)),
+                      forces_us=timed(lambda: sw.forces(xr)), update_us=timed(lambda: sw.engine.update(x0, xr, ur, sw.f[: e - b] if e - b == sw.f.shape[0] else sw.f, u0)))
+            if mode == "p2p":
+                bd["barrier_us"] = timed(lambda: sw.hdl.barrier(channel=0))
+            if mode == "allgather":
+                bd["all_gather_us"] = timed(lambda: dist.all_gather_into_tensor(sw.gathered, sw.buf[0]))
+            res[mode]["breakdown"] = bd
+        st = sw.engine.status().cpu().numpy()
+        res[mode]["status_nonzero"] = int((st[: e - b] != 0).sum())
+        if a.check:
+            from oracle import mlp_numpy
+            from ndp_nmpc_qd_b200.dnwash_nn_est.downwash_nn import DEFAULT_WEIGHTS
+
+            # oracle on the full swarm (every rank recomputes the full reference tensor on the host)
+            t_all = torch.as_tensor(t0 + 0.02 * a.steps, device=dev)
+            xa, _ = rg.horizon(t_all, None, 20, 0.1, torch.as_tensor(off, device=dev).contiguous())
+            traj = xa[:, :, 0:6].float().cpu().numpy()
+            ref = mlp_numpy.swarm_forces(mlp_numpy.load_npz(DEFAULT_WEIGHTS), traj, b, e - b)
+            err = float(np.abs(sw.f[: e - b].cpu().numpy() - ref).max())
+            res[mode]["force_err_vs_oracle"] = err
+            assert err < 1e-4, err
+        del sw
+    if world > 1:
+        assert torch.equal(f_by_mode["p2p"], f_by_mode["allgather"]), "fused peer-memory exchange != NCCL all-gather path"
+        dist.barrier()
+    if rank == 0:
+        print(json.dumps(dict(n_gpus=world, quads=n_all, steps=a.steps, **res)), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
