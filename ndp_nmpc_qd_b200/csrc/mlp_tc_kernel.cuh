@@ -195,7 +195,9 @@ __global__ void __launch_bounds__(MLPT_CTA_THREADS, 1) mlp_tc_kernel(const __gri
     int stamp = 0;
     MLPT_STAMP(stamp++);
     const long long n_tiles = (io.M + MLPT_ROWS - 1) / MLPT_ROWS;
-    const long long tile0 = (long long)blockIdx.x * MLPT_GROUPS + grp, tstride = (long long)gridDim.x * MLPT_GROUPS;
+    // tile -> (CTA, group): consecutive tiles go to different SMs, so a ragged last round adds one tile to
+    // as many SMs as it has tiles instead of two tiles (both groups) to half as many
+    const long long tile0 = (long long)grp * gridDim.x + blockIdx.x, tstride = (long long)gridDim.x * MLPT_GROUPS;
     float xn[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     bool on_n = false;
     if (tile0 < n_tiles && tile0 * MLPT_ROWS + t < io.M) on_n = mlp_fetch_row(io, tile0 * MLPT_ROWS + t, xn);

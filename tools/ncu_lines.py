@@ -27,7 +27,7 @@ def sass_stats(path):
     by_op, st = collections.Counter(), collections.Counter()
     tot = 0
     for r in rows[2:]:
-        if len(r) < len(hdr):
+        if len(r) < len(hdr) or r[ix["Instructions Executed"]] == "Instructions Executed":
             continue
         src = r[ix["Source"]].strip().split()
         op = (src[1] if src[0].startswith("@") else src[0]).split(".")[0]
