@@ -73,6 +73,9 @@ typedef struct ndp_config {
     int32_t ipm_max_iter; /* acados qp_solver_iter_max (50)              */
     int32_t polish_max;   /* active-set refinement rounds after the IPM  */
     double ipm_tol_mu;    /* IPM complementarity target (<=0: precision default) */
+    int32_t active_set_first; /* active-set rounds tried from the unconstrained step's violated bounds before
+                               * the IPM (0: IPM first); both routes end at the same QP solution */
+    int32_t reserved_;
 } ndp_config;
 
 typedef struct ndp_handle ndp_handle;

@@ -131,6 +131,7 @@ RtiCfg<T> make_cfg(const ndp_config& g) {
     c.N = g.N;
     c.ipm_max_iter = g.ipm_max_iter;
     c.polish_max = g.polish_max;
+    c.as_first_max = g.active_set_first;
     c.h = (T)(g.T / g.N);
     c.inv_mass = (T)(1.0 / g.mass);
     c.g = (T)g.gravity;
@@ -262,6 +263,8 @@ void ndp_default_config(ndp_config* c) {
     c->u_max[3] = 9.81 / 0.36;
     c->ipm_max_iter = 50;
     c->polish_max = 6;
+    c->active_set_first = 6;
+    c->reserved_ = 0;
     c->ipm_tol_mu = 0.0;
 }
 

@@ -32,7 +32,7 @@ constexpr int RTI_PPC = RTI_THREADS / GL;  // problems per CTA (upper bound)
 
 template <typename T>
 struct RtiCfg {
-    int N, ipm_max_iter, polish_max;
+    int N, ipm_max_iter, polish_max, as_first_max;
     T h, inv_mass, g;
     T Q[10], R[4], hQ[10], hR[4], umin[4], umax[4], vmin[3], vmax[3];  // hQ = h Q, hR = h R (stage cost scaled by the interval)
     T tol_mu, tol_res, mu0, t_floor, t_min, big;
@@ -632,142 +632,61 @@ __device__ __forceinline__ void forward_sweep(const RtiCfg<T>& c, int N, int lan
 
 enum { IPM_LL = 0, IPM_LU, IPM_TL, IPM_TU, IPM_CL, IPM_CU, IPM_ACT };
 
-constexpr int RTI_CTA = 64;  // threads per CTA of the nominal launch (4 problems)
-
+// Constrained QP of one problem (the unconstrained step left its box): kept out of line so that the nominal
+// path of rti_step_kernel keeps its register allocation.  On return sDz holds the QP step; returns the status.
 template <typename T, int kN>
-__global__ void __launch_bounds__(RTI_CTA, (sizeof(T) == 4) ? 8 : 3) rti_step_kernel(const RtiCfg<T> c, const RtiArgs<T> a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+__device__ __noinline__ int constrained_qp(const RtiCfg<T>& c, int lane, unsigned mask, T* sm, T* ws, const T* sTriv, T dx0, T lo, T hi,
+                                           T* gX, T* gU, const T* gY, int* counts) {
     const int N = (kN > 0) ? kN : c.N;
     const SmemLayout L(N);
     const WsLayout WL(N);
-    const int lane = threadIdx.x & 15;
-    const int grp = threadIdx.x >> 4;
-    const unsigned mask = 0xFFFFu << (threadIdx.x & 16);
-    const int ppc = blockDim.x >> 4;  // problems per CTA
-    T* sTriv = reinterpret_cast<T*>(smem_raw);  // [10][TLD] constant tile of the trivial columns 0..5, shared by the CTA
-    T* sm = sTriv + 10 * TLD + (size_t)grp * L.total;
-    T* ws = a.ws + (size_t)(blockIdx.x * ppc + grp) * a.ws_stride;
     T* sX = sm + L.oX;
     T* sU = sm + L.oU;
     T* sDz = sm + L.oDz;
-    for (int i = threadIdx.x; i < 10 * TLD; i += blockDim.x) {
-        const int r = i / TLD, cc = i - r * TLD;
-        sTriv[i] = (cc < 6 && cc == r) ? T(1) : ((cc >= 3 && cc < 6 && cc - 3 == r) ? c.h : T(0));
-    }
-    for (int i = lane; i < 20 * TLD; i += GL) sm[L.oT0 + i] = T(0);
-    __syncthreads();
-
-    // per-lane box of the variable this lane owns (lanes 3..5: v, lanes 10..13: u)
-    T lo = T(-1e30), hi = T(1e30);
-#pragma unroll
-    for (int m = 0; m < 3; m++)
-        if (lane == 3 + m) { lo = c.vmin[m]; hi = c.vmax[m]; }
-#pragma unroll
-    for (int m = 0; m < 4; m++)
-        if (lane == 10 + m) { lo = c.umin[m]; hi = c.umax[m]; }
     const bool isx = lane < 10, isu = (lane >= 10 && lane < 14), isv = (lane >= 3 && lane < 6);
-
-    for (int prob = blockIdx.x * ppc + grp; prob < a.B; prob += gridDim.x * ppc) {
-        T* gX = a.X + (size_t)prob * (N + 1) * NX;
-        T* gU = a.U + (size_t)prob * N * NU;
-        // ---- stage the problem record in shared memory (asynchronous copies, one wait) ----
-        {
-            constexpr int E2 = 8 / (int)sizeof(T);  // elements per 8-byte copy (records are 8-byte aligned)
-            T* sY = sm + L.oY;
-            T* sPar = sm + L.oPar;
-            for (int i = lane; i < (N + 1) * NX / E2; i += GL) cp_async<8>(sX + E2 * i, gX + E2 * i);
-            for (int i = lane; i < N * NU / E2; i += GL) cp_async<8>(sU + E2 * i, gU + E2 * i);
-            if (a.xr == nullptr) {
-                const T* gY = a.yref + (size_t)prob * (N + 1) * NYS;
-                const T* gP = a.par + (size_t)prob * (N + 1) * NPS;
-                for (int i = lane; i < (N + 1) * (NYS / E2); i += GL) {
-                    const int k = i / (NYS / E2), q = i - k * (NYS / E2);
-                    cp_async<8>(sY + k * SYS + E2 * q, gY + k * NYS + E2 * q);
-                }
-                for (int i = lane; i < (N + 1) * NPS / E2; i += GL) cp_async<8>(sPar + E2 * i, gP + E2 * i);
-            } else {
-                // yref_k = [xr_k; ur_k], p_k = [xr_k[6:10]; f_k]   (nmpc_body_rate_ctl.py:95-104)
-                const T* gxr = a.xr + (size_t)prob * (N + 1) * NX;
-                const T* gur = a.ur + (size_t)prob * N * NU;
-                for (int i = lane; i < (N + 1) * (NX / E2); i += GL) {
-                    const int k = i / (NX / E2), q = (i - k * (NX / E2)) * E2;
-                    cp_async<8>(sY + k * SYS + q, gxr + k * NX + q);
-                    if (q >= 6) cp_async<8>(sPar + k * NPS + q - 6, gxr + k * NX + q);
-                }
-                for (int i = lane; i < N * (NU / E2); i += GL) {
-                    const int k = i / (NU / E2), q = (i - k * (NU / E2)) * E2;
-                    cp_async<8>(sY + k * SYS + NX + q, gur + k * NU + q);
-                }
-                if (lane < NU) sY[N * SYS + NX + lane] = T(0);
-                if (a.f) {
-                    const T* gf = a.f + (size_t)prob * (N + 1) * 3;
-                    for (int i = lane; i < (N + 1) * 3; i += GL) {
-                        const int k = i / 3, m = i - k * 3;
-                        cp_async<(int)sizeof(T)>(sPar + k * NPS + 4 + m, gf + i);
-                    }
-                    for (int k = lane; k <= N; k += GL) sPar[k * NPS + 7] = T(0);
-                } else {
-                    for (int i = lane; i < (N + 1) * 4; i += GL) sPar[(i >> 2) * NPS + 4 + (i & 3)] = T(0);
-                }
+    auto iter_at = [&](int k) -> T { return isx ? sX[k * NX + lane] : (isu ? sU[k * NU + (lane - 10)] : T(0)); };
+    auto has_box = [&](int k) -> bool { return (isu && k < N) || (isv && k >= 1 && k < N); };
+    int status = 0, n_fact = 0, n_ipm = 0, n_pol = 0;
+    bool viol = false, bad = false;
+    int nact_l = 0;
+        {   // the accepted-sweep ring overwrote the cost records: rebuild them from the stored yref
+                        T* sY = sm + L.oY;
+            for (int i = lane; i < (N + 1) * SYS; i += GL) {
+                const int k = i >> 4, e = i & 15;
+                sY[i] = (e < NYS) ? gY[k * NYS + e] : T(0);
             }
-            for (int i = lane; i < (N + 1) * 2; i += GL) sY[(i >> 1) * SYS + NYS + (i & 1)] = T(0);
-        }
-        const T x0v = isx ? a.x0[(size_t)prob * NX + lane] : T(0);
-        cp_async_wait_all();
-        __syncwarp(mask);
-        if (a.xr != nullptr) {
-            // persist yref / p as if set stage by stage (a later plain solve or get sees them)
-            T* wY = a.yref_w + (size_t)prob * (N + 1) * NYS;
-            T* wP = a.par_w + (size_t)prob * (N + 1) * NPS;
-            for (int i = lane; i < (N + 1) * NYS; i += GL) {
-                const int k = i / NYS;
-                wY[i] = sm[L.oY + k * SYS + (i - k * NYS)];
-            }
-            for (int i = lane; i < (N + 1) * NPS; i += GL) wP[i] = sm[L.oPar + i];
+            __syncwarp(mask);
+            cost_records<T>(N, lane, sY, sX, sU, sm + L.oPar);
             __syncwarp(mask);
         }
-        cost_records<T>(N, lane, sm + L.oY, sX, sU, sm + L.oPar);
+        T* wI = ws + WL.oIpm;
+        T* wZ = ws + WL.oZc;
+        T* bD = ws + WL.oBarD;
+        T* bG = ws + WL.oBarG;
+        const int FS = N * 16;  // field stride
+        bool ipm_ok = false, pol_ok = false;
+        // Phase 0: primal-dual active-set rounds seeded by the bounds the unconstrained step violates (its
+        // tentative iterate is in gX / gU).  A fixed point of the rounds satisfies the KKT conditions of the QP,
+        // so it is the same solution the interior-point method converges to, at one Riccati factorisation per
+        // round instead of two per IPM iteration.  Phase 1 (velocity box involved, or no fixed point within
+        // as_first_max rounds): Mehrotra IPM, then the rounds again from the IPM's active set.
+        for (int k = 0; k <= N; k++) {
+            bD[k * 16 + lane] = T(0);
+            bG[k * 16 + lane] = T(0);
+            wZ[k * 16 + lane] = (k == 0 && isx) ? dx0 : T(0);
+        }
+        bool seed_x = false;
+        for (int k = 0; k < N; k++)
+            if (has_box(k)) {
+                const T v = isu ? gU[k * NU + (lane - 10)] : gX[k * NX + lane];
+                wI[IPM_ACT * FS + k * 16 + lane] = isu ? ((v < lo) ? T(1) : ((v > hi) ? T(2) : T(0))) : T(0);
+                if (isv) seed_x |= !(v >= lo && v <= hi);
+            }
+        seed_x = __any_sync(mask, seed_x);
         __syncwarp(mask);
-        const T dx0 = isx ? x0v - sX[lane] : T(0);
-
-        int status = 0, n_fact = 0, n_ipm = 0, n_pol = 0;
-        // iterate value of the variable this lane owns at stage k
-        auto iter_at = [&](int k) -> T { return isx ? sX[k * NX + lane] : (isu ? sU[k * NU + (lane - 10)] : T(0)); };
-        auto has_box = [&](int k) -> bool { return (isu && k < N) || (isv && k >= 1 && k < N); };
-
-        // ---- preparation + unconstrained feedback; the step is accepted on the fly ----
-        bool ok = backward_sweep<T, true, false, false>(c, N, lane, mask, sm, L, ws, WL, sTriv);
-        n_fact++;
-        bool viol = false, bad = false;
-        int nact_l = 0;
-        forward_sweep<T, true>(c, N, lane, mask, dx0, sm, L, ws, WL, lo, hi, gX, gU, a.u0 ? a.u0 + (size_t)prob * NU : nullptr, viol, bad,
-                               nact_l);
-        if (!ok) status = 4;
-        const bool nominal = ok && !viol;
-
-        if (ok && viol) {
-            {   // the accepted-sweep ring overwrote the cost records: rebuild them from the stored yref
-                const T* gY = (a.xr != nullptr ? a.yref_w : a.yref) + (size_t)prob * (N + 1) * NYS;
-                T* sY = sm + L.oY;
-                for (int i = lane; i < (N + 1) * SYS; i += GL) {
-                    const int k = i >> 4, e = i & 15;
-                    sY[i] = (e < NYS) ? gY[k * NYS + e] : T(0);
-                }
-                __syncwarp(mask);
-                cost_records<T>(N, lane, sY, sX, sU, sm + L.oPar);
-                __syncwarp(mask);
-            }
-            // ================= Mehrotra IPM on the Riccati kernel =================
-            T* wI = ws + WL.oIpm;
-            T* wZ = ws + WL.oZc;
-            T* bD = ws + WL.oBarD;
-            T* bG = ws + WL.oBarG;
-            const int FS = N * 16;  // field stride
-            for (int k = 0; k <= N; k++) {
-                bD[k * 16 + lane] = T(0);
-                bG[k * 16 + lane] = T(0);
-                wZ[k * 16 + lane] = (k == 0 && isx) ? dx0 : T(0);
-            }
+        for (int phase = (seed_x || c.as_first_max <= 0) ? 1 : 0; phase < 2 && !pol_ok && status == 0; phase++) {
+        if (phase == 1) {
+        // ================= Mehrotra IPM on the Riccati kernel =================
             int nb_l = 0;
             for (int k = 0; k < N; k++)
                 if (has_box(k)) {
@@ -783,7 +702,7 @@ __global__ void __launch_bounds__(RTI_CTA, (sizeof(T) == 4) ? 8 : 3) rti_step_ke
             const T inv_m = T(1) / (T(2) * grp_sum<T>((T)nb_l, mask));
             __syncwarp(mask);
             T res_lin = T(1), mu_prev = T(1e30), mu = T(0);
-            bool ipm_ok = false, any_x_act = false;
+            bool any_x_act = false;
             int it = 0;
             for (it = 0; it <= c.ipm_max_iter; it++) {
                 // complementarity, affine barrier terms
@@ -912,9 +831,10 @@ __global__ void __launch_bounds__(RTI_CTA, (sizeof(T) == 4) ? 8 : 3) rti_step_ke
                 n_ipm++;
                 __syncwarp(mask);
             }
-            // ================= active-set refinement =================
-            bool pol_ok = false;
-            if (status == 0 && c.polish_max > 0) {
+        }
+        // ================= active-set rounds =================
+        if (status == 0 && (phase ? c.polish_max : c.as_first_max) > 0) {
+            if (phase == 1)
                 for (int k = 0; k < N; k++)
                     if (has_box(k)) {
                         const int e = k * 16 + lane;
@@ -922,86 +842,213 @@ __global__ void __launch_bounds__(RTI_CTA, (sizeof(T) == 4) ? 8 : 3) rti_step_ke
                         const T ll = wI[IPM_LL * FS + e], lu = wI[IPM_LU * FS + e];
                         wI[IPM_ACT * FS + e] = (tl < ll) ? T(1) : ((tu < lu) ? T(2) : T(0));
                     }
-                for (int round = 0; round < c.polish_max; round++) {
-                    for (int k = 0; k < N; k++)
-                        if (has_box(k)) {
-                            const int e = k * 16 + lane;
-                            const T it_v = iter_at(k);
-                            const T lb = lo - it_v, ub = hi - it_v;
-                            if (isu) {
-                                const T act = wI[IPM_ACT * FS + e];
-                                bD[e] = (act != T(0)) ? c.big : T(0);
-                                bG[e] = (act != T(0)) ? -c.big * (act == T(1) ? lb : ub) : T(0);
-                            } else {
-                                // velocity boxes cannot be pinned inside the input-elimination Riccati: an
-                                // active one keeps its interior-point barrier term, an inactive one is dropped
-                                // (and checked for feasibility below)
-                                const T act = wI[IPM_ACT * FS + e];
-                                const T tl = wI[IPM_TL * FS + e], tu = wI[IPM_TU * FS + e];
-                                const T ll = wI[IPM_LL * FS + e], lu = wI[IPM_LU * FS + e];
-                                const T gl = ll / tl, gu = lu / tu;
-                                bD[e] = (act != T(0)) ? gl + gu : T(0);
-                                bG[e] = (act != T(0)) ? (-gu * ub + lu) - (gl * lb + ll) : T(0);
-                            }
-                        }
-                    __syncwarp(mask);
-                    if (!backward_sweep<T, false, true, true>(c, N, lane, mask, sm, L, ws, WL, sTriv)) break;
-                    n_fact++;
-                    n_pol++;
-                    forward_sweep<T, false>(c, N, lane, mask, dx0, sm, L, ws, WL, lo, hi, gX, gU, nullptr, viol, bad, nact_l);
-                    bool changed = false, xviol = false;
-                    if (isv)
-                        for (int k = 1; k < N; k++) {
-                            const int e = k * 16 + lane;
-                            const T it_v = iter_at(k);
-                            if (wI[IPM_ACT * FS + e] == T(0)) xviol |= !(sDz[e] >= lo - it_v && sDz[e] <= hi - it_v);
-                        }
-                    if (isu)
-                        for (int k = 0; k < N; k++) {
-                            const int e = k * 16 + lane;
-                            const T it_v = iter_at(k);
-                            const T lb = lo - it_v, ub = hi - it_v;
+            for (int round = 0; round < (phase ? c.polish_max : c.as_first_max); round++) {
+                for (int k = 0; k < N; k++)
+                    if (has_box(k)) {
+                        const int e = k * 16 + lane;
+                        const T it_v = iter_at(k);
+                        const T lb = lo - it_v, ub = hi - it_v;
+                        if (isu) {
                             const T act = wI[IPM_ACT * FS + e];
-                            if (act != T(0)) {
-                                const T* hr = ws + WL.oHrow + (k * 4 + (lane - 10)) * 16;
-                                T gq = hr[14];
-#pragma unroll
-                                for (int i = 0; i < 14; i++) gq += hr[i] * sDz[k * 16 + i];
-                                const T lam = (act == T(2)) ? -gq : gq;
-                                if (lam < T(0)) { wI[IPM_ACT * FS + e] = T(0); changed = true; }
-                            } else {
-                                const T zn = sDz[e];
-                                if (zn > ub) { wI[IPM_ACT * FS + e] = T(2); changed = true; }
-                                else if (zn < lb) { wI[IPM_ACT * FS + e] = T(1); changed = true; }
-                            }
+                            bD[e] = (act != T(0)) ? c.big : T(0);
+                            bG[e] = (act != T(0)) ? -c.big * (act == T(1) ? lb : ub) : T(0);
+                        } else {
+                            // velocity boxes cannot be pinned inside the input-elimination Riccati: an
+                            // active one keeps its interior-point barrier term, an inactive one is dropped
+                            // (and checked for feasibility below)
+                            const T act = wI[IPM_ACT * FS + e];
+                            const T tl = wI[IPM_TL * FS + e], tu = wI[IPM_TU * FS + e];
+                            const T ll = wI[IPM_LL * FS + e], lu = wI[IPM_LU * FS + e];
+                            const T gl = ll / tl, gu = lu / tu;
+                            bD[e] = (act != T(0)) ? gl + gu : T(0);
+                            bG[e] = (act != T(0)) ? (-gu * ub + lu) - (gl * lb + ll) : T(0);
                         }
-                    changed = __any_sync(mask, changed);
-                    xviol = __any_sync(mask, xviol);
-                    __syncwarp(mask);
-                    if (xviol) break;  // a dropped velocity box is violated: keep the interior-point iterate
-                    if (!changed) { pol_ok = true; break; }
-                }
-                if (pol_ok && isu) {
-                    // pinned inputs sit exactly on their bound
+                    }
+                __syncwarp(mask);
+                if (!backward_sweep<T, false, true, true>(c, N, lane, mask, sm, L, ws, WL, sTriv)) break;
+                n_fact++;
+                n_pol++;
+                forward_sweep<T, false>(c, N, lane, mask, dx0, sm, L, ws, WL, lo, hi, gX, gU, nullptr, viol, bad, nact_l);
+                bool changed = false, xviol = false;
+                if (isv)
+                    for (int k = 1; k < N; k++) {
+                        const int e = k * 16 + lane;
+                        const T it_v = iter_at(k);
+                        if (wI[IPM_ACT * FS + e] == T(0)) xviol |= !(sDz[e] >= lo - it_v && sDz[e] <= hi - it_v);
+                    }
+                if (isu)
                     for (int k = 0; k < N; k++) {
                         const int e = k * 16 + lane;
-                        const T act = wI[IPM_ACT * FS + e];
                         const T it_v = iter_at(k);
-                        if (act == T(1)) sDz[e] = lo - it_v;
-                        if (act == T(2)) sDz[e] = hi - it_v;
+                        const T lb = lo - it_v, ub = hi - it_v;
+                        const T act = wI[IPM_ACT * FS + e];
+                        if (act != T(0)) {
+                            const T* hr = ws + WL.oHrow + (k * 4 + (lane - 10)) * 16;
+                            T gq = hr[14];
+#pragma unroll
+                            for (int i = 0; i < 14; i++) gq += hr[i] * sDz[k * 16 + i];
+                            const T lam = (act == T(2)) ? -gq : gq;
+                            if (lam < T(0)) { wI[IPM_ACT * FS + e] = T(0); changed = true; }
+                        } else {
+                            const T zn = sDz[e];
+                            if (zn > ub) { wI[IPM_ACT * FS + e] = T(2); changed = true; }
+                            else if (zn < lb) { wI[IPM_ACT * FS + e] = T(1); changed = true; }
+                        }
                     }
+                changed = __any_sync(mask, changed);
+                xviol = __any_sync(mask, xviol);
+                __syncwarp(mask);
+                if (xviol) break;  // a dropped velocity box is violated: keep the interior-point iterate
+                if (!changed) { pol_ok = true; break; }
+            }
+            if (pol_ok && isu) {
+                // pinned inputs sit exactly on their bound
+                for (int k = 0; k < N; k++) {
+                    const int e = k * 16 + lane;
+                    const T act = wI[IPM_ACT * FS + e];
+                    const T it_v = iter_at(k);
+                    if (act == T(1)) sDz[e] = lo - it_v;
+                    if (act == T(2)) sDz[e] = hi - it_v;
                 }
             }
-            if (!pol_ok) {
-                // fall back to the interior-point iterate
-                if (lane < 14)
-                    for (int k = 0; k <= N; k++) {
-                        if (k == N && !isx) break;
-                        sDz[k * 16 + lane] = wZ[k * 16 + lane];
+        }
+        }
+        if (!pol_ok) {
+            // fall back to the interior-point iterate
+            if (lane < 14)
+                for (int k = 0; k <= N; k++) {
+                    if (k == N && !isx) break;
+                    sDz[k * 16 + lane] = wZ[k * 16 + lane];
+                }
+            if (!ipm_ok && status == 0) status = 4;
+        }
+        __syncwarp(mask);
+    counts[0] = n_fact;
+    counts[1] = n_ipm;
+    counts[2] = n_pol;
+    return status;
+}
+
+constexpr int RTI_CTA = 64;  // threads per CTA of the nominal launch (4 problems)
+
+template <typename T, int kN>
+__global__ void __launch_bounds__(RTI_CTA, (sizeof(T) == 4) ? 8 : 3) rti_step_kernel(const __grid_constant__ RtiCfg<T> c, const RtiArgs<T> a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int N = (kN > 0) ? kN : c.N;
+    const SmemLayout L(N);
+    const WsLayout WL(N);
+    const int lane = threadIdx.x & 15;
+    const int grp = threadIdx.x >> 4;
+    const unsigned mask = 0xFFFFu << (threadIdx.x & 16);
+    const int ppc = blockDim.x >> 4;  // problems per CTA
+    T* sTriv = reinterpret_cast<T*>(smem_raw);  // [10][TLD] constant tile of the trivial columns 0..5, shared by the CTA
+    T* sm = sTriv + 10 * TLD + (size_t)grp * L.total;
+    T* ws = a.ws + (size_t)(blockIdx.x * ppc + grp) * a.ws_stride;
+    T* sX = sm + L.oX;
+    T* sU = sm + L.oU;
+    T* sDz = sm + L.oDz;
+    for (int i = threadIdx.x; i < 10 * TLD; i += blockDim.x) {
+        const int r = i / TLD, cc = i - r * TLD;
+        sTriv[i] = (cc < 6 && cc == r) ? T(1) : ((cc >= 3 && cc < 6 && cc - 3 == r) ? c.h : T(0));
+    }
+    for (int i = lane; i < 20 * TLD; i += GL) sm[L.oT0 + i] = T(0);
+    __syncthreads();
+
+    // per-lane box of the variable this lane owns (lanes 3..5: v, lanes 10..13: u)
+    T lo = T(-1e30), hi = T(1e30);
+#pragma unroll
+    for (int m = 0; m < 3; m++)
+        if (lane == 3 + m) { lo = c.vmin[m]; hi = c.vmax[m]; }
+#pragma unroll
+    for (int m = 0; m < 4; m++)
+        if (lane == 10 + m) { lo = c.umin[m]; hi = c.umax[m]; }
+    const bool isx = lane < 10, isu = (lane >= 10 && lane < 14), isv = (lane >= 3 && lane < 6);
+
+    for (int prob = blockIdx.x * ppc + grp; prob < a.B; prob += gridDim.x * ppc) {
+        T* gX = a.X + (size_t)prob * (N + 1) * NX;
+        T* gU = a.U + (size_t)prob * N * NU;
+        // ---- stage the problem record in shared memory (asynchronous copies, one wait) ----
+        {
+            constexpr int E2 = 8 / (int)sizeof(T);  // elements per 8-byte copy (records are 8-byte aligned)
+            T* sY = sm + L.oY;
+            T* sPar = sm + L.oPar;
+            for (int i = lane; i < (N + 1) * NX / E2; i += GL) cp_async<8>(sX + E2 * i, gX + E2 * i);
+            for (int i = lane; i < N * NU / E2; i += GL) cp_async<8>(sU + E2 * i, gU + E2 * i);
+            if (a.xr == nullptr) {
+                const T* gY = a.yref + (size_t)prob * (N + 1) * NYS;
+                const T* gP = a.par + (size_t)prob * (N + 1) * NPS;
+                for (int i = lane; i < (N + 1) * (NYS / E2); i += GL) {
+                    const int k = i / (NYS / E2), q = i - k * (NYS / E2);
+                    cp_async<8>(sY + k * SYS + E2 * q, gY + k * NYS + E2 * q);
+                }
+                for (int i = lane; i < (N + 1) * NPS / E2; i += GL) cp_async<8>(sPar + E2 * i, gP + E2 * i);
+            } else {
+                // yref_k = [xr_k; ur_k], p_k = [xr_k[6:10]; f_k]   (nmpc_body_rate_ctl.py:95-104)
+                const T* gxr = a.xr + (size_t)prob * (N + 1) * NX;
+                const T* gur = a.ur + (size_t)prob * N * NU;
+                for (int i = lane; i < (N + 1) * (NX / E2); i += GL) {
+                    const int k = i / (NX / E2), q = (i - k * (NX / E2)) * E2;
+                    cp_async<8>(sY + k * SYS + q, gxr + k * NX + q);
+                    if (q >= 6) cp_async<8>(sPar + k * NPS + q - 6, gxr + k * NX + q);
+                }
+                for (int i = lane; i < N * (NU / E2); i += GL) {
+                    const int k = i / (NU / E2), q = (i - k * (NU / E2)) * E2;
+                    cp_async<8>(sY + k * SYS + NX + q, gur + k * NU + q);
+                }
+                if (lane < NU) sY[N * SYS + NX + lane] = T(0);
+                if (a.f) {
+                    const T* gf = a.f + (size_t)prob * (N + 1) * 3;
+                    for (int i = lane; i < (N + 1) * 3; i += GL) {
+                        const int k = i / 3, m = i - k * 3;
+                        cp_async<(int)sizeof(T)>(sPar + k * NPS + 4 + m, gf + i);
                     }
-                if (!ipm_ok && status == 0) status = 4;
+                    for (int k = lane; k <= N; k += GL) sPar[k * NPS + 7] = T(0);
+                } else {
+                    for (int i = lane; i < (N + 1) * 4; i += GL) sPar[(i >> 2) * NPS + 4 + (i & 3)] = T(0);
+                }
             }
+            for (int i = lane; i < (N + 1) * 2; i += GL) sY[(i >> 1) * SYS + NYS + (i & 1)] = T(0);
+        }
+        const T x0v = isx ? a.x0[(size_t)prob * NX + lane] : T(0);
+        cp_async_wait_all();
+        __syncwarp(mask);
+        if (a.xr != nullptr) {
+            // persist yref / p as if set stage by stage (a later plain solve or get sees them)
+            T* wY = a.yref_w + (size_t)prob * (N + 1) * NYS;
+            T* wP = a.par_w + (size_t)prob * (N + 1) * NPS;
+            for (int i = lane; i < (N + 1) * NYS; i += GL) {
+                const int k = i / NYS;
+                wY[i] = sm[L.oY + k * SYS + (i - k * NYS)];
+            }
+            for (int i = lane; i < (N + 1) * NPS; i += GL) wP[i] = sm[L.oPar + i];
             __syncwarp(mask);
+        }
+        cost_records<T>(N, lane, sm + L.oY, sX, sU, sm + L.oPar);
+        __syncwarp(mask);
+        const T dx0 = isx ? x0v - sX[lane] : T(0);
+
+        int status = 0, n_fact = 0, n_ipm = 0, n_pol = 0;
+        // iterate value of the variable this lane owns at stage k
+        auto iter_at = [&](int k) -> T { return isx ? sX[k * NX + lane] : (isu ? sU[k * NU + (lane - 10)] : T(0)); };
+        auto has_box = [&](int k) -> bool { return (isu && k < N) || (isv && k >= 1 && k < N); };
+
+        // ---- preparation + unconstrained feedback; the step is accepted on the fly ----
+        bool ok = backward_sweep<T, true, false, false>(c, N, lane, mask, sm, L, ws, WL, sTriv);
+        n_fact++;
+        bool viol = false, bad = false;
+        int nact_l = 0;
+        forward_sweep<T, true>(c, N, lane, mask, dx0, sm, L, ws, WL, lo, hi, gX, gU, a.u0 ? a.u0 + (size_t)prob * NU : nullptr, viol, bad,
+                               nact_l);
+        if (!ok) status = 4;
+        const bool nominal = ok && !viol;
+
+        if (ok && viol) {
+            int cnt[3];
+            status = constrained_qp<T, kN>(c, lane, mask, sm, ws, sTriv, dx0, lo, hi, gX, gU,
+                                           (a.xr != nullptr ? a.yref_w : a.yref) + (size_t)prob * (N + 1) * NYS, cnt);
+            n_fact += cnt[0];
+            n_ipm = cnt[1];
+            n_pol = cnt[2];
         }
 
         // ---- write back ----

@@ -96,17 +96,23 @@ def test_golden_problems(built_lib, prec):
     assert rel_err(u0, g["u0"]) < TOL[prec]
     assert rel_err(X, g["X"]) < TOL[prec] and rel_err(U, g["U"]) < TOL[prec]
     assert stats[:4, 0].max() == 1  # nominal problems: one Riccati sweep, no IPM
-    assert stats[8:, 1].min() >= 1  # saturated problems went through the IPM
+    assert stats[8:, 0].min() >= 2  # saturated problems needed constrained sweeps (active-set rounds or IPM)
+    # the IPM-first route (active_set_first=0) ends at the same solutions
+    e2 = _engine(B, prec, active_set_first=0)
+    u0b, Xb, Ub, stb, statsb = _run_engine(e2, w, g["fd"])
+    assert np.all(stb == 0) and statsb[8:, 1].min() >= 1
+    assert rel_err(u0b, g["u0"]) < TOL[prec] and rel_err(Xb, g["X"]) < TOL[prec] and rel_err(Ub, g["U"]) < TOL[prec]
 
 
+@pytest.mark.parametrize("as_first", [6, 0])
 @pytest.mark.parametrize("prec,scale", [("f32", 1.0), ("f64", 1.0), ("f32", 5.0), ("f64", 5.0), ("f32", 15.0), ("f64", 15.0)])
-def test_rti_step_vs_oracle(built_lib, c_oracle, prec, scale):
+def test_rti_step_vs_oracle(built_lib, c_oracle, prec, scale, as_first):
     """(2) SQP-RTI linearisation + Riccati/IPM QP, config-3 distribution; scale 5 / 15 are the stress
     variants that activate the input bounds."""
     B = 512
     w = wl.independent_problems(B, seed=21, scale=scale)
     fd = np.random.default_rng(4).normal(size=(B, 21, 3))
-    e = _engine(B, prec)
+    e = _engine(B, prec, active_set_first=as_first)
     u0, X, U, st, stats = _run_engine(e, w, fd)
     ou0, oX, oU, ost, r = _run_oracle(c_oracle, make_cfg(), w, fd)
     ok = (ost == 0)
@@ -119,19 +125,25 @@ def test_rti_step_vs_oracle(built_lib, c_oracle, prec, scale):
         assert stats[:, 0].max() == 1 and r["n_active"].max() == 0
     if scale == 15.0:
         assert (r["n_active"] > 0).mean() > 0.5
+        if as_first == 0:
+            assert stats[r["n_active"] > 0, 1].min() >= 1  # IPM route taken
+        print(f"scale 15 {prec} as_first={as_first}: Riccati sweeps mean {stats[:, 0].mean():.2f} max {stats[:, 0].max()}, "
+              f"IPM share {(stats[:, 1] > 0).mean():.3f}")
 
 
+@pytest.mark.parametrize("as_first", [6, 0])
 @pytest.mark.parametrize("prec", ["f32", "f64"])
-def test_tightened_bounds(built_lib, c_oracle, prec):
+def test_tightened_bounds(built_lib, c_oracle, prec, as_first):
     """Forced saturation: omega_max = 1.5 rad/s, c_max = 15 m/s^2 (SURVEY.md 8d stress variant)."""
     B = 256
     kw = dict(u_min=[-1.5, -1.5, -1.5, 0.0], u_max=[1.5, 1.5, 1.5, 15.0])
     w = wl.independent_problems(B, seed=31, scale=5.0)
-    e = _engine(B, prec, np_=4, **kw)
+    e = _engine(B, prec, np_=4, active_set_first=as_first, **kw)
     u0, X, U, st, stats = _run_engine(e, w)
     ou0, oX, oU, ost, r = _run_oracle(c_oracle, make_cfg(**kw), w)
     ok = ost == 0
     assert ok.mean() > 0.99 and np.all(st[ok] == 0)
+    print(f"tight {prec} as_first={as_first}: Riccati sweeps mean {stats[:, 0].mean():.2f} max {stats[:, 0].max()}, IPM share {(stats[:, 1] > 0).mean():.3f}")
     assert (r["n_active"] > 0).mean() > 0.8
     tol = TOL[prec] if prec == "f32" else 1e-8
     assert rel_err(u0[ok], ou0[ok]) < tol and rel_err(U[ok], oU[ok]) < tol and rel_err(X[ok], oX[ok]) < tol
