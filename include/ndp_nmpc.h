@@ -179,6 +179,11 @@ int ndp_mlp_forward_swarm_parts(ndp_mlp* m, int precision, int32_t n_parts, cons
                                 int64_t n_all, int64_t ego_begin, int64_t n_ego, int32_t n_nodes, const float* odom_xy_dev,
                                 double r_horiz, void* out_dev, int path, void* stream);
 
+/* Upper bound (pairs) up to which the swarm entry points size their pair buffers for the worst case
+ * n_ego * (n_all - 1) and never read the pair count back (default 2 Mi pairs).  Above it they start from the
+ * budget, read the 4-byte count back once per call and grow on demand. */
+int ndp_mlp_set_pair_budget(ndp_mlp* m, int64_t max_pairs);
+
 int64_t ndp_mlp_launch_count(const ndp_mlp* m);
 
 /* ---- host-buffer step pipeline ----

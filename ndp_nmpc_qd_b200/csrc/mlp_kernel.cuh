@@ -46,7 +46,8 @@ struct MlpIo {
     int n_nodes;
     int accumulate;
     int other_ld;  // mode 1: row stride of `other` (10 = full state rows, 6 = position+velocity only)
-    long long M;  // total rows
+    long long M;  // total rows (host-known), or the row capacity when m_dev is set
+    const int* m_dev;  // optional: device-side count of n_nodes-row groups (pairs); rows = min(*m_dev * n_nodes, M)
     const float* in;
     const void* ego;
     const void* other;
@@ -57,6 +58,13 @@ struct MlpIo {
     int prof;           // debug: record phase timestamps of CTA 0 (mlp_tc_kernel)
     void* out;          // mode 0: float [M][3]; mode 1: precision [P][n_nodes][3]; mode 2: float [n_pairs][n_nodes][3]
 };
+
+// number of rows of this launch
+__device__ __forceinline__ long long mlp_rows(const MlpIo& io) {
+    if (!io.m_dev) return io.M;
+    const long long r = (long long)(*io.m_dev) * io.n_nodes;
+    return r < io.M ? r : io.M;
+}
 
 // feature row + gate for row index `row`
 __device__ __forceinline__ bool mlp_fetch_row(const MlpIo& io, long long row, float (&x)[6]) {
@@ -242,14 +250,20 @@ __global__ void __launch_bounds__(MLPF_THREADS, 1) mlp_fp32_kernel(const float* 
 }
 
 // ---- swarm support: neighbour lists and ordered reduction ----
-// count / fill gated neighbours of each ego (deterministic order: ascending j).  The node-0 positions of
-// all quads stream through shared memory tiles, so every (possibly remote) position is read once per CTA.
-constexpr int SWARM_TILE = 1024;
-template <bool kFill>
-__global__ void swarm_neighbours_kernel(const TrajParts tp, const float* __restrict__ odom_xy, int n_all, int ego_begin, int n_ego, int n_nodes,
-                                        float r2, int* __restrict__ counts, const int* __restrict__ offsets, int2* __restrict__ pairs) {
+// One warp per ego builds its gated neighbour list in ascending j (deterministic order inside the ego's
+// segment): ballot-compacted count pass, one atomicAdd on *total for the segment offset, fill pass.  The
+// node-0 positions of all quads stream through shared-memory tiles, so every (possibly remote) position is
+// read once per CTA.  Segments of different egos land in arrival order; the per-ego sum (swarm_reduce_kernel)
+// walks only the ego's own segment, so the result does not depend on it.  Pairs beyond `cap` are dropped
+// (*total still counts them: the host re-runs with a larger buffer when it cannot rule that out up front).
+constexpr int SWARM_TILE = 2048;
+constexpr int SWARM_CTA = 1024;  // 32 egos per CTA
+__global__ void __launch_bounds__(SWARM_CTA) swarm_pairs_kernel(const TrajParts tp, const float* __restrict__ odom_xy, int n_all, int ego_begin,
+                                                                 int n_ego, int n_nodes, float r2, int* __restrict__ total,
+                                                                 int2* __restrict__ seg, int2* __restrict__ pairs, int cap) {
     __shared__ float2 sxy[SWARM_TILE];
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * (SWARM_CTA / 32) + (threadIdx.x >> 5);
     const bool act = i < n_ego;
     const int gi = ego_begin + i;
     float ex = 0.f, ey = 0.f;
@@ -258,59 +272,58 @@ __global__ void swarm_neighbours_kernel(const TrajParts tp, const float* __restr
         ex = odom_xy ? odom_xy[i * 2] : me[0];
         ey = odom_xy ? odom_xy[i * 2 + 1] : me[1];
     }
-    int cnt = 0, o = (kFill && act) ? offsets[i] : 0;
-    for (int j0 = 0; j0 < n_all; j0 += SWARM_TILE) {
-        const int m = min(SWARM_TILE, n_all - j0);
-        __syncthreads();
-        for (int e = threadIdx.x; e < m; e += blockDim.x) {
-            const float* q = tp.row(j0 + e, n_nodes);
-            sxy[e] = make_float2(q[0], q[1]);
-        }
-        __syncthreads();
-        if (act) {
-            for (int e = 0; e < m; e++) {
-                const int j = j0 + e;
-                if (j == gi) continue;
-                const float dx = sxy[e].x - ex, dy = sxy[e].y - ey;
-                if (dx * dx + dy * dy < r2) {
-                    if (kFill) pairs[o++] = make_int2(gi, j);
-                    else cnt++;
+    int cnt = 0, off = 0;
+    for (int pass = 0; pass < 2; pass++) {
+        for (int j0 = 0; j0 < n_all; j0 += SWARM_TILE) {
+            const int m = min(SWARM_TILE, n_all - j0);
+            if (pass == 0 || n_all > SWARM_TILE) {   // a single tile stays resident for the fill pass
+                __syncthreads();
+                for (int e = threadIdx.x; e < m; e += SWARM_CTA) {
+                    const float* q = tp.row(j0 + e, n_nodes);
+                    sxy[e] = make_float2(q[0], q[1]);
+                }
+                __syncthreads();
+            }
+            if (act) {
+                for (int e0 = 0; e0 < m; e0 += 32) {
+                    const int e = e0 + lane, j = j0 + e;
+                    bool hit = false;
+                    if (e < m && j != gi) {
+                        const float dx = sxy[e].x - ex, dy = sxy[e].y - ey;
+                        hit = dx * dx + dy * dy < r2;
+                    }
+                    const unsigned b = __ballot_sync(0xFFFFFFFFu, hit);
+                    if (pass == 0) cnt += __popc(b);
+                    else {
+                        const int o = off + __popc(b & ((1u << lane) - 1u));
+                        if (hit && o < cap) pairs[o] = make_int2(gi, j);
+                        off += __popc(b);
+                    }
                 }
             }
         }
+        if (pass == 0 && act) {
+            if (lane == 0) {
+                off = cnt ? atomicAdd(total, cnt) : 0;
+                seg[i] = make_int2(off, cnt);
+            }
+            off = __shfl_sync(0xFFFFFFFFu, off, 0);
+        }
     }
-    if (!kFill && act) counts[i] = cnt;
-}
-// exclusive scan of counts[n] -> offsets[n+1] (single CTA; n <= a few 10^5)
-__global__ void swarm_scan_kernel(const int* __restrict__ counts, int n, int* __restrict__ offsets) {
-    __shared__ int part[1024];
-    const int t = threadIdx.x;
-    const int per = (n + blockDim.x - 1) / blockDim.x;
-    const int b = t * per, e = min(n, b + per);
-    int s = 0;
-    for (int i = b; i < e; i++) s += counts[i];
-    part[t] = s;
-    __syncthreads();
-    if (t == 0) {
-        int run = 0;
-        for (int i = 0; i < (int)blockDim.x; i++) { const int v = part[i]; part[i] = run; run += v; }
-        offsets[n] = run;
-    }
-    __syncthreads();
-    int run = part[t];
-    for (int i = b; i < e; i++) { offsets[i] = run; run += counts[i]; }
 }
 // f[i][k][:] = sum over the ego's pair segment, in list order
 template <typename TO>
-__global__ void swarm_reduce_kernel(const float* __restrict__ fpair, const int* __restrict__ offsets, int n_ego, int n_nodes,
+__global__ void swarm_reduce_kernel(const float* __restrict__ fpair, const int2* __restrict__ seg, int n_ego, int n_nodes, int cap,
                                     TO* __restrict__ out) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long total = (long long)n_ego * n_nodes * 3;
     if (idx >= total) return;
     const int i = (int)(idx / (n_nodes * 3));
     const int rem = (int)(idx - (long long)i * n_nodes * 3);
+    const int2 sg = seg[i];
+    const int end = min(sg.x + sg.y, cap);
     float acc = 0.f;
-    for (int p = offsets[i]; p < offsets[i + 1]; p++) acc += fpair[(long long)p * n_nodes * 3 + rem];
+    for (int p = sg.x; p < end; p++) acc += fpair[(long long)p * n_nodes * 3 + rem];
     out[idx] = (TO)acc;
 }
 

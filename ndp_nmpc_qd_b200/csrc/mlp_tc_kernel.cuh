@@ -151,6 +151,9 @@ __global__ void __launch_bounds__(MLPT_CTA_THREADS, 1) mlp_tc_kernel(const __gri
     __half* sA2h = reinterpret_cast<__half*>(act + MLPT_A2H);
     __half* sA2l = reinterpret_cast<__half*>(act + MLPT_A2L);
     const MlpSmall& sq = *reinterpret_cast<const MlpSmall*>(smt + MLPT_S_PAR);
+    const long long M = mlp_rows(io);
+    const long long n_tiles = (M + MLPT_ROWS - 1) / MLPT_ROWS;
+    if ((long long)blockIdx.x >= n_tiles) return;  // device-sized launches: nothing for this CTA (before any barrier / TMA / TMEM setup)
     {
         float* dstp = reinterpret_cast<float*>(smt + MLPT_S_PAR);
         const float* srcp = reinterpret_cast<const float*>(&sp);
@@ -194,13 +197,12 @@ __global__ void __launch_bounds__(MLPT_CTA_THREADS, 1) mlp_tc_kernel(const __gri
 
     int stamp = 0;
     MLPT_STAMP(stamp++);
-    const long long n_tiles = (io.M + MLPT_ROWS - 1) / MLPT_ROWS;
     // tile -> (CTA, group): consecutive tiles go to different SMs, so a ragged last round adds one tile to
     // as many SMs as it has tiles instead of two tiles (both groups) to half as many
     const long long tile0 = (long long)grp * gridDim.x + blockIdx.x, tstride = (long long)gridDim.x * MLPT_GROUPS;
     float xn[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     bool on_n = false;
-    if (tile0 < n_tiles && tile0 * MLPT_ROWS + t < io.M) on_n = mlp_fetch_row(io, tile0 * MLPT_ROWS + t, xn);
+    if (tile0 < n_tiles && tile0 * MLPT_ROWS + t < M) on_n = mlp_fetch_row(io, tile0 * MLPT_ROWS + t, xn);
     for (long long tile = tile0; tile < n_tiles; tile += tstride) {
         const long long row = tile * MLPT_ROWS + t;
         float x[6];
@@ -212,7 +214,7 @@ __global__ void __launch_bounds__(MLPT_CTA_THREADS, 1) mlp_tc_kernel(const __gri
 #pragma unroll
             for (int i = 0; i < 6; i++) xn[i] = 0.f;
             on_n = false;
-            if (tile + tstride < n_tiles && nrow < io.M) on_n = mlp_fetch_row(io, nrow, xn);
+            if (tile + tstride < n_tiles && nrow < M) on_n = mlp_fetch_row(io, nrow, xn);
         }
         MLPT_STAMP(stamp++);
         // ---- layer 1 (CUDA cores, fp32) -> h1 hi/lo operand tiles ----
@@ -342,7 +344,7 @@ __global__ void __launch_bounds__(MLPT_CTA_THREADS, 1) mlp_tc_kernel(const __gri
         if (hf) sOut[t] = make_float4(o0, o1, o2, 0.f);
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         group_sync(grp);
-        if (!hf && row < io.M) {
+        if (!hf && row < M) {
             const float4 p = sOut[t];
             mlp_store_row(io, row, on, o0 + p.x, o1 + p.y, o2 + p.z);
         }
@@ -385,7 +387,7 @@ inline void mlp_tc_small(const float* host_params, MlpSmall* sp) {
 }
 
 inline int mlp_tc_launch(const MlpSmall& sp, const void* wimg, const MlpIo& io, int n_sm, cudaStream_t st) {
-    const long long tiles = (io.M + MLPT_ROWS - 1) / MLPT_ROWS;
+    const long long tiles = (io.M + MLPT_ROWS - 1) / MLPT_ROWS;  // io.M is the row capacity when the count lives on the device
     const long long ctas = (tiles + MLPT_GROUPS - 1) / MLPT_GROUPS;
     const int grd = (int)(ctas < n_sm ? ctas : n_sm);
     mlp_tc_kernel<<<grd, MLPT_CTA_THREADS, MLPT_SMEM, st>>>(sp, reinterpret_cast<const __half*>(wimg), io);

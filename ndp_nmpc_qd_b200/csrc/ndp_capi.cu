@@ -420,8 +420,8 @@ struct ndp_mlp {
     ndp::MlpSmall small;  // fp32 side parameters passed by value to the tensor-core kernel
     int n_sm;
     // swarm scratch (grown on demand)
-    int* counts; int* offsets; int2* pairs; float* fpair;
-    long long cap_ego, cap_pairs, cap_rows;
+    int* total; int2* seg; int2* pairs; float* fpair;
+    long long cap_ego, cap_pairs, cap_rows, pair_budget;
     std::atomic<long long> launches;
     std::mutex mu;
 };
@@ -464,8 +464,9 @@ int ndp_mlp_create(const float* W1, const float* b1, const float* W2, const floa
     std::memcpy(host + MLP_OB4, b4, sizeof(float) * MLP_OUT);
     ndp_mlp* m = new ndp_mlp();
     m->launches = 0;
-    m->counts = m->offsets = nullptr; m->pairs = nullptr; m->fpair = nullptr;
+    m->total = nullptr; m->seg = nullptr; m->pairs = nullptr; m->fpair = nullptr;
     m->cap_ego = m->cap_pairs = m->cap_rows = 0;
+    m->pair_budget = 2ll << 20;  // 2 Mi pairs: 16 MB of pair indices + 0.5 GB of per-pair forces at 21 nodes
     m->params = nullptr; m->tc_weights = nullptr;
     int dev = 0;
     cudaGetDevice(&dev);
@@ -484,7 +485,7 @@ int ndp_mlp_create(const float* W1, const float* b1, const float* W2, const floa
 int ndp_mlp_destroy(ndp_mlp* m) {
     if (!m) return 0;
     cudaFree(m->params); cudaFree(m->tc_weights);
-    cudaFree(m->counts); cudaFree(m->offsets); cudaFree(m->pairs); cudaFree(m->fpair);
+    cudaFree(m->total); cudaFree(m->seg); cudaFree(m->pairs); cudaFree(m->fpair);
     delete m;
     return 0;
 }
@@ -540,47 +541,64 @@ int ndp_mlp_forward_swarm_parts(ndp_mlp* m, int precision, int32_t n_parts, cons
     std::lock_guard<std::mutex> lk(m->mu);
     cudaStream_t st = (cudaStream_t)stream;
     if (n_ego > m->cap_ego) {
-        cudaFree(m->counts); cudaFree(m->offsets);
-        CU(cudaMalloc(&m->counts, sizeof(int) * n_ego));
-        CU(cudaMalloc(&m->offsets, sizeof(int) * (n_ego + 1)));
+        cudaFree(m->seg);
+        CU(cudaMalloc(&m->seg, sizeof(int2) * n_ego));
         m->cap_ego = n_ego;
     }
+    if (!m->total) CU(cudaMalloc(&m->total, sizeof(int)));
+    auto reserve_pairs = [&](long long cap) -> int {
+        if (cap > m->cap_pairs || cap * n_nodes > m->cap_rows) {
+            cudaFree(m->pairs); cudaFree(m->fpair);
+            m->pairs = nullptr; m->fpair = nullptr; m->cap_pairs = m->cap_rows = 0;
+            CU(cudaMalloc(&m->pairs, sizeof(int2) * cap));
+            CU(cudaMalloc(&m->fpair, sizeof(float) * cap * n_nodes * 3));
+            m->cap_pairs = cap;
+            m->cap_rows = cap * n_nodes;
+        }
+        return 0;
+    };
+    // Pair buffers sized for the worst case (every other quad inside the gate) whenever that fits the budget:
+    // the pair count then never leaves the device and the whole step is four asynchronous launches.  Larger
+    // swarms start from the budget and verify the count with one 4-byte read-back per step.
+    const long long worst = (long long)n_ego * (n_all - 1);
+    const bool sized = worst <= m->pair_budget;
+    if (int rc = reserve_pairs(sized ? (worst > 0 ? worst : 1) : (m->cap_pairs > m->pair_budget ? m->cap_pairs : m->pair_budget))) return rc;
     const float r2 = (float)(r_horiz * r_horiz);
-    const int blk = 128, grd = (int)((n_ego + blk - 1) / blk);
-    swarm_neighbours_kernel<false><<<grd, blk, 0, st>>>(tp, odom_xy, (int)n_all, (int)ego_begin, (int)n_ego, n_nodes, r2, m->counts, nullptr, nullptr);
-    swarm_scan_kernel<<<1, 1024, 0, st>>>(m->counts, (int)n_ego, m->offsets);
-    m->launches += 2;
-    int n_pairs = 0;
-    // the pair count sizes the next launches: one 4-byte read-back per swarm step
-    CU(cudaMemcpyAsync(&n_pairs, m->offsets + n_ego, sizeof(int), cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    if (n_pairs > m->cap_pairs) {
-        cudaFree(m->pairs); cudaFree(m->fpair);
-        const long long cap = (long long)n_pairs * 5 / 4 + 1024;
-        CU(cudaMalloc(&m->pairs, sizeof(int2) * cap));
-        CU(cudaMalloc(&m->fpair, sizeof(float) * cap * n_nodes * 3));
-        m->cap_pairs = cap;
-        m->cap_rows = cap * n_nodes;
-    } else if ((long long)n_pairs * n_nodes > m->cap_rows) {
-        cudaFree(m->fpair);
-        CU(cudaMalloc(&m->fpair, sizeof(float) * m->cap_pairs * n_nodes * 3));
-        m->cap_rows = m->cap_pairs * n_nodes;
-    }
-    if (n_pairs > 0) {
-        swarm_neighbours_kernel<true><<<grd, blk, 0, st>>>(tp, odom_xy, (int)n_all, (int)ego_begin, (int)n_ego, n_nodes, r2, nullptr, m->offsets, m->pairs);
+    const int grd = (int)((n_ego + SWARM_CTA / 32 - 1) / (SWARM_CTA / 32));
+    int n_pairs = -1;  // -1: known to the device only
+    for (;;) {
+        CU(cudaMemsetAsync(m->total, 0, sizeof(int), st));
+        swarm_pairs_kernel<<<grd, SWARM_CTA, 0, st>>>(tp, odom_xy, (int)n_all, (int)ego_begin, (int)n_ego, n_nodes, r2, m->total, m->seg, m->pairs,
+                                                     (int)m->cap_pairs);
         m->launches++;
+        if (sized && path != 1) break;
+        CU(cudaMemcpyAsync(&n_pairs, m->total, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        if (n_pairs <= m->cap_pairs) break;
+        if (int rc = reserve_pairs((long long)n_pairs * 5 / 4 + 1024)) return rc;
+    }
+    if (n_pairs != 0) {
         MlpIo io{};
-        io.mode = 2; io.precision = NDP_F32; io.n_nodes = n_nodes; io.M = (long long)n_pairs * n_nodes;
+        io.mode = 2; io.precision = NDP_F32; io.n_nodes = n_nodes;
         io.tp = tp; io.pairs = m->pairs; io.out = m->fpair;
-        int rc = mlp_run(m, io, path, st);
+        if (n_pairs < 0) { io.M = m->cap_pairs * n_nodes; io.m_dev = m->total; }
+        else io.M = (long long)n_pairs * n_nodes;
+        int rc = mlp_run(m, io, n_pairs < 0 ? 2 : path, st);
         if (rc) return rc;
     }
     const long long tot = (long long)n_ego * n_nodes * 3;
     const int g2 = (int)((tot + 255) / 256);
-    if (precision == NDP_F64) swarm_reduce_kernel<double><<<g2, 256, 0, st>>>(m->fpair, m->offsets, (int)n_ego, n_nodes, (double*)out);
-    else swarm_reduce_kernel<float><<<g2, 256, 0, st>>>(m->fpair, m->offsets, (int)n_ego, n_nodes, (float*)out);
+    if (precision == NDP_F64) swarm_reduce_kernel<double><<<g2, 256, 0, st>>>(m->fpair, m->seg, (int)n_ego, n_nodes, (int)m->cap_pairs, (double*)out);
+    else swarm_reduce_kernel<float><<<g2, 256, 0, st>>>(m->fpair, m->seg, (int)n_ego, n_nodes, (int)m->cap_pairs, (float*)out);
     m->launches++;
     CU(cudaGetLastError());
+    return 0;
+}
+
+int ndp_mlp_set_pair_budget(ndp_mlp* m, int64_t max_pairs) {
+    if (!m || max_pairs < 1) return fail(NDP_E_ARG, "ndp_mlp_set_pair_budget: bad argument");
+    std::lock_guard<std::mutex> lk(m->mu);
+    m->pair_budget = max_pairs;
     return 0;
 }
 

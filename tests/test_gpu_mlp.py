@@ -159,3 +159,33 @@ def test_swarm_parts_equal_single_buffer(nn, mlp_weights):
         assert torch.equal(out, single)
         ref = mlp_numpy.swarm_forces(mlp_weights, traj, ego_begin, n_ego)
         assert np.abs(out.cpu().numpy() - ref).max() < 5e-5
+
+
+def test_swarm_device_sized_vs_read_back_and_multi_tile(nn, mlp_weights):
+    """The pair count stays on the device when the worst case fits the pair budget; above the budget the
+    4-byte count is read back and the buffers grow.  Both routes give identical forces; n_all > one
+    2048-position tile exercises the tiled neighbour search."""
+    from ndp_nmpc_qd_b200 import _lib
+
+    rng = np.random.default_rng(11)
+    n_all, n_nodes = 2500, 21
+    traj = np.zeros((n_all, n_nodes, 6), np.float32)
+    traj[:, :, 0:2] = rng.uniform(0, 30.0, size=(n_all, 1, 2)) + 0.02 * np.arange(n_nodes)[None, :, None]
+    traj[:, :, 2] = rng.uniform(0.5, 3.5, size=(n_all, 1))
+    traj[:, :, 3:6] = 0.2 * rng.normal(size=(n_all, 1, 3))
+    t = torch.as_tensor(traj, device="cuda")
+    ego_begin, n_ego = 300, 500   # worst case 500 * 2499 pairs < 2 Mi: device-sized
+    l0 = nn.launch_count
+    f_dev = nn.forward_swarm(t, ego_begin, n_ego)
+    assert nn.launch_count - l0 == 3  # pair lists, MLP, ordered sum (+ one 4-byte memset)
+    from ndp_nmpc_qd_b200.dnwash_nn_est import DownwashNN
+
+    nn2 = DownwashNN()  # fresh handle: no buffers yet
+    _lib.check(nn2.lib.ndp_mlp_set_pair_budget(nn2._h, 64), "budget")   # forces read-back + growth from 64 pairs
+    f_rb = nn2.forward_swarm(t, ego_begin, n_ego)
+    assert nn2.launch_count == 4  # the pair-list kernel ran twice (overflow, then the grown buffer)
+    torch.cuda.synchronize()
+    assert torch.equal(f_dev, f_rb)
+    ref = mlp_numpy.swarm_forces(mlp_weights, traj, ego_begin, n_ego)
+    assert np.abs(ref).max() > 1.0
+    assert np.abs(f_dev.cpu().numpy() - ref).max() < 3e-4
