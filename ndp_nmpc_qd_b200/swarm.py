@@ -56,6 +56,7 @@ class SwarmStep:
         self.nn = DownwashNN(device=self.device)
         self.f = torch.zeros((max(self.n_local, 1), N + 1, 3), dtype=self.dtype, device=self.device)
         self.step_no = 0
+        self.trace = None  # set to a list to collect (label, cuda event) marks of every step (tools/swarm_multi_gpu.py --trace)
         shape = (2, self.part, N + 1, 6)  # double-buffered by step parity: one barrier per step is enough
         if self.mode == "p2p":
             import torch.distributed._symmetric_memory as symm
@@ -74,13 +75,17 @@ class SwarmStep:
         par = self.step_no & 1
         self.step_no += 1
         mine = self.buf[par]
+        self._mark("begin")
         if self.n_local:
             pack_horizons(xr_local, mine[: self.n_local])
+        self._mark("pack")
         if self.mode == "p2p":
             self.hdl.barrier(channel=par)  # every shard of this parity is written; peers are done with its previous use
+            self._mark("exchange")
             parts, part_rows = self._ptrs[par], self.part
         elif self.mode == "allgather":
             self.dist.all_gather_into_tensor(self.gathered, mine, group=self.group)
+            self._mark("exchange")
             parts, part_rows = [self.gathered.data_ptr()], self.world * self.part
         else:
             parts, part_rows = [mine.data_ptr()], self.part
@@ -90,10 +95,19 @@ class SwarmStep:
                 self.nn._h, _lib.NDP_F32 if self.dtype == torch.float32 else _lib.NDP_F64, len(parts), ptrs, part_rows, self.n_all,
                 self.begin, self.n_local, self.N + 1, None if odom_xy is None else C.c_void_p(odom_xy.data_ptr()), float(DP.r_horiz),
                 C.c_void_p(self.f.data_ptr()), 0, C.c_void_p(torch.cuda.current_stream().cuda_stream)), "ndp_mlp_forward_swarm_parts")
+        self._mark("forces")
         return self.f
+
+    def _mark(self, label: str):
+        if self.trace is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self.trace.append((label, ev))
 
     def step(self, x0: torch.Tensor, xr: torch.Tensor, ur: torch.Tensor, odom_xy: Optional[torch.Tensor] = None,
              u0: Optional[torch.Tensor] = None) -> torch.Tensor:
         """one RTI step of the local egos: exchange + gated all-pairs MLP + NDP-NMPC update."""
         f = self.forces(xr, odom_xy)
-        return self.engine.update(x0, xr, ur, f, u0)
+        u0 = self.engine.update(x0, xr, ur, f, u0)
+        self._mark("update")
+        return u0

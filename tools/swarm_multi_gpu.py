@@ -20,8 +20,10 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quads", type=int, default=1024)
     ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=200)
     ap.add_argument("--check", action="store_true")
     ap.add_argument("--breakdown", action="store_true")
+    ap.add_argument("--trace", action="store_true", help="per-phase device time inside the timed step loop (CUDA event marks)")
     a = ap.parse_args()
     rank, world, lr = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(lr)
@@ -47,7 +49,7 @@ def main():
         x0 = xr[:, 0].contiguous()
         sw.engine.reset(xr, ur)
         u0 = torch.empty((e - b, 4), dtype=torch.float32, device=dev)
-        for _ in range(5):
+        for _ in range(a.warmup):   # long enough for clocks / lazy module loads to settle (the first mode timed is otherwise inflated)
             sw.step(x0, xr, ur, None, u0)
         torch.cuda.synchronize()
         if world > 1:
@@ -64,6 +66,26 @@ def main():
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         res[mode] = dict(ms_per_step=float(ms) / a.steps, quad_steps_per_s=n_all * a.steps / (float(ms) * 1e-3))
+        if a.trace:
+            t_keep, f_keep = t_loc.clone(), sw.f.clone()
+            sw.trace = []
+            for _ in range(a.steps):
+                t_loc.add_(0.02)
+                rg.horizon(t_loc, None, 20, 0.1, off_loc, xr=xr, ur=ur)
+                sw.step(x0, xr, ur, None, u0)
+            torch.cuda.synchronize()
+            acc, prev = {}, None
+            for label, ev in sw.trace:
+                if label != "begin":
+                    acc[label] = acc.get(label, 0.0) + prev.elapsed_time(ev) * 1e3 / a.steps
+                else:
+                    if prev is not None:
+                        acc["refgen"] = acc.get("refgen", 0.0) + prev.elapsed_time(ev) * 1e3 / a.steps
+                prev = ev
+            res[mode]["trace_us_rank%d" % rank] = acc
+            sw.trace = None
+            t_loc.copy_(t_keep)
+            sw.f.copy_(f_keep)
         f_by_mode[mode] = sw.f[: e - b].clone()
         if a.breakdown:
             import time
