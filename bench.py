@@ -317,9 +317,45 @@ def run_native(args, rank, local_rank, world):
         out["cpu_baseline"] = cpu_oracle_rate(sets, seconds=12.0)[0]
     if world == 1 and not args.no_latency:
         out["latency_b1"] = batch1_latency(dev)
+        out["stress"] = stress_variant(dev, B)
     print(json.dumps(out), flush=True)
     if dist is not None:
         dist.destroy_process_group()
+
+
+def stress_variant(dev, B, steps=20):
+    """SURVEY.md 8(d) stress variant of config 3 (exercises the inequality path, which the nominal
+    distribution never does): 5x perturbation scale, tightened bounds (omega_max 1.5 rad/s, c_max 15 m/s^2),
+    disturbance forces ~ N(0, 1 N).  Every timed solve starts from the iterate reset to the reference."""
+    import torch
+
+    from ndp_nmpc_qd_b200 import workloads as wl
+    from ndp_nmpc_qd_b200.solver import Engine
+
+    w = wl.independent_problems(B, N=N_HORIZON, seed=5, scale=5.0)
+    fd = np.random.default_rng(6).normal(size=(B, N_HORIZON + 1, 3))
+    eng = Engine(batch=B, N=N_HORIZON, np_=7, precision="f32", device=dev, u_min=[-1.5, -1.5, -1.5, 0.0], u_max=[1.5, 1.5, 1.5, 15.0])
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float32, device=dev)
+    x0, xr, ur, f = t(w["x0"]), t(w["xr"]), t(w["ur"]), t(fd)
+    u0 = torch.empty((B, NU), dtype=torch.float32, device=dev)
+    ms = []
+    for s in range(steps + 3):
+        eng.reset(xr, ur)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        eng.update(x0, xr, ur, f, u0)
+        e1.record()
+        torch.cuda.synchronize()
+        if s >= 3:
+            ms.append(e0.elapsed_time(e1))
+    st, status = eng.stats().cpu().numpy(), eng.status().cpu().numpy()
+    n_fact = float(st[:, 0].mean())
+    k_ms = float(np.mean(ms))
+    return dict(value=B / (k_ms * 1e-3), unit=UNIT, kernel_ms=k_ms, riccati_sweeps_mean=n_fact, riccati_sweeps_max=int(st[:, 0].max()),
+                constrained_share=float((st[:, 0] > 1).mean()), ipm_share=float((st[:, 1] > 0).mean()),
+                active_bounds_mean=float(st[:, 3].mean()), status_nonzero=int((status != 0).sum()),
+                achieved_tflops=algorithmic_flop_per_solve(N_HORIZON, n_fact) * B / (k_ms * 1e-3) / 1e12,
+                note="RTI kernel only (no MLP): 5x perturbation, omega_max 1.5, c_max 15, f ~ N(0,1); iterate reset before every solve")
 
 
 def batch1_latency(dev):

@@ -33,22 +33,23 @@ def is_stale() -> bool:
     return any(os.path.getmtime(s) > t for s in sources())
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not is_stale():
+def build(force: bool = False, verbose: bool = False, defines=(), out: str = OUT) -> str:
+    """defines / out: variant builds for A/B measurements (tools/), the product is the default."""
+    if not force and out == OUT and not is_stale():
         return OUT
-    os.makedirs(OUT_DIR, exist_ok=True)
+    os.makedirs(os.path.dirname(out), exist_ok=True)
     cmd = [
         _nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
         "-Xcompiler", "-fPIC", "-shared", "--expt-relaxed-constexpr", "-Xptxas", "-v" if verbose else "-O3",
-        "-ccbin", "/usr/bin/g++", "-o", OUT, SRC, "-lcuda",
-    ]
+        "-ccbin", "/usr/bin/g++", "-o", out, SRC, "-lcuda",
+    ] + [f"-D{d}" for d in defines]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
         raise RuntimeError("nvcc failed building libndp_nmpc_b200.so")
     if verbose:
         sys.stderr.write(res.stderr)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":

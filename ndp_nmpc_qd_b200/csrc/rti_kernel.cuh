@@ -266,14 +266,32 @@ __device__ __forceinline__ void backward_terminal(const RtiCfg<T>& c, int N, int
     __syncwarp(mask);
 }
 
+// Active set of one lane's box (the input or velocity component this lane owns) over the horizon: bit k of
+// `lo` / `hi` = pinned at the lower / upper bound at stage k.  Two 64-bit words each: N <= 128.
+struct StageMask {
+    unsigned long long w0, w1;
+    __device__ __forceinline__ StageMask() : w0(0ull), w1(0ull) {}
+    __device__ __forceinline__ bool test(int k) const { return (((k < 64) ? w0 : w1) >> (k & 63)) & 1ull; }
+    __device__ __forceinline__ void set(int k) { const unsigned long long b = 1ull << (k & 63); if (k < 64) w0 |= b; else w1 |= b; }
+    __device__ __forceinline__ void clear(int k) { const unsigned long long b = ~(1ull << (k & 63)); if (k < 64) w0 &= b; else w1 &= b; }
+};
+// active-set data of the rounds that keep it in registers (backward_stage kBar == 2)
+template <typename T>
+struct ActiveSet {
+    StageMask lo_m, hi_m;
+    T lo, hi, big;
+};
+
 // One backward Riccati stage on the tile `sT` ([10][TLD]: columns 6..13 of [A_k B_k], then b_k), which
 // must be complete and visible.  colp = this lane's column inside the tile (or the constant tile of the
 // trivial columns 0..5: dx+/dp = [I;0;0], dx+/dv = [hI;I;0]).  kBar: add the barrier / active-set
-// diagonal and gradient; kRows: store the rows of [Hux Guu | g_u] needed by the active-set multiplier
-// test.  Returns false on a non-positive pivot.
-template <typename T, bool kBar, bool kRows>
+// diagonal and gradient (1: from the workspace arrays oBarD / oBarG; 2: pinned inputs of the register-held
+// active set `as`); kRows: store the rows of [Hux Guu | g_u] needed by the active-set multiplier test.
+// Returns false on a non-positive pivot.
+template <typename T, int kBar, bool kRows>
 __device__ __forceinline__ bool backward_stage(const RtiCfg<T>& c, int k, int j, unsigned mask, T* sm, const SmemLayout& L, T* ws,
-                                               const WsLayout& WL, const T* __restrict__ sT, const T* __restrict__ colp) {
+                                               const WsLayout& WL, const T* __restrict__ sT, const T* __restrict__ colp,
+                                               const ActiveSet<T>* as) {
     const T* sX = sm + L.oX;
     const T* sU = sm + L.oU;
     const T* sPar = sm + L.oPar;
@@ -326,7 +344,19 @@ __device__ __forceinline__ bool backward_stage(const RtiCfg<T>& c, int k, int j,
             for (int m = 0; m < 4; m++) ws[WL.oHrow + (k * 4 + m) * 16 + 14] = H[10 + m];
         }
     }
-    if (kBar) {
+    if (kBar == 2) {
+        // pinned input m: penalty big (u_m - bound)^2 / 2 -> diagonal big, gradient -big * (bound - iterate)
+        const bool at_lo = as->lo_m.test(k), at_hi = as->hi_m.test(k);
+        const bool pin = (j >= 10 && j < 14) && (at_lo || at_hi);
+        const T bnd = (at_lo ? as->lo : as->hi) - sU[k * NU + ((j - 10) & 3)];
+        const T g_own = pin ? -as->big * bnd : T(0);
+#pragma unroll
+        for (int m = 0; m < 4; m++) {
+            const T gm = __shfl_sync(mask, g_own, 10 + m, GL);
+            if (j == 14) H[10 + m] += gm;
+            else H[10 + m] += (pin && j == 10 + m) ? as->big : T(0);
+        }
+    } else if (kBar == 1) {
         if (j < 14) {
             const T d = ws[WL.oBarD + k * 16 + j];
 #pragma unroll
@@ -412,9 +442,9 @@ __device__ __forceinline__ void tile_to_ws(const T* __restrict__ sT, T* __restri
 // state is integrated redundantly by every lane, so x+ comes for free) straight into the two tiles,
 // which are also saved to the workspace for the forward sweep / later IPM sweeps.  !kLin: tiles are
 // re-loaded from the workspace, one stage ahead of their use.
-template <typename T, bool kLin, bool kBar, bool kRows>
+template <typename T, bool kLin, int kBar, bool kRows>
 __device__ __forceinline__ bool backward_sweep(const RtiCfg<T>& c, int N, int j, unsigned mask, T* sm, const SmemLayout& L, T* ws,
-                                               const WsLayout& WL, const T* __restrict__ sTriv) {
+                                               const WsLayout& WL, const T* __restrict__ sTriv, const ActiveSet<T>* as) {
     backward_terminal<T>(c, N, j, mask, sm, L);
     bool ok = true;
     T* sT0 = sm + L.oT0;
@@ -448,10 +478,10 @@ __device__ __forceinline__ bool backward_sweep(const RtiCfg<T>& c, int N, int j,
             }
             __syncwarp(mask);
             tile_to_ws<T>(sT0, ws + WL.oRec + (long long)k * 14 * TLD, j);
-            ok &= backward_stage<T, kBar, kRows>(c, k, j, mask, sm, L, ws, WL, sT0, col0);
+            ok &= backward_stage<T, kBar, kRows>(c, k, j, mask, sm, L, ws, WL, sT0, col0, as);
             if (k >= 1) {
                 tile_to_ws<T>(sT1, ws + WL.oRec + (long long)(k - 1) * 14 * TLD, j);
-                ok &= backward_stage<T, kBar, kRows>(c, k - 1, j, mask, sm, L, ws, WL, sT1, col1);
+                ok &= backward_stage<T, kBar, kRows>(c, k - 1, j, mask, sm, L, ws, WL, sT1, col1, as);
             }
         }
     } else {
@@ -477,7 +507,7 @@ __device__ __forceinline__ bool backward_sweep(const RtiCfg<T>& c, int N, int j,
         int par = 0;
         for (int k = N - 1; k >= 0; k--) {
             if (k >= 1) fetch(k - 1);
-            ok &= backward_stage<T, kBar, kRows>(c, k, j, mask, sm, L, ws, WL, par ? sT1 : sT0, par ? col1 : col0);
+            ok &= backward_stage<T, kBar, kRows>(c, k, j, mask, sm, L, ws, WL, par ? sT1 : sT0, par ? col1 : col0, as);
             if (k >= 1) {
                 put(par ? sT0 : sT1);
                 __syncwarp(mask);
@@ -633,10 +663,11 @@ __device__ __forceinline__ void forward_sweep(const RtiCfg<T>& c, int N, int lan
 enum { IPM_LL = 0, IPM_LU, IPM_TL, IPM_TU, IPM_CL, IPM_CU, IPM_ACT };
 
 // Constrained QP of one problem (the unconstrained step left its box): kept out of line so that the nominal
-// path of rti_step_kernel keeps its register allocation.  On return sDz holds the QP step; returns the status.
+// path of rti_step_kernel keeps its register allocation (nothing but the problem loop's own state is live
+// across the call): solves the QP, writes the new iterate, u0, status and statistics of the problem.
 template <typename T, int kN>
-__device__ __noinline__ int constrained_qp(const RtiCfg<T>& c, int lane, unsigned mask, T* sm, T* ws, const T* sTriv, T dx0, T lo, T hi,
-                                           T* gX, T* gU, const T* gY, int* counts) {
+__device__ __noinline__ void constrained_qp(const RtiCfg<T>& c, int lane, unsigned mask, T* sm, T* ws, const T* sTriv, T dx0, T lo, T hi,
+                                            T* gX, T* gU, const T* gY, T* gu0, int32_t* g_status, int32_t* g_stats) {
     const int N = (kN > 0) ? kN : c.N;
     const SmemLayout L(N);
     const WsLayout WL(N);
@@ -646,7 +677,7 @@ __device__ __noinline__ int constrained_qp(const RtiCfg<T>& c, int lane, unsigne
     const bool isx = lane < 10, isu = (lane >= 10 && lane < 14), isv = (lane >= 3 && lane < 6);
     auto iter_at = [&](int k) -> T { return isx ? sX[k * NX + lane] : (isu ? sU[k * NU + (lane - 10)] : T(0)); };
     auto has_box = [&](int k) -> bool { return (isu && k < N) || (isv && k >= 1 && k < N); };
-    int status = 0, n_fact = 0, n_ipm = 0, n_pol = 0;
+    int status = 0, n_fact = 1, n_ipm = 0, n_pol = 0;  // the unconstrained sweep counts as the first factorisation
     bool viol = false, bad = false;
     int nact_l = 0;
         {   // the accepted-sweep ring overwrote the cost records: rebuild them from the stored yref
@@ -668,24 +699,77 @@ __device__ __noinline__ int constrained_qp(const RtiCfg<T>& c, int lane, unsigne
         // Phase 0: primal-dual active-set rounds seeded by the bounds the unconstrained step violates (its
         // tentative iterate is in gX / gU).  A fixed point of the rounds satisfies the KKT conditions of the QP,
         // so it is the same solution the interior-point method converges to, at one Riccati factorisation per
-        // round instead of two per IPM iteration.  Phase 1 (velocity box involved, or no fixed point within
-        // as_first_max rounds): Mehrotra IPM, then the rounds again from the IPM's active set.
-        for (int k = 0; k <= N; k++) {
-            bD[k * 16 + lane] = T(0);
-            bG[k * 16 + lane] = T(0);
-            wZ[k * 16 + lane] = (k == 0 && isx) ? dx0 : T(0);
-        }
+        // round instead of two per IPM iteration.  The active set lives in registers (two bit masks per lane),
+        // so a round touches the workspace only for the stage tiles and the multiplier rows.
+        // Phase 1 (velocity box involved, or no fixed point within as_first_max rounds): Mehrotra IPM, then the
+        // rounds again from the IPM's active set.
+        ActiveSet<T> as;
+        as.lo = lo; as.hi = hi; as.big = c.big;
         bool seed_x = false;
         for (int k = 0; k < N; k++)
             if (has_box(k)) {
                 const T v = isu ? gU[k * NU + (lane - 10)] : gX[k * NX + lane];
-                wI[IPM_ACT * FS + k * 16 + lane] = isu ? ((v < lo) ? T(1) : ((v > hi) ? T(2) : T(0))) : T(0);
-                if (isv) seed_x |= !(v >= lo && v <= hi);
+                if (isu) {
+                    if (v < lo) as.lo_m.set(k);
+                    else if (v > hi) as.hi_m.set(k);
+                } else {
+                    seed_x |= !(v >= lo && v <= hi);
+                }
             }
         seed_x = __any_sync(mask, seed_x);
         __syncwarp(mask);
-        for (int phase = (seed_x || c.as_first_max <= 0) ? 1 : 0; phase < 2 && !pol_ok && status == 0; phase++) {
-        if (phase == 1) {
+        if (!seed_x && c.as_first_max > 0) {
+            for (int round = 0; round < c.as_first_max; round++) {
+                if (!backward_sweep<T, false, 2, true>(c, N, lane, mask, sm, L, ws, WL, sTriv, &as)) break;
+                n_fact++;
+                n_pol++;
+                forward_sweep<T, false>(c, N, lane, mask, dx0, sm, L, ws, WL, lo, hi, gX, gU, nullptr, viol, bad, nact_l);
+                bool changed = false, xviol = false;
+                if (isv)
+                    for (int k = 1; k < N; k++) {
+                        const T it_v = sX[k * NX + lane], zn = sDz[k * 16 + lane];
+                        xviol |= !(zn >= lo - it_v && zn <= hi - it_v);
+                    }
+                if (isu)
+                    for (int k = 0; k < N; k++) {
+                        const T it_v = sU[k * NU + (lane - 10)];
+                        const bool at_lo = as.lo_m.test(k), at_hi = as.hi_m.test(k);
+                        if (at_lo || at_hi) {
+                            // multiplier of the pinned input from the un-penalised row of [Hux Guu | g_u]
+                            const T* hr = ws + WL.oHrow + (k * 4 + (lane - 10)) * 16;
+                            T gq = hr[14];
+#pragma unroll
+                            for (int i = 0; i < 14; i++) gq += hr[i] * sDz[k * 16 + i];
+                            if ((at_hi ? -gq : gq) < T(0)) { as.lo_m.clear(k); as.hi_m.clear(k); changed = true; }
+                        } else {
+                            const T zn = sDz[k * 16 + lane];
+                            if (zn > hi - it_v) { as.hi_m.set(k); changed = true; }
+                            else if (zn < lo - it_v) { as.lo_m.set(k); changed = true; }
+                        }
+                    }
+                changed = __any_sync(mask, changed);
+                xviol = __any_sync(mask, xviol);
+                __syncwarp(mask);
+                if (xviol) break;  // a velocity box is violated: that needs the interior-point route
+                if (!changed) { pol_ok = true; break; }
+            }
+            if (pol_ok && isu) {
+                // pinned inputs sit exactly on their bound
+                for (int k = 0; k < N; k++) {
+                    const T it_v = sU[k * NU + (lane - 10)];
+                    if (as.lo_m.test(k)) sDz[k * 16 + lane] = lo - it_v;
+                    if (as.hi_m.test(k)) sDz[k * 16 + lane] = hi - it_v;
+                }
+            }
+        }
+        if (!pol_ok && status == 0) {
+        {
+            for (int k = 0; k <= N; k++) {
+                bD[k * 16 + lane] = T(0);
+                bG[k * 16 + lane] = T(0);
+                wZ[k * 16 + lane] = (k == 0 && isx) ? dx0 : T(0);
+            }
+            __syncwarp(mask);
         // ================= Mehrotra IPM on the Riccati kernel =================
             int nb_l = 0;
             for (int k = 0; k < N; k++)
@@ -731,7 +815,7 @@ __device__ __noinline__ int constrained_qp(const RtiCfg<T>& c, int lane, unsigne
                 mu_prev = mu;
                 __syncwarp(mask);
                 // ---- predictor ----
-                if (!backward_sweep<T, false, true, false>(c, N, lane, mask, sm, L, ws, WL, sTriv)) { status = 4; break; }
+                if (!backward_sweep<T, false, 1, false>(c, N, lane, mask, sm, L, ws, WL, sTriv, nullptr)) { status = 4; break; }
                 n_fact++;
                 forward_sweep<T, false>(c, N, lane, mask, dx0, sm, L, ws, WL, lo, hi, gX, gU, nullptr, viol, bad, nact_l);
                 T amax = T(1e30);
@@ -782,7 +866,7 @@ __device__ __noinline__ int constrained_qp(const RtiCfg<T>& c, int lane, unsigne
                         bG[e] = ((sigma_mu - cu) / tu - gu * ub + lu) - ((sigma_mu - cl) / tl + gl * lb + ll);
                     }
                 __syncwarp(mask);
-                if (!backward_sweep<T, false, true, false>(c, N, lane, mask, sm, L, ws, WL, sTriv)) { status = 4; break; }
+                if (!backward_sweep<T, false, 1, false>(c, N, lane, mask, sm, L, ws, WL, sTriv, nullptr)) { status = 4; break; }
                 n_fact++;
                 forward_sweep<T, false>(c, N, lane, mask, dx0, sm, L, ws, WL, lo, hi, gX, gU, nullptr, viol, bad, nact_l);
                 amax = T(1e30);
@@ -833,8 +917,7 @@ __device__ __noinline__ int constrained_qp(const RtiCfg<T>& c, int lane, unsigne
             }
         }
         // ================= active-set rounds =================
-        if (status == 0 && (phase ? c.polish_max : c.as_first_max) > 0) {
-            if (phase == 1)
+        if (status == 0 && c.polish_max > 0) {
                 for (int k = 0; k < N; k++)
                     if (has_box(k)) {
                         const int e = k * 16 + lane;
@@ -842,7 +925,7 @@ __device__ __noinline__ int constrained_qp(const RtiCfg<T>& c, int lane, unsigne
                         const T ll = wI[IPM_LL * FS + e], lu = wI[IPM_LU * FS + e];
                         wI[IPM_ACT * FS + e] = (tl < ll) ? T(1) : ((tu < lu) ? T(2) : T(0));
                     }
-            for (int round = 0; round < (phase ? c.polish_max : c.as_first_max); round++) {
+            for (int round = 0; round < c.polish_max; round++) {
                 for (int k = 0; k < N; k++)
                     if (has_box(k)) {
                         const int e = k * 16 + lane;
@@ -865,7 +948,7 @@ __device__ __noinline__ int constrained_qp(const RtiCfg<T>& c, int lane, unsigne
                         }
                     }
                 __syncwarp(mask);
-                if (!backward_sweep<T, false, true, true>(c, N, lane, mask, sm, L, ws, WL, sTriv)) break;
+                if (!backward_sweep<T, false, 1, true>(c, N, lane, mask, sm, L, ws, WL, sTriv, nullptr)) break;
                 n_fact++;
                 n_pol++;
                 forward_sweep<T, false>(c, N, lane, mask, dx0, sm, L, ws, WL, lo, hi, gX, gU, nullptr, viol, bad, nact_l);
@@ -923,10 +1006,33 @@ __device__ __noinline__ int constrained_qp(const RtiCfg<T>& c, int lane, unsigne
             if (!ipm_ok && status == 0) status = 4;
         }
         __syncwarp(mask);
-    counts[0] = n_fact;
-    counts[1] = n_ipm;
-    counts[2] = n_pol;
-    return status;
+    // ---- write back: full step, overwrite the tentative iterate of the unconstrained sweep ----
+    bool bad2 = false;
+    nact_l = 0;
+    if (lane < 14)
+        for (int k = 0; k <= N; k++) {
+            if (k == N && !isx) break;
+            const T v = iter_at(k) + sDz[k * 16 + lane];
+            bad2 |= !(fabs(v) <= T(1e30));
+            if (has_box(k)) nact_l += (v <= lo) + (v >= hi);
+            if (isx) sX[k * NX + lane] = v;
+            else sU[k * NU + (lane - 10)] = v;
+        }
+    bad2 = __any_sync(mask, bad2);
+    const int nact = (int)grp_sum<float>((float)nact_l, mask);
+    if (bad2) status = 1;
+    __syncwarp(mask);
+    for (int i = lane; i < (N + 1) * NX; i += GL) gX[i] = sX[i];
+    for (int i = lane; i < N * NU; i += GL) gU[i] = sU[i];
+    if (gu0 && lane < NU) gu0[lane] = sU[lane];
+    if (lane == 0) {
+        *g_status = status;
+        g_stats[0] = n_fact;
+        g_stats[1] = n_ipm;
+        g_stats[2] = n_pol;
+        g_stats[3] = nact;
+    }
+    __syncwarp(mask);
 }
 
 constexpr int RTI_CTA = 64;  // threads per CTA of the nominal launch (4 problems)
@@ -962,7 +1068,7 @@ __global__ void __launch_bounds__(RTI_CTA, (sizeof(T) == 4) ? 8 : 3) rti_step_ke
 #pragma unroll
     for (int m = 0; m < 4; m++)
         if (lane == 10 + m) { lo = c.umin[m]; hi = c.umax[m]; }
-    const bool isx = lane < 10, isu = (lane >= 10 && lane < 14), isv = (lane >= 3 && lane < 6);
+    const bool isx = lane < 10;
 
     for (int prob = blockIdx.x * ppc + grp; prob < a.B; prob += gridDim.x * ppc) {
         T* gX = a.X + (size_t)prob * (N + 1) * NX;
@@ -1027,63 +1133,34 @@ __global__ void __launch_bounds__(RTI_CTA, (sizeof(T) == 4) ? 8 : 3) rti_step_ke
         __syncwarp(mask);
         const T dx0 = isx ? x0v - sX[lane] : T(0);
 
-        int status = 0, n_fact = 0, n_ipm = 0, n_pol = 0;
-        // iterate value of the variable this lane owns at stage k
-        auto iter_at = [&](int k) -> T { return isx ? sX[k * NX + lane] : (isu ? sU[k * NU + (lane - 10)] : T(0)); };
-        auto has_box = [&](int k) -> bool { return (isu && k < N) || (isv && k >= 1 && k < N); };
+        int status = 0;
 
         // ---- preparation + unconstrained feedback; the step is accepted on the fly ----
-        bool ok = backward_sweep<T, true, false, false>(c, N, lane, mask, sm, L, ws, WL, sTriv);
-        n_fact++;
+        bool ok = backward_sweep<T, true, 0, false>(c, N, lane, mask, sm, L, ws, WL, sTriv, nullptr);
         bool viol = false, bad = false;
         int nact_l = 0;
         forward_sweep<T, true>(c, N, lane, mask, dx0, sm, L, ws, WL, lo, hi, gX, gU, a.u0 ? a.u0 + (size_t)prob * NU : nullptr, viol, bad,
                                nact_l);
-        if (!ok) status = 4;
-        const bool nominal = ok && !viol;
-
         if (ok && viol) {
-            int cnt[3];
-            status = constrained_qp<T, kN>(c, lane, mask, sm, ws, sTriv, dx0, lo, hi, gX, gU,
-                                           (a.xr != nullptr ? a.yref_w : a.yref) + (size_t)prob * (N + 1) * NYS, cnt);
-            n_fact += cnt[0];
-            n_ipm = cnt[1];
-            n_pol = cnt[2];
-        }
-
-        // ---- write back ----
-        int nact;
-        if (nominal || !ok) {
-            // the forward sweep already stored the new iterate and u0
-            nact = (int)grp_sum<float>((float)nact_l, mask);
-            if (bad) status = 1;
+            // Called through an opaque function pointer: ptxas then allocates the nominal path against the plain ABI
+            // instead of against this callee's register use (measured: 77.2 us vs 81-84 us per launch at B = 4096
+            // with a direct call, and the nominal path no longer moves when the constrained path changes).
+            auto fn = &constrained_qp<T, kN>;
+            asm volatile("" : "+l"(fn));
+            fn(c, lane, mask, sm, ws, sTriv, dx0, lo, hi, gX, gU, (a.xr != nullptr ? a.yref_w : a.yref) + (size_t)prob * (N + 1) * NYS,
+               a.u0 ? a.u0 + (size_t)prob * NU : nullptr, a.status + prob, a.stats + (size_t)prob * 4);
         } else {
-            // constrained step from the IPM / active-set rounds: full step, overwrite the tentative iterate
-            bool bad2 = false;
-            nact_l = 0;
-            if (lane < 14)
-                for (int k = 0; k <= N; k++) {
-                    if (k == N && !isx) break;
-                    const T v = iter_at(k) + sDz[k * 16 + lane];
-                    bad2 |= !(fabs(v) <= T(1e30));
-                    if (has_box(k)) nact_l += (v <= lo) + (v >= hi);
-                    if (isx) sX[k * NX + lane] = v;
-                    else sU[k * NU + (lane - 10)] = v;
-                }
-            bad2 = __any_sync(mask, bad2);
-            nact = (int)grp_sum<float>((float)nact_l, mask);
-            if (bad2) status = 1;
-            __syncwarp(mask);
-            for (int i = lane; i < (N + 1) * NX; i += GL) gX[i] = sX[i];
-            for (int i = lane; i < N * NU; i += GL) gU[i] = sU[i];
-            if (a.u0 && lane < NU) a.u0[(size_t)prob * NU + lane] = sU[lane];
-        }
-        if (lane == 0) {
-            a.status[prob] = status;
-            a.stats[prob * 4 + 0] = n_fact;
-            a.stats[prob * 4 + 1] = n_ipm;
-            a.stats[prob * 4 + 2] = n_pol;
-            a.stats[prob * 4 + 3] = nact;
+            // the forward sweep already stored the new iterate and u0
+            if (!ok) status = 4;
+            const int nact = (int)grp_sum<float>((float)nact_l, mask);
+            if (bad) status = 1;
+            if (lane == 0) {
+                a.status[prob] = status;
+                a.stats[prob * 4 + 0] = 1;
+                a.stats[prob * 4 + 1] = 0;
+                a.stats[prob * 4 + 2] = 0;
+                a.stats[prob * 4 + 3] = nact;
+            }
         }
         __syncwarp(mask);
     }

@@ -19,6 +19,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quads", type=int, default=1024)
     ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--dense", action="store_true")
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
     n_all = a.quads
@@ -54,6 +55,22 @@ def main():
                         f_abs_max=float(f.abs().max())))
     for o in out:
         print(json.dumps(o))
+    if a.dense:
+        # SURVEY.md 8(d) config 4, un-gated dense case: every pair passes the gate -> n (n - 1) x 21 MLP rows per step
+        traj = xr[:, :, 0:6].float().contiguous()
+        ms = []
+        for s in range(6):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            f = sw.nn.forward_swarm(traj, 0, n_all, r_horiz=1e6)
+            e1.record()
+            torch.cuda.synchronize()
+            if s >= 2:
+                ms.append(e0.elapsed_time(e1))
+        rows = n_all * (n_all - 1) * 21
+        t = float(np.mean(ms)) * 1e-3
+        print(json.dumps(dict(dense_rows=rows, forces_ms=t * 1e3, mlp_rows_per_s=rows / t, algorithmic_tflops=rows * 35072 / t / 1e12,
+                              f_abs_max=float(f.abs().max()))))
 
 
 if __name__ == "__main__":
