@@ -40,7 +40,7 @@ struct ndp_handle {
     void *X, *U, *yref, *par, *ws;
     int32_t *status, *stats;
     long long ws_stride;
-    int slots, grid, ppc;
+    int slots, grid, ppc, lat;
     size_t smem;
     std::atomic<long long> launches;
     std::mutex mu;
@@ -148,6 +148,40 @@ RtiCfg<T> make_cfg(const ndp_config& g) {
     return c;
 }
 
+// ---- the RTI kernel instantiations live in their own translation units (rti_inst.cu) ----
+#define NDP_RTI_DECL(tag, T)                                                                                   \
+    void rti_launch_##tag(int, int, size_t, cudaStream_t, const RtiCfg<T>&, const RtiArgs<T>&);                \
+    const void* rti_kernel_##tag();
+NDP_RTI_DECL(f32_20_0, float) NDP_RTI_DECL(f32_40_0, float) NDP_RTI_DECL(f32_80_0, float) NDP_RTI_DECL(f32_0_0, float)
+NDP_RTI_DECL(f32_20_1, float)
+NDP_RTI_DECL(f64_20_0, double) NDP_RTI_DECL(f64_40_0, double) NDP_RTI_DECL(f64_80_0, double) NDP_RTI_DECL(f64_0_0, double)
+#undef NDP_RTI_DECL
+
+template <typename T>
+struct RtiInst {
+    void (*launch)(int, int, size_t, cudaStream_t, const RtiCfg<T>&, const RtiArgs<T>&);
+    const void* (*kernel)();
+};
+// lat: the latency build (fp32, N = 20 only)
+template <typename T> RtiInst<T> rti_inst(int N, bool lat);
+template <> RtiInst<float> rti_inst<float>(int N, bool lat) {
+    if (lat && N == 20) return {rti_launch_f32_20_1, rti_kernel_f32_20_1};
+    switch (N) {
+        case 20: return {rti_launch_f32_20_0, rti_kernel_f32_20_0};
+        case 40: return {rti_launch_f32_40_0, rti_kernel_f32_40_0};
+        case 80: return {rti_launch_f32_80_0, rti_kernel_f32_80_0};
+        default: return {rti_launch_f32_0_0, rti_kernel_f32_0_0};
+    }
+}
+template <> RtiInst<double> rti_inst<double>(int N, bool) {
+    switch (N) {
+        case 20: return {rti_launch_f64_20_0, rti_kernel_f64_20_0};
+        case 40: return {rti_launch_f64_40_0, rti_kernel_f64_40_0};
+        case 80: return {rti_launch_f64_80_0, rti_kernel_f64_80_0};
+        default: return {rti_launch_f64_0_0, rti_kernel_f64_0_0};
+    }
+}
+
 template <typename T>
 int launch_solve(ndp_handle* h, const void* x0, void* u0, cudaStream_t st, const void* xr = nullptr, const void* ur = nullptr,
                  const void* f = nullptr) {
@@ -170,12 +204,7 @@ int launch_solve(ndp_handle* h, const void* x0, void* u0, cudaStream_t st, const
     a.ws_stride = h->ws_stride;
     a.B = h->cfg.batch;
     const int thr = h->ppc * GL;
-    switch (h->cfg.N) {
-        case 20: rti_step_kernel<T, 20><<<h->grid, thr, h->smem, st>>>(c, a); break;
-        case 40: rti_step_kernel<T, 40><<<h->grid, thr, h->smem, st>>>(c, a); break;
-        case 80: rti_step_kernel<T, 80><<<h->grid, thr, h->smem, st>>>(c, a); break;
-        default: rti_step_kernel<T, 0><<<h->grid, thr, h->smem, st>>>(c, a); break;
-    }
+    rti_inst<T>(h->cfg.N, h->lat != 0).launch(h->grid, thr, h->smem, st, c, a);
     h->launches++;
     CU(cudaGetLastError());
     return 0;
@@ -185,21 +214,8 @@ int launch_solve(ndp_handle* h, const void* x0, void* u0, cudaStream_t st, const
 
 using namespace ndp;
 
-static const void* rti_kernel_ptr(int elt, int N) {
-    if (elt == 4) {
-        switch (N) {
-            case 20: return (const void*)rti_step_kernel<float, 20>;
-            case 40: return (const void*)rti_step_kernel<float, 40>;
-            case 80: return (const void*)rti_step_kernel<float, 80>;
-            default: return (const void*)rti_step_kernel<float, 0>;
-        }
-    }
-    switch (N) {
-        case 20: return (const void*)rti_step_kernel<double, 20>;
-        case 40: return (const void*)rti_step_kernel<double, 40>;
-        case 80: return (const void*)rti_step_kernel<double, 80>;
-        default: return (const void*)rti_step_kernel<double, 0>;
-    }
+static const void* rti_kernel_ptr(int elt, int N, bool lat) {
+    return elt == 4 ? rti_inst<float>(N, lat).kernel() : rti_inst<double>(N, false).kernel();
 }
 
 static int field_geom(const ndp_handle* h, int field, void** base, int* n_int, int* sdim, int* dim, int* dim_last, int* n_stages) {
@@ -288,13 +304,20 @@ int ndp_create(const ndp_config* cfg, ndp_handle** out) {
     while (h->ppc > 1 && ((size_t)L.total * h->ppc + 10 * TLD) * h->elt > 200 * 1024) h->ppc >>= 1;  // long horizons / fp64: fewer problems per CTA
     h->smem = ((size_t)L.total * h->ppc + 10 * TLD) * h->elt;
     if (h->smem > 227 * 1024) { delete h; return fail(NDP_E_CONFIG, "ndp_create: horizon too long for shared memory"); }
-    const void* kfn = rti_kernel_ptr(h->elt, N);
-    cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem);
-    if (e != cudaSuccess) { delete h; return cuda_fail(e, "cudaFuncSetAttribute(rti_step_kernel)"); }
-    int occ = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, h->ppc * GL, h->smem);
-    if (e != cudaSuccess || occ < 1) { delete h; return e != cudaSuccess ? cuda_fail(e, "occupancy") : fail(NDP_E_CONFIG, "kernel does not fit"); }
     const int need = (B + h->ppc - 1) / h->ppc;
+    const void* kfn = nullptr;
+    cudaError_t e = cudaSuccess;
+    int occ = 0;
+    // latency build first (fp32): taken when the whole batch is resident at its lower occupancy
+    for (int lat = (h->elt == 4 && N == 20) ? 1 : 0; lat >= 0; lat--) {
+        kfn = rti_kernel_ptr(h->elt, N, lat != 0);
+        e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem);
+        if (e != cudaSuccess) { delete h; return cuda_fail(e, "cudaFuncSetAttribute(rti_step_kernel)"); }
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, h->ppc * GL, h->smem);
+        if (e != cudaSuccess || occ < 1) { delete h; return e != cudaSuccess ? cuda_fail(e, "occupancy") : fail(NDP_E_CONFIG, "kernel does not fit"); }
+        h->lat = lat;
+        if (lat == 0 || need <= n_sm * occ) break;
+    }
     const int cap = n_sm * occ;  // persistent: at most one resident wave, grid-stride over problems
     h->grid = need < cap ? need : cap;
     h->slots = h->grid * h->ppc;

@@ -1,0 +1,20 @@
+// One instantiation of the fused SQP-RTI kernel per translation unit (precision x horizon x latency build):
+// the constrained path is reached through a function pointer (rti_kernel.cuh), and ptxas compiles a kernel
+// against every address-taken candidate of its module -- one candidate per module keeps that to seconds, and the
+// instantiations build in parallel (ndp_nmpc_qd_b200/build.py).
+//   nvcc -c rti_inst.cu -DNDP_INST_T=float -DNDP_INST_N=20 -DNDP_INST_LAT=false -DNDP_INST_TAG=f32_20_0
+#include "rti_kernel.cuh"
+
+#define NDP_CAT2(a, b) a##b
+#define NDP_CAT(a, b) NDP_CAT2(a, b)
+
+namespace ndp {
+
+void NDP_CAT(rti_launch_, NDP_INST_TAG)(int grid, int threads, size_t smem, cudaStream_t st, const RtiCfg<NDP_INST_T>& c,
+                                        const RtiArgs<NDP_INST_T>& a) {
+    rti_step_kernel<NDP_INST_T, NDP_INST_N, NDP_INST_LAT><<<grid, threads, smem, st>>>(c, a);
+}
+
+const void* NDP_CAT(rti_kernel_, NDP_INST_TAG)() { return (const void*)rti_step_kernel<NDP_INST_T, NDP_INST_N, NDP_INST_LAT>; }
+
+}  // namespace ndp

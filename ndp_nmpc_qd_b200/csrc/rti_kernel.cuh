@@ -1037,8 +1037,12 @@ __device__ __noinline__ void constrained_qp(const RtiCfg<T>& c, int lane, unsign
 
 constexpr int RTI_CTA = 64;  // threads per CTA of the nominal launch (4 problems)
 
-template <typename T, int kN>
-__global__ void __launch_bounds__(RTI_CTA, (sizeof(T) == 4) ? 8 : 3) rti_step_kernel(const __grid_constant__ RtiCfg<T> c, const RtiArgs<T> a) {
+// kLat: the latency build (fp32 only) -- same code with half the resident CTAs per SM, i.e. twice the registers,
+// which ptxas spends on instruction-level parallelism.  Chosen when the whole batch is resident at that occupancy
+// (B <= 148 * 4 * 4 problems): a lone group's solve drops from ~63 to ~55 us and an active-set round from 36 to 31 us,
+// while at B = 4096 the 8-CTA build wins (77 vs 86 us) because the batch then fits one wave.
+template <typename T, int kN, bool kLat>
+__global__ void __launch_bounds__(RTI_CTA, (sizeof(T) == 4) ? (kLat ? 4 : 8) : 3) rti_step_kernel(const __grid_constant__ RtiCfg<T> c, const RtiArgs<T> a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int N = (kN > 0) ? kN : c.N;
     const SmemLayout L(N);
