@@ -37,7 +37,7 @@ class NdpConfig(C.Structure):
         ("u_min", C.c_double * 4), ("u_max", C.c_double * 4),
         ("v_min", C.c_double * 3), ("v_max", C.c_double * 3),
         ("ipm_max_iter", C.c_int32), ("polish_max", C.c_int32), ("ipm_tol_mu", C.c_double),
-        ("active_set_first", C.c_int32), ("reserved_", C.c_int32),
+        ("active_set_first", C.c_int32), ("active_set_warm", C.c_int32),
     ]
 
 

@@ -39,6 +39,7 @@ struct ndp_handle {
     int elt;  // bytes per element
     void *X, *U, *yref, *par, *ws;
     int32_t *status, *stats;
+    unsigned long long* as_store;  // [B][4][4] active set of the previous solve
     long long ws_stride;
     int slots, grid, ppc, lat;
     size_t smem;
@@ -200,6 +201,7 @@ int launch_solve(ndp_handle* h, const void* x0, void* u0, cudaStream_t st, const
     a.u0 = (T*)u0;
     a.status = h->status;
     a.stats = h->stats;
+    a.as_store = h->cfg.active_set_warm ? h->as_store : nullptr;
     a.ws = (T*)h->ws;
     a.ws_stride = h->ws_stride;
     a.B = h->cfg.batch;
@@ -280,7 +282,7 @@ void ndp_default_config(ndp_config* c) {
     c->ipm_max_iter = 50;
     c->polish_max = 6;
     c->active_set_first = 6;
-    c->reserved_ = 0;
+    c->active_set_warm = 0;
     c->ipm_tol_mu = 0.0;
 }
 
@@ -325,12 +327,14 @@ int ndp_create(const ndp_config* cfg, ndp_handle** out) {
     const size_t eb = (size_t)h->elt;
     h->X = h->U = h->yref = h->par = h->ws = nullptr;
     h->status = h->stats = nullptr;
+    h->as_store = nullptr;
     bool ok = cudaMalloc(&h->X, (size_t)B * (N + 1) * NX * eb) == cudaSuccess && cudaMalloc(&h->U, (size_t)B * N * NU * eb) == cudaSuccess &&
               cudaMalloc(&h->yref, (size_t)B * (N + 1) * NYS * eb) == cudaSuccess &&
               cudaMalloc(&h->par, (size_t)B * (N + 1) * NPS * eb) == cudaSuccess &&
               cudaMalloc(&h->ws, (size_t)h->slots * h->ws_stride * eb) == cudaSuccess &&
               cudaMalloc(&h->status, (size_t)B * sizeof(int32_t)) == cudaSuccess &&
-              cudaMalloc(&h->stats, (size_t)B * 4 * sizeof(int32_t)) == cudaSuccess;
+              cudaMalloc(&h->stats, (size_t)B * 4 * sizeof(int32_t)) == cudaSuccess &&
+              cudaMalloc(&h->as_store, (size_t)B * 16 * sizeof(unsigned long long)) == cudaSuccess;
     if (!ok) { ndp_destroy(h); return fail(NDP_E_ALLOC, "ndp_create: cudaMalloc failed"); }
     // acados initialises the iterate, yref and p to zeros
     cudaMemset(h->X, 0, (size_t)B * (N + 1) * NX * eb);
@@ -340,6 +344,7 @@ int ndp_create(const ndp_config* cfg, ndp_handle** out) {
     cudaMemset(h->ws, 0, (size_t)h->slots * h->ws_stride * eb);
     cudaMemset(h->status, 0, (size_t)B * sizeof(int32_t));
     cudaMemset(h->stats, 0, (size_t)B * 4 * sizeof(int32_t));
+    cudaMemset(h->as_store, 0, (size_t)B * 16 * sizeof(unsigned long long));
     CU(cudaDeviceSynchronize());
     *out = h;
     return 0;
@@ -348,12 +353,14 @@ int ndp_create(const ndp_config* cfg, ndp_handle** out) {
 int ndp_destroy(ndp_handle* h) {
     if (!h) return 0;
     cudaFree(h->X); cudaFree(h->U); cudaFree(h->yref); cudaFree(h->par); cudaFree(h->ws);
-    cudaFree(h->status); cudaFree(h->stats);
+    cudaFree(h->status); cudaFree(h->stats); cudaFree(h->as_store);
     delete h;
     return 0;
 }
 
 int ndp_set(ndp_handle* h, int field, int stage, const void* dev, int64_t ld, void* stream) {
+    if (h && (field == NDP_FIELD_X || field == NDP_FIELD_U))  // the iterate is being overwritten: drop the active-set guess
+        cudaMemsetAsync(h->as_store, 0, (size_t)h->cfg.batch * 16 * sizeof(unsigned long long), (cudaStream_t)stream);
     return set_get<true>(h, field, stage, const_cast<void*>(dev), ld, stream);
 }
 int ndp_get(ndp_handle* h, int field, int stage, void* dev, int64_t ld, void* stream) {
@@ -367,6 +374,7 @@ int ndp_reset(ndp_handle* h, const void* xr, const void* ur, void* stream) {
     const int N = h->cfg.N, B = h->cfg.batch;
     CU(cudaMemcpyAsync(h->X, xr, (size_t)B * (N + 1) * NX * eb, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     CU(cudaMemcpyAsync(h->U, ur, (size_t)B * N * NU * eb, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    CU(cudaMemsetAsync(h->as_store, 0, (size_t)B * 16 * sizeof(unsigned long long), (cudaStream_t)stream));  // a new iterate: no active-set guess
     return 0;
 }
 

@@ -55,6 +55,7 @@ struct RtiArgs {
     const T* f;
     T* yref_w;
     T* par_w;
+    unsigned long long* as_store;  // [B][4 inputs][4]: active set of the previous solve (lo.w0 lo.w1 hi.w0 hi.w1), or null
     T* ws;            // [slots][ws_stride]
     long long ws_stride;
     int B;
@@ -667,7 +668,8 @@ enum { IPM_LL = 0, IPM_LU, IPM_TL, IPM_TU, IPM_CL, IPM_CU, IPM_ACT };
 // across the call): solves the QP, writes the new iterate, u0, status and statistics of the problem.
 template <typename T, int kN>
 __device__ __noinline__ void constrained_qp(const RtiCfg<T>& c, int lane, unsigned mask, T* sm, T* ws, const T* sTriv, T dx0, T lo, T hi,
-                                            T* gX, T* gU, const T* gY, T* gu0, int32_t* g_status, int32_t* g_stats) {
+                                            T* gX, T* gU, const T* gY, T* gu0, int32_t* g_status, int32_t* g_stats,
+                                            unsigned long long* g_as, bool warm) {
     const int N = (kN > 0) ? kN : c.N;
     const SmemLayout L(N);
     const WsLayout WL(N);
@@ -677,10 +679,13 @@ __device__ __noinline__ void constrained_qp(const RtiCfg<T>& c, int lane, unsign
     const bool isx = lane < 10, isu = (lane >= 10 && lane < 14), isv = (lane >= 3 && lane < 6);
     auto iter_at = [&](int k) -> T { return isx ? sX[k * NX + lane] : (isu ? sU[k * NU + (lane - 10)] : T(0)); };
     auto has_box = [&](int k) -> bool { return (isu && k < N) || (isv && k >= 1 && k < N); };
-    int status = 0, n_fact = 1, n_ipm = 0, n_pol = 0;  // the unconstrained sweep counts as the first factorisation
+    // warm: the previous solve of this problem ended with active bounds; nothing has been computed yet and the
+    // first round linearises and factorises with that active set pinned (if it is still the right one, the
+    // constrained step costs one sweep).  !warm: the unconstrained sweep has run and left the box.
+    int status = 0, n_fact = warm ? 0 : 1, n_ipm = 0, n_pol = 0;
     bool viol = false, bad = false;
     int nact_l = 0;
-        {   // the accepted-sweep ring overwrote the cost records: rebuild them from the stored yref
+        if (!warm) {   // the accepted-sweep ring overwrote the cost records: rebuild them from the stored yref
                         T* sY = sm + L.oY;
             for (int i = lane; i < (N + 1) * SYS; i += GL) {
                 const int k = i >> 4, e = i & 15;
@@ -706,21 +711,33 @@ __device__ __noinline__ void constrained_qp(const RtiCfg<T>& c, int lane, unsign
         ActiveSet<T> as;
         as.lo = lo; as.hi = hi; as.big = c.big;
         bool seed_x = false;
-        for (int k = 0; k < N; k++)
-            if (has_box(k)) {
-                const T v = isu ? gU[k * NU + (lane - 10)] : gX[k * NX + lane];
-                if (isu) {
-                    if (v < lo) as.lo_m.set(k);
-                    else if (v > hi) as.hi_m.set(k);
-                } else {
-                    seed_x |= !(v >= lo && v <= hi);
-                }
+        if (warm) {
+            if (isu) {
+                const unsigned long long* p = g_as + (lane - 10) * 4;
+                as.lo_m.w0 = p[0]; as.lo_m.w1 = p[1]; as.hi_m.w0 = p[2]; as.hi_m.w1 = p[3];
             }
-        seed_x = __any_sync(mask, seed_x);
+        } else {
+            for (int k = 0; k < N; k++)
+                if (has_box(k)) {
+                    const T v = isu ? gU[k * NU + (lane - 10)] : gX[k * NX + lane];
+                    if (isu) {
+                        if (v < lo) as.lo_m.set(k);
+                        else if (v > hi) as.hi_m.set(k);
+                    } else {
+                        seed_x |= !(v >= lo && v <= hi);
+                    }
+                }
+            seed_x = __any_sync(mask, seed_x);
+        }
         __syncwarp(mask);
-        if (!seed_x && c.as_first_max > 0) {
-            for (int round = 0; round < c.as_first_max; round++) {
-                if (!backward_sweep<T, false, 2, true>(c, N, lane, mask, sm, L, ws, WL, sTriv, &as)) break;
+        bool lin_done = !warm;  // [A B b] tiles of this iterate are in the workspace
+        if (!seed_x && (c.as_first_max > 0 || warm)) {
+            for (int round = 0; round < (c.as_first_max > 1 ? c.as_first_max : 1); round++) {
+                bool fact_ok;
+                if (!lin_done) fact_ok = backward_sweep<T, true, 2, true>(c, N, lane, mask, sm, L, ws, WL, sTriv, &as);
+                else fact_ok = backward_sweep<T, false, 2, true>(c, N, lane, mask, sm, L, ws, WL, sTriv, &as);
+                lin_done = true;
+                if (!fact_ok) break;
                 n_fact++;
                 n_pol++;
                 forward_sweep<T, false>(c, N, lane, mask, dx0, sm, L, ws, WL, lo, hi, gX, gU, nullptr, viol, bad, nact_l);
@@ -1009,12 +1026,17 @@ __device__ __noinline__ void constrained_qp(const RtiCfg<T>& c, int lane, unsign
     // ---- write back: full step, overwrite the tentative iterate of the unconstrained sweep ----
     bool bad2 = false;
     nact_l = 0;
+    StageMask fin_lo, fin_hi;  // inputs that end on a bound: the next solve's first guess
+    const T as_eps = (sizeof(T) == 4 ? T(1e-5) : T(1e-11)) * (T(1) + fabs(lo) + fabs(hi));
     if (lane < 14)
         for (int k = 0; k <= N; k++) {
             if (k == N && !isx) break;
             const T v = iter_at(k) + sDz[k * 16 + lane];
             bad2 |= !(fabs(v) <= T(1e30));
             if (has_box(k)) nact_l += (v <= lo) + (v >= hi);
+            // (it + (bound - it) need not round back to the bound exactly: compare with a few ulps of slack)
+            if (isu && v <= lo + as_eps) fin_lo.set(k);
+            else if (isu && v >= hi - as_eps) fin_hi.set(k);
             if (isx) sX[k * NX + lane] = v;
             else sU[k * NU + (lane - 10)] = v;
         }
@@ -1025,6 +1047,11 @@ __device__ __noinline__ void constrained_qp(const RtiCfg<T>& c, int lane, unsign
     for (int i = lane; i < (N + 1) * NX; i += GL) gX[i] = sX[i];
     for (int i = lane; i < N * NU; i += GL) gU[i] = sU[i];
     if (gu0 && lane < NU) gu0[lane] = sU[lane];
+    if (g_as && isu) {
+        const bool keep = (status == 0);
+        unsigned long long* p = g_as + (lane - 10) * 4;
+        p[0] = keep ? fin_lo.w0 : 0ull; p[1] = keep ? fin_lo.w1 : 0ull; p[2] = keep ? fin_hi.w0 : 0ull; p[3] = keep ? fin_hi.w1 : 0ull;
+    }
     if (lane == 0) {
         *g_status = status;
         g_stats[0] = n_fact;
@@ -1120,6 +1147,14 @@ __global__ void __launch_bounds__(RTI_CTA, (sizeof(T) == 4) ? (kLat ? 4 : 8) : 3
             for (int i = lane; i < (N + 1) * 2; i += GL) sY[(i >> 1) * SYS + NYS + (i & 1)] = T(0);
         }
         const T x0v = isx ? a.x0[(size_t)prob * NX + lane] : T(0);
+        // active set the previous solve of this problem ended with (first guess of this one)
+        unsigned long long* g_as = a.as_store ? a.as_store + (size_t)prob * 16 : nullptr;
+        unsigned long long as_any = 0ull;
+        if (g_as && lane >= 10 && lane < 14) {
+            const ulonglong2 m0 = *reinterpret_cast<const ulonglong2*>(g_as + (lane - 10) * 4);
+            const ulonglong2 m1 = *reinterpret_cast<const ulonglong2*>(g_as + (lane - 10) * 4 + 2);
+            as_any = m0.x | m0.y | m1.x | m1.y;
+        }
         cp_async_wait_all();
         __syncwarp(mask);
         if (a.xr != nullptr) {
@@ -1140,19 +1175,22 @@ __global__ void __launch_bounds__(RTI_CTA, (sizeof(T) == 4) ? (kLat ? 4 : 8) : 3
         int status = 0;
 
         // ---- preparation + unconstrained feedback; the step is accepted on the fly ----
-        bool ok = backward_sweep<T, true, 0, false>(c, N, lane, mask, sm, L, ws, WL, sTriv, nullptr);
-        bool viol = false, bad = false;
+        const bool warm = __any_sync(mask, as_any != 0ull);
+        bool ok = true, viol = false, bad = false;
         int nact_l = 0;
-        forward_sweep<T, true>(c, N, lane, mask, dx0, sm, L, ws, WL, lo, hi, gX, gU, a.u0 ? a.u0 + (size_t)prob * NU : nullptr, viol, bad,
-                               nact_l);
-        if (ok && viol) {
+        if (!warm) {
+            ok = backward_sweep<T, true, 0, false>(c, N, lane, mask, sm, L, ws, WL, sTriv, nullptr);
+            forward_sweep<T, true>(c, N, lane, mask, dx0, sm, L, ws, WL, lo, hi, gX, gU, a.u0 ? a.u0 + (size_t)prob * NU : nullptr, viol, bad,
+                                   nact_l);
+        }
+        if (warm || (ok && viol)) {
             // Called through an opaque function pointer: ptxas then allocates the nominal path against the plain ABI
             // instead of against this callee's register use (measured: 77.2 us vs 81-84 us per launch at B = 4096
             // with a direct call, and the nominal path no longer moves when the constrained path changes).
             auto fn = &constrained_qp<T, kN>;
             asm volatile("" : "+l"(fn));
             fn(c, lane, mask, sm, ws, sTriv, dx0, lo, hi, gX, gU, (a.xr != nullptr ? a.yref_w : a.yref) + (size_t)prob * (N + 1) * NYS,
-               a.u0 ? a.u0 + (size_t)prob * NU : nullptr, a.status + prob, a.stats + (size_t)prob * 4);
+               a.u0 ? a.u0 + (size_t)prob * NU : nullptr, a.status + prob, a.stats + (size_t)prob * 4, g_as, warm);
         } else {
             // the forward sweep already stored the new iterate and u0
             if (!ok) status = 4;

@@ -240,3 +240,48 @@ def test_fused_update_equals_set_reference_plus_solve(built_lib):
     u3 = e2.update(x0, xr, ur, None)  # f = NULL -> zero forces
     e1.set_reference(xr, ur, None)
     assert torch.equal(e1.solve(x0), u3)
+
+
+@pytest.mark.parametrize("prec", ["f32", "f64"])
+def test_warm_active_set_closed_loop(built_lib, c_oracle, prec):
+    """Saturating closed loop (tightened input bounds, moving x0): a solve that ends with active bounds leaves them
+    as the first guess of the next solve (active_set_warm).  Every step must still be the oracle's QP solution, the
+    cold route (active_set_warm=0) must agree, and the warm route must need fewer Riccati sweeps."""
+    B, steps = 128, 6
+    kw = dict(u_min=[-1.5, -1.5, -1.5, 0.0], u_max=[1.5, 1.5, 1.5, 15.0])
+    w = wl.independent_problems(B, seed=61, scale=5.0)
+    rng = np.random.default_rng(8)
+    x0_seq = [w["x0"] + 0.03 * s * rng.normal(size=w["x0"].shape) for s in range(steps)]
+    ew, ec = _engine(B, prec, np_=4, active_set_warm=1, **kw), _engine(B, prec, np_=4, active_set_warm=0, **kw)
+    dt, dev = ew.dtype, ew.device
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=dt, device=dev)
+    xr, ur = t(w["xr"]), t(w["ur"])
+    X, U = w["xr"].copy(), w["ur"].copy()
+    cfg = make_cfg(**kw)
+    sweeps = {"warm": [], "cold": []}
+    for e in (ew, ec):
+        e.reset(xr, ur)
+        e.set_reference(xr, ur, None)
+    tol = TOL[prec] if prec == "f32" else 1e-7  # fp64: five warm-started steps on top of the single-step 1e-8
+    for s in range(steps):
+        r = c_oracle.rti_batch(cfg, x0_seq[s], w["xr"], w["ur"], None, X, U)
+        ok = r["status"] == 0
+        for name, e in (("warm", ew), ("cold", ec)):
+            u0 = e.solve(t(x0_seq[s]))
+            torch.cuda.synchronize()
+            st, stats = e.status().cpu().numpy(), e.stats().cpu().numpy()
+            assert np.all(st[ok] == 0), (name, s, np.bincount(st[ok]))
+            assert rel_err(u0.cpu().numpy().astype(np.float64)[ok], r["u0"][ok]) < tol, (name, s)
+            assert rel_err(e.get_all("u").cpu().numpy().astype(np.float64)[ok], U[ok]) < tol, (name, s)
+            assert rel_err(e.get_all("x").cpu().numpy().astype(np.float64)[ok], X[ok]) < tol, (name, s)
+            sweeps[name].append(float(stats[:, 0].mean()))
+        assert (r["n_active"] > 0).mean() > 0.3
+    print(f"warm active set {prec}: Riccati sweeps per solve warm {np.round(sweeps['warm'], 2)} cold {np.round(sweeps['cold'], 2)}")
+    assert np.mean(sweeps["warm"][1:]) < np.mean(sweeps["cold"][1:])
+    # reset drops the guess: the first solve after it takes the cold route again
+    ew.reset(xr, ur)
+    ew.solve(t(x0_seq[0]))
+    ec.reset(xr, ur)
+    ec.solve(t(x0_seq[0]))
+    torch.cuda.synchronize()
+    assert np.array_equal(ew.stats().cpu().numpy(), ec.stats().cpu().numpy())
