@@ -216,6 +216,7 @@ class BatchedOcpSolver:
         self._do_X, self._do_U, self._do_u0 = regions(self._d_out, (self._sz_X, self._sz_U, self._sz_u0), out_shapes)
         self._dirty_ref = True
         self._dirty_it = False
+        self._it_stale = False  # the device iterate is newer than the host mirror (fetched on demand by get / set)
         self._status = np.zeros(B, np.int32)
         self.stream = torch.cuda.Stream(device=self.device)
 
@@ -228,10 +229,28 @@ class BatchedOcpSolver:
     def N(self) -> int:
         return self._N
 
+    def _sync_iterate(self) -> None:
+        """Bring the host mirror of (X, U) up to date with the device iterate.  The per-step path only reads u0 and
+        the status back; the predicted trajectory crosses PCIe when somebody asks for it (the node's viz timer,
+        nmpc_node.py:233-237, or a per-stage set of x / u)."""
+        if not self._it_stale:
+            return
+        e = self.engine
+        with torch.cuda.stream(self.stream):
+            _lib.check(e.lib.ndp_get(e._h, _lib.FIELD_X, -1, _ptr(self._do_X), 0, _stream_ptr(self.stream)), "ndp_get")
+            _lib.check(e.lib.ndp_get(e._h, _lib.FIELD_U, -1, _ptr(self._do_U), 0, _stream_ptr(self.stream)), "ndp_get")
+            self._pin_out[:self._sz_X + self._sz_U].copy_(self._d_out[:self._sz_X + self._sz_U], non_blocking=True)
+        self.stream.synchronize()
+        self._h_X[...] = self._ho_X
+        self._h_U[...] = self._ho_U
+        self._it_stale = False
+
     def set(self, stage: int, field: str, value) -> None:
         """solver.set(stage, field, value) -- nmpc_body_rate_ctl.py:89-91,97-104."""
         v = np.asarray(value)
         with self._lock:
+            if field in ("x", "u"):
+                self._sync_iterate()
             if field == "x":
                 self._h_X[:, stage, :] = v.reshape(-1, NX)
                 self._dirty_it = True
@@ -251,6 +270,8 @@ class BatchedOcpSolver:
     def get(self, stage: int, field: str) -> np.ndarray:
         """solver.get(stage, field): a fresh float64 copy (the node mutates it, nmpc_node.py:237-238)."""
         with self._lock:
+            if field in ("x", "u"):
+                self._sync_iterate()
             if field == "x":
                 out = self._h_X[:, stage, :]
             elif field == "u":
@@ -283,14 +304,12 @@ class BatchedOcpSolver:
                 else:
                     self._d_in[:self._sz_x0].copy_(self._pin_in[:self._sz_x0], non_blocking=True)
                 e.solve(self._dv_x0, self._do_u0, stream=self.stream)
-                _lib.check(e.lib.ndp_get(e._h, _lib.FIELD_X, -1, _ptr(self._do_X), 0, _stream_ptr(self.stream)), "ndp_get")
-                _lib.check(e.lib.ndp_get(e._h, _lib.FIELD_U, -1, _ptr(self._do_U), 0, _stream_ptr(self.stream)), "ndp_get")
                 e.status(self._d_status, stream=self.stream)
-                self._pin_out.copy_(self._d_out, non_blocking=True)
+                o = self._sz_X + self._sz_U
+                self._pin_out[o:].copy_(self._d_out[o:], non_blocking=True)   # u0 only; (X, U) on demand (_sync_iterate)
                 self._pin_status.copy_(self._d_status, non_blocking=True)
             self.stream.synchronize()
-            self._h_X[...] = self._ho_X
-            self._h_U[...] = self._ho_U
+            self._it_stale = True
             self._status = self._pin_status.numpy().copy()
             u0 = np.array(self._ho_u0, dtype=np.float64)
         return u0[0] if self.batch == 1 else u0
@@ -307,6 +326,7 @@ class BatchedOcpSolver:
     def set_all(self, field: str, value) -> None:
         v = np.asarray(value)
         with self._lock:
+            self._sync_iterate()
             if field == "x":
                 self._h_X[...] = v.reshape(self.batch, self._N + 1, NX)
                 self._dirty_it = True
@@ -318,6 +338,7 @@ class BatchedOcpSolver:
 
     def get_all(self, field: str) -> np.ndarray:
         with self._lock:
+            self._sync_iterate()
             src = {"x": self._h_X, "u": self._h_U}[field]
             return np.array(src, dtype=np.float64)
 
