@@ -68,7 +68,8 @@ struct SmemLayout {
     int oX, oU, oPar, oY, oDz, oP, op, oT0, oT1, oHux, total;  // oY and oDz are adjacent: see forward_sweep
     __host__ __device__ constexpr explicit SmemLayout(int N)
         : oX(0), oU(al4((N + 1) * NX)), oPar(oU + N * NU), oY(oPar + (N + 1) * NPS), oDz(oY + (N + 1) * SYS),
-          // QP step [k][lane]; sY | sDz also hosts the 4 x (14 x TLD) ring of the accepted forward sweep
+          // QP step [k][lane]; the FW_RING x (14 x TLD) ring of the accepted forward sweep runs from oY over sDz, P+,
+          // p+ and the tiles: oY .. oHux must span at least FW_RING * 14 * TLD elements (static_assert below)
           oP(oY + (((N + 1) * (SYS + 16) > 4 * 14 * TLD) ? (N + 1) * (SYS + 16) : 4 * 14 * TLD)),
           op(oP + 10 * 12),        // P+ rows, stride 12; then p+
           oT0(op + 12),            // tile of stage k:   rows r = 0..9 of [A B](:,6..13) | b | pad3, stride TLD
@@ -532,13 +533,15 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int kPending>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory"); }
 
-constexpr int FW_RING = 4;            // stages of forward-sweep records in flight
+constexpr int FW_RING = 6;            // stages of forward-sweep records in flight (L2 latency / stage time ~ 4-5)
 constexpr int FW_REC = 14 * TLD;      // one stage: 14 lanes x TLD
+static_assert(SmemLayout(1).oHux - SmemLayout(1).oY >= FW_RING * FW_REC, "forward-sweep ring does not fit the dead shared-memory regions");
 
 // Forward substitution: lane i < 10 carries dx_k[i], lanes 10..13 compute du_k[m].
 // kFinal (the accepted sweep of the nominal path): the stage records stream from the L2-resident
 // workspace through a FW_RING-deep shared-memory ring (cp.async groups; each lane copies and reads only
-// its own record, so no barrier is needed) laid over the cost records + sDz, which are dead by then; the
+// its own record, so no barrier is needed) laid over the cost records, sDz, P+, p+ and the two stage tiles,
+// which are all dead by then (the tiles' zero pad columns are restored afterwards); the
 // new iterate (X + dx, U + du) is written to global memory as it is produced and the box test / NaN
 // test / active count are fused in (returned through viol / bad / nact).
 // !kFinal (IPM sweeps): records are register-prefetched and the step goes to sDz[k][lane].
@@ -624,6 +627,9 @@ __device__ __forceinline__ void forward_sweep(const RtiCfg<T>& c, int N, int lan
             gp[N * its] = v;
             b_l |= !(fabs(v) <= T(1e30));
         }
+        __syncwarp(mask);
+        // the ring ran over the stage tiles: restore their zero pad columns (9..11) for the next problem
+        for (int i = lane; i < 20 * 3; i += GL) sm[L.oT0 + (i / 3) * TLD + 9 + (i % 3)] = T(0);
         viol = __any_sync(mask, v_l);
         bad = __any_sync(mask, b_l);
         nact = n_l;
