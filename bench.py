@@ -375,12 +375,39 @@ def batch1_latency(dev):
         t0 = time.perf_counter()
         f = nn.update(other, xr[0])
         t1 = time.perf_counter()
-        ctl.update(xr[0, 0], xr[0], ur[0], f)
+        u_last = ctl.update(xr[0, 0], xr[0], ur[0], f)
         t2 = time.perf_counter()
         if i >= 20:
             lat_n.append(t1 - t0); lat_u.append(t2 - t1)
+    # the leader's whole tick (DownwashNN.update + controller.update) as ONE call through the C ABI:
+    # ndp_pipeline_submit/wait at batch 1 (pinned host record -> H2D -> MLP + RTI kernels -> D2H)
+    from ndp_nmpc_qd_b200.pipeline import HostStepPipeline
+    from ndp_nmpc_qd_b200.solver import Engine
+    import torch
+
+    eng = Engine(batch=1, N=N_HORIZON, np_=7, precision="f32", device=dev)
+    pipe = HostStepPipeline(eng, nn, depth=1)
+    xr, ur = wl.reference_horizon([1.0])
+    t32 = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float32, device=dev)
+    eng.reset(t32(xr), t32(ur))
+    torch.cuda.synchronize()
+    sl, lat_f, u_f = pipe.slots[0], [], None
+    for i in range(220):
+        xr, ur = wl.reference_horizon([1.0 + 0.02 * i])
+        other = xr[0].copy(); other[:, 2] += 0.8
+        t0 = time.perf_counter()
+        sl.x0[...] = xr[:, 0]; sl.xr[...] = xr; sl.ur[...] = ur
+        sl.other[...] = other[None, :, 0:6]; sl.gate_xy[...] = xr[:, 0, 0:2]
+        u_f = pipe.step(0).u0[0].copy()
+        t1 = time.perf_counter()
+        if i >= 20:
+            lat_f.append(t1 - t0)
     return dict(update_p50_us=float(np.median(lat_u) * 1e6), update_p99_us=float(np.quantile(lat_u, 0.99) * 1e6),
-                downwash_update_p50_us=float(np.median(lat_n) * 1e6), note="NDPNMPCBodyRateController.update / DownwashNN.update, host numpy in -> out")
+                downwash_update_p50_us=float(np.median(lat_n) * 1e6),
+                fused_tick_p50_us=float(np.median(lat_f) * 1e6), fused_tick_p99_us=float(np.quantile(lat_f, 0.99) * 1e6),
+                fused_tick_u0_vs_dropin=float(np.abs(u_f - u_last).max()),
+                note="NDPNMPCBodyRateController.update / DownwashNN.update, host numpy in -> out; fused_tick = both in one "
+                     "ndp_pipeline_submit/wait call at batch 1 (same inputs, same closed sequence)")
 
 
 def main():

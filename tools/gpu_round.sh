@@ -13,3 +13,6 @@ timeout 400 ncu --set full --clock-control none --import-source on -k regex:rti_
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:mlp_tc_kernel -s 4 -c 2 -o gpurun_out/prof_mlp -f \
   python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-latency > gpurun_out/prof_mlp.log 2>&1
 tail -3 gpurun_out/pytest_gpu.log; cat gpurun_out/smoke.log | tail -2; cat gpurun_out/bench.json
+timeout 900 python tools/closed_loop_sweep.py > gpurun_out/closed_loop_sweep.jsonl 2> gpurun_out/closed_loop_sweep.err
+timeout 300 python tools/gpu_stress_sweep.py 0 6 10 16 > gpurun_out/stress_sweep.jsonl 2>&1
+tail -2 gpurun_out/closed_loop_sweep.err; wc -l gpurun_out/closed_loop_sweep.jsonl
