@@ -151,7 +151,8 @@ int ndp_mlp_destroy(ndp_mlp* m);
  * odometry x,y -- the force is zeroed when the neighbour's node-0 horizontal distance to it is
  * >= r_horiz (ndp_nmpc_leader_node.py:65-76, params/downwash_params.py:10).
  * out: [P][n_nodes][3] in `precision`.  accumulate != 0 adds into out (sum over neighbours).
- * path: 0 = auto, 1 = CUDA-core fp32 kernel, 2 = tcgen05 tensor-core kernel. */
+ * path: 0 = auto (<= 512 rows: 3, >= 2048 rows: 2, else 1), 1 = CUDA-core fp32 tile kernel, 2 = tcgen05 tensor-core
+ * kernel, 3 = latency kernel, one CTA per row (the reference's own 21-row call). */
 int ndp_mlp_forward_pairs(ndp_mlp* m, int precision, int64_t P, int32_t n_nodes, const void* ego_dev,
                           const void* other_dev, const void* gate_xy_dev, double r_horiz, void* out_dev,
                           int accumulate, int path, void* stream);

@@ -249,6 +249,74 @@ __global__ void __launch_bounds__(MLPF_THREADS, 1) mlp_fp32_kernel(const float* 
     }
 }
 
+// Latency kernel for a handful of rows (the reference's own call: 21 rows per DownwashNN.update): one CTA per row,
+// 256 threads split every layer's dot products (partial sums combined with shuffles); the weights are read straight
+// from L2 (71 KB per row) instead of being staged per CTA, so 21 rows take 21 SMs for a few microseconds instead of
+// one SM for ~50.  fp32 FMA arithmetic like mlp_fp32_kernel (summation order differs: ~1e-7 relative).
+constexpr int MLPR_THREADS = 256;
+constexpr long long MLPR_MAX_ROWS = 512;
+__global__ void __launch_bounds__(MLPR_THREADS) mlp_row_kernel(const float* __restrict__ params, const MlpIo io) {
+    __shared__ __align__(16) float sx[8], h1[MLP_H1], h2[MLP_H2], h3[MLP_H3], so[4];
+    const long long row = blockIdx.x;
+    const int t = threadIdx.x;
+    if (t == 0) {
+        float x[6];
+        const bool on = mlp_fetch_row(io, row, x);
+#pragma unroll
+        for (int i = 0; i < 6; i++) sx[i] = x[i];
+        sx[6] = on ? 1.f : 0.f;
+    }
+    __syncthreads();
+    if (t < MLP_H1) {   // layer 1: 128 outputs, K = 6
+        const float* w = params + MLP_OW1 + t * MLP_IN;
+        float acc = params[MLP_OB1 + t];
+#pragma unroll
+        for (int q = 0; q < MLP_IN; q++) acc = fmaf(w[q], sx[q], acc);
+        h1[t] = fmaxf(acc, 0.f);
+    }
+    __syncthreads();
+    {   // layer 2: 64 outputs x K = 128, four threads per output (32 inputs each)
+        const int o = t >> 2, part = t & 3;
+        const float4* w = reinterpret_cast<const float4*>(params + MLP_OW2 + o * MLP_H1 + part * 32);
+        const float4* a = reinterpret_cast<const float4*>(h1 + part * 32);
+        float acc = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const float4 wv = w[i], av = a[i];
+            acc = fmaf(wv.x, av.x, acc); acc = fmaf(wv.y, av.y, acc); acc = fmaf(wv.z, av.z, acc); acc = fmaf(wv.w, av.w, acc);
+        }
+        acc += __shfl_xor_sync(0xFFFFFFFFu, acc, 1);
+        acc += __shfl_xor_sync(0xFFFFFFFFu, acc, 2);
+        if (part == 0) h2[o] = fmaxf(acc + params[MLP_OB2 + o], 0.f);
+    }
+    __syncthreads();
+    {   // layer 3: 128 outputs x K = 64, two threads per output
+        const int o = t >> 1, part = t & 1;
+        const float4* w = reinterpret_cast<const float4*>(params + MLP_OW3 + o * MLP_H2 + part * 32);
+        const float4* a = reinterpret_cast<const float4*>(h2 + part * 32);
+        float acc = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const float4 wv = w[i], av = a[i];
+            acc = fmaf(wv.x, av.x, acc); acc = fmaf(wv.y, av.y, acc); acc = fmaf(wv.z, av.z, acc); acc = fmaf(wv.w, av.w, acc);
+        }
+        acc += __shfl_xor_sync(0xFFFFFFFFu, acc, 1);
+        if (part == 0) h3[o] = fmaxf(acc + params[MLP_OB3 + o], 0.f);
+    }
+    __syncthreads();
+    if (t < 32 * MLP_OUT) {   // layer 4: 3 outputs x K = 128, one warp per output
+        const int o = t >> 5, lane = t & 31;
+        const float4 wv = *reinterpret_cast<const float4*>(params + MLP_OW4 + o * MLP_H3 + lane * 4);
+        const float4 av = *reinterpret_cast<const float4*>(h3 + lane * 4);
+        float acc = fmaf(wv.x, av.x, fmaf(wv.y, av.y, fmaf(wv.z, av.z, wv.w * av.w)));
+#pragma unroll
+        for (int s = 16; s >= 1; s >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, s);
+        if (lane == 0) so[o] = acc + params[MLP_OB4 + o];
+    }
+    __syncthreads();
+    if (t == 0) mlp_store_row(io, row, sx[6] != 0.f, so[0], so[1], so[2]);
+}
+
 // ---- swarm support: neighbour lists and ordered reduction ----
 // One warp per ego builds its gated neighbour list in ascending j (deterministic order inside the ego's
 // segment): ballot-compacted count pass, one atomicAdd on *total for the segment offset, fill pass.  The

@@ -461,8 +461,11 @@ namespace ndp {
 
 static int mlp_run(ndp_mlp* m, MlpIo io, int path, cudaStream_t st) {
     if (io.M <= 0) return 0;
-    if (path == 0) path = (io.M >= MLPT_MIN_ROWS) ? 2 : 1;
-    if (path == 2) {
+    if (path == 0) path = (io.M >= MLPT_MIN_ROWS) ? 2 : ((io.M <= MLPR_MAX_ROWS && !io.m_dev) ? 3 : 1);
+    if (path == 3) {   // latency path: one CTA per row
+        mlp_row_kernel<<<(int)io.M, MLPR_THREADS, 0, st>>>(m->params, io);
+        CU(cudaGetLastError());
+    } else if (path == 2) {
         int rc = mlp_tc_launch(m->small, m->tc_weights, io, m->n_sm, st);
         if (rc) return cuda_fail((cudaError_t)rc, "mlp_tc_kernel launch");
     } else if (path == 1) {
@@ -661,6 +664,8 @@ struct ndp_pipeline {
     size_t f_bytes;
     cudaStream_t s_in, s_cmp, s_out;
     cudaEvent_t *e_in, *e_cmp, *e_out;
+    cudaGraphExec_t gexec;  // depth 1 (latency path): the whole step as one graph launch on s_cmp
+    bool graph_tried;
 };
 
 extern "C" {
@@ -705,6 +710,7 @@ int ndp_pipeline_create(ndp_handle* h, ndp_mlp* mlp, double r_horiz, int depth, 
 int ndp_pipeline_destroy(ndp_pipeline* p) {
     if (!p) return 0;
     if (p->s_cmp) cudaStreamSynchronize(p->s_cmp);
+    if (p->gexec) cudaGraphExecDestroy(p->gexec);
     if (p->s_out) cudaStreamSynchronize(p->s_out);
     if (p->s_in) cudaStreamSynchronize(p->s_in);
     for (int s = 0; s < p->depth; s++) {
@@ -736,9 +742,61 @@ int ndp_pipeline_buffers(ndp_pipeline* p, int slot, void** x0, void** xr, void**
     return 0;
 }
 
+// depth 1: copy-in, kernels, copy-out of the only slot on one stream (what the graph of the latency path holds)
+static int pipeline_enqueue_serial(ndp_pipeline* p, cudaStream_t st) {
+    ndp_handle* h = p->h;
+    const size_t in_used = p->o_gate + (p->mlp ? (size_t)h->cfg.batch * 2 * h->elt : 0);
+    const size_t out_used = p->o_status + (size_t)h->cfg.batch * sizeof(int32_t);
+    // small records (the one-problem tick is 1.7 KB in, 20 B out): the kernels read the pinned host record and write u0
+    // straight over PCIe (unified addressing: cudaHostAlloc memory is device-accessible at the same address), which
+    // saves the two copy operations and their scheduling gaps; large records keep the staged copies
+    const bool zero_copy = in_used <= (64u << 10);
+    unsigned char* in = zero_copy ? p->h_in : p->d_in;
+    unsigned char* out = zero_copy ? p->h_out : p->d_out;
+    if (!zero_copy) CU(cudaMemcpyAsync(p->d_in, p->h_in, in_used, cudaMemcpyHostToDevice, st));
+    if (p->mlp) {
+        int rc = ndp_mlp_forward_pairs_ex(p->mlp, h->cfg.precision, h->cfg.batch, h->cfg.N + 1, in + p->o_xr, in + p->o_other, 6,
+                                          in + p->o_gate, p->r_horiz, p->d_f, 0, 0, st);
+        if (rc) return rc;
+    }
+    int rc = ndp_update(h, in + p->o_x0, in + p->o_xr, in + p->o_ur, p->mlp ? p->d_f : nullptr, out, st);
+    if (rc) return rc;
+    if (zero_copy) {
+        CU(cudaMemcpyAsync(p->h_out + p->o_status, h->status, (size_t)h->cfg.batch * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    } else {
+        CU(cudaMemcpyAsync(p->d_out + p->o_status, h->status, (size_t)h->cfg.batch * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+        CU(cudaMemcpyAsync(p->h_out, p->d_out, out_used, cudaMemcpyDeviceToHost, st));
+    }
+    return 0;
+}
+
 int ndp_pipeline_submit(ndp_pipeline* p, int slot) {
     if (!p || slot < 0 || slot >= p->depth) return fail(NDP_E_ARG, "ndp_pipeline_submit: bad slot");
     ndp_handle* h = p->h;
+    if (p->depth == 1) {
+        // latency path (the reference's one-problem tick): nothing to overlap, so the step is captured once into a
+        // CUDA graph and replayed with a single launch; falls back to plain stream order if capture is refused
+        if (!p->gexec && !p->graph_tried) {
+            p->graph_tried = true;
+            cudaGraph_t g = nullptr;
+            if (cudaStreamBeginCapture(p->s_cmp, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+                const int rc = pipeline_enqueue_serial(p, p->s_cmp);
+                const cudaError_t e = cudaStreamEndCapture(p->s_cmp, &g);
+                if (rc != 0 || e != cudaSuccess || !g || cudaGraphInstantiate(&p->gexec, g, 0) != cudaSuccess) p->gexec = nullptr;
+                if (g) cudaGraphDestroy(g);
+                cudaGetLastError();
+            }
+        }
+        if (p->gexec) {
+            CU(cudaGraphLaunch(p->gexec, p->s_cmp));
+            h->launches++;
+        } else {
+            int rc = pipeline_enqueue_serial(p, p->s_cmp);
+            if (rc) return rc;
+        }
+        CU(cudaEventRecord(p->e_out[0], p->s_cmp));
+        return 0;
+    }
     unsigned char* din = p->d_in + (size_t)slot * p->in_bytes;
     unsigned char* dout = p->d_out + (size_t)slot * p->out_bytes;
     unsigned char* df = p->d_f + (size_t)slot * p->f_bytes;

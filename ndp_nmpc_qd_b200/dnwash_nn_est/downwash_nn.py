@@ -51,7 +51,7 @@ def _sp(stream=None):
 
 
 class DownwashNN:
-    PATH_AUTO, PATH_FP32, PATH_TENSOR = 0, 1, 2
+    PATH_AUTO, PATH_FP32, PATH_TENSOR, PATH_ROWS = 0, 1, 2, 3
 
     def __init__(self, weights: Optional[str] = None, device: str | torch.device = "cuda:0"):
         self.lib = _lib.load()

@@ -26,6 +26,23 @@ def test_rows_vs_reference_module(nn):
     assert np.abs(y - g["y64"]).max() < 2e-5
 
 
+def test_latency_row_kernel(nn, mlp_weights):
+    """One CTA per row (path 3, what `auto` picks up to 512 rows, i.e. for the reference's own 21-row call): against
+    the reference module's golden outputs, the numpy oracle and the fp32 tile kernel."""
+    g = golden("mlp_golden.npz")
+    x = torch.as_tensor(g["x"][:512], device="cuda").contiguous()
+    y = nn.forward_rows(x, path=nn.PATH_ROWS).cpu().numpy()
+    assert np.abs(y - g["y32"][:512]).max() < 1e-5
+    rng = np.random.default_rng(2)
+    for M in (1, 21, 100, 512):
+        xs = (rng.normal(size=(M, 6)) * 1.5).astype(np.float32)
+        xt = torch.as_tensor(xs, device="cuda")
+        y3, y1, ya = (nn.forward_rows(xt, path=p).cpu().numpy() for p in (nn.PATH_ROWS, nn.PATH_FP32, nn.PATH_AUTO))
+        assert np.abs(y3 - mlp_numpy.mlp_forward(mlp_weights, xs, np.float64)).max() < 2e-5, M
+        assert np.abs(y3 - y1).max() < 1e-5, M
+        assert np.array_equal(ya, y3), M   # auto == the row kernel at these sizes
+
+
 def test_rows_ragged_sizes(nn, mlp_weights):
     rng = np.random.default_rng(0)
     for M in (1, 21, 63, 64, 65, 1000, 20000):

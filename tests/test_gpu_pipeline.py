@@ -88,6 +88,17 @@ def test_pipelined_steps_equal_sequential_device_path(built_lib):
         got[s] = pipe.wait(s % depth).u0.copy()
     for s in range(steps):
         assert np.array_equal(got[s], ref[s]), s
+    # depth 1 = the latency path: the step is captured once into a CUDA graph and replayed (same kernels, same order)
+    eng3 = Engine(batch=B, np_=7)
+    eng3.reset(xr, ur)
+    torch.cuda.synchronize()
+    pipe1 = HostStepPipeline(eng3, nn, depth=1)
+    for s in range(steps):
+        sl = pipe1.slots[0]
+        _fill(sl, base)
+        sl.x0[...] = x0s[s]
+        assert np.array_equal(pipe1.step(0).u0, ref[s]), s
+        assert np.all(sl.status == 0)
 
 
 def test_pipeline_without_downwash(built_lib, c_oracle):
