@@ -108,6 +108,14 @@ int ndp_reset(ndp_handle* h, const void* xr_dev, const void* ur_dev, void* strea
  * yref_k = [xr_k; ur_k], p_k = [xr_k[6:10]; f_k].  f_dev may be NULL (zeros / np == 4). */
 int ndp_set_reference(ndp_handle* h, const void* xr_dev, const void* ur_dev, const void* f_dev, void* stream);
 
+/* The acados-style mirror's whole solve_for_x0 from PINNED HOST buffers in engine precision (latency path of the
+ * one-problem controller, nmpc_body_rate_ctl.py:95-107): x0 [B][10], yref [B][N+1][14] (stage rows [xr; ur], terminal
+ * row: first 10), p [B][N+1][8] (q_r(4) f(3) pad) -> [upload of yref / p when upload_ref != 0,] one SQP_RTI step,
+ * u0 [B][4] and status [B] back in host memory.  Synchronous.  The sequence is captured once per set of buffers into a
+ * CUDA graph and replayed; small batches read x0 / write u0 over PCIe from the kernel itself. */
+int ndp_solve_host(ndp_handle* h, const void* x0_host, const void* yref_host, const void* p_host, int upload_ref,
+                   void* u0_host, int32_t* status_host);
+
 /* u0 = solver.solve_for_x0(x0) -- nmpc_body_rate_ctl.py:107: one SQP_RTI step for every problem
  * (x0 constraint, linearise, QP, full step).  x0_dev [B][10], u0_dev [B][4] (may be NULL). */
 int ndp_solve(ndp_handle* h, const void* x0_dev, void* u0_dev, void* stream);

@@ -43,6 +43,12 @@ struct ndp_handle {
     long long ws_stride;
     int slots, grid, ppc, lat;
     size_t smem;
+    // ndp_solve_host: private stream, the two captured step graphs (with / without reference upload) and the
+    // host pointers they were captured for
+    cudaStream_t hs;
+    cudaGraphExec_t hgraph[2];
+    const void* hptr[5];
+    void* d_hx0; void* d_hu0;  // staging for batches too large for zero-copy
     std::atomic<long long> launches;
     std::mutex mu;
 };
@@ -328,6 +334,8 @@ int ndp_create(const ndp_config* cfg, ndp_handle** out) {
     h->X = h->U = h->yref = h->par = h->ws = nullptr;
     h->status = h->stats = nullptr;
     h->as_store = nullptr;
+    h->hs = nullptr; h->hgraph[0] = h->hgraph[1] = nullptr; h->d_hx0 = h->d_hu0 = nullptr;
+    for (auto& q : h->hptr) q = nullptr;
     bool ok = cudaMalloc(&h->X, (size_t)B * (N + 1) * NX * eb) == cudaSuccess && cudaMalloc(&h->U, (size_t)B * N * NU * eb) == cudaSuccess &&
               cudaMalloc(&h->yref, (size_t)B * (N + 1) * NYS * eb) == cudaSuccess &&
               cudaMalloc(&h->par, (size_t)B * (N + 1) * NPS * eb) == cudaSuccess &&
@@ -354,6 +362,9 @@ int ndp_destroy(ndp_handle* h) {
     if (!h) return 0;
     cudaFree(h->X); cudaFree(h->U); cudaFree(h->yref); cudaFree(h->par); cudaFree(h->ws);
     cudaFree(h->status); cudaFree(h->stats); cudaFree(h->as_store);
+    for (auto& g : h->hgraph) if (g) cudaGraphExecDestroy(g);
+    if (h->hs) cudaStreamDestroy(h->hs);
+    cudaFree(h->d_hx0); cudaFree(h->d_hu0);
     delete h;
     return 0;
 }
@@ -405,6 +416,66 @@ int ndp_update(ndp_handle* h, const void* x0, const void* xr, const void* ur, co
     std::lock_guard<std::mutex> lk(h->mu);
     return h->elt == 4 ? launch_solve<float>(h, x0, u0, (cudaStream_t)stream, xr, ur, f)
                        : launch_solve<double>(h, x0, u0, (cudaStream_t)stream, xr, ur, f);
+}
+
+// one host-buffer step on stream st: [reference upload,] solve, results back (what ndp_solve_host captures)
+static int solve_host_enqueue(ndp_handle* h, const void* x0, const void* yref, const void* p, bool upload, void* u0, int32_t* status,
+                              cudaStream_t st) {
+    const size_t eb = (size_t)h->elt, B = (size_t)h->cfg.batch, N = (size_t)h->cfg.N;
+    if (upload) {
+        CU(cudaMemcpyAsync(h->yref, yref, B * (N + 1) * NYS * eb, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(h->par, p, B * (N + 1) * NPS * eb, cudaMemcpyHostToDevice, st));
+    }
+    // small batches: the kernel reads x0 from / writes u0 to the pinned host buffers itself (unified addressing)
+    const bool zero_copy = B * NX * eb <= (16u << 10);
+    const void* x0_k = x0;
+    void* u0_k = u0;
+    if (!zero_copy) {
+        CU(cudaMemcpyAsync(h->d_hx0, x0, B * NX * eb, cudaMemcpyHostToDevice, st));
+        x0_k = h->d_hx0; u0_k = h->d_hu0;
+    }
+    int rc = h->elt == 4 ? launch_solve<float>(h, x0_k, u0_k, st) : launch_solve<double>(h, x0_k, u0_k, st);
+    if (rc) return rc;
+    if (!zero_copy) CU(cudaMemcpyAsync(u0, h->d_hu0, B * NU * eb, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(status, h->status, B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    return 0;
+}
+
+int ndp_solve_host(ndp_handle* h, const void* x0_host, const void* yref_host, const void* p_host, int upload_ref, void* u0_host,
+                   int32_t* status_host) {
+    if (!h || !x0_host || !u0_host || !status_host || (upload_ref && (!yref_host || !p_host)))
+        return fail(NDP_E_ARG, "ndp_solve_host: null argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (!h->hs) CU(cudaStreamCreateWithFlags(&h->hs, cudaStreamNonBlocking));
+    if (!h->d_hx0) {   // staging for batches above the zero-copy size (allocated outside any capture)
+        CU(cudaMalloc(&h->d_hx0, (size_t)h->cfg.batch * NX * h->elt));
+        CU(cudaMalloc(&h->d_hu0, (size_t)h->cfg.batch * NU * h->elt));
+    }
+    const void* key[5] = {x0_host, yref_host, p_host, u0_host, status_host};
+    if (std::memcmp(key, h->hptr, sizeof(key)) != 0) {   // new buffers: drop the graphs captured for the old ones
+        for (auto& g : h->hgraph) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
+        std::memcpy(h->hptr, key, sizeof(key));
+    }
+    const int v = upload_ref ? 1 : 0;
+    if (!h->hgraph[v] && (!upload_ref || (yref_host && p_host))) {
+        cudaGraph_t g = nullptr;
+        if (cudaStreamBeginCapture(h->hs, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+            const int rc = solve_host_enqueue(h, x0_host, yref_host, p_host, upload_ref != 0, u0_host, status_host, h->hs);
+            const cudaError_t e = cudaStreamEndCapture(h->hs, &g);
+            if (rc != 0 || e != cudaSuccess || !g || cudaGraphInstantiate(&h->hgraph[v], g, 0) != cudaSuccess) h->hgraph[v] = nullptr;
+            if (g) cudaGraphDestroy(g);
+            cudaGetLastError();
+        }
+    }
+    if (h->hgraph[v]) {
+        CU(cudaGraphLaunch(h->hgraph[v], h->hs));
+        h->launches++;
+    } else {
+        int rc = solve_host_enqueue(h, x0_host, yref_host, p_host, upload_ref != 0, u0_host, status_host, h->hs);
+        if (rc) return rc;
+    }
+    CU(cudaStreamSynchronize(h->hs));
+    return 0;
 }
 
 int ndp_status(ndp_handle* h, int32_t* status_dev, void* stream) {

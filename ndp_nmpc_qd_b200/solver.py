@@ -185,18 +185,23 @@ class BatchedOcpSolver:
         self.device, self.dtype = self.engine.device, self.engine.dtype
         self._lock = threading.RLock()  # get() from a viz thread while solve() runs (nmpc_node.py:233-237)
         B = batch
-        nyf = N * NY + NX  # flat yref record: 14 per stage, 10 at the terminal node
-        # one pinned block per direction, each made of contiguous [B, ...] regions
-        self._sz_x0, self._sz_y, self._sz_p = B * NX, B * nyf, B * (N + 1) * np_
-        self._sz_X, self._sz_U, self._sz_u0 = B * (N + 1) * NX, B * N * NU, B * NU
-        self._pin_in = torch.zeros(self._sz_x0 + self._sz_y + self._sz_p, dtype=self.dtype).pin_memory()
-        self._pin_it = torch.zeros(self._sz_X + self._sz_U, dtype=self.dtype).pin_memory()
-        self._pin_out = torch.zeros(self._sz_X + self._sz_U + self._sz_u0, dtype=self.dtype).pin_memory()
+        NPS = 8  # device stride of a parameter record: q_r(4) f(3) pad
+        # host mirrors in pinned memory, in the layouts the library stores (ndp_solve_host copies them as they are):
+        # yref [B, N+1, 14] (terminal row: first 10 used), p [B, N+1, 8], x0 [B, 10]; outputs u0 [B, 4], status [B]
+        self._pin_x0 = torch.zeros((B, NX), dtype=self.dtype).pin_memory()
+        self._pin_yref = torch.zeros((B, N + 1, NY), dtype=self.dtype).pin_memory()
+        self._pin_p = torch.zeros((B, N + 1, NPS), dtype=self.dtype).pin_memory()
+        self._pin_u0 = torch.zeros((B, NU), dtype=self.dtype).pin_memory()
         self._pin_status = torch.zeros((B,), dtype=torch.int32).pin_memory()
-        self._d_in = torch.zeros_like(self._pin_in, device=self.device)
+        self._h_x0, self._h_yref, self._h_pfull = self._pin_x0.numpy(), self._pin_yref.numpy(), self._pin_p.numpy()
+        self._h_p = self._h_pfull[:, :, :np_]
+        self._ho_u0 = self._pin_u0.numpy()
+        # iterate mirror (uploaded after reset / set of x, u; read back on demand)
+        self._sz_X, self._sz_U = B * (N + 1) * NX, B * N * NU
+        self._pin_it = torch.zeros(self._sz_X + self._sz_U, dtype=self.dtype).pin_memory()
+        self._pin_out = torch.zeros(self._sz_X + self._sz_U, dtype=self.dtype).pin_memory()
         self._d_it = torch.zeros_like(self._pin_it, device=self.device)
         self._d_out = torch.zeros_like(self._pin_out, device=self.device)
-        self._d_status = torch.zeros((B,), dtype=torch.int32, device=self.device)
 
         def regions(t, sizes, shapes):
             out, o = [], 0
@@ -205,24 +210,20 @@ class BatchedOcpSolver:
                 o += n
             return out
 
-        in_shapes = [(B, NX), (B, nyf), (B, N + 1, np_)]
-        self._h_x0, self._h_yref, self._h_p = (r.numpy() for r in regions(self._pin_in, (self._sz_x0, self._sz_y, self._sz_p), in_shapes))
-        self._dv_x0, self._dv_yref, self._dv_p = regions(self._d_in, (self._sz_x0, self._sz_y, self._sz_p), in_shapes)
         it_shapes = [(B, N + 1, NX), (B, N, NU)]
         self._h_X, self._h_U = (r.numpy() for r in regions(self._pin_it, (self._sz_X, self._sz_U), it_shapes))
         self._dv_X, self._dv_U = regions(self._d_it, (self._sz_X, self._sz_U), it_shapes)
-        out_shapes = it_shapes + [(B, NU)]
-        self._ho_X, self._ho_U, self._ho_u0 = (r.numpy() for r in regions(self._pin_out, (self._sz_X, self._sz_U, self._sz_u0), out_shapes))
-        self._do_X, self._do_U, self._do_u0 = regions(self._d_out, (self._sz_X, self._sz_U, self._sz_u0), out_shapes)
+        self._ho_X, self._ho_U = (r.numpy() for r in regions(self._pin_out, (self._sz_X, self._sz_U), it_shapes))
+        self._do_X, self._do_U = regions(self._d_out, (self._sz_X, self._sz_U), it_shapes)
         self._dirty_ref = True
         self._dirty_it = False
         self._it_stale = False  # the device iterate is newer than the host mirror (fetched on demand by get / set)
         self._status = np.zeros(B, np.int32)
         self.stream = torch.cuda.Stream(device=self.device)
+        self._hp = [C.c_void_p(t.data_ptr()) for t in (self._pin_x0, self._pin_yref, self._pin_p, self._pin_u0, self._pin_status)]
 
-    def _yslice(self, stage: int):
-        o = stage * NY
-        return slice(o, o + (NX if stage == self._N else NY))
+    def _ydim(self, stage: int) -> int:
+        return NX if stage == self._N else NY
 
     # ---- acados surface ----
     @property
@@ -239,7 +240,7 @@ class BatchedOcpSolver:
         with torch.cuda.stream(self.stream):
             _lib.check(e.lib.ndp_get(e._h, _lib.FIELD_X, -1, _ptr(self._do_X), 0, _stream_ptr(self.stream)), "ndp_get")
             _lib.check(e.lib.ndp_get(e._h, _lib.FIELD_U, -1, _ptr(self._do_U), 0, _stream_ptr(self.stream)), "ndp_get")
-            self._pin_out[:self._sz_X + self._sz_U].copy_(self._d_out[:self._sz_X + self._sz_U], non_blocking=True)
+            self._pin_out.copy_(self._d_out, non_blocking=True)
         self.stream.synchronize()
         self._h_X[...] = self._ho_X
         self._h_U[...] = self._ho_U
@@ -258,8 +259,8 @@ class BatchedOcpSolver:
                 self._h_U[:, stage, :] = v.reshape(-1, NU)
                 self._dirty_it = True
             elif field == "yref":
-                sl = self._yslice(stage)
-                self._h_yref[:, sl] = v.reshape(-1, sl.stop - sl.start)
+                d = self._ydim(stage)
+                self._h_yref[:, stage, :d] = v.reshape(-1, d)
                 self._dirty_ref = True
             elif field == "p":
                 self._h_p[:, stage, :] = v.reshape(-1, self.np)
@@ -277,7 +278,7 @@ class BatchedOcpSolver:
             elif field == "u":
                 out = self._h_U[:, stage, :]
             elif field == "yref":
-                out = self._h_yref[:, self._yslice(stage)]
+                out = self._h_yref[:, stage, :self._ydim(stage)]
             elif field == "p":
                 out = self._h_p[:, stage, :]
             else:
@@ -286,29 +287,22 @@ class BatchedOcpSolver:
         return out[0] if self.batch == 1 else out
 
     def solve_for_x0(self, x0_bar) -> np.ndarray:
-        """u0 = solver.solve_for_x0(x0) -- nmpc_body_rate_ctl.py:107."""
+        """u0 = solver.solve_for_x0(x0) -- nmpc_body_rate_ctl.py:107.  One C call (ndp_solve_host): reference upload if
+        it changed, one SQP_RTI step, u0 and status back; the predicted trajectory is read back on demand."""
         with self._lock:
             e = self.engine
             self._h_x0[:, :] = np.asarray(x0_bar).reshape(-1, NX)
-            with torch.cuda.stream(self.stream):
-                if self._dirty_it:
+            if self._dirty_it:
+                with torch.cuda.stream(self.stream):
                     self._d_it.copy_(self._pin_it, non_blocking=True)
                     e.set_all("x", self._dv_X, stream=self.stream)
                     e.set_all("u", self._dv_U, stream=self.stream)
-                    self._dirty_it = False
-                if self._dirty_ref:  # x0 | yref | p in one transfer
-                    self._d_in.copy_(self._pin_in, non_blocking=True)
-                    e.set_all("yref", self._dv_yref, stream=self.stream)
-                    e.set_all("p", self._dv_p, stream=self.stream)
-                    self._dirty_ref = False
-                else:
-                    self._d_in[:self._sz_x0].copy_(self._pin_in[:self._sz_x0], non_blocking=True)
-                e.solve(self._dv_x0, self._do_u0, stream=self.stream)
-                e.status(self._d_status, stream=self.stream)
-                o = self._sz_X + self._sz_U
-                self._pin_out[o:].copy_(self._d_out[o:], non_blocking=True)   # u0 only; (X, U) on demand (_sync_iterate)
-                self._pin_status.copy_(self._d_status, non_blocking=True)
-            self.stream.synchronize()
+                self.stream.synchronize()
+                self._dirty_it = False
+            with torch.cuda.device(self.device):
+                _lib.check(e.lib.ndp_solve_host(e._h, self._hp[0], self._hp[1], self._hp[2], 1 if self._dirty_ref else 0,
+                                                self._hp[3], self._hp[4]), "ndp_solve_host")
+            self._dirty_ref = False
             self._it_stale = True
             self._status = self._pin_status.numpy().copy()
             u0 = np.array(self._ho_u0, dtype=np.float64)
@@ -348,10 +342,9 @@ class BatchedOcpSolver:
         ur = np.asarray(ur).reshape(self.batch, self._N, NU)
         with self._lock:
             N = self._N
-            ys = self._h_yref[:, :N * NY].reshape(self.batch, N, NY)
-            ys[:, :, :NX] = xr[:, :N, :]
-            ys[:, :, NX:] = ur
-            self._h_yref[:, N * NY:] = xr[:, N, :]
+            self._h_yref[:, :N, :NX] = xr[:, :N, :]
+            self._h_yref[:, :N, NX:] = ur
+            self._h_yref[:, N, :NX] = xr[:, N, :]
             self._h_p[:, :, :4] = xr[:, :, 6:10]
             if f is not None:
                 if self.np != 7:
