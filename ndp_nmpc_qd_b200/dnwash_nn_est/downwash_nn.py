@@ -71,8 +71,6 @@ class DownwashNN:
             _lib.check(self.lib.ndp_mlp_create(*args, C.byref(self._h)), "ndp_mlp_create")
         self._pin_in = torch.zeros((2, 21, 10), dtype=torch.float64).pin_memory()
         self._pin_out = torch.zeros((21, 3), dtype=torch.float64).pin_memory()
-        self._d_in = torch.zeros((2, 21, 10), dtype=torch.float64, device=self.device)
-        self._d_out = torch.zeros((21, 3), dtype=torch.float64, device=self.device)
         self.stream = torch.cuda.Stream(device=self.device)
 
     def close(self):
@@ -93,15 +91,16 @@ class DownwashNN:
         if n != self._pin_in.shape[1]:
             self._pin_in = torch.zeros((2, n, 10), dtype=torch.float64).pin_memory()
             self._pin_out = torch.zeros((n, 3), dtype=torch.float64).pin_memory()
-            self._d_in = torch.zeros((2, n, 10), dtype=torch.float64, device=self.device)
-            self._d_out = torch.zeros((n, 3), dtype=torch.float64, device=self.device)
         h = self._pin_in.numpy()
         h[0] = ego_pred_x
         h[1] = other_pred_x
-        with torch.cuda.stream(self.stream):
-            self._d_in.copy_(self._pin_in, non_blocking=True)
-            self.forward_pairs(self._d_in[0:1], self._d_in[1:2], out=self._d_out.view(1, n, 3), stream=self.stream)
-            self._pin_out.copy_(self._d_out, non_blocking=True)
+        # latency path: the row kernel reads the pinned host arrays and writes the forces over PCIe itself (unified
+        # addressing makes pinned host memory device-accessible at the same address) -- one launch, no copy operations
+        sp = C.c_void_p(self.stream.cuda_stream)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.ndp_mlp_forward_pairs(self._h, _lib.NDP_F64, 1, n, C.c_void_p(self._pin_in[0].data_ptr()),
+                                                      C.c_void_p(self._pin_in[1].data_ptr()), None, float(DP.r_horiz),
+                                                      C.c_void_p(self._pin_out.data_ptr()), 0, 0, sp), "ndp_mlp_forward_pairs")
         self.stream.synchronize()
         return self._pin_out.numpy().astype(np.float32)
 
