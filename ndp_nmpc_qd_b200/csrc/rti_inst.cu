@@ -5,6 +5,14 @@
 //   nvcc -c rti_inst.cu -DNDP_INST_T=float -DNDP_INST_N=20 -DNDP_INST_LAT=false -DNDP_INST_TAG=f32_20_0
 #include "rti_kernel.cuh"
 
+// a bare `nvcc -c rti_inst.cu` builds the headline instantiation
+#ifndef NDP_INST_T
+#define NDP_INST_T float
+#define NDP_INST_N 20
+#define NDP_INST_LAT false
+#define NDP_INST_TAG f32_20_0
+#endif
+
 #define NDP_CAT2(a, b) a##b
 #define NDP_CAT(a, b) NDP_CAT2(a, b)
 
