@@ -5,7 +5,7 @@ Reference semantics generalised: the reference's leader evaluates the MLP agains
 reference horizon arrives as a PredXU message (ndp_nmpc_leader_node.py:60-76, nmpc_node.py:116-133); here
 every ego sums the MLP force over all neighbours inside the 1 m horizontal gate.
 
-Two exchange modes, same results:
+Two exchange modes, same results (mode="auto" picks by the size of the exchanged tensor):
   "p2p"        each rank writes its [n_local, N+1, 6] fp32 horizons into a symmetric-memory buffer; after one
                device-side barrier the gating / MLP kernels read the peers' shards directly over NVLink
                (ndp_mlp_forward_swarm_parts): the transfer is fused into the feature construction.
@@ -50,6 +50,11 @@ class SwarmStep:
         self.n_all, self.N = n_all, N
         self.part, self.begin, self.end = shard_bounds(n_all, self.world, self.rank)
         self.n_local = self.end - self.begin
+        if mode == "auto":
+            # measured on 4 / 8 B200 (profiles/r1_swarm_n*.json): peer-memory reads win while the step is latency-bound
+            # (1024 quads: 174 vs 185 us per step at 8 GPUs); with several MB of horizons the repeated remote reads of the
+            # MLP's feature fetch cost more than one all-gather (8192 quads: 489 vs 444 us)
+            mode = "p2p" if n_all * (N + 1) * 6 * 4 <= (1 << 20) else "allgather"
         self.mode = mode if self.world > 1 else "local"
         self.dtype = torch.float32 if precision == "f32" else torch.float64
         self.engine = Engine(batch=max(self.n_local, 1), N=N, np_=7, precision=precision, device=self.device)
