@@ -120,6 +120,14 @@ int ndp_solve_host(ndp_handle* h, const void* x0_host, const void* yref_host, co
  * (x0 constraint, linearise, QP, full step).  x0_dev [B][10], u0_dev [B][4] (may be NULL). */
 int ndp_solve(ndp_handle* h, const void* x0_dev, void* u0_dev, void* stream);
 
+/* ndp_update_ex flag: f_dev is written by the kernel launched immediately before on the same stream (the downwash MLP)
+ * and every other input is older than that kernel.  The solve is then launched as a programmatic dependent of it: its
+ * prologue and the staging of (iterate, x0, xr, ur) run while the MLP drains, and it synchronises on the MLP
+ * (griddepcontrol.wait) only before it reads f. */
+#define NDP_UPDATE_F_FROM_PREVIOUS_KERNEL 1
+int ndp_update_ex(ndp_handle* h, const void* x0_dev, const void* xr_dev, const void* ur_dev, const void* f_dev, void* u0_dev,
+                  int flags, void* stream);
+
 /* controller.update(x0, xr, ur[, f]) in ONE launch -- nmpc_body_rate_ctl.py:93-112: the reference
  * upload of ndp_set_reference fused into the solve (yref / p are stored as if set).  f_dev may be NULL. */
 int ndp_update(ndp_handle* h, const void* x0_dev, const void* xr_dev, const void* ur_dev, const void* f_dev,

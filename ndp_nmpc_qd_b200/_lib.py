@@ -22,7 +22,7 @@ EXPORTS = [
     "ndp_mlp_create", "ndp_mlp_destroy", "ndp_mlp_forward_pairs", "ndp_mlp_forward_rows", "ndp_mlp_forward_swarm",
     "ndp_mlp_launch_count", "ndp_mlp_forward_pairs_ex", "ndp_mlp_forward_swarm_parts",
     "ndp_pipeline_create", "ndp_pipeline_destroy", "ndp_pipeline_buffers", "ndp_pipeline_submit", "ndp_pipeline_wait",
-    "ndp_pipeline_bytes", "ndp_pipeline_stream", "ndp_mlp_set_pair_budget", "ndp_solve_host",
+    "ndp_pipeline_bytes", "ndp_pipeline_stream", "ndp_mlp_set_pair_budget", "ndp_solve_host", "ndp_update_ex",
     "ndp_plant_create", "ndp_plant_destroy", "ndp_plant_reset", "ndp_plant_forward", "ndp_plant_autopilot", "ndp_plant_dynamics",
     "ndp_plant_nmpc_x0", "ndp_plant_cmd_from_u0", "ndp_plant_launch_count",
     "ndp_refgen_create", "ndp_refgen_destroy", "ndp_refgen_horizon", "ndp_refgen_launch_count",
@@ -70,6 +70,8 @@ def load() -> C.CDLL:
     lib.ndp_set_reference.argtypes = [vp, vp, vp, vp, vp]
     lib.ndp_solve.argtypes = [vp, vp, vp, vp]
     lib.ndp_update.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    lib.ndp_update_ex.argtypes = [vp, vp, vp, vp, vp, vp, i32, vp]
+    lib.ndp_update_ex.restype = C.c_int
     lib.ndp_solve_host.argtypes = [vp, vp, vp, vp, i32, vp, vp]
     lib.ndp_solve_host.restype = C.c_int
     lib.ndp_status.argtypes = [vp, vp, vp]

@@ -154,6 +154,9 @@ __global__ void __launch_bounds__(MLPT_CTA_THREADS, 1) mlp_tc_kernel(const __gri
     const long long M = mlp_rows(io);
     const long long n_tiles = (M + MLPT_ROWS - 1) / MLPT_ROWS;
     if ((long long)blockIdx.x >= n_tiles) return;  // device-sized launches: nothing for this CTA (before any barrier / TMA / TMEM setup)
+    // a solve launched as a programmatic dependent (NDP_UPDATE_F_FROM_PREVIOUS_KERNEL) may be scheduled as CTAs of this
+    // grid retire; it synchronises on this grid's completion itself before it reads the forces
+    asm volatile("griddepcontrol.launch_dependents;");
     {
         float* dstp = reinterpret_cast<float*>(smt + MLPT_S_PAR);
         const float* srcp = reinterpret_cast<const float*>(&sp);

@@ -157,7 +157,7 @@ RtiCfg<T> make_cfg(const ndp_config& g) {
 
 // ---- the RTI kernel instantiations live in their own translation units (rti_inst.cu) ----
 #define NDP_RTI_DECL(tag, T)                                                                                   \
-    void rti_launch_##tag(int, int, size_t, cudaStream_t, const RtiCfg<T>&, const RtiArgs<T>&);                \
+    void rti_launch_##tag(int, int, size_t, cudaStream_t, const RtiCfg<T>&, const RtiArgs<T>&, bool);          \
     const void* rti_kernel_##tag();
 NDP_RTI_DECL(f32_20_0, float) NDP_RTI_DECL(f32_40_0, float) NDP_RTI_DECL(f32_80_0, float) NDP_RTI_DECL(f32_0_0, float)
 NDP_RTI_DECL(f32_20_1, float)
@@ -166,7 +166,7 @@ NDP_RTI_DECL(f64_20_0, double) NDP_RTI_DECL(f64_40_0, double) NDP_RTI_DECL(f64_8
 
 template <typename T>
 struct RtiInst {
-    void (*launch)(int, int, size_t, cudaStream_t, const RtiCfg<T>&, const RtiArgs<T>&);
+    void (*launch)(int, int, size_t, cudaStream_t, const RtiCfg<T>&, const RtiArgs<T>&, bool);
     const void* (*kernel)();
 };
 // lat: the latency build (fp32, N = 20 only)
@@ -191,7 +191,7 @@ template <> RtiInst<double> rti_inst<double>(int N, bool) {
 
 template <typename T>
 int launch_solve(ndp_handle* h, const void* x0, void* u0, cudaStream_t st, const void* xr = nullptr, const void* ur = nullptr,
-                 const void* f = nullptr) {
+                 const void* f = nullptr, bool pdl = false) {
     RtiCfg<T> c = make_cfg<T>(h->cfg);
     RtiArgs<T> a;
     a.xr = (const T*)xr;
@@ -212,7 +212,7 @@ int launch_solve(ndp_handle* h, const void* x0, void* u0, cudaStream_t st, const
     a.ws_stride = h->ws_stride;
     a.B = h->cfg.batch;
     const int thr = h->ppc * GL;
-    rti_inst<T>(h->cfg.N, h->lat != 0).launch(h->grid, thr, h->smem, st, c, a);
+    rti_inst<T>(h->cfg.N, h->lat != 0).launch(h->grid, thr, h->smem, st, c, a, pdl && xr && f);
     h->launches++;
     CU(cudaGetLastError());
     return 0;
@@ -410,12 +410,17 @@ int ndp_solve(ndp_handle* h, const void* x0, void* u0, void* stream) {
     return h->elt == 4 ? launch_solve<float>(h, x0, u0, (cudaStream_t)stream) : launch_solve<double>(h, x0, u0, (cudaStream_t)stream);
 }
 
-int ndp_update(ndp_handle* h, const void* x0, const void* xr, const void* ur, const void* f, void* u0, void* stream) {
+int ndp_update_ex(ndp_handle* h, const void* x0, const void* xr, const void* ur, const void* f, void* u0, int flags, void* stream) {
     if (!h || !x0 || !xr || !ur) return fail(NDP_E_ARG, "ndp_update: null argument");
     if ((((uintptr_t)xr) | ((uintptr_t)ur)) & 7) return fail(NDP_E_ARG, "ndp_update: xr / ur must be 8-byte aligned");
     std::lock_guard<std::mutex> lk(h->mu);
-    return h->elt == 4 ? launch_solve<float>(h, x0, u0, (cudaStream_t)stream, xr, ur, f)
-                       : launch_solve<double>(h, x0, u0, (cudaStream_t)stream, xr, ur, f);
+    const bool pdl = (flags & NDP_UPDATE_F_FROM_PREVIOUS_KERNEL) != 0;
+    return h->elt == 4 ? launch_solve<float>(h, x0, u0, (cudaStream_t)stream, xr, ur, f, pdl)
+                       : launch_solve<double>(h, x0, u0, (cudaStream_t)stream, xr, ur, f, pdl);
+}
+
+int ndp_update(ndp_handle* h, const void* x0, const void* xr, const void* ur, const void* f, void* u0, void* stream) {
+    return ndp_update_ex(h, x0, xr, ur, f, u0, 0, stream);
 }
 
 // one host-buffer step on stream st: [reference upload,] solve, results back (what ndp_solve_host captures)
@@ -830,7 +835,8 @@ static int pipeline_enqueue_serial(ndp_pipeline* p, cudaStream_t st) {
                                           in + p->o_gate, p->r_horiz, p->d_f, 0, 0, st);
         if (rc) return rc;
     }
-    int rc = ndp_update(h, in + p->o_x0, in + p->o_xr, in + p->o_ur, p->mlp ? p->d_f : nullptr, out, st);
+    int rc = ndp_update_ex(h, in + p->o_x0, in + p->o_xr, in + p->o_ur, p->mlp ? p->d_f : nullptr, out,
+                           p->mlp ? NDP_UPDATE_F_FROM_PREVIOUS_KERNEL : 0, st);
     if (rc) return rc;
     if (zero_copy) {
         CU(cudaMemcpyAsync(p->h_out + p->o_status, h->status, (size_t)h->cfg.batch * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
@@ -883,7 +889,8 @@ int ndp_pipeline_submit(ndp_pipeline* p, int slot) {
                                           p->r_horiz, df, 0, 0, p->s_cmp);
         if (rc) return rc;
     }
-    int rc = ndp_update(h, din + p->o_x0, din + p->o_xr, din + p->o_ur, p->mlp ? df : nullptr, dout, p->s_cmp);
+    int rc = ndp_update_ex(h, din + p->o_x0, din + p->o_xr, din + p->o_ur, p->mlp ? df : nullptr, dout,
+                           p->mlp ? NDP_UPDATE_F_FROM_PREVIOUS_KERNEL : 0, p->s_cmp);
     if (rc) return rc;
     CU(cudaMemcpyAsync(dout + p->o_status, h->status, (size_t)h->cfg.batch * sizeof(int32_t), cudaMemcpyDeviceToDevice, p->s_cmp));
     CU(cudaEventRecord(p->e_cmp[slot], p->s_cmp));

@@ -18,9 +18,25 @@
 
 namespace ndp {
 
+// pdl: launch as a programmatic dependent of the previous kernel in the stream (the kernel then starts while that
+// kernel drains and synchronises on it with griddepcontrol.wait before it reads the forces)
 void NDP_CAT(rti_launch_, NDP_INST_TAG)(int grid, int threads, size_t smem, cudaStream_t st, const RtiCfg<NDP_INST_T>& c,
-                                        const RtiArgs<NDP_INST_T>& a) {
-    rti_step_kernel<NDP_INST_T, NDP_INST_N, NDP_INST_LAT><<<grid, threads, smem, st>>>(c, a);
+                                        const RtiArgs<NDP_INST_T>& a, bool pdl) {
+    if (!pdl) {
+        rti_step_kernel<NDP_INST_T, NDP_INST_N, NDP_INST_LAT><<<grid, threads, smem, st>>>(c, a);
+        return;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, rti_step_kernel<NDP_INST_T, NDP_INST_N, NDP_INST_LAT>, c, a);
 }
 
 const void* NDP_CAT(rti_kernel_, NDP_INST_TAG)() { return (const void*)rti_step_kernel<NDP_INST_T, NDP_INST_N, NDP_INST_LAT>; }

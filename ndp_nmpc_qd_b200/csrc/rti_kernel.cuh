@@ -1139,18 +1139,24 @@ __global__ void __launch_bounds__(RTI_CTA, (sizeof(T) == 4) ? (kLat ? 4 : 8) : 3
                     cp_async<8>(sY + k * SYS + NX + q, gur + k * NU + q);
                 }
                 if (lane < NU) sY[N * SYS + NX + lane] = T(0);
-                if (a.f) {
-                    const T* gf = a.f + (size_t)prob * (N + 1) * 3;
-                    for (int i = lane; i < (N + 1) * 3; i += GL) {
-                        const int k = i / 3, m = i - k * 3;
-                        cp_async<(int)sizeof(T)>(sPar + k * NPS + 4 + m, gf + i);
-                    }
-                    for (int k = lane; k <= N; k += GL) sPar[k * NPS + 7] = T(0);
-                } else {
+                if (!a.f) {
                     for (int i = lane; i < (N + 1) * 4; i += GL) sPar[(i >> 2) * NPS + 4 + (i & 3)] = T(0);
                 }
             }
             for (int i = lane; i < (N + 1) * 2; i += GL) sY[(i >> 1) * SYS + NYS + (i & 1)] = T(0);
+            if (a.xr != nullptr && a.f) {
+                // The forces come last: when this kernel was launched as a programmatic dependent of the kernel that
+                // produces them (ndp_update_ex, NDP_UPDATE_F_FROM_PREVIOUS_KERNEL), everything above -- which only
+                // reads older data -- has run under that kernel's tail; wait for its completion here (a no-op for an
+                // ordinary launch).
+                asm volatile("griddepcontrol.wait;" ::: "memory");
+                const T* gf = a.f + (size_t)prob * (N + 1) * 3;
+                for (int i = lane; i < (N + 1) * 3; i += GL) {
+                    const int k = i / 3, m = i - k * 3;
+                    cp_async<(int)sizeof(T)>(sPar + k * NPS + 4 + m, gf + i);
+                }
+                for (int k = lane; k <= N; k += GL) sPar[k * NPS + 7] = T(0);
+            }
         }
         const T x0v = isx ? a.x0[(size_t)prob * NX + lane] : T(0);
         // active set the previous solve of this problem ended with (first guess of this one)

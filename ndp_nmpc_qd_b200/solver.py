@@ -138,8 +138,11 @@ class Engine:
         return u0
 
     def update(self, x0: torch.Tensor, xr: torch.Tensor, ur: torch.Tensor, f: Optional[torch.Tensor] = None,
-               u0: Optional[torch.Tensor] = None, stream=None) -> torch.Tensor:
-        """controller.update() in one launch: reference upload fused into the RTI solve."""
+               u0: Optional[torch.Tensor] = None, stream=None, f_from_prev_kernel: bool = False) -> torch.Tensor:
+        """controller.update() in one launch: reference upload fused into the RTI solve.
+        f_from_prev_kernel: f is written by the kernel launched just before on this stream (DownwashNN) and all other
+        inputs are older -- the solve is then a programmatic dependent launch that stages its inputs while that kernel
+        drains (NDP_UPDATE_F_FROM_PREVIOUS_KERNEL, include/ndp_nmpc.h)."""
         self._chk(x0, (self.batch, NX))
         self._chk(xr, (self.batch, self.N + 1, NX))
         self._chk(ur, (self.batch, self.N, NU))
@@ -148,7 +151,8 @@ class Engine:
         if u0 is None:
             u0 = torch.empty((self.batch, NU), dtype=self.dtype, device=self.device)
         self._chk(u0, (self.batch, NU))
-        _lib.check(self.lib.ndp_update(self._h, _ptr(x0), _ptr(xr), _ptr(ur), _ptr(f), _ptr(u0), _stream_ptr(stream)), "ndp_update")
+        _lib.check(self.lib.ndp_update_ex(self._h, _ptr(x0), _ptr(xr), _ptr(ur), _ptr(f), _ptr(u0), 1 if (f_from_prev_kernel and f is not None) else 0,
+                                          _stream_ptr(stream)), "ndp_update")
         return u0
 
     def status(self, out: Optional[torch.Tensor] = None, stream=None) -> torch.Tensor:
