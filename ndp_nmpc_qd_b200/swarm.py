@@ -61,7 +61,7 @@ class SwarmStep:
         self.nn = DownwashNN(device=self.device)
         self.f = torch.zeros((max(self.n_local, 1), N + 1, 3), dtype=self.dtype, device=self.device)
         self.step_no = 0
-        self.trace = None  # set to a list to collect (label, cuda event) marks of every step (tools/swarm_multi_gpu.py --trace)
+        self.trace = None  # set to a list to collect (label, cuda event) marks of every step (tests/diag/swarm_multi_gpu.py --trace)
         shape = (2, self.part, N + 1, 6)  # double-buffered by step parity: one barrier per step is enough
         if self.mode == "p2p":
             import torch.distributed._symmetric_memory as symm

@@ -4,7 +4,7 @@ Reference: dnwash_nn_est/nn_net.py:7-18 (Linear 6-128, ReLU, Linear 128-64, ReLU
 ReLU, Linear 128-3), dnwash_nn_est/downwash_nn.py:21-29 (features = (other - ego)[:, 0:6] computed
 in float64 then cast to float32), gate ndp_nmpc_leader_node.py:65-76.  Pinned against outputs of
 the reference's own torch module with the shipped weights (tests/golden/mlp_golden.npz, generated
-by tools/make_golden.py).
+by tests/golden/make_golden.py).
 """
 from __future__ import annotations
 

@@ -2,7 +2,7 @@
 
 numpy float64 restatement of /root/reference/dop_sim/scripts/quadrotor/ (file:line below are relative to
 that directory).  Pinned: tests/golden/plant_golden.npz holds outputs of the reference's own TorchScript
-module (tools/make_plant_golden.py) and tests/test_plant_oracle.py checks this file against them,
+module (tests/golden/make_plant_golden.py) and tests/test_plant_oracle.py checks this file against them,
 including the SURVEY.md B.4 known answer.
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may import this module.

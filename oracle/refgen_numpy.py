@@ -4,7 +4,7 @@ numpy float64 restatement of ndp_nmpc/scripts/pt_pub/: piecewise-polynomial eval
 branch after the end (base_pt_publisher.py:81-148), differential flatness (pt_publisher.py:188-248) and the
 state/input packing traj_full_pt_2_x_u (pt_publisher.py:124-147).  quaternion_from_matrix restates the ROS
 `tf` package's algorithm [EXT] (tf_conversions is not in /root/reference).  Pinned against
-tests/golden/refgen_golden.npz (outputs of the reference's own functions, tools/make_refgen_golden.py).
+tests/golden/refgen_golden.npz (outputs of the reference's own functions, tests/golden/make_refgen_golden.py).
 """
 from __future__ import annotations
 

@@ -1,6 +1,6 @@
 """Diagnostic run for a GPU box: prints parity numbers without asserting (so one call tells a lot)."""
 import sys, os, time, traceback
-ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "..")
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np, torch
 from conftest import rel_err

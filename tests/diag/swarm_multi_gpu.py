@@ -1,6 +1,6 @@
 """Coupled swarm on several GPUs of one node (BASELINE.json config 4): correctness of the fused peer-memory
 exchange against the NCCL all-gather baseline and the CPU oracle, and step timings of both.
-  python -m torch.distributed.run --nnodes=1 --nproc-per-node=N --master-addr 127.0.0.1 tools/swarm_multi_gpu.py [--quads 1024]"""
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node=N --master-addr 127.0.0.1 tests/diag/swarm_multi_gpu.py [--quads 1024]"""
 import argparse
 import json
 import os
@@ -10,7 +10,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
 from ndp_nmpc_qd_b200 import traj_gen  # noqa: E402
 from ndp_nmpc_qd_b200.swarm import SwarmStep  # noqa: E402
 from ndp_nmpc_qd_b200.traj_gen.refgen import RefGen  # noqa: E402

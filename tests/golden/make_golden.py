@@ -15,7 +15,7 @@ import sys
 import numpy as np
 import torch
 
-ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "..")
 REF = "/root/reference/ndp_nmpc/scripts"
 OUT = os.path.join(ROOT, "tests", "golden")
 sys.path.insert(0, ROOT)

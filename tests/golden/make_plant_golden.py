@@ -14,7 +14,7 @@ import sys
 import numpy as np
 import torch
 
-ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "..")
 sys.path.insert(0, "/root/reference/dop_sim/scripts")
 from quadrotor.mul_quadrotors import MulQuadrotors  # noqa: E402  (reference module)
 

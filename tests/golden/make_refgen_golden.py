@@ -20,7 +20,7 @@ import types
 import numpy as np
 import yaml
 
-ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "..")
 REF = "/root/reference"
 
 

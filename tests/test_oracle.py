@@ -1,5 +1,5 @@
 """CPU tests of the oracle itself: pinned against the golden vectors generated from the
-reference's own code (tools/make_golden.py), the SURVEY.md known answers and an independent
+reference's own code (tests/golden/make_golden.py), the SURVEY.md known answers and an independent
 dense-KKT solve."""
 import numpy as np
 import pytest

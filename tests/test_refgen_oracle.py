@@ -1,5 +1,5 @@
 """CPU tests: min-snap planner (host) and the reference-generation oracle against outputs of the
-reference's own code (tests/golden/refgen_golden.npz, tools/make_refgen_golden.py)."""
+reference's own code (tests/golden/refgen_golden.npz, tests/golden/make_refgen_golden.py)."""
 import numpy as np
 import pytest
 
