@@ -333,6 +333,12 @@ def run_native(args, rank, local_rank, world):
     if world == 1 and not args.no_latency:
         out["latency_b1"] = batch1_latency(dev)
         out["stress"] = stress_variant(dev, B)
+        # fp32 build's first step on the same problems, for the fp32-vs-fp64 distance
+        eng.reset(d_sets[0]["xr"], d_sets[0]["ur"])
+        nn.forward_pairs(d_sets[0]["xr"], d_sets[0]["other"], d_sets[0]["gate"], out=f_buf)
+        eng.update(d_sets[0]["x0"], d_sets[0]["xr"], d_sets[0]["ur"], f_buf, u0_buf)
+        torch.cuda.synchronize()
+        out["f64_build"] = f64_build(dev, sets[0], u0_buf.cpu().numpy().astype(np.float64))
     print(json.dumps(out), flush=True)
     if dist is not None:
         dist.destroy_process_group()
@@ -371,6 +377,39 @@ def stress_variant(dev, B, steps=20):
                 active_bounds_mean=float(st[:, 3].mean()), status_nonzero=int((status != 0).sum()),
                 achieved_tflops=algorithmic_flop_per_solve(N_HORIZON, n_fact) * B / (k_ms * 1e-3) / 1e12,
                 note="RTI kernel only (no MLP): 5x perturbation, omega_max 1.5, c_max 15, f ~ N(0,1); iterate reset before every solve")
+
+
+def f64_build(dev, w, u0_f32):
+    """The fp64 build of the same solve on one step's problems (north star: 'tighter for an fp64 build'): kernel time
+    and the distance of the fp32 build's u0 from it."""
+    import torch
+
+    from ndp_nmpc_qd_b200.dnwash_nn_est import DownwashNN
+    from ndp_nmpc_qd_b200.solver import Engine
+
+    B = w["x0"].shape[0]
+    eng = Engine(batch=B, N=N_HORIZON, np_=7, precision="f64", device=dev)
+    nn = DownwashNN(device=dev)
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device=dev)
+    x0, xr, ur, other = t(w["x0"]), t(w["xr"]), t(w["ur"]), t(w["other"])
+    f = nn.forward_pairs(xr, other, t(w["xr"][:, 0, 0:2]))
+    u0 = torch.empty((B, NU), dtype=torch.float64, device=dev)
+    ms = []
+    for s in range(8):
+        eng.reset(xr, ur)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        eng.update(x0, xr, ur, f, u0)
+        e1.record()
+        torch.cuda.synchronize()
+        if s >= 2:
+            ms.append(e0.elapsed_time(e1))
+    k_ms = float(np.mean(ms))
+    ref = u0.cpu().numpy()
+    rel = float((np.abs(u0_f32 - ref).max(1) / np.maximum(np.abs(ref).max(1), 1.0)).max()) if u0_f32 is not None else None
+    return dict(kernel_ms=k_ms, value=B / (k_ms * 1e-3), unit=UNIT, u0_rel_diff_f32_vs_f64=rel,
+                status_nonzero=int((eng.status().cpu().numpy() != 0).sum()),
+                note="rti_step_kernel<double>, same problems, first RTI step from the iterate reset to the reference (MLP forces from the fp32-accurate kernel)")
 
 
 def batch1_latency(dev):

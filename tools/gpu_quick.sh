@@ -1,10 +1,9 @@
 #!/bin/bash
+# quick check: GPU tests + the bench line (own arm)
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
 tail -3 gpurun_out/pytest_gpu.log
-python - <<'PY'
-import sys, json, torch
-sys.path.insert(0, '.')
-import bench
-print(json.dumps(bench.batch1_latency(torch.device('cuda', 0))))
-PY
+timeout 400 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err
+tail -3 gpurun_out/bench.err
+python -c "
+import json; d=json.load(open('gpurun_out/bench.json')); print(d['value'], d['e2e']['value'], json.dumps(d.get('f64_build')), json.dumps(d['latency_b1'])[:300])"
