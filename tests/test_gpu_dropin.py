@@ -97,3 +97,32 @@ def test_acados_style_set_get_surface(built_lib, c_oracle):
     assert rel_err(s.get(s.N, "x")[None], X[:, s.N]) < 1e-4
     with pytest.raises(Exception):
         s.set(0, "nope", x0)
+
+
+@pytest.mark.parametrize("B", [7, 1000])
+def test_batched_mirror_equals_device_path(built_lib, B):
+    """BatchedOcpSolver with a batch axis (host mirrors, one ndp_solve_host call per solve: zero-copy x0 / u0 for the
+    small batch, staged copies for the large one) == the device-pointer Engine path, three warm-started steps."""
+    import torch
+
+    from ndp_nmpc_qd_b200.solver import BatchedOcpSolver, Engine
+
+    w = wl.independent_problems(B, seed=90 + B, scale=3.0)
+    fd = np.random.default_rng(3).normal(size=(B, 21, 3))
+    s = BatchedOcpSolver(batch=B, np_=7)
+    s.reset(w["xr"], w["ur"])
+    e = Engine(batch=B, np_=7)
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float32, device="cuda")
+    xr, ur, f = t(w["xr"]), t(w["ur"]), t(fd)
+    e.reset(xr, ur)
+    e.set_reference(xr, ur, f)
+    rng = np.random.default_rng(4)
+    for step in range(3):
+        x0 = w["x0"] + 0.02 * step * rng.normal(size=w["x0"].shape)
+        if step != 1:   # step 1 reuses the uploaded reference (ndp_solve_host without the upload)
+            s.set_reference(w["xr"], w["ur"], fd)
+        u0 = s.solve_for_x0(x0)
+        ref = e.solve(t(x0)).cpu().numpy()
+        assert np.array_equal(u0.astype(np.float32), ref), step
+        assert np.array_equal(s.status, e.status().cpu().numpy())
+    assert np.array_equal(s.get_all("x").astype(np.float32), e.get_all("x").cpu().numpy())
