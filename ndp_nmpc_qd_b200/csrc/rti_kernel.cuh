@@ -548,7 +548,7 @@ static_assert(SmemLayout(1).oHux - SmemLayout(1).oY >= FW_RING * FW_REC, "forwar
 template <typename T, bool kFinal>
 __device__ __forceinline__ void forward_sweep(const RtiCfg<T>& c, int N, int lane, unsigned mask, T dx0, T* sm, const SmemLayout& L,
                                               const T* ws, const WsLayout& WL, T lo, T hi, T* gX, T* gU, T* gu0, bool& viol, bool& bad,
-                                              int& nact) {
+                                              int& nact, bool rezero_pads = true) {
     T* sDz = sm + L.oDz;
     const bool isx = lane < 10, isu = (lane >= 10 && lane < 14), isv = (lane >= 3 && lane < 6);
     const T* rec = ws + WL.oRec + (long long)((lane < 14) ? lane : 13) * TLD;
@@ -628,8 +628,10 @@ __device__ __forceinline__ void forward_sweep(const RtiCfg<T>& c, int N, int lan
             b_l |= !(fabs(v) <= T(1e30));
         }
         __syncwarp(mask);
-        // the ring ran over the stage tiles: restore their zero pad columns (9..11) for the next problem
-        for (int i = lane; i < 20 * 3; i += GL) sm[L.oT0 + (i / 3) * TLD + 9 + (i % 3)] = T(0);
+        // the ring ran over the stage tiles: restore their zero pad columns (9..11) for the next problem of the
+        // persistent loop (the constrained path of this problem reloads whole tiles, pads included, from the workspace)
+        if (rezero_pads)
+            for (int i = lane; i < 20; i += GL) { T* q = sm + L.oT0 + i * TLD + 9; q[0] = T(0); q[1] = T(0); q[2] = T(0); }
         viol = __any_sync(mask, v_l);
         bad = __any_sync(mask, b_l);
         nact = n_l;
@@ -1204,7 +1206,7 @@ __global__ void __launch_bounds__(RTI_CTA, (sizeof(T) == 4) ? (kLat ? 4 : 8) : 3
         if (!warm) {
             ok = backward_sweep<T, true, 0, false>(c, N, lane, mask, sm, L, ws, WL, sTriv, nullptr);
             forward_sweep<T, true>(c, N, lane, mask, dx0, sm, L, ws, WL, lo, hi, gX, gU, a.u0 ? a.u0 + (size_t)prob * NU : nullptr, viol, bad,
-                                   nact_l);
+                                   nact_l, prob + (int)gridDim.x * ppc < a.B);
         }
         if (warm || (ok && viol)) {
             // Called through an opaque function pointer: ptxas then allocates the nominal path against the plain ABI
