@@ -112,7 +112,13 @@ def make_workload(B, seed, n_sets):
 
 
 def cpu_oracle_rate(sets, seconds=12.0, threads=0):
-    """Time the fp64 oracle port (HPIPM-like tolerance) + numpy MLP on a bounded sample."""
+    """Time the fp64 oracle port (HPIPM-like tolerance) + numpy MLP on a bounded sample, on every host core this
+    process may use (torchrun exports OMP_NUM_THREADS=1, which must not throttle the CPU arm)."""
+    if threads <= 0:
+        try:
+            threads = len(os.sched_getaffinity(0))
+        except AttributeError:
+            threads = os.cpu_count() or 1
     from oracle import mlp_numpy
     from oracle.c_oracle import COracle, make_cfg
     from ndp_nmpc_qd_b200.dnwash_nn_est.downwash_nn import DEFAULT_WEIGHTS
