@@ -34,8 +34,8 @@ constexpr float MLPT_LO_INV = 1.f / 2048.f;
 constexpr int MLPT_W2_ELEMS = MLP_H2 * MLP_H1;
 constexpr int MLPT_W3_ELEMS = MLP_H3 * MLP_H2;
 constexpr int MLPT_WIMG_ELEMS = 2 * MLPT_W2_ELEMS + 2 * MLPT_W3_ELEMS;
-// fp32 side parameters (layers 1 and 4, biases): passed by value as a kernel argument, staged once per
-// CTA in shared memory and read with broadcast 128-bit loads (indexed constant-bank loads measured 4x slower)
+// fp32 side parameters (layers 1 and 4, biases): a small device buffer, staged once per CTA in shared memory and
+// read with broadcast 128-bit loads (indexed constant-bank loads measured 4x slower)
 struct alignas(16) MlpSmall {
     float W1[MLP_H1 * MLP_IN], b1[MLP_H1], b2[MLP_H2], b3[MLP_H3], W4[MLP_OUT * MLP_H3], b4[4];
 };
@@ -139,7 +139,7 @@ __device__ __forceinline__ void group_sync(int grp) { asm volatile("bar.sync %0,
 // a group, threads t and t + 128 share row t (= TMEM lane t: warps w and w + 4 address the same lane
 // quarter) and each owns one half of the columns of every layer.  Features of the next tile are
 // prefetched while the current one computes.
-__global__ void __launch_bounds__(MLPT_CTA_THREADS, 1) mlp_tc_kernel(const __grid_constant__ MlpSmall sp, const __half* __restrict__ wimg, const MlpIo io) {
+__global__ void __launch_bounds__(MLPT_CTA_THREADS, 1) mlp_tc_kernel(const MlpSmall* __restrict__ gsp, const __half* __restrict__ wimg, const MlpIo io) {
     extern __shared__ __align__(1024) unsigned char smt[];
     uint64_t* sBar = reinterpret_cast<uint64_t*>(smt + MLPT_S_BAR);
     uint32_t* sTmem = reinterpret_cast<uint32_t*>(smt + MLPT_S_BAR + 32);
@@ -158,9 +158,12 @@ __global__ void __launch_bounds__(MLPT_CTA_THREADS, 1) mlp_tc_kernel(const __gri
     // grid retire; it synchronises on this grid's completion itself before it reads the forces
     asm volatile("griddepcontrol.launch_dependents;");
     {
-        float* dstp = reinterpret_cast<float*>(smt + MLPT_S_PAR);
-        const float* srcp = reinterpret_cast<const float*>(&sp);
-        for (int i = threadIdx.x; i < (int)(sizeof(MlpSmall) / 4); i += MLPT_CTA_THREADS) dstp[i] = srcp[i];
+        // side parameters: one coalesced 128-bit load per thread from the device copy (staging them from the kernel's
+        // constant-bank argument took 9 % of the kernel: every lane of a warp read a different constant address)
+        static_assert(sizeof(MlpSmall) % 16 == 0, "MlpSmall is copied as float4");
+        float4* dstp = reinterpret_cast<float4*>(smt + MLPT_S_PAR);
+        const float4* srcp = reinterpret_cast<const float4*>(gsp);
+        for (int i = threadIdx.x; i < (int)(sizeof(MlpSmall) / 16); i += MLPT_CTA_THREADS) dstp[i] = srcp[i];
     }
 
     // ---- one-time setup: mbarriers, weights -> smem by TMA bulk copy (lands under the first tile's
@@ -389,11 +392,11 @@ inline void mlp_tc_small(const float* host_params, MlpSmall* sp) {
     for (int i = 0; i < 4; i++) sp->b4[i] = i < MLP_OUT ? host_params[MLP_OB4 + i] : 0.f;
 }
 
-inline int mlp_tc_launch(const MlpSmall& sp, const void* wimg, const MlpIo& io, int n_sm, cudaStream_t st) {
+inline int mlp_tc_launch(const MlpSmall* sp_dev, const void* wimg, const MlpIo& io, int n_sm, cudaStream_t st) {
     const long long tiles = (io.M + MLPT_ROWS - 1) / MLPT_ROWS;  // io.M is the row capacity when the count lives on the device
     const long long ctas = (tiles + MLPT_GROUPS - 1) / MLPT_GROUPS;
     const int grd = (int)(ctas < n_sm ? ctas : n_sm);
-    mlp_tc_kernel<<<grd, MLPT_CTA_THREADS, MLPT_SMEM, st>>>(sp, reinterpret_cast<const __half*>(wimg), io);
+    mlp_tc_kernel<<<grd, MLPT_CTA_THREADS, MLPT_SMEM, st>>>(sp_dev, reinterpret_cast<const __half*>(wimg), io);
     return (int)cudaGetLastError();
 }
 

@@ -524,7 +524,7 @@ int ndp_rk4_sens(int precision, int64_t M, double hh, double mass, double gravit
 struct ndp_mlp {
     float* params;     // packed fp32 parameters (mlp_kernel.cuh layout)
     void* tc_weights;  // tensor-core operand images (mlp_tc_kernel.cuh)
-    ndp::MlpSmall small;  // fp32 side parameters passed by value to the tensor-core kernel
+    ndp::MlpSmall* d_small;  // fp32 side parameters of the tensor-core kernel (device copy)
     int n_sm;
     // swarm scratch (grown on demand)
     int* total; int2* seg; int2* pairs; float* fpair;
@@ -542,7 +542,7 @@ static int mlp_run(ndp_mlp* m, MlpIo io, int path, cudaStream_t st) {
         mlp_row_kernel<<<(int)io.M, MLPR_THREADS, 0, st>>>(m->params, io);
         CU(cudaGetLastError());
     } else if (path == 2) {
-        int rc = mlp_tc_launch(m->small, m->tc_weights, io, m->n_sm, st);
+        int rc = mlp_tc_launch(m->d_small, m->tc_weights, io, m->n_sm, st);
         if (rc) return cuda_fail((cudaError_t)rc, "mlp_tc_kernel launch");
     } else if (path == 1) {
         const long long tiles = (io.M + MLPF_ROWS - 1) / MLPF_ROWS;
@@ -577,14 +577,19 @@ int ndp_mlp_create(const float* W1, const float* b1, const float* W2, const floa
     m->total = nullptr; m->seg = nullptr; m->pairs = nullptr; m->fpair = nullptr;
     m->cap_ego = m->cap_pairs = m->cap_rows = 0;
     m->pair_budget = 2ll << 20;  // 2 Mi pairs: 16 MB of pair indices + 0.5 GB of per-pair forces at 21 nodes
-    m->params = nullptr; m->tc_weights = nullptr;
+    m->params = nullptr; m->tc_weights = nullptr; m->d_small = nullptr;
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&m->n_sm, cudaDevAttrMultiProcessorCount, dev);
     cudaError_t e = cudaMalloc(&m->params, sizeof(float) * MLP_NPARAM);
     if (e == cudaSuccess) e = cudaMemcpy(m->params, host, sizeof(float) * MLP_NPARAM, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = (cudaError_t)mlp_tc_prepare(host, &m->tc_weights);
-    mlp_tc_small(host, &m->small);
+    {
+        MlpSmall hs;
+        mlp_tc_small(host, &hs);
+        if (e == cudaSuccess) e = cudaMalloc(&m->d_small, sizeof(MlpSmall));
+        if (e == cudaSuccess) e = cudaMemcpy(m->d_small, &hs, sizeof(MlpSmall), cudaMemcpyHostToDevice);
+    }
     if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_fp32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MLPF_SMEM);
     delete[] host;
     if (e != cudaSuccess) { ndp_mlp_destroy(m); return cuda_fail(e, "ndp_mlp_create"); }
@@ -594,7 +599,7 @@ int ndp_mlp_create(const float* W1, const float* b1, const float* W2, const floa
 
 int ndp_mlp_destroy(ndp_mlp* m) {
     if (!m) return 0;
-    cudaFree(m->params); cudaFree(m->tc_weights);
+    cudaFree(m->params); cudaFree(m->tc_weights); cudaFree(m->d_small);
     cudaFree(m->total); cudaFree(m->seg); cudaFree(m->pairs); cudaFree(m->fpair);
     delete m;
     return 0;
