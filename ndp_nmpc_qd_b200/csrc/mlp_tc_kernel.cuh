@@ -154,6 +154,13 @@ __global__ void __launch_bounds__(MLPT_CTA_THREADS, 1) mlp_tc_kernel(const MlpSm
     const long long M = mlp_rows(io);
     const long long n_tiles = (M + MLPT_ROWS - 1) / MLPT_ROWS;
     if ((long long)blockIdx.x >= n_tiles) return;  // device-sized launches: nothing for this CTA (before any barrier / TMA / TMEM setup)
+    // tile -> (CTA, group): consecutive tiles go to different SMs, so a ragged last round adds one tile to
+    // as many SMs as it has tiles instead of two tiles (both groups) to half as many.  The first tile's features are
+    // requested before anything else, so that their DRAM latency runs under the one-off setup below.
+    const long long tile0 = (long long)grp * gridDim.x + blockIdx.x, tstride = (long long)gridDim.x * MLPT_GROUPS;
+    float xn[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    bool on_n = false;
+    if (tile0 < n_tiles && tile0 * MLPT_ROWS + t < M) on_n = mlp_fetch_row(io, tile0 * MLPT_ROWS + t, xn);
     // a solve launched as a programmatic dependent (NDP_UPDATE_F_FROM_PREVIOUS_KERNEL) may be scheduled as CTAs of this
     // grid retire; it synchronises on this grid's completion itself before it reads the forces
     asm volatile("griddepcontrol.launch_dependents;");
@@ -203,12 +210,6 @@ __global__ void __launch_bounds__(MLPT_CTA_THREADS, 1) mlp_tc_kernel(const MlpSm
 
     int stamp = 0;
     MLPT_STAMP(stamp++);
-    // tile -> (CTA, group): consecutive tiles go to different SMs, so a ragged last round adds one tile to
-    // as many SMs as it has tiles instead of two tiles (both groups) to half as many
-    const long long tile0 = (long long)grp * gridDim.x + blockIdx.x, tstride = (long long)gridDim.x * MLPT_GROUPS;
-    float xn[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    bool on_n = false;
-    if (tile0 < n_tiles && tile0 * MLPT_ROWS + t < M) on_n = mlp_fetch_row(io, tile0 * MLPT_ROWS + t, xn);
     for (long long tile = tile0; tile < n_tiles; tile += tstride) {
         const long long row = tile * MLPT_ROWS + t;
         float x[6];
