@@ -273,6 +273,32 @@ int ndp_refgen_horizon(ndp_refgen* g, int precision, int64_t B, const int32_t* t
                        double th_pred, const double* offset_dev, void* xr_dev, void* ur_dev, void* stream);
 int64_t ndp_refgen_launch_count(const ndp_refgen* g);
 
+/* ---- wire formats between the nodes, batched ----
+ * PredXU (ndp_nmpc/msg/PredXU.msg:1-4): Float64MultiArray[] x, Float64MultiArray[] u.  One quadrotor's payload here is
+ * the flat float64 array [x_0 .. x_N (10 each) | u_0 .. u_{N-1} (4 each)], ndp_predxu_len(N) = (N+1)*10 + N*4 doubles
+ * (2 320 B at N = 20); msg_dev is [B][ndp_predxu_len(N)].
+ * pack: do_pub_ref (nmpc_node.py:116-133) -- the reference horizon (xr [B][N+1][10], ur [B][N][4] in `precision`).
+ * unpack: FollowerNode.sub_pred_callback (nmpc_follower_node.py:57-74) -- x rows get offset[b][0:3] (float64 [B][3],
+ * the alpha-filtered formation offset; NULL: none, as in ndp_nmpc_leader_node.py:69-71) added to their position. */
+int64_t ndp_predxu_len(int32_t N);
+int ndp_predxu_pack(int precision, int64_t B, int32_t N, const void* xr_dev, const void* ur_dev, double* msg_dev, void* stream);
+int ndp_predxu_unpack(int precision, int64_t B, int32_t N, const double* msg_dev, const double* offset_dev, void* xr_dev,
+                      void* ur_dev, void* stream);
+
+/* ---- hover-throttle estimator hook, batched on the device ----
+ * HoverThrottleEstimator(ts).update(vz, throttle) -- hv_throttle_est/hover_throttle_estimator.py:15-53, called at 50 Hz
+ * from nmpc_node.py:251-253 with vz = odometry twist.linear.z and throttle = the last AttitudeTarget thrust.
+ * est_dev: float64 [n][8] = {vz[k-1], az[k-1], f_collect, k_throttle, P00, P01, P10, P11}; init sets x = (0, 50),
+ * P = I (estimator_params.py:13).  vz / throttle: float64 with element strides vz_ld / throttle_ld (e.g. the plant
+ * state column 15 with stride 35 and the command column 3 with stride 4).  k_throttle_dev [n] (may be NULL) receives
+ * the estimate that nmpc_u_2_att_tgt divides by. */
+int ndp_hover_throttle_init(int64_t n, double* est_dev, double* k_throttle_dev, void* stream);
+int ndp_hover_throttle_update(int64_t n, double ts, const double* vz_dev, int64_t vz_ld, const double* throttle_dev,
+                              int64_t throttle_ld, double* est_dev, double* k_throttle_dev, void* stream);
+/* nmpc_u_2_att_tgt with one k_throttle per quadrotor (float64 [n] on the device) -- nmpc_node.py:273-283 */
+int ndp_plant_cmd_from_u0_dev(int64_t n, int precision, const void* u0_dev, double mass, const double* k_throttle_dev,
+                              double* cmd_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -26,6 +26,8 @@ EXPORTS = [
     "ndp_plant_create", "ndp_plant_destroy", "ndp_plant_reset", "ndp_plant_forward", "ndp_plant_autopilot", "ndp_plant_dynamics",
     "ndp_plant_nmpc_x0", "ndp_plant_cmd_from_u0", "ndp_plant_launch_count",
     "ndp_refgen_create", "ndp_refgen_destroy", "ndp_refgen_horizon", "ndp_refgen_launch_count",
+    "ndp_predxu_len", "ndp_predxu_pack", "ndp_predxu_unpack", "ndp_hover_throttle_init", "ndp_hover_throttle_update",
+    "ndp_plant_cmd_from_u0_dev",
 ]
 
 
@@ -117,6 +119,15 @@ def load() -> C.CDLL:
     lib.ndp_refgen_horizon.argtypes = [vp, i32, i64, vp, vp, i32, dbl, vp, vp, vp, vp]
     lib.ndp_refgen_launch_count.argtypes = [vp]
     lib.ndp_refgen_launch_count.restype = i64
+    lib.ndp_predxu_len.argtypes = [i32]
+    lib.ndp_predxu_len.restype = i64
+    lib.ndp_predxu_pack.argtypes = [i32, i64, i32, vp, vp, vp, vp]
+    lib.ndp_predxu_unpack.argtypes = [i32, i64, i32, vp, vp, vp, vp, vp]
+    lib.ndp_hover_throttle_init.argtypes = [i64, vp, vp, vp]
+    lib.ndp_hover_throttle_update.argtypes = [i64, dbl, vp, i64, vp, i64, vp, vp, vp]
+    lib.ndp_plant_cmd_from_u0_dev.argtypes = [i64, i32, vp, dbl, vp, vp, vp]
+    for name in ("ndp_predxu_pack", "ndp_predxu_unpack", "ndp_hover_throttle_init", "ndp_hover_throttle_update", "ndp_plant_cmd_from_u0_dev"):
+        getattr(lib, name).restype = C.c_int
     for name in ("ndp_refgen_create", "ndp_refgen_destroy", "ndp_refgen_horizon"):
         getattr(lib, name).restype = C.c_int
     for name in ("ndp_plant_create", "ndp_plant_destroy", "ndp_plant_reset", "ndp_plant_forward", "ndp_plant_autopilot",

@@ -17,6 +17,7 @@ from .params import nmpc_params as CP
 from .solver import Engine
 from .traj_gen.min_snap import Trajectory
 from .traj_gen.refgen import RefGen
+from .wire import BatchedHoverThrottleEstimator
 
 MASS, GRAVITY = 1.4844, 9.81
 # throttle that makes the plant hover: 4 (k_th thr + b_th) = m g (atp_rate.py:92, control_param.py:19-20);
@@ -29,12 +30,16 @@ class ClosedLoop:
     def __init__(self, trajectories: Sequence[Trajectory], traj_id: np.ndarray, t_start: np.ndarray, N: int = CP.N_node,
                  precision: str = "f32", ts_sim: float = 0.01, ts_ctl_plant: float = 0.01, ts_nmpc: float = CP.ts_nmpc,
                  offset: Optional[np.ndarray] = None, has_motor_model: bool = True, has_battery: bool = False,
-                 has_downwash: bool = False, group: int = 1, k_throttle: float = K_THROTTLE, device="cuda:0", **engine_overrides):
+                 has_downwash: bool = False, group: int = 1, k_throttle: Optional[float] = K_THROTTLE, device="cuda:0",
+                 **engine_overrides):
+        """k_throttle: fixed thrust scale of nmpc_u_2_att_tgt, or None to run the reference's HoverThrottleEstimator on the
+        device (one filter per scenario, estimator_params.py:13 initial guess 50): like the node, the filter is updated
+        only while no trajectory is tracked (`hover()`; nmpc_node.py:146,196) and its estimate is frozen during `step()`."""
         self.device = torch.device(device)
         B = len(traj_id)
         self.B, self.N, self.ts_sim, self.ts_nmpc = B, N, ts_sim, ts_nmpc
         self.sim_per_ctl = int(round(ts_nmpc / ts_sim))
-        self.k_throttle = float(k_throttle)
+        self.k_throttle = None if k_throttle is None else float(k_throttle)
         self.dtype = torch.float32 if precision == "f32" else torch.float64
         dev = self.device
         self.refgen = RefGen(trajectories, device=dev)
@@ -49,6 +54,7 @@ class ClosedLoop:
         self.u0 = torch.empty((B, 4), dtype=self.dtype, device=dev)
         self.cmd = torch.zeros((B, 4, 1), dtype=torch.float64, device=dev)
         self.state = torch.zeros((B, 35, 1), dtype=torch.float64, device=dev)
+        self.estimator = BatchedHoverThrottleEstimator(B, ts_nmpc, device=dev) if k_throttle is None else None
         self.reset_to_reference()
 
     def reset_to_reference(self):
@@ -67,10 +73,34 @@ class ClosedLoop:
         self.refgen.horizon(self.t, self.traj_id, self.N, CP.th_pred, self.offset, xr=self.xr, ur=self.ur)
         self.plant.nmpc_x0(self.state, self.x0)
         self.engine.update(self.x0, self.xr, self.ur, None, self.u0)
-        self.plant.cmd_from_u0(self.u0, self.cmd, MASS, self.k_throttle)
+        self._command_and_simulate()
+        self.t.add_(self.ts_nmpc)
+
+    def _command_and_simulate(self):
+        if self.estimator is not None:
+            self.plant.cmd_from_u0_dev(self.u0, self.cmd, MASS, self.estimator.k_throttle)
+        else:
+            self.plant.cmd_from_u0(self.u0, self.cmd, MASS, self.k_throttle)
         for _ in range(self.sim_per_ctl):
             self.plant(self.ts_sim, self.state, self.cmd)
-        self.t.add_(self.ts_nmpc)
+
+    def hover(self, steps: int):
+        """The node before a trajectory arrives (nmpc_node.py:84-101): the reference is the fixed point of
+        gen_fix_pt_ref (pt_publisher.py:40-55: every node = the odometry at start-up, u_ref = (0, 0, 0, m g) -- the
+        reference's own quirk), the controller runs at 50 Hz and the hover-throttle filter is
+        updated every tick from (odometry v_z, last thrust command)."""
+        x_fix = torch.empty((self.B, 10), dtype=self.dtype, device=self.device)
+        self.plant.nmpc_x0(self.state, x_fix)
+        self.xr.copy_(x_fix[:, None, :].expand(-1, self.N + 1, -1))
+        self.ur.zero_()
+        self.ur[:, :, 3] = MASS * GRAVITY
+        self.engine.reset(self.xr, self.ur)
+        for _ in range(steps):
+            if self.estimator is not None:
+                self.estimator.update(self.state[:, 15, 0], self.cmd[:, 3, 0])
+            self.plant.nmpc_x0(self.state, self.x0)
+            self.engine.update(self.x0, self.xr, self.ur, None, self.u0)
+            self._command_and_simulate()
 
     def position_error(self) -> torch.Tensor:
         """|p - p_ref(t)| per scenario, against the reference at the current time."""

@@ -8,6 +8,7 @@
 #include <atomic>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <string>
 
@@ -32,9 +33,42 @@ int cuda_fail(cudaError_t e, const char* where) {
         if (e_ != cudaSuccess) return cuda_fail(e_, #call); \
     } while (0)
 
+// Every handle remembers the CUDA device it was created on; its entry points run there whatever the caller's
+// current device is (and restore the caller's device on return), so a handle built for cuda:1 can be driven from
+// a thread whose current device is cuda:0.
+struct DeviceGuard {
+    int prev = -1, dev = -1;
+    explicit DeviceGuard(int d) : dev(d) {
+        if (d >= 0 && cudaGetDevice(&prev) == cudaSuccess && prev != d) cudaSetDevice(d);
+        else prev = -1;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+// device that owns a caller pointer (entry points without a handle); -1 if unknown
+int device_of(const void* p) {
+    cudaPointerAttributes a;
+    if (p && cudaPointerGetAttributes(&a, p) == cudaSuccess && (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged)) return a.device;
+    cudaGetLastError();
+    return -1;
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per-kernel, per-device state shared by every handle: only ever raise it
+int raise_dyn_smem(const void* kfn, int dev, size_t bytes) {
+    static std::mutex mu;
+    static std::map<std::pair<const void*, int>, size_t> cur;
+    std::lock_guard<std::mutex> lk(mu);
+    size_t& c = cur[{kfn, dev}];
+    if (bytes <= c) return 0;
+    cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return (int)e;
+    c = bytes;
+    return 0;
+}
+
 }  // namespace
 
 struct ndp_handle {
+    int dev;  // CUDA device of the handle
     ndp_config cfg;
     int elt;  // bytes per element
     void *X, *U, *yref, *par, *ws;
@@ -244,6 +278,7 @@ static int set_get(ndp_handle* h, int field, int stage, void* dev, int64_t ld, v
     if (field_geom(h, field, &base, &n_int, &sdim, &dim, &dim_last, &n_stages)) return fail(NDP_E_ARG, "ndp_set/get: unknown field");
     cudaStream_t st = (cudaStream_t)stream;
     const int B = h->cfg.batch;
+    DeviceGuard dg(h->dev);
     std::lock_guard<std::mutex> lk(h->mu);
     if (stage >= 0) {
         if (stage >= n_stages) return fail(NDP_E_ARG, "ndp_set/get: stage out of range");
@@ -302,6 +337,7 @@ int ndp_create(const ndp_config* cfg, ndp_handle** out) {
     CU(cudaGetDevice(&dev));
     CU(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
     ndp_handle* h = new ndp_handle();
+    h->dev = dev;
     h->cfg = *cfg;
     h->elt = cfg->precision == NDP_F64 ? 8 : 4;
     h->launches = 0;
@@ -319,7 +355,7 @@ int ndp_create(const ndp_config* cfg, ndp_handle** out) {
     // latency build first (fp32): taken when the whole batch is resident at its lower occupancy
     for (int lat = (h->elt == 4 && N == 20) ? 1 : 0; lat >= 0; lat--) {
         kfn = rti_kernel_ptr(h->elt, N, lat != 0);
-        e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem);
+        e = (cudaError_t)raise_dyn_smem(kfn, dev, h->smem);
         if (e != cudaSuccess) { delete h; return cuda_fail(e, "cudaFuncSetAttribute(rti_step_kernel)"); }
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, h->ppc * GL, h->smem);
         if (e != cudaSuccess || occ < 1) { delete h; return e != cudaSuccess ? cuda_fail(e, "occupancy") : fail(NDP_E_CONFIG, "kernel does not fit"); }
@@ -360,6 +396,7 @@ int ndp_create(const ndp_config* cfg, ndp_handle** out) {
 
 int ndp_destroy(ndp_handle* h) {
     if (!h) return 0;
+    DeviceGuard dg(h->dev);
     cudaFree(h->X); cudaFree(h->U); cudaFree(h->yref); cudaFree(h->par); cudaFree(h->ws);
     cudaFree(h->status); cudaFree(h->stats); cudaFree(h->as_store);
     for (auto& g : h->hgraph) if (g) cudaGraphExecDestroy(g);
@@ -370,6 +407,7 @@ int ndp_destroy(ndp_handle* h) {
 }
 
 int ndp_set(ndp_handle* h, int field, int stage, const void* dev, int64_t ld, void* stream) {
+    DeviceGuard dg(h ? h->dev : -1);
     if (h && (field == NDP_FIELD_X || field == NDP_FIELD_U))  // the iterate is being overwritten: drop the active-set guess
         cudaMemsetAsync(h->as_store, 0, (size_t)h->cfg.batch * 16 * sizeof(unsigned long long), (cudaStream_t)stream);
     return set_get<true>(h, field, stage, const_cast<void*>(dev), ld, stream);
@@ -380,6 +418,7 @@ int ndp_get(ndp_handle* h, int field, int stage, void* dev, int64_t ld, void* st
 
 int ndp_reset(ndp_handle* h, const void* xr, const void* ur, void* stream) {
     if (!h || !xr || !ur) return fail(NDP_E_ARG, "ndp_reset: null argument");
+    DeviceGuard dg(h->dev);
     std::lock_guard<std::mutex> lk(h->mu);
     const size_t eb = (size_t)h->elt;
     const int N = h->cfg.N, B = h->cfg.batch;
@@ -391,6 +430,7 @@ int ndp_reset(ndp_handle* h, const void* xr, const void* ur, void* stream) {
 
 int ndp_set_reference(ndp_handle* h, const void* xr, const void* ur, const void* f, void* stream) {
     if (!h || !xr || !ur) return fail(NDP_E_ARG, "ndp_set_reference: null argument");
+    DeviceGuard dg(h->dev);
     std::lock_guard<std::mutex> lk(h->mu);
     const int N = h->cfg.N, B = h->cfg.batch;
     const long long tot = (long long)B * (N + 1);
@@ -406,6 +446,7 @@ int ndp_set_reference(ndp_handle* h, const void* xr, const void* ur, const void*
 
 int ndp_solve(ndp_handle* h, const void* x0, void* u0, void* stream) {
     if (!h || !x0) return fail(NDP_E_ARG, "ndp_solve: null argument");
+    DeviceGuard dg(h->dev);
     std::lock_guard<std::mutex> lk(h->mu);
     return h->elt == 4 ? launch_solve<float>(h, x0, u0, (cudaStream_t)stream) : launch_solve<double>(h, x0, u0, (cudaStream_t)stream);
 }
@@ -413,6 +454,7 @@ int ndp_solve(ndp_handle* h, const void* x0, void* u0, void* stream) {
 int ndp_update_ex(ndp_handle* h, const void* x0, const void* xr, const void* ur, const void* f, void* u0, int flags, void* stream) {
     if (!h || !x0 || !xr || !ur) return fail(NDP_E_ARG, "ndp_update: null argument");
     if ((((uintptr_t)xr) | ((uintptr_t)ur)) & 7) return fail(NDP_E_ARG, "ndp_update: xr / ur must be 8-byte aligned");
+    DeviceGuard dg(h->dev);
     std::lock_guard<std::mutex> lk(h->mu);
     const bool pdl = (flags & NDP_UPDATE_F_FROM_PREVIOUS_KERNEL) != 0;
     return h->elt == 4 ? launch_solve<float>(h, x0, u0, (cudaStream_t)stream, xr, ur, f, pdl)
@@ -450,6 +492,7 @@ int ndp_solve_host(ndp_handle* h, const void* x0_host, const void* yref_host, co
                    int32_t* status_host) {
     if (!h || !x0_host || !u0_host || !status_host || (upload_ref && (!yref_host || !p_host)))
         return fail(NDP_E_ARG, "ndp_solve_host: null argument");
+    DeviceGuard dg(h->dev);
     std::lock_guard<std::mutex> lk(h->mu);
     if (!h->hs) CU(cudaStreamCreateWithFlags(&h->hs, cudaStreamNonBlocking));
     if (!h->d_hx0) {   // staging for batches above the zero-copy size (allocated outside any capture)
@@ -485,6 +528,7 @@ int ndp_solve_host(ndp_handle* h, const void* x0_host, const void* yref_host, co
 
 int ndp_status(ndp_handle* h, int32_t* status_dev, void* stream) {
     if (!h || !status_dev) return fail(NDP_E_ARG, "ndp_status: null argument");
+    DeviceGuard dg(h->dev);
     std::lock_guard<std::mutex> lk(h->mu);
     CU(cudaMemcpyAsync(status_dev, h->status, (size_t)h->cfg.batch * sizeof(int32_t), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     return 0;
@@ -492,6 +536,7 @@ int ndp_status(ndp_handle* h, int32_t* status_dev, void* stream) {
 
 int ndp_stats(ndp_handle* h, int32_t* stats_dev, void* stream) {
     if (!h || !stats_dev) return fail(NDP_E_ARG, "ndp_stats: null argument");
+    DeviceGuard dg(h->dev);
     std::lock_guard<std::mutex> lk(h->mu);
     CU(cudaMemcpyAsync(stats_dev, h->stats, (size_t)h->cfg.batch * 4 * sizeof(int32_t), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     return 0;
@@ -503,6 +548,7 @@ int ndp_rk4_sens(int precision, int64_t M, double hh, double mass, double gravit
                  void* AB, void* stream) {
     if (!x || !u || !xn || !AB || M < 0) return fail(NDP_E_ARG, "ndp_rk4_sens: bad argument");
     if (M == 0) return 0;
+    DeviceGuard dg(device_of(x));
     ndp_config g;
     ndp_default_config(&g);
     g.N = 1; g.T = hh; g.mass = mass; g.gravity = gravity;
@@ -522,6 +568,7 @@ int ndp_rk4_sens(int precision, int64_t M, double hh, double mass, double gravit
 
 // ======================= downwash MLP =======================
 struct ndp_mlp {
+    int dev;
     float* params;     // packed fp32 parameters (mlp_kernel.cuh layout)
     void* tc_weights;  // tensor-core operand images (mlp_tc_kernel.cuh)
     ndp::MlpSmall* d_small;  // fp32 side parameters of the tensor-core kernel (device copy)
@@ -580,6 +627,7 @@ int ndp_mlp_create(const float* W1, const float* b1, const float* W2, const floa
     m->params = nullptr; m->tc_weights = nullptr; m->d_small = nullptr;
     int dev = 0;
     cudaGetDevice(&dev);
+    m->dev = dev;
     cudaDeviceGetAttribute(&m->n_sm, cudaDevAttrMultiProcessorCount, dev);
     cudaError_t e = cudaMalloc(&m->params, sizeof(float) * MLP_NPARAM);
     if (e == cudaSuccess) e = cudaMemcpy(m->params, host, sizeof(float) * MLP_NPARAM, cudaMemcpyHostToDevice);
@@ -599,6 +647,7 @@ int ndp_mlp_create(const float* W1, const float* b1, const float* W2, const floa
 
 int ndp_mlp_destroy(ndp_mlp* m) {
     if (!m) return 0;
+    DeviceGuard dg(m->dev);
     cudaFree(m->params); cudaFree(m->tc_weights); cudaFree(m->d_small);
     cudaFree(m->total); cudaFree(m->seg); cudaFree(m->pairs); cudaFree(m->fpair);
     delete m;
@@ -612,6 +661,7 @@ int ndp_debug_mlp_prof(long long* host128) {
 
 int ndp_mlp_forward_rows(ndp_mlp* m, int64_t M, const float* in, float* out, int path, void* stream) {
     if (!m || !in || !out || M < 0) return fail(NDP_E_ARG, "ndp_mlp_forward_rows: bad argument");
+    DeviceGuard dg(m->dev);
     std::lock_guard<std::mutex> lk(m->mu);
     MlpIo io{};
     io.prof = (path >= 100);
@@ -632,6 +682,7 @@ int ndp_mlp_forward_pairs_ex(ndp_mlp* m, int precision, int64_t P, int32_t n_nod
                              const void* gate_xy, double r_horiz, void* out, int accumulate, int path, void* stream) {
     if (!m || !ego || !other || !out || P < 0 || n_nodes < 1 || other_ld < 6) return fail(NDP_E_ARG, "ndp_mlp_forward_pairs: bad argument");
     if (precision != NDP_F32 && precision != NDP_F64) return fail(NDP_E_ARG, "ndp_mlp_forward_pairs: bad precision");
+    DeviceGuard dg(m->dev);
     std::lock_guard<std::mutex> lk(m->mu);
     MlpIo io{};
     io.mode = 1; io.precision = precision; io.n_nodes = n_nodes; io.accumulate = accumulate; io.other_ld = other_ld;
@@ -647,6 +698,7 @@ int ndp_mlp_forward_swarm_parts(ndp_mlp* m, int precision, int32_t n_parts, cons
         return fail(NDP_E_ARG, "ndp_mlp_forward_swarm: bad argument");
     if (precision != NDP_F32 && precision != NDP_F64) return fail(NDP_E_ARG, "ndp_mlp_forward_swarm: bad precision");
     if (n_ego == 0) return 0;
+    DeviceGuard dg(m->dev);
     TrajParts tp{};
     tp.n_parts = n_parts; tp.part_rows = (int)part_rows;
     for (int r = 0; r < n_parts; r++) {
@@ -754,6 +806,7 @@ extern "C" {
 int ndp_pipeline_create(ndp_handle* h, ndp_mlp* mlp, double r_horiz, int depth, ndp_pipeline** out) {
     if (!h || !out || depth < 1 || depth > 64) return fail(NDP_E_ARG, "ndp_pipeline_create: bad argument");
     if (mlp && h->cfg.np != 7) return fail(NDP_E_CONFIG, "ndp_pipeline_create: downwash forces need np = 7");
+    DeviceGuard dg(h->dev);
     ndp_pipeline* p = new ndp_pipeline();
     std::memset(p, 0, sizeof(*p));
     p->h = h; p->mlp = mlp; p->depth = depth; p->r_horiz = r_horiz;
@@ -790,6 +843,7 @@ int ndp_pipeline_create(ndp_handle* h, ndp_mlp* mlp, double r_horiz, int depth, 
 
 int ndp_pipeline_destroy(ndp_pipeline* p) {
     if (!p) return 0;
+    DeviceGuard dg(p->h->dev);
     if (p->s_cmp) cudaStreamSynchronize(p->s_cmp);
     if (p->gexec) cudaGraphExecDestroy(p->gexec);
     if (p->s_out) cudaStreamSynchronize(p->s_out);
@@ -855,6 +909,7 @@ static int pipeline_enqueue_serial(ndp_pipeline* p, cudaStream_t st) {
 int ndp_pipeline_submit(ndp_pipeline* p, int slot) {
     if (!p || slot < 0 || slot >= p->depth) return fail(NDP_E_ARG, "ndp_pipeline_submit: bad slot");
     ndp_handle* h = p->h;
+    DeviceGuard dg(h->dev);
     if (p->depth == 1) {
         // latency path (the reference's one-problem tick): nothing to overlap, so the step is captured once into a
         // CUDA graph and replayed with a single launch; falls back to plain stream order if capture is refused
@@ -908,6 +963,7 @@ int ndp_pipeline_submit(ndp_pipeline* p, int slot) {
 
 int ndp_pipeline_wait(ndp_pipeline* p, int slot) {
     if (!p || slot < 0 || slot >= p->depth) return fail(NDP_E_ARG, "ndp_pipeline_wait: bad slot");
+    DeviceGuard dg(p->h->dev);
     CU(cudaEventSynchronize(p->e_out[slot]));
     return 0;
 }
@@ -928,6 +984,7 @@ void* ndp_pipeline_stream(ndp_pipeline* p) { return p ? (void*)p->s_cmp : nullpt
 #include "plant_kernel.cuh"
 
 struct ndp_plant {
+    int dev;
     ndp::PlantCfg pc;
     ndp::AutopilotCfg ac;
     int has_battery;
@@ -944,6 +1001,8 @@ int ndp_plant_create(int64_t n, double ts_sim, double ts_ctl, int has_downwash, 
     if (!out || n < 1 || ts_sim <= 0 || ts_ctl <= 0) return fail(NDP_E_ARG, "ndp_plant_create: bad argument");
     if (group <= 0 || group > n) group = n;
     ndp_plant* p = new ndp_plant();
+    p->dev = 0;
+    cudaGetDevice(&p->dev);
     p->launches = 0;
     p->has_battery = has_battery;
     p->ts_ctl = ts_ctl; p->ctl_t = 999.0; p->all_sim_t = 0.0;
@@ -985,6 +1044,7 @@ int ndp_plant_create(int64_t n, double ts_sim, double ts_ctl, int has_downwash, 
 
 int ndp_plant_destroy(ndp_plant* p) {
     if (!p) return 0;
+    DeviceGuard dg(p->dev);
     cudaFree(p->pid); cudaFree(p->delta); cudaFree(p->pos);
     delete p;
     return 0;
@@ -992,6 +1052,7 @@ int ndp_plant_destroy(ndp_plant* p) {
 
 int ndp_plant_reset(ndp_plant* p, void* stream) {
     if (!p) return fail(NDP_E_ARG, "ndp_plant_reset: null");
+    DeviceGuard dg(p->dev);
     std::lock_guard<std::mutex> lk(p->mu);
     p->ctl_t = 999.0; p->all_sim_t = 0.0;
     CU(cudaMemsetAsync(p->pid, 0, sizeof(double) * p->pc.n * 9, (cudaStream_t)stream));
@@ -1001,6 +1062,7 @@ int ndp_plant_reset(ndp_plant* p, void* stream) {
 
 int ndp_plant_autopilot(ndp_plant* p, const double* state, const double* cmd, double all_sim_t, void* stream) {
     if (!p || !state || !cmd) return fail(NDP_E_ARG, "ndp_plant_autopilot: null argument");
+    DeviceGuard dg(p->dev);
     ndp::AutopilotCfg a = p->ac;
     a.voltage_cf = p->has_battery ? (4.2 - all_sim_t / 705.0 * (4.2 - 3.6)) / 4.2 : 1.0;  // atp_rate.py:86-90
     const int grd = (int)((a.n + 127) / 128);
@@ -1012,6 +1074,7 @@ int ndp_plant_autopilot(ndp_plant* p, const double* state, const double* cmd, do
 
 int ndp_plant_dynamics(ndp_plant* p, double dt, double* state, void* stream) {
     if (!p || !state) return fail(NDP_E_ARG, "ndp_plant_dynamics: null argument");
+    DeviceGuard dg(p->dev);
     ndp::PlantCfg c = p->pc;
     c.dt = dt;
     cudaStream_t st = (cudaStream_t)stream;
@@ -1028,6 +1091,7 @@ int ndp_plant_dynamics(ndp_plant* p, double dt, double* state, void* stream) {
 
 int ndp_plant_forward(ndp_plant* p, double ts_sim, double* state, const double* cmd, void* stream) {
     if (!p || !state || !cmd) return fail(NDP_E_ARG, "ndp_plant_forward: null argument");
+    DeviceGuard dg(p->dev);
     std::lock_guard<std::mutex> lk(p->mu);
     if (p->ctl_t > p->ts_ctl) {  // mul_quadrotors.py:41-43
         int rc = ndp_plant_autopilot(p, state, cmd, p->all_sim_t, stream);
@@ -1044,6 +1108,7 @@ int ndp_plant_forward(ndp_plant* p, double ts_sim, double* state, const double* 
 int ndp_plant_nmpc_x0(int64_t n, const double* state, int precision, void* x0, void* stream) {
     if (!state || !x0 || n < 0) return fail(NDP_E_ARG, "ndp_plant_nmpc_x0: bad argument");
     if (n == 0) return 0;
+    DeviceGuard dg(device_of(state));
     const int grd = (int)((n + 255) / 256);
     if (precision == NDP_F32) ndp::plant_nmpc_x0_kernel<float><<<grd, 256, 0, (cudaStream_t)stream>>>(n, state, (float*)x0);
     else ndp::plant_nmpc_x0_kernel<double><<<grd, 256, 0, (cudaStream_t)stream>>>(n, state, (double*)x0);
@@ -1054,6 +1119,7 @@ int ndp_plant_nmpc_x0(int64_t n, const double* state, int precision, void* x0, v
 int ndp_plant_cmd_from_u0(int64_t n, int precision, const void* u0, double mass, double k_throttle, double* cmd, void* stream) {
     if (!u0 || !cmd || n < 0) return fail(NDP_E_ARG, "ndp_plant_cmd_from_u0: bad argument");
     if (n == 0) return 0;
+    DeviceGuard dg(device_of(cmd));
     const int grd = (int)((n + 255) / 256);
     if (precision == NDP_F32) ndp::plant_cmd_from_u0_kernel<float><<<grd, 256, 0, (cudaStream_t)stream>>>(n, (const float*)u0, mass, k_throttle, cmd);
     else ndp::plant_cmd_from_u0_kernel<double><<<grd, 256, 0, (cudaStream_t)stream>>>(n, (const double*)u0, mass, k_throttle, cmd);
@@ -1069,6 +1135,7 @@ int64_t ndp_plant_launch_count(const ndp_plant* p) { return p ? (int64_t)p->laun
 #include "refgen_kernel.cuh"
 
 struct ndp_refgen {
+    int dev;
     ndp::RefGenTable tb;
     int* d_seg_off;
     double *d_t_cum, *d_cxyz, *d_cyaw, *d_final;
@@ -1083,6 +1150,8 @@ int ndp_refgen_create(int32_t n_traj, const int32_t* seg_off, const double* t_cu
     const int total = seg_off[n_traj];
     if (total < n_traj) return fail(NDP_E_ARG, "ndp_refgen_create: every trajectory needs at least one segment");
     ndp_refgen* g = new ndp_refgen();
+    g->dev = 0;
+    cudaGetDevice(&g->dev);
     g->launches = 0;
     g->d_seg_off = nullptr; g->d_t_cum = g->d_cxyz = g->d_cyaw = g->d_final = nullptr;
     double* cxyz = new double[(size_t)total * 24];
@@ -1112,6 +1181,7 @@ int ndp_refgen_create(int32_t n_traj, const int32_t* seg_off, const double* t_cu
 
 int ndp_refgen_destroy(ndp_refgen* g) {
     if (!g) return 0;
+    DeviceGuard dg(g->dev);
     cudaFree(g->d_seg_off); cudaFree(g->d_t_cum); cudaFree(g->d_cxyz); cudaFree(g->d_cyaw); cudaFree(g->d_final);
     delete g;
     return 0;
@@ -1123,6 +1193,7 @@ int ndp_refgen_horizon(ndp_refgen* g, int precision, int64_t B, const int32_t* t
     if (precision != NDP_F32 && precision != NDP_F64) return fail(NDP_E_ARG, "ndp_refgen_horizon: bad precision");
     if (B == 0) return 0;  // empty batch: nothing to do (pointers may be null)
     if (!t0 || !xr || !ur) return fail(NDP_E_ARG, "ndp_refgen_horizon: null argument");
+    DeviceGuard dg(g->dev);
     const long long tot = (long long)B * (N + 1);
     const int grd = (int)((tot + 127) / 128);
     if (precision == NDP_F32)
@@ -1135,5 +1206,78 @@ int ndp_refgen_horizon(ndp_refgen* g, int precision, int64_t B, const int32_t* t
 }
 
 int64_t ndp_refgen_launch_count(const ndp_refgen* g) { return g ? (int64_t)g->launches.load() : 0; }
+
+}  // extern "C"
+
+// ======================= wire formats and the hover-throttle hook, batched =======================
+#include "wire_kernel.cuh"
+
+extern "C" {
+
+int64_t ndp_predxu_len(int32_t N) { return N < 1 ? 0 : (int64_t)ndp::predxu_len(N); }
+
+int ndp_predxu_pack(int precision, int64_t B, int32_t N, const void* xr, const void* ur, double* msg, void* stream) {
+    if (B < 0 || N < 1 || (precision != NDP_F32 && precision != NDP_F64)) return fail(NDP_E_ARG, "ndp_predxu_pack: bad argument");
+    if (B == 0) return 0;
+    if (!xr || !ur || !msg) return fail(NDP_E_ARG, "ndp_predxu_pack: null argument");
+    DeviceGuard dg(device_of(msg));
+    const long long tot = B * ndp::predxu_len(N);
+    const int grd = (int)((tot + 255) / 256);
+    if (precision == NDP_F32) ndp::predxu_pack_kernel<float><<<grd, 256, 0, (cudaStream_t)stream>>>(B, N, (const float*)xr, (const float*)ur, msg);
+    else ndp::predxu_pack_kernel<double><<<grd, 256, 0, (cudaStream_t)stream>>>(B, N, (const double*)xr, (const double*)ur, msg);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int ndp_predxu_unpack(int precision, int64_t B, int32_t N, const double* msg, const double* offset, void* xr, void* ur, void* stream) {
+    if (B < 0 || N < 1 || (precision != NDP_F32 && precision != NDP_F64)) return fail(NDP_E_ARG, "ndp_predxu_unpack: bad argument");
+    if (B == 0) return 0;
+    if (!xr || !ur || !msg) return fail(NDP_E_ARG, "ndp_predxu_unpack: null argument");
+    DeviceGuard dg(device_of(msg));
+    const long long tot = B * ndp::predxu_len(N);
+    const int grd = (int)((tot + 255) / 256);
+    if (precision == NDP_F32) ndp::predxu_unpack_kernel<float><<<grd, 256, 0, (cudaStream_t)stream>>>(B, N, msg, offset, (float*)xr, (float*)ur);
+    else ndp::predxu_unpack_kernel<double><<<grd, 256, 0, (cudaStream_t)stream>>>(B, N, msg, offset, (double*)xr, (double*)ur);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int ndp_hover_throttle_init(int64_t n, double* est, double* k_throttle, void* stream) {
+    if (n < 0) return fail(NDP_E_ARG, "ndp_hover_throttle_init: bad argument");
+    if (n == 0) return 0;
+    if (!est) return fail(NDP_E_ARG, "ndp_hover_throttle_init: null argument");
+    DeviceGuard dg(device_of(est));
+    ndp::hover_throttle_init_kernel<<<(int)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n, 50.0 /* estimator_params.py:13 */, est, k_throttle);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int ndp_hover_throttle_update(int64_t n, double ts, const double* vz, int64_t vz_ld, const double* throttle, int64_t throttle_ld, double* est,
+                              double* k_throttle, void* stream) {
+    if (n < 0 || ts <= 0) return fail(NDP_E_ARG, "ndp_hover_throttle_update: bad argument");
+    if (n == 0) return 0;
+    if (!vz || !throttle || !est) return fail(NDP_E_ARG, "ndp_hover_throttle_update: null argument");
+    DeviceGuard dg(device_of(est));
+    ndp::HoverThrottleCfg c;
+    const double tau = 0.05;  // differentiator.py:11
+    c.a1 = (2.0 * tau - ts) / (2.0 * tau + ts);
+    c.a2 = 2.0 / (2.0 * tau + ts);
+    c.mass = 1.4844; c.gravity = 9.81; c.q0 = 0.1; c.q1 = 0.1; c.r = 1.225;  // estimator_params.py:17-18
+    ndp::hover_throttle_update_kernel<<<(int)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n, c, vz, vz_ld < 1 ? 1 : vz_ld, throttle,
+                                                                                                   throttle_ld < 1 ? 1 : throttle_ld, est, k_throttle);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int ndp_plant_cmd_from_u0_dev(int64_t n, int precision, const void* u0, double mass, const double* k_throttle, double* cmd, void* stream) {
+    if (!u0 || !cmd || !k_throttle || n < 0) return fail(NDP_E_ARG, "ndp_plant_cmd_from_u0_dev: bad argument");
+    if (n == 0) return 0;
+    DeviceGuard dg(device_of(cmd));
+    const int grd = (int)((n + 255) / 256);
+    if (precision == NDP_F32) ndp::cmd_from_u0_dev_kernel<float><<<grd, 256, 0, (cudaStream_t)stream>>>(n, (const float*)u0, mass, k_throttle, cmd);
+    else ndp::cmd_from_u0_dev_kernel<double><<<grd, 256, 0, (cudaStream_t)stream>>>(n, (const double*)u0, mass, k_throttle, cmd);
+    CU(cudaGetLastError());
+    return 0;
+}
 
 }  // extern "C"

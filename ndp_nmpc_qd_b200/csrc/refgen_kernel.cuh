@@ -51,10 +51,15 @@ __global__ void refgen_horizon_kernel(const RefGenTable tb, long long B, const i
     if (idx >= B * (N + 1)) return;
     const long long b = idx / (N + 1);
     const int k = (int)(idx - b * (N + 1));
-    const int tj = traj_id ? traj_id[b] : 0;
-    const double t = t0[b] + k * th_pred;
+    // an out-of-range trajectory id is clamped (the host wrapper validates ids it can see; a bad id produced on the
+    // device must not read outside the tables)
+    int tj = traj_id ? traj_id[b] : 0;
+    tj = tj < 0 ? 0 : (tj >= tb.n_traj ? tb.n_traj - 1 : tj);
     const int s0 = tb.seg_off[tj], n_seg = tb.seg_off[tj + 1] - s0;
     const double* tc = tb.t_cum + s0 + tj;
+    // the reference never evaluates before its start time (t = ros_t - start_ros_t >= 0, base_pt_publisher.py:91):
+    // clamp instead of extrapolating segment 0 backwards
+    const double t = fmax(t0[b] + k * th_pred, tc[0]);
     double pos[3], vel[3] = {0, 0, 0}, acc[3] = {0, 0, 0}, jerk[3] = {0, 0, 0}, yaw = 0.0, yaw_dot = 0.0;
     if (t >= tc[n_seg]) {  // finished: hover at the final point (base_pt_publisher.py:93-96)
 #pragma unroll
@@ -75,15 +80,21 @@ __global__ void refgen_horizon_kernel(const RefGenTable tb, long long B, const i
     }
     // differential flatness
     const double tx = acc[0] + 0.0, ty = acc[1] + 0.0, tz = acc[2] + gravity;
-    const double tn = sqrt(tx * tx + ty * ty + tz * tz);
-    const double zb[3] = {tx / tn, ty / tn, tz / tn};
+    // The reference raises ValueError for a free-fall point (|t_des| = 0) and for z_b parallel to x_c
+    // (pt_publisher.py:203-204,214-215).  A kernel cannot raise: those points fall back to the hover attitude
+    // (z_b = e_z) resp. to y_b = e_y x-rotated by yaw, and the thrust direction stays finite instead of NaN.
+    double tn = sqrt(tx * tx + ty * ty + tz * tz);
+    const bool free_fall = !(tn > 1e-9);
+    const double zb[3] = {free_fall ? 0.0 : tx / tn, free_fall ? 0.0 : ty / tn, free_fall ? 1.0 : tz / tn};
+    if (free_fall) tn = 0.0;
     const double u1 = tn * mass;
     const double xc[3] = {cos(yaw), sin(yaw), 0.0};
     double yb[3] = {zb[1] * xc[2] - zb[2] * xc[1], zb[2] * xc[0] - zb[0] * xc[2], zb[0] * xc[1] - zb[1] * xc[0]};
-    const double yn = sqrt(yb[0] * yb[0] + yb[1] * yb[1] + yb[2] * yb[2]);
+    double yn = sqrt(yb[0] * yb[0] + yb[1] * yb[1] + yb[2] * yb[2]);
+    if (!(yn > 1e-9)) { yb[0] = -sin(yaw); yb[1] = cos(yaw); yb[2] = 0.0; yn = 1.0; }
     yb[0] /= yn; yb[1] /= yn; yb[2] /= yn;
     const double xb[3] = {yb[1] * zb[2] - yb[2] * zb[1], yb[2] * zb[0] - yb[0] * zb[2], yb[0] * zb[1] - yb[1] * zb[0]};
-    const double zj = zb[0] * jerk[0] + zb[1] * jerk[1] + zb[2] * jerk[2], mu = mass / u1;
+    const double zj = zb[0] * jerk[0] + zb[1] * jerk[1] + zb[2] * jerk[2], mu = free_fall ? 0.0 : mass / u1;
     const double ho[3] = {mu * (jerk[0] - zj * zb[0]), mu * (jerk[1] - zj * zb[1]), mu * (jerk[2] - zj * zb[2])};
     const double wp = -(ho[0] * yb[0] + ho[1] * yb[1] + ho[2] * yb[2]);
     const double wq = ho[0] * xb[0] + ho[1] * xb[1] + ho[2] * xb[2];

@@ -1056,12 +1056,19 @@ __device__ __noinline__ void constrained_qp(const RtiCfg<T>& c, int lane, unsign
             // (it + (bound - it) need not round back to the bound exactly: compare with a few ulps of slack)
             if (isu && v <= lo + as_eps) fin_lo.set(k);
             else if (isu && v >= hi - as_eps) fin_hi.set(k);
-            if (isx) sX[k * NX + lane] = v;
-            else sU[k * NU + (lane - 10)] = v;
         }
     bad2 = __any_sync(mask, bad2);
     const int nact = (int)grp_sum<float>((float)nact_l, mask);
     if (bad2) status = 1;
+    // A failed QP leaves the iterate as it was (acados SQP_RTI returns without updating it), so the next solve is
+    // not warm-started from a poisoned point; u0 is then the previous first input.
+    if (status == 0 && lane < 14)
+        for (int k = 0; k <= N; k++) {
+            if (k == N && !isx) break;
+            const T v = iter_at(k) + sDz[k * 16 + lane];
+            if (isx) sX[k * NX + lane] = v;
+            else sU[k * NU + (lane - 10)] = v;
+        }
     __syncwarp(mask);
     for (int i = lane; i < (N + 1) * NX; i += GL) gX[i] = sX[i];
     for (int i = lane; i < N * NU; i += GL) gU[i] = sU[i];
@@ -1221,6 +1228,13 @@ __global__ void __launch_bounds__(RTI_CTA, (sizeof(T) == 4) ? (kLat ? 4 : 8) : 3
             if (!ok) status = 4;
             const int nact = (int)grp_sum<float>((float)nact_l, mask);
             if (bad) status = 1;
+            if (status != 0) {
+                // failed factorisation / NaN step: put the previous iterate back (it is still in shared memory) and
+                // return the previous first input -- acados SQP_RTI does not update the iterate when the QP fails
+                for (int i = lane; i < (N + 1) * NX; i += GL) gX[i] = sX[i];
+                for (int i = lane; i < N * NU; i += GL) gU[i] = sU[i];
+                if (a.u0 && lane < NU) a.u0[(size_t)prob * NU + lane] = sU[lane];
+            }
             if (lane == 0) {
                 a.status[prob] = status;
                 a.stats[prob * 4 + 0] = 1;

@@ -45,8 +45,9 @@ def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
-def _sp(stream=None):
-    s = stream if stream is not None else torch.cuda.current_stream()
+def _sp(stream=None, device=None):
+    # the current stream OF THE OBJECT'S DEVICE (not of whatever device is current in the calling thread)
+    s = stream if stream is not None else torch.cuda.current_stream(device)
     return C.c_void_p(s.cuda_stream)
 
 
@@ -109,7 +110,7 @@ class DownwashNN:
         """The nn.Sequential itself: x [M,6] float32 CUDA -> [M,3] float32."""
         assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.shape[-1] == 6
         out = torch.empty((x.shape[0], 3), dtype=torch.float32, device=x.device)
-        _lib.check(self.lib.ndp_mlp_forward_rows(self._h, x.shape[0], _ptr(x), _ptr(out), path, _sp(stream)), "ndp_mlp_forward_rows")
+        _lib.check(self.lib.ndp_mlp_forward_rows(self._h, x.shape[0], _ptr(x), _ptr(out), path, _sp(stream, self.device)), "ndp_mlp_forward_rows")
         return out
 
     def forward_pairs(self, ego: torch.Tensor, other: torch.Tensor, gate_xy: Optional[torch.Tensor] = None,
@@ -127,7 +128,7 @@ class DownwashNN:
         if gate_xy is not None:
             assert gate_xy.dtype == ego.dtype and gate_xy.is_contiguous() and gate_xy.shape == (P, 2)
         _lib.check(self.lib.ndp_mlp_forward_pairs(self._h, prec, P, n, _ptr(ego), _ptr(other), _ptr(gate_xy), float(r_horiz),
-                                                  _ptr(out), int(accumulate), path, _sp(stream)), "ndp_mlp_forward_pairs")
+                                                  _ptr(out), int(accumulate), path, _sp(stream, self.device)), "ndp_mlp_forward_pairs")
         return out
 
     def forward_swarm(self, traj: torch.Tensor, ego_begin: int, n_ego: int, odom_xy: Optional[torch.Tensor] = None,
@@ -141,7 +142,7 @@ class DownwashNN:
         if odom_xy is not None:
             assert odom_xy.dtype == torch.float32 and odom_xy.is_contiguous() and odom_xy.shape == (n_ego, 2)
         _lib.check(self.lib.ndp_mlp_forward_swarm(self._h, prec, n_all, ego_begin, n_ego, n, _ptr(traj), _ptr(odom_xy),
-                                                  float(r_horiz), _ptr(out), path, _sp(stream)), "ndp_mlp_forward_swarm")
+                                                  float(r_horiz), _ptr(out), path, _sp(stream, self.device)), "ndp_mlp_forward_swarm")
         return out
 
     @property

@@ -16,8 +16,9 @@ import torch
 from .. import _lib
 
 
-def _sp(stream=None):
-    s = stream if stream is not None else torch.cuda.current_stream()
+def _sp(stream=None, device=None):
+    # the current stream OF THE OBJECT'S DEVICE (not of whatever device is current in the calling thread)
+    s = stream if stream is not None else torch.cuda.current_stream(device)
     return C.c_void_p(s.cuda_stream)
 
 
@@ -51,20 +52,20 @@ class MulQuadrotors:
     def forward(self, ts_sim: float, ego_states: torch.Tensor, body_rate_cmd: torch.Tensor, stream=None) -> torch.Tensor:
         self._chk(ego_states, body_rate_cmd)
         _lib.check(self.lib.ndp_plant_forward(self._h, float(ts_sim), C.c_void_p(ego_states.data_ptr()),
-                                              C.c_void_p(body_rate_cmd.data_ptr()), _sp(stream)), "ndp_plant_forward")
+                                              C.c_void_p(body_rate_cmd.data_ptr()), _sp(stream, self.device)), "ndp_plant_forward")
         return ego_states
 
     __call__ = forward
 
     def reset(self, stream=None):
-        _lib.check(self.lib.ndp_plant_reset(self._h, _sp(stream)), "ndp_plant_reset")
+        _lib.check(self.lib.ndp_plant_reset(self._h, _sp(stream, self.device)), "ndp_plant_reset")
 
     # ---- glue to the batched NMPC engine (device side, no host round trip) ----
     def nmpc_x0(self, ego_states: torch.Tensor, out: torch.Tensor, stream=None) -> torch.Tensor:
         """odom_2_nmpc_x (pt_publisher.py:106-122): x0 [n,10] = (p, v, qw, qx, qy, qz) in out's dtype."""
         prec = _lib.NDP_F32 if out.dtype == torch.float32 else _lib.NDP_F64
         assert out.is_cuda and out.is_contiguous() and out.numel() == self.num_agent * 10
-        _lib.check(self.lib.ndp_plant_nmpc_x0(self.num_agent, C.c_void_p(ego_states.data_ptr()), prec, C.c_void_p(out.data_ptr()), _sp(stream)),
+        _lib.check(self.lib.ndp_plant_nmpc_x0(self.num_agent, C.c_void_p(ego_states.data_ptr()), prec, C.c_void_p(out.data_ptr()), _sp(stream, self.device)),
                    "ndp_plant_nmpc_x0")
         return out
 
@@ -73,7 +74,16 @@ class MulQuadrotors:
         prec = _lib.NDP_F32 if u0.dtype == torch.float32 else _lib.NDP_F64
         assert u0.is_cuda and u0.is_contiguous() and cmd.is_cuda and cmd.dtype == torch.float64 and cmd.is_contiguous()
         _lib.check(self.lib.ndp_plant_cmd_from_u0(self.num_agent, prec, C.c_void_p(u0.data_ptr()), float(mass), float(k_throttle),
-                                                  C.c_void_p(cmd.data_ptr()), _sp(stream)), "ndp_plant_cmd_from_u0")
+                                                  C.c_void_p(cmd.data_ptr()), _sp(stream, self.device)), "ndp_plant_cmd_from_u0")
+        return cmd
+
+    def cmd_from_u0_dev(self, u0: torch.Tensor, cmd: torch.Tensor, mass: float, k_throttle: torch.Tensor, stream=None) -> torch.Tensor:
+        """nmpc_u_2_att_tgt with one hover-throttle estimate per quadrotor (k_throttle float64 [n] on the device)."""
+        prec = _lib.NDP_F32 if u0.dtype == torch.float32 else _lib.NDP_F64
+        assert u0.is_cuda and u0.is_contiguous() and cmd.is_cuda and cmd.dtype == torch.float64 and cmd.is_contiguous()
+        assert k_throttle.is_cuda and k_throttle.dtype == torch.float64 and k_throttle.is_contiguous() and k_throttle.numel() == self.num_agent
+        _lib.check(self.lib.ndp_plant_cmd_from_u0_dev(self.num_agent, prec, C.c_void_p(u0.data_ptr()), float(mass), C.c_void_p(k_throttle.data_ptr()),
+                                                      C.c_void_p(cmd.data_ptr()), _sp(stream, self.device)), "ndp_plant_cmd_from_u0_dev")
         return cmd
 
     @property

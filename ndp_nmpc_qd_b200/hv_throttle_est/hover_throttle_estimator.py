@@ -38,7 +38,8 @@ class Differentiator:
 
     def update(self, x):
         x_dot = self.a1 * self.x_dot_delay_1 + self.a2 * (x - self.x_delay_1)
-        self.x_delay_1 = x
+        # batched callers may hand in one preallocated buffer that they overwrite every tick: keep a private copy
+        self.x_delay_1 = np.array(x, dtype=np.float64, copy=True) if isinstance(x, np.ndarray) else x
         self.x_dot_delay_1 = x_dot
         return x_dot
 

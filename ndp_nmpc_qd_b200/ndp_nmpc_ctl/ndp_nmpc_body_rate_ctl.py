@@ -5,10 +5,10 @@ f_i] (:97-104), forces enter the velocity dynamics as f / mass (:155-157).
 """
 from __future__ import annotations
 
-from ..nmpc_ctl.nmpc_body_rate_ctl import NMPCBodyRateController
+from ..nmpc_ctl.nmpc_body_rate_ctl import BodyRateControllerBase
 
 
-class NDPNMPCBodyRateController(NMPCBodyRateController):
+class NDPNMPCBodyRateController(BodyRateControllerBase):
     N_PARAMS = 7  # p = [quaternion_r; disturb_f]  (ndp_nmpc_body_rate_ctl.py:197)
 
     def update(self, x0, xr, ur, f):

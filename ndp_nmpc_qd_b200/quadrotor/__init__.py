@@ -1,4 +1,5 @@
-"""Drop-in for ndp_nmpc/scripts/dnwash_nn_est (reference import: nmpc_node.py:31)."""
+"""Drop-in for dop_sim/scripts/quadrotor (reference import: dop_qd_node.py:22 `from quadrotor import MulQuadrotors`):
+the batched CUDA plant of ndp_nmpc_qd_b200.dop_sim under the simulator node's import name."""
 if not __package__ or "." not in __package__:
     # imported by the reference's bare name (PYTHONPATH=<repo>/ndp_nmpc_qd_b200): become the real module
     import os as _os
@@ -11,4 +12,4 @@ if not __package__ or "." not in __package__:
 
     _alias(__name__)
 else:
-    from .downwash_nn import DownwashNN  # noqa: F401
+    from ..dop_sim.mul_quadrotors import MulQuadrotors  # noqa: F401

@@ -25,8 +25,9 @@ def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
-def _stream_ptr(stream: Optional[torch.cuda.Stream]):
-    s = stream if stream is not None else torch.cuda.current_stream()
+def _stream_ptr(stream=None, device=None):
+    # the current stream OF THE OBJECT'S DEVICE (not of whatever device is current in the calling thread)
+    s = stream if stream is not None else torch.cuda.current_stream(device)
     return C.c_void_p(s.cuda_stream)
 
 
@@ -89,13 +90,13 @@ class Engine:
 
     def set_stage(self, stage: int, field: str, value: torch.Tensor, stream=None):
         self._chk(value, (self.batch, self.dim(field, stage)))
-        _lib.check(self.lib.ndp_set(self._h, _lib.FIELDS[field], stage, _ptr(value), value.shape[1], _stream_ptr(stream)), "ndp_set")
+        _lib.check(self.lib.ndp_set(self._h, _lib.FIELDS[field], stage, _ptr(value), value.shape[1], _stream_ptr(stream, self.device)), "ndp_set")
 
     def get_stage(self, stage: int, field: str, out: Optional[torch.Tensor] = None, stream=None) -> torch.Tensor:
         if out is None:
             out = torch.empty((self.batch, self.dim(field, stage)), dtype=self.dtype, device=self.device)
         self._chk(out, (self.batch, self.dim(field, stage)))
-        _lib.check(self.lib.ndp_get(self._h, _lib.FIELDS[field], stage, _ptr(out), out.shape[1], _stream_ptr(stream)), "ndp_get")
+        _lib.check(self.lib.ndp_get(self._h, _lib.FIELDS[field], stage, _ptr(out), out.shape[1], _stream_ptr(stream, self.device)), "ndp_get")
         return out
 
     def _flat_len(self, field: str) -> int:
@@ -106,7 +107,7 @@ class Engine:
         """value: [B, n_stages, dim] ('yref': flat [B, N*14+10])."""
         assert value.is_cuda and value.dtype == self.dtype and value.is_contiguous()
         assert value.numel() == self.batch * self._flat_len(field)
-        _lib.check(self.lib.ndp_set(self._h, _lib.FIELDS[field], -1, _ptr(value), 0, _stream_ptr(stream)), "ndp_set")
+        _lib.check(self.lib.ndp_set(self._h, _lib.FIELDS[field], -1, _ptr(value), 0, _stream_ptr(stream, self.device)), "ndp_set")
 
     def get_all(self, field: str, stream=None) -> torch.Tensor:
         ns, d = self.n_stages(field), self.dim(field, 0)
@@ -114,27 +115,27 @@ class Engine:
             out = torch.empty((self.batch, self._flat_len(field)), dtype=self.dtype, device=self.device)
         else:
             out = torch.empty((self.batch, ns, d), dtype=self.dtype, device=self.device)
-        _lib.check(self.lib.ndp_get(self._h, _lib.FIELDS[field], -1, _ptr(out), 0, _stream_ptr(stream)), "ndp_get")
+        _lib.check(self.lib.ndp_get(self._h, _lib.FIELDS[field], -1, _ptr(out), 0, _stream_ptr(stream, self.device)), "ndp_get")
         return out
 
     def reset(self, xr: torch.Tensor, ur: torch.Tensor, stream=None):
         self._chk(xr, (self.batch, self.N + 1, NX))
         self._chk(ur, (self.batch, self.N, NU))
-        _lib.check(self.lib.ndp_reset(self._h, _ptr(xr), _ptr(ur), _stream_ptr(stream)), "ndp_reset")
+        _lib.check(self.lib.ndp_reset(self._h, _ptr(xr), _ptr(ur), _stream_ptr(stream, self.device)), "ndp_reset")
 
     def set_reference(self, xr: torch.Tensor, ur: torch.Tensor, f: Optional[torch.Tensor] = None, stream=None):
         self._chk(xr, (self.batch, self.N + 1, NX))
         self._chk(ur, (self.batch, self.N, NU))
         if f is not None:
             self._chk(f, (self.batch, self.N + 1, 3))
-        _lib.check(self.lib.ndp_set_reference(self._h, _ptr(xr), _ptr(ur), _ptr(f), _stream_ptr(stream)), "ndp_set_reference")
+        _lib.check(self.lib.ndp_set_reference(self._h, _ptr(xr), _ptr(ur), _ptr(f), _stream_ptr(stream, self.device)), "ndp_set_reference")
 
     def solve(self, x0: torch.Tensor, u0: Optional[torch.Tensor] = None, stream=None) -> torch.Tensor:
         self._chk(x0, (self.batch, NX))
         if u0 is None:
             u0 = torch.empty((self.batch, NU), dtype=self.dtype, device=self.device)
         self._chk(u0, (self.batch, NU))
-        _lib.check(self.lib.ndp_solve(self._h, _ptr(x0), _ptr(u0), _stream_ptr(stream)), "ndp_solve")
+        _lib.check(self.lib.ndp_solve(self._h, _ptr(x0), _ptr(u0), _stream_ptr(stream, self.device)), "ndp_solve")
         return u0
 
     def update(self, x0: torch.Tensor, xr: torch.Tensor, ur: torch.Tensor, f: Optional[torch.Tensor] = None,
@@ -152,19 +153,19 @@ class Engine:
             u0 = torch.empty((self.batch, NU), dtype=self.dtype, device=self.device)
         self._chk(u0, (self.batch, NU))
         _lib.check(self.lib.ndp_update_ex(self._h, _ptr(x0), _ptr(xr), _ptr(ur), _ptr(f), _ptr(u0), 1 if (f_from_prev_kernel and f is not None) else 0,
-                                          _stream_ptr(stream)), "ndp_update")
+                                          _stream_ptr(stream, self.device)), "ndp_update")
         return u0
 
     def status(self, out: Optional[torch.Tensor] = None, stream=None) -> torch.Tensor:
         if out is None:
             out = torch.empty((self.batch,), dtype=torch.int32, device=self.device)
-        _lib.check(self.lib.ndp_status(self._h, _ptr(out), _stream_ptr(stream)), "ndp_status")
+        _lib.check(self.lib.ndp_status(self._h, _ptr(out), _stream_ptr(stream, self.device)), "ndp_status")
         return out
 
     def stats(self, stream=None) -> torch.Tensor:
         """int32 [B, 4]: Riccati factorisations, IPM iterations, active-set rounds, active bounds."""
         out = torch.empty((self.batch, 4), dtype=torch.int32, device=self.device)
-        _lib.check(self.lib.ndp_stats(self._h, _ptr(out), _stream_ptr(stream)), "ndp_stats")
+        _lib.check(self.lib.ndp_stats(self._h, _ptr(out), _stream_ptr(stream, self.device)), "ndp_stats")
         return out
 
     @property

@@ -99,7 +99,7 @@ class SwarmStep:
             _lib.check(self.nn.lib.ndp_mlp_forward_swarm_parts(
                 self.nn._h, _lib.NDP_F32 if self.dtype == torch.float32 else _lib.NDP_F64, len(parts), ptrs, part_rows, self.n_all,
                 self.begin, self.n_local, self.N + 1, None if odom_xy is None else C.c_void_p(odom_xy.data_ptr()), float(DP.r_horiz),
-                C.c_void_p(self.f.data_ptr()), 0, C.c_void_p(torch.cuda.current_stream().cuda_stream)), "ndp_mlp_forward_swarm_parts")
+                C.c_void_p(self.f.data_ptr()), 0, C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)), "ndp_mlp_forward_swarm_parts")
         self._mark("forces")
         return self.f
 

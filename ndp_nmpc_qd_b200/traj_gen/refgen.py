@@ -17,8 +17,9 @@ from ..params import nmpc_params as CP
 from .min_snap import Trajectory
 
 
-def _sp(stream=None):
-    s = stream if stream is not None else torch.cuda.current_stream()
+def _sp(stream=None, device=None):
+    # the current stream OF THE OBJECT'S DEVICE (not of whatever device is current in the calling thread)
+    s = stream if stream is not None else torch.cuda.current_stream(device)
     return C.c_void_p(s.cuda_stream)
 
 
@@ -59,7 +60,7 @@ class RefGen:
         assert xr.dtype == ur.dtype and xr.is_contiguous() and ur.is_contiguous() and xr.numel() == B * (N + 1) * 10 and ur.numel() == B * N * 4
         prec = _lib.NDP_F32 if xr.dtype == torch.float32 else _lib.NDP_F64
         p = lambda t: None if t is None else C.c_void_p(t.data_ptr())
-        _lib.check(self.lib.ndp_refgen_horizon(self._h, prec, B, p(traj_id), p(t0), int(N), float(th_pred), p(offset), p(xr), p(ur), _sp(stream)),
+        _lib.check(self.lib.ndp_refgen_horizon(self._h, prec, B, p(traj_id), p(t0), int(N), float(th_pred), p(offset), p(xr), p(ur), _sp(stream, self.device)),
                    "ndp_refgen_horizon")
         return xr, ur
 

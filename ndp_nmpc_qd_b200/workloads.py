@@ -132,3 +132,29 @@ def independent_problems(B, N=20, seed=0, scale=1.0, name=None, with_neighbour=F
         other[:, :, 3:6] += 0.1 * rng.normal(size=(B, 1, 3))
         out["other"] = other
     return out
+
+
+V_BOX = (4.5, 4.5, 1.4)  # ~79 % of the peak axis speeds of "eight_high_dyn" (5.7, 5.7, 1.7 m/s)
+
+
+def velocity_box_problems(B, N=20, seed=0, v_max=V_BOX, sigma_p=0.05, sigma_v=0.05):
+    """Feasible problems whose solution rides a VELOCITY bound (nmpc_body_rate_ctl.py:59-61,66: lbx/ubx on idx 3,4,5,
+    stages 1..N-1), which the reference's own limits (+-20 m/s) never activate: trajectory phases of "eight_high_dyn"
+    where the start speed is inside 85 % of the tightened box `v_max` on every axis while the reference exceeds 110 % of
+    it later in the horizon, x0 = xr_0 + a small perturbation.  Use with v_min = -v_max, v_max = v_max.
+    Returns dict of float64 arrays x0, xr, ur."""
+    rng = np.random.default_rng(seed)
+    vm = np.asarray(v_max, dtype=np.float64)
+    xs, us = [], []
+    have = 0
+    while have < B:
+        t0 = rng.uniform(0.0, PATHS["eight_high_dyn"][0], size=max(4 * B, 64))
+        xr, ur = reference_horizon(t0, N, 0.1, "eight_high_dyn")
+        sel = np.all(np.abs(xr[:, 0, 3:6]) <= 0.85 * vm, 1) & np.any(np.abs(xr[:, :, 3:6]).max(1) > 1.1 * vm, 1)
+        xs.append(xr[sel]); us.append(ur[sel])
+        have += int(sel.sum())
+    xr, ur = np.concatenate(xs)[:B], np.concatenate(us)[:B]
+    x0 = xr[:, 0, :].copy()
+    x0[:, 0:3] += sigma_p * rng.normal(size=(B, 3))
+    x0[:, 3:6] += sigma_v * rng.normal(size=(B, 3))
+    return dict(x0=x0, xr=xr, ur=ur)

@@ -33,6 +33,7 @@ class OrcCfg(C.Structure):
         ("max_iter", C.c_int),
         ("mu0", C.c_double),
         ("t_floor", C.c_double),
+        ("polish", C.c_int),
     ]
 
 
@@ -45,12 +46,14 @@ def build(force: bool = False) -> str:
     return out
 
 
-def make_cfg(N=20, T=None, tol=1e-13, tol_mu=None, max_iter=100, u_min=None, u_max=None, v_min=None, v_max=None) -> OrcCfg:
+def make_cfg(N=20, T=None, tol=None, tol_mu=None, max_iter=100, u_min=None, u_max=None, v_min=None, v_max=None, polish=None) -> OrcCfg:
     """Constants of params/nmpc_params.py:9-35 and params/fhnp_params.py:9-19.
 
-    tol / max_iter default to a much tighter solve than HPIPM's own (res 1e-8, 50 iterations): the
-    parity target is the exact solution of the QP, which an IPM stopped at mu ~ 1e-10 misses by up
-    to ~3e-7 on weakly active bounds.  Use make_cfg(tol=1e-8, max_iter=50) to time HPIPM-like work.
+    Default (tol=None): interior-point iterations to 1e-9 -- far enough to identify the active set while the
+    barrier-weighted Riccati recursion is still accurate -- followed by exact primal-dual active-set rounds
+    (nmpc_oracle.c: orc_polish), which land on the KKT point of the QP itself (no barrier floor; needed for active
+    velocity bounds, where the plain IPM of this file is only good to ~3e-5).  An explicit tol gives the plain IPM
+    without the polish: make_cfg(tol=1e-8, max_iter=50) is the HPIPM-like amount of work the CPU baseline times.
     th_pred = T/N is 0.1 s in the reference; for N != 20 the horizon is T = 0.1 N
     (th_pred must stay a multiple of ts_nmpc).
     """
@@ -64,8 +67,15 @@ def make_cfg(N=20, T=None, tol=1e-13, tol_mu=None, max_iter=100, u_min=None, u_m
     c.u_max[:] = list(u_max) if u_max is not None else [6, 6, 6, 9.81 / 0.36]
     c.v_min[:] = list(v_min) if v_min is not None else [-20, -20, -20]
     c.v_max[:] = list(v_max) if v_max is not None else [20, 20, 20]
+    # default: IPM to 1e-9 (enough to identify the active set while the barrier-weighted Riccati recursion is still
+    # accurate) + exact active-set polish; an explicit tol gives the plain IPM (HPIPM-like work: tol=1e-8, max_iter=50)
+    if polish is None:
+        polish = 20 if tol is None else 0
+    if tol is None:
+        tol = 1e-9
     c.tol, c.max_iter, c.mu0, c.t_floor = tol, max_iter, 10.0, 0.1
     c.tol_mu = tol if tol_mu is None else tol_mu
+    c.polish = int(polish)
     return c
 
 

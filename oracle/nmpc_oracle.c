@@ -54,6 +54,7 @@ typedef struct {
     int max_iter;     /* acados qp_solver_iter_max default 50 */
     double mu0;       /* IPM cold start */
     double t_floor;   /* slack floor at cold start */
+    int polish;       /* > 0: after the IPM, up to `polish` exact active-set rounds (see orc_polish) */
 } orc_cfg;
 
 /* xdot = f(x,u;fd)   ndp_nmpc_body_rate_ctl.py:151-162 */
@@ -285,6 +286,286 @@ static void riccati_forward(const orc_cfg* c, const orc_ws* w, real (*dx)[NX], r
     }
 }
 
+/* ---------------------------------------------------------------------------------------------
+ * Exact solve for a GIVEN active set (used to polish the interior-point iterate).
+ *
+ * An IPM whose barrier terms enter the Riccati recursion as diagonal weights lambda/t loses
+ * accuracy on problems with active STATE bounds: the weight (~1/mu) on a velocity component at
+ * stage k+1 reappears at stage k inside [A B]'P+[A B], and the Schur complement that eliminates
+ * the inputs then subtracts two numbers of size 1/mu (measured here: u0 off by 3e-5 at mu = 1e-8,
+ * by 1e-1 at mu = 1e-13, against the dense KKT solve of oracle/nmpc_numpy.py).  HPIPM meets the same
+ * effect with iterative refinement and its LQ-factorisation fallback [EXT].  The restatement
+ * removes it at the root: once the IPM has identified the active set, the QP is solved as an
+ * equality-constrained LQ problem with
+ *   - pinned inputs eliminated exactly (u_m = bound), and
+ *   - pinned velocity components of x_{k+1} treated as the stage-k mixed constraint
+ *     E (A dx_k + B du_k + b_k) = beta, resolved in the range/null space of the free inputs
+ *     (needs E B_free of full row rank: collective thrust and the two tilt rates move the velocity),
+ * followed by primal-dual active-set updates (release on a wrong multiplier sign, add on a violated
+ * bound) until the set is a fixed point -- which is the KKT point of the QP, with no barrier floor. */
+typedef struct {
+    signed char au[NMAX][NU];       /* -1 lower, +1 upper, 0 free */
+    signed char av[NMAX + 1][NBX];  /* stages 1..N-1 */
+} orc_aset;
+
+typedef struct {
+    real K[NMAX][NU * NX], kap[NMAX][NU];
+    real Tx[NMAX][NBX * NX], T0[NMAX][NBX]; /* nu_k = -(Tx dx_k + T0), rows = pinned velocity components of stage k+1 */
+    int na[NMAX], ra[NMAX][NBX];             /* number / indices (0..2) of those components */
+    real S[NMAX][NZ * NZ], g[NMAX][NZ];      /* stage quadratic incl. cost-to-go, [x;u] ordering */
+} orc_eqws;
+
+static int chol_n(int n, const real* G, real* L) { /* lower Cholesky n <= 4, row-major stride 4 */
+    memset(L, 0, sizeof(real) * 16);
+    for (int j = 0; j < n; j++) {
+        real s = G[j * 4 + j];
+        for (int k = 0; k < j; k++) s -= L[j * 4 + k] * L[j * 4 + k];
+        if (!(s > 0)) return 1;
+        L[j * 4 + j] = sqrt(s);
+        for (int i = j + 1; i < n; i++) {
+            real a = G[i * 4 + j];
+            for (int k = 0; k < j; k++) a -= L[i * 4 + k] * L[j * 4 + k];
+            L[i * 4 + j] = a / L[j * 4 + j];
+        }
+    }
+    return 0;
+}
+static void chol_n_solve(int n, const real* L, real* v) {
+    for (int i = 0; i < n; i++) {
+        real a = v[i];
+        for (int k = 0; k < i; k++) a -= L[i * 4 + k] * v[k];
+        v[i] = a / L[i * 4 + i];
+    }
+    for (int i = n - 1; i >= 0; i--) {
+        real a = v[i];
+        for (int k = i + 1; k < n; k++) a -= L[k * 4 + i] * v[k];
+        v[i] = a / L[i * 4 + i];
+    }
+}
+
+/* backward + forward sweep of the equality-constrained LQ problem; fills dx, du and the equality-form
+ * multipliers lam_u (pinned inputs) and nu_v[k] (pinned velocity components of stage k+1).  Nonzero: singular. */
+static int orc_eq_solve(const orc_cfg* c, orc_ws* w, orc_eqws* e, const orc_aset* as, real (*dx)[NX], real (*du)[NU],
+                        real (*lam_u)[NU], real (*nu_v)[NBX]) {
+    int N = c->N;
+    memcpy(w->P[N], w->Hxx[N], sizeof(real) * NX * NX);
+    memcpy(w->p[N], w->gx[N], sizeof(real) * NX);
+    for (int k = N - 1; k >= 0; k--) {
+        const real* AB = w->AB[k];
+        const real* Pn = w->P[k + 1];
+        real* S = e->S[k];
+        real* g = e->g[k];
+        real W[NX * NZ], wv[NX];
+        for (int i = 0; i < NX; i++) {
+            real a = w->p[k + 1][i];
+            for (int r = 0; r < NX; r++) a += Pn[i * NX + r] * w->b[k][r];
+            wv[i] = a;
+            for (int j = 0; j < NZ; j++) {
+                real t = 0;
+                for (int r = 0; r < NX; r++) t += Pn[i * NX + r] * AB[r * NZ + j];
+                W[i * NZ + j] = t;
+            }
+        }
+        for (int i = 0; i < NZ; i++) {
+            for (int j = 0; j < NZ; j++) {
+                real a = 0;
+                for (int r = 0; r < NX; r++) a += AB[r * NZ + i] * W[r * NZ + j];
+                if (i < NX && j < NX) a += w->Hxx[k][i * NX + j];
+                if (i >= NX && i == j) a += w->Huu[k][i - NX];
+                S[i * NZ + j] = a;
+            }
+            real a = 0;
+            for (int r = 0; r < NX; r++) a += AB[r * NZ + i] * wv[r];
+            g[i] = a + (i < NX ? w->gx[k][i] : w->gu[k][i - NX]);
+        }
+        /* pinned inputs (value bu) / pinned velocity components of x_{k+1} (value bv) */
+        int pin[NU]; real bu[NU];
+        for (int m = 0; m < NU; m++) {
+            pin[m] = as->au[k][m] != 0;
+            bu[m] = as->au[k][m] > 0 ? w->ubu[k][m] : w->lbu[k][m];
+        }
+        int na = 0; real bv[NBX];
+        if (k + 1 <= N - 1)
+            for (int m = 0; m < NBX; m++)
+                if (as->av[k + 1][m]) { e->ra[k][na] = m; bv[na] = as->av[k + 1][m] > 0 ? w->ubx[k + 1][m] : w->lbx[k + 1][m]; na++; }
+        e->na[k] = na;
+        real G[16], hx[NU * NX], hg[NU];
+        for (int i = 0; i < NU; i++) {
+            for (int j = 0; j < NU; j++) G[i * 4 + j] = (pin[i] || pin[j]) ? (i == j ? 1 : 0) : S[(NX + i) * NZ + NX + j];
+            for (int j = 0; j < NX; j++) hx[i * NX + j] = pin[i] ? 0 : S[(NX + i) * NZ + j];
+            if (pin[i]) hg[i] = -bu[i];
+            else {
+                real a = g[NX + i];
+                for (int m = 0; m < NU; m++) if (pin[m]) a += S[(NX + i) * NZ + NX + m] * bu[m];
+                hg[i] = a;
+            }
+        }
+        real L[16];
+        if (chol_n(4, G, L)) return 1;
+        real Ku[NU * NX], ku[NU];
+        for (int j = 0; j < NX; j++) {
+            real v[4];
+            for (int m = 0; m < 4; m++) v[m] = hx[m * NX + j];
+            chol_n_solve(4, L, v);
+            for (int m = 0; m < 4; m++) Ku[m * NX + j] = -v[m];
+        }
+        { real v[4]; for (int m = 0; m < 4; m++) v[m] = hg[m]; chol_n_solve(4, L, v); for (int m = 0; m < 4; m++) ku[m] = -v[m]; }
+        real* K = e->K[k];
+        real* kap = e->kap[k];
+        memcpy(K, Ku, sizeof(Ku));
+        memcpy(kap, ku, sizeof(ku));
+        if (na) {
+            real D[NBX * NU], Y[NU * NBX], Sn[16], Ln[16];
+            for (int a = 0; a < na; a++)
+                for (int m = 0; m < NU; m++) D[a * NU + m] = pin[m] ? 0 : AB[(3 + e->ra[k][a]) * NZ + NX + m];
+            for (int a = 0; a < na; a++) {
+                real v[4];
+                for (int m = 0; m < 4; m++) v[m] = D[a * NU + m];
+                chol_n_solve(4, L, v);
+                for (int m = 0; m < 4; m++) Y[m * NBX + a] = v[m];
+            }
+            for (int a = 0; a < na; a++)
+                for (int b2 = 0; b2 < na; b2++) {
+                    real t = 0;
+                    for (int m = 0; m < NU; m++) t += D[a * NU + m] * Y[m * NBX + b2];
+                    Sn[a * 4 + b2] = t;
+                }
+            if (chol_n(na, Sn, Ln)) return 2;
+            /* right-hand sides d_x - D Ku (per x column) and d_0 - D ku */
+            for (int j = 0; j <= NX; j++) {
+                real v[4] = {0, 0, 0, 0};
+                for (int a = 0; a < na; a++) {
+                    int r = 3 + e->ra[k][a];
+                    real t;
+                    if (j < NX) {
+                        t = -AB[r * NZ + j];
+                        for (int m = 0; m < NU; m++) t -= D[a * NU + m] * Ku[m * NX + j];
+                    } else {
+                        t = bv[a] - w->b[k][r];
+                        for (int m = 0; m < NU; m++) {
+                            if (pin[m]) t -= AB[r * NZ + NX + m] * bu[m];
+                            t -= D[a * NU + m] * ku[m];
+                        }
+                    }
+                    v[a] = t;
+                }
+                chol_n_solve(na, Ln, v);
+                for (int a = 0; a < na; a++) {
+                    if (j < NX) e->Tx[k][a * NX + j] = v[a]; else e->T0[k][a] = v[a];
+                }
+            }
+            for (int m = 0; m < NU; m++) {
+                for (int j = 0; j < NX; j++) {
+                    real t = 0;
+                    for (int a = 0; a < na; a++) t += Y[m * NBX + a] * e->Tx[k][a * NX + j];
+                    K[m * NX + j] += t;
+                }
+                real t = 0;
+                for (int a = 0; a < na; a++) t += Y[m * NBX + a] * e->T0[k][a];
+                kap[m] += t;
+            }
+        }
+        /* value function under the affine policy du = K dx + kap (the pinned rows of K are 0, of kap the pinned value) */
+        real SuK[NU * NX], gk[NU];
+        for (int m = 0; m < NU; m++) {
+            for (int j = 0; j < NX; j++) {
+                real t = 0;
+                for (int n = 0; n < NU; n++) t += S[(NX + m) * NZ + NX + n] * K[n * NX + j];
+                SuK[m * NX + j] = t;
+            }
+            real t = g[NX + m];
+            for (int n = 0; n < NU; n++) t += S[(NX + m) * NZ + NX + n] * kap[n];
+            gk[m] = t;
+        }
+        for (int i = 0; i < NX; i++) {
+            for (int j = 0; j < NX; j++) {
+                real a = S[i * NZ + j];
+                for (int m = 0; m < NU; m++) a += S[i * NZ + NX + m] * K[m * NX + j] + K[m * NX + i] * S[(NX + m) * NZ + j] + K[m * NX + i] * SuK[m * NX + j];
+                w->P[k][i * NX + j] = a;
+            }
+            real a = g[i];
+            for (int m = 0; m < NU; m++) a += S[i * NZ + NX + m] * kap[m] + K[m * NX + i] * gk[m];
+            w->p[k][i] = a;
+        }
+        for (int i = 0; i < NX; i++)
+            for (int j = 0; j < i; j++) {
+                real a = (real)0.5 * (w->P[k][i * NX + j] + w->P[k][j * NX + i]);
+                w->P[k][i * NX + j] = w->P[k][j * NX + i] = a;
+            }
+    }
+    for (int k = 0; k < N; k++) {
+        for (int m = 0; m < NU; m++) {
+            real a = e->kap[k][m];
+            for (int j = 0; j < NX; j++) a += e->K[k][m * NX + j] * dx[k][j];
+            du[k][m] = a;
+        }
+        for (int i = 0; i < NX; i++) {
+            real a = w->b[k][i];
+            for (int j = 0; j < NX; j++) a += w->AB[k][i * NZ + j] * dx[k][j];
+            for (int m = 0; m < NU; m++) a += w->AB[k][i * NZ + NX + m] * du[k][m];
+            dx[k + 1][i] = a;
+        }
+        real nu[NBX] = {0, 0, 0};
+        for (int a = 0; a < e->na[k]; a++) {
+            real t = e->T0[k][a];
+            for (int j = 0; j < NX; j++) t += e->Tx[k][a * NX + j] * dx[k][j];
+            nu[a] = -t;
+            nu_v[k][e->ra[k][a]] = -t;
+        }
+        for (int m = 0; m < NU; m++) {
+            real t = e->g[k][NX + m];
+            for (int j = 0; j < NX; j++) t += e->S[k][(NX + m) * NZ + j] * dx[k][j];
+            for (int n = 0; n < NU; n++) t += e->S[k][(NX + m) * NZ + NX + n] * du[k][n];
+            for (int a = 0; a < e->na[k]; a++) t += w->AB[k][(3 + e->ra[k][a]) * NZ + NX + m] * nu[a];
+            lam_u[k][m] = -t;
+        }
+    }
+    return 0;
+}
+
+/* Primal-dual active-set rounds from the set `as`.  Returns 1 when a fixed point was reached (dx, du hold the QP
+ * solution), 0 otherwise (dx, du untouched). */
+static int orc_polish(const orc_cfg* c, orc_ws* w, orc_aset* as, real (*dx)[NX], real (*du)[NU], int max_rounds, int* rounds) {
+    int N = c->N;
+    orc_eqws* e = (orc_eqws*)malloc(sizeof(orc_eqws));
+    real (*tx)[NX] = (real(*)[NX])malloc(sizeof(real) * (N + 1) * NX);
+    real (*tu)[NU] = (real(*)[NU])malloc(sizeof(real) * N * NU * 2);
+    real (*lam)[NU] = tu + N;
+    real (*nu)[NBX] = (real(*)[NBX])malloc(sizeof(real) * N * NBX);
+    memcpy(tx[0], dx[0], sizeof(real) * NX);
+    const real eps = (sizeof(real) == 8) ? (real)1e-11 : (real)1e-5;
+    int fixed = 0, r = 0;
+    for (r = 0; r < max_rounds; r++) {
+        memset(nu, 0, sizeof(real) * N * NBX);
+        if (orc_eq_solve(c, w, e, as, tx, tu, lam, nu)) break;
+        int changed = 0;
+        for (int k = 0; k < N; k++) {
+            for (int m = 0; m < NU; m++) {
+                if (as->au[k][m]) {
+                    /* equality-form multiplier: upper bound needs lam >= 0, lower bound lam <= 0 */
+                    if ((as->au[k][m] > 0 ? lam[k][m] : -lam[k][m]) < 0) { as->au[k][m] = 0; changed = 1; }
+                } else if (tu[k][m] > w->ubu[k][m] + eps) { as->au[k][m] = 1; changed = 1; }
+                else if (tu[k][m] < w->lbu[k][m] - eps) { as->au[k][m] = -1; changed = 1; }
+            }
+            if (k + 1 <= N - 1)
+                for (int m = 0; m < NBX; m++) {
+                    if (as->av[k + 1][m]) {
+                        if ((as->av[k + 1][m] > 0 ? nu[k][m] : -nu[k][m]) < 0) { as->av[k + 1][m] = 0; changed = 1; }
+                    } else if (tx[k + 1][3 + m] > w->ubx[k + 1][m] + eps) { as->av[k + 1][m] = 1; changed = 1; }
+                    else if (tx[k + 1][3 + m] < w->lbx[k + 1][m] - eps) { as->av[k + 1][m] = -1; changed = 1; }
+                }
+        }
+        if (!changed) { fixed = 1; r++; break; }
+    }
+    if (fixed) {
+        memcpy(dx, tx, sizeof(real) * (N + 1) * NX);
+        memcpy(du, tu, sizeof(real) * N * NU);
+    }
+    if (rounds) *rounds = r;
+    free(e); free(tx); free(tu); free(nu);
+    return fixed;
+}
+
 typedef struct {
     int status;    /* acados codes: 0 ok, 1 NaN, 4 QP failure */
     int n_iter;    /* IPM iterations */
@@ -458,6 +739,26 @@ int orc_rti_step(const orc_cfg* c, const real* x0, const real* xr, const real* u
 done:;
     int nact = 0;
     for (int i = 0; i < nb; i++) { nact += (tl[i] < ll[i]); nact += (tu[i] < lu[i]); }
+    if (c->polish > 0 && nact > 0 && status != 1) {
+        /* exact solve on the IPM's active set (t < lambda marks a bound as active), see orc_polish */
+        orc_aset as;
+        memset(&as, 0, sizeof(as));
+        for (int i = 0; i < nb; i++) {
+            int k = bs[3 * i], isx = bs[3 * i + 1], m = bs[3 * i + 2];
+            signed char a = (tl[i] < ll[i]) ? -1 : ((tu[i] < lu[i]) ? 1 : 0);
+            if (isx) as.av[k][m] = a; else as.au[k][m] = a;
+        }
+        int rounds = 0;
+        if (orc_polish(c, w, &as, dx, du, c->polish, &rounds)) {
+            status = 0;
+            nact = 0;
+            for (int k = 0; k < N; k++) {
+                for (int m = 0; m < NU; m++) nact += as.au[k][m] != 0;
+                if (k >= 1) for (int m = 0; m < NBX; m++) nact += as.av[k][m] != 0;
+            }
+        }
+        if (getenv("ORC_TRACE")) fprintf(stderr, "polish: rounds %d status %d nact %d\n", rounds, status, nact);
+    }
     /* ---- update: full step ---- */
     int nan = 0;
     for (int k = 0; k <= N; k++)
