@@ -149,9 +149,34 @@ def cpu_oracle_rate(sets, seconds=12.0, threads=0):
                 n_iter_mean=float(np.mean(its))), n_tot, t_tot
 
 
+def acados_probe():
+    """look for a real acados before falling back to the oracle port -- `import acados_template`,
+    $ACADOS_SOURCE_DIR, baseline/_ref/.  Reports what it found; this image has none of them."""
+    found = {}
+    try:
+        import acados_template  # noqa: F401
+
+        found["acados_template"] = getattr(acados_template, "__file__", "importable")
+    except Exception as e:
+        found["acados_template"] = f"not importable ({type(e).__name__})"
+    try:
+        import casadi  # noqa: F401
+
+        found["casadi"] = "importable"
+    except Exception as e:
+        found["casadi"] = f"not importable ({type(e).__name__})"
+    src = os.environ.get("ACADOS_SOURCE_DIR")
+    found["ACADOS_SOURCE_DIR"] = src if src and os.path.isdir(src) else ("unset" if not src else f"{src} (missing)")
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    found["baseline/_ref"] = sorted(os.listdir(ref))[:8] if os.path.isdir(ref) else "absent"
+    found["usable"] = bool(found["acados_template"].startswith("/") and found["casadi"] == "importable" and src and os.path.isdir(src))
+    return found
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
+    probe = acados_probe()
     sets = make_workload(args.batch, 0, 1)
     times = []
     info = None
@@ -168,7 +193,8 @@ def run_reference(args, rank, world):
                data="synthetic", impl="reference",
                config=dict(workload=f"config 3: {args.batch} independent single-quad NDP-NMPC problems per GPU, N=20, one gated neighbour each (downwash MLP on)",
                            note="acados/HPIPM/CasADi are not installable here (un-vendored, no network); this arm is the fp64 CPU oracle port on all host threads; each step is a bounded sample"),
-               cpu_baseline=info, e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+               cpu_baseline=info, e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0,
+               acados_probe=probe)
     print(json.dumps(out), flush=True)
 
 
@@ -189,8 +215,9 @@ def run_native(args, rank, local_rank, world):
     B, K, W = args.batch, args.steps, args.warmup
     n_sets = 8
     sets = make_workload(B, seed=1000 * rank, n_sets=n_sets)
-    dt = torch.float32
-    eng = Engine(batch=B, N=N_HORIZON, np_=7, precision="f32", device=dev)
+    f64 = args.dtype == "f64"
+    dt = torch.float64 if f64 else torch.float32
+    eng = Engine(batch=B, N=N_HORIZON, np_=7, precision=args.dtype, device=dev)
     nn = DownwashNN(device=dev)
     t = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=dt, device=dev)
     d_sets = [dict(x0=t(w["x0"]), xr=t(w["xr"]), ur=t(w["ur"]), other=t(w["other"]), gate=t(w["xr"][:, 0, 0:2])) for w in sets]
@@ -242,6 +269,10 @@ def run_native(args, rank, local_rank, world):
     total_ms = float(step_ms.sum())
     stats = eng.stats().cpu().numpy()
     status = eng.status().cpu().numpy()
+    if args.kernels_only:
+        if rank == 0:
+            print(json.dumps(dict(kernels_only=True, ms_per_step=total_ms / K, rti_ms=float(solve_ms.mean()), mlp_ms=float(mlp_ms.mean()))), flush=True)
+        return
     # ---------- end-to-end timing through the host-buffer C ABI (e2e) ----------
     # ndp_pipeline_*: every step copies that step's record (x0, xr, ur, neighbour horizon, gate) from pinned
     # host memory, runs the MLP + RTI kernels and copies (u0, status) back; consecutive steps overlap
@@ -299,19 +330,24 @@ def run_native(args, rank, local_rank, world):
     peaks = measured_peaks()
     n_fact = float(stats[:, 0].mean())
     flop = algorithmic_flop_per_solve(N_HORIZON, n_fact)
-    fp32_peak = 148 * 128 * 2 * peaks["sm_max_mhz"] * 1e6 / 1e12  # TFLOP/s, CUDA-core FMA pipe
+    elt = 8 if f64 else 4
+    lanes = 64 if f64 else 128  # FMA lanes per SM of the pipe the kernel computes in (FP64: 64 per SM, spec, unmeasured)
+    fp32_peak = 148 * lanes * 2 * peaks["sm_max_mhz"] * 1e6 / 1e12  # TFLOP/s, CUDA-core FMA pipe
     solve_s = float(solve_ms.mean()) * 1e-3
     ach_tf = flop * B / solve_s / 1e12
     traffic = None
-    prof = os.path.join(ROOT, "profiles", "ncu_rti_summary.json")
+    prof = os.path.join(ROOT, "profiles", "ncu_rti_summary_f64.json" if f64 else "ncu_rti_summary.json")
+    traffic_src = None
     if os.path.exists(prof):
         try:
-            traffic = json.load(open(prof)).get("dram_bytes_per_launch")
+            pj = json.load(open(prof))
+            traffic = pj.get("dram_bytes_per_launch")
+            traffic_src = f"{os.path.relpath(prof, ROOT)} written by `bench.py --profile` on {pj.get('when', pj.get('source', '?'))}"
         except Exception:
             traffic = None
     out = dict(
         metric=METRIC, value=world * B * K / (total_ms * 1e-3), unit=UNIT, n_gpus=world, steps=K, warmup=W,
-        ms_per_step=total_ms / K, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+        ms_per_step=total_ms / K, higher_is_better=True, scaling="weak", vs_baseline=None, dtype=args.dtype, data="synthetic",
         config=dict(workload=f"config 3: {B} independent single-quad NDP-NMPC problems per GPU, N=20, one gated neighbour each (downwash MLP on)",
                     batch_per_gpu=B, horizon=N_HORIZON, l2="flushed between timed iterations (256 MiB memset outside the event pair)",
                     inputs="8 pre-generated control steps cycled; iterate warm-started, no shift",
@@ -322,11 +358,13 @@ def run_native(args, rank, local_rank, world):
                  api="ndp_pipeline_submit/wait (include/ndp_nmpc.h): pinned host record -> H2D -> MLP + RTI kernels -> D2H (u0, status)",
                  mode=f"{depth} steps in flight (upload of step i+1 overlaps the kernels of step i); p50_step_ms is the one-step-at-a-time latency"),
         gpu_launches=int(launches),
-        roofline=dict(bound="fp32", kernel="rti_step_kernel<float>", achieved=ach_tf, peak=fp32_peak, unit="TFLOP/s", frac=ach_tf / fp32_peak,
-                      traffic=traffic, flop_per_solve=flop, n_fact_mean=n_fact, kernel_ms=float(solve_ms.mean()),
-                      peak_source=f"148 SM x 128 FMA x 2 x {peaks['sm_max_mhz']:.0f} MHz ({peaks['source']} sm_max_mhz)",
-                      hbm=dict(achieved=compulsory_bytes_per_solve(N_HORIZON) * B / solve_s / 1e9, peak=peaks["hbm_gbs"], unit="GB/s",
-                               frac=compulsory_bytes_per_solve(N_HORIZON) * B / solve_s / 1e9 / peaks["hbm_gbs"], bytes_per_solve=compulsory_bytes_per_solve(N_HORIZON))),
+        roofline=dict(bound="fp64" if f64 else "fp32", kernel="rti_step_kernel<double>" if f64 else "rti_step_kernel<float>", achieved=ach_tf, peak=fp32_peak,
+                      unit="TFLOP/s", frac=ach_tf / fp32_peak,
+                      traffic=traffic, traffic_source=traffic_src, flop_per_solve=flop, n_fact_mean=n_fact, kernel_ms=float(solve_ms.mean()),
+                      peak_source=f"148 SM x {lanes} FMA x 2 x {peaks['sm_max_mhz']:.0f} MHz ({peaks['source']} sm_max_mhz)",
+                      hbm=dict(achieved=compulsory_bytes_per_solve(N_HORIZON, elt) * B / solve_s / 1e9, peak=peaks["hbm_gbs"], unit="GB/s",
+                               frac=compulsory_bytes_per_solve(N_HORIZON, elt) * B / solve_s / 1e9 / peaks["hbm_gbs"],
+                               bytes_per_solve=compulsory_bytes_per_solve(N_HORIZON, elt))),
         mlp=dict(kernel_ms=float(mlp_ms.mean()), rows=B * (N_HORIZON + 1), note="fused feature + gate + MLP kernel (events 0-1 of the per-kernel pass)"),
         step_breakdown=dict(serialised_step_ms=float(serial_step_ms.mean()),
                             note="value times the step with the solve launched as a programmatic dependent of the MLP kernel; "
@@ -334,9 +372,11 @@ def run_native(args, rank, local_rank, world):
         p50_step_ms=float(np.median(step_ms)), p99_step_ms=float(np.quantile(step_ms, 0.99)),
         solver=dict(status_nonzero=int((status != 0).sum()), ipm_iters_mean=float(stats[:, 1].mean()), active_bounds_mean=float(stats[:, 3].mean())),
     )
+    # parity of the benched problems against the CPU oracle (a parity figure with every number)
+    out["parity"] = parity_check(eng, nn, sets, dev, dt, f_buf, u0_buf)
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_oracle_rate(sets, seconds=12.0)[0]
-    if world == 1 and not args.no_latency:
+    if world == 1 and not args.no_latency and not f64:
         out["latency_b1"] = batch1_latency(dev)
         out["stress"] = stress_variant(dev, B)
         # fp32 build's first step on the same problems, for the fp32-vs-fp64 distance
@@ -348,6 +388,44 @@ def run_native(args, rank, local_rank, world):
     print(json.dumps(out), flush=True)
     if dist is not None:
         dist.destroy_process_group()
+
+
+def parity_check(eng, nn, sets, dev, dt, f_buf, u0_buf, steps=3):
+    """The benched batch, `steps` warm-started control steps from the iterate reset to the reference: downwash MLP +
+    SQP-RTI step on the GPU against the CPU oracle chain (numpy MLP -> fp64 C SQP-RTI oracle solved to the exact QP
+    solution).  Per-component errors |a - b| / max(|b|, 1); the north-star gate is 1e-4 (fp32 build)."""
+    import torch
+
+    from oracle import mlp_numpy
+    from oracle.c_oracle import COracle, make_cfg
+    from ndp_nmpc_qd_b200.dnwash_nn_est.downwash_nn import DEFAULT_WEIGHTS
+
+    co, cfg, wts = COracle(), make_cfg(), mlp_numpy.load_npz(DEFAULT_WEIGHTS)
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=dt, device=dev)
+    rel = lambda a, b: float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1.0)))
+    w0 = sets[0]
+    xr, ur = t(w0["xr"]), t(w0["ur"])
+    eng.reset(xr, ur)
+    X, U = w0["xr"].copy(), w0["ur"].copy()
+    worst = dict(u0_rel_max=0.0, X_rel_max=0.0, U_rel_max=0.0, mlp_abs_max=0.0)
+    n_ok = 0
+    for s in range(steps):
+        w = sets[s % len(sets)]
+        nn.forward_pairs(t(w["xr"]), t(w["other"]), t(w["xr"][:, 0, 0:2]), out=f_buf)
+        eng.update(t(w["x0"]), t(w["xr"]), t(w["ur"]), f_buf, u0_buf)
+        torch.cuda.synchronize()
+        f_ref = mlp_numpy.gated_pairs(wts, w["xr"], w["other"], w["xr"][:, 0, 0:2], 1.0, np.float32).astype(np.float64)
+        r = co.rti_batch(cfg, w["x0"], w["xr"], w["ur"], f_ref, X, U)
+        ok = r["status"] == 0
+        n_ok += int(ok.sum())
+        gX, gU = eng.get_all("x").cpu().numpy().astype(np.float64), eng.get_all("u").cpu().numpy().astype(np.float64)
+        worst["u0_rel_max"] = max(worst["u0_rel_max"], rel(u0_buf.cpu().numpy().astype(np.float64)[ok], r["u0"][ok]))
+        worst["X_rel_max"] = max(worst["X_rel_max"], rel(gX[ok], X[ok]))
+        worst["U_rel_max"] = max(worst["U_rel_max"], rel(gU[ok], U[ok]))
+        worst["mlp_abs_max"] = max(worst["mlp_abs_max"], float(np.abs(f_buf.cpu().numpy().astype(np.float64) - f_ref).max()))
+    worst.update(problems=int(w0["x0"].shape[0]), steps=steps, compared=n_ok, gate=1e-4 if dt == torch.float32 else 1e-9,
+                 oracle="numpy MLP + fp64 C SQP-RTI oracle (IPM + exact active-set polish), per-component |a-b|/max(|b|,1)")
+    return worst
 
 
 def stress_variant(dev, B, steps=20):
@@ -470,6 +548,56 @@ def batch1_latency(dev):
                      "ndp_pipeline_submit/wait call at batch 1 (same inputs, same closed sequence)")
 
 
+def run_profile(args):
+    """`bench.py --profile`: regenerate the measured DRAM traffic of the dominant kernel (roofline.traffic) instead of
+    trusting a committed number -- one ncu pass (dram__bytes_read/write, gpu__time_duration; --clock-control none) over a
+    short kernels-only run of this same benchmark; the summary goes to profiles/ncu_rti_summary.json, which the normal
+    run reads.  Numbers printed by the profiled child are never bench values."""
+    import csv
+    import datetime
+    import tempfile
+
+    tmp = tempfile.NamedTemporaryFile(suffix=".csv", delete=False).name
+    child = [sys.executable, os.path.abspath(__file__), "--steps", "6", "--warmup", "3", "--batch", str(args.batch), "--dtype", args.dtype,
+             "--kernels-only"]
+    cmd = ["ncu", "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum", "--clock-control", "none",
+           "-k", "regex:rti_step_kernel|mlp_tc_kernel", "-c", "80", "--csv", "--log-file", tmp] + child
+    rc = subprocess.call(cmd, stdout=subprocess.DEVNULL)
+    rows, header = [], None
+    for row in csv.reader(open(tmp, errors="replace")):
+        if header is None:
+            if row and row[0] == "ID":
+                header = row
+            continue
+        if len(row) == len(header):
+            rows.append(dict(zip(header, row)))
+    per = {}
+    for r in rows:
+        k = "rti" if "rti_step_kernel" in r["Kernel Name"] else "mlp"
+        v = float(r["Metric Value"].replace(",", ""))
+        unit = r.get("Metric Unit", "")
+        if "byte" in unit.lower():
+            v *= {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
+        if r["Metric Name"] == "gpu__time_duration.sum":
+            v *= {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(unit, 1e-3)
+        per.setdefault(k, {}).setdefault(r["ID"], {})[r["Metric Name"]] = v
+    out = dict(command=" ".join(cmd), when=datetime.datetime.utcnow().isoformat() + "Z", ncu_exit_code=rc, batch=args.batch, dtype=args.dtype)
+    for k, launches in per.items():
+        ls = list(launches.values())[len(launches) // 2:]  # second half: past the warm-up steps
+        if not ls:
+            continue
+        tr = [l.get("dram__bytes_read.sum", 0.0) + l.get("dram__bytes_write.sum", 0.0) for l in ls]
+        out[k] = dict(launches=len(ls), dram_bytes_per_launch=float(np.mean(tr)), dram_read=float(np.mean([l.get("dram__bytes_read.sum", 0.0) for l in ls])),
+                      dram_write=float(np.mean([l.get("dram__bytes_write.sum", 0.0) for l in ls])),
+                      kernel_us_under_ncu=float(np.mean([l.get("gpu__time_duration.sum", 0.0) for l in ls])))
+    if "rti" in out:
+        out["dram_bytes_per_launch"] = out["rti"]["dram_bytes_per_launch"]
+        out["algorithmic_bytes_per_launch"] = compulsory_bytes_per_solve(N_HORIZON, 8 if args.dtype == "f64" else 4) * args.batch
+    dst = os.path.join(ROOT, "profiles", "ncu_rti_summary.json" if args.dtype == "f32" else "ncu_rti_summary_f64.json")
+    json.dump(out, open(dst, "w"), indent=1)
+    print(json.dumps(dict(profile=dst, **{k: out[k] for k in ("rti", "mlp") if k in out})), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -477,6 +605,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--batch", type=int, default=4096, help="problems per GPU")
+    ap.add_argument("--dtype", default="f32", choices=["f32", "f64"], help="engine precision (f64: the like-for-like build against the fp64 reference path)")
+    ap.add_argument("--profile", action="store_true", help="re-measure roofline.traffic with ncu (writes profiles/ncu_rti_summary.json)")
+    ap.add_argument("--kernels-only", action="store_true", help="device-resident timing only (what --profile runs under ncu)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-latency", action="store_true")
     args = ap.parse_args()
@@ -486,6 +617,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if args.profile:
+        run_profile(args)
         return
     if world == 1 and args.gpus > 1:
         # launched without torchrun: re-exec under it

@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_C", "libndp_nmpc_b200.so")
+# NDP_NMPC_LIB: an alternative build of the same library (A/B measurements of kernel variants, tools/ab_variants.py)
+LIB_PATH = os.environ.get("NDP_NMPC_LIB") or os.path.join(_HERE, "_C", "libndp_nmpc_b200.so")
 
 NDP_F32, NDP_F64 = 0, 1
 FIELD_X, FIELD_U, FIELD_YREF, FIELD_P = 0, 1, 2, 3

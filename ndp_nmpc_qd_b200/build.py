@@ -53,10 +53,12 @@ def build(force: bool = False, verbose: bool = False, defines=(), out: str = OUT
     os.makedirs(obj_dir, exist_ok=True)
     common = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
               "--expt-relaxed-constexpr", "-Xptxas", "-v" if verbose else "-O3", "-ccbin", "/usr/bin/g++"] + [f"-D{d}" for d in defines]
+    rdc = []
     jobs = [(os.path.join(obj_dir, "ndp_capi.o"), [SRC])]
     for tag, typ, n, lat in RTI_INSTANCES:
         jobs.append((os.path.join(obj_dir, f"rti_{tag}.o"),
-                     [RTI_INST, f"-DNDP_INST_T={typ}", f"-DNDP_INST_N={n}", f"-DNDP_INST_LAT={lat}", f"-DNDP_INST_TAG={tag}"]))
+                     [RTI_INST, f"-DNDP_INST_T={typ}", f"-DNDP_INST_N={n}", f"-DNDP_INST_LAT={lat}", f"-DNDP_INST_TAG={tag}",
+                      f"-DNDP_INST_LAT_IS_TRUE={1 if lat == 'true' else 0}"] + rdc))
 
     def compile_one(job):
         obj, args = job
@@ -70,7 +72,10 @@ def build(force: bool = False, verbose: bool = False, defines=(), out: str = OUT
             raise RuntimeError("nvcc failed building libndp_nmpc_b200.so")
         if verbose:
             sys.stderr.write(res.stderr)
-    res = subprocess.run([_nvcc(), "-shared", "-ccbin", "/usr/bin/g++", "-o", out] + [j[0] for j in jobs] + ["-lcuda"], capture_output=True, text=True)
+    link = [_nvcc(), "-shared", "-ccbin", "/usr/bin/g++", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out] + [j[0] for j in jobs] + ["-lcuda"]
+    if rdc:
+        link += ["-lcudadevrt"]
+    res = subprocess.run(link, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
         raise RuntimeError("nvcc failed linking libndp_nmpc_b200.so")

@@ -73,9 +73,14 @@ struct ndp_handle {
     int elt;  // bytes per element
     void *X, *U, *yref, *par, *ws;
     int32_t *status, *stats;
-    unsigned long long* as_store;  // [B][4][4] active set of the previous solve
-    long long ws_stride;
+    unsigned long long* as_store;  // [B][AS_OWNERS][4] active set a problem's constrained solve starts from
+    long long ws_stride;           // nominal kernel: forward-sweep records only
     int slots, grid, ppc, lat;
+    void* ws_c;                    // constrained kernel: [slots_c][ws_c_stride]
+    long long ws_c_stride;
+    int slots_c, grid_c;
+    int* queue;                    // [B] problems handed from the nominal to the constrained kernel
+    int* qctl;                     // {count, head, done, pad}
     size_t smem;
     // ndp_solve_host: private stream, the two captured step graphs (with / without reference upload) and the
     // host pointers they were captured for
@@ -180,7 +185,7 @@ RtiCfg<T> make_cfg(const ndp_config& g) {
     for (int i = 0; i < 4; i++) { c.R[i] = (T)g.R[i]; c.hR[i] = (T)(g.R[i] * g.T / g.N); c.umin[i] = (T)g.u_min[i]; c.umax[i] = (T)g.u_max[i]; }
     for (int i = 0; i < 3; i++) { c.vmin[i] = (T)g.v_min[i]; c.vmax[i] = (T)g.v_max[i]; }
     const bool f32 = sizeof(T) == 4;
-    c.tol_mu = (T)(g.ipm_tol_mu > 0 ? g.ipm_tol_mu : (f32 ? 1e-4 : 1e-9));
+    c.tol_mu = (T)(g.ipm_tol_mu > 0 ? g.ipm_tol_mu : (f32 ? 1e-4 : 1e-11));
     c.tol_res = (T)(f32 ? 1e-6 : 1e-11);  // contraction of the linear residuals (prod of 1 - alpha)
     c.t_min = (T)1e-12;
     c.mu0 = (T)10.0;
@@ -192,7 +197,9 @@ RtiCfg<T> make_cfg(const ndp_config& g) {
 // ---- the RTI kernel instantiations live in their own translation units (rti_inst.cu) ----
 #define NDP_RTI_DECL(tag, T)                                                                                   \
     void rti_launch_##tag(int, int, size_t, cudaStream_t, const RtiCfg<T>&, const RtiArgs<T>&, bool);          \
-    const void* rti_kernel_##tag();
+    const void* rti_kernel_##tag();                                                                            \
+    void rti_claunch_##tag(int, int, size_t, cudaStream_t, const RtiCfg<T>&, const RtiArgs<T>&);               \
+    const void* rti_ckernel_##tag();
 NDP_RTI_DECL(f32_20_0, float) NDP_RTI_DECL(f32_40_0, float) NDP_RTI_DECL(f32_80_0, float) NDP_RTI_DECL(f32_0_0, float)
 NDP_RTI_DECL(f32_20_1, float)
 NDP_RTI_DECL(f64_20_0, double) NDP_RTI_DECL(f64_40_0, double) NDP_RTI_DECL(f64_80_0, double) NDP_RTI_DECL(f64_0_0, double)
@@ -202,24 +209,26 @@ template <typename T>
 struct RtiInst {
     void (*launch)(int, int, size_t, cudaStream_t, const RtiCfg<T>&, const RtiArgs<T>&, bool);
     const void* (*kernel)();
+    void (*claunch)(int, int, size_t, cudaStream_t, const RtiCfg<T>&, const RtiArgs<T>&);  // constrained kernel (shared by the latency build)
+    const void* (*ckernel)();
 };
 // lat: the latency build (fp32, N = 20 only)
 template <typename T> RtiInst<T> rti_inst(int N, bool lat);
 template <> RtiInst<float> rti_inst<float>(int N, bool lat) {
-    if (lat && N == 20) return {rti_launch_f32_20_1, rti_kernel_f32_20_1};
+    if (lat && N == 20) return {rti_launch_f32_20_1, rti_kernel_f32_20_1, rti_claunch_f32_20_0, rti_ckernel_f32_20_0};
     switch (N) {
-        case 20: return {rti_launch_f32_20_0, rti_kernel_f32_20_0};
-        case 40: return {rti_launch_f32_40_0, rti_kernel_f32_40_0};
-        case 80: return {rti_launch_f32_80_0, rti_kernel_f32_80_0};
-        default: return {rti_launch_f32_0_0, rti_kernel_f32_0_0};
+        case 20: return {rti_launch_f32_20_0, rti_kernel_f32_20_0, rti_claunch_f32_20_0, rti_ckernel_f32_20_0};
+        case 40: return {rti_launch_f32_40_0, rti_kernel_f32_40_0, rti_claunch_f32_40_0, rti_ckernel_f32_40_0};
+        case 80: return {rti_launch_f32_80_0, rti_kernel_f32_80_0, rti_claunch_f32_80_0, rti_ckernel_f32_80_0};
+        default: return {rti_launch_f32_0_0, rti_kernel_f32_0_0, rti_claunch_f32_0_0, rti_ckernel_f32_0_0};
     }
 }
 template <> RtiInst<double> rti_inst<double>(int N, bool) {
     switch (N) {
-        case 20: return {rti_launch_f64_20_0, rti_kernel_f64_20_0};
-        case 40: return {rti_launch_f64_40_0, rti_kernel_f64_40_0};
-        case 80: return {rti_launch_f64_80_0, rti_kernel_f64_80_0};
-        default: return {rti_launch_f64_0_0, rti_kernel_f64_0_0};
+        case 20: return {rti_launch_f64_20_0, rti_kernel_f64_20_0, rti_claunch_f64_20_0, rti_ckernel_f64_20_0};
+        case 40: return {rti_launch_f64_40_0, rti_kernel_f64_40_0, rti_claunch_f64_40_0, rti_ckernel_f64_40_0};
+        case 80: return {rti_launch_f64_80_0, rti_kernel_f64_80_0, rti_claunch_f64_80_0, rti_ckernel_f64_80_0};
+        default: return {rti_launch_f64_0_0, rti_kernel_f64_0_0, rti_claunch_f64_0_0, rti_ckernel_f64_0_0};
     }
 }
 
@@ -241,13 +250,23 @@ int launch_solve(ndp_handle* h, const void* x0, void* u0, cudaStream_t st, const
     a.u0 = (T*)u0;
     a.status = h->status;
     a.stats = h->stats;
-    a.as_store = h->cfg.active_set_warm ? h->as_store : nullptr;
+    a.as_store = h->as_store;
+    a.as_warm = h->cfg.active_set_warm ? 1 : 0;
     a.ws = (T*)h->ws;
     a.ws_stride = h->ws_stride;
+    a.queue = h->queue;
+    a.qctl = h->qctl;
     a.B = h->cfg.batch;
     const int thr = h->ppc * GL;
-    rti_inst<T>(h->cfg.N, h->lat != 0).launch(h->grid, thr, h->smem, st, c, a, pdl && xr && f);
-    h->launches++;
+    const RtiInst<T> inst = rti_inst<T>(h->cfg.N, h->lat != 0);
+    inst.launch(h->grid, thr, h->smem, st, c, a, pdl && xr && f);
+    CU(cudaGetLastError());
+    // the problems whose unconstrained step left its box: second kernel, launched as a programmatic dependent so that its
+    // launch latency hides under the nominal kernel (it exits at once when the queue is empty)
+    a.ws = (T*)h->ws_c;
+    a.ws_stride = h->ws_c_stride;
+    inst.claunch(h->grid_c, thr, h->smem, st, c, a);
+    h->launches += 2;
     CU(cudaGetLastError());
     return 0;
 }
@@ -258,6 +277,9 @@ using namespace ndp;
 
 static const void* rti_kernel_ptr(int elt, int N, bool lat) {
     return elt == 4 ? rti_inst<float>(N, lat).kernel() : rti_inst<double>(N, false).kernel();
+}
+static const void* rti_ckernel_ptr(int elt, int N) {
+    return elt == 4 ? rti_inst<float>(N, false).ckernel() : rti_inst<double>(N, false).ckernel();
 }
 
 static int field_geom(const ndp_handle* h, int field, void** base, int* n_int, int* sdim, int* dim, int* dim_last, int* n_stages) {
@@ -321,8 +343,8 @@ void ndp_default_config(ndp_config* c) {
     c->u_min[3] = 0;
     c->u_max[3] = 9.81 / 0.36;
     c->ipm_max_iter = 50;
-    c->polish_max = 6;
-    c->active_set_first = 6;
+    c->polish_max = 12;
+    c->active_set_first = 16;
     c->active_set_warm = 0;
     c->ipm_tol_mu = 0.0;
 }
@@ -365,11 +387,23 @@ int ndp_create(const ndp_config* cfg, ndp_handle** out) {
     const int cap = n_sm * occ;  // persistent: at most one resident wave, grid-stride over problems
     h->grid = need < cap ? need : cap;
     h->slots = h->grid * h->ppc;
-    h->ws_stride = WL.total;
+    h->ws_stride = WL.oBarD;  // the nominal kernel only keeps the stage records of its forward sweep
+    {
+        const void* cfn = rti_ckernel_ptr(h->elt, N);
+        e = (cudaError_t)raise_dyn_smem(cfn, dev, h->smem);
+        int occ_c = 0;
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, cfn, h->ppc * GL, h->smem);
+        if (e != cudaSuccess || occ_c < 1) { delete h; return e != cudaSuccess ? cuda_fail(e, "constrained kernel occupancy") : fail(NDP_E_CONFIG, "constrained kernel does not fit"); }
+        const int cap_c = n_sm * occ_c;
+        h->grid_c = need < cap_c ? need : cap_c;
+        h->slots_c = h->grid_c * h->ppc;
+        h->ws_c_stride = WL.total;
+    }
     const size_t eb = (size_t)h->elt;
     h->X = h->U = h->yref = h->par = h->ws = nullptr;
     h->status = h->stats = nullptr;
     h->as_store = nullptr;
+    h->ws_c = nullptr; h->queue = nullptr; h->qctl = nullptr;
     h->hs = nullptr; h->hgraph[0] = h->hgraph[1] = nullptr; h->d_hx0 = h->d_hu0 = nullptr;
     for (auto& q : h->hptr) q = nullptr;
     bool ok = cudaMalloc(&h->X, (size_t)B * (N + 1) * NX * eb) == cudaSuccess && cudaMalloc(&h->U, (size_t)B * N * NU * eb) == cudaSuccess &&
@@ -378,7 +412,9 @@ int ndp_create(const ndp_config* cfg, ndp_handle** out) {
               cudaMalloc(&h->ws, (size_t)h->slots * h->ws_stride * eb) == cudaSuccess &&
               cudaMalloc(&h->status, (size_t)B * sizeof(int32_t)) == cudaSuccess &&
               cudaMalloc(&h->stats, (size_t)B * 4 * sizeof(int32_t)) == cudaSuccess &&
-              cudaMalloc(&h->as_store, (size_t)B * 16 * sizeof(unsigned long long)) == cudaSuccess;
+              cudaMalloc(&h->as_store, (size_t)B * AS_OWNERS * 4 * sizeof(unsigned long long)) == cudaSuccess &&
+              cudaMalloc(&h->ws_c, (size_t)h->slots_c * h->ws_c_stride * eb) == cudaSuccess &&
+              cudaMalloc((void**)&h->queue, (size_t)B * sizeof(int)) == cudaSuccess && cudaMalloc((void**)&h->qctl, 4 * sizeof(int)) == cudaSuccess;
     if (!ok) { ndp_destroy(h); return fail(NDP_E_ALLOC, "ndp_create: cudaMalloc failed"); }
     // acados initialises the iterate, yref and p to zeros
     cudaMemset(h->X, 0, (size_t)B * (N + 1) * NX * eb);
@@ -388,7 +424,9 @@ int ndp_create(const ndp_config* cfg, ndp_handle** out) {
     cudaMemset(h->ws, 0, (size_t)h->slots * h->ws_stride * eb);
     cudaMemset(h->status, 0, (size_t)B * sizeof(int32_t));
     cudaMemset(h->stats, 0, (size_t)B * 4 * sizeof(int32_t));
-    cudaMemset(h->as_store, 0, (size_t)B * 16 * sizeof(unsigned long long));
+    cudaMemset(h->as_store, 0, (size_t)B * AS_OWNERS * 4 * sizeof(unsigned long long));
+    cudaMemset(h->ws_c, 0, (size_t)h->slots_c * h->ws_c_stride * eb);
+    cudaMemset(h->qctl, 0, 4 * sizeof(int));
     CU(cudaDeviceSynchronize());
     *out = h;
     return 0;
@@ -399,6 +437,7 @@ int ndp_destroy(ndp_handle* h) {
     DeviceGuard dg(h->dev);
     cudaFree(h->X); cudaFree(h->U); cudaFree(h->yref); cudaFree(h->par); cudaFree(h->ws);
     cudaFree(h->status); cudaFree(h->stats); cudaFree(h->as_store);
+    cudaFree(h->ws_c); cudaFree(h->queue); cudaFree(h->qctl);
     for (auto& g : h->hgraph) if (g) cudaGraphExecDestroy(g);
     if (h->hs) cudaStreamDestroy(h->hs);
     cudaFree(h->d_hx0); cudaFree(h->d_hu0);
@@ -409,7 +448,7 @@ int ndp_destroy(ndp_handle* h) {
 int ndp_set(ndp_handle* h, int field, int stage, const void* dev, int64_t ld, void* stream) {
     DeviceGuard dg(h ? h->dev : -1);
     if (h && (field == NDP_FIELD_X || field == NDP_FIELD_U))  // the iterate is being overwritten: drop the active-set guess
-        cudaMemsetAsync(h->as_store, 0, (size_t)h->cfg.batch * 16 * sizeof(unsigned long long), (cudaStream_t)stream);
+        cudaMemsetAsync(h->as_store, 0, (size_t)h->cfg.batch * AS_OWNERS * 4 * sizeof(unsigned long long), (cudaStream_t)stream);
     return set_get<true>(h, field, stage, const_cast<void*>(dev), ld, stream);
 }
 int ndp_get(ndp_handle* h, int field, int stage, void* dev, int64_t ld, void* stream) {
@@ -424,7 +463,7 @@ int ndp_reset(ndp_handle* h, const void* xr, const void* ur, void* stream) {
     const int N = h->cfg.N, B = h->cfg.batch;
     CU(cudaMemcpyAsync(h->X, xr, (size_t)B * (N + 1) * NX * eb, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     CU(cudaMemcpyAsync(h->U, ur, (size_t)B * N * NU * eb, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
-    CU(cudaMemsetAsync(h->as_store, 0, (size_t)B * 16 * sizeof(unsigned long long), (cudaStream_t)stream));  // a new iterate: no active-set guess
+    CU(cudaMemsetAsync(h->as_store, 0, (size_t)B * AS_OWNERS * 4 * sizeof(unsigned long long), (cudaStream_t)stream));  // a new iterate: no active-set guess
     return 0;
 }
 

@@ -13,6 +13,9 @@
 #define NDP_INST_TAG f32_20_0
 #endif
 
+#ifndef NDP_INST_LAT_IS_TRUE
+#define NDP_INST_LAT_IS_TRUE 0
+#endif
 #define NDP_CAT2(a, b) a##b
 #define NDP_CAT(a, b) NDP_CAT2(a, b)
 
@@ -40,5 +43,25 @@ void NDP_CAT(rti_launch_, NDP_INST_TAG)(int grid, int threads, size_t smem, cuda
 }
 
 const void* NDP_CAT(rti_kernel_, NDP_INST_TAG)() { return (const void*)rti_step_kernel<NDP_INST_T, NDP_INST_N, NDP_INST_LAT>; }
+
+#if !NDP_INST_LAT_IS_TRUE
+// the constrained kernel of this (precision, horizon): always a programmatic dependent of the nominal launch before it
+void NDP_CAT(rti_claunch_, NDP_INST_TAG)(int grid, int threads, size_t smem, cudaStream_t st, const RtiCfg<NDP_INST_T>& c,
+                                         const RtiArgs<NDP_INST_T>& a) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, rti_constrained_kernel<NDP_INST_T, NDP_INST_N>, c, a);
+}
+
+const void* NDP_CAT(rti_ckernel_, NDP_INST_TAG)() { return (const void*)rti_constrained_kernel<NDP_INST_T, NDP_INST_N>; }
+#endif
 
 }  // namespace ndp

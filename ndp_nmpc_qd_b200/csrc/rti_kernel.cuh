@@ -20,6 +20,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 namespace ndp {
 
 constexpr int NX = 10, NU = 4, NZ = 14, GL = 16;
@@ -55,11 +57,23 @@ struct RtiArgs {
     const T* f;
     T* yref_w;
     T* par_w;
-    unsigned long long* as_store;  // [B][4 inputs][4]: active set of the previous solve (lo.w0 lo.w1 hi.w0 hi.w1), or null
-    T* ws;            // [slots][ws_stride]
+    // [B][AS_OWNERS][4]: active set a problem starts its constrained solve from (lo.w0 lo.w1 hi.w0 hi.w1 per owning lane:
+    // the three velocity components, then the four inputs) -- written by the nominal kernel for the problems it hands
+    // over (the bounds the unconstrained step violates) and, with as_warm, left by the constrained kernel as the first
+    // guess of the problem's next solve
+    unsigned long long* as_store;
+    int as_warm;
+    T* ws;            // nominal kernel: [slots][ws_stride] forward-sweep records; constrained kernel: its full workspace
     long long ws_stride;
+    // hand-over from the nominal to the constrained kernel: queue [B] of problem indices (bit 31: the unconstrained
+    // sweep has run), qctl = {count, head, done}
+    int* queue;
+    int* qctl;
     int B;
 };
+
+constexpr int AS_OWNERS = 7;
+__device__ __forceinline__ int as_owner(int lane) { return (lane >= 10) ? lane - 7 : lane - 3; }  // lanes 3..5 -> 0..2, 10..13 -> 3..6
 
 __host__ __device__ constexpr int al4(int o) { return (o + 3) & ~3; }
 
@@ -81,14 +95,16 @@ struct SmemLayout {
 
 // ---- per-slot global workspace layout (elements of T) ----
 struct WsLayout {
-    long long oRec, oBarD, oBarG, oIpm, oZc, oHrow, total;
+    long long oRec, oBarD, oBarG, oIpm, oZc, oHrow, oTv, total;
     __host__ __device__ constexpr explicit WsLayout(int N)
         : oRec(0),                                   // [k][14][TLD]: rows 0..9 = tile rows (x-lane records of the
                                                      // forward sweep), rows 10..13 = [K(m, 0..9) kappa_m pad]
           oBarD(oRec + (long long)N * 14 * TLD), oBarG(oBarD + (long long)(N + 1) * 16), oIpm(oBarG + (long long)(N + 1) * 16),
           oZc(oIpm + (long long)7 * N * 16),  // LL LU TL TU CL CU ACT, each [k][lane]
           oHrow(oZc + (long long)(N + 1) * 16),  // [k][m][16]: row m of [Hux Guu], [14] = gradient
-          total(oHrow + (long long)N * 4 * 16) {}
+          oTv(oHrow + (long long)N * 4 * 16),    // [k][a][12]: multiplier row of pinned velocity component a of stage k+1:
+                                                 // nu = -(T(a, 0..9) . dx_k + T(a, 10))
+          total(oTv + (long long)N * 3 * 12) {}
 };
 
 template <typename T> struct Vec4;
@@ -290,8 +306,16 @@ struct ActiveSet {
 // diagonal and gradient (1: from the workspace arrays oBarD / oBarG; 2: pinned inputs of the register-held
 // active set `as`); kRows: store the rows of [Hux Guu | g_u] needed by the active-set multiplier test.
 // Returns false on a non-positive pivot.
+//
+// kBar == 2 also pins VELOCITY components exactly.  A pinned component a of x_{k+1} (lanes 3..5 carry those masks) is the
+// stage-k mixed constraint  E (A dx_k + B du_k + b_k) = beta,  resolved in the range space of the inputs:
+//   Y = G^-1 (E B)',  S = (E B) Y,   K = K_unc + Y S^-1 R_x,  kappa = kappa_unc + Y S^-1 r_0,
+//   R = [0 | beta] - E [A | b] + (E B) G^-1 [H_ux | g_u]   (one column per lane),   P = P_unc + R_x' S^-1 R_x,  p = p_unc + R_x' S^-1 r_0
+// -- an added positive semi-definite term, so nothing of size 1/mu is ever subtracted (the barrier-weighted recursion
+// loses every fp32 digit on such problems; oracle/nmpc_oracle.c orc_eq_solve is the scalar restatement of this block).
+// With kRows the rows T = S^-1 R are kept for the multiplier test  nu = -(T_x dx_k + t_0).
 template <typename T, int kBar, bool kRows>
-__device__ __forceinline__ bool backward_stage(const RtiCfg<T>& c, int k, int j, unsigned mask, T* sm, const SmemLayout& L, T* ws,
+__device__ __forceinline__ bool backward_stage(const RtiCfg<T>& c, int N, int k, int j, unsigned mask, T* sm, const SmemLayout& L, T* ws,
                                                const WsLayout& WL, const T* __restrict__ sT, const T* __restrict__ colp,
                                                const ActiveSet<T>* as) {
     const T* sX = sm + L.oX;
@@ -393,7 +417,76 @@ __device__ __forceinline__ bool backward_stage(const RtiCfg<T>& c, int k, int j,
     const T x2 = (y2 - l32 * x3) * i22;
     const T x1 = (y1 - l21 * x2 - l31 * x3) * i11;
     const T x0 = (y0 - l10 * x1 - l20 * x2 - l30 * x3) * i00;
-    const T K0 = -x0, K1 = -x1, K2 = -x2, K3 = -x3;  // K[:,j] (j < 10) or kappa (j == 14)
+    T K0 = -x0, K1 = -x1, K2 = -x2, K3 = -x3;  // K[:,j] (j < 10) or kappa (j == 14)
+    bool ok_v = true;
+    bool vpins = false;
+    T tv0 = T(0), tv1 = T(0), tv2 = T(0);
+    if (kBar == 2) {
+        const int k1 = k + 1;
+        const bool mine = (j >= 3 && j < 6) && (k1 < N) && (as->lo_m.test(k1) || as->hi_m.test(k1));
+        const unsigned pins = (__ballot_sync(mask, mine) >> (((mask & 1u) ? 0 : 16) + 3)) & 7u;
+        if (pins) {  // uniform over the group
+            vpins = true;
+            const T beta_own = mine ? ((as->lo_m.test(k1) ? as->lo : as->hi) - sX[k1 * NX + j]) : T(0);
+            T D[3][4], beta[3], Y[3][4];
+#pragma unroll
+            for (int a = 0; a < 3; a++) {
+                const bool on = (pins >> a) & 1u;
+                beta[a] = __shfl_sync(mask, beta_own, 3 + a, GL);
+#pragma unroll
+                for (int m = 0; m < 4; m++) {
+                    const T d = __shfl_sync(mask, col[3 + a], 10 + m, GL);
+                    D[a][m] = on ? d : T(0);
+                }
+                // Y_a = G^-1 D_a' with the Cholesky factors of G
+                const T f0 = D[a][0] * i00;
+                const T f1 = (D[a][1] - l10 * f0) * i11;
+                const T f2 = (D[a][2] - l20 * f0 - l21 * f1) * i22;
+                const T f3 = (D[a][3] - l30 * f0 - l31 * f1 - l32 * f2) * i33;
+                Y[a][3] = f3 * i33;
+                Y[a][2] = (f2 - l32 * Y[a][3]) * i22;
+                Y[a][1] = (f1 - l21 * Y[a][2] - l31 * Y[a][3]) * i11;
+                Y[a][0] = (f0 - l10 * Y[a][1] - l20 * Y[a][2] - l30 * Y[a][3]) * i00;
+            }
+            auto dot4 = [](const T (&p)[4], const T (&q)[4]) { return p[0] * q[0] + p[1] * q[1] + p[2] * q[2] + p[3] * q[3]; };
+            // S = D Y (identity on the rows that are not pinned), 3x3 Cholesky
+            const T s00 = dot4(D[0], Y[0]) + ((pins & 1u) ? T(0) : T(1));
+            const T s10 = dot4(D[1], Y[0]), s11 = dot4(D[1], Y[1]) + ((pins & 2u) ? T(0) : T(1));
+            const T s20 = dot4(D[2], Y[0]), s21 = dot4(D[2], Y[1]), s22 = dot4(D[2], Y[2]) + ((pins & 4u) ? T(0) : T(1));
+            const T piv = sizeof(T) == 4 ? T(1e-7) : T(1e-10);  // (E B_free) G^-1 (E B_free)' of a controllable component is >~ 1e-5
+            const T j00 = trsqrt(s00);
+            const T m10 = s10 * j00, m20 = s20 * j00;
+            const T d1 = s11 - m10 * m10;
+            const T j11 = trsqrt(d1);
+            const T m21 = (s21 - m20 * m10) * j11;
+            const T d2 = s22 - m20 * m20 - m21 * m21;
+            const T j22 = trsqrt(d2);
+            ok_v = (s00 > piv) && (d1 > piv) && (d2 > piv);
+            // this lane's column of R, then t = S^-1 r
+            const T xs[4] = {x0, x1, x2, x3};
+            T r[3];
+#pragma unroll
+            for (int a = 0; a < 3; a++)
+                r[a] = ((pins >> a) & 1u) ? (((j == 14) ? beta[a] : T(0)) - col[3 + a] + dot4(D[a], xs)) : T(0);
+            const T q0 = r[0] * j00;
+            const T q1 = (r[1] - m10 * q0) * j11;
+            const T q2 = (r[2] - m20 * q0 - m21 * q1) * j22;
+            tv2 = q2 * j22;
+            tv1 = (q1 - m21 * tv2) * j11;
+            tv0 = (q0 - m10 * tv1 - m20 * tv2) * j00;
+            K0 += Y[0][0] * tv0 + Y[1][0] * tv1 + Y[2][0] * tv2;
+            K1 += Y[0][1] * tv0 + Y[1][1] * tv1 + Y[2][1] * tv2;
+            K2 += Y[0][2] * tv0 + Y[1][2] * tv1 + Y[2][2] * tv2;
+            K3 += Y[0][3] * tv0 + Y[1][3] * tv1 + Y[2][3] * tv2;
+            // R rows through shared memory (the step region is dead during a backward sweep) for the P update
+            T* sRv = sm + L.oDz;
+            if (j < 10) { sRv[j] = r[0]; sRv[12 + j] = r[1]; sRv[24 + j] = r[2]; }
+            if (kRows && (j < 10 || j == 14)) {
+                T* tvp = ws + WL.oTv + (long long)k * 36 + ((j == 14) ? 10 : j);
+                tvp[0] = tv0; tvp[12] = tv1; tvp[24] = tv2;
+            }
+        }
+    }
     if (j < 10) Vec4<T>::st(sHux + j * 4, H[10], H[11], H[12], H[13]);
     // feedback rows for the forward sweep: rec[k][10+m][j] = K(m, j), [10] = kappa_m
     if (j < 10 || j == 14) {
@@ -406,7 +499,12 @@ __device__ __forceinline__ bool backward_stage(const RtiCfg<T>& c, int k, int j,
     for (int i = 0; i < 10; i++) {
         T h0, h1, h2, h3;
         Vec4<T>::ld(sHux + i * 4, h0, h1, h2, h3);
-        Pn[i] = H[i] + h0 * K0 + h1 * K1 + h2 * K2 + h3 * K3;
+        Pn[i] = H[i] - (h0 * x0 + h1 * x1 + h2 * x2 + h3 * x3);  // unconstrained part: H_xx + H_xu K_unc
+    }
+    if (kBar == 2 && vpins) {
+        const T* sRv = sm + L.oDz;
+#pragma unroll
+        for (int i = 0; i < 10; i++) Pn[i] += sRv[i] * tv0 + sRv[12 + i] * tv1 + sRv[24 + i] * tv2;
     }
     if (j < 10) {
         // keep P exactly symmetric (lower triangle mirrored): without this the antisymmetric rounding
@@ -422,7 +520,7 @@ __device__ __forceinline__ bool backward_stage(const RtiCfg<T>& c, int k, int j,
         Vec4<T>::st(sp + 8, Pn[8], Pn[9], T(0), T(0));
     }
     __syncwarp(mask);
-    return ok;
+    return ok && ok_v;
 }
 
 // copy one finished tile ([10][TLD], 30 vectors of 4) to the workspace record of stage k
@@ -446,7 +544,7 @@ __device__ __forceinline__ void tile_to_ws(const T* __restrict__ sT, T* __restri
 // re-loaded from the workspace, one stage ahead of their use.
 template <typename T, bool kLin, int kBar, bool kRows>
 __device__ __forceinline__ bool backward_sweep(const RtiCfg<T>& c, int N, int j, unsigned mask, T* sm, const SmemLayout& L, T* ws,
-                                               const WsLayout& WL, const T* __restrict__ sTriv, const ActiveSet<T>* as) {
+                                               const WsLayout& WL, const T* __restrict__ sTriv, const ActiveSet<T>* as, bool zero_b = false) {
     backward_terminal<T>(c, N, j, mask, sm, L);
     bool ok = true;
     T* sT0 = sm + L.oT0;
@@ -480,10 +578,10 @@ __device__ __forceinline__ bool backward_sweep(const RtiCfg<T>& c, int N, int j,
             }
             __syncwarp(mask);
             tile_to_ws<T>(sT0, ws + WL.oRec + (long long)k * 14 * TLD, j);
-            ok &= backward_stage<T, kBar, kRows>(c, k, j, mask, sm, L, ws, WL, sT0, col0, as);
+            ok &= backward_stage<T, kBar, kRows>(c, N, k, j, mask, sm, L, ws, WL, sT0, col0, as);
             if (k >= 1) {
                 tile_to_ws<T>(sT1, ws + WL.oRec + (long long)(k - 1) * 14 * TLD, j);
-                ok &= backward_stage<T, kBar, kRows>(c, k - 1, j, mask, sm, L, ws, WL, sT1, col1, as);
+                ok &= backward_stage<T, kBar, kRows>(c, N, k - 1, j, mask, sm, L, ws, WL, sT1, col1, as);
             }
         }
     } else {
@@ -500,7 +598,8 @@ __device__ __forceinline__ bool backward_sweep(const RtiCfg<T>& c, int N, int j,
 #pragma unroll
             for (int q = 0; q < 2; q++) {
                 const int idx = j + q * GL;
-                if (idx < 30) Vec4<T>::st(t + idx * 4, pre[q][0], pre[q][1], pre[q][2], pre[q][3]);
+                // vector idx covers tile elements 4 idx .. 4 idx + 3; the b column is element 8 of each 12-wide row
+                if (idx < 30) Vec4<T>::st(t + idx * 4, (zero_b && (idx % 3) == 2) ? T(0) : pre[q][0], pre[q][1], pre[q][2], pre[q][3]);
             }
         };
         fetch(N - 1);
@@ -509,7 +608,7 @@ __device__ __forceinline__ bool backward_sweep(const RtiCfg<T>& c, int N, int j,
         int par = 0;
         for (int k = N - 1; k >= 0; k--) {
             if (k >= 1) fetch(k - 1);
-            ok &= backward_stage<T, kBar, kRows>(c, k, j, mask, sm, L, ws, WL, par ? sT1 : sT0, par ? col1 : col0, as);
+            ok &= backward_stage<T, kBar, kRows>(c, N, k, j, mask, sm, L, ws, WL, par ? sT1 : sT0, par ? col1 : col0, as);
             if (k >= 1) {
                 put(par ? sT0 : sT1);
                 __syncwarp(mask);
@@ -542,13 +641,14 @@ static_assert(SmemLayout(1).oHux - SmemLayout(1).oY >= FW_RING * FW_REC, "forwar
 // workspace through a FW_RING-deep shared-memory ring (cp.async groups; each lane copies and reads only
 // its own record, so no barrier is needed) laid over the cost records, sDz, P+, p+ and the two stage tiles,
 // which are all dead by then (the tiles' zero pad columns are restored afterwards); the
-// new iterate (X + dx, U + du) is written to global memory as it is produced and the box test / NaN
-// test / active count are fused in (returned through viol / bad / nact).
+// new iterate (X + dx, U + du) replaces the old one IN SHARED MEMORY as it is produced (the caller copies it out with
+// wide stores once the step is accepted -- global memory keeps the old iterate until then, which is what a failed or
+// handed-over problem needs) and the box test / NaN test / active count are fused in (returned through viol / bad / nact).
 // !kFinal (IPM sweeps): records are register-prefetched and the step goes to sDz[k][lane].
 template <typename T, bool kFinal>
 __device__ __forceinline__ void forward_sweep(const RtiCfg<T>& c, int N, int lane, unsigned mask, T dx0, T* sm, const SmemLayout& L,
                                               const T* ws, const WsLayout& WL, T lo, T hi, T* gX, T* gU, T* gu0, bool& viol, bool& bad,
-                                              int& nact, bool rezero_pads = true) {
+                                              int& nact, bool rezero_pads = true, bool zero_b = false) {
     T* sDz = sm + L.oDz;
     const bool isx = lane < 10, isu = (lane >= 10 && lane < 14), isv = (lane >= 3 && lane < 6);
     const T* rec = ws + WL.oRec + (long long)((lane < 14) ? lane : 13) * TLD;
@@ -569,15 +669,17 @@ __device__ __forceinline__ void forward_sweep(const RtiCfg<T>& c, int N, int lan
         T um[4];
 #pragma unroll
         for (int m = 0; m < 4; m++) um[m] = __shfl_sync(mask, du, 10 + m, GL);
-        T xn = cf[8] + ((lane < 3) ? z + c.h * zv : ((lane < 6) ? z : T(0)));
+        T xn = ((zero_b && !kFinal) ? T(0) : cf[8]) + ((lane < 3) ? z + c.h * zv : ((lane < 6) ? z : T(0)));
         xn += cf[0] * xj[6] + cf[1] * xj[7] + cf[2] * xj[8] + cf[3] * xj[9];
         xn += cf[4] * um[0] + cf[5] * um[1] + cf[6] * um[2] + cf[7] * um[3];
         du_out = isx ? z : du;
         z = xn;
     };
     if (kFinal) {
-        const T* itp = isx ? sm + L.oX + lane : sm + L.oU + ((lane - 10) & 3);
+        T* itp = isx ? sm + L.oX + lane : sm + L.oU + ((lane - 10) & 3);
+#ifdef NDP_DIRECT_STORE
         T* gp = isx ? gX + lane : gU + ((lane - 10) & 3);
+#endif
         const int its = isx ? NX : NU;
         T* ring = sm + L.oY + ((lane < 14) ? lane : 13) * TLD;  // [FW_RING][14][TLD] over sY | sDz
         auto issue = [&](int k) {
@@ -611,8 +713,11 @@ __device__ __forceinline__ void forward_sweep(const RtiCfg<T>& c, int N, int lan
             stage(k, cf, dz);
             if (lane < 14) {
                 const T v = it_cur + dz;
+#ifdef NDP_DIRECT_STORE
                 gp[k * its] = v;
-                if (k == 0 && isu && gu0) gu0[lane - 10] = v;
+#else
+                itp[k * its] = v;
+#endif
                 b_l |= !(fabs(v) <= T(1e30));
                 if (isu || (isv && k >= 1)) {
                     v_l |= !(v >= lo && v <= hi);
@@ -624,7 +729,11 @@ __device__ __forceinline__ void forward_sweep(const RtiCfg<T>& c, int N, int lan
         cp_async_wait<0>();
         if (isx) {
             const T v = it_cur + z;
+#ifdef NDP_DIRECT_STORE
             gp[N * its] = v;
+#else
+            itp[N * its] = v;
+#endif
             b_l |= !(fabs(v) <= T(1e30));
         }
         __syncwarp(mask);
@@ -671,13 +780,25 @@ __device__ __forceinline__ void forward_sweep(const RtiCfg<T>& c, int N, int lan
 
 enum { IPM_LL = 0, IPM_LU, IPM_TL, IPM_TU, IPM_CL, IPM_CU, IPM_ACT };
 
+constexpr int AS_HIST = 6;  // active-set hashes remembered for the cycle test
+
 // Constrained QP of one problem (the unconstrained step left its box): kept out of line so that the nominal
 // path of rti_step_kernel keeps its register allocation (nothing but the problem loop's own state is live
 // across the call): solves the QP, writes the new iterate, u0, status and statistics of the problem.
+//
+// Route: primal-dual active-set rounds with EXACT pins -- inputs and velocity components alike (backward_stage,
+// kBar == 2) -- seeded by the bounds the unconstrained step violates; one Riccati factorisation per round, the active
+// set lives in registers (two bit masks per owning lane: lanes 10..13 the inputs, lanes 3..5 the velocities).  A
+// fixed point of the rounds satisfies the KKT conditions of the QP, i.e. it is the solution the reference's
+// interior-point method converges to, without a barrier floor.  The plain update (release every wrong-signed
+// multiplier, add every violated bound) can cycle; a repeated set (hash test) switches to a damped update (add every
+// violated bound; release only the single worst multiplier, and only once nothing is violated).  If as_first_max
+// rounds find no fixed point: Mehrotra predictor-corrector IPM (HPIPM's algorithm) for an active-set estimate, then
+// the rounds again from that estimate.
 template <typename T, int kN>
-__device__ __noinline__ void constrained_qp(const RtiCfg<T>& c, int lane, unsigned mask, T* sm, T* ws, const T* sTriv, T dx0, T lo, T hi,
-                                            T* gX, T* gU, const T* gY, T* gu0, int32_t* g_status, int32_t* g_stats,
-                                            unsigned long long* g_as, bool warm) {
+__device__ __forceinline__ void constrained_qp(const RtiCfg<T>& c, int lane, unsigned mask, T* sm, T* ws, const T* sTriv, T dx0, T lo, T hi,
+                                               T* gX, T* gU, T* gu0, int32_t* g_status, int32_t* g_stats, unsigned long long* g_as,
+                                               bool keep_set, int n_fact0) {
     const int N = (kN > 0) ? kN : c.N;
     const SmemLayout L(N);
     const WsLayout WL(N);
@@ -687,365 +808,373 @@ __device__ __noinline__ void constrained_qp(const RtiCfg<T>& c, int lane, unsign
     const bool isx = lane < 10, isu = (lane >= 10 && lane < 14), isv = (lane >= 3 && lane < 6);
     auto iter_at = [&](int k) -> T { return isx ? sX[k * NX + lane] : (isu ? sU[k * NU + (lane - 10)] : T(0)); };
     auto has_box = [&](int k) -> bool { return (isu && k < N) || (isv && k >= 1 && k < N); };
-    // warm: the previous solve of this problem ended with active bounds; nothing has been computed yet and the
-    // first round linearises and factorises with that active set pinned (if it is still the right one, the
-    // constrained step costs one sweep).  !warm: the unconstrained sweep has run and left the box.
-    int status = 0, n_fact = warm ? 0 : 1, n_ipm = 0, n_pol = 0;
+    // The problem arrives staged in shared memory (iterate, cost records) with the set to start from in g_as; nothing
+    // has been linearised in THIS kernel yet: the first round integrates and factorises with that set pinned.
+    int status = 0, n_fact = n_fact0, n_ipm = 0, n_pol = 0;
     bool viol = false, bad = false;
     int nact_l = 0;
-        if (!warm) {   // the accepted-sweep ring overwrote the cost records: rebuild them from the stored yref
-                        T* sY = sm + L.oY;
-            for (int i = lane; i < (N + 1) * SYS; i += GL) {
-                const int k = i >> 4, e = i & 15;
-                sY[i] = (e < NYS) ? gY[k * NYS + e] : T(0);
+    T* wI = ws + WL.oIpm;
+    T* wZ = ws + WL.oZc;
+    T* bD = ws + WL.oBarD;
+    T* bG = ws + WL.oBarG;
+    const int FS = N * 16;  // field stride
+    bool ipm_ok = false, pol_ok = false;
+    ActiveSet<T> as;
+    as.lo = lo; as.hi = hi; as.big = c.big;
+    bool lin_done = false;  // [A B b] tiles of this iterate are in the workspace
+    // a released variable that lands within a few ulps of its bound is not a violation (it would be re-pinned and
+    // released for ever)
+    const T feas_eps = (sizeof(T) == 4 ? T(5e-7) : T(1e-13)) * fmax(T(1), fmax(fabs(lo), fabs(hi)));
+
+    // ---- primal-dual active-set rounds from the set in `as` ----
+    auto pdas = [&](int max_rounds) -> bool {
+        unsigned long long hist[AS_HIST];
+#pragma unroll
+        for (int q = 0; q < AS_HIST; q++) hist[q] = 0ull;
+        bool damped = false;
+        for (int round = 0; round < max_rounds; round++) {
+            // cycle test on a hash of the whole set
+            {
+                unsigned long long h = (as.lo_m.w0 * 0x9E3779B97F4A7C15ull) ^ (as.hi_m.w0 * 0xC2B2AE3D27D4EB4Full) ^
+                                       (as.lo_m.w1 * 0x165667B19E3779F9ull) ^ (as.hi_m.w1 * 0x27D4EB2F165667C5ull);
+                h *= (unsigned long long)(2 * lane + 1);
+#pragma unroll
+                for (int o = 8; o >= 1; o >>= 1) h += __shfl_xor_sync(mask, h, o, GL);
+                h |= 1ull;
+#pragma unroll
+                for (int q = 0; q < AS_HIST; q++) damped |= (hist[q] == h);
+#pragma unroll
+                for (int q = AS_HIST - 1; q > 0; q--) hist[q] = hist[q - 1];
+                hist[0] = h;
             }
-            __syncwarp(mask);
-            cost_records<T>(N, lane, sY, sX, sU, sm + L.oPar);
-            __syncwarp(mask);
-        }
-        T* wI = ws + WL.oIpm;
-        T* wZ = ws + WL.oZc;
-        T* bD = ws + WL.oBarD;
-        T* bG = ws + WL.oBarG;
-        const int FS = N * 16;  // field stride
-        bool ipm_ok = false, pol_ok = false;
-        // Phase 0: primal-dual active-set rounds seeded by the bounds the unconstrained step violates (its
-        // tentative iterate is in gX / gU).  A fixed point of the rounds satisfies the KKT conditions of the QP,
-        // so it is the same solution the interior-point method converges to, at one Riccati factorisation per
-        // round instead of two per IPM iteration.  The active set lives in registers (two bit masks per lane),
-        // so a round touches the workspace only for the stage tiles and the multiplier rows.
-        // Phase 1 (velocity box involved, or no fixed point within as_first_max rounds): Mehrotra IPM, then the
-        // rounds again from the IPM's active set.
-        ActiveSet<T> as;
-        as.lo = lo; as.hi = hi; as.big = c.big;
-        bool seed_x = false;
-        if (warm) {
-            if (isu) {
-                const unsigned long long* p = g_as + (lane - 10) * 4;
-                as.lo_m.w0 = p[0]; as.lo_m.w1 = p[1]; as.hi_m.w0 = p[2]; as.hi_m.w1 = p[3];
-            }
-        } else {
-            for (int k = 0; k < N; k++)
-                if (has_box(k)) {
-                    const T v = isu ? gU[k * NU + (lane - 10)] : gX[k * NX + lane];
-                    if (isu) {
-                        if (v < lo) as.lo_m.set(k);
-                        else if (v > hi) as.hi_m.set(k);
+            bool fact_ok;
+            if (!lin_done) fact_ok = backward_sweep<T, true, 2, true>(c, N, lane, mask, sm, L, ws, WL, sTriv, &as);
+            else fact_ok = backward_sweep<T, false, 2, true>(c, N, lane, mask, sm, L, ws, WL, sTriv, &as);
+            lin_done = true;
+            if (!fact_ok) return false;
+            n_fact++;
+            n_pol++;
+            forward_sweep<T, false>(c, N, lane, mask, dx0, sm, L, ws, WL, lo, hi, gX, gU, nullptr, viol, bad, nact_l);
+            bool changed = false, any_viol = false;
+            T worst = T(0);  // most wrong-signed multiplier of this lane's pinned bounds (damped mode releases one)
+            int worst_k = -1;
+            for (int k = 0; k < N; k++) {
+                // multipliers of the velocity components of stage k+1 pinned in this sweep
+                const int k1 = k + 1;
+                const bool vp = isv && (k1 < N) && (as.lo_m.test(k1) || as.hi_m.test(k1));
+                T nu = T(0);
+                if (vp) {
+                    const T* tv = ws + WL.oTv + (long long)k * 36 + (lane - 3) * 12;
+                    nu = tv[10];
+#pragma unroll
+                    for (int i = 0; i < 10; i++) nu += tv[i] * sDz[k * 16 + i];
+                    nu = -nu;
+                }
+                const unsigned vb = (__ballot_sync(mask, vp) >> (((mask & 1u) ? 0 : 16) + 3)) & 7u;
+                T nu0 = T(0), nu1 = T(0), nu2 = T(0);
+                if (vb) {
+                    nu0 = __shfl_sync(mask, nu, 3, GL);
+                    nu1 = __shfl_sync(mask, nu, 4, GL);
+                    nu2 = __shfl_sync(mask, nu, 5, GL);
+                }
+                if (isu) {
+                    const T it_v = sU[k * NU + (lane - 10)];
+                    const bool at_lo = as.lo_m.test(k), at_hi = as.hi_m.test(k);
+                    if (at_lo || at_hi) {
+                        // multiplier of the pinned input from the un-penalised row of [Hux Guu | g_u] (+ the pinned
+                        // velocity rows of this stage's mixed constraint)
+                        const T* hr = ws + WL.oHrow + (k * 4 + (lane - 10)) * 16;
+                        T gq = hr[14];
+#pragma unroll
+                        for (int i = 0; i < 14; i++) gq += hr[i] * sDz[k * 16 + i];
+                        if (vb) {
+                            const T* eb = ws + WL.oRec + ((long long)k * 14 + 3) * TLD + 4 + (lane - 10);  // (E B)(a, m)
+                            gq += eb[0] * nu0 + eb[TLD] * nu1 + eb[2 * TLD] * nu2;
+                        }
+                        const T lam = at_hi ? -gq : gq;  // >= 0 at a KKT point
+                        if (lam < T(0)) {
+                            if (!damped) { as.lo_m.clear(k); as.hi_m.clear(k); changed = true; }
+                            else if (lam < worst) { worst = lam; worst_k = k; }
+                        }
                     } else {
-                        seed_x |= !(v >= lo && v <= hi);
+                        const T zn = sDz[k * 16 + lane];
+                        if (zn > hi - it_v + feas_eps) { as.hi_m.set(k); changed = true; any_viol = true; }
+                        else if (zn < lo - it_v - feas_eps) { as.lo_m.set(k); changed = true; any_viol = true; }
                     }
                 }
-            seed_x = __any_sync(mask, seed_x);
+                if (isv && k1 < N) {
+                    if (vp) {
+                        const T lam = as.hi_m.test(k1) ? nu : -nu;
+                        if (lam < T(0)) {
+                            if (!damped) { as.lo_m.clear(k1); as.hi_m.clear(k1); changed = true; }
+                            else if (lam < worst) { worst = lam; worst_k = k1; }
+                        }
+                    } else {
+                        const T it_v = sX[k1 * NX + lane], zn = sDz[k1 * 16 + lane];
+                        if (zn > hi - it_v + feas_eps) { as.hi_m.set(k1); changed = true; any_viol = true; }
+                        else if (zn < lo - it_v - feas_eps) { as.lo_m.set(k1); changed = true; any_viol = true; }
+                    }
+                }
+            }
+            any_viol = __any_sync(mask, any_viol);
+            if (damped && !any_viol) {
+                // release the single worst multiplier of the problem
+                const T w_all = grp_min<T>(worst, mask);
+                const bool cand = (worst_k >= 0) && (worst == w_all) && (w_all < T(0));
+                const unsigned cb = (__ballot_sync(mask, cand) >> ((mask & 1u) ? 0 : 16)) & 0xFFFFu;
+                if (cand && (cb & ((1u << lane) - 1u)) == 0u) { as.lo_m.clear(worst_k); as.hi_m.clear(worst_k); changed = true; }
+            }
+            changed = __any_sync(mask, changed);
+            __syncwarp(mask);
+            if (!changed) {
+                // pinned variables sit exactly on their bound
+                if (isu || isv)
+                    for (int k = 0; k < N; k++) {
+                        const T it_v = iter_at(k);
+                        if (as.lo_m.test(k)) sDz[k * 16 + lane] = lo - it_v;
+                        if (as.hi_m.test(k)) sDz[k * 16 + lane] = hi - it_v;
+                    }
+                return true;
+            }
+        }
+        return false;
+    };
+
+    // Phase 0: rounds from the handed-over set (the bounds the unconstrained step violates, or the previous solve's final set)
+    if (isu || isv) {
+        const unsigned long long* p = g_as + as_owner(lane) * 4;
+        as.lo_m.w0 = p[0]; as.lo_m.w1 = p[1]; as.hi_m.w0 = p[2]; as.hi_m.w1 = p[3];
+    }
+    __syncwarp(mask);
+    if (c.as_first_max > 0) pol_ok = pdas(c.as_first_max);
+
+    if (!pol_ok) {
+        // ================= Mehrotra IPM on the Riccati kernel: active-set estimate for the rounds =================
+        // (t < lambda marks a bound as active).  The rounds are tried from the estimate after convergence and, since only
+        // the active set has to be right, not the barrier iterate, every 3rd iteration before that.
+        auto rounds_from_ipm = [&](int max_rounds) -> bool {
+            as.lo_m = StageMask(); as.hi_m = StageMask();
+            for (int k = 0; k < N; k++)
+                if (has_box(k)) {
+                    const int e = k * 16 + lane;
+                    if (wI[IPM_TL * FS + e] < wI[IPM_LL * FS + e]) as.lo_m.set(k);
+                    else if (wI[IPM_TU * FS + e] < wI[IPM_LU * FS + e]) as.hi_m.set(k);
+                }
+            __syncwarp(mask);
+            return pdas(max_rounds);
+        };
+        if (!lin_done) {
+            // warm start without a usable guess: linearise with an empty set first
+            as.lo_m = StageMask(); as.hi_m = StageMask();
+            if (!backward_sweep<T, true, 2, false>(c, N, lane, mask, sm, L, ws, WL, sTriv, &as)) status = 4;
+            lin_done = true;
+            n_fact++;
+        }
+        for (int k = 0; k <= N; k++) {
+            bD[k * 16 + lane] = T(0);
+            bG[k * 16 + lane] = T(0);
+            wZ[k * 16 + lane] = (k == 0 && isx) ? dx0 : T(0);
         }
         __syncwarp(mask);
-        bool lin_done = !warm;  // [A B b] tiles of this iterate are in the workspace
-        if (!seed_x && (c.as_first_max > 0 || warm)) {
-            for (int round = 0; round < (c.as_first_max > 1 ? c.as_first_max : 1); round++) {
-                bool fact_ok;
-                if (!lin_done) fact_ok = backward_sweep<T, true, 2, true>(c, N, lane, mask, sm, L, ws, WL, sTriv, &as);
-                else fact_ok = backward_sweep<T, false, 2, true>(c, N, lane, mask, sm, L, ws, WL, sTriv, &as);
-                lin_done = true;
-                if (!fact_ok) break;
-                n_fact++;
-                n_pol++;
-                forward_sweep<T, false>(c, N, lane, mask, dx0, sm, L, ws, WL, lo, hi, gX, gU, nullptr, viol, bad, nact_l);
-                bool changed = false, xviol = false;
-                if (isv)
-                    for (int k = 1; k < N; k++) {
-                        const T it_v = sX[k * NX + lane], zn = sDz[k * 16 + lane];
-                        xviol |= !(zn >= lo - it_v && zn <= hi - it_v);
-                    }
-                if (isu)
-                    for (int k = 0; k < N; k++) {
-                        const T it_v = sU[k * NU + (lane - 10)];
-                        const bool at_lo = as.lo_m.test(k), at_hi = as.hi_m.test(k);
-                        if (at_lo || at_hi) {
-                            // multiplier of the pinned input from the un-penalised row of [Hux Guu | g_u]
-                            const T* hr = ws + WL.oHrow + (k * 4 + (lane - 10)) * 16;
-                            T gq = hr[14];
-#pragma unroll
-                            for (int i = 0; i < 14; i++) gq += hr[i] * sDz[k * 16 + i];
-                            if ((at_hi ? -gq : gq) < T(0)) { as.lo_m.clear(k); as.hi_m.clear(k); changed = true; }
-                        } else {
-                            const T zn = sDz[k * 16 + lane];
-                            if (zn > hi - it_v) { as.hi_m.set(k); changed = true; }
-                            else if (zn < lo - it_v) { as.lo_m.set(k); changed = true; }
-                        }
-                    }
-                changed = __any_sync(mask, changed);
-                xviol = __any_sync(mask, xviol);
-                __syncwarp(mask);
-                if (xviol) break;  // a velocity box is violated: that needs the interior-point route
-                if (!changed) { pol_ok = true; break; }
+        int nb_l = 0;
+        for (int k = 0; k < N; k++)
+            if (has_box(k)) {
+                const T it_v = iter_at(k);
+                const T lb = lo - it_v, ub = hi - it_v;
+                const T tl = fmax(-lb, c.t_floor), tu = fmax(ub, c.t_floor);
+                wI[IPM_TL * FS + k * 16 + lane] = tl;
+                wI[IPM_TU * FS + k * 16 + lane] = tu;
+                wI[IPM_LL * FS + k * 16 + lane] = c.mu0 / tl;
+                wI[IPM_LU * FS + k * 16 + lane] = c.mu0 / tu;
+                nb_l++;
             }
-            if (pol_ok && isu) {
-                // pinned inputs sit exactly on their bound
-                for (int k = 0; k < N; k++) {
-                    const T it_v = sU[k * NU + (lane - 10)];
-                    if (as.lo_m.test(k)) sDz[k * 16 + lane] = lo - it_v;
-                    if (as.hi_m.test(k)) sDz[k * 16 + lane] = hi - it_v;
-                }
+        const T inv_m = T(1) / (T(2) * grp_sum<T>((T)nb_l, mask));
+        __syncwarp(mask);
+        T res_lin = T(1), mu_prev = T(1e30), mu = T(0);
+        // a Cholesky pivot lost to the barrier weights (fp32 with active velocity bounds) ends the interior-point
+        // iteration, not the solve: its active-set estimate still goes to the rounds
+        bool ipm_broken = false;
+        int it = 0;
+        for (it = 0; status == 0 && it <= c.ipm_max_iter; it++) {
+            if (it >= 3 && (it % 3) == 0 && res_lin <= T(1e-1) && c.polish_max > 0) {
+                if (rounds_from_ipm(3)) { pol_ok = true; break; }
             }
-        }
-        if (!pol_ok && status == 0) {
-        // ================= active-set rounds from the IPM's current active-set estimate =================
-        // (t < lambda marks a bound as active).  Run after the IPM has converged, and -- since only the active set has
-        // to be right, not the barrier iterate -- tried every 3rd iteration before that, two rounds at a time (stress
-        // variant: 13.0 -> 10.8 sweeps per solve on the IPM-first route; the hardest problems still need the
-        // converged iterate).  A failed attempt only costs its sweeps: it writes bD / bG / sDz / the multiplier
-        // rows, all of which the next IPM iteration recomputes.
-        auto run_rounds = [&](int max_rounds) -> bool {
-            bool fixed = false;
-                for (int k = 0; k < N; k++)
-                    if (has_box(k)) {
-                        const int e = k * 16 + lane;
-                        const T tl = wI[IPM_TL * FS + e], tu = wI[IPM_TU * FS + e];
-                        const T ll = wI[IPM_LL * FS + e], lu = wI[IPM_LU * FS + e];
-                        wI[IPM_ACT * FS + e] = (tl < ll) ? T(1) : ((tu < lu) ? T(2) : T(0));
-                    }
-            for (int round = 0; round < max_rounds; round++) {
-                for (int k = 0; k < N; k++)
-                    if (has_box(k)) {
-                        const int e = k * 16 + lane;
-                        const T it_v = iter_at(k);
-                        const T lb = lo - it_v, ub = hi - it_v;
-                        if (isu) {
-                            const T act = wI[IPM_ACT * FS + e];
-                            bD[e] = (act != T(0)) ? c.big : T(0);
-                            bG[e] = (act != T(0)) ? -c.big * (act == T(1) ? lb : ub) : T(0);
-                        } else {
-                            // velocity boxes cannot be pinned inside the input-elimination Riccati: an
-                            // active one keeps its interior-point barrier term, an inactive one is dropped
-                            // (and checked for feasibility below)
-                            const T act = wI[IPM_ACT * FS + e];
-                            const T tl = wI[IPM_TL * FS + e], tu = wI[IPM_TU * FS + e];
-                            const T ll = wI[IPM_LL * FS + e], lu = wI[IPM_LU * FS + e];
-                            const T gl = ll / tl, gu = lu / tu;
-                            bD[e] = (act != T(0)) ? gl + gu : T(0);
-                            bG[e] = (act != T(0)) ? (-gu * ub + lu) - (gl * lb + ll) : T(0);
-                        }
-                    }
-                __syncwarp(mask);
-                if (!backward_sweep<T, false, 1, true>(c, N, lane, mask, sm, L, ws, WL, sTriv, nullptr)) break;
-                n_fact++;
-                n_pol++;
-                forward_sweep<T, false>(c, N, lane, mask, dx0, sm, L, ws, WL, lo, hi, gX, gU, nullptr, viol, bad, nact_l);
-                bool changed = false, xviol = false;
-                if (isv)
-                    for (int k = 1; k < N; k++) {
-                        const int e = k * 16 + lane;
-                        const T it_v = iter_at(k);
-                        if (wI[IPM_ACT * FS + e] == T(0)) xviol |= !(sDz[e] >= lo - it_v && sDz[e] <= hi - it_v);
-                    }
-                if (isu)
-                    for (int k = 0; k < N; k++) {
-                        const int e = k * 16 + lane;
-                        const T it_v = iter_at(k);
-                        const T lb = lo - it_v, ub = hi - it_v;
-                        const T act = wI[IPM_ACT * FS + e];
-                        if (act != T(0)) {
-                            const T* hr = ws + WL.oHrow + (k * 4 + (lane - 10)) * 16;
-                            T gq = hr[14];
-#pragma unroll
-                            for (int i = 0; i < 14; i++) gq += hr[i] * sDz[k * 16 + i];
-                            const T lam = (act == T(2)) ? -gq : gq;
-                            if (lam < T(0)) { wI[IPM_ACT * FS + e] = T(0); changed = true; }
-                        } else {
-                            const T zn = sDz[e];
-                            if (zn > ub) { wI[IPM_ACT * FS + e] = T(2); changed = true; }
-                            else if (zn < lb) { wI[IPM_ACT * FS + e] = T(1); changed = true; }
-                        }
-                    }
-                changed = __any_sync(mask, changed);
-                xviol = __any_sync(mask, xviol);
-                __syncwarp(mask);
-                if (xviol) break;  // a dropped velocity box is violated: keep the interior-point iterate
-                if (!changed) { fixed = true; break; }
-            }
-            if (fixed && isu) {
-                // pinned inputs sit exactly on their bound
-                for (int k = 0; k < N; k++) {
-                    const int e = k * 16 + lane;
-                    const T act = wI[IPM_ACT * FS + e];
-                    const T it_v = iter_at(k);
-                    if (act == T(1)) sDz[e] = lo - it_v;
-                    if (act == T(2)) sDz[e] = hi - it_v;
-                }
-            }
-            return fixed;
-        };
-        {
-            for (int k = 0; k <= N; k++) {
-                bD[k * 16 + lane] = T(0);
-                bG[k * 16 + lane] = T(0);
-                wZ[k * 16 + lane] = (k == 0 && isx) ? dx0 : T(0);
-            }
-            __syncwarp(mask);
-        // ================= Mehrotra IPM on the Riccati kernel =================
-            int nb_l = 0;
+            // complementarity, affine barrier terms
+            T mu_l = T(0);
             for (int k = 0; k < N; k++)
                 if (has_box(k)) {
+                    const int e = k * 16 + lane;
                     const T it_v = iter_at(k);
                     const T lb = lo - it_v, ub = hi - it_v;
-                    const T tl = fmax(-lb, c.t_floor), tu = fmax(ub, c.t_floor);
-                    wI[IPM_TL * FS + k * 16 + lane] = tl;
-                    wI[IPM_TU * FS + k * 16 + lane] = tu;
-                    wI[IPM_LL * FS + k * 16 + lane] = c.mu0 / tl;
-                    wI[IPM_LU * FS + k * 16 + lane] = c.mu0 / tu;
-                    nb_l++;
+                    const T tl = wI[IPM_TL * FS + e], tu = wI[IPM_TU * FS + e];
+                    const T ll = wI[IPM_LL * FS + e], lu = wI[IPM_LU * FS + e];
+                    mu_l += ll * tl + lu * tu;
+                    const T gl = ll / tl, gu = lu / tu;
+                    bD[e] = gl + gu;
+                    bG[e] = (-gu * ub + lu) - (gl * lb + ll);
                 }
-            const T inv_m = T(1) / (T(2) * grp_sum<T>((T)nb_l, mask));
+            mu = grp_sum<T>(mu_l, mask) * inv_m;
+            if (it > 0 && res_lin <= c.tol_res && mu < c.tol_mu) { ipm_ok = true; break; }
+            if (it > 3 && res_lin <= c.tol_res && mu > T(0.9) * mu_prev && mu < T(1e-2)) { ipm_ok = true; break; }
+            if (!(mu == mu)) { ipm_broken = true; break; }  // NaN
+            if (it == c.ipm_max_iter) break;
+            mu_prev = mu;
             __syncwarp(mask);
-            T res_lin = T(1), mu_prev = T(1e30), mu = T(0);
-            bool any_x_act = false;
-            int it = 0;
-            for (it = 0; it <= c.ipm_max_iter; it++) {
-                if (it >= 3 && (it % 3) == 0 && res_lin <= T(1e-1) && !any_x_act && c.polish_max > 0) {
-                    if (run_rounds(2)) { pol_ok = true; break; }
+            // ---- predictor ----
+            if (!backward_sweep<T, false, 1, false>(c, N, lane, mask, sm, L, ws, WL, sTriv, nullptr)) { ipm_broken = true; break; }
+            n_fact++;
+            forward_sweep<T, false>(c, N, lane, mask, dx0, sm, L, ws, WL, lo, hi, gX, gU, nullptr, viol, bad, nact_l);
+            T amax = T(1e30);
+            for (int k = 0; k < N; k++)
+                if (has_box(k)) {
+                    const int e = k * 16 + lane;
+                    const T it_v = iter_at(k);
+                    const T lb = lo - it_v, ub = hi - it_v;
+                    const T zn = sDz[e];
+                    const T tl = wI[IPM_TL * FS + e], tu = wI[IPM_TU * FS + e];
+                    const T ll = wI[IPM_LL * FS + e], lu = wI[IPM_LU * FS + e];
+                    const T dtl = (zn - lb) - tl, dtu = (ub - zn) - tu;
+                    const T dll = -(ll / tl) * dtl - ll, dlu = -(lu / tu) * dtu - lu;
+                    wI[IPM_CL * FS + e] = dll * dtl;
+                    wI[IPM_CU * FS + e] = dlu * dtu;
+                    if (dtl < T(0)) amax = fmin(amax, -tl / dtl);
+                    if (dtu < T(0)) amax = fmin(amax, -tu / dtu);
+                    if (dll < T(0)) amax = fmin(amax, -ll / dll);
+                    if (dlu < T(0)) amax = fmin(amax, -lu / dlu);
                 }
-                // complementarity, affine barrier terms
-                T mu_l = T(0);
-                bool xa_l = false;
-                for (int k = 0; k < N; k++)
-                    if (has_box(k)) {
-                        const int e = k * 16 + lane;
-                        const T it_v = iter_at(k);
-                        const T lb = lo - it_v, ub = hi - it_v;
-                        const T tl = wI[IPM_TL * FS + e], tu = wI[IPM_TU * FS + e];
-                        const T ll = wI[IPM_LL * FS + e], lu = wI[IPM_LU * FS + e];
-                        mu_l += ll * tl + lu * tu;
-                        const T gl = ll / tl, gu = lu / tu;
-                        bD[e] = gl + gu;
-                        bG[e] = (-gu * ub + lu) - (gl * lb + ll);
-                        if (isv) xa_l |= (tl < ll) || (tu < lu);
-                    }
-                mu = grp_sum<T>(mu_l, mask) * inv_m;
-                any_x_act = __any_sync(mask, xa_l);
-                const T tol = any_x_act ? c.tol_mu * T(0.01) : c.tol_mu;
-                if (it > 0 && res_lin <= c.tol_res && mu < tol) { ipm_ok = true; break; }
-                if (it > 3 && res_lin <= c.tol_res && mu > T(0.9) * mu_prev && mu < T(1e-2)) { ipm_ok = true; break; }
-                if (!(mu == mu)) { status = 4; break; }  // NaN
-                if (it == c.ipm_max_iter) break;
-                mu_prev = mu;
-                __syncwarp(mask);
-                // ---- predictor ----
-                if (!backward_sweep<T, false, 1, false>(c, N, lane, mask, sm, L, ws, WL, sTriv, nullptr)) { status = 4; break; }
-                n_fact++;
-                forward_sweep<T, false>(c, N, lane, mask, dx0, sm, L, ws, WL, lo, hi, gX, gU, nullptr, viol, bad, nact_l);
-                T amax = T(1e30);
-                for (int k = 0; k < N; k++)
-                    if (has_box(k)) {
-                        const int e = k * 16 + lane;
-                        const T it_v = iter_at(k);
-                        const T lb = lo - it_v, ub = hi - it_v;
-                        const T zn = sDz[e];
-                        const T tl = wI[IPM_TL * FS + e], tu = wI[IPM_TU * FS + e];
-                        const T ll = wI[IPM_LL * FS + e], lu = wI[IPM_LU * FS + e];
-                        const T dtl = (zn - lb) - tl, dtu = (ub - zn) - tu;
-                        const T dll = -(ll / tl) * dtl - ll, dlu = -(lu / tu) * dtu - lu;
-                        wI[IPM_CL * FS + e] = dll * dtl;
-                        wI[IPM_CU * FS + e] = dlu * dtu;
-                        if (dtl < T(0)) amax = fmin(amax, -tl / dtl);
-                        if (dtu < T(0)) amax = fmin(amax, -tu / dtu);
-                        if (dll < T(0)) amax = fmin(amax, -ll / dll);
-                        if (dlu < T(0)) amax = fmin(amax, -lu / dlu);
-                    }
-                const T a_aff = fmin(grp_min<T>(amax, mask), T(1));
-                T mua_l = T(0);
-                for (int k = 0; k < N; k++)
-                    if (has_box(k)) {
-                        const int e = k * 16 + lane;
-                        const T it_v = iter_at(k);
-                        const T lb = lo - it_v, ub = hi - it_v;
-                        const T zn = sDz[e];
-                        const T tl = wI[IPM_TL * FS + e], tu = wI[IPM_TU * FS + e];
-                        const T ll = wI[IPM_LL * FS + e], lu = wI[IPM_LU * FS + e];
-                        const T dtl = (zn - lb) - tl, dtu = (ub - zn) - tu;
-                        const T dll = -(ll / tl) * dtl - ll, dlu = -(lu / tu) * dtu - lu;
-                        mua_l += (ll + a_aff * dll) * (tl + a_aff * dtl) + (lu + a_aff * dlu) * (tu + a_aff * dtu);
-                    }
-                const T mu_aff = grp_sum<T>(mua_l, mask) * inv_m;
-                const T sg = mu_aff / mu;
-                const T sigma_mu = sg * sg * sg * mu;
-                // ---- corrector ----
-                for (int k = 0; k < N; k++)
-                    if (has_box(k)) {
-                        const int e = k * 16 + lane;
-                        const T it_v = iter_at(k);
-                        const T lb = lo - it_v, ub = hi - it_v;
-                        const T tl = wI[IPM_TL * FS + e], tu = wI[IPM_TU * FS + e];
-                        const T ll = wI[IPM_LL * FS + e], lu = wI[IPM_LU * FS + e];
-                        const T gl = ll / tl, gu = lu / tu;
-                        const T cl = wI[IPM_CL * FS + e], cu = wI[IPM_CU * FS + e];
-                        bG[e] = ((sigma_mu - cu) / tu - gu * ub + lu) - ((sigma_mu - cl) / tl + gl * lb + ll);
-                    }
-                __syncwarp(mask);
-                if (!backward_sweep<T, false, 1, false>(c, N, lane, mask, sm, L, ws, WL, sTriv, nullptr)) { status = 4; break; }
-                n_fact++;
-                forward_sweep<T, false>(c, N, lane, mask, dx0, sm, L, ws, WL, lo, hi, gX, gU, nullptr, viol, bad, nact_l);
-                amax = T(1e30);
-                for (int k = 0; k < N; k++)
-                    if (has_box(k)) {
-                        const int e = k * 16 + lane;
-                        const T it_v = iter_at(k);
-                        const T lb = lo - it_v, ub = hi - it_v;
-                        const T zn = sDz[e];
-                        const T tl = wI[IPM_TL * FS + e], tu = wI[IPM_TU * FS + e];
-                        const T ll = wI[IPM_LL * FS + e], lu = wI[IPM_LU * FS + e];
-                        const T cl = wI[IPM_CL * FS + e], cu = wI[IPM_CU * FS + e];
-                        const T dtl = (zn - lb) - tl, dtu = (ub - zn) - tu;
-                        const T dll = (sigma_mu - cl) / tl - (ll / tl) * dtl - ll;
-                        const T dlu = (sigma_mu - cu) / tu - (lu / tu) * dtu - lu;
-                        if (dtl < T(0)) amax = fmin(amax, -tl / dtl);
-                        if (dtu < T(0)) amax = fmin(amax, -tu / dtu);
-                        if (dll < T(0)) amax = fmin(amax, -ll / dll);
-                        if (dlu < T(0)) amax = fmin(amax, -lu / dlu);
-                    }
-                const T alpha = fmin(T(1), T(0.995) * grp_min<T>(amax, mask));
-                for (int k = 0; k < N; k++)
-                    if (has_box(k)) {
-                        const int e = k * 16 + lane;
-                        const T it_v = iter_at(k);
-                        const T lb = lo - it_v, ub = hi - it_v;
-                        const T zn = sDz[e];
-                        const T tl = wI[IPM_TL * FS + e], tu = wI[IPM_TU * FS + e];
-                        const T ll = wI[IPM_LL * FS + e], lu = wI[IPM_LU * FS + e];
-                        const T cl = wI[IPM_CL * FS + e], cu = wI[IPM_CU * FS + e];
-                        const T dtl = (zn - lb) - tl, dtu = (ub - zn) - tu;
-                        const T dll = (sigma_mu - cl) / tl - (ll / tl) * dtl - ll;
-                        const T dlu = (sigma_mu - cu) / tu - (lu / tu) * dtu - lu;
-                        wI[IPM_TL * FS + e] = fmax(tl + alpha * dtl, c.t_min);
-                        wI[IPM_TU * FS + e] = fmax(tu + alpha * dtu, c.t_min);
-                        wI[IPM_LL * FS + e] = fmax(ll + alpha * dll, c.t_min);
-                        wI[IPM_LU * FS + e] = fmax(lu + alpha * dlu, c.t_min);
-                    }
-                if (lane < 14)
-                    for (int k = 0; k <= N; k++) {
-                        if (k == N && !isx) break;
-                        const int e = k * 16 + lane;
-                        wZ[e] += alpha * (sDz[e] - wZ[e]);
-                    }
-                res_lin *= (T(1) - alpha);
-                n_ipm++;
-                __syncwarp(mask);
-            }
-        }
-        if (!pol_ok && status == 0 && c.polish_max > 0) pol_ok = run_rounds(c.polish_max);
-        }
-        if (!pol_ok) {
-            // fall back to the interior-point iterate
+            const T a_aff = fmin(grp_min<T>(amax, mask), T(1));
+            T mua_l = T(0);
+            for (int k = 0; k < N; k++)
+                if (has_box(k)) {
+                    const int e = k * 16 + lane;
+                    const T it_v = iter_at(k);
+                    const T lb = lo - it_v, ub = hi - it_v;
+                    const T zn = sDz[e];
+                    const T tl = wI[IPM_TL * FS + e], tu = wI[IPM_TU * FS + e];
+                    const T ll = wI[IPM_LL * FS + e], lu = wI[IPM_LU * FS + e];
+                    const T dtl = (zn - lb) - tl, dtu = (ub - zn) - tu;
+                    const T dll = -(ll / tl) * dtl - ll, dlu = -(lu / tu) * dtu - lu;
+                    mua_l += (ll + a_aff * dll) * (tl + a_aff * dtl) + (lu + a_aff * dlu) * (tu + a_aff * dtu);
+                }
+            const T mu_aff = grp_sum<T>(mua_l, mask) * inv_m;
+            const T sg = mu_aff / mu;
+            const T sigma_mu = sg * sg * sg * mu;
+            // ---- corrector ----
+            for (int k = 0; k < N; k++)
+                if (has_box(k)) {
+                    const int e = k * 16 + lane;
+                    const T it_v = iter_at(k);
+                    const T lb = lo - it_v, ub = hi - it_v;
+                    const T tl = wI[IPM_TL * FS + e], tu = wI[IPM_TU * FS + e];
+                    const T ll = wI[IPM_LL * FS + e], lu = wI[IPM_LU * FS + e];
+                    const T gl = ll / tl, gu = lu / tu;
+                    const T cl = wI[IPM_CL * FS + e], cu = wI[IPM_CU * FS + e];
+                    bG[e] = ((sigma_mu - cu) / tu - gu * ub + lu) - ((sigma_mu - cl) / tl + gl * lb + ll);
+                }
+            __syncwarp(mask);
+            if (!backward_sweep<T, false, 1, false>(c, N, lane, mask, sm, L, ws, WL, sTriv, nullptr)) { ipm_broken = true; break; }
+            n_fact++;
+            forward_sweep<T, false>(c, N, lane, mask, dx0, sm, L, ws, WL, lo, hi, gX, gU, nullptr, viol, bad, nact_l);
+            amax = T(1e30);
+            for (int k = 0; k < N; k++)
+                if (has_box(k)) {
+                    const int e = k * 16 + lane;
+                    const T it_v = iter_at(k);
+                    const T lb = lo - it_v, ub = hi - it_v;
+                    const T zn = sDz[e];
+                    const T tl = wI[IPM_TL * FS + e], tu = wI[IPM_TU * FS + e];
+                    const T ll = wI[IPM_LL * FS + e], lu = wI[IPM_LU * FS + e];
+                    const T cl = wI[IPM_CL * FS + e], cu = wI[IPM_CU * FS + e];
+                    const T dtl = (zn - lb) - tl, dtu = (ub - zn) - tu;
+                    const T dll = (sigma_mu - cl) / tl - (ll / tl) * dtl - ll;
+                    const T dlu = (sigma_mu - cu) / tu - (lu / tu) * dtu - lu;
+                    if (dtl < T(0)) amax = fmin(amax, -tl / dtl);
+                    if (dtu < T(0)) amax = fmin(amax, -tu / dtu);
+                    if (dll < T(0)) amax = fmin(amax, -ll / dll);
+                    if (dlu < T(0)) amax = fmin(amax, -lu / dlu);
+                }
+            const T alpha = fmin(T(1), T(0.995) * grp_min<T>(amax, mask));
+            for (int k = 0; k < N; k++)
+                if (has_box(k)) {
+                    const int e = k * 16 + lane;
+                    const T it_v = iter_at(k);
+                    const T lb = lo - it_v, ub = hi - it_v;
+                    const T zn = sDz[e];
+                    const T tl = wI[IPM_TL * FS + e], tu = wI[IPM_TU * FS + e];
+                    const T ll = wI[IPM_LL * FS + e], lu = wI[IPM_LU * FS + e];
+                    const T cl = wI[IPM_CL * FS + e], cu = wI[IPM_CU * FS + e];
+                    const T dtl = (zn - lb) - tl, dtu = (ub - zn) - tu;
+                    const T dll = (sigma_mu - cl) / tl - (ll / tl) * dtl - ll;
+                    const T dlu = (sigma_mu - cu) / tu - (lu / tu) * dtu - lu;
+                    wI[IPM_TL * FS + e] = fmax(tl + alpha * dtl, c.t_min);
+                    wI[IPM_TU * FS + e] = fmax(tu + alpha * dtu, c.t_min);
+                    wI[IPM_LL * FS + e] = fmax(ll + alpha * dll, c.t_min);
+                    wI[IPM_LU * FS + e] = fmax(lu + alpha * dlu, c.t_min);
+                }
             if (lane < 14)
                 for (int k = 0; k <= N; k++) {
                     if (k == N && !isx) break;
-                    sDz[k * 16 + lane] = wZ[k * 16 + lane];
+                    const int e = k * 16 + lane;
+                    wZ[e] += alpha * (sDz[e] - wZ[e]);
                 }
-            if (!ipm_ok && status == 0) status = 4;
+            res_lin *= (T(1) - alpha);
+            n_ipm++;
+            __syncwarp(mask);
         }
-        __syncwarp(mask);
+        if (!pol_ok && status == 0 && c.polish_max > 0 && n_ipm > 0) pol_ok = rounds_from_ipm(c.polish_max);
+        if (ipm_broken && !pol_ok) status = 4;
+    }
+    if (pol_ok && status == 0) {
+        // Defect correction for pinned velocities.  Holding a velocity component through the previous stage's inputs is a
+        // stiff feedback (gains ~ 1e2, cost-to-go ~ 1e4 against stage weights ~ 10), and the Schur complement of the next
+        // stage loses about three digits to it: fp32 ends 2e-4 off the solution, fp64 5e-13.  One more sweep with the
+        // same factorisation structure, linearised AT the computed step (iterate advanced in shared memory, stage
+        // residuals b zeroed, cost gradient and pinned values re-evaluated there), solves for the small remainder.
+        // (The fp64 build takes the sweep whenever anything is pinned: it also removes the O(multiplier / big) offset of
+        // the penalty that pins the inputs, 1e-8 on u0 otherwise.)
+        const bool any_pin = (as.lo_m.w0 | as.lo_m.w1 | as.hi_m.w0 | as.hi_m.w1) != 0ull;
+        if (__any_sync(mask, any_pin && (isv || (sizeof(T) == 8 && isu)))) {
+            T* sY = sm + L.oY;
+            if (lane < 14)
+                for (int k = 0; k <= N; k++) {
+                    if (k == N && !isx) break;
+                    const T dz = sDz[k * 16 + lane];
+                    if (isx) sX[k * NX + lane] += dz;
+                    else sU[k * NU + (lane - 10)] += dz;
+                    if (lane < 6 || lane >= 10) sY[k * SYS + lane] += dz;  // residual records are linear in the iterate
+                }
+            __syncwarp(mask);
+            if (backward_sweep<T, false, 2, false>(c, N, lane, mask, sm, L, ws, WL, sTriv, &as, true)) {
+                n_fact++;
+                forward_sweep<T, false>(c, N, lane, mask, T(0), sm, L, ws, WL, lo, hi, gX, gU, nullptr, viol, bad, nact_l, true, true);
+                if (isu || isv)
+                    for (int k = 0; k < N; k++) {
+                        const T it_v = iter_at(k);
+                        if (as.lo_m.test(k)) sDz[k * 16 + lane] = lo - it_v;
+                        if (as.hi_m.test(k)) sDz[k * 16 + lane] = hi - it_v;
+                    }
+            } else {
+                // keep the unrefined solution: the step relative to the advanced iterate is zero
+                if (lane < 14)
+                    for (int k = 0; k <= N; k++) sDz[k * 16 + lane] = T(0);
+            }
+            __syncwarp(mask);
+        }
+    }
+    if (!pol_ok) {
+        // fall back to the interior-point iterate
+        if (lane < 14)
+            for (int k = 0; k <= N; k++) {
+                if (k == N && !isx) break;
+                sDz[k * 16 + lane] = wZ[k * 16 + lane];
+            }
+        if (!ipm_ok && status == 0) status = 4;
+    }
+    __syncwarp(mask);
     // ---- write back: full step, overwrite the tentative iterate of the unconstrained sweep ----
     bool bad2 = false;
     nact_l = 0;
-    StageMask fin_lo, fin_hi;  // inputs that end on a bound: the next solve's first guess
+    StageMask fin_lo, fin_hi;  // variables that end on a bound: the next solve's first guess
     const T as_eps = (sizeof(T) == 4 ? T(1e-5) : T(1e-11)) * (T(1) + fabs(lo) + fabs(hi));
     if (lane < 14)
         for (int k = 0; k <= N; k++) {
@@ -1054,8 +1183,8 @@ __device__ __noinline__ void constrained_qp(const RtiCfg<T>& c, int lane, unsign
             bad2 |= !(fabs(v) <= T(1e30));
             if (has_box(k)) nact_l += (v <= lo) + (v >= hi);
             // (it + (bound - it) need not round back to the bound exactly: compare with a few ulps of slack)
-            if (isu && v <= lo + as_eps) fin_lo.set(k);
-            else if (isu && v >= hi - as_eps) fin_hi.set(k);
+            if (has_box(k) && v <= lo + as_eps) fin_lo.set(k);
+            else if (has_box(k) && v >= hi - as_eps) fin_hi.set(k);
         }
     bad2 = __any_sync(mask, bad2);
     const int nact = (int)grp_sum<float>((float)nact_l, mask);
@@ -1073,9 +1202,9 @@ __device__ __noinline__ void constrained_qp(const RtiCfg<T>& c, int lane, unsign
     for (int i = lane; i < (N + 1) * NX; i += GL) gX[i] = sX[i];
     for (int i = lane; i < N * NU; i += GL) gU[i] = sU[i];
     if (gu0 && lane < NU) gu0[lane] = sU[lane];
-    if (g_as && isu) {
-        const bool keep = (status == 0);
-        unsigned long long* p = g_as + (lane - 10) * 4;
+    if (isu || isv) {
+        const bool keep = keep_set && (status == 0);
+        unsigned long long* p = g_as + as_owner(lane) * 4;
         p[0] = keep ? fin_lo.w0 : 0ull; p[1] = keep ? fin_lo.w1 : 0ull; p[2] = keep ? fin_hi.w0 : 0ull; p[3] = keep ? fin_hi.w1 : 0ull;
     }
     if (lane == 0) {
@@ -1088,12 +1217,95 @@ __device__ __noinline__ void constrained_qp(const RtiCfg<T>& c, int lane, unsign
     __syncwarp(mask);
 }
 
-constexpr int RTI_CTA = 64;  // threads per CTA of the nominal launch (4 problems)
+constexpr int RTI_CTA = 64;  // threads per CTA of both launches (4 problems)
+constexpr int QUEUE_SWEPT = 1 << 30;  // queue entry flag: the unconstrained sweep of this solve has run (statistics)
 
+// Stage one problem record in shared memory with asynchronous copies (one wait): iterate, then either the stored
+// yref / p (kFused == false) or -- controller.update()'s 42 solver.set calls, nmpc_body_rate_ctl.py:95-104 -- yref_k =
+// [xr_k; ur_k], p_k = [xr_k[6:10]; f_k] built from (xr, ur, f) and persisted to yref_w / par_w as if set stage by stage.
+template <typename T>
+__device__ __forceinline__ void stage_problem(const RtiArgs<T>& a, int N, const SmemLayout& L, int lane, unsigned mask, T* sm, int prob,
+                                              bool fused) {
+    constexpr int E2 = 8 / (int)sizeof(T);  // elements per 8-byte copy (records are 8-byte aligned)
+    T* sX = sm + L.oX;
+    T* sU = sm + L.oU;
+    T* sY = sm + L.oY;
+    T* sPar = sm + L.oPar;
+    const T* gX = a.X + (size_t)prob * (N + 1) * NX;
+    const T* gU = a.U + (size_t)prob * N * NU;
+    for (int i = lane; i < (N + 1) * NX / E2; i += GL) cp_async<8>(sX + E2 * i, gX + E2 * i);
+    for (int i = lane; i < N * NU / E2; i += GL) cp_async<8>(sU + E2 * i, gU + E2 * i);
+    if (!fused) {
+        const T* gY = a.yref + (size_t)prob * (N + 1) * NYS;
+        const T* gP = a.par + (size_t)prob * (N + 1) * NPS;
+        for (int i = lane; i < (N + 1) * (NYS / E2); i += GL) {
+            const int k = i / (NYS / E2), q = i - k * (NYS / E2);
+            cp_async<8>(sY + k * SYS + E2 * q, gY + k * NYS + E2 * q);
+        }
+        for (int i = lane; i < (N + 1) * NPS / E2; i += GL) cp_async<8>(sPar + E2 * i, gP + E2 * i);
+    } else {
+        const T* gxr = a.xr + (size_t)prob * (N + 1) * NX;
+        const T* gur = a.ur + (size_t)prob * N * NU;
+        for (int i = lane; i < (N + 1) * (NX / E2); i += GL) {
+            const int k = i / (NX / E2), q = (i - k * (NX / E2)) * E2;
+            cp_async<8>(sY + k * SYS + q, gxr + k * NX + q);
+            if (q >= 6) cp_async<8>(sPar + k * NPS + q - 6, gxr + k * NX + q);
+        }
+        for (int i = lane; i < N * (NU / E2); i += GL) {
+            const int k = i / (NU / E2), q = (i - k * (NU / E2)) * E2;
+            cp_async<8>(sY + k * SYS + NX + q, gur + k * NU + q);
+        }
+        if (lane < NU) sY[N * SYS + NX + lane] = T(0);
+        if (!a.f) {
+            for (int i = lane; i < (N + 1) * 4; i += GL) sPar[(i >> 2) * NPS + 4 + (i & 3)] = T(0);
+        }
+    }
+    for (int i = lane; i < (N + 1) * 2; i += GL) sY[(i >> 1) * SYS + NYS + (i & 1)] = T(0);
+    if (fused && a.f) {
+        // The forces come last: when this kernel was launched as a programmatic dependent of the kernel that
+        // produces them (ndp_update_ex, NDP_UPDATE_F_FROM_PREVIOUS_KERNEL), everything above -- which only
+        // reads older data -- has run under that kernel's tail; wait for its completion here (a no-op for an
+        // ordinary launch).
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        const T* gf = a.f + (size_t)prob * (N + 1) * 3;
+        for (int i = lane; i < (N + 1) * 3; i += GL) {
+            const int k = i / 3, m = i - k * 3;
+            cp_async<(int)sizeof(T)>(sPar + k * NPS + 4 + m, gf + i);
+        }
+        for (int k = lane; k <= N; k += GL) sPar[k * NPS + 7] = T(0);
+    }
+    cp_async_wait_all();
+    __syncwarp(mask);
+    if (fused) {
+        // persist yref / p as if set stage by stage (a later plain solve, a get, or the constrained kernel sees them)
+        T* wY = a.yref_w + (size_t)prob * (N + 1) * NYS;
+        T* wP = a.par_w + (size_t)prob * (N + 1) * NPS;
+        for (int i = lane; i < (N + 1) * NYS; i += GL) {
+            const int k = i / NYS;
+            wY[i] = sm[L.oY + k * SYS + (i - k * NYS)];
+        }
+        for (int i = lane; i < (N + 1) * NPS; i += GL) wP[i] = sm[L.oPar + i];
+        __syncwarp(mask);
+    }
+}
+
+// per-lane box of the variable this lane owns (lanes 3..5: v, lanes 10..13: u)
+template <typename T>
+__device__ __forceinline__ void lane_box(const RtiCfg<T>& c, int lane, T& lo, T& hi) {
+    lo = T(-1e30); hi = T(1e30);
+#pragma unroll
+    for (int m = 0; m < 3; m++)
+        if (lane == 3 + m) { lo = c.vmin[m]; hi = c.vmax[m]; }
+#pragma unroll
+    for (int m = 0; m < 4; m++)
+        if (lane == 10 + m) { lo = c.umin[m]; hi = c.umax[m]; }
+}
+
+// ---- nominal kernel: one RTI step per problem with the unconstrained Riccati sweep; a step that leaves its box is
+// handed over to rti_constrained_kernel (queue), with global memory still holding the old iterate ----
 // kLat: the latency build (fp32 only) -- same code with half the resident CTAs per SM, i.e. twice the registers,
 // which ptxas spends on instruction-level parallelism.  Chosen when the whole batch is resident at that occupancy
-// (B <= 148 * 4 * 4 problems): a lone group's solve drops from ~63 to ~55 us and an active-set round from 36 to 31 us,
-// while at B = 4096 the 8-CTA build wins (77 vs 86 us) because the batch then fits one wave.
+// (B <= 148 * 4 * 4 problems).
 template <typename T, int kN, bool kLat>
 __global__ void __launch_bounds__(RTI_CTA, (sizeof(T) == 4) ? (kLat ? 4 : 8) : 3) rti_step_kernel(const __grid_constant__ RtiCfg<T> c, const RtiArgs<T> a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1109,132 +1321,96 @@ __global__ void __launch_bounds__(RTI_CTA, (sizeof(T) == 4) ? (kLat ? 4 : 8) : 3
     T* ws = a.ws + (size_t)(blockIdx.x * ppc + grp) * a.ws_stride;
     T* sX = sm + L.oX;
     T* sU = sm + L.oU;
-    T* sDz = sm + L.oDz;
     for (int i = threadIdx.x; i < 10 * TLD; i += blockDim.x) {
         const int r = i / TLD, cc = i - r * TLD;
         sTriv[i] = (cc < 6 && cc == r) ? T(1) : ((cc >= 3 && cc < 6 && cc - 3 == r) ? c.h : T(0));
     }
     for (int i = lane; i < 20 * TLD; i += GL) sm[L.oT0 + i] = T(0);
     __syncthreads();
-
-    // per-lane box of the variable this lane owns (lanes 3..5: v, lanes 10..13: u)
-    T lo = T(-1e30), hi = T(1e30);
-#pragma unroll
-    for (int m = 0; m < 3; m++)
-        if (lane == 3 + m) { lo = c.vmin[m]; hi = c.vmax[m]; }
-#pragma unroll
-    for (int m = 0; m < 4; m++)
-        if (lane == 10 + m) { lo = c.umin[m]; hi = c.umax[m]; }
-    const bool isx = lane < 10;
+    T lo, hi;
+    lane_box<T>(c, lane, lo, hi);
+    const bool isx = lane < 10, isu = (lane >= 10 && lane < 14), isv = (lane >= 3 && lane < 6);
 
     for (int prob = blockIdx.x * ppc + grp; prob < a.B; prob += gridDim.x * ppc) {
         T* gX = a.X + (size_t)prob * (N + 1) * NX;
         T* gU = a.U + (size_t)prob * N * NU;
-        // ---- stage the problem record in shared memory (asynchronous copies, one wait) ----
-        {
-            constexpr int E2 = 8 / (int)sizeof(T);  // elements per 8-byte copy (records are 8-byte aligned)
-            T* sY = sm + L.oY;
-            T* sPar = sm + L.oPar;
-            for (int i = lane; i < (N + 1) * NX / E2; i += GL) cp_async<8>(sX + E2 * i, gX + E2 * i);
-            for (int i = lane; i < N * NU / E2; i += GL) cp_async<8>(sU + E2 * i, gU + E2 * i);
-            if (a.xr == nullptr) {
-                const T* gY = a.yref + (size_t)prob * (N + 1) * NYS;
-                const T* gP = a.par + (size_t)prob * (N + 1) * NPS;
-                for (int i = lane; i < (N + 1) * (NYS / E2); i += GL) {
-                    const int k = i / (NYS / E2), q = i - k * (NYS / E2);
-                    cp_async<8>(sY + k * SYS + E2 * q, gY + k * NYS + E2 * q);
-                }
-                for (int i = lane; i < (N + 1) * NPS / E2; i += GL) cp_async<8>(sPar + E2 * i, gP + E2 * i);
-            } else {
-                // yref_k = [xr_k; ur_k], p_k = [xr_k[6:10]; f_k]   (nmpc_body_rate_ctl.py:95-104)
-                const T* gxr = a.xr + (size_t)prob * (N + 1) * NX;
-                const T* gur = a.ur + (size_t)prob * N * NU;
-                for (int i = lane; i < (N + 1) * (NX / E2); i += GL) {
-                    const int k = i / (NX / E2), q = (i - k * (NX / E2)) * E2;
-                    cp_async<8>(sY + k * SYS + q, gxr + k * NX + q);
-                    if (q >= 6) cp_async<8>(sPar + k * NPS + q - 6, gxr + k * NX + q);
-                }
-                for (int i = lane; i < N * (NU / E2); i += GL) {
-                    const int k = i / (NU / E2), q = (i - k * (NU / E2)) * E2;
-                    cp_async<8>(sY + k * SYS + NX + q, gur + k * NU + q);
-                }
-                if (lane < NU) sY[N * SYS + NX + lane] = T(0);
-                if (!a.f) {
-                    for (int i = lane; i < (N + 1) * 4; i += GL) sPar[(i >> 2) * NPS + 4 + (i & 3)] = T(0);
-                }
-            }
-            for (int i = lane; i < (N + 1) * 2; i += GL) sY[(i >> 1) * SYS + NYS + (i & 1)] = T(0);
-            if (a.xr != nullptr && a.f) {
-                // The forces come last: when this kernel was launched as a programmatic dependent of the kernel that
-                // produces them (ndp_update_ex, NDP_UPDATE_F_FROM_PREVIOUS_KERNEL), everything above -- which only
-                // reads older data -- has run under that kernel's tail; wait for its completion here (a no-op for an
-                // ordinary launch).
-                asm volatile("griddepcontrol.wait;" ::: "memory");
-                const T* gf = a.f + (size_t)prob * (N + 1) * 3;
-                for (int i = lane; i < (N + 1) * 3; i += GL) {
-                    const int k = i / 3, m = i - k * 3;
-                    cp_async<(int)sizeof(T)>(sPar + k * NPS + 4 + m, gf + i);
-                }
-                for (int k = lane; k <= N; k += GL) sPar[k * NPS + 7] = T(0);
-            }
-        }
+        stage_problem<T>(a, N, L, lane, mask, sm, prob, a.xr != nullptr);
         const T x0v = isx ? a.x0[(size_t)prob * NX + lane] : T(0);
-        // active set the previous solve of this problem ended with (first guess of this one)
-        unsigned long long* g_as = a.as_store ? a.as_store + (size_t)prob * 16 : nullptr;
+        // a set left by the previous solve of this problem (active_set_warm): straight to the constrained kernel
+        unsigned long long* g_as = a.as_store + (size_t)prob * (AS_OWNERS * 4);
         unsigned long long as_any = 0ull;
-        if (g_as && lane >= 10 && lane < 14) {
-            const ulonglong2 m0 = *reinterpret_cast<const ulonglong2*>(g_as + (lane - 10) * 4);
-            const ulonglong2 m1 = *reinterpret_cast<const ulonglong2*>(g_as + (lane - 10) * 4 + 2);
+        if (a.as_warm && (isu || isv)) {
+            const ulonglong2 m0 = *reinterpret_cast<const ulonglong2*>(g_as + as_owner(lane) * 4);
+            const ulonglong2 m1 = *reinterpret_cast<const ulonglong2*>(g_as + as_owner(lane) * 4 + 2);
             as_any = m0.x | m0.y | m1.x | m1.y;
         }
-        cp_async_wait_all();
-        __syncwarp(mask);
-        if (a.xr != nullptr) {
-            // persist yref / p as if set stage by stage (a later plain solve or get sees them)
-            T* wY = a.yref_w + (size_t)prob * (N + 1) * NYS;
-            T* wP = a.par_w + (size_t)prob * (N + 1) * NPS;
-            for (int i = lane; i < (N + 1) * NYS; i += GL) {
-                const int k = i / NYS;
-                wY[i] = sm[L.oY + k * SYS + (i - k * NYS)];
-            }
-            for (int i = lane; i < (N + 1) * NPS; i += GL) wP[i] = sm[L.oPar + i];
-            __syncwarp(mask);
-        }
-        cost_records<T>(N, lane, sm + L.oY, sX, sU, sm + L.oPar);
-        __syncwarp(mask);
-        const T dx0 = isx ? x0v - sX[lane] : T(0);
-
-        int status = 0;
-
-        // ---- preparation + unconstrained feedback; the step is accepted on the fly ----
         const bool warm = __any_sync(mask, as_any != 0ull);
         bool ok = true, viol = false, bad = false;
         int nact_l = 0;
         if (!warm) {
+            cost_records<T>(N, lane, sm + L.oY, sX, sU, sm + L.oPar);
+            __syncwarp(mask);
+            const T dx0 = isx ? x0v - sX[lane] : T(0);
+            // ---- preparation + unconstrained feedback; the step is accepted on the fly ----
             ok = backward_sweep<T, true, 0, false>(c, N, lane, mask, sm, L, ws, WL, sTriv, nullptr);
-            forward_sweep<T, true>(c, N, lane, mask, dx0, sm, L, ws, WL, lo, hi, gX, gU, a.u0 ? a.u0 + (size_t)prob * NU : nullptr, viol, bad,
-                                   nact_l, prob + (int)gridDim.x * ppc < a.B);
+            forward_sweep<T, true>(c, N, lane, mask, dx0, sm, L, ws, WL, lo, hi, gX, gU, nullptr, viol, bad, nact_l,
+                                   prob + (int)gridDim.x * ppc < a.B);
         }
-        if (warm || (ok && viol)) {
-            // Called through an opaque function pointer: ptxas then allocates the nominal path against the plain ABI
-            // instead of against this callee's register use (measured: 77.2 us vs 81-84 us per launch at B = 4096
-            // with a direct call, and the nominal path no longer moves when the constrained path changes).
-            auto fn = &constrained_qp<T, kN>;
-            asm volatile("" : "+l"(fn));
-            fn(c, lane, mask, sm, ws, sTriv, dx0, lo, hi, gX, gU, (a.xr != nullptr ? a.yref_w : a.yref) + (size_t)prob * (N + 1) * NYS,
-               a.u0 ? a.u0 + (size_t)prob * NU : nullptr, a.status + prob, a.stats + (size_t)prob * 4, g_as, warm);
+        if (warm || (ok && viol && !bad)) {
+            if (!warm && (isu || isv)) {
+                // the bounds the unconstrained step violates seed the active-set rounds
+                StageMask m_lo, m_hi;
+                for (int k = isv ? 1 : 0; k < N; k++) {
+#ifdef NDP_DIRECT_STORE
+                    const T v = isu ? gU[k * NU + (lane - 10)] : gX[k * NX + lane];  // this lane's own stores
+#else
+                    const T v = isu ? sU[k * NU + (lane - 10)] : sX[k * NX + lane];
+#endif
+                    if (v < lo) m_lo.set(k);
+                    else if (v > hi) m_hi.set(k);
+                }
+                unsigned long long* p = g_as + as_owner(lane) * 4;
+                p[0] = m_lo.w0; p[1] = m_lo.w1; p[2] = m_hi.w0; p[3] = m_hi.w1;
+            }
+            __syncwarp(mask);
+#ifdef NDP_DIRECT_STORE
+            if (!warm) {  // put the old iterate back (it is still in shared memory)
+                for (int i = lane; i < (N + 1) * NX; i += GL) gX[i] = sX[i];
+                for (int i = lane; i < N * NU; i += GL) gU[i] = sU[i];
+            }
+#endif
+            if (lane == 0) {
+                __threadfence();
+                const int slot = atomicAdd(a.qctl, 1);
+                a.queue[slot] = prob | (warm ? 0 : QUEUE_SWEPT);
+            }
         } else {
-            // the forward sweep already stored the new iterate and u0
+            int status = 0;
             if (!ok) status = 4;
-            const int nact = (int)grp_sum<float>((float)nact_l, mask);
             if (bad) status = 1;
-            if (status != 0) {
-                // failed factorisation / NaN step: put the previous iterate back (it is still in shared memory) and
-                // return the previous first input -- acados SQP_RTI does not update the iterate when the QP fails
+            const int nact = (int)grp_sum<float>((float)nact_l, mask);
+#ifdef NDP_DIRECT_STORE
+            if (status == 0) {
+                if (a.u0 && lane < NU) a.u0[(size_t)prob * NU + lane] = gU[lane];
+            } else {
                 for (int i = lane; i < (N + 1) * NX; i += GL) gX[i] = sX[i];
                 for (int i = lane; i < N * NU; i += GL) gU[i] = sU[i];
                 if (a.u0 && lane < NU) a.u0[(size_t)prob * NU + lane] = sU[lane];
             }
+#else
+            if (status == 0) {
+                // accepted: the new iterate goes out with 8-byte stores
+                constexpr int E2 = 8 / (int)sizeof(T);
+                typedef typename std::conditional<sizeof(T) == 4, float2, double>::type V2;
+                for (int i = lane; i < (N + 1) * NX / E2; i += GL) reinterpret_cast<V2*>(gX)[i] = reinterpret_cast<const V2*>(sX)[i];
+                for (int i = lane; i < N * NU / E2; i += GL) reinterpret_cast<V2*>(gU)[i] = reinterpret_cast<const V2*>(sU)[i];
+                if (a.u0 && lane < NU) a.u0[(size_t)prob * NU + lane] = sU[lane];
+            } else if (a.u0 && lane < NU) {
+                // failed factorisation / NaN step: global memory still holds the previous iterate (acados SQP_RTI does not
+                // update it when the QP fails); return the previous first input
+                a.u0[(size_t)prob * NU + lane] = gU[lane];
+            }
+#endif
             if (lane == 0) {
                 a.status[prob] = status;
                 a.stats[prob * 4 + 0] = 1;
@@ -1244,6 +1420,65 @@ __global__ void __launch_bounds__(RTI_CTA, (sizeof(T) == 4) ? (kLat ? 4 : 8) : 3
             }
         }
         __syncwarp(mask);
+    }
+}
+
+// ---- constrained kernel: the problems the nominal kernel handed over, pulled from the queue by 16-lane groups (so a
+// hard problem never blocks the others) with a register budget of its own ----
+template <typename T, int kN>
+__global__ void __launch_bounds__(RTI_CTA, (sizeof(T) == 4) ? 4 : 2) rti_constrained_kernel(const __grid_constant__ RtiCfg<T> c, const RtiArgs<T> a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // launched as a programmatic dependent of the nominal kernel: wait for its queue (a no-op for an ordinary launch)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const int count = *reinterpret_cast<volatile int*>(a.qctl);
+    const int N = (kN > 0) ? kN : c.N;
+    const SmemLayout L(N);
+    const int lane = threadIdx.x & 15;
+    const int grp = threadIdx.x >> 4;
+    const unsigned mask = 0xFFFFu << (threadIdx.x & 16);
+    const int ppc = blockDim.x >> 4;
+    if (count > 0) {
+        T* sTriv = reinterpret_cast<T*>(smem_raw);
+        T* sm = sTriv + 10 * TLD + (size_t)grp * L.total;
+        T* ws = a.ws + (size_t)(blockIdx.x * ppc + grp) * a.ws_stride;
+        for (int i = threadIdx.x; i < 10 * TLD; i += blockDim.x) {
+            const int r = i / TLD, cc = i - r * TLD;
+            sTriv[i] = (cc < 6 && cc == r) ? T(1) : ((cc >= 3 && cc < 6 && cc - 3 == r) ? c.h : T(0));
+        }
+        for (int i = lane; i < 20 * TLD; i += GL) sm[L.oT0 + i] = T(0);
+        __syncthreads();
+        T lo, hi;
+        lane_box<T>(c, lane, lo, hi);
+        const bool isx = lane < 10;
+        RtiArgs<T> as_plain = a;  // the references were persisted by the nominal kernel: stage the stored yref / p
+        as_plain.xr = nullptr;
+        for (;;) {
+            int slot = 0;
+            if (lane == 0) slot = atomicAdd(a.qctl + 1, 1);
+            slot = __shfl_sync(mask, slot, 0, GL);
+            if (slot >= count) break;
+            const int entry = a.queue[slot];
+            const int prob = entry & (QUEUE_SWEPT - 1);
+            stage_problem<T>(as_plain, N, L, lane, mask, sm, prob, false);
+            cost_records<T>(N, lane, sm + L.oY, sm + L.oX, sm + L.oU, sm + L.oPar);
+            __syncwarp(mask);
+            const T dx0 = isx ? a.x0[(size_t)prob * NX + lane] - sm[L.oX + lane] : T(0);
+            constrained_qp<T, kN>(c, lane, mask, sm, ws, sTriv, dx0, lo, hi, a.X + (size_t)prob * (N + 1) * NX, a.U + (size_t)prob * N * NU,
+                                  a.u0 ? a.u0 + (size_t)prob * NU : nullptr, a.status + prob, a.stats + (size_t)prob * 4,
+                                  a.as_store + (size_t)prob * (AS_OWNERS * 4), a.as_warm != 0, (entry & QUEUE_SWEPT) ? 1 : 0);
+            // the tiles' zero pad columns (the sweeps of this problem may have run the ring over them)
+            for (int i = lane; i < 20; i += GL) { T* q = sm + L.oT0 + i * TLD + 9; q[0] = T(0); q[1] = T(0); q[2] = T(0); }
+            __syncwarp(mask);
+        }
+    }
+    // the last CTA out re-arms the queue for the next solve
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(a.qctl + 2, 1) == (int)gridDim.x - 1) {
+            a.qctl[0] = 0; a.qctl[1] = 0; a.qctl[2] = 0;
+            __threadfence();
+        }
     }
 }
 

@@ -34,6 +34,7 @@ class OrcCfg(C.Structure):
         ("mu0", C.c_double),
         ("t_floor", C.c_double),
         ("polish", C.c_int),
+        ("pdas_first", C.c_int),
     ]
 
 
@@ -46,7 +47,7 @@ def build(force: bool = False) -> str:
     return out
 
 
-def make_cfg(N=20, T=None, tol=None, tol_mu=None, max_iter=100, u_min=None, u_max=None, v_min=None, v_max=None, polish=None) -> OrcCfg:
+def make_cfg(N=20, T=None, tol=None, tol_mu=None, max_iter=100, u_min=None, u_max=None, v_min=None, v_max=None, polish=None, pdas_first=0) -> OrcCfg:
     """Constants of params/nmpc_params.py:9-35 and params/fhnp_params.py:9-19.
 
     Default (tol=None): interior-point iterations to 1e-9 -- far enough to identify the active set while the
@@ -76,6 +77,7 @@ def make_cfg(N=20, T=None, tol=None, tol_mu=None, max_iter=100, u_min=None, u_ma
     c.tol, c.max_iter, c.mu0, c.t_floor = tol, max_iter, 10.0, 0.1
     c.tol_mu = tol if tol_mu is None else tol_mu
     c.polish = int(polish)
+    c.pdas_first = int(pdas_first)
     return c
 
 

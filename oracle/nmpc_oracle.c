@@ -55,6 +55,8 @@ typedef struct {
     double mu0;       /* IPM cold start */
     double t_floor;   /* slack floor at cold start */
     int polish;       /* > 0: after the IPM, up to `polish` exact active-set rounds (see orc_polish) */
+    int pdas_first;   /* > 0: up to `pdas_first` active-set rounds from the unconstrained step's violated bounds BEFORE
+                         the IPM (the route the CUDA kernel takes first); the IPM runs only if they find no fixed point */
 } orc_cfg;
 
 /* xdot = f(x,u;fd)   ndp_nmpc_body_rate_ctl.py:151-162 */
@@ -303,6 +305,9 @@ static void riccati_forward(const orc_cfg* c, const orc_ws* w, real (*dx)[NX], r
  *     (needs E B_free of full row rank: collective thrust and the two tilt rates move the velocity),
  * followed by primal-dual active-set updates (release on a wrong multiplier sign, add on a violated
  * bound) until the set is a fixed point -- which is the KKT point of the QP, with no barrier floor. */
+#ifndef ORC_PDAS_FREE
+#define ORC_PDAS_FREE 1000
+#endif
 typedef struct {
     signed char au[NMAX][NU];       /* -1 lower, +1 upper, 0 free */
     signed char av[NMAX + 1][NBX];  /* stages 1..N-1 */
@@ -535,25 +540,60 @@ static int orc_polish(const orc_cfg* c, orc_ws* w, orc_aset* as, real (*dx)[NX],
     memcpy(tx[0], dx[0], sizeof(real) * NX);
     const real eps = (sizeof(real) == 8) ? (real)1e-11 : (real)1e-5;
     int fixed = 0, r = 0;
+    unsigned long long hist[64];
+    int n_hist = 0, cycling = 0;
     for (r = 0; r < max_rounds; r++) {
         memset(nu, 0, sizeof(real) * N * NBX);
         if (orc_eq_solve(c, w, e, as, tx, tu, lam, nu)) break;
         int changed = 0;
+        /* Rounds 0..ORC_PDAS_FREE-1: plain primal-dual update (release every wrong-signed multiplier, add every violated
+         * bound).  That iteration can cycle between a few sets; later rounds therefore release only the single most
+         * wrong-signed multiplier, and only once no bound is violated. */
+        /* cycle detection: hash of the set each round; a repeat switches to the damped update for good */
+        {
+            unsigned long long hsh = 1469598103934665603ull;
+            for (int k = 0; k < N; k++) {
+                for (int m = 0; m < NU; m++) hsh = (hsh ^ (unsigned long long)(as->au[k][m] + 2)) * 1099511628211ull;
+                for (int m = 0; m < NBX; m++) hsh = (hsh ^ (unsigned long long)(as->av[k][m] + 5)) * 1099511628211ull;
+            }
+            for (int q = 0; q < n_hist; q++) if (hist[q] == hsh) cycling = 1;
+            if (n_hist < 64) hist[n_hist++] = hsh;
+        }
+        const int damped = cycling || r >= ORC_PDAS_FREE;
+        int n_viol = 0;
+        real worst = 0; int wk = -1, wm = -1, wx = 0;
         for (int k = 0; k < N; k++) {
             for (int m = 0; m < NU; m++) {
                 if (as->au[k][m]) {
                     /* equality-form multiplier: upper bound needs lam >= 0, lower bound lam <= 0 */
-                    if ((as->au[k][m] > 0 ? lam[k][m] : -lam[k][m]) < 0) { as->au[k][m] = 0; changed = 1; }
-                } else if (tu[k][m] > w->ubu[k][m] + eps) { as->au[k][m] = 1; changed = 1; }
-                else if (tu[k][m] < w->lbu[k][m] - eps) { as->au[k][m] = -1; changed = 1; }
+                    real v = as->au[k][m] > 0 ? lam[k][m] : -lam[k][m];
+                    if (v < 0) {
+                        if (!damped) { as->au[k][m] = 0; changed = 1; }
+                        else if (v < worst) { worst = v; wk = k; wm = m; wx = 0; }
+                    }
+                } else if (tu[k][m] > w->ubu[k][m] + eps) { as->au[k][m] = 1; changed = 1; n_viol++; }
+                else if (tu[k][m] < w->lbu[k][m] - eps) { as->au[k][m] = -1; changed = 1; n_viol++; }
             }
             if (k + 1 <= N - 1)
                 for (int m = 0; m < NBX; m++) {
                     if (as->av[k + 1][m]) {
-                        if ((as->av[k + 1][m] > 0 ? nu[k][m] : -nu[k][m]) < 0) { as->av[k + 1][m] = 0; changed = 1; }
-                    } else if (tx[k + 1][3 + m] > w->ubx[k + 1][m] + eps) { as->av[k + 1][m] = 1; changed = 1; }
-                    else if (tx[k + 1][3 + m] < w->lbx[k + 1][m] - eps) { as->av[k + 1][m] = -1; changed = 1; }
+                        real v = as->av[k + 1][m] > 0 ? nu[k][m] : -nu[k][m];
+                        if (v < 0) {
+                            if (!damped) { as->av[k + 1][m] = 0; changed = 1; }
+                            else if (v < worst) { worst = v; wk = k + 1; wm = m; wx = 1; }
+                        }
+                    } else if (tx[k + 1][3 + m] > w->ubx[k + 1][m] + eps) { as->av[k + 1][m] = 1; changed = 1; n_viol++; }
+                    else if (tx[k + 1][3 + m] < w->lbx[k + 1][m] - eps) { as->av[k + 1][m] = -1; changed = 1; n_viol++; }
                 }
+        }
+        if (damped && n_viol == 0 && wk >= 0) {
+            if (getenv("ORC_REL_ALL")) {
+                for (int k = 0; k < N; k++) {
+                    for (int m = 0; m < NU; m++) if (as->au[k][m] && (as->au[k][m] > 0 ? lam[k][m] : -lam[k][m]) < 0) as->au[k][m] = 0;
+                    if (k + 1 <= N - 1) for (int m = 0; m < NBX; m++) if (as->av[k + 1][m] && (as->av[k + 1][m] > 0 ? nu[k][m] : -nu[k][m]) < 0) as->av[k + 1][m] = 0;
+                }
+            } else if (wx) as->av[wk][wm] = 0; else as->au[wk][wm] = 0;
+            changed = 1;
         }
         if (!changed) { fixed = 1; r++; break; }
     }
@@ -659,11 +699,36 @@ int orc_rti_step(const orc_cfg* c, const real* x0, const real* xr, const real* u
     int status = 4, it = 0;
     real mu = 0, res = 0;
     real tol = (real)c->tol;
+    int pdas_rounds = 0;
+    if (c->pdas_first > 0) {
+        /* unconstrained step (empty active set), then rounds from the bounds it violates */
+        orc_aset as;
+        memset(&as, 0, sizeof(as));
+        if (orc_polish(c, w, &as, dx, du, c->pdas_first + 1, &pdas_rounds)) {
+            int na2 = 0;
+            for (int k = 0; k < N; k++) {
+                for (int m = 0; m < NU; m++) na2 += as.au[k][m] != 0;
+                if (k >= 1) for (int m = 0; m < NBX; m++) na2 += as.av[k][m] != 0;
+            }
+            int nan2 = 0;
+            for (int k = 0; k <= N; k++)
+                for (int i = 0; i < NX; i++) { X[k * NX + i] += dx[k][i]; nan2 |= !isfinite(X[k * NX + i]); }
+            for (int k = 0; k < N; k++)
+                for (int m = 0; m < NU; m++) { U[k * NU + m] += du[k][m]; nan2 |= !isfinite(U[k * NU + m]); }
+            if (st) { st->status = nan2 ? 1 : 0; st->n_iter = -pdas_rounds; st->n_active = na2; st->res = 0; st->mu = 0; }
+            free(bs); free(lb); free(dx); free(du);
+            if (own) free(w);
+            return nan2 ? 1 : 0;
+        }
+    }
     /* residual tracking: the Newton system is solved exactly, so the stationarity and
      * dynamics residuals contract by (1-alpha) each iteration; res_lin is that factor times
      * the initial residual bound (checked explicitly below for the slack equations). */
     real res_lin = 1;
-    for (it = 0; it <= c->max_iter; it++) {
+    real tol_mu = (real)c->tol_mu;
+    int polish_tries = 0;
+ipm_again:
+    for (; it <= c->max_iter; it++) {
         mu = 0; res = 0;
         for (int i = 0; i < nb; i++) {
             mu += ll[i] * tl[i] + lu[i] * tu[i];
@@ -671,7 +736,7 @@ int orc_rti_step(const orc_cfg* c, const real* x0, const real* xr, const real* u
             res = fmax(res, fabs(tu[i] - (ub[i] - zb[i])));
         }
         mu /= (2 * nb);
-        if (it > 0 && res < tol && mu < (real)c->tol_mu && res_lin < tol) { status = 0; break; }
+        if (it > 0 && res < tol && mu < tol_mu && res_lin < tol) { status = 0; break; }
         if (it == c->max_iter) break;
         real sigma_mu = 0;
         real alpha = 1;
@@ -739,7 +804,7 @@ int orc_rti_step(const orc_cfg* c, const real* x0, const real* xr, const real* u
 done:;
     int nact = 0;
     for (int i = 0; i < nb; i++) { nact += (tl[i] < ll[i]); nact += (tu[i] < lu[i]); }
-    if (c->polish > 0 && nact > 0 && status != 1) {
+    if (c->polish > 0 && status != 1) {
         /* exact solve on the IPM's active set (t < lambda marks a bound as active), see orc_polish */
         orc_aset as;
         memset(&as, 0, sizeof(as));
@@ -756,6 +821,14 @@ done:;
                 for (int m = 0; m < NU; m++) nact += as.au[k][m] != 0;
                 if (k >= 1) for (int m = 0; m < NBX; m++) nact += as.av[k][m] != 0;
             }
+        }
+        else if (polish_tries == 0 && status == 0 && tol > (real)1e-13 && sizeof(real) == 8) {
+            /* no fixed point from this active-set estimate (the rounds can cycle on near-degenerate bounds): carry the
+             * interior-point iteration on to its floor instead, then try the rounds once more */
+            polish_tries = 1;
+            tol = tol_mu = (real)1e-13;
+            status = 4;
+            goto ipm_again;
         }
         if (getenv("ORC_TRACE")) fprintf(stderr, "polish: rounds %d status %d nact %d\n", rounds, status, nact);
     }

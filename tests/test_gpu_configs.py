@@ -93,7 +93,7 @@ def test_config1_free_run(built_lib, config1_oracle):
     print(f"config 1 free run: max |p_gpu - p_oracle| {np.abs(pos_g - pos_o).max():.2e} m, tracking RMSE gpu {err(g.log):.5f} oracle {err(s.log):.5f}")
     assert np.abs(pos_g - pos_o).max() < 2e-3
     assert abs(err(g.log) - err(s.log)) < 1e-4
-    assert abs(g.k_throttle - s.k_throttle) < 1e-6
+    assert abs(g.k_throttle - s.k_throttle) < 1e-4
 
 
 @pytest.fixture(scope="module")
