@@ -254,6 +254,8 @@ def run_native(args, rank, local_rank, world):
     # per-kernel durations for the roofline: the same K steps again with an event between the two kernels (which
     # serialises them: an ordinary launch of the solve)
     evk = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
+    eng.kernel_timing(True)  # the library brackets its two kernels (nominal SQP-RTI, constrained QPs) with events of its own
+    nom_ms, con_ms = [], []
     for s in range(K):
         d = d_sets[(W + s) % n_sets]
         flush.zero_()
@@ -262,8 +264,11 @@ def run_native(args, rank, local_rank, world):
         evk[s][1].record()
         eng.update(d["x0"], d["xr"], d["ur"], f_buf, u0_buf)
         evk[s][2].record()
+        a_ms, c_ms = eng.last_kernel_ms()
+        nom_ms.append(a_ms); con_ms.append(c_ms)
     torch.cuda.synchronize()
-    solve_ms = np.array([e[1].elapsed_time(e[2]) for e in evk])
+    eng.kernel_timing(False)
+    solve_ms = np.array(nom_ms)  # the dominant kernel's own duration (roofline); the constrained kernel is listed beside it
     mlp_ms = np.array([e[0].elapsed_time(e[1]) for e in evk])
     serial_step_ms = np.array([e[0].elapsed_time(e[2]) for e in evk])
     total_ms = float(step_ms.sum())
@@ -274,23 +279,35 @@ def run_native(args, rank, local_rank, world):
             print(json.dumps(dict(kernels_only=True, ms_per_step=total_ms / K, rti_ms=float(solve_ms.mean()), mlp_ms=float(mlp_ms.mean()))), flush=True)
         return
     # ---------- end-to-end timing through the host-buffer C ABI (e2e) ----------
-    # ndp_pipeline_*: every step copies that step's record (x0, xr, ur, neighbour horizon, gate) from pinned
-    # host memory, runs the MLP + RTI kernels and copies (u0, status) back; consecutive steps overlap
-    # (upload of step i+1 under the kernels of step i), results are consumed on the host in order.
-    from ndp_nmpc_qd_b200.pipeline import HostStepPipeline
+    # ndp_pipeline_* in long-list mode: the reference lists live on the device (as in the reference's own publisher, which
+    # appends ONE new point per tick: pt_publisher.py:78-97) and every step copies that step's record -- x0, the new ego
+    # point, the neighbour's new point, the gate position: 128 B per problem -- from pinned host memory, runs the list push,
+    # the MLP and the RTI kernels and copies (u0, status) back; consecutive steps overlap (upload of step i+1 under the
+    # kernels of step i), results are consumed on the host in order.  Every step has its own pre-filled pinned slot.
+    from ndp_nmpc_qd_b200 import workloads as wl
+    from ndp_nmpc_qd_b200.pipeline import HostStepPipeline, LongList
 
-    depth = 4
-    pipe = HostStepPipeline(eng, nn, depth=depth)
-    for sl, w in zip(pipe.slots, sets):
-        sl.x0[...] = w["x0"]; sl.xr[...] = w["xr"]; sl.ur[...] = w["ur"]
-        sl.other[...] = w["other"][:, :, 0:6]; sl.gate_xy[...] = w["xr"][:, 0, 0:2]
+    inflight = 4
+    n_lat = min(W + min(K, 30), 60)            # one-step-at-a-time latency samples (the first W are warm-up)
+    n_thr = min(K, 448 - n_lat)                # overlapped steps timed for the throughput
+    n_slots = n_lat + n_thr
+    lists = wl.sliding_lists(sets[0], n_slots + 1)
+    ll = LongList(eng, with_other=True)
+    pipe = HostStepPipeline(eng, nn, depth=n_slots, longlist=ll)
+    rng = np.random.default_rng(7 + rank)
+    for j, sl in enumerate(pipe.slots):        # tick j + 1: the lists hold points j + 1 .. j + 101
+        x0 = lists["x_list"][:, j + 1] + 0.02 * rng.normal(size=(B, 10)) * np.array([1, 1, 1, 2, 2, 2, 0.2, 0.2, 0.2, 0.2])
+        x0[:, 6:10] /= np.linalg.norm(x0[:, 6:10], axis=1, keepdims=True)
+        sl.x0[...] = x0; sl.xr[:, 0] = lists["x_list"][:, j + 101]; sl.ur[:, 0] = lists["u_list"][:, j + 101]
+        sl.other[:, 0] = lists["other_list"][:, j + 101]; sl.gate_xy[...] = x0[:, 0:2]
+    ll.reset(lists["x_list"][:, :101], lists["u_list"][:, :101], lists["other_list"][:, :101])
     eng.reset(d_sets[0]["xr"], d_sets[0]["ur"])
     torch.cuda.synchronize()
     # latency: one step at a time (submit + wait)
     e2e_lat = []
-    for s in range(W + min(K, 50)):
+    for s in range(n_lat):
         t0 = time.perf_counter()
-        pipe.step(s % depth)
+        pipe.step(s)
         if s >= W:
             e2e_lat.append(time.perf_counter() - t0)
     chk = float(pipe.slots[0].u0[0, 3])
@@ -298,25 +315,29 @@ def run_native(args, rank, local_rank, world):
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()
-    # throughput: `depth` steps in flight
+    # throughput: `inflight` steps in flight
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     cs = torch.cuda.ExternalStream(pipe.lib.ndp_pipeline_stream(pipe._p), device=dev)
     t_host0 = time.perf_counter()
     e0.record(cs)
     acc = 0.0
-    for s in range(K):
-        if s >= depth:
-            acc += float(pipe.wait(s % depth).u0[0, 3])  # host reads the step's result before the slot is reused
-        pipe.submit(s % depth)
-    for s in range(max(0, K - depth), K):
-        acc += float(pipe.wait(s % depth).u0[0, 3])
+    for s in range(n_lat, n_slots):
+        if s - n_lat >= inflight:
+            acc += float(pipe.wait(s - inflight).u0[0, 3])  # the host reads a step's result while later steps are in flight
+        pipe.submit(s)
+    for s in range(max(n_lat, n_slots - inflight), n_slots):
+        acc += float(pipe.wait(s).u0[0, 3])
     e1.record(cs)
     torch.cuda.synchronize()
     t_host = (time.perf_counter() - t_host0) * 1e3
-    e2e_ms = max(e0.elapsed_time(e1), t_host)  # device span of the K steps vs host wall clock incl. the last D2H: report the slower
-    e2e_bad = int((pipe.slots[(K - 1) % depth].status != 0).sum())
+    e2e_ms = max(e0.elapsed_time(e1), t_host)  # device span of the steps vs host wall clock incl. the last D2H: report the slower
+    e2e_bad = int(sum(int((pipe.slots[s].status != 0).sum()) for s in range(n_lat, n_slots)))
     h2d_b, d2h_b = pipe.h2d_bytes_per_step, pipe.d2h_bytes_per_step
+    e2e_steps = n_thr
+    depth = inflight
     clocks = sampler.stop() if sampler else None
+    # ---------- configs 4 and 5 under the same clock (all ranks take part) ----------
+    extras = None if args.no_extras else config45(args, rank, world, dev, dist)
     # ---------- reduce over ranks: max time ----------
     red = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device=dev)
     if dist is not None:
@@ -353,9 +374,11 @@ def run_native(args, rank, local_rank, world):
                     inputs="8 pre-generated control steps cycled; iterate warm-started, no shift",
                     parallelism=f"{world} independent shards, no collective"),
         clocks=clocks,
-        e2e=dict(value=world * B * K / (e2e_ms * 1e-3), unit=UNIT, h2d_bytes_per_step=int(h2d_b), d2h_bytes_per_step=int(d2h_b),
-                 ms_per_step=e2e_ms / K, p50_step_ms=float(np.median(e2e_lat) * 1e3), status_nonzero=e2e_bad,
-                 api="ndp_pipeline_submit/wait (include/ndp_nmpc.h): pinned host record -> H2D -> MLP + RTI kernels -> D2H (u0, status)",
+        e2e=dict(value=world * B * e2e_steps / (e2e_ms * 1e-3), unit=UNIT, h2d_bytes_per_step=int(h2d_b), d2h_bytes_per_step=int(d2h_b),
+                 ms_per_step=e2e_ms / e2e_steps, steps=e2e_steps, p50_step_ms=float(np.median(e2e_lat) * 1e3), status_nonzero=e2e_bad,
+                 api="ndp_pipeline_create_ll / submit / wait (include/ndp_nmpc.h): pinned host record -> H2D -> list push + MLP + RTI kernels -> D2H (u0, status)",
+                 inputs="per step and problem: x0, ONE new reference point (x, u), the neighbour's new point, the gate position (128 B); "
+                        "the 101-point reference lists live on the device, as the reference's publisher keeps them (pt_publisher.py:78-97)",
                  mode=f"{depth} steps in flight (upload of step i+1 overlaps the kernels of step i); p50_step_ms is the one-step-at-a-time latency"),
         gpu_launches=int(launches),
         roofline=dict(bound="fp64" if f64 else "fp32", kernel="rti_step_kernel<double>" if f64 else "rti_step_kernel<float>", achieved=ach_tf, peak=fp32_peak,
@@ -366,6 +389,7 @@ def run_native(args, rank, local_rank, world):
                                frac=compulsory_bytes_per_solve(N_HORIZON, elt) * B / solve_s / 1e9 / peaks["hbm_gbs"],
                                bytes_per_solve=compulsory_bytes_per_solve(N_HORIZON, elt))),
         mlp=dict(kernel_ms=float(mlp_ms.mean()), rows=B * (N_HORIZON + 1), note="fused feature + gate + MLP kernel (events 0-1 of the per-kernel pass)"),
+        constrained_kernel=dict(kernel_ms=float(np.mean(con_ms)), note="rti_constrained_kernel of the same steps: takes the problems whose unconstrained step leaves its box (none on this workload: it reads an empty queue and exits)"),
         step_breakdown=dict(serialised_step_ms=float(serial_step_ms.mean()),
                             note="value times the step with the solve launched as a programmatic dependent of the MLP kernel; "
                                  "roofline.kernel_ms / mlp.kernel_ms come from a second pass of the same steps with an event between the two kernels"),
@@ -374,6 +398,8 @@ def run_native(args, rank, local_rank, world):
     )
     # parity of the benched problems against the CPU oracle (a parity figure with every number)
     out["parity"] = parity_check(eng, nn, sets, dev, dt, f_buf, u0_buf)
+    if extras:
+        out.update(extras)
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_oracle_rate(sets, seconds=12.0)[0]
     if world == 1 and not args.no_latency and not f64:
@@ -388,6 +414,46 @@ def run_native(args, rank, local_rank, world):
     print(json.dumps(out), flush=True)
     if dist is not None:
         dist.destroy_process_group()
+
+
+def config45(args, rank, world, dev, dist):
+    """BASELINE.json config 4 (coupled swarm: the one case with an exchange step) and config 5 (horizon x batch closed-loop
+    sweep with batched dop_sim rollouts) on the ranks of this run.
+      swarm        1024 (and 8192) quads in total, sharded over the ranks (STRONG scaling: the step is latency-bound),
+                   per exchange mode: one process -> local; several -> fused peer-memory reads (p2p) and NCCL all-gather
+      closed_loop  every rank runs its own scenarios (weak scaling, no collective): ms per control step, max over ranks"""
+    import torch
+
+    from ndp_nmpc_qd_b200.closed_loop import time_closed_loop
+    from ndp_nmpc_qd_b200.swarm import time_swarm
+
+    out = {}
+    modes = ["local"] if world == 1 else ["p2p", "allgather"]
+    sw = {}
+    for quads in (1024, 8192):
+        try:
+            sw[str(quads)] = time_swarm(quads, modes, steps=40, warmup=60, device=dev)
+        except Exception as ex:  # noqa: BLE001 -- e.g. symmetric memory unavailable on this box
+            sw[str(quads)] = dict(error=f"{type(ex).__name__}: {ex}"[:300])
+    out["swarm"] = dict(nranks=world, scaling="strong", quads=sw,
+                        note="ms per coupled RTI step: reference generation + exchange + gated all-pairs MLP + local solves; device time, max over ranks")
+    cl = []
+    for N, B, steps in ((20, 32768, 60), (40, 32768, 40), (80, 32768, 30), (20, 262144, 20), (80, 262144, 10)):
+        try:
+            r = time_closed_loop(N, B, steps=steps, device=dev, seed=1000 * rank + N + B)
+            ms = torch.tensor([r["ms_per_control_step"]], dtype=torch.float64, device=dev)
+            bad = torch.tensor([r["status_nonzero"]], dtype=torch.int64, device=dev)
+            if dist is not None:
+                dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+                dist.all_reduce(bad)
+            cl.append(dict(N=N, batch_per_gpu=B, control_steps=steps, ms_per_control_step=float(ms), solves_per_s=world * B / (float(ms) * 1e-3),
+                           sim_steps_per_s=2 * world * B / (float(ms) * 1e-3), pos_rmse_m_rank0=r["pos_rmse_m"], status_nonzero=int(bad),
+                           launch_mode=r["launch_mode"]))
+        except Exception as ex:  # noqa: BLE001
+            cl.append(dict(N=N, batch_per_gpu=B, error=f"{type(ex).__name__}: {ex}"[:300]))
+    out["closed_loop"] = dict(nranks=world, scaling="weak", points=cl,
+                              note="RefGen -> odometry -> SQP-RTI -> AttitudeTarget -> 2 plant steps per control step, CUDA-graph replay; th_pred stays 0.1 s (T = 0.1 N)")
+    return out
 
 
 def parity_check(eng, nn, sets, dev, dt, f_buf, u0_buf, steps=3):
@@ -608,6 +674,7 @@ def main():
     ap.add_argument("--dtype", default="f32", choices=["f32", "f64"], help="engine precision (f64: the like-for-like build against the fp64 reference path)")
     ap.add_argument("--profile", action="store_true", help="re-measure roofline.traffic with ncu (writes profiles/ncu_rti_summary.json)")
     ap.add_argument("--kernels-only", action="store_true", help="device-resident timing only (what --profile runs under ncu)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the config 4 (swarm) / config 5 (closed-loop sweep) blocks")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-latency", action="store_true")
     args = ap.parse_args()

@@ -140,8 +140,17 @@ int ndp_status(ndp_handle* h, int32_t* status_dev, void* stream);
  * active-set rounds, active bounds at the solution}. */
 int ndp_stats(ndp_handle* h, int32_t* stats_dev, void* stream);
 
-/* Number of kernel launches issued on behalf of this handle so far. */
+/* Number of kernel launches issued on behalf of this handle so far (two per solve: the nominal SQP-RTI kernel and the
+ * constrained-QP kernel that takes the problems whose unconstrained step leaves its box; the latter exits at once when
+ * there are none). */
 int64_t ndp_launch_count(const ndp_handle* h);
+
+/* Measurement aid: with enable != 0 every solve records CUDA events on its stream before, between and after its two
+ * kernels; ndp_last_kernel_ms waits for the last solve and returns the two device durations (the roofline figure of
+ * bench.py is the nominal kernel's own time).  The event between the kernels costs the second one its programmatic
+ * overlap, so leave this off outside measurements. */
+int ndp_kernel_timing(ndp_handle* h, int enable);
+int ndp_last_kernel_ms(ndp_handle* h, float* nominal_ms, float* constrained_ms);
 
 const char* ndp_last_error(void);
 
@@ -228,6 +237,26 @@ int ndp_pipeline_submit(ndp_pipeline* p, int slot); /* asynchronous */
 int ndp_pipeline_wait(ndp_pipeline* p, int slot);   /* blocks until the slot's u0 / status are in host memory */
 int ndp_pipeline_bytes(const ndp_pipeline* p, int64_t* h2d_bytes_per_step, int64_t* d2h_bytes_per_step);
 void* ndp_pipeline_stream(ndp_pipeline* p);         /* the compute stream (cudaStream_t) */
+
+/* ---- device-resident sliding reference lists ----
+ * NMPCRefPublisher (pt_pub/pt_publisher.py:57-103): `len` = long_list_size = 101 points (x[10], u[4]) per quadrotor at
+ * ts_nmpc; every tick get_nmpc_pts pops the front, appends ONE new point and returns every `stride` = 5th point
+ * (params/nmpc_params.py:40-43): xr = list[0::5] (N+1 nodes), ur = the same without its last entry.  The lists stay on
+ * the device as rings, so a control tick uploads one point per quadrotor (56 B) instead of the horizon (1 160 B);
+ * with_other adds the neighbour's list (the 6 position / velocity columns DownwashNN reads, downwash_nn.py:24).
+ * reset: _gen_long_list_w_traj -- x_long [B][len][10], u_long [B][len][4], other_long [B][len][6] (host or device memory).
+ * push: new_x [B][10], new_u [B][4], new_other [B][6] -> xr [B][N+1][10], ur [B][N][4], other [B][N+1][6] (device). */
+typedef struct ndp_longlist ndp_longlist;
+int ndp_longlist_create(int precision, int64_t B, int32_t N, int32_t stride, int32_t len, int with_other, ndp_longlist** out);
+int ndp_longlist_destroy(ndp_longlist* l);
+int ndp_longlist_reset(ndp_longlist* l, const void* x_long, const void* u_long, const void* other_long, void* stream);
+int ndp_longlist_push(ndp_longlist* l, const void* new_x_dev, const void* new_u_dev, const void* new_other_dev, void* xr_dev,
+                      void* ur_dev, void* other_dev, void* stream);
+int64_t ndp_longlist_launch_count(const ndp_longlist* l);
+/* Step pipeline over such lists: a slot's input record is x0 [B][10], ONE new ego point (ndp_pipeline_buffers: xr ->
+ * new_x [B][10], ur -> new_u [B][4]), the neighbour's new point (other -> [B][6]) and gate_xy [B][2] -- 128 B per problem
+ * instead of 1 712 B; each submitted step pushes the points into the lists before the MLP / SQP-RTI kernels. */
+int ndp_pipeline_create_ll(ndp_handle* h, ndp_mlp* mlp, double r_horiz, int depth, ndp_longlist* ll, ndp_pipeline** out);
 
 /* ---- batched dop_sim quadrotor plant (closed-loop rollouts) ----
  * dop_sim/scripts/quadrotor/mul_quadrotors.py:19-50 MulQuadrotors(num_agent, ts_sim, ts_control, float64,

@@ -29,6 +29,8 @@ EXPORTS = [
     "ndp_refgen_create", "ndp_refgen_destroy", "ndp_refgen_horizon", "ndp_refgen_launch_count",
     "ndp_predxu_len", "ndp_predxu_pack", "ndp_predxu_unpack", "ndp_hover_throttle_init", "ndp_hover_throttle_update",
     "ndp_plant_cmd_from_u0_dev",
+    "ndp_longlist_create", "ndp_longlist_destroy", "ndp_longlist_reset", "ndp_longlist_push", "ndp_longlist_launch_count",
+    "ndp_pipeline_create_ll", "ndp_kernel_timing", "ndp_last_kernel_ms",
 ]
 
 
@@ -128,6 +130,19 @@ def load() -> C.CDLL:
     lib.ndp_hover_throttle_update.argtypes = [i64, dbl, vp, i64, vp, i64, vp, vp, vp]
     lib.ndp_plant_cmd_from_u0_dev.argtypes = [i64, i32, vp, dbl, vp, vp, vp]
     for name in ("ndp_predxu_pack", "ndp_predxu_unpack", "ndp_hover_throttle_init", "ndp_hover_throttle_update", "ndp_plant_cmd_from_u0_dev"):
+        getattr(lib, name).restype = C.c_int
+    lib.ndp_kernel_timing.argtypes = [vp, i32]
+    lib.ndp_kernel_timing.restype = C.c_int
+    lib.ndp_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    lib.ndp_last_kernel_ms.restype = C.c_int
+    lib.ndp_longlist_create.argtypes = [i32, i64, i32, i32, i32, i32, C.POINTER(vp)]
+    lib.ndp_longlist_destroy.argtypes = [vp]
+    lib.ndp_longlist_reset.argtypes = [vp, vp, vp, vp, vp]
+    lib.ndp_longlist_push.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.ndp_longlist_launch_count.argtypes = [vp]
+    lib.ndp_longlist_launch_count.restype = i64
+    lib.ndp_pipeline_create_ll.argtypes = [vp, vp, dbl, i32, vp, C.POINTER(vp)]
+    for name in ("ndp_longlist_create", "ndp_longlist_destroy", "ndp_longlist_reset", "ndp_longlist_push", "ndp_pipeline_create_ll"):
         getattr(lib, name).restype = C.c_int
     for name in ("ndp_refgen_create", "ndp_refgen_destroy", "ndp_refgen_horizon"):
         getattr(lib, name).restype = C.c_int

@@ -110,3 +110,66 @@ class ClosedLoop:
     @property
     def launch_count(self) -> int:
         return self.engine.launch_count + self.plant.launch_count + self.refgen.launch_count
+
+
+def time_closed_loop(N: int, B: int, steps: int = 250, precision: str = "f32", device="cuda:0", seed: Optional[int] = None, use_graph: bool = True,
+                     trajectories=None) -> dict:
+    """One point of BASELINE.json config 5 (horizon x batch sweep, closed loop with batched dop_sim rollouts) on one
+    GPU: B scenarios on randomly phased eight_high_dyn / eight_low references, `steps` control steps (two plant steps
+    each) timed with CUDA events.  The control step (6 library kernels + a clock update) is captured once into a CUDA
+    graph and replayed, so small batches measure the device and not the Python launch rate."""
+    from . import traj_gen
+
+    dev = torch.device(device)
+    trs = trajectories or [traj_gen.plan_named("eight_high_dyn"), traj_gen.plan_named("eight_low")]
+    rng = np.random.default_rng(B + N if seed is None else seed)
+    tid = (rng.random(B) < 0.5).astype(np.int32)
+    t0 = np.array([rng.uniform(0, trs[j].duration - 6.0) for j in tid])
+    with torch.cuda.device(dev):
+        cl = ClosedLoop(trs, tid, t0, N=N, precision=precision, offset=rng.normal(size=(B, 3)) * 2.0, device=dev)
+        for _ in range(5):
+            cl.step()
+        torch.cuda.synchronize(dev)
+        graph, mode = None, "eager"
+        if use_graph:
+            try:
+                cap = torch.cuda.Stream(device=dev)
+                cap.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(cap):
+                    cl.step()
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=cap):
+                        cl.step()
+                torch.cuda.current_stream(dev).wait_stream(cap)
+                graph, mode = g, "cuda graph replay"
+            except Exception:  # noqa: BLE001
+                graph = None
+        torch.cuda.synchronize(dev)
+        l0 = cl.launch_count
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            if graph is not None:
+                graph.replay()
+            else:
+                cl.step()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1)
+        launches = (cl.launch_count - l0) / steps if graph is None else None
+        sq = torch.zeros((), dtype=torch.float64, device=dev)
+        n_err = min(steps, 50)
+        for _ in range(n_err):
+            cl.step()
+            sq += (cl.position_error() ** 2).mean()
+        torch.cuda.synchronize(dev)
+        st = cl.engine.status().cpu().numpy()
+        stats = cl.engine.stats().cpu().numpy()
+        out = dict(N=N, batch=B, control_steps=steps, ms_per_control_step=ms / steps, solves_per_s=B * steps / (ms * 1e-3),
+                   sim_steps_per_s=cl.sim_per_ctl * B * steps / (ms * 1e-3), pos_rmse_m=float(torch.sqrt(sq / n_err)),
+                   status_nonzero=int((st != 0).sum()), riccati_sweeps_mean=float(stats[:, 0].mean()), launch_mode=mode, precision=precision)
+        if launches is not None:
+            out["launches_per_step"] = launches
+        del cl
+        torch.cuda.empty_cache()
+    return out

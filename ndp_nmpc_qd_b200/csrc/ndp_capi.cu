@@ -73,6 +73,7 @@ struct ndp_handle {
     int elt;  // bytes per element
     void *X, *U, *yref, *par, *ws;
     int32_t *status, *stats;
+    int32_t* status_mirror;  // set by the step pipeline around its launches: the kernels also write the status into its output record
     unsigned long long* as_store;  // [B][AS_OWNERS][4] active set a problem's constrained solve starts from
     long long ws_stride;           // nominal kernel: forward-sweep records only
     int slots, grid, ppc, lat;
@@ -81,6 +82,8 @@ struct ndp_handle {
     int slots_c, grid_c;
     int* queue;                    // [B] problems handed from the nominal to the constrained kernel
     int* qctl;                     // {count, head, done, pad}
+    int timing;                    // ndp_kernel_timing: record events around the two kernels of every solve
+    cudaEvent_t tev[3];
     size_t smem;
     // ndp_solve_host: private stream, the two captured step graphs (with / without reference upload) and the
     // host pointers they were captured for
@@ -190,7 +193,6 @@ RtiCfg<T> make_cfg(const ndp_config& g) {
     c.t_min = (T)1e-12;
     c.mu0 = (T)10.0;
     c.t_floor = (T)0.1;
-    c.big = (T)(f32 ? 1e9 : 1e12);
     return c;
 }
 
@@ -249,6 +251,7 @@ int launch_solve(ndp_handle* h, const void* x0, void* u0, cudaStream_t st, const
     a.U = (T*)h->U;
     a.u0 = (T*)u0;
     a.status = h->status;
+    a.status2 = h->status_mirror;
     a.stats = h->stats;
     a.as_store = h->as_store;
     a.as_warm = h->cfg.active_set_warm ? 1 : 0;
@@ -259,8 +262,10 @@ int launch_solve(ndp_handle* h, const void* x0, void* u0, cudaStream_t st, const
     a.B = h->cfg.batch;
     const int thr = h->ppc * GL;
     const RtiInst<T> inst = rti_inst<T>(h->cfg.N, h->lat != 0);
+    if (h->timing) cudaEventRecord(h->tev[0], st);
     inst.launch(h->grid, thr, h->smem, st, c, a, pdl && xr && f);
     CU(cudaGetLastError());
+    if (h->timing) cudaEventRecord(h->tev[1], st);
     // the problems whose unconstrained step left its box: second kernel, launched as a programmatic dependent so that its
     // launch latency hides under the nominal kernel (it exits at once when the queue is empty)
     a.ws = (T*)h->ws_c;
@@ -268,6 +273,7 @@ int launch_solve(ndp_handle* h, const void* x0, void* u0, cudaStream_t st, const
     inst.claunch(h->grid_c, thr, h->smem, st, c, a);
     h->launches += 2;
     CU(cudaGetLastError());
+    if (h->timing) cudaEventRecord(h->tev[2], st);
     return 0;
 }
 
@@ -343,8 +349,8 @@ void ndp_default_config(ndp_config* c) {
     c->u_min[3] = 0;
     c->u_max[3] = 9.81 / 0.36;
     c->ipm_max_iter = 50;
-    c->polish_max = 12;
-    c->active_set_first = 16;
+    c->polish_max = 24;
+    c->active_set_first = 20;
     c->active_set_warm = 0;
     c->ipm_tol_mu = 0.0;
 }
@@ -402,8 +408,11 @@ int ndp_create(const ndp_config* cfg, ndp_handle** out) {
     const size_t eb = (size_t)h->elt;
     h->X = h->U = h->yref = h->par = h->ws = nullptr;
     h->status = h->stats = nullptr;
+    h->status_mirror = nullptr;
     h->as_store = nullptr;
     h->ws_c = nullptr; h->queue = nullptr; h->qctl = nullptr;
+    h->timing = 0;
+    for (auto& e2 : h->tev) e2 = nullptr;
     h->hs = nullptr; h->hgraph[0] = h->hgraph[1] = nullptr; h->d_hx0 = h->d_hu0 = nullptr;
     for (auto& q : h->hptr) q = nullptr;
     bool ok = cudaMalloc(&h->X, (size_t)B * (N + 1) * NX * eb) == cudaSuccess && cudaMalloc(&h->U, (size_t)B * N * NU * eb) == cudaSuccess &&
@@ -438,6 +447,7 @@ int ndp_destroy(ndp_handle* h) {
     cudaFree(h->X); cudaFree(h->U); cudaFree(h->yref); cudaFree(h->par); cudaFree(h->ws);
     cudaFree(h->status); cudaFree(h->stats); cudaFree(h->as_store);
     cudaFree(h->ws_c); cudaFree(h->queue); cudaFree(h->qctl);
+    for (auto& e2 : h->tev) if (e2) cudaEventDestroy(e2);
     for (auto& g : h->hgraph) if (g) cudaGraphExecDestroy(g);
     if (h->hs) cudaStreamDestroy(h->hs);
     cudaFree(h->d_hx0); cudaFree(h->d_hu0);
@@ -582,6 +592,25 @@ int ndp_stats(ndp_handle* h, int32_t* stats_dev, void* stream) {
 }
 
 int64_t ndp_launch_count(const ndp_handle* h) { return h ? (int64_t)h->launches.load() : 0; }
+
+int ndp_kernel_timing(ndp_handle* h, int enable) {
+    if (!h) return fail(NDP_E_ARG, "ndp_kernel_timing: null");
+    DeviceGuard dg(h->dev);
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (enable && !h->tev[0])
+        for (auto& e : h->tev) CU(cudaEventCreate(&e));
+    h->timing = enable ? 1 : 0;
+    return 0;
+}
+
+int ndp_last_kernel_ms(ndp_handle* h, float* nominal_ms, float* constrained_ms) {
+    if (!h || !h->tev[0]) return fail(NDP_E_STATE, "ndp_last_kernel_ms: timing was not enabled");
+    DeviceGuard dg(h->dev);
+    CU(cudaEventSynchronize(h->tev[2]));
+    if (nominal_ms) CU(cudaEventElapsedTime(nominal_ms, h->tev[0], h->tev[1]));
+    if (constrained_ms) CU(cudaEventElapsedTime(constrained_ms, h->tev[1], h->tev[2]));
+    return 0;
+}
 
 int ndp_rk4_sens(int precision, int64_t M, double hh, double mass, double gravity, const void* x, const void* u, const void* f, void* xn,
                  void* AB, void* stream) {
@@ -838,23 +867,39 @@ struct ndp_pipeline {
     cudaEvent_t *e_in, *e_cmp, *e_out;
     cudaGraphExec_t gexec;  // depth 1 (latency path): the whole step as one graph launch on s_cmp
     bool graph_tried;
+    // long-list mode: the reference horizons live on the device (ndp_longlist); a slot carries ONE new point per list
+    ndp_longlist* ll;
+    unsigned char *d_xr, *d_ur, *d_other;  // horizons gathered from the lists for the step being computed
 };
+
+static int pipeline_create_impl(ndp_handle* h, ndp_mlp* mlp, double r_horiz, int depth, ndp_longlist* ll, ndp_pipeline** out);
 
 extern "C" {
 
 int ndp_pipeline_create(ndp_handle* h, ndp_mlp* mlp, double r_horiz, int depth, ndp_pipeline** out) {
-    if (!h || !out || depth < 1 || depth > 64) return fail(NDP_E_ARG, "ndp_pipeline_create: bad argument");
+    return pipeline_create_impl(h, mlp, r_horiz, depth, nullptr, out);
+}
+int ndp_pipeline_create_ll(ndp_handle* h, ndp_mlp* mlp, double r_horiz, int depth, ndp_longlist* ll, ndp_pipeline** out) {
+    if (!ll) return fail(NDP_E_ARG, "ndp_pipeline_create_ll: null list");
+    return pipeline_create_impl(h, mlp, r_horiz, depth, ll, out);
+}
+
+}  // extern "C"
+
+static int pipeline_create_impl(ndp_handle* h, ndp_mlp* mlp, double r_horiz, int depth, ndp_longlist* ll, ndp_pipeline** out) {
+    if (!h || !out || depth < 1 || depth > 512) return fail(NDP_E_ARG, "ndp_pipeline_create: bad argument");
     if (mlp && h->cfg.np != 7) return fail(NDP_E_CONFIG, "ndp_pipeline_create: downwash forces need np = 7");
     DeviceGuard dg(h->dev);
     ndp_pipeline* p = new ndp_pipeline();
     std::memset(p, 0, sizeof(*p));
-    p->h = h; p->mlp = mlp; p->depth = depth; p->r_horiz = r_horiz;
+    p->h = h; p->mlp = mlp; p->depth = depth; p->r_horiz = r_horiz; p->ll = ll;
     const size_t eb = (size_t)h->elt, B = (size_t)h->cfg.batch, N = (size_t)h->cfg.N;
+    const size_t nodes = ll ? 1 : N + 1, nodes_u = ll ? 1 : N;  // long-list mode: one new point per list and step
     size_t o = 0;
     p->o_x0 = o; o += B * NX * eb;
-    p->o_xr = o; o += B * (N + 1) * NX * eb;
-    p->o_ur = o; o += B * N * NU * eb;
-    p->o_other = o; if (mlp) o += B * (N + 1) * 6 * eb;  // neighbour horizon: the 6 columns DownwashNN reads
+    p->o_xr = o; o += B * nodes * NX * eb;
+    p->o_ur = o; o += B * nodes_u * NU * eb;
+    p->o_other = o; if (mlp) o += B * nodes * 6 * eb;  // neighbour horizon: the 6 columns DownwashNN reads
     p->o_gate = o; if (mlp) o += B * 2 * eb;
     p->in_bytes = (o + 255) & ~(size_t)255;
     p->o_status = B * NU * eb;
@@ -872,6 +917,9 @@ int ndp_pipeline_create(ndp_handle* h, ndp_mlp* mlp, double r_horiz, int depth, 
         ok = cudaEventCreateWithFlags(&p->e_in[s], cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&p->e_cmp[s], cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&p->e_out[s], cudaEventDisableTiming) == cudaSuccess;
+    if (ok && ll)
+        ok = cudaMalloc((void**)&p->d_xr, B * (N + 1) * NX * eb) == cudaSuccess && cudaMalloc((void**)&p->d_ur, B * N * NU * eb) == cudaSuccess &&
+             (!mlp || cudaMalloc((void**)&p->d_other, B * (N + 1) * 6 * eb) == cudaSuccess);
     if (!ok) { ndp_pipeline_destroy(p); return fail(NDP_E_ALLOC, "ndp_pipeline_create: allocation failed"); }
     std::memset(p->h_in, 0, p->in_bytes * depth);
     std::memset(p->h_out, 0, p->out_bytes * depth);
@@ -879,6 +927,8 @@ int ndp_pipeline_create(ndp_handle* h, ndp_mlp* mlp, double r_horiz, int depth, 
     *out = p;
     return 0;
 }
+
+extern "C" {
 
 int ndp_pipeline_destroy(ndp_pipeline* p) {
     if (!p) return 0;
@@ -898,6 +948,7 @@ int ndp_pipeline_destroy(ndp_pipeline* p) {
     if (p->s_out) cudaStreamDestroy(p->s_out);
     cudaFreeHost(p->h_in); cudaFreeHost(p->h_out);
     cudaFree(p->d_in); cudaFree(p->d_out); cudaFree(p->d_f);
+    cudaFree(p->d_xr); cudaFree(p->d_ur); cudaFree(p->d_other);
     delete p;
     return 0;
 }
@@ -916,32 +967,44 @@ int ndp_pipeline_buffers(ndp_pipeline* p, int slot, void** x0, void** xr, void**
     return 0;
 }
 
+// the kernels of one step on stream st: [list push + gather,] downwash MLP, SQP-RTI step; `in` is the step's input record
+// (device copy, or the pinned host record itself), `out` receives u0 and -- written by the kernels -- the status
+static int pipeline_compute(ndp_pipeline* p, unsigned char* in, unsigned char* out, unsigned char* df, cudaStream_t st) {
+    ndp_handle* h = p->h;
+    const void *xr = in + p->o_xr, *ur = in + p->o_ur, *other = in + p->o_other;
+    if (p->ll) {
+        // one new point per list arrives with the step: pop / append / gather every 5th point on the device
+        int rc = ndp_longlist_push(p->ll, in + p->o_xr, in + p->o_ur, p->mlp ? in + p->o_other : nullptr, p->d_xr, p->d_ur, p->d_other, st);
+        if (rc) return rc;
+        xr = p->d_xr; ur = p->d_ur; other = p->d_other;
+    }
+    if (p->mlp) {
+        int rc = ndp_mlp_forward_pairs_ex(p->mlp, h->cfg.precision, h->cfg.batch, h->cfg.N + 1, xr, other, 6, in + p->o_gate, p->r_horiz, df, 0, 0, st);
+        if (rc) return rc;
+    }
+    h->status_mirror = reinterpret_cast<int32_t*>(out + p->o_status);
+    // (with the list push in between, the MLP is no longer the kernel right before an unrelated input: the programmatic
+    // dependency on it stays valid -- every other input of the solve is older than the MLP launch)
+    int rc = ndp_update_ex(h, in + p->o_x0, xr, ur, p->mlp ? df : nullptr, out, p->mlp ? NDP_UPDATE_F_FROM_PREVIOUS_KERNEL : 0, st);
+    h->status_mirror = nullptr;
+    return rc;
+}
+
 // depth 1: copy-in, kernels, copy-out of the only slot on one stream (what the graph of the latency path holds)
 static int pipeline_enqueue_serial(ndp_pipeline* p, cudaStream_t st) {
     ndp_handle* h = p->h;
     const size_t in_used = p->o_gate + (p->mlp ? (size_t)h->cfg.batch * 2 * h->elt : 0);
     const size_t out_used = p->o_status + (size_t)h->cfg.batch * sizeof(int32_t);
     // small records (the one-problem tick is 1.7 KB in, 20 B out): the kernels read the pinned host record and write u0
-    // straight over PCIe (unified addressing: cudaHostAlloc memory is device-accessible at the same address), which
-    // saves the two copy operations and their scheduling gaps; large records keep the staged copies
+    // and the status straight over PCIe (unified addressing: cudaHostAlloc memory is device-accessible at the same
+    // address), which saves the copy operations and their scheduling gaps; large records keep the staged copies
     const bool zero_copy = in_used <= (64u << 10);
     unsigned char* in = zero_copy ? p->h_in : p->d_in;
     unsigned char* out = zero_copy ? p->h_out : p->d_out;
     if (!zero_copy) CU(cudaMemcpyAsync(p->d_in, p->h_in, in_used, cudaMemcpyHostToDevice, st));
-    if (p->mlp) {
-        int rc = ndp_mlp_forward_pairs_ex(p->mlp, h->cfg.precision, h->cfg.batch, h->cfg.N + 1, in + p->o_xr, in + p->o_other, 6,
-                                          in + p->o_gate, p->r_horiz, p->d_f, 0, 0, st);
-        if (rc) return rc;
-    }
-    int rc = ndp_update_ex(h, in + p->o_x0, in + p->o_xr, in + p->o_ur, p->mlp ? p->d_f : nullptr, out,
-                           p->mlp ? NDP_UPDATE_F_FROM_PREVIOUS_KERNEL : 0, st);
+    int rc = pipeline_compute(p, in, out, p->d_f, st);
     if (rc) return rc;
-    if (zero_copy) {
-        CU(cudaMemcpyAsync(p->h_out + p->o_status, h->status, (size_t)h->cfg.batch * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    } else {
-        CU(cudaMemcpyAsync(p->d_out + p->o_status, h->status, (size_t)h->cfg.batch * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
-        CU(cudaMemcpyAsync(p->h_out, p->d_out, out_used, cudaMemcpyDeviceToHost, st));
-    }
+    if (!zero_copy) CU(cudaMemcpyAsync(p->h_out, p->d_out, out_used, cudaMemcpyDeviceToHost, st));
     return 0;
 }
 
@@ -952,7 +1015,8 @@ int ndp_pipeline_submit(ndp_pipeline* p, int slot) {
     if (p->depth == 1) {
         // latency path (the reference's one-problem tick): nothing to overlap, so the step is captured once into a
         // CUDA graph and replayed with a single launch; falls back to plain stream order if capture is refused
-        if (!p->gexec && !p->graph_tried) {
+        // (long-list mode is not captured: the list head advances on the host and is a kernel argument)
+        if (!p->gexec && !p->graph_tried && !p->ll) {
             p->graph_tried = true;
             cudaGraph_t g = nullptr;
             if (cudaStreamBeginCapture(p->s_cmp, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
@@ -983,15 +1047,8 @@ int ndp_pipeline_submit(ndp_pipeline* p, int slot) {
     // compute
     CU(cudaStreamWaitEvent(p->s_cmp, p->e_in[slot], 0));
     CU(cudaStreamWaitEvent(p->s_cmp, p->e_out[slot], 0));
-    if (p->mlp) {
-        int rc = ndp_mlp_forward_pairs_ex(p->mlp, h->cfg.precision, h->cfg.batch, h->cfg.N + 1, din + p->o_xr, din + p->o_other, 6, din + p->o_gate,
-                                          p->r_horiz, df, 0, 0, p->s_cmp);
-        if (rc) return rc;
-    }
-    int rc = ndp_update_ex(h, din + p->o_x0, din + p->o_xr, din + p->o_ur, p->mlp ? df : nullptr, dout,
-                           p->mlp ? NDP_UPDATE_F_FROM_PREVIOUS_KERNEL : 0, p->s_cmp);
+    int rc = pipeline_compute(p, din, dout, df, p->s_cmp);
     if (rc) return rc;
-    CU(cudaMemcpyAsync(dout + p->o_status, h->status, (size_t)h->cfg.batch * sizeof(int32_t), cudaMemcpyDeviceToDevice, p->s_cmp));
     CU(cudaEventRecord(p->e_cmp[slot], p->s_cmp));
     // copy-out
     CU(cudaStreamWaitEvent(p->s_out, p->e_cmp[slot], 0));
@@ -1318,5 +1375,75 @@ int ndp_plant_cmd_from_u0_dev(int64_t n, int precision, const void* u0, double m
     CU(cudaGetLastError());
     return 0;
 }
+
+}  // extern "C"
+
+// ======================= device-resident sliding reference lists =======================
+struct ndp_longlist {
+    int dev, precision, N, stride, len, head;
+    long long B;
+    void *ring_x, *ring_u, *ring_o;
+    std::atomic<long long> launches;
+};
+
+extern "C" {
+
+int ndp_longlist_create(int precision, int64_t B, int32_t N, int32_t stride, int32_t len, int with_other, ndp_longlist** out) {
+    if (!out || B < 1 || N < 1 || stride < 1 || len < stride * N + 1 || (precision != NDP_F32 && precision != NDP_F64))
+        return fail(NDP_E_ARG, "ndp_longlist_create: bad argument (len must cover stride * N + 1 points)");
+    ndp_longlist* l = new ndp_longlist();
+    l->dev = 0;
+    cudaGetDevice(&l->dev);
+    l->precision = precision; l->B = B; l->N = N; l->stride = stride; l->len = len; l->head = 0; l->launches = 0;
+    l->ring_x = l->ring_u = l->ring_o = nullptr;
+    const size_t eb = precision == NDP_F64 ? 8 : 4;
+    bool ok = cudaMalloc(&l->ring_x, (size_t)B * len * 10 * eb) == cudaSuccess && cudaMalloc(&l->ring_u, (size_t)B * len * 4 * eb) == cudaSuccess &&
+              (!with_other || cudaMalloc(&l->ring_o, (size_t)B * len * 6 * eb) == cudaSuccess);
+    if (!ok) { ndp_longlist_destroy(l); return fail(NDP_E_ALLOC, "ndp_longlist_create: cudaMalloc failed"); }
+    *out = l;
+    return 0;
+}
+
+int ndp_longlist_destroy(ndp_longlist* l) {
+    if (!l) return 0;
+    DeviceGuard dg(l->dev);
+    cudaFree(l->ring_x); cudaFree(l->ring_u); cudaFree(l->ring_o);
+    delete l;
+    return 0;
+}
+
+int ndp_longlist_reset(ndp_longlist* l, const void* x_long, const void* u_long, const void* other_long, void* stream) {
+    if (!l || !x_long || !u_long || (l->ring_o && !other_long)) return fail(NDP_E_ARG, "ndp_longlist_reset: null argument");
+    DeviceGuard dg(l->dev);
+    const size_t eb = l->precision == NDP_F64 ? 8 : 4;
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaMemcpyAsync(l->ring_x, x_long, (size_t)l->B * l->len * 10 * eb, cudaMemcpyDefault, st));
+    CU(cudaMemcpyAsync(l->ring_u, u_long, (size_t)l->B * l->len * 4 * eb, cudaMemcpyDefault, st));
+    if (l->ring_o) CU(cudaMemcpyAsync(l->ring_o, other_long, (size_t)l->B * l->len * 6 * eb, cudaMemcpyDefault, st));
+    l->head = 0;
+    return 0;
+}
+
+int ndp_longlist_push(ndp_longlist* l, const void* new_x, const void* new_u, const void* new_other, void* xr, void* ur, void* other, void* stream) {
+    if (!l || !new_x || !new_u || !xr || !ur || (l->ring_o && (!new_other || !other))) return fail(NDP_E_ARG, "ndp_longlist_push: null argument");
+    DeviceGuard dg(l->dev);
+    l->head = (l->head + 1) % l->len;  // pop the front; the kernel appends at the freed slot
+    const long long per = (long long)(l->N + 1) * 10 + (long long)l->N * 4 + (l->ring_o ? (long long)(l->N + 1) * 6 : 0);
+    const long long tot = l->B * per;
+    const int grd = (int)((tot + 255) / 256);
+    if (l->precision == NDP_F32)
+        ndp::longlist_push_kernel<float><<<grd, 256, 0, (cudaStream_t)stream>>>(l->B, l->N, l->stride, l->len, l->head, (const float*)new_x, (const float*)new_u,
+                                                                                 (const float*)new_other, (float*)l->ring_x, (float*)l->ring_u, (float*)l->ring_o,
+                                                                                 (float*)xr, (float*)ur, (float*)other);
+    else
+        ndp::longlist_push_kernel<double><<<grd, 256, 0, (cudaStream_t)stream>>>(l->B, l->N, l->stride, l->len, l->head, (const double*)new_x, (const double*)new_u,
+                                                                                  (const double*)new_other, (double*)l->ring_x, (double*)l->ring_u, (double*)l->ring_o,
+                                                                                  (double*)xr, (double*)ur, (double*)other);
+    l->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int64_t ndp_longlist_launch_count(const ndp_longlist* l) { return l ? (int64_t)l->launches.load() : 0; }
 
 }  // extern "C"

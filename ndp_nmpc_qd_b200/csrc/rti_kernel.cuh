@@ -37,7 +37,7 @@ struct RtiCfg {
     int N, ipm_max_iter, polish_max, as_first_max;
     T h, inv_mass, g;
     T Q[10], R[4], hQ[10], hR[4], umin[4], umax[4], vmin[3], vmax[3];  // hQ = h Q, hR = h R (stage cost scaled by the interval)
-    T tol_mu, tol_res, mu0, t_floor, t_min, big;
+    T tol_mu, tol_res, mu0, t_floor, t_min;
 };
 
 template <typename T>
@@ -49,6 +49,7 @@ struct RtiArgs {
     T* U;           // [B][N][4]
     T* u0;          // [B][4] or null
     int32_t* status;  // [B]
+    int32_t* status2; // optional second destination of the status (a caller's output record), or null
     int32_t* stats;   // [B][4]
     // optional fused controller.update(): when xr != null the kernel builds yref / p from
     // (xr[B][N+1][10], ur[B][N][4], f[B][N+1][3] or null) itself and stores them in yref_w / par_w
@@ -297,7 +298,7 @@ struct StageMask {
 template <typename T>
 struct ActiveSet {
     StageMask lo_m, hi_m;
-    T lo, hi, big;
+    T lo, hi;
 };
 
 // One backward Riccati stage on the tile `sT` ([10][TLD]: columns 6..13 of [A_k B_k], then b_k), which
@@ -370,17 +371,18 @@ __device__ __forceinline__ bool backward_stage(const RtiCfg<T>& c, int N, int k,
             for (int m = 0; m < 4; m++) ws[WL.oHrow + (k * 4 + m) * 16 + 14] = H[10 + m];
         }
     }
+    // pinned inputs of the register-held active set (kBar == 2): flag and value (bound - iterate) of each input, known to
+    // every lane; the elimination itself happens on the gathered 4x4 block below
+    bool upin[4] = {false, false, false, false};
+    T ubeta[4] = {T(0), T(0), T(0), T(0)};
     if (kBar == 2) {
-        // pinned input m: penalty big (u_m - bound)^2 / 2 -> diagonal big, gradient -big * (bound - iterate)
         const bool at_lo = as->lo_m.test(k), at_hi = as->hi_m.test(k);
         const bool pin = (j >= 10 && j < 14) && (at_lo || at_hi);
         const T bnd = (at_lo ? as->lo : as->hi) - sU[k * NU + ((j - 10) & 3)];
-        const T g_own = pin ? -as->big * bnd : T(0);
 #pragma unroll
         for (int m = 0; m < 4; m++) {
-            const T gm = __shfl_sync(mask, g_own, 10 + m, GL);
-            if (j == 14) H[10 + m] += gm;
-            else H[10 + m] += (pin && j == 10 + m) ? as->big : T(0);
+            upin[m] = __shfl_sync(mask, (int)pin, 10 + m, GL) != 0;
+            ubeta[m] = __shfl_sync(mask, bnd, 10 + m, GL);
         }
     } else if (kBar == 1) {
         if (j < 14) {
@@ -393,11 +395,32 @@ __device__ __forceinline__ bool backward_stage(const RtiCfg<T>& c, int N, int k,
         }
     }
     // 4x4 input block G = Huu from lanes 10..13, Cholesky, solve for this lane's column
-    const T g00 = __shfl_sync(mask, H[10], 10, GL), g10 = __shfl_sync(mask, H[11], 10, GL);
-    const T g20 = __shfl_sync(mask, H[12], 10, GL), g30 = __shfl_sync(mask, H[13], 10, GL);
-    const T g11 = __shfl_sync(mask, H[11], 11, GL), g21 = __shfl_sync(mask, H[12], 11, GL);
-    const T g31 = __shfl_sync(mask, H[13], 11, GL), g22 = __shfl_sync(mask, H[12], 12, GL);
-    const T g32 = __shfl_sync(mask, H[13], 12, GL), g33 = __shfl_sync(mask, H[13], 13, GL);
+    T g00 = __shfl_sync(mask, H[10], 10, GL), g10 = __shfl_sync(mask, H[11], 10, GL);
+    T g20 = __shfl_sync(mask, H[12], 10, GL), g30 = __shfl_sync(mask, H[13], 10, GL);
+    T g11 = __shfl_sync(mask, H[11], 11, GL), g21 = __shfl_sync(mask, H[12], 11, GL);
+    T g31 = __shfl_sync(mask, H[13], 11, GL), g22 = __shfl_sync(mask, H[12], 12, GL);
+    T g32 = __shfl_sync(mask, H[13], 12, GL), g33 = __shfl_sync(mask, H[13], 13, GL);
+    const T hu0 = H[10], hu1 = H[11], hu2 = H[12], hu3 = H[13];  // un-eliminated rows of this column (what sHux keeps)
+    if (kBar == 2) {
+        // EXACT elimination of the pinned inputs: du_m = beta_m.  Their rows / columns leave the 4x4 block (identity
+        // instead), the free rows of the gradient column pick up G(f, m) beta_m, and the pinned rows of every column
+        // become the constant -beta_m (gradient lane) or 0, so that the common solve returns kappa_m = beta_m, K(m, :) = 0.
+        if (upin[0] | upin[1] | upin[2] | upin[3]) {
+            if (j == 14) {
+                H[10] += (upin[1] ? g10 * ubeta[1] : T(0)) + (upin[2] ? g20 * ubeta[2] : T(0)) + (upin[3] ? g30 * ubeta[3] : T(0));
+                H[11] += (upin[0] ? g10 * ubeta[0] : T(0)) + (upin[2] ? g21 * ubeta[2] : T(0)) + (upin[3] ? g31 * ubeta[3] : T(0));
+                H[12] += (upin[0] ? g20 * ubeta[0] : T(0)) + (upin[1] ? g21 * ubeta[1] : T(0)) + (upin[3] ? g32 * ubeta[3] : T(0));
+                H[13] += (upin[0] ? g30 * ubeta[0] : T(0)) + (upin[1] ? g31 * ubeta[1] : T(0)) + (upin[2] ? g32 * ubeta[2] : T(0));
+            }
+#pragma unroll
+            for (int m = 0; m < 4; m++)
+                if (upin[m]) H[10 + m] = (j == 14) ? -ubeta[m] : T(0);
+            if (upin[0]) { g00 = T(1); g10 = T(0); g20 = T(0); g30 = T(0); }
+            if (upin[1]) { g11 = T(1); g10 = T(0); g21 = T(0); g31 = T(0); }
+            if (upin[2]) { g22 = T(1); g20 = T(0); g21 = T(0); g32 = T(0); }
+            if (upin[3]) { g33 = T(1); g30 = T(0); g31 = T(0); g32 = T(0); }
+        }
+    }
     const T i00 = trsqrt(g00);
     const T l10 = g10 * i00, l20 = g20 * i00, l30 = g30 * i00;
     const T e1 = g11 - l10 * l10;
@@ -428,7 +451,7 @@ __device__ __forceinline__ bool backward_stage(const RtiCfg<T>& c, int N, int k,
         if (pins) {  // uniform over the group
             vpins = true;
             const T beta_own = mine ? ((as->lo_m.test(k1) ? as->lo : as->hi) - sX[k1 * NX + j]) : T(0);
-            T D[3][4], beta[3], Y[3][4];
+            T D[3][4], Df[3][4], beta[3], Y[3][4];
 #pragma unroll
             for (int a = 0; a < 3; a++) {
                 const bool on = (pins >> a) & 1u;
@@ -436,7 +459,8 @@ __device__ __forceinline__ bool backward_stage(const RtiCfg<T>& c, int N, int k,
 #pragma unroll
                 for (int m = 0; m < 4; m++) {
                     const T d = __shfl_sync(mask, col[3 + a], 10 + m, GL);
-                    D[a][m] = on ? d : T(0);
+                    Df[a][m] = on ? d : T(0);                 // E B, every input (right-hand side: pinned inputs move x+ by B beta)
+                    D[a][m] = (on && !upin[m]) ? d : T(0);    // E B restricted to the free inputs (the constraint's handle)
                 }
                 // Y_a = G^-1 D_a' with the Cholesky factors of G
                 const T f0 = D[a][0] * i00;
@@ -467,7 +491,7 @@ __device__ __forceinline__ bool backward_stage(const RtiCfg<T>& c, int N, int k,
             T r[3];
 #pragma unroll
             for (int a = 0; a < 3; a++)
-                r[a] = ((pins >> a) & 1u) ? (((j == 14) ? beta[a] : T(0)) - col[3 + a] + dot4(D[a], xs)) : T(0);
+                r[a] = ((pins >> a) & 1u) ? (((j == 14) ? beta[a] : T(0)) - col[3 + a] + dot4(Df[a], xs)) : T(0);
             const T q0 = r[0] * j00;
             const T q1 = (r[1] - m10 * q0) * j11;
             const T q2 = (r[2] - m20 * q0 - m21 * q1) * j22;
@@ -487,7 +511,7 @@ __device__ __forceinline__ bool backward_stage(const RtiCfg<T>& c, int N, int k,
             }
         }
     }
-    if (j < 10) Vec4<T>::st(sHux + j * 4, H[10], H[11], H[12], H[13]);
+    if (j < 10) Vec4<T>::st(sHux + j * 4, hu0, hu1, hu2, hu3);
     // feedback rows for the forward sweep: rec[k][10+m][j] = K(m, j), [10] = kappa_m
     if (j < 10 || j == 14) {
         T* kr = ws + WL.oRec + ((long long)k * 14 + 10) * TLD + ((j == 14) ? 10 : j);
@@ -797,8 +821,8 @@ constexpr int AS_HIST = 6;  // active-set hashes remembered for the cycle test
 // the rounds again from that estimate.
 template <typename T, int kN>
 __device__ __forceinline__ void constrained_qp(const RtiCfg<T>& c, int lane, unsigned mask, T* sm, T* ws, const T* sTriv, T dx0, T lo, T hi,
-                                               T* gX, T* gU, T* gu0, int32_t* g_status, int32_t* g_stats, unsigned long long* g_as,
-                                               bool keep_set, int n_fact0) {
+                                               T* gX, T* gU, T* gu0, int32_t* g_status, int32_t* g_status2, int32_t* g_stats,
+                                               unsigned long long* g_as, bool keep_set, int n_fact0) {
     const int N = (kN > 0) ? kN : c.N;
     const SmemLayout L(N);
     const WsLayout WL(N);
@@ -820,7 +844,7 @@ __device__ __forceinline__ void constrained_qp(const RtiCfg<T>& c, int lane, uns
     const int FS = N * 16;  // field stride
     bool ipm_ok = false, pol_ok = false;
     ActiveSet<T> as;
-    as.lo = lo; as.hi = hi; as.big = c.big;
+    as.lo = lo; as.hi = hi;
     bool lin_done = false;  // [A B b] tiles of this iterate are in the workspace
     // a released variable that lands within a few ulps of its bound is not a violation (it would be re-pinned and
     // released for ever)
@@ -1130,10 +1154,8 @@ __device__ __forceinline__ void constrained_qp(const RtiCfg<T>& c, int lane, uns
         // stage loses about three digits to it: fp32 ends 2e-4 off the solution, fp64 5e-13.  One more sweep with the
         // same factorisation structure, linearised AT the computed step (iterate advanced in shared memory, stage
         // residuals b zeroed, cost gradient and pinned values re-evaluated there), solves for the small remainder.
-        // (The fp64 build takes the sweep whenever anything is pinned: it also removes the O(multiplier / big) offset of
-        // the penalty that pins the inputs, 1e-8 on u0 otherwise.)
-        const bool any_pin = (as.lo_m.w0 | as.lo_m.w1 | as.hi_m.w0 | as.hi_m.w1) != 0ull;
-        if (__any_sync(mask, any_pin && (isv || (sizeof(T) == 8 && isu)))) {
+        const bool vown = isv && ((as.lo_m.w0 | as.lo_m.w1 | as.hi_m.w0 | as.hi_m.w1) != 0ull);
+        if (sizeof(T) == 4 && __any_sync(mask, vown)) {
             T* sY = sm + L.oY;
             if (lane < 14)
                 for (int k = 0; k <= N; k++) {
@@ -1209,6 +1231,7 @@ __device__ __forceinline__ void constrained_qp(const RtiCfg<T>& c, int lane, uns
     }
     if (lane == 0) {
         *g_status = status;
+        if (g_status2) *g_status2 = status;
         g_stats[0] = n_fact;
         g_stats[1] = n_ipm;
         g_stats[2] = n_pol;
@@ -1413,6 +1436,7 @@ __global__ void __launch_bounds__(RTI_CTA, (sizeof(T) == 4) ? (kLat ? 4 : 8) : 3
 #endif
             if (lane == 0) {
                 a.status[prob] = status;
+                if (a.status2) a.status2[prob] = status;
                 a.stats[prob * 4 + 0] = 1;
                 a.stats[prob * 4 + 1] = 0;
                 a.stats[prob * 4 + 2] = 0;
@@ -1464,7 +1488,8 @@ __global__ void __launch_bounds__(RTI_CTA, (sizeof(T) == 4) ? 4 : 2) rti_constra
             __syncwarp(mask);
             const T dx0 = isx ? a.x0[(size_t)prob * NX + lane] - sm[L.oX + lane] : T(0);
             constrained_qp<T, kN>(c, lane, mask, sm, ws, sTriv, dx0, lo, hi, a.X + (size_t)prob * (N + 1) * NX, a.U + (size_t)prob * N * NU,
-                                  a.u0 ? a.u0 + (size_t)prob * NU : nullptr, a.status + prob, a.stats + (size_t)prob * 4,
+                                  a.u0 ? a.u0 + (size_t)prob * NU : nullptr, a.status + prob, a.status2 ? a.status2 + prob : nullptr,
+                                  a.stats + (size_t)prob * 4,
                                   a.as_store + (size_t)prob * (AS_OWNERS * 4), a.as_warm != 0, (entry & QUEUE_SWEPT) ? 1 : 0);
             // the tiles' zero pad columns (the sweeps of this problem may have run the ring over them)
             for (int i = lane; i < 20; i += GL) { T* q = sm + L.oT0 + i * TLD + 9; q[0] = T(0); q[1] = T(0); q[2] = T(0); }

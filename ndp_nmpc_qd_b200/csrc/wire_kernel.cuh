@@ -102,3 +102,45 @@ __global__ void cmd_from_u0_dev_kernel(long long n, const T* __restrict__ u0, do
 }
 
 }  // namespace ndp
+
+// ---- device-resident sliding reference list (NMPCRefPublisher, pt_pub/pt_publisher.py:57-103) ----
+// The reference keeps `long_list_size` = 101 points (x, u) at ts_nmpc = 0.02 s per quadrotor and, every control tick,
+// pops the front, appends ONE new point (the trajectory at t + T_horizon) and hands the controller every 5th point
+// (xr = list[0::5], 21 nodes; ur = the same without its last entry; params/nmpc_params.py:40-43).  Here the lists live
+// on the device as rings -- list[i] = ring[(head + i) % len] -- so a tick uploads one point per quadrotor instead of the
+// whole horizon; `other` is the neighbour's list (the 6 position / velocity columns DownwashNN reads), fed by the
+// neighbour's own new point.  One thread per output element; node N takes the new point straight from the input.
+namespace ndp {
+
+template <typename T>
+__global__ void longlist_push_kernel(long long B, int N, int stride, int len, int head, const T* __restrict__ new_x, const T* __restrict__ new_u,
+                                     const T* __restrict__ new_o, T* __restrict__ ring_x, T* __restrict__ ring_u, T* __restrict__ ring_o,
+                                     T* __restrict__ xr, T* __restrict__ ur, T* __restrict__ other) {
+    const int nx = (N + 1) * 10, nu = N * 4, no = ring_o ? (N + 1) * 6 : 0;
+    const int per = nx + nu + no;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= B * per) return;
+    const long long b = idx / per;
+    int r = (int)(idx - b * per);
+    const int tail = (head + len - 1) % len;  // where the appended point goes (head is the list's front AFTER the pop)
+    if (r < nx) {
+        const int k = r / 10, e = r - k * 10;
+        const int slot = (head + stride * k) % len;
+        // a node that falls on the list's last entry reads the point appended by this very tick
+        xr[b * nx + r] = (stride * k == len - 1) ? new_x[b * 10 + e] : ring_x[(b * len + slot) * 10 + e];
+        if (k == 0) ring_x[(b * len + tail) * 10 + e] = new_x[b * 10 + e];  // tail = the slot the pop just freed: nobody reads it
+    } else if (r < nx + nu) {
+        r -= nx;
+        const int k = r / 4, e = r - k * 4;
+        ur[b * nu + r] = ring_u[(b * len + (head + stride * k) % len) * 4 + e];
+        if (k == 0) ring_u[(b * len + tail) * 4 + e] = new_u[b * 4 + e];  // the new u point is not part of this tick's ur
+    } else {
+        r -= nx + nu;
+        const int k = r / 6, e = r - k * 6;
+        const int slot = (head + stride * k) % len;
+        other[b * no + r] = (stride * k == len - 1) ? new_o[b * 6 + e] : ring_o[(b * len + slot) * 6 + e];
+        if (k == 0) ring_o[(b * len + tail) * 6 + e] = new_o[b * 6 + e];
+    }
+}
+
+}  // namespace ndp

@@ -172,6 +172,16 @@ class Engine:
     def launch_count(self) -> int:
         return int(self.lib.ndp_launch_count(self._h))
 
+    def kernel_timing(self, enable: bool = True) -> None:
+        """Measurement aid (ndp_kernel_timing): events around the two kernels of every solve."""
+        _lib.check(self.lib.ndp_kernel_timing(self._h, 1 if enable else 0), "ndp_kernel_timing")
+
+    def last_kernel_ms(self):
+        """(nominal kernel ms, constrained kernel ms) of the last solve; waits for it."""
+        a, b = C.c_float(), C.c_float()
+        _lib.check(self.lib.ndp_last_kernel_ms(self._h, C.byref(a), C.byref(b)), "ndp_last_kernel_ms")
+        return float(a.value), float(b.value)
+
 
 class BatchedOcpSolver:
     """acados-style surface over `Engine` with host mirrors, so that the per-stage

@@ -116,3 +116,76 @@ class SwarmStep:
         u0 = self.engine.update(x0, xr, ur, f, u0)
         self._mark("update")
         return u0
+
+
+def lattice_swarm(n_all: int, seed: int = 0):
+    """quads on a square lattice of 0.8 m pitch, altitude offsets U(0, 3) m, phase-shifted
+    eight_low references.  Returns (position offsets [n,3], trajectory phases [n])."""
+    import numpy as np
+
+    side = int(np.ceil(np.sqrt(n_all)))
+    rng = np.random.default_rng(seed)
+    off = np.stack([(np.arange(n_all) % side) * 0.8, (np.arange(n_all) // side) * 0.8, rng.uniform(0.0, 3.0, n_all)], 1)
+    return off, rng.uniform(0, 20.0, n_all)
+
+
+def time_swarm(n_all: int, modes, steps: int = 50, warmup: int = 100, device=None, N: int = 20) -> dict:
+    """Times the coupled-swarm RTI step (reference generation + exchange + gated all-pairs MLP + local solves) of
+    `n_all` quads sharded over the ranks of the initialised process group, for each exchange mode; device time, max over
+    ranks.  With more than one mode the forces of the modes are compared bit for bit."""
+    import numpy as np
+    import torch.distributed as dist
+
+    from . import traj_gen
+    from .traj_gen.refgen import RefGen
+
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    dev = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+    off, t0 = lattice_swarm(n_all)
+    rg = RefGen([traj_gen.plan_named("eight_low")], device=dev)
+    out, forces = {}, {}
+    # every mode is measured twice in turn and the second pass is reported: the first timed loop over freshly allocated
+    # buffers runs 2-3 x slower than the same loop a moment later, whichever mode it is (tests/diag/swarm_multi_gpu.py)
+    for rep, mode in [(r, m) for r in range(2) for m in modes]:
+        sw = SwarmStep(n_all, N=N, mode=mode, device=dev)
+        b, e = sw.begin, sw.end
+        t_loc = torch.as_tensor(t0[b:e], device=dev)
+        off_loc = torch.as_tensor(off[b:e], device=dev).contiguous()
+        xr, ur = rg.horizon(t_loc, None, N, 0.1, off_loc)
+        x0 = xr[:, 0].contiguous()
+        sw.engine.reset(xr, ur)
+        u0 = torch.empty((max(e - b, 1), 4), dtype=torch.float32, device=dev)
+        for _ in range(warmup):
+            sw.step(x0, xr, ur, None, u0)
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            t_loc.add_(0.02)
+            rg.horizon(t_loc, None, N, 0.1, off_loc, xr=xr, ur=ur)
+            sw.step(x0, xr, ur, None, u0)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        bad = torch.tensor([int((sw.engine.status()[: e - b] != 0).sum())], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            dist.all_reduce(bad)
+        stats = sw.engine.stats()[: e - b]
+        first = out.get(sw.mode, {}).get("ms_per_step")
+        out[sw.mode] = dict(ms_per_step=float(ms) / steps, quad_steps_per_s=n_all * steps / (float(ms) * 1e-3), status_nonzero=int(bad),
+                            riccati_sweeps_max_rank0=int(stats[:, 0].max()) if e > b else 0)
+        if first is not None:
+            out[sw.mode]["ms_per_step_first_pass"] = first
+        forces[sw.mode] = sw.f[: e - b].clone()
+        del sw
+    if len(forces) > 1:
+        ks = list(forces)
+        same = all(torch.equal(forces[ks[0]], forces[k]) for k in ks[1:])
+        flag = torch.tensor([int(same)], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        out["modes_bit_identical"] = bool(int(flag))
+    return out

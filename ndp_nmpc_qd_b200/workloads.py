@@ -114,9 +114,11 @@ def independent_problems(B, N=20, seed=0, scale=1.0, name=None, with_neighbour=F
     xr = np.zeros((B, N + 1, 10))
     ur = np.zeros((B, N, 4))
     which = rng.random(B) < 0.5 if name is None else np.full(B, name == "eight_high_dyn")
+    t0_all = np.zeros(B)
     for nm, mask in (("eight_high_dyn", which), ("eight_low", ~which)):
         if mask.any():
             t0 = rng.uniform(0.0, PATHS[nm][0], size=int(mask.sum()))
+            t0_all[mask] = t0
             xr[mask], ur[mask] = reference_horizon(t0, N, 0.1, nm)
     x0 = xr[:, 0, :].copy()
     x0[:, 0:3] += scale * 0.1 * rng.normal(size=(B, 3))
@@ -124,13 +126,32 @@ def independent_problems(B, N=20, seed=0, scale=1.0, name=None, with_neighbour=F
     dq = random_rotation_quat(rng, B, np.deg2rad(min(10.0 * scale, 170.0)))
     q = quat_mul(x0[:, 6:10], dq)
     x0[:, 6:10] = q / np.linalg.norm(q, axis=1, keepdims=True)
-    out = dict(x0=x0, xr=xr, ur=ur)
+    out = dict(x0=x0, xr=xr, ur=ur, t0=t0_all, high_dyn=which)
     if with_neighbour:
         other = xr.copy()
         off = np.concatenate([rng.uniform(-0.5, 0.5, size=(B, 2)), rng.uniform(0.5, 1.5, size=(B, 1))], 1)
         other[:, :, 0:3] += off[:, None, :]
         other[:, :, 3:6] += 0.1 * rng.normal(size=(B, 1, 3))
         out["other"] = other
+        out["other_offset"] = np.concatenate([off, other[:, 0, 3:6] - xr[:, 0, 3:6]], 1)  # constant (p, v) offset of the neighbour
+    return out
+
+
+def sliding_lists(w, n_ticks, ts=0.02, length=101):
+    """The 50 Hz lists NMPCRefPublisher keeps (pt_pub/pt_publisher.py:57-103) for the problems of `independent_problems`:
+    point i = the reference at t0 + ts * i, i < length + n_ticks; tick j sees points j .. j + length - 1, i.e. every 5th of
+    them is the horizon at t0 + ts * j.  Returns float64 x_list [B, length + n_ticks, 10], u_list [.., 4] and, when the
+    workload has a neighbour, other_list [.., 6] (its position / velocity columns)."""
+    B = w["x0"].shape[0]
+    n = length + n_ticks
+    xl, ul = np.zeros((B, n, 10)), np.zeros((B, n, 4))
+    for nm, mask in (("eight_high_dyn", w["high_dyn"]), ("eight_low", ~w["high_dyn"])):
+        if mask.any():
+            t = w["t0"][mask][:, None] + ts * np.arange(n)[None, :]
+            xl[mask], ul[mask] = diff_flatness(*figure_eight(t, nm))
+    out = dict(x_list=xl, u_list=ul)
+    if "other_offset" in w:
+        out["other_list"] = xl[:, :, 0:6] + w["other_offset"][:, None, :]
     return out
 
 

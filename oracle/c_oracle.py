@@ -71,7 +71,7 @@ def make_cfg(N=20, T=None, tol=None, tol_mu=None, max_iter=100, u_min=None, u_ma
     # default: IPM to 1e-9 (enough to identify the active set while the barrier-weighted Riccati recursion is still
     # accurate) + exact active-set polish; an explicit tol gives the plain IPM (HPIPM-like work: tol=1e-8, max_iter=50)
     if polish is None:
-        polish = 20 if tol is None else 0
+        polish = 150 if tol is None else 0  # rounds; the damped phase after a detected cycle releases one bound per round
     if tol is None:
         tol = 1e-9
     c.tol, c.max_iter, c.mu0, c.t_floor = tol, max_iter, 10.0, 0.1

@@ -595,6 +595,16 @@ static int orc_polish(const orc_cfg* c, orc_ws* w, orc_aset* as, real (*dx)[NX],
             } else if (wx) as->av[wk][wm] = 0; else as->au[wk][wm] = 0;
             changed = 1;
         }
+        if (getenv("ORC_KTOP")) {
+            static signed char prev_u[NMAX][NU], prev_v[NMAX + 1][NBX];
+            int ktop = -1;
+            for (int k = 0; k < N; k++) {
+                for (int m = 0; m < NU; m++) if (as->au[k][m] != prev_u[k][m]) ktop = k > ktop ? k : ktop;
+                for (int m = 0; m < NBX; m++) if (as->av[k][m] != prev_v[k][m]) ktop = (k - 1) > ktop ? (k - 1) : ktop;
+            }
+            memcpy(prev_u, as->au, sizeof(prev_u)); memcpy(prev_v, as->av, sizeof(prev_v));
+            fprintf(stderr, "KTOP %d %d\n", r, ktop);
+        }
         if (!changed) { fixed = 1; r++; break; }
     }
     if (fixed) {

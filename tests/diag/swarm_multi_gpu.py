@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--check", action="store_true")
     ap.add_argument("--breakdown", action="store_true")
     ap.add_argument("--trace", action="store_true", help="per-phase device time inside the timed step loop (CUDA event marks)")
+    ap.add_argument("--dump", default=None, help="directory: every rank saves the forces of its shard after the last step (per mode)")
     a = ap.parse_args()
     rank, world, lr = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(lr)
@@ -95,6 +96,9 @@ def main():
             t_loc.copy_(t_keep)
             sw.f.copy_(f_keep)
         f_by_mode[mode] = sw.f[: e - b].clone()
+        if a.dump:
+            os.makedirs(a.dump, exist_ok=True)
+            np.save(os.path.join(a.dump, f"f_{mode}_w{world}_r{rank}.npy"), sw.f[: e - b].cpu().numpy())
         if a.breakdown:
             import time
 

@@ -239,12 +239,15 @@ def main():
     CLOCK[0] = 100.0
     pub.reset(tc, Time(CLOCK[0]))
     xr0, ur0 = pub.get_nmpc_ref_from_long_list()
-    seq_x, seq_u = [xr0], [ur0]
+    out["longlist_x_init"], out["longlist_u_init"] = np.array(pub.x_long_list), np.array(pub.u_long_list)  # the 101 points after reset
+    seq_x, seq_u, new_x, new_u = [xr0], [ur0], [], []
     for j in range(130):
         xr_j, ur_j = pub.get_nmpc_pts(Time(CLOCK[0]))
         seq_x.append(xr_j); seq_u.append(ur_j)
+        new_x.append(pub.x_long_list[-1]); new_u.append(pub.u_long_list[-1])  # the point this tick appended
         CLOCK[0] += 0.02
     out["longlist_xr"], out["longlist_ur"] = np.stack(seq_x), np.stack(seq_u)
+    out["longlist_new_x"], out["longlist_new_u"] = np.stack(new_x), np.stack(new_u)
     # the hover reference before any trajectory (gen_fix_pt_ref, pt_publisher.py:40-55)
     xf, uf = NMPCRefPublisher().gen_fix_pt_ref(sim.mul_odom[0])
     out["fixpt_xr"], out["fixpt_ur"] = xf, uf

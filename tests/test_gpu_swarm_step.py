@@ -44,3 +44,29 @@ def test_swarm_step_vs_oracles(built_lib, c_oracle, mlp_weights):
     assert ok.mean() > 0.98 and np.all(st[ok] == 0)
     assert rel_err(u0[ok], r["u0"][ok]) < 1e-4
     assert rel_err(sw.engine.get_all("x").cpu().numpy().astype(np.float64)[ok], X[ok]) < 1e-4
+
+
+def test_swarm_two_gpus_bit_identical(built_lib, tmp_path):
+    """Config 4 on two GPUs (skipped on a one-GPU box): the fused peer-memory exchange, the NCCL all-gather path and the
+    single-GPU run must produce the same downwash forces bit for bit, and match the CPU oracle (tests/diag/swarm_multi_gpu.py
+    --check asserts p2p == all-gather and |f - oracle| < 1e-4 on every rank)."""
+    import os
+    import subprocess
+    import sys
+
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = os.path.join(root, "tests", "diag", "swarm_multi_gpu.py")
+    common = ["--quads", "300", "--steps", "4", "--warmup", "3", "--repeat", "1", "--check", "--dump", str(tmp_path)]
+    r1 = subprocess.run([sys.executable, script] + common, capture_output=True, text=True, timeout=600)
+    assert r1.returncode == 0, r1.stdout + r1.stderr
+    r2 = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                         "--master-port", "29641", script] + common, capture_output=True, text=True, timeout=600)
+    assert r2.returncode == 0, r2.stdout + r2.stderr
+    single = np.load(tmp_path / "f_local_w1_r0.npy")
+    for mode in ("p2p", "allgather"):
+        both = np.concatenate([np.load(tmp_path / f"f_{mode}_w2_r{r}.npy") for r in (0, 1)])
+        assert np.array_equal(both, single), mode
