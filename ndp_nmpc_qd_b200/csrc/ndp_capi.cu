@@ -77,6 +77,8 @@ struct ndp_handle {
     unsigned long long* as_store;  // [B][AS_OWNERS][4] active set a problem's constrained solve starts from
     long long ws_stride;           // nominal kernel: forward-sweep records only
     int slots, grid, ppc, lat;
+    int ppc_c;                     // problems per CTA / dynamic smem of the constrained kernel (its layout carries the QP step array)
+    size_t smem_c;
     void* ws_c;                    // constrained kernel: [slots_c][ws_c_stride]
     long long ws_c_stride;
     int slots_c, grid_c;
@@ -268,9 +270,12 @@ int launch_solve(ndp_handle* h, const void* x0, void* u0, cudaStream_t st, const
     if (h->timing) cudaEventRecord(h->tev[1], st);
     // the problems whose unconstrained step left its box: second kernel, launched as a programmatic dependent so that its
     // launch latency hides under the nominal kernel (it exits at once when the queue is empty)
+    a.ws_n = (T*)h->ws;
+    a.ws_n_stride = h->ws_stride;
+    a.ws_n_slots = h->slots;
     a.ws = (T*)h->ws_c;
     a.ws_stride = h->ws_c_stride;
-    inst.claunch(h->grid_c, thr, h->smem, st, c, a);
+    inst.claunch(h->grid_c, h->ppc_c * GL, h->smem_c, st, c, a);
     h->launches += 2;
     CU(cudaGetLastError());
     if (h->timing) cudaEventRecord(h->tev[2], st);
@@ -370,16 +375,31 @@ int ndp_create(const ndp_config* cfg, ndp_handle** out) {
     h->elt = cfg->precision == NDP_F64 ? 8 : 4;
     h->launches = 0;
     const int N = cfg->N, B = cfg->batch;
-    const SmemLayout L(N);
+    const SmemLayout L(N, true), Lc(N);
     const WsLayout WL(N);
-    h->ppc = 4;  // 64-thread CTAs: 4096 problems -> 1024 CTAs = 6.9 per SM (8-problem CTAs leave a 15 % imbalance)
-    while (h->ppc > 1 && ((size_t)L.total * h->ppc + 10 * TLD) * h->elt > 200 * 1024) h->ppc >>= 1;  // long horizons / fp64: fewer problems per CTA
-    h->smem = ((size_t)L.total * h->ppc + 10 * TLD) * h->elt;
-    if (h->smem > 227 * 1024) { delete h; return fail(NDP_E_CONFIG, "ndp_create: horizon too long for shared memory"); }
-    const int need = (B + h->ppc - 1) / h->ppc;
+    auto smem_of = [&](const SmemLayout& l, int ppc) { return ((size_t)l.total * ppc + 10 * TLD) * h->elt; };
     const void* kfn = nullptr;
     cudaError_t e = cudaSuccess;
     int occ = 0;
+    // Problems per CTA: 4 (64-thread CTAs: 4096 problems -> 1024 CTAs = 6.9 per SM; 8-problem CTAs leave a 15 % imbalance)
+    // unless a smaller CTA keeps more problems resident per SM -- long horizons and fp64 are bound by shared memory
+    // (N = 80 fp32: 14 KB per problem -> 3 CTAs of 4, but 7 CTAs of 2)
+    {
+        int best = -1, best_ppc = 0;
+        const void* k0 = rti_kernel_ptr(h->elt, N, false);
+        for (int ppc = 4; ppc >= 1; ppc >>= 1) {
+            const size_t sm = smem_of(L, ppc);
+            if (sm > 227 * 1024) continue;
+            if (raise_dyn_smem(k0, dev, sm) != 0) continue;
+            int o = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k0, ppc * GL, sm) != cudaSuccess) { cudaGetLastError(); continue; }
+            if (o * ppc > best) { best = o * ppc; best_ppc = ppc; }
+        }
+        if (best_ppc == 0) { delete h; return fail(NDP_E_CONFIG, "ndp_create: horizon too long for shared memory"); }
+        h->ppc = best_ppc;
+    }
+    h->smem = smem_of(L, h->ppc);
+    const int need = (B + h->ppc - 1) / h->ppc;
     // latency build first (fp32): taken when the whole batch is resident at its lower occupancy
     for (int lat = (h->elt == 4 && N == 20) ? 1 : 0; lat >= 0; lat--) {
         kfn = rti_kernel_ptr(h->elt, N, lat != 0);
@@ -396,13 +416,18 @@ int ndp_create(const ndp_config* cfg, ndp_handle** out) {
     h->ws_stride = WL.oBarD;  // the nominal kernel only keeps the stage records of its forward sweep
     {
         const void* cfn = rti_ckernel_ptr(h->elt, N);
-        e = (cudaError_t)raise_dyn_smem(cfn, dev, h->smem);
+        h->ppc_c = 4;
+        while (h->ppc_c > 1 && smem_of(Lc, h->ppc_c) > 200 * 1024) h->ppc_c >>= 1;
+        h->smem_c = smem_of(Lc, h->ppc_c);
+        if (h->smem_c > 227 * 1024) { delete h; return fail(NDP_E_CONFIG, "ndp_create: horizon too long for shared memory"); }
+        e = (cudaError_t)raise_dyn_smem(cfn, dev, h->smem_c);
         int occ_c = 0;
-        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, cfn, h->ppc * GL, h->smem);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, cfn, h->ppc_c * GL, h->smem_c);
         if (e != cudaSuccess || occ_c < 1) { delete h; return e != cudaSuccess ? cuda_fail(e, "constrained kernel occupancy") : fail(NDP_E_CONFIG, "constrained kernel does not fit"); }
         const int cap_c = n_sm * occ_c;
-        h->grid_c = need < cap_c ? need : cap_c;
-        h->slots_c = h->grid_c * h->ppc;
+        const int need_c = (B + h->ppc_c - 1) / h->ppc_c;
+        h->grid_c = need_c < cap_c ? need_c : cap_c;
+        h->slots_c = h->grid_c * h->ppc_c;
         h->ws_c_stride = WL.total;
     }
     const size_t eb = (size_t)h->elt;

@@ -71,6 +71,11 @@ struct RtiArgs {
     int* queue;
     int* qctl;
     int B;
+    // constrained kernel only: the nominal kernel's record workspace (its slot s holds the stage tiles of problem s when
+    // no slot was reused, i.e. ws_n_slots >= B)
+    T* ws_n;
+    long long ws_n_stride;
+    int ws_n_slots;
 };
 
 constexpr int AS_OWNERS = 7;
@@ -81,11 +86,13 @@ __host__ __device__ constexpr int al4(int o) { return (o + 3) & ~3; }
 // ---- per-problem shared memory layout (elements of T; every region 4-element aligned) ----
 struct SmemLayout {
     int oX, oU, oPar, oY, oDz, oP, op, oT0, oT1, oHux, total;  // oY and oDz are adjacent: see forward_sweep
-    __host__ __device__ constexpr explicit SmemLayout(int N)
+    // nominal: the layout of rti_step_kernel, which never forms a QP step array (sDz, (N+1) x 16 elements -- 5 KB of the
+    // 19 KB per problem at N = 80): only the constrained kernel's layout carries it
+    __host__ __device__ constexpr explicit SmemLayout(int N, bool nominal = false)
         : oX(0), oU(al4((N + 1) * NX)), oPar(oU + N * NU), oY(oPar + (N + 1) * NPS), oDz(oY + (N + 1) * SYS),
           // QP step [k][lane]; the FW_RING x (14 x TLD) ring of the accepted forward sweep runs from oY over sDz, P+,
           // p+ and the tiles: oY .. oHux must span at least FW_RING * 14 * TLD elements (static_assert below)
-          oP(oY + (((N + 1) * (SYS + 16) > 4 * 14 * TLD) ? (N + 1) * (SYS + 16) : 4 * 14 * TLD)),
+          oP(oY + (((N + 1) * (nominal ? SYS : SYS + 16) > 636) ? (N + 1) * (nominal ? SYS : SYS + 16) : 636)),
           op(oP + 10 * 12),        // P+ rows, stride 12; then p+
           oT0(op + 12),            // tile of stage k:   rows r = 0..9 of [A B](:,6..13) | b | pad3, stride TLD
           oT1(oT0 + 10 * TLD),     // tile of stage k-1 (the integrator fills two stages per pass)
@@ -96,7 +103,7 @@ struct SmemLayout {
 
 // ---- per-slot global workspace layout (elements of T) ----
 struct WsLayout {
-    long long oRec, oBarD, oBarG, oIpm, oZc, oHrow, oTv, total;
+    long long oRec, oBarD, oBarG, oIpm, oZc, oHrow, oTv, oPs, total;
     __host__ __device__ constexpr explicit WsLayout(int N)
         : oRec(0),                                   // [k][14][TLD]: rows 0..9 = tile rows (x-lane records of the
                                                      // forward sweep), rows 10..13 = [K(m, 0..9) kappa_m pad]
@@ -105,7 +112,9 @@ struct WsLayout {
           oHrow(oZc + (long long)(N + 1) * 16),  // [k][m][16]: row m of [Hux Guu], [14] = gradient
           oTv(oHrow + (long long)N * 4 * 16),    // [k][a][12]: multiplier row of pinned velocity component a of stage k+1:
                                                  // nu = -(T(a, 0..9) . dx_k + T(a, 10))
-          total(oTv + (long long)N * 3 * 12) {}
+          oPs(oTv + (long long)N * 3 * 12),      // [k][132]: (P_k | p_k) as left in shared memory by backward stage k -- lets an
+                                                 // active-set round restart its backward sweep at the highest stage that changed
+          total(oPs + (long long)N * 132) {}
 };
 
 template <typename T> struct Vec4;
@@ -317,7 +326,7 @@ struct ActiveSet {
 // With kRows the rows T = S^-1 R are kept for the multiplier test  nu = -(T_x dx_k + t_0).
 template <typename T, int kBar, bool kRows>
 __device__ __forceinline__ bool backward_stage(const RtiCfg<T>& c, int N, int k, int j, unsigned mask, T* sm, const SmemLayout& L, T* ws,
-                                               const WsLayout& WL, const T* __restrict__ sT, const T* __restrict__ colp,
+                                               const WsLayout& WL, T* rec, const T* __restrict__ sT, const T* __restrict__ colp,
                                                const ActiveSet<T>* as) {
     const T* sX = sm + L.oX;
     const T* sU = sm + L.oU;
@@ -514,7 +523,7 @@ __device__ __forceinline__ bool backward_stage(const RtiCfg<T>& c, int N, int k,
     if (j < 10) Vec4<T>::st(sHux + j * 4, hu0, hu1, hu2, hu3);
     // feedback rows for the forward sweep: rec[k][10+m][j] = K(m, j), [10] = kappa_m
     if (j < 10 || j == 14) {
-        T* kr = ws + WL.oRec + ((long long)k * 14 + 10) * TLD + ((j == 14) ? 10 : j);
+        T* kr = rec + ((long long)k * 14 + 10) * TLD + ((j == 14) ? 10 : j);
         kr[0] = K0; kr[TLD] = K1; kr[2 * TLD] = K2; kr[3 * TLD] = K3;
     }
     __syncwarp(mask);
@@ -544,6 +553,19 @@ __device__ __forceinline__ bool backward_stage(const RtiCfg<T>& c, int N, int k,
         Vec4<T>::st(sp + 8, Pn[8], Pn[9], T(0), T(0));
     }
     __syncwarp(mask);
+    if (kBar == 2) {
+        // keep (P_k | p_k) -- 132 contiguous elements from sP -- for partial sweeps of later rounds
+        T* dst = ws + WL.oPs + (long long)k * 132;
+#pragma unroll
+        for (int q = 0; q < 3; q++) {
+            const int idx = j + q * GL;
+            if (idx < 33) {
+                T a0, a1, a2, a3;
+                Vec4<T>::ld(sP + idx * 4, a0, a1, a2, a3);
+                Vec4<T>::st(dst + idx * 4, a0, a1, a2, a3);
+            }
+        }
+    }
     return ok && ok_v;
 }
 
@@ -568,8 +590,27 @@ __device__ __forceinline__ void tile_to_ws(const T* __restrict__ sT, T* __restri
 // re-loaded from the workspace, one stage ahead of their use.
 template <typename T, bool kLin, int kBar, bool kRows>
 __device__ __forceinline__ bool backward_sweep(const RtiCfg<T>& c, int N, int j, unsigned mask, T* sm, const SmemLayout& L, T* ws,
-                                               const WsLayout& WL, const T* __restrict__ sTriv, const ActiveSet<T>* as, bool zero_b = false) {
-    backward_terminal<T>(c, N, j, mask, sm, L);
+                                               const WsLayout& WL, T* rec, const T* __restrict__ sTriv, const ActiveSet<T>* as, bool zero_b = false,
+                                               int k_top = 1 << 30) {
+    // k_top (!kLin, kBar == 2): the highest stage whose pins changed since the previous sweep of this problem -- the
+    // stages above it are unchanged, so the recursion restarts from the saved (P, p) of stage k_top + 1
+    const int k_first = (!kLin && kBar == 2 && k_top < N - 1) ? k_top : N - 1;
+    if (k_first == N - 1) {
+        backward_terminal<T>(c, N, j, mask, sm, L);
+    } else {
+        const T* src = ws + WL.oPs + (long long)(k_first + 1) * 132;
+        T* sP = sm + L.oP;
+#pragma unroll
+        for (int q = 0; q < 3; q++) {
+            const int idx = j + q * GL;
+            if (idx < 33) {
+                T a0, a1, a2, a3;
+                Vec4<T>::ld(src + idx * 4, a0, a1, a2, a3);
+                Vec4<T>::st(sP + idx * 4, a0, a1, a2, a3);
+            }
+        }
+        __syncwarp(mask);
+    }
     bool ok = true;
     T* sT0 = sm + L.oT0;
     T* sT1 = sm + L.oT1;
@@ -601,11 +642,11 @@ __device__ __forceinline__ bool backward_sweep(const RtiCfg<T>& c, int N, int j,
                 if (cj < 2) tb[(8 + cj) * TLD] = b1 - xn[8 + cj];
             }
             __syncwarp(mask);
-            tile_to_ws<T>(sT0, ws + WL.oRec + (long long)k * 14 * TLD, j);
-            ok &= backward_stage<T, kBar, kRows>(c, N, k, j, mask, sm, L, ws, WL, sT0, col0, as);
+            tile_to_ws<T>(sT0, rec + (long long)k * 14 * TLD, j);
+            ok &= backward_stage<T, kBar, kRows>(c, N, k, j, mask, sm, L, ws, WL, rec, sT0, col0, as);
             if (k >= 1) {
-                tile_to_ws<T>(sT1, ws + WL.oRec + (long long)(k - 1) * 14 * TLD, j);
-                ok &= backward_stage<T, kBar, kRows>(c, N, k - 1, j, mask, sm, L, ws, WL, sT1, col1, as);
+                tile_to_ws<T>(sT1, rec + (long long)(k - 1) * 14 * TLD, j);
+                ok &= backward_stage<T, kBar, kRows>(c, N, k - 1, j, mask, sm, L, ws, WL, rec, sT1, col1, as);
             }
         }
     } else {
@@ -615,7 +656,7 @@ __device__ __forceinline__ bool backward_sweep(const RtiCfg<T>& c, int N, int j,
 #pragma unroll
             for (int q = 0; q < 2; q++) {
                 const int idx = j + q * GL;
-                if (idx < 30) Vec4<T>::ld(ws + WL.oRec + (long long)k * 14 * TLD + idx * 4, pre[q][0], pre[q][1], pre[q][2], pre[q][3]);
+                if (idx < 30) Vec4<T>::ld(rec + (long long)k * 14 * TLD + idx * 4, pre[q][0], pre[q][1], pre[q][2], pre[q][3]);
             }
         };
         auto put = [&](T* t) {
@@ -626,13 +667,13 @@ __device__ __forceinline__ bool backward_sweep(const RtiCfg<T>& c, int N, int j,
                 if (idx < 30) Vec4<T>::st(t + idx * 4, (zero_b && (idx % 3) == 2) ? T(0) : pre[q][0], pre[q][1], pre[q][2], pre[q][3]);
             }
         };
-        fetch(N - 1);
+        fetch(k_first);
         put(sT0);
         __syncwarp(mask);
         int par = 0;
-        for (int k = N - 1; k >= 0; k--) {
+        for (int k = k_first; k >= 0; k--) {
             if (k >= 1) fetch(k - 1);
-            ok &= backward_stage<T, kBar, kRows>(c, N, k, j, mask, sm, L, ws, WL, par ? sT1 : sT0, par ? col1 : col0, as);
+            ok &= backward_stage<T, kBar, kRows>(c, N, k, j, mask, sm, L, ws, WL, rec, par ? sT1 : sT0, par ? col1 : col0, as);
             if (k >= 1) {
                 put(par ? sT0 : sT1);
                 __syncwarp(mask);
@@ -658,7 +699,8 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 constexpr int FW_RING = 6;            // stages of forward-sweep records in flight (L2 latency / stage time ~ 4-5)
 constexpr int FW_REC = 14 * TLD;      // one stage: 14 lanes x TLD
-static_assert(SmemLayout(1).oHux - SmemLayout(1).oY >= FW_RING * FW_REC, "forward-sweep ring does not fit the dead shared-memory regions");
+static_assert(SmemLayout(1, true).oHux - SmemLayout(1, true).oY >= FW_RING * FW_REC && SmemLayout(80, true).oHux - SmemLayout(80, true).oY >= FW_RING * FW_REC,
+              "forward-sweep ring does not fit the dead shared-memory regions");
 
 // Forward substitution: lane i < 10 carries dx_k[i], lanes 10..13 compute du_k[m].
 // kFinal (the accepted sweep of the nominal path): the stage records stream from the L2-resident
@@ -671,11 +713,11 @@ static_assert(SmemLayout(1).oHux - SmemLayout(1).oY >= FW_RING * FW_REC, "forwar
 // !kFinal (IPM sweeps): records are register-prefetched and the step goes to sDz[k][lane].
 template <typename T, bool kFinal>
 __device__ __forceinline__ void forward_sweep(const RtiCfg<T>& c, int N, int lane, unsigned mask, T dx0, T* sm, const SmemLayout& L,
-                                              const T* ws, const WsLayout& WL, T lo, T hi, T* gX, T* gU, T* gu0, bool& viol, bool& bad,
+                                              const T* rec_base, const WsLayout& WL, T lo, T hi, T* gX, T* gU, T* gu0, bool& viol, bool& bad,
                                               int& nact, bool rezero_pads = true, bool zero_b = false) {
     T* sDz = sm + L.oDz;
     const bool isx = lane < 10, isu = (lane >= 10 && lane < 14), isv = (lane >= 3 && lane < 6);
-    const T* rec = ws + WL.oRec + (long long)((lane < 14) ? lane : 13) * TLD;
+    const T* rec = rec_base + (long long)((lane < 14) ? lane : 13) * TLD;
     T z = isx ? dx0 : T(0);
     // one stage: consumes this lane's record cf, the iterate value it_cur (kFinal)
     auto stage = [&](int k, const T (&cf)[12], T& du_out) {
@@ -820,9 +862,9 @@ constexpr int AS_HIST = 6;  // active-set hashes remembered for the cycle test
 // rounds find no fixed point: Mehrotra predictor-corrector IPM (HPIPM's algorithm) for an active-set estimate, then
 // the rounds again from that estimate.
 template <typename T, int kN>
-__device__ __forceinline__ void constrained_qp(const RtiCfg<T>& c, int lane, unsigned mask, T* sm, T* ws, const T* sTriv, T dx0, T lo, T hi,
-                                               T* gX, T* gU, T* gu0, int32_t* g_status, int32_t* g_status2, int32_t* g_stats,
-                                               unsigned long long* g_as, bool keep_set, int n_fact0) {
+__device__ __forceinline__ void constrained_qp(const RtiCfg<T>& c, int lane, unsigned mask, T* sm, T* ws, T* rec, bool have_tiles, const T* sTriv,
+                                               T dx0, T lo, T hi, T* gX, T* gU, T* gu0, int32_t* g_status, int32_t* g_status2,
+                                               int32_t* g_stats, unsigned long long* g_as, bool keep_set, int n_fact0) {
     const int N = (kN > 0) ? kN : c.N;
     const SmemLayout L(N);
     const WsLayout WL(N);
@@ -845,7 +887,9 @@ __device__ __forceinline__ void constrained_qp(const RtiCfg<T>& c, int lane, uns
     bool ipm_ok = false, pol_ok = false;
     ActiveSet<T> as;
     as.lo = lo; as.hi = hi;
-    bool lin_done = false;  // [A B b] tiles of this iterate are in the workspace
+    // [A B b] tiles of this iterate are in `rec`: left there by the nominal kernel's sweep when its workspace slot was
+    // not reused for a later problem (have_tiles), else produced by the first sweep here
+    bool lin_done = have_tiles;
     // a released variable that lands within a few ulps of its bound is not a violation (it would be re-pinned and
     // released for ever)
     const T feas_eps = (sizeof(T) == 4 ? T(5e-7) : T(1e-13)) * fmax(T(1), fmax(fabs(lo), fabs(hi)));
@@ -856,6 +900,7 @@ __device__ __forceinline__ void constrained_qp(const RtiCfg<T>& c, int lane, uns
 #pragma unroll
         for (int q = 0; q < AS_HIST; q++) hist[q] = 0ull;
         bool damped = false;
+        int k_top = N - 1;  // first round of a call: full sweep (nothing saved yet, or saved under other multipliers)
         for (int round = 0; round < max_rounds; round++) {
             // cycle test on a hash of the whole set
             {
@@ -872,16 +917,17 @@ __device__ __forceinline__ void constrained_qp(const RtiCfg<T>& c, int lane, uns
                 hist[0] = h;
             }
             bool fact_ok;
-            if (!lin_done) fact_ok = backward_sweep<T, true, 2, true>(c, N, lane, mask, sm, L, ws, WL, sTriv, &as);
-            else fact_ok = backward_sweep<T, false, 2, true>(c, N, lane, mask, sm, L, ws, WL, sTriv, &as);
+            if (!lin_done) fact_ok = backward_sweep<T, true, 2, true>(c, N, lane, mask, sm, L, ws, WL, rec, sTriv, &as);
+            else fact_ok = backward_sweep<T, false, 2, true>(c, N, lane, mask, sm, L, ws, WL, rec, sTriv, &as, false, k_top);
             lin_done = true;
             if (!fact_ok) return false;
             n_fact++;
             n_pol++;
-            forward_sweep<T, false>(c, N, lane, mask, dx0, sm, L, ws, WL, lo, hi, gX, gU, nullptr, viol, bad, nact_l);
+            forward_sweep<T, false>(c, N, lane, mask, dx0, sm, L, rec, WL, lo, hi, gX, gU, nullptr, viol, bad, nact_l);
             bool changed = false, any_viol = false;
             T worst = T(0);  // most wrong-signed multiplier of this lane's pinned bounds (damped mode releases one)
             int worst_k = -1;
+            int top_l = -1;  // highest backward stage whose pins this lane changed (a velocity pin of stage k acts at stage k - 1)
             for (int k = 0; k < N; k++) {
                 // multipliers of the velocity components of stage k+1 pinned in this sweep
                 const int k1 = k + 1;
@@ -912,31 +958,31 @@ __device__ __forceinline__ void constrained_qp(const RtiCfg<T>& c, int lane, uns
 #pragma unroll
                         for (int i = 0; i < 14; i++) gq += hr[i] * sDz[k * 16 + i];
                         if (vb) {
-                            const T* eb = ws + WL.oRec + ((long long)k * 14 + 3) * TLD + 4 + (lane - 10);  // (E B)(a, m)
+                            const T* eb = rec + ((long long)k * 14 + 3) * TLD + 4 + (lane - 10);  // (E B)(a, m)
                             gq += eb[0] * nu0 + eb[TLD] * nu1 + eb[2 * TLD] * nu2;
                         }
                         const T lam = at_hi ? -gq : gq;  // >= 0 at a KKT point
                         if (lam < T(0)) {
-                            if (!damped) { as.lo_m.clear(k); as.hi_m.clear(k); changed = true; }
+                            if (!damped) { as.lo_m.clear(k); as.hi_m.clear(k); changed = true; top_l = k; }
                             else if (lam < worst) { worst = lam; worst_k = k; }
                         }
                     } else {
                         const T zn = sDz[k * 16 + lane];
-                        if (zn > hi - it_v + feas_eps) { as.hi_m.set(k); changed = true; any_viol = true; }
-                        else if (zn < lo - it_v - feas_eps) { as.lo_m.set(k); changed = true; any_viol = true; }
+                        if (zn > hi - it_v + feas_eps) { as.hi_m.set(k); changed = true; any_viol = true; top_l = k; }
+                        else if (zn < lo - it_v - feas_eps) { as.lo_m.set(k); changed = true; any_viol = true; top_l = k; }
                     }
                 }
                 if (isv && k1 < N) {
                     if (vp) {
                         const T lam = as.hi_m.test(k1) ? nu : -nu;
                         if (lam < T(0)) {
-                            if (!damped) { as.lo_m.clear(k1); as.hi_m.clear(k1); changed = true; }
+                            if (!damped) { as.lo_m.clear(k1); as.hi_m.clear(k1); changed = true; top_l = k; }
                             else if (lam < worst) { worst = lam; worst_k = k1; }
                         }
                     } else {
                         const T it_v = sX[k1 * NX + lane], zn = sDz[k1 * 16 + lane];
-                        if (zn > hi - it_v + feas_eps) { as.hi_m.set(k1); changed = true; any_viol = true; }
-                        else if (zn < lo - it_v - feas_eps) { as.lo_m.set(k1); changed = true; any_viol = true; }
+                        if (zn > hi - it_v + feas_eps) { as.hi_m.set(k1); changed = true; any_viol = true; top_l = k; }
+                        else if (zn < lo - it_v - feas_eps) { as.lo_m.set(k1); changed = true; any_viol = true; top_l = k; }
                     }
                 }
             }
@@ -946,9 +992,18 @@ __device__ __forceinline__ void constrained_qp(const RtiCfg<T>& c, int lane, uns
                 const T w_all = grp_min<T>(worst, mask);
                 const bool cand = (worst_k >= 0) && (worst == w_all) && (w_all < T(0));
                 const unsigned cb = (__ballot_sync(mask, cand) >> ((mask & 1u) ? 0 : 16)) & 0xFFFFu;
-                if (cand && (cb & ((1u << lane) - 1u)) == 0u) { as.lo_m.clear(worst_k); as.hi_m.clear(worst_k); changed = true; }
+                if (cand && (cb & ((1u << lane) - 1u)) == 0u) {
+                    as.lo_m.clear(worst_k); as.hi_m.clear(worst_k); changed = true;
+                    top_l = isv ? worst_k - 1 : worst_k;
+                }
             }
             changed = __any_sync(mask, changed);
+#pragma unroll
+            for (int o = 8; o >= 1; o >>= 1) {
+                const int other = __shfl_xor_sync(mask, top_l, o, GL);
+                top_l = other > top_l ? other : top_l;
+            }
+            k_top = top_l;
             __syncwarp(mask);
             if (!changed) {
                 // pinned variables sit exactly on their bound
@@ -990,7 +1045,7 @@ __device__ __forceinline__ void constrained_qp(const RtiCfg<T>& c, int lane, uns
         if (!lin_done) {
             // warm start without a usable guess: linearise with an empty set first
             as.lo_m = StageMask(); as.hi_m = StageMask();
-            if (!backward_sweep<T, true, 2, false>(c, N, lane, mask, sm, L, ws, WL, sTriv, &as)) status = 4;
+            if (!backward_sweep<T, true, 2, false>(c, N, lane, mask, sm, L, ws, WL, rec, sTriv, &as)) status = 4;
             lin_done = true;
             n_fact++;
         }
@@ -1045,9 +1100,9 @@ __device__ __forceinline__ void constrained_qp(const RtiCfg<T>& c, int lane, uns
             mu_prev = mu;
             __syncwarp(mask);
             // ---- predictor ----
-            if (!backward_sweep<T, false, 1, false>(c, N, lane, mask, sm, L, ws, WL, sTriv, nullptr)) { ipm_broken = true; break; }
+            if (!backward_sweep<T, false, 1, false>(c, N, lane, mask, sm, L, ws, WL, rec, sTriv, nullptr)) { ipm_broken = true; break; }
             n_fact++;
-            forward_sweep<T, false>(c, N, lane, mask, dx0, sm, L, ws, WL, lo, hi, gX, gU, nullptr, viol, bad, nact_l);
+            forward_sweep<T, false>(c, N, lane, mask, dx0, sm, L, rec, WL, lo, hi, gX, gU, nullptr, viol, bad, nact_l);
             T amax = T(1e30);
             for (int k = 0; k < N; k++)
                 if (has_box(k)) {
@@ -1096,9 +1151,9 @@ __device__ __forceinline__ void constrained_qp(const RtiCfg<T>& c, int lane, uns
                     bG[e] = ((sigma_mu - cu) / tu - gu * ub + lu) - ((sigma_mu - cl) / tl + gl * lb + ll);
                 }
             __syncwarp(mask);
-            if (!backward_sweep<T, false, 1, false>(c, N, lane, mask, sm, L, ws, WL, sTriv, nullptr)) { ipm_broken = true; break; }
+            if (!backward_sweep<T, false, 1, false>(c, N, lane, mask, sm, L, ws, WL, rec, sTriv, nullptr)) { ipm_broken = true; break; }
             n_fact++;
-            forward_sweep<T, false>(c, N, lane, mask, dx0, sm, L, ws, WL, lo, hi, gX, gU, nullptr, viol, bad, nact_l);
+            forward_sweep<T, false>(c, N, lane, mask, dx0, sm, L, rec, WL, lo, hi, gX, gU, nullptr, viol, bad, nact_l);
             amax = T(1e30);
             for (int k = 0; k < N; k++)
                 if (has_box(k)) {
@@ -1154,8 +1209,11 @@ __device__ __forceinline__ void constrained_qp(const RtiCfg<T>& c, int lane, uns
         // stage loses about three digits to it: fp32 ends 2e-4 off the solution, fp64 5e-13.  One more sweep with the
         // same factorisation structure, linearised AT the computed step (iterate advanced in shared memory, stage
         // residuals b zeroed, cost gradient and pinned values re-evaluated there), solves for the small remainder.
+        // The same sweep is taken by heavily saturated problems (a dozen or more pinned variables), whose fp32 error
+        // otherwise compounds over warm-started steps.
         const bool vown = isv && ((as.lo_m.w0 | as.lo_m.w1 | as.hi_m.w0 | as.hi_m.w1) != 0ull);
-        if (sizeof(T) == 4 && __any_sync(mask, vown)) {
+        const int n_pin = (int)grp_sum<float>((float)(__popcll(as.lo_m.w0 | as.hi_m.w0) + __popcll(as.lo_m.w1 | as.hi_m.w1)), mask);
+        if (sizeof(T) == 4 && (__any_sync(mask, vown) || n_pin >= 12)) {
             T* sY = sm + L.oY;
             if (lane < 14)
                 for (int k = 0; k <= N; k++) {
@@ -1166,9 +1224,9 @@ __device__ __forceinline__ void constrained_qp(const RtiCfg<T>& c, int lane, uns
                     if (lane < 6 || lane >= 10) sY[k * SYS + lane] += dz;  // residual records are linear in the iterate
                 }
             __syncwarp(mask);
-            if (backward_sweep<T, false, 2, false>(c, N, lane, mask, sm, L, ws, WL, sTriv, &as, true)) {
+            if (backward_sweep<T, false, 2, false>(c, N, lane, mask, sm, L, ws, WL, rec, sTriv, &as, true)) {
                 n_fact++;
-                forward_sweep<T, false>(c, N, lane, mask, T(0), sm, L, ws, WL, lo, hi, gX, gU, nullptr, viol, bad, nact_l, true, true);
+                forward_sweep<T, false>(c, N, lane, mask, T(0), sm, L, rec, WL, lo, hi, gX, gU, nullptr, viol, bad, nact_l, true, true);
                 if (isu || isv)
                     for (int k = 0; k < N; k++) {
                         const T it_v = iter_at(k);
@@ -1333,7 +1391,7 @@ template <typename T, int kN, bool kLat>
 __global__ void __launch_bounds__(RTI_CTA, (sizeof(T) == 4) ? (kLat ? 4 : 8) : 3) rti_step_kernel(const __grid_constant__ RtiCfg<T> c, const RtiArgs<T> a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int N = (kN > 0) ? kN : c.N;
-    const SmemLayout L(N);
+    const SmemLayout L(N, true);
     const WsLayout WL(N);
     const int lane = threadIdx.x & 15;
     const int grp = threadIdx.x >> 4;
@@ -1375,7 +1433,7 @@ __global__ void __launch_bounds__(RTI_CTA, (sizeof(T) == 4) ? (kLat ? 4 : 8) : 3
             __syncwarp(mask);
             const T dx0 = isx ? x0v - sX[lane] : T(0);
             // ---- preparation + unconstrained feedback; the step is accepted on the fly ----
-            ok = backward_sweep<T, true, 0, false>(c, N, lane, mask, sm, L, ws, WL, sTriv, nullptr);
+            ok = backward_sweep<T, true, 0, false>(c, N, lane, mask, sm, L, ws, WL, ws, sTriv, nullptr);
             forward_sweep<T, true>(c, N, lane, mask, dx0, sm, L, ws, WL, lo, hi, gX, gU, nullptr, viol, bad, nact_l,
                                    prob + (int)gridDim.x * ppc < a.B);
         }
@@ -1487,7 +1545,10 @@ __global__ void __launch_bounds__(RTI_CTA, (sizeof(T) == 4) ? 4 : 2) rti_constra
             cost_records<T>(N, lane, sm + L.oY, sm + L.oX, sm + L.oU, sm + L.oPar);
             __syncwarp(mask);
             const T dx0 = isx ? a.x0[(size_t)prob * NX + lane] - sm[L.oX + lane] : T(0);
-            constrained_qp<T, kN>(c, lane, mask, sm, ws, sTriv, dx0, lo, hi, a.X + (size_t)prob * (N + 1) * NX, a.U + (size_t)prob * N * NU,
+            // stage tiles [A B b]: the nominal kernel's, when its sweep ran (QUEUE_SWEPT) and its slot still holds them
+            const bool have_tiles = (entry & QUEUE_SWEPT) && a.ws_n_slots >= a.B;
+            T* rec = have_tiles ? a.ws_n + (size_t)prob * a.ws_n_stride : ws + WsLayout(N).oRec;
+            constrained_qp<T, kN>(c, lane, mask, sm, ws, rec, have_tiles, sTriv, dx0, lo, hi, a.X + (size_t)prob * (N + 1) * NX, a.U + (size_t)prob * N * NU,
                                   a.u0 ? a.u0 + (size_t)prob * NU : nullptr, a.status + prob, a.status2 ? a.status2 + prob : nullptr,
                                   a.stats + (size_t)prob * 4,
                                   a.as_store + (size_t)prob * (AS_OWNERS * 4), a.as_warm != 0, (entry & QUEUE_SWEPT) ? 1 : 0);
