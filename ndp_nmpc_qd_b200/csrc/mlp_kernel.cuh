@@ -111,6 +111,54 @@ __device__ __forceinline__ bool mlp_fetch_row(const MlpIo& io, long long row, fl
     }
 }
 
+// Two-phase form of mlp_fetch_row for software prefetching: issue() only LOADS (nothing depends on the values, so an
+// in-order warp does not wait for them), finish() forms the features / gate one tile later.
+struct MlpRaw {
+    float o[6], e[6], ox, oy, gx, gy;
+    bool gated, on;
+};
+__device__ __forceinline__ void mlp_fetch_issue(const MlpIo& io, long long row, MlpRaw& r) {
+    r.gated = false; r.on = true;
+    r.ox = r.oy = r.gx = r.gy = 0.f;
+    if (io.mode == 1 && io.precision == 0) {
+        const long long p = row / io.n_nodes;
+        const float* e = (const float*)io.ego + row * 10;
+        const float* o = (const float*)io.other + row * io.other_ld;
+#pragma unroll
+        for (int i = 0; i < 6; i++) { r.o[i] = o[i]; r.e[i] = e[i]; }
+        if (io.gate_xy) {
+            const float* o0 = (const float*)io.other + p * io.n_nodes * io.other_ld;
+            const float* g = (const float*)io.gate_xy + p * 2;
+            r.ox = o0[0]; r.oy = o0[1]; r.gx = g[0]; r.gy = g[1];
+            r.gated = true;
+        }
+    } else if (io.mode == 2) {
+        const long long p = row / io.n_nodes;
+        const int k = (int)(row - p * io.n_nodes);
+        const int2 pr = io.pairs[p];
+        const float* e = io.tp.row(pr.x, io.n_nodes) + k * 6;
+        const float* o = io.tp.row(pr.y, io.n_nodes) + k * 6;
+#pragma unroll
+        for (int i = 0; i < 6; i++) { r.o[i] = o[i]; r.e[i] = e[i]; }
+    } else {
+        // plain rows / fp64 pairs: formed at once (not the throughput paths)
+        float x[6];
+        r.on = mlp_fetch_row(io, row, x);
+#pragma unroll
+        for (int i = 0; i < 6; i++) { r.o[i] = x[i]; r.e[i] = 0.f; }
+    }
+}
+__device__ __forceinline__ bool mlp_fetch_finish(const MlpIo& io, const MlpRaw& r, float (&x)[6]) {
+#pragma unroll
+    for (int i = 0; i < 6; i++) x[i] = r.o[i] - r.e[i];
+    bool on = r.on;
+    if (r.gated) {
+        const float dx = r.ox - r.gx, dy = r.oy - r.gy;
+        on = dx * dx + dy * dy < (float)io.r2;
+    }
+    return on;
+}
+
 __device__ __forceinline__ void mlp_store_row(const MlpIo& io, long long row, bool on, float f0, float f1, float f2) {
     if (!on) { f0 = 0.f; f1 = 0.f; f2 = 0.f; }
     if (io.mode == 1 && io.precision == 1) {

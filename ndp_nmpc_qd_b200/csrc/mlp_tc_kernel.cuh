@@ -158,9 +158,11 @@ __global__ void __launch_bounds__(MLPT_CTA_THREADS, 1) mlp_tc_kernel(const MlpSm
     // as many SMs as it has tiles instead of two tiles (both groups) to half as many.  The first tile's features are
     // requested before anything else, so that their DRAM latency runs under the one-off setup below.
     const long long tile0 = (long long)grp * gridDim.x + blockIdx.x, tstride = (long long)gridDim.x * MLPT_GROUPS;
-    float xn[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    bool on_n = false;
-    if (tile0 < n_tiles && tile0 * MLPT_ROWS + t < M) on_n = mlp_fetch_row(io, tile0 * MLPT_ROWS + t, xn);
+    MlpRaw raw;  // loaded, not yet used: the features are formed one tile later (mlp_fetch_finish)
+#pragma unroll
+    for (int i = 0; i < 6; i++) { raw.o[i] = 0.f; raw.e[i] = 0.f; }
+    raw.gated = false; raw.on = false; raw.ox = raw.oy = raw.gx = raw.gy = 0.f;
+    if (tile0 < n_tiles && tile0 * MLPT_ROWS + t < M) mlp_fetch_issue(io, tile0 * MLPT_ROWS + t, raw);
     // a solve launched as a programmatic dependent (NDP_UPDATE_F_FROM_PREVIOUS_KERNEL) may be scheduled as CTAs of this
     // grid retire; it synchronises on this grid's completion itself before it reads the forces
     asm volatile("griddepcontrol.launch_dependents;");
@@ -213,15 +215,13 @@ __global__ void __launch_bounds__(MLPT_CTA_THREADS, 1) mlp_tc_kernel(const MlpSm
     for (long long tile = tile0; tile < n_tiles; tile += tstride) {
         const long long row = tile * MLPT_ROWS + t;
         float x[6];
-#pragma unroll
-        for (int i = 0; i < 6; i++) x[i] = xn[i];
-        const bool on = on_n;
-        {   // prefetch the next tile's features; the loads complete under this tile's compute
+        const bool on = mlp_fetch_finish(io, raw, x);
+        {   // prefetch the next tile's raw rows; the loads complete under this tile's compute
             const long long nrow = row + tstride * MLPT_ROWS;
 #pragma unroll
-            for (int i = 0; i < 6; i++) xn[i] = 0.f;
-            on_n = false;
-            if (tile + tstride < n_tiles && nrow < M) on_n = mlp_fetch_row(io, nrow, xn);
+            for (int i = 0; i < 6; i++) { raw.o[i] = 0.f; raw.e[i] = 0.f; }
+            raw.gated = false; raw.on = false;
+            if (tile + tstride < n_tiles && nrow < M) mlp_fetch_issue(io, nrow, raw);
         }
         MLPT_STAMP(stamp++);
         // ---- layer 1 (CUDA cores, fp32) -> h1 hi/lo operand tiles ----
