@@ -33,7 +33,9 @@ constexpr float MLPT_LO_INV = 1.f / 2048.f;
 // fp16 operand images (elements): [W2 hi; W2 lo] [128 x 128], [W3 hi; W3 lo] [256 x 64]
 constexpr int MLPT_W2_ELEMS = MLP_H2 * MLP_H1;
 constexpr int MLPT_W3_ELEMS = MLP_H3 * MLP_H2;
-constexpr int MLPT_WIMG_ELEMS = 2 * MLPT_W2_ELEMS + 2 * MLPT_W3_ELEMS;
+constexpr int MLPT_K1 = 16;                        // layer-1 K padded to one MMA k-step: 6 features, a constant 1 (bias column), zeros
+constexpr int MLPT_W1_ELEMS = MLP_H1 * MLPT_K1;    // [W1 | b1 | 0] per half: [128 x 16]
+constexpr int MLPT_WIMG_ELEMS = 2 * MLPT_W2_ELEMS + 2 * MLPT_W3_ELEMS + 2 * MLPT_W1_ELEMS;
 // fp32 side parameters (layers 1 and 4, biases): a small device buffer, staged once per CTA in shared memory and
 // read with broadcast 128-bit loads (indexed constant-bank loads measured 4x slower)
 struct alignas(16) MlpSmall {
@@ -48,10 +50,12 @@ constexpr int MLPT_S_W2H = 0;
 constexpr int MLPT_S_W2L = MLPT_S_W2H + MLPT_W2_ELEMS * 2;
 constexpr int MLPT_S_W3H = MLPT_S_W2L + MLPT_W2_ELEMS * 2;
 constexpr int MLPT_S_W3L = MLPT_S_W3H + MLPT_W3_ELEMS * 2;
-constexpr int MLPT_S_ACT = MLPT_S_W3L + MLPT_W3_ELEMS * 2;
+constexpr int MLPT_S_W1H = MLPT_S_W3L + MLPT_W3_ELEMS * 2;   // [W1_hi; W1_lo]: 256 rows x 16
+constexpr int MLPT_S_ACT = MLPT_S_W1H + 2 * MLPT_W1_ELEMS * 2;
 constexpr int MLPT_ACT_BYTES = 2 * MLPT_ROWS * MLP_H1 * 2;       // h1 hi + lo [128 x 128] fp16
 constexpr int MLPT_A1H = 0, MLPT_A1L = MLPT_ROWS * MLP_H1 * 2;   // offsets inside a group's region
 constexpr int MLPT_A2H = 0, MLPT_A2L = MLPT_ROWS * MLP_H2 * 2;
+constexpr int MLPT_A0H = 0, MLPT_A0L = MLPT_ROWS * MLPT_K1 * 2;  // feature tiles [128 x 16] hi / lo (dead once layer 1 has committed)
 constexpr int MLPT_S_PAR = MLPT_S_ACT + MLPT_GROUPS * MLPT_ACT_BYTES;  // fp32 side parameters (MlpSmall image)
 constexpr int MLPT_S_OUT = MLPT_S_PAR + (int)sizeof(MlpSmall);         // layer-4 partial sums of the upper column half [groups][128][4] fp32
 constexpr int MLPT_S_BAR = MLPT_S_OUT + MLPT_GROUPS * MLPT_ROWS * 16;  // 3 mbarriers (24 B) + tmem base (4 B)
@@ -150,19 +154,30 @@ __global__ void __launch_bounds__(MLPT_CTA_THREADS, 1) mlp_tc_kernel(const MlpSm
     __half* sA1l = reinterpret_cast<__half*>(act + MLPT_A1L);
     __half* sA2h = reinterpret_cast<__half*>(act + MLPT_A2H);
     __half* sA2l = reinterpret_cast<__half*>(act + MLPT_A2L);
+    __half* sA0h = reinterpret_cast<__half*>(act + MLPT_A0H);
+    __half* sA0l = reinterpret_cast<__half*>(act + MLPT_A0L);
     const MlpSmall& sq = *reinterpret_cast<const MlpSmall*>(smt + MLPT_S_PAR);
+    int stamp = 0;
+    MLPT_STAMP(stamp++);  // kernel entry
     const long long M = mlp_rows(io);
-    const long long n_tiles = (M + MLPT_ROWS - 1) / MLPT_ROWS;
-    if ((long long)blockIdx.x >= n_tiles) return;  // device-sized launches: nothing for this CTA (before any barrier / TMA / TMEM setup)
-    // tile -> (CTA, group): consecutive tiles go to different SMs, so a ragged last round adds one tile to
-    // as many SMs as it has tiles instead of two tiles (both groups) to half as many.  The first tile's features are
-    // requested before anything else, so that their DRAM latency runs under the one-off setup below.
-    const long long tile0 = (long long)grp * gridDim.x + blockIdx.x, tstride = (long long)gridDim.x * MLPT_GROUPS;
+    // Rows are dealt to the (CTA, group) pairs in units of 32 (one warp's rows), as evenly as they go: every group gets
+    // floor or ceil of (row-warps / groups) of them as one contiguous range, walked in 128-row tiles.  The last tile of a
+    // range is then partial everywhere (its idle warps skip the CUDA-core phases) instead of a full extra round on a
+    // fraction of the SMs: 86 016 rows on 296 groups are 128 + 128 + 32 (or 64) rows each, not three full tiles on 80
+    // groups and two on the rest.  Group g of CTA c has index g * gridDim.x + c, so the longer ranges land on different SMs.
+    const long long n_w = (M + 31) / 32, n_grp = (long long)gridDim.x * MLPT_GROUPS;
+    const long long gidx = (long long)grp * gridDim.x + blockIdx.x;
+    const long long w_q = n_w / n_grp, w_r = n_w % n_grp;
+    const long long row_begin = (gidx * w_q + (gidx < w_r ? gidx : w_r)) * 32;
+    const long long row_end_raw = row_begin + (w_q + (gidx < w_r ? 1 : 0)) * 32;
+    const long long row_end = row_end_raw < M ? row_end_raw : M;
+    if ((long long)blockIdx.x * 32 >= M) return;  // device-sized launches: no rows for either group of this CTA (before any barrier / TMA / TMEM setup)
+    const long long n_tiles = row_end > row_begin ? (row_end - row_begin + MLPT_ROWS - 1) / MLPT_ROWS : 0;
     MlpRaw raw;  // loaded, not yet used: the features are formed one tile later (mlp_fetch_finish)
 #pragma unroll
     for (int i = 0; i < 6; i++) { raw.o[i] = 0.f; raw.e[i] = 0.f; }
     raw.gated = false; raw.on = false; raw.ox = raw.oy = raw.gx = raw.gy = 0.f;
-    if (tile0 < n_tiles && tile0 * MLPT_ROWS + t < M) mlp_fetch_issue(io, tile0 * MLPT_ROWS + t, raw);
+    if (row_begin + t < row_end) mlp_fetch_issue(io, row_begin + t, raw);
     // a solve launched as a programmatic dependent (NDP_UPDATE_F_FROM_PREVIOUS_KERNEL) may be scheduled as CTAs of this
     // grid retire; it synchronises on this grid's completion itself before it reads the forces
     asm volatile("griddepcontrol.launch_dependents;");
@@ -183,7 +198,8 @@ __global__ void __launch_bounds__(MLPT_CTA_THREADS, 1) mlp_tc_kernel(const MlpSm
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(sBar + 1)), "r"(1) : "memory");
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(wbar), "r"(1) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        constexpr uint32_t kBytes = MLPT_WIMG_ELEMS * 2, kChunk = 16384;
+        constexpr uint32_t kBytes = MLPT_WIMG_ELEMS * 2, kChunk = 8192;
+        static_assert(kBytes % kChunk == 0, "weight image is copied in whole chunks");
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(wbar), "r"(kBytes) : "memory");
 #pragma unroll
         for (uint32_t o = 0; o < kBytes; o += kChunk)
@@ -203,54 +219,77 @@ __global__ void __launch_bounds__(MLPT_CTA_THREADS, 1) mlp_tc_kernel(const MlpSm
     const uint32_t tmem = *sTmem + grp * 256;
     // layer-2 accumulators alias the front of the layer-3 ones (dead by then)
     const uint32_t tD1m = tmem + 0, tD1c = tmem + 64, tD2m = tmem + 0, tD2c = tmem + 128;
+    const uint32_t tD0m = tmem + 0, tD0c = tmem + 128;  // layer 1 (dead before layer 2 is issued)
     const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;  // this warp's TMEM lane quarter
-    const uint32_t aW2h = smem_u32(smt + MLPT_S_W2H), aW3h = smem_u32(smt + MLPT_S_W3H);
+    const uint32_t aW2h = smem_u32(smt + MLPT_S_W2H), aW3h = smem_u32(smt + MLPT_S_W3H), aW1h = smem_u32(smt + MLPT_S_W1H);
     const uint32_t aA1h = smem_u32(sA1h), aA1l = smem_u32(sA1l), aA2h = smem_u32(sA2h), aA2l = smem_u32(sA2l);
+    const uint32_t aA0h = smem_u32(sA0h), aA0l = smem_u32(sA0l);
     constexpr uint32_t ID1 = umma_idesc(128, MLP_H2), ID2 = umma_idesc(128, MLP_H3);
+    constexpr uint32_t ID0 = umma_idesc(128, MLP_H1), ID0C = umma_idesc(128, 2 * MLP_H1);
     constexpr uint32_t ID1C = umma_idesc(128, 2 * MLP_H2), ID2C = umma_idesc(128, 2 * MLP_H3);  // concatenated hi|lo operands
     uint32_t phase = 0;
 
-    int stamp = 0;
-    MLPT_STAMP(stamp++);
-    for (long long tile = tile0; tile < n_tiles; tile += tstride) {
-        const long long row = tile * MLPT_ROWS + t;
+    MLPT_STAMP(stamp++);  // setup done
+    for (long long tile = 0; tile < n_tiles; tile++) {
+        const long long row = row_begin + tile * MLPT_ROWS + t;
+        // this warp's 32 rows lie inside the range (uniform per warp: ranges are multiples of 32 rows but for the very last)
+        const bool live = row_begin + tile * MLPT_ROWS + (t & ~31) < row_end;
         float x[6];
         const bool on = mlp_fetch_finish(io, raw, x);
         {   // prefetch the next tile's raw rows; the loads complete under this tile's compute
-            const long long nrow = row + tstride * MLPT_ROWS;
+            const long long nrow = row + MLPT_ROWS;
 #pragma unroll
             for (int i = 0; i < 6; i++) { raw.o[i] = 0.f; raw.e[i] = 0.f; }
             raw.gated = false; raw.on = false;
-            if (tile + tstride < n_tiles && nrow < M) mlp_fetch_issue(io, nrow, raw);
+            if (nrow < row_end) mlp_fetch_issue(io, nrow, raw);
         }
         MLPT_STAMP(stamp++);
-        // ---- layer 1 (CUDA cores, fp32) -> h1 hi/lo operand tiles ----
-#pragma unroll 2
-        for (int kb = hf * (MLP_H1 / 16); kb < (hf + 1) * (MLP_H1 / 16); kb++) {
-            float w[48], bb[8], h[8];
-            const float4* wp = reinterpret_cast<const float4*>(sq.W1 + kb * 48);
-            const float4* bp = reinterpret_cast<const float4*>(sq.b1 + kb * 8);
-#pragma unroll
-            for (int i = 0; i < 12; i++) {
-                const float4 v = wp[i];
-                w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
-            }
-#pragma unroll
-            for (int i = 0; i < 2; i++) {
-                const float4 v = bp[i];
-                bb[4 * i] = v.x; bb[4 * i + 1] = v.y; bb[4 * i + 2] = v.z; bb[4 * i + 3] = v.w;
-            }
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                float acc = bb[i];
-#pragma unroll
-                for (int q = 0; q < 6; q++) acc = fmaf(w[i * 6 + q], x[q], acc);
-                h[i] = fmaxf(acc, 0.f);
-            }
-            const int off = umma_off(t, kb * 8, MLPT_ROWS);
-            split_store8(h, sA1h + off, sA1l + off);
+        // ---- layer 1 on the tensor cores too: D0[128 x 128] = [x | 1 | 0][128 x 16] . [W1 | b1 | 0]^T (one k-step, the same
+        //      hi / lo split; the bias rides on the constant-1 column).  On the CUDA cores this layer was 45 % of the
+        //      kernel's instructions (768 FFMA + 112 LDS.128 per row). ----
+        if (live && !hf) {
+            float v[8] = {x[0], x[1], x[2], x[3], x[4], x[5], 1.f, 0.f};
+            const int off = umma_off(t, 0, MLPT_ROWS);
+            split_store8(v, sA0h + off, sA0l + off);
+            const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+            *reinterpret_cast<uint4*>(sA0h + umma_off(t, 8, MLPT_ROWS)) = z;   // k = 8..15: the MMA's k-step is 16 wide
+            *reinterpret_cast<uint4*>(sA0l + umma_off(t, 8, MLPT_ROWS)) = z;
         }
         MLPT_STAMP(stamp++);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        group_sync(grp);
+        if (warp == 0) {
+          if (elect_one_sync()) {
+            mbar_wait(wbar, 0);  // weights have landed (returns immediately after the first tile)
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint64_t dAh = umma_desc(aA0h, (MLPT_ROWS / 8) * 128, 128), dAl = umma_desc(aA0l, (MLPT_ROWS / 8) * 128, 128);
+            const uint64_t dB = umma_desc(aW1h, (2 * MLP_H1 / 8) * 128, 128);  // [W1_hi; W1_lo], 256 rows
+            umma_f16(tD0m, dAh, dB, ID0C, 0);   // main (cols 0..127) and x_hi . W1_lo (cols 128..255)
+            umma_f16(tD0c, dAl, dB, ID0, 1);    // + x_lo . W1_hi
+            umma_commit(bar);
+          }
+          __syncwarp();
+        }
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // ---- epilogue 0: h1 = relu(D0) -> hi/lo operand tiles ----
+#pragma unroll 1
+        for (int c0 = hf * 64; live && c0 < hf * 64 + 64; c0 += 32) {
+            float m[32], cr[32];
+            tmem_ld32(tD0m + lane_sel + c0, m);
+            tmem_ld32(tD0c + lane_sel + c0, cr);
+#pragma unroll
+            for (int kb = 0; kb < 4; kb++) {
+                float h[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) h[i] = fmaxf(fmaf(cr[kb * 8 + i], MLPT_LO_INV, m[kb * 8 + i]), 0.f);
+                const int off = umma_off(t, c0 + kb * 8, MLPT_ROWS);
+                split_store8(h, sA1h + off, sA1l + off);
+            }
+        }
+        MLPT_STAMP(stamp++);
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         group_sync(grp);
         MLPT_STAMP(stamp++);
@@ -280,7 +319,7 @@ __global__ void __launch_bounds__(MLPT_CTA_THREADS, 1) mlp_tc_kernel(const MlpSm
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         MLPT_STAMP(stamp++);
         // ---- epilogue 1: h2 = relu(D1 + b2) -> hi/lo operand tiles (over the dead h1 tiles) ----
-        {
+        if (live) {
             const int c0 = hf * 32;
             float m[32], cr[32];
             tmem_ld32(tD1m + lane_sel + c0, m);
@@ -327,7 +366,7 @@ __global__ void __launch_bounds__(MLPT_CTA_THREADS, 1) mlp_tc_kernel(const MlpSm
         // ---- epilogue 2: h3 = relu(D2 + b3); layer 4 (CUDA cores, fp32): out = W4 h3 + b4 ----
         float o0 = hf ? 0.f : sq.b4[0], o1 = hf ? 0.f : sq.b4[1], o2 = hf ? 0.f : sq.b4[2];
 #pragma unroll 1
-        for (int c0 = hf * 64; c0 < hf * 64 + 64; c0 += 32) {
+        for (int c0 = hf * 64; live && c0 < hf * 64 + 64; c0 += 32) {
             float m[32], cr[32];
             tmem_ld32(tD2m + lane_sel + c0, m);
             tmem_ld32(tD2c + lane_sel + c0, cr);
@@ -351,14 +390,16 @@ __global__ void __launch_bounds__(MLPT_CTA_THREADS, 1) mlp_tc_kernel(const MlpSm
         if (hf) sOut[t] = make_float4(o0, o1, o2, 0.f);
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         group_sync(grp);
-        if (!hf && row < M) {
+        if (!hf && row < row_end) {
             const float4 p = sOut[t];
             mlp_store_row(io, row, on, o0 + p.x, o1 + p.y, o2 + p.z);
         }
         MLPT_STAMP(stamp++);
     }
+    MLPT_STAMP(stamp++);  // this group's tiles done
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    MLPT_STAMP(stamp++);  // both groups done
     if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*sTmem), "r"(512) : "memory");
 }
 
@@ -377,6 +418,15 @@ inline int mlp_tc_prepare(const float* host_params, void** out) {
     };
     put(host_params + MLP_OW2, MLP_H2, MLP_H1, img);
     put(host_params + MLP_OW3, MLP_H3, MLP_H2, img + 2 * MLPT_W2_ELEMS);
+    {   // layer 1: [W1 | b1 | 0] with K padded to 16 (the kernel feeds [x | 1 | 0])
+        float* w1 = new float[MLP_H1 * MLPT_K1]();
+        for (int r = 0; r < MLP_H1; r++) {
+            for (int k = 0; k < MLP_IN; k++) w1[r * MLPT_K1 + k] = host_params[MLP_OW1 + r * MLP_IN + k];
+            w1[r * MLPT_K1 + MLP_IN] = host_params[MLP_OB1 + r];
+        }
+        put(w1, MLP_H1, MLPT_K1, img + 2 * MLPT_W2_ELEMS + 2 * MLPT_W3_ELEMS);
+        delete[] w1;
+    }
     cudaError_t e = cudaMalloc(out, sizeof(__half) * MLPT_WIMG_ELEMS);
     if (e == cudaSuccess) e = cudaMemcpy(*out, img, sizeof(__half) * MLPT_WIMG_ELEMS, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MLPT_SMEM);
