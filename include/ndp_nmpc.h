@@ -213,6 +213,10 @@ int ndp_mlp_forward_swarm_parts(ndp_mlp* m, int precision, int32_t n_parts, cons
  * budget, read the 4-byte count back once per call and grow on demand. */
 int ndp_mlp_set_pair_budget(ndp_mlp* m, int64_t max_pairs);
 
+/* Swarm entry points: restrict the pairwise interaction to contiguous blocks of `group` quads (independent scenarios
+ * batched side by side, like the `group` of ndp_plant_create); 0 (default): every quad sees every other. */
+int ndp_mlp_set_group(ndp_mlp* m, int32_t group);
+
 int64_t ndp_mlp_launch_count(const ndp_mlp* m);
 
 /* ---- host-buffer step pipeline ----

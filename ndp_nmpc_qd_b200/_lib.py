@@ -30,7 +30,7 @@ EXPORTS = [
     "ndp_predxu_len", "ndp_predxu_pack", "ndp_predxu_unpack", "ndp_hover_throttle_init", "ndp_hover_throttle_update",
     "ndp_plant_cmd_from_u0_dev",
     "ndp_longlist_create", "ndp_longlist_destroy", "ndp_longlist_reset", "ndp_longlist_push", "ndp_longlist_launch_count",
-    "ndp_pipeline_create_ll", "ndp_kernel_timing", "ndp_last_kernel_ms",
+    "ndp_pipeline_create_ll", "ndp_kernel_timing", "ndp_last_kernel_ms", "ndp_mlp_set_group",
 ]
 
 
@@ -94,6 +94,8 @@ def load() -> C.CDLL:
     lib.ndp_mlp_launch_count.argtypes = [vp]
     lib.ndp_mlp_set_pair_budget.argtypes = [vp, i64]
     lib.ndp_mlp_set_pair_budget.restype = C.c_int
+    lib.ndp_mlp_set_group.argtypes = [vp, i32]
+    lib.ndp_mlp_set_group.restype = C.c_int
     lib.ndp_mlp_forward_swarm_parts.argtypes = [vp, i32, i32, C.POINTER(vp), i64, i64, i64, i64, i32, vp, dbl, vp, i32, vp]
     lib.ndp_mlp_forward_swarm_parts.restype = C.c_int
     lib.ndp_mlp_forward_pairs_ex.argtypes = [vp, i32, i64, i32, vp, vp, i32, vp, dbl, vp, i32, i32, vp]

@@ -31,10 +31,14 @@ class ClosedLoop:
                  precision: str = "f32", ts_sim: float = 0.01, ts_ctl_plant: float = 0.01, ts_nmpc: float = CP.ts_nmpc,
                  offset: Optional[np.ndarray] = None, has_motor_model: bool = True, has_battery: bool = False,
                  has_downwash: bool = False, group: int = 1, k_throttle: Optional[float] = K_THROTTLE, device="cuda:0",
-                 **engine_overrides):
+                 downwash_mlp: bool = False, **engine_overrides):
         """k_throttle: fixed thrust scale of nmpc_u_2_att_tgt, or None to run the reference's HoverThrottleEstimator on the
         device (one filter per scenario, estimator_params.py:13 initial guess 50): like the node, the filter is updated
-        only while no trajectory is tracked (`hover()`; nmpc_node.py:146,196) and its estimate is frozen during `step()`."""
+        only while no trajectory is tracked (`hover()`; nmpc_node.py:146,196) and its estimate is frozen during `step()`.
+        downwash_mlp: the coupled variant -- scenarios are contiguous blocks of `group` quadrotors (formation offsets via
+        `offset`), the plant couples them physically (has_downwash, same blocks) and every controller is the NDP-NMPC one:
+        per step the forces are the gated sum of DownwashNN over the block's other reference horizons
+        (ndp_nmpc_leader_node.py:60-76, generalised to every quad of the block; gate on the ego's odometry position)."""
         self.device = torch.device(device)
         B = len(traj_id)
         self.B, self.N, self.ts_sim, self.ts_nmpc = B, N, ts_sim, ts_nmpc
@@ -43,7 +47,16 @@ class ClosedLoop:
         self.dtype = torch.float32 if precision == "f32" else torch.float64
         dev = self.device
         self.refgen = RefGen(trajectories, device=dev)
-        self.engine = Engine(batch=B, N=N, np_=4, precision=precision, device=dev, **engine_overrides)
+        self.downwash_mlp = bool(downwash_mlp)
+        self.engine = Engine(batch=B, N=N, np_=7 if downwash_mlp else 4, precision=precision, device=dev, **engine_overrides)
+        self.f = None
+        if downwash_mlp:
+            from .dnwash_nn_est import DownwashNN
+
+            self.nn = DownwashNN(device=dev)
+            self.nn.set_group(group if 0 < group < B else 0)
+            self.traj6 = torch.empty((B, N + 1, 6), dtype=torch.float32, device=dev)
+            self.odom_xy = torch.empty((B, 2), dtype=torch.float32, device=dev)
         self.plant = MulQuadrotors(B, ts_sim, ts_ctl_plant, torch.float64, has_downwash, has_motor_model, has_battery, group=group, device=dev)
         self.traj_id = torch.as_tensor(np.asarray(traj_id, dtype=np.int32), device=dev)
         self.t = torch.as_tensor(np.asarray(t_start, dtype=np.float64), device=dev)
@@ -72,7 +85,11 @@ class ClosedLoop:
         """one control period: returns nothing; self.u0 / self.state hold the latest command and plant state."""
         self.refgen.horizon(self.t, self.traj_id, self.N, CP.th_pred, self.offset, xr=self.xr, ur=self.ur)
         self.plant.nmpc_x0(self.state, self.x0)
-        self.engine.update(self.x0, self.xr, self.ur, None, self.u0)
+        if self.downwash_mlp:
+            self.traj6.copy_(self.xr[:, :, 0:6])
+            self.odom_xy.copy_(self.state[:, 3:5, 0])
+            self.f = self.nn.forward_swarm(self.traj6, 0, self.B, odom_xy=self.odom_xy, out_dtype=self.dtype)
+        self.engine.update(self.x0, self.xr, self.ur, self.f, self.u0)
         self._command_and_simulate()
         self.t.add_(self.ts_nmpc)
 
@@ -109,7 +126,7 @@ class ClosedLoop:
 
     @property
     def launch_count(self) -> int:
-        return self.engine.launch_count + self.plant.launch_count + self.refgen.launch_count
+        return self.engine.launch_count + self.plant.launch_count + self.refgen.launch_count + (self.nn.launch_count if self.downwash_mlp else 0)
 
 
 def time_closed_loop(N: int, B: int, steps: int = 250, precision: str = "f32", device="cuda:0", seed: Optional[int] = None, use_graph: bool = True,

@@ -376,7 +376,7 @@ constexpr int SWARM_TILE = 2048;
 constexpr int SWARM_CTA = 1024;  // 32 egos per CTA
 __global__ void __launch_bounds__(SWARM_CTA) swarm_pairs_kernel(const TrajParts tp, const float* __restrict__ odom_xy, int n_all, int ego_begin,
                                                                  int n_ego, int n_nodes, float r2, int* __restrict__ total,
-                                                                 int2* __restrict__ seg, int2* __restrict__ pairs, int cap) {
+                                                                 int2* __restrict__ seg, int2* __restrict__ pairs, int cap, int group) {
     __shared__ float2 sxy[SWARM_TILE];
     const int lane = threadIdx.x & 31;
     const int i = blockIdx.x * (SWARM_CTA / 32) + (threadIdx.x >> 5);
@@ -404,7 +404,8 @@ __global__ void __launch_bounds__(SWARM_CTA) swarm_pairs_kernel(const TrajParts 
                 for (int e0 = 0; e0 < m; e0 += 32) {
                     const int e = e0 + lane, j = j0 + e;
                     bool hit = false;
-                    if (e < m && j != gi) {
+                    // group > 0: only quads of the same contiguous block of `group` interact (independent scenarios)
+                    if (e < m && j != gi && (group <= 0 || j / group == gi / group)) {
                         const float dx = sxy[e].x - ex, dy = sxy[e].y - ey;
                         hit = dx * dx + dy * dy < r2;
                     }

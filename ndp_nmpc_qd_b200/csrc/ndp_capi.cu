@@ -669,6 +669,7 @@ struct ndp_mlp {
     // swarm scratch (grown on demand)
     int* total; int2* seg; int2* pairs; float* fpair;
     long long cap_ego, cap_pairs, cap_rows, pair_budget;
+    int group;  // swarm entry points: quads interact inside contiguous blocks of `group` only (0: everybody)
     std::atomic<long long> launches;
     std::mutex mu;
 };
@@ -716,6 +717,7 @@ int ndp_mlp_create(const float* W1, const float* b1, const float* W2, const floa
     m->launches = 0;
     m->total = nullptr; m->seg = nullptr; m->pairs = nullptr; m->fpair = nullptr;
     m->cap_ego = m->cap_pairs = m->cap_rows = 0;
+    m->group = 0;
     m->pair_budget = 2ll << 20;  // 2 Mi pairs: 16 MB of pair indices + 0.5 GB of per-pair forces at 21 nodes
     m->params = nullptr; m->tc_weights = nullptr; m->d_small = nullptr;
     int dev = 0;
@@ -829,7 +831,7 @@ int ndp_mlp_forward_swarm_parts(ndp_mlp* m, int precision, int32_t n_parts, cons
     for (;;) {
         CU(cudaMemsetAsync(m->total, 0, sizeof(int), st));
         swarm_pairs_kernel<<<grd, SWARM_CTA, 0, st>>>(tp, odom_xy, (int)n_all, (int)ego_begin, (int)n_ego, n_nodes, r2, m->total, m->seg, m->pairs,
-                                                     (int)m->cap_pairs);
+                                                     (int)m->cap_pairs, m->group);
         m->launches++;
         if (sized && path != 1) break;
         CU(cudaMemcpyAsync(&n_pairs, m->total, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -852,6 +854,13 @@ int ndp_mlp_forward_swarm_parts(ndp_mlp* m, int precision, int32_t n_parts, cons
     else swarm_reduce_kernel<float><<<g2, 256, 0, st>>>(m->fpair, m->seg, (int)n_ego, n_nodes, (int)m->cap_pairs, (float*)out);
     m->launches++;
     CU(cudaGetLastError());
+    return 0;
+}
+
+int ndp_mlp_set_group(ndp_mlp* m, int32_t group) {
+    if (!m || group < 0) return fail(NDP_E_ARG, "ndp_mlp_set_group: bad argument");
+    std::lock_guard<std::mutex> lk(m->mu);
+    m->group = group;
     return 0;
 }
 

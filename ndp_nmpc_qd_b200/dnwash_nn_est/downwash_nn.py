@@ -145,6 +145,10 @@ class DownwashNN:
                                                   float(r_horiz), _ptr(out), path, _sp(stream, self.device)), "ndp_mlp_forward_swarm")
         return out
 
+    def set_group(self, group: int) -> None:
+        """forward_swarm: quads interact inside contiguous blocks of `group` only (0: all pairs)."""
+        _lib.check(self.lib.ndp_mlp_set_group(self._h, int(group)), "ndp_mlp_set_group")
+
     @property
     def launch_count(self) -> int:
         return int(self.lib.ndp_mlp_launch_count(self._h))

@@ -78,3 +78,53 @@ def test_closed_loop_large_batch_runs(built_lib):
     assert (cl.engine.status().cpu().numpy() == 0).all()
     err = cl.position_error().cpu().numpy()
     assert np.isfinite(err).all() and err.max() < 1.0 and np.sqrt((err**2).mean()) < 0.3
+
+
+def test_coupled_closed_loop_with_downwash_mlp(built_lib, c_oracle, mlp_weights):
+    """Coupled variant of config 5: blocks of 3 quadrotors (a follower 0.6 m above its leader, one beside it) whose plants
+    interact through the simulator's pairwise downwash and whose NDP-NMPC controllers get the gated DownwashNN sum of the
+    block's other reference horizons.  Against the same loop on the CPU oracles (numpy MLP / swarm sum, C SQP-RTI, numpy
+    plant); two blocks far apart in index but at the SAME place in space check that `group` keeps scenarios independent."""
+    import torch
+    from ndp_nmpc_qd_b200.closed_loop import ClosedLoop, K_THROTTLE, MASS, GRAVITY
+    from oracle import mlp_numpy
+
+    tr = traj_gen.plan_named("eight_low")
+    G, steps = 3, 25
+    off1 = np.array([[0.0, 0.0, 0.0], [0.05, 0.1, 0.6], [0.0, 1.2, 0.0]])
+    off = np.concatenate([off1, off1])          # second block: same positions -> would couple without `group`
+    tid = np.zeros(2 * G, np.int32)
+    t0 = np.array([5.0] * G + [5.0] * G)
+    cl = ClosedLoop([tr], tid, t0, precision="f64", offset=off, has_downwash=True, has_battery=False, group=G, downwash_mlp=True)
+    u_hist, f_hist = [], []
+    for _ in range(steps):
+        cl.step()
+        u_hist.append(cl.u0.cpu().numpy().copy()); f_hist.append(cl.f.cpu().numpy().copy())
+    torch.cuda.synchronize()
+    assert (cl.engine.status().cpu().numpy() == 0).all()
+    u_hist, f_hist = np.stack(u_hist), np.stack(f_hist)
+    assert np.array_equal(u_hist[:, :G], u_hist[:, G:])  # the two blocks are identical scenarios and do not see each other
+    assert np.abs(f_hist[:, 0]).max() > 0.1 and np.abs(f_hist[:, 2]).max() == 0.0  # leader under the follower; the third outside the gate
+    # oracle loop for one block
+    hor = lambda t: [np.stack(a) for a in zip(*[orf.horizon(tr, t[b], 20, 0.1, off1[b]) for b in range(G)])]
+    t = np.array(t0[:G], dtype=np.float64)
+    xr, ur = hor(t)
+    s = np.zeros((G, 35))
+    s[:, 3:6], s[:, 13:16], s[:, 9:13] = xr[:, 0, 0:3], xr[:, 0, 3:6], xr[:, 0, 6:10]
+    s[:, 31:35] = np.sqrt(MASS * GRAVITY / 4 / (2.8158e-08 * 1e6))
+    plant = PlantOracle(G, 0.01, 0.01, True, True, False)
+    X, U = xr.copy(), ur.copy()
+    cfg = make_cfg()
+    for k in range(steps):
+        xr, ur = hor(t)
+        x0 = np.concatenate([s[:, 3:6], s[:, 13:16], s[:, 9:13]], 1)
+        f = mlp_numpy.swarm_forces(mlp_weights, xr[:, :, 0:6].astype(np.float32), 0, G, odom_xy=s[:, 3:5].astype(np.float32))
+        r = c_oracle.rti_batch(cfg, x0, xr, ur, f, X, U)
+        assert (r["status"] == 0).all()
+        assert np.abs(f_hist[k, :G] - f).max() < 2e-4, k
+        assert np.abs(u_hist[k, :G] - r["u0"]).max() < 2e-4 * max(1.0, np.abs(r["u0"]).max()), k  # forces from the fp32-accurate MLP
+        cmd = np.concatenate([r["u0"][:, 0:3], r["u0"][:, 3:4] * MASS / K_THROTTLE], 1)
+        for _ in range(2):
+            s = plant.forward(0.01, s, cmd)
+        t = t + 0.02
+    assert np.abs(cl.state.cpu().numpy()[:G, 3:6, 0] - s[:, 3:6]).max() < 1e-4

@@ -206,3 +206,31 @@ def test_swarm_device_sized_vs_read_back_and_multi_tile(nn, mlp_weights):
     ref = mlp_numpy.swarm_forces(mlp_weights, traj, ego_begin, n_ego)
     assert np.abs(ref).max() > 1.0
     assert np.abs(f_dev.cpu().numpy() - ref).max() < 3e-4
+
+
+def test_swarm_group_restricts_neighbours_to_the_block(nn, mlp_weights):
+    """ndp_mlp_set_group(G): quadrotor i only sees j with j // G == i // G (independent scenarios batched side by side,
+    like MulQuadrotors' `group`); equal to the oracle run block by block, and group 0 restores all pairs."""
+    import torch
+
+    rng = np.random.default_rng(11)
+    G, nb, n = 5, 12, 21
+    n_all = G * nb
+    traj = np.zeros((n_all, n, 6), np.float32)
+    traj[:, :, 0:2] = rng.uniform(0, 1.5, size=(n_all, 1, 2))  # every block in the same 1.5 m square: blocks overlap in space
+    traj[:, :, 2] = rng.uniform(0.5, 3.5, size=(n_all, 1))
+    traj[:, :, 3:6] = 0.2 * rng.normal(size=(n_all, n, 3))
+    t = torch.as_tensor(traj, device="cuda")
+    all_pairs = nn.forward_swarm(t, 0, n_all, path=nn.PATH_FP32).clone()
+    nn.set_group(G)
+    try:
+        f = nn.forward_swarm(t, 0, n_all, path=nn.PATH_FP32).cpu().numpy()
+        sub = nn.forward_swarm(t, 2 * G + 1, 2 * G, path=nn.PATH_FP32).cpu().numpy()  # ego range starting inside a block
+    finally:
+        nn.set_group(0)
+    ref = np.concatenate([mlp_numpy.swarm_forces(mlp_weights, traj[b * G:(b + 1) * G], 0, G) for b in range(nb)])
+    assert np.abs(ref).max() > 1.0
+    assert np.abs(f - ref).max() < 1e-4
+    assert np.array_equal(sub, f[2 * G + 1:4 * G + 1])
+    assert not np.allclose(all_pairs.cpu().numpy(), f, atol=1e-3)
+    assert torch.equal(nn.forward_swarm(t, 0, n_all, path=nn.PATH_FP32), all_pairs)
