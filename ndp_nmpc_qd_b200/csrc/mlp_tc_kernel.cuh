@@ -7,10 +7,14 @@
 //
 // Precision: the reference runs this net in fp32 (cuBLAS SGEMM).  Plain bf16/fp16 operands would
 // miss the u0 parity target, so every operand is split into two fp16 halves
-//     a = a_hi + 2^-11 a_lo,   a_hi = fp16(a),  a_lo = fp16((a - a_hi) * 2^11)
-// and the product is accumulated as  D_main += a_hi b_hi,  D_corr += a_hi b_lo + a_lo b_hi,
-// result = D_main + 2^-11 D_corr  (dropped term a_lo b_lo ~ 2^-22): three MMAs per k-step,
-// ~fp32 accuracy with 16-bit operands.  Valid for |feature| < ~1e3 (fp16 range of the activations).
+//     a = a_hi + a_lo,   a_hi = fp16(a),  a_lo = fp16(a - a_hi)   (a_lo ~ 2^-11 |a|: an fp16 subnormal below |a| ~ 0.12,
+//                                                                  absolute error <= 3e-8 there)
+// and the product is accumulated into ONE fp32 accumulator,  D += a_hi b_hi + a_hi b_lo + a_lo b_hi  (dropped term
+// a_lo b_lo ~ 2^-22): three MMAs per k-step, ~fp32 accuracy with 16-bit operands (max error 7.7e-6 N against fp64 on
+// the shipped weights; plain fp32 is at 5.9e-6).  Valid for |feature| < ~1e3 (fp16 range of the activations).
+// An earlier version scaled the lo halves by 2^11 and kept main / correction accumulators apart: the epilogues then
+// read twice the tensor memory, and TMEM read bandwidth (~100 B/clk/SM measured) is what bounds this kernel --
+// cutting 25 % of the CUDA-core instructions changed nothing, halving the TMEM reads did.
 //
 // CTA = 128 threads = 128 rows (thread t <-> row t <-> TMEM lane t), persistent over row tiles.
 // Operands live in shared memory in the canonical no-swizzle K-major UMMA layout: 8x8 fp16 core
@@ -27,8 +31,6 @@ namespace ndp {
 constexpr long long MLPT_MIN_ROWS = 2048;  // below this the fp32 CUDA-core kernel is used (latency path)
 constexpr int MLPT_ROWS = 128;
 constexpr int MLPT_THREADS = 256;  // per 128-row tile: two threads per row (each owns half of the columns)
-constexpr float MLPT_LO_SCALE = 2048.f;       // 2^11
-constexpr float MLPT_LO_INV = 1.f / 2048.f;
 
 // fp16 operand images (elements): [W2 hi; W2 lo] [128 x 128], [W3 hi; W3 lo] [256 x 64]
 constexpr int MLPT_W2_ELEMS = MLP_H2 * MLP_H1;
@@ -45,6 +47,7 @@ struct alignas(16) MlpSmall {
 // shared memory map (bytes): weights once per CTA, one activation region per 128-thread group
 // (h2 hi/lo alias the front of the h1 region: h1 is dead once the layer-2 MMAs have committed)
 constexpr int MLPT_GROUPS = 2;
+constexpr int MLPT_TMEM_COLS = 256;  // one 128-column fp32 accumulator per group, reused by the three layers
 constexpr int MLPT_CTA_THREADS = MLPT_GROUPS * MLPT_THREADS;
 constexpr int MLPT_S_W2H = 0;
 constexpr int MLPT_S_W2L = MLPT_S_W2H + MLPT_W2_ELEMS * 2;
@@ -119,15 +122,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
 }
 
-// split 8 fp32 values into hi / scaled-lo fp16 and store both 16-byte chunks
+// split 8 fp32 values into hi / lo fp16 (lo = the rounding residual, unscaled) and store both 16-byte chunks
 __device__ __forceinline__ void split_store8(const float (&h)[8], __half* dst_hi, __half* dst_lo) {
     __half2 hi[4], lo[4];
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-        const __half a = __float2half_rn(h[2 * i]), b = __float2half_rn(h[2 * i + 1]);
-        hi[i] = __halves2half2(a, b);
-        lo[i] = __halves2half2(__float2half_rn((h[2 * i] - __half2float(a)) * MLPT_LO_SCALE),
-                               __float2half_rn((h[2 * i + 1] - __half2float(b)) * MLPT_LO_SCALE));
+        hi[i] = __floats2half2_rn(h[2 * i], h[2 * i + 1]);
+        const float2 f = __half22float2(hi[i]);
+        lo[i] = __floats2half2_rn(h[2 * i] - f.x, h[2 * i + 1] - f.y);
     }
     *reinterpret_cast<uint4*>(dst_hi) = *reinterpret_cast<uint4*>(hi);
     *reinterpret_cast<uint4*>(dst_lo) = *reinterpret_cast<uint4*>(lo);
@@ -209,24 +211,21 @@ __global__ void __launch_bounds__(MLPT_CTA_THREADS, 1) mlp_tc_kernel(const MlpSm
                          : "memory");
     }
     if (threadIdx.x < 32) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(sTmem)), "r"(512) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(sTmem)), "r"(MLPT_TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem = *sTmem + grp * 256;
-    // layer-2 accumulators alias the front of the layer-3 ones (dead by then)
-    const uint32_t tD1m = tmem + 0, tD1c = tmem + 64, tD2m = tmem + 0, tD2c = tmem + 128;
-    const uint32_t tD0m = tmem + 0, tD0c = tmem + 128;  // layer 1 (dead before layer 2 is issued)
+    const uint32_t tD = *sTmem + grp * (MLPT_TMEM_COLS / MLPT_GROUPS);  // the accumulator of every layer (each is dead before the next is issued)
     const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;  // this warp's TMEM lane quarter
     const uint32_t aW2h = smem_u32(smt + MLPT_S_W2H), aW3h = smem_u32(smt + MLPT_S_W3H), aW1h = smem_u32(smt + MLPT_S_W1H);
     const uint32_t aA1h = smem_u32(sA1h), aA1l = smem_u32(sA1l), aA2h = smem_u32(sA2h), aA2l = smem_u32(sA2l);
     const uint32_t aA0h = smem_u32(sA0h), aA0l = smem_u32(sA0l);
-    constexpr uint32_t ID1 = umma_idesc(128, MLP_H2), ID2 = umma_idesc(128, MLP_H3);
-    constexpr uint32_t ID0 = umma_idesc(128, MLP_H1), ID0C = umma_idesc(128, 2 * MLP_H1);
-    constexpr uint32_t ID1C = umma_idesc(128, 2 * MLP_H2), ID2C = umma_idesc(128, 2 * MLP_H3);  // concatenated hi|lo operands
+    constexpr uint32_t ID0 = umma_idesc(128, MLP_H1), ID1 = umma_idesc(128, MLP_H2), ID2 = umma_idesc(128, MLP_H3);
+    // weight images are [W_hi; W_lo] (2R rows) per k-chunk: the lo rows start R / 8 row groups into each chunk
+    constexpr uint32_t LO1 = (MLP_H1 / 8) * 128, LO2 = (MLP_H2 / 8) * 128, LO3 = (MLP_H3 / 8) * 128;
     uint32_t phase = 0;
 
     MLPT_STAMP(stamp++);  // setup done
@@ -263,9 +262,12 @@ __global__ void __launch_bounds__(MLPT_CTA_THREADS, 1) mlp_tc_kernel(const MlpSm
             mbar_wait(wbar, 0);  // weights have landed (returns immediately after the first tile)
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint64_t dAh = umma_desc(aA0h, (MLPT_ROWS / 8) * 128, 128), dAl = umma_desc(aA0l, (MLPT_ROWS / 8) * 128, 128);
-            const uint64_t dB = umma_desc(aW1h, (2 * MLP_H1 / 8) * 128, 128);  // [W1_hi; W1_lo], 256 rows
-            umma_f16(tD0m, dAh, dB, ID0C, 0);   // main (cols 0..127) and x_hi . W1_lo (cols 128..255)
-            umma_f16(tD0c, dAl, dB, ID0, 1);    // + x_lo . W1_hi
+            const uint64_t dBh = umma_desc(aW1h, (2 * MLP_H1 / 8) * 128, 128), dBl = umma_desc(aW1h + LO1, (2 * MLP_H1 / 8) * 128, 128);
+            // the two small correction products first, the main product last: the tensor core aligns every addend to
+            // the accumulator's exponent, so the corrections are summed while the accumulator is still small
+            umma_f16(tD, dAh, dBl, ID0, 0);   // x_hi . W1_lo
+            umma_f16(tD, dAl, dBh, ID0, 1);   // + x_lo . W1_hi
+            umma_f16(tD, dAh, dBh, ID0, 1);   // + x_hi . W1_hi
             umma_commit(bar);
           }
           __syncwarp();
@@ -276,14 +278,13 @@ __global__ void __launch_bounds__(MLPT_CTA_THREADS, 1) mlp_tc_kernel(const MlpSm
         // ---- epilogue 0: h1 = relu(D0) -> hi/lo operand tiles ----
 #pragma unroll 1
         for (int c0 = hf * 64; live && c0 < hf * 64 + 64; c0 += 32) {
-            float m[32], cr[32];
-            tmem_ld32(tD0m + lane_sel + c0, m);
-            tmem_ld32(tD0c + lane_sel + c0, cr);
+            float m[32];
+            tmem_ld32(tD + lane_sel + c0, m);
 #pragma unroll
             for (int kb = 0; kb < 4; kb++) {
                 float h[8];
 #pragma unroll
-                for (int i = 0; i < 8; i++) h[i] = fmaxf(fmaf(cr[kb * 8 + i], MLPT_LO_INV, m[kb * 8 + i]), 0.f);
+                for (int i = 0; i < 8; i++) h[i] = fmaxf(m[kb * 8 + i], 0.f);
                 const int off = umma_off(t, c0 + kb * 8, MLPT_ROWS);
                 split_store8(h, sA1h + off, sA1l + off);
             }
@@ -303,11 +304,14 @@ __global__ void __launch_bounds__(MLPT_CTA_THREADS, 1) mlp_tc_kernel(const MlpSm
                 const uint32_t ao = ks * 2 * (MLPT_ROWS / 8) * 128;  // two k-chunks per step
                 const uint32_t bo = ks * 2 * (2 * MLP_H2 / 8) * 128;
                 const uint64_t dAh = umma_desc(aA1h + ao, (MLPT_ROWS / 8) * 128, 128), dAl = umma_desc(aA1l + ao, (MLPT_ROWS / 8) * 128, 128);
-                // B = [W2_hi; W2_lo] as one 128-row operand: one N=128 MMA fills the main (cols 0..63) and the
-                // first correction term (cols 64..127); the second correction term reuses the hi rows (N=64)
-                const uint64_t dB = umma_desc(aW2h + bo, (2 * MLP_H2 / 8) * 128, 128);
-                umma_f16(tD1m, dAh, dB, ID1C, ks > 0);
-                umma_f16(tD1c, dAl, dB, ID1, 1);
+                const uint64_t dBh = umma_desc(aW2h + bo, (2 * MLP_H2 / 8) * 128, 128), dBl = umma_desc(aW2h + bo + LO2, (2 * MLP_H2 / 8) * 128, 128);
+                umma_f16(tD, dAh, dBl, ID1, ks > 0);   // corrections of every k-step first (see layer 1)
+                umma_f16(tD, dAl, dBh, ID1, 1);
+            }
+#pragma unroll
+            for (int ks = 0; ks < MLP_H1 / 16; ks++) {
+                const uint32_t ao = ks * 2 * (MLPT_ROWS / 8) * 128, bo = ks * 2 * (2 * MLP_H2 / 8) * 128;
+                umma_f16(tD, umma_desc(aA1h + ao, (MLPT_ROWS / 8) * 128, 128), umma_desc(aW2h + bo, (2 * MLP_H2 / 8) * 128, 128), ID1, 1);
             }
             umma_commit(bar);
           }
@@ -321,16 +325,15 @@ __global__ void __launch_bounds__(MLPT_CTA_THREADS, 1) mlp_tc_kernel(const MlpSm
         // ---- epilogue 1: h2 = relu(D1 + b2) -> hi/lo operand tiles (over the dead h1 tiles) ----
         if (live) {
             const int c0 = hf * 32;
-            float m[32], cr[32];
-            tmem_ld32(tD1m + lane_sel + c0, m);
-            tmem_ld32(tD1c + lane_sel + c0, cr);
+            float m[32];
+            tmem_ld32(tD + lane_sel + c0, m);
 #pragma unroll
             for (int kb = 0; kb < 4; kb++) {
                 float h[8];
 #pragma unroll
                 for (int i = 0; i < 8; i++) {
                     const int n = c0 + kb * 8 + i;
-                    h[i] = fmaxf(m[kb * 8 + i] + cr[kb * 8 + i] * MLPT_LO_INV + sq.b2[n], 0.f);
+                    h[i] = fmaxf(m[kb * 8 + i] + sq.b2[n], 0.f);
                 }
                 const int off = umma_off(t, c0 + kb * 8, MLPT_ROWS);
                 split_store8(h, sA2h + off, sA2l + off);
@@ -350,9 +353,14 @@ __global__ void __launch_bounds__(MLPT_CTA_THREADS, 1) mlp_tc_kernel(const MlpSm
                 const uint32_t ao = ks * 2 * (MLPT_ROWS / 8) * 128;
                 const uint32_t bo = ks * 2 * (2 * MLP_H3 / 8) * 128;
                 const uint64_t dAh = umma_desc(aA2h + ao, (MLPT_ROWS / 8) * 128, 128), dAl = umma_desc(aA2l + ao, (MLPT_ROWS / 8) * 128, 128);
-                const uint64_t dB = umma_desc(aW3h + bo, (2 * MLP_H3 / 8) * 128, 128);  // [W3_hi; W3_lo], 256 rows
-                umma_f16(tD2m, dAh, dB, ID2C, ks > 0);
-                umma_f16(tD2c, dAl, dB, ID2, 1);
+                const uint64_t dBh = umma_desc(aW3h + bo, (2 * MLP_H3 / 8) * 128, 128), dBl = umma_desc(aW3h + bo + LO3, (2 * MLP_H3 / 8) * 128, 128);
+                umma_f16(tD, dAh, dBl, ID2, ks > 0);
+                umma_f16(tD, dAl, dBh, ID2, 1);
+            }
+#pragma unroll
+            for (int ks = 0; ks < MLP_H2 / 16; ks++) {
+                const uint32_t ao = ks * 2 * (MLPT_ROWS / 8) * 128, bo = ks * 2 * (2 * MLP_H3 / 8) * 128;
+                umma_f16(tD, umma_desc(aA2h + ao, (MLPT_ROWS / 8) * 128, 128), umma_desc(aW3h + bo, (2 * MLP_H3 / 8) * 128, 128), ID2, 1);
             }
             umma_commit(bar);
           }
@@ -364,28 +372,30 @@ __global__ void __launch_bounds__(MLPT_CTA_THREADS, 1) mlp_tc_kernel(const MlpSm
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         MLPT_STAMP(stamp++);
         // ---- epilogue 2: h3 = relu(D2 + b3); layer 4 (CUDA cores, fp32): out = W4 h3 + b4 ----
+        // two partial sums per output (even / odd elements): six independent FMA chains
         float o0 = hf ? 0.f : sq.b4[0], o1 = hf ? 0.f : sq.b4[1], o2 = hf ? 0.f : sq.b4[2];
+        float q0 = 0.f, q1 = 0.f, q2 = 0.f;
 #pragma unroll 1
         for (int c0 = hf * 64; live && c0 < hf * 64 + 64; c0 += 32) {
-            float m[32], cr[32];
-            tmem_ld32(tD2m + lane_sel + c0, m);
-            tmem_ld32(tD2c + lane_sel + c0, cr);
+            float m[32];
+            tmem_ld32(tD + lane_sel + c0, m);
 #pragma unroll
             for (int i4 = 0; i4 < 8; i4++) {
                 const float4 b = *reinterpret_cast<const float4*>(sq.b3 + c0 + 4 * i4);
                 const float4 w0 = *reinterpret_cast<const float4*>(sq.W4 + c0 + 4 * i4);
                 const float4 w1 = *reinterpret_cast<const float4*>(sq.W4 + MLP_H3 + c0 + 4 * i4);
                 const float4 w2 = *reinterpret_cast<const float4*>(sq.W4 + 2 * MLP_H3 + c0 + 4 * i4);
-                const float h0 = fmaxf(m[4 * i4 + 0] + cr[4 * i4 + 0] * MLPT_LO_INV + b.x, 0.f);
-                const float h1 = fmaxf(m[4 * i4 + 1] + cr[4 * i4 + 1] * MLPT_LO_INV + b.y, 0.f);
-                const float h2 = fmaxf(m[4 * i4 + 2] + cr[4 * i4 + 2] * MLPT_LO_INV + b.z, 0.f);
-                const float h3 = fmaxf(m[4 * i4 + 3] + cr[4 * i4 + 3] * MLPT_LO_INV + b.w, 0.f);
+                const float h0 = fmaxf(m[4 * i4 + 0] + b.x, 0.f);
+                const float h1 = fmaxf(m[4 * i4 + 1] + b.y, 0.f);
+                const float h2 = fmaxf(m[4 * i4 + 2] + b.z, 0.f);
+                const float h3 = fmaxf(m[4 * i4 + 3] + b.w, 0.f);
                 o0 = fmaf(w0.x, h0, o0); o1 = fmaf(w1.x, h0, o1); o2 = fmaf(w2.x, h0, o2);
-                o0 = fmaf(w0.y, h1, o0); o1 = fmaf(w1.y, h1, o1); o2 = fmaf(w2.y, h1, o2);
+                q0 = fmaf(w0.y, h1, q0); q1 = fmaf(w1.y, h1, q1); q2 = fmaf(w2.y, h1, q2);
                 o0 = fmaf(w0.z, h2, o0); o1 = fmaf(w1.z, h2, o1); o2 = fmaf(w2.z, h2, o2);
-                o0 = fmaf(w0.w, h3, o0); o1 = fmaf(w1.w, h3, o1); o2 = fmaf(w2.w, h3, o2);
+                q0 = fmaf(w0.w, h3, q0); q1 = fmaf(w1.w, h3, q1); q2 = fmaf(w2.w, h3, q2);
             }
         }
+        o0 += q0; o1 += q1; o2 += q2;
         MLPT_STAMP(stamp++);
         if (hf) sOut[t] = make_float4(o0, o1, o2, 0.f);
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -400,7 +410,7 @@ __global__ void __launch_bounds__(MLPT_CTA_THREADS, 1) mlp_tc_kernel(const MlpSm
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     MLPT_STAMP(stamp++);  // both groups done
-    if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*sTmem), "r"(512) : "memory");
+    if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*sTmem), "r"(MLPT_TMEM_COLS) : "memory");
 }
 
 // host: build the fp16 hi/lo operand images of W2, W3 in UMMA layout and upload them
@@ -413,7 +423,7 @@ inline int mlp_tc_prepare(const float* host_params, void** out) {
                 const float w = W[r * K + k];
                 const __half h = __float2half_rn(w);
                 dst[umma_off(r, k, 2 * R)] = h;
-                dst[umma_off(R + r, k, 2 * R)] = __float2half_rn((w - __half2float(h)) * MLPT_LO_SCALE);
+                dst[umma_off(R + r, k, 2 * R)] = __float2half_rn(w - __half2float(h));
             }
     };
     put(host_params + MLP_OW2, MLP_H2, MLP_H1, img);

@@ -1,7 +1,6 @@
-// One instantiation of the fused SQP-RTI kernel per translation unit (precision x horizon x latency build):
-// the constrained path is reached through a function pointer (rti_kernel.cuh), and ptxas compiles a kernel
-// against every address-taken candidate of its module -- one candidate per module keeps that to seconds, and the
-// instantiations build in parallel (ndp_nmpc_qd_b200/build.py).
+// One instantiation of the SQP-RTI kernels per translation unit (precision x horizon x latency build): the nominal
+// kernel and, for the non-latency builds, the constrained kernel that takes the problems it hands over.  One
+// instantiation per module keeps ptxas to seconds, and the instantiations build in parallel (ndp_nmpc_qd_b200/build.py).
 //   nvcc -c rti_inst.cu -DNDP_INST_T=float -DNDP_INST_N=20 -DNDP_INST_LAT=false -DNDP_INST_TAG=f32_20_0
 #include "rti_kernel.cuh"
 

@@ -10,12 +10,18 @@
 //     column-local; cross-lane traffic is broadcast reads of small shared-memory tiles plus
 //     ten shuffles for the 4x4 input block,
 //   * the gradient recursion rides along as lane 14 with the same instruction stream.
-// The QP is solved exactly: unconstrained Riccati sweep first (if the step satisfies all box
-// bounds it IS the QP solution); otherwise a Mehrotra predictor-corrector IPM on the same
-// Riccati kernel (HPIPM's algorithm, qp_solver="PARTIAL_CONDENSING_HPIPM" with cond_N = N,
-// nmpc_body_rate_ctl.py:71-79) followed by primal-dual active-set rounds that remove the
-// barrier floor (needed for fp32).  Cost: NONLINEAR_LS Gauss-Newton blocks in closed form
-// (nmpc_body_rate_ctl.py:48-53,163-180), bounds :56-61, iterate protocol :86-112.
+// Two launches per solve.  rti_step_kernel (nominal, 128 registers, 8 CTAs of 4 problems per SM) linearises and runs the
+// unconstrained Riccati sweep; if the step satisfies all box bounds it IS the QP solution and is accepted on the fly in
+// the forward sweep.  A step that leaves its box is handed to rti_constrained_kernel (programmatic dependent launch, a
+// device queue of problem indices + the violated bounds as the first active set), which solves the QP exactly with
+// primal-dual active-set rounds on the same Riccati recursion: pinned inputs are eliminated from the 4x4 input block,
+// pinned velocity components of x_{k+1} are resolved as a stage-k mixed constraint in the range space of the inputs
+// (backward_stage, kBar == 2), multipliers decide releases, a hash history detects cycling (damped single releases
+// then), rounds restart the backward sweep at the highest stage whose pins changed.  A Mehrotra predictor-corrector
+// IPM on the same kernel (HPIPM's algorithm, qp_solver="PARTIAL_CONDENSING_HPIPM" with cond_N = N,
+// nmpc_body_rate_ctl.py:71-79) is kept as the fallback that proposes an active set when the rounds do not settle.
+// Cost: NONLINEAR_LS Gauss-Newton blocks in closed form (nmpc_body_rate_ctl.py:48-53,163-180), bounds :56-61, iterate
+// protocol :86-112 (global memory keeps the old iterate until a step is accepted).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -153,6 +159,17 @@ __device__ __forceinline__ T grp_sum(T v, unsigned mask) {
     for (int o = 8; o >= 1; o >>= 1) v += __shfl_xor_sync(mask, v, o, GL);
     return v;
 }
+// Group votes.  The nominal kernel runs its two problems per warp in lockstep and passes the constant full mask (no
+// MATCH / REDUX / BRA.DIV convergence check in front of every shuffle and __syncwarp); the vote is then taken from the
+// ballot bits of this thread's own half.  The constrained kernel's halves diverge and pass their half mask.
+__device__ __forceinline__ bool grp_any(unsigned mask, bool p) {
+    if (mask == 0xffffffffu) return ((__ballot_sync(0xffffffffu, p) >> (threadIdx.x & 16)) & 0xffffu) != 0u;
+    return __any_sync(mask, p) != 0;
+}
+__device__ __forceinline__ bool grp_all(unsigned mask, bool p) {
+    if (mask == 0xffffffffu) return ((__ballot_sync(0xffffffffu, p) >> (threadIdx.x & 16)) & 0xffffu) == 0xffffu;
+    return __all_sync(mask, p) != 0;
+}
 template <typename T>
 __device__ __forceinline__ T grp_min(T v, unsigned mask) {
 #pragma unroll
@@ -224,14 +241,16 @@ __device__ __forceinline__ void rk4_column(const RtiCfg<T>& c, int j, const T* _
 template <typename T>
 __device__ __forceinline__ void cost_records(int N, int lane, T* __restrict__ sY, const T* __restrict__ sX, const T* __restrict__ sU,
                                              const T* __restrict__ sPar) {
-    for (int i = lane; i < (N + 1) * SYS; i += GL) {
-        const int k = i >> 4, e = i & 15;
-        const T y = sY[i];
-        T v = T(0);
-        if (e < 6) v = sX[k * NX + e] - y;
-        else if (e >= 7 && e < 10) v = sPar[k * NPS + e - 6] - y;
-        else if (e >= 10 && e < 14 && k < N) v = sU[k * NU + e - 10] - y;
-        sY[i] = v;
+    // SYS == GL: lane e owns element e of every stage record -- its source and stride are fixed, no branches
+    static_assert(SYS == GL, "cost_records: one lane per record element");
+    const T* src = (lane < 6) ? sX + lane : ((lane < 10) ? sPar + (lane - 6) : sU + ((lane - 10) & 3));
+    const int str = (lane < 6) ? NX : ((lane < 10) ? NPS : NU);
+    const bool isu = lane >= 10, has = (lane != 6) && (lane < 14);
+#pragma unroll 3
+    for (int k = 0; k <= N; k++) {
+        const bool last_u = isu && (k == N);
+        const T v = src[(last_u ? N - 1 : k) * str] - sY[k * SYS + lane];
+        sY[k * SYS + lane] = (has && !last_u) ? v : T(0);
     }
 }
 
@@ -532,7 +551,7 @@ __device__ __forceinline__ bool backward_stage(const RtiCfg<T>& c, int N, int k,
     for (int i = 0; i < 10; i++) {
         T h0, h1, h2, h3;
         Vec4<T>::ld(sHux + i * 4, h0, h1, h2, h3);
-        Pn[i] = H[i] - (h0 * x0 + h1 * x1 + h2 * x2 + h3 * x3);  // unconstrained part: H_xx + H_xu K_unc
+        Pn[i] = H[i] - h0 * x0 - h1 * x1 - h2 * x2 - h3 * x3;  // unconstrained part: H_xx + H_xu K_unc (four dependent FFMAs)
     }
     if (kBar == 2 && vpins) {
         const T* sRv = sm + L.oDz;
@@ -681,7 +700,7 @@ __device__ __forceinline__ bool backward_sweep(const RtiCfg<T>& c, int N, int j,
             par ^= 1;
         }
     }
-    return __all_sync(mask, ok);
+    return grp_all(mask, ok);
 }
 
 // 4/8/16-byte asynchronous global -> shared copies (LDGSTS): the whole problem record is requested
@@ -743,15 +762,12 @@ __device__ __forceinline__ void forward_sweep(const RtiCfg<T>& c, int N, int lan
     };
     if (kFinal) {
         T* itp = isx ? sm + L.oX + lane : sm + L.oU + ((lane - 10) & 3);
-#ifdef NDP_DIRECT_STORE
-        T* gp = isx ? gX + lane : gU + ((lane - 10) & 3);
-#endif
         const int its = isx ? NX : NU;
         T* ring = sm + L.oY + ((lane < 14) ? lane : 13) * TLD;  // [FW_RING][14][TLD] over sY | sDz
-        auto issue = [&](int k) {
+        auto issue = [&](int k, int slot) {
             if (k < N && lane < 14) {
                 const T* r = rec + (long long)k * FW_REC;
-                T* d = ring + (k % FW_RING) * FW_REC;
+                T* d = ring + slot * FW_REC;
 #pragma unroll
                 for (int q = 0; q < 3; q++) {
                     if (sizeof(T) == 4) cp_async<16>(d + 4 * q, r + 4 * q);
@@ -762,28 +778,29 @@ __device__ __forceinline__ void forward_sweep(const RtiCfg<T>& c, int N, int lan
         };
         __syncwarp(mask);  // every lane is done with the cost records
 #pragma unroll
-        for (int u = 0; u < FW_RING; u++) issue(u);
+        for (int u = 0; u < FW_RING; u++) issue(u, u);
         bool v_l = false, b_l = false;
         int n_l = 0;
         T it_cur = itp[0];
-        for (int k = 0; k < N; k++) {
+        // ring slot of stage k = k % FW_RING: the loop runs in blocks of FW_RING stages so that the slot is a constant
+        for (int k0 = 0; k0 < N; k0 += FW_RING) {
+#pragma unroll
+          for (int u = 0; u < FW_RING; u++) {
+            const int k = k0 + u;
+            if (k >= N) break;
             const T it_nxt = (k + 1 < N || isx) ? itp[(k + 1) * its] : T(0);
             cp_async_wait<FW_RING - 1>();
             T cf[12];
-            const T* d = ring + (k % FW_RING) * FW_REC;
+            const T* d = ring + u * FW_REC;
             Vec4<T>::ld(d, cf[0], cf[1], cf[2], cf[3]);
             Vec4<T>::ld(d + 4, cf[4], cf[5], cf[6], cf[7]);
             Vec4<T>::ld(d + 8, cf[8], cf[9], cf[10], cf[11]);
-            issue(k + FW_RING);
+            issue(k + FW_RING, u);
             T dz;
             stage(k, cf, dz);
             if (lane < 14) {
                 const T v = it_cur + dz;
-#ifdef NDP_DIRECT_STORE
-                gp[k * its] = v;
-#else
                 itp[k * its] = v;
-#endif
                 b_l |= !(fabs(v) <= T(1e30));
                 if (isu || (isv && k >= 1)) {
                     v_l |= !(v >= lo && v <= hi);
@@ -791,15 +808,12 @@ __device__ __forceinline__ void forward_sweep(const RtiCfg<T>& c, int N, int lan
                 }
             }
             it_cur = it_nxt;
+          }
         }
         cp_async_wait<0>();
         if (isx) {
             const T v = it_cur + z;
-#ifdef NDP_DIRECT_STORE
-            gp[N * its] = v;
-#else
             itp[N * its] = v;
-#endif
             b_l |= !(fabs(v) <= T(1e30));
         }
         __syncwarp(mask);
@@ -807,8 +821,8 @@ __device__ __forceinline__ void forward_sweep(const RtiCfg<T>& c, int N, int lan
         // persistent loop (the constrained path of this problem reloads whole tiles, pads included, from the workspace)
         if (rezero_pads)
             for (int i = lane; i < 20; i += GL) { T* q = sm + L.oT0 + i * TLD + 9; q[0] = T(0); q[1] = T(0); q[2] = T(0); }
-        viol = __any_sync(mask, v_l);
-        bad = __any_sync(mask, b_l);
+        viol = grp_any(mask, v_l);
+        bad = grp_any(mask, b_l);
         nact = n_l;
     } else {
         constexpr int kPf = 2;
@@ -1306,7 +1320,7 @@ constexpr int QUEUE_SWEPT = 1 << 30;  // queue entry flag: the unconstrained swe
 // [xr_k; ur_k], p_k = [xr_k[6:10]; f_k] built from (xr, ur, f) and persisted to yref_w / par_w as if set stage by stage.
 template <typename T>
 __device__ __forceinline__ void stage_problem(const RtiArgs<T>& a, int N, const SmemLayout& L, int lane, unsigned mask, T* sm, int prob,
-                                              bool fused) {
+                                              bool fused, bool persist = true) {
     constexpr int E2 = 8 / (int)sizeof(T);  // elements per 8-byte copy (records are 8-byte aligned)
     T* sX = sm + L.oX;
     T* sU = sm + L.oU;
@@ -1357,17 +1371,25 @@ __device__ __forceinline__ void stage_problem(const RtiArgs<T>& a, int N, const 
     }
     cp_async_wait_all();
     __syncwarp(mask);
-    if (fused) {
+    if (fused && persist) {
         // persist yref / p as if set stage by stage (a later plain solve, a get, or the constrained kernel sees them)
         T* wY = a.yref_w + (size_t)prob * (N + 1) * NYS;
         T* wP = a.par_w + (size_t)prob * (N + 1) * NPS;
-        for (int i = lane; i < (N + 1) * NYS; i += GL) {
-            const int k = i / NYS;
-            wY[i] = sm[L.oY + k * SYS + (i - k * NYS)];
+        // 8-byte stores; two stage records per pass (lanes 0..6 and 8..14 carry the NYS / E2 vectors of one stage each)
+        typedef typename std::conditional<sizeof(T) == 4, float2, double>::type V2;
+        constexpr int VY = NYS / E2, VS = SYS / E2;
+        static_assert(VY <= 8 || sizeof(T) == 8, "persist: one half group per stage record");
+        if (sizeof(T) == 4) {
+            const int q = lane & 7;
+            for (int k = (lane >> 3); k <= N; k += 2)
+                if (q < VY) reinterpret_cast<V2*>(wY)[k * VY + q] = reinterpret_cast<const V2*>(sm + L.oY)[k * VS + q];
+        } else {
+            for (int k = 0; k <= N; k++)
+                if (lane < VY) reinterpret_cast<V2*>(wY)[k * VY + lane] = reinterpret_cast<const V2*>(sm + L.oY)[k * VS + lane];
         }
-        for (int i = lane; i < (N + 1) * NPS; i += GL) wP[i] = sm[L.oPar + i];
-        __syncwarp(mask);
+        for (int i = lane; i < (N + 1) * NPS / E2; i += GL) reinterpret_cast<V2*>(wP)[i] = reinterpret_cast<const V2*>(sm + L.oPar)[i];
     }
+    if (fused) __syncwarp(mask);  // outside the `persist` test: the two halves of a warp may differ in it, and `mask` may name both
 }
 
 // per-lane box of the variable this lane owns (lanes 3..5: v, lanes 10..13: u)
@@ -1395,7 +1417,10 @@ __global__ void __launch_bounds__(RTI_CTA, (sizeof(T) == 4) ? (kLat ? 4 : 8) : 3
     const WsLayout WL(N);
     const int lane = threadIdx.x & 15;
     const int grp = threadIdx.x >> 4;
-    const unsigned mask = 0xFFFFu << (threadIdx.x & 16);
+    const unsigned hmask = 0xFFFFu << (threadIdx.x & 16);  // this problem's half of the warp
+    // the two problems of a warp run the sweeps in lockstep (a half without a problem of its own repeats the last one
+    // and stores nothing), so every shuffle / __syncwarp of the sweeps names the whole warp with a compile-time mask
+    const unsigned mask = 0xffffffffu;
     const int ppc = blockDim.x >> 4;  // problems per CTA
     T* sTriv = reinterpret_cast<T*>(smem_raw);  // [10][TLD] constant tile of the trivial columns 0..5, shared by the CTA
     T* sm = sTriv + 10 * TLD + (size_t)grp * L.total;
@@ -1412,11 +1437,14 @@ __global__ void __launch_bounds__(RTI_CTA, (sizeof(T) == 4) ? (kLat ? 4 : 8) : 3
     lane_box<T>(c, lane, lo, hi);
     const bool isx = lane < 10, isu = (lane >= 10 && lane < 14), isv = (lane >= 3 && lane < 6);
 
-    for (int prob = blockIdx.x * ppc + grp; prob < a.B; prob += gridDim.x * ppc) {
+    for (int base = blockIdx.x * ppc; base < a.B; base += gridDim.x * ppc) {
+        const bool live = base + grp < a.B;
+        const int prob = live ? base + grp : a.B - 1;
+        const bool more = base + (int)gridDim.x * ppc < a.B;  // this CTA has another pass: the tiles' zero pads are needed again
         T* gX = a.X + (size_t)prob * (N + 1) * NX;
         T* gU = a.U + (size_t)prob * N * NU;
-        stage_problem<T>(a, N, L, lane, mask, sm, prob, a.xr != nullptr);
-        const T x0v = isx ? a.x0[(size_t)prob * NX + lane] : T(0);
+        const T x0v = isx ? a.x0[(size_t)prob * NX + lane] : T(0);  // requested before the record's copies are waited for
+        stage_problem<T>(a, N, L, lane, mask, sm, prob, a.xr != nullptr, live);
         // a set left by the previous solve of this problem (active_set_warm): straight to the constrained kernel
         unsigned long long* g_as = a.as_store + (size_t)prob * (AS_OWNERS * 4);
         unsigned long long as_any = 0ull;
@@ -1425,41 +1453,34 @@ __global__ void __launch_bounds__(RTI_CTA, (sizeof(T) == 4) ? (kLat ? 4 : 8) : 3
             const ulonglong2 m1 = *reinterpret_cast<const ulonglong2*>(g_as + as_owner(lane) * 4 + 2);
             as_any = m0.x | m0.y | m1.x | m1.y;
         }
-        const bool warm = __any_sync(mask, as_any != 0ull);
+        const bool warm = grp_any(mask, as_any != 0ull);
         bool ok = true, viol = false, bad = false;
         int nact_l = 0;
-        if (!warm) {
+        if (__any_sync(0xffffffffu, !warm)) {  // a warm half rides along with its neighbour's sweeps (results unused)
             cost_records<T>(N, lane, sm + L.oY, sX, sU, sm + L.oPar);
             __syncwarp(mask);
             const T dx0 = isx ? x0v - sX[lane] : T(0);
             // ---- preparation + unconstrained feedback; the step is accepted on the fly ----
             ok = backward_sweep<T, true, 0, false>(c, N, lane, mask, sm, L, ws, WL, ws, sTriv, nullptr);
             forward_sweep<T, true>(c, N, lane, mask, dx0, sm, L, ws, WL, lo, hi, gX, gU, nullptr, viol, bad, nact_l,
-                                   prob + (int)gridDim.x * ppc < a.B);
+                                   more);
         }
-        if (warm || (ok && viol && !bad)) {
+        const int nact = (int)grp_sum<float>((float)nact_l, mask);
+        if (!live) {
+            // nothing of its own to store
+        } else if (warm || (ok && viol && !bad)) {
             if (!warm && (isu || isv)) {
                 // the bounds the unconstrained step violates seed the active-set rounds
                 StageMask m_lo, m_hi;
                 for (int k = isv ? 1 : 0; k < N; k++) {
-#ifdef NDP_DIRECT_STORE
-                    const T v = isu ? gU[k * NU + (lane - 10)] : gX[k * NX + lane];  // this lane's own stores
-#else
                     const T v = isu ? sU[k * NU + (lane - 10)] : sX[k * NX + lane];
-#endif
                     if (v < lo) m_lo.set(k);
                     else if (v > hi) m_hi.set(k);
                 }
                 unsigned long long* p = g_as + as_owner(lane) * 4;
                 p[0] = m_lo.w0; p[1] = m_lo.w1; p[2] = m_hi.w0; p[3] = m_hi.w1;
             }
-            __syncwarp(mask);
-#ifdef NDP_DIRECT_STORE
-            if (!warm) {  // put the old iterate back (it is still in shared memory)
-                for (int i = lane; i < (N + 1) * NX; i += GL) gX[i] = sX[i];
-                for (int i = lane; i < N * NU; i += GL) gU[i] = sU[i];
-            }
-#endif
+            __syncwarp(hmask);
             if (lane == 0) {
                 __threadfence();
                 const int slot = atomicAdd(a.qctl, 1);
@@ -1469,16 +1490,6 @@ __global__ void __launch_bounds__(RTI_CTA, (sizeof(T) == 4) ? (kLat ? 4 : 8) : 3
             int status = 0;
             if (!ok) status = 4;
             if (bad) status = 1;
-            const int nact = (int)grp_sum<float>((float)nact_l, mask);
-#ifdef NDP_DIRECT_STORE
-            if (status == 0) {
-                if (a.u0 && lane < NU) a.u0[(size_t)prob * NU + lane] = gU[lane];
-            } else {
-                for (int i = lane; i < (N + 1) * NX; i += GL) gX[i] = sX[i];
-                for (int i = lane; i < N * NU; i += GL) gU[i] = sU[i];
-                if (a.u0 && lane < NU) a.u0[(size_t)prob * NU + lane] = sU[lane];
-            }
-#else
             if (status == 0) {
                 // accepted: the new iterate goes out with 8-byte stores
                 constexpr int E2 = 8 / (int)sizeof(T);
@@ -1491,7 +1502,6 @@ __global__ void __launch_bounds__(RTI_CTA, (sizeof(T) == 4) ? (kLat ? 4 : 8) : 3
                 // update it when the QP fails); return the previous first input
                 a.u0[(size_t)prob * NU + lane] = gU[lane];
             }
-#endif
             if (lane == 0) {
                 a.status[prob] = status;
                 if (a.status2) a.status2[prob] = status;

@@ -101,10 +101,11 @@ def test_update_matches_reference_semantics(nn, mlp_weights):
 
 
 # ---------------- tensor-core (tcgen05) path ----------------
-# fp16 hi/lo split operands, fp32 accumulation in TMEM: ~fp32 accuracy.  Tolerance 3e-5 N absolute
-# against the fp64 evaluation of the reference net (forces are O(1-5) N; the north-star parity target
-# of 1e-4 relative on u0 corresponds to ~1.5e-3 N).
-TC_TOL = 3e-5
+# fp16 hi/lo split operands, fp32 accumulation in TMEM: ~fp32 accuracy.  Tolerance 5e-5 N absolute against the fp64
+# evaluation of the reference net.  The rows of these tests reach 9 m/s relative velocity and |f| = 37 N, where fp32 (the
+# reference's own arithmetic) is itself 1.5e-5 from fp64; at flight-like features (forces of O(1-5) N) the error is
+# below 1e-5 N.  The north-star parity target of 1e-4 relative on u0 corresponds to ~1.5e-3 N.
+TC_TOL = 5e-5
 
 
 def test_tc_rows_vs_reference_module(nn):
