@@ -161,28 +161,6 @@ __global__ void __launch_bounds__(MLPT_CTA_THREADS, 1) mlp_tc_kernel(const MlpSm
     const MlpSmall& sq = *reinterpret_cast<const MlpSmall*>(smt + MLPT_S_PAR);
     int stamp = 0;
     MLPT_STAMP(stamp++);  // kernel entry
-    const long long M = mlp_rows(io);
-    // Rows are dealt to the (CTA, group) pairs in units of 32 (one warp's rows), as evenly as they go: every group gets
-    // floor or ceil of (row-warps / groups) of them as one contiguous range, walked in 128-row tiles.  The last tile of a
-    // range is then partial everywhere (its idle warps skip the CUDA-core phases) instead of a full extra round on a
-    // fraction of the SMs: 86 016 rows on 296 groups are 128 + 128 + 32 (or 64) rows each, not three full tiles on 80
-    // groups and two on the rest.  Group g of CTA c has index g * gridDim.x + c, so the longer ranges land on different SMs.
-    const long long n_w = (M + 31) / 32, n_grp = (long long)gridDim.x * MLPT_GROUPS;
-    const long long gidx = (long long)grp * gridDim.x + blockIdx.x;
-    const long long w_q = n_w / n_grp, w_r = n_w % n_grp;
-    const long long row_begin = (gidx * w_q + (gidx < w_r ? gidx : w_r)) * 32;
-    const long long row_end_raw = row_begin + (w_q + (gidx < w_r ? 1 : 0)) * 32;
-    const long long row_end = row_end_raw < M ? row_end_raw : M;
-    if ((long long)blockIdx.x * 32 >= M) return;  // device-sized launches: no rows for either group of this CTA (before any barrier / TMA / TMEM setup)
-    const long long n_tiles = row_end > row_begin ? (row_end - row_begin + MLPT_ROWS - 1) / MLPT_ROWS : 0;
-    MlpRaw raw;  // loaded, not yet used: the features are formed one tile later (mlp_fetch_finish)
-#pragma unroll
-    for (int i = 0; i < 6; i++) { raw.o[i] = 0.f; raw.e[i] = 0.f; }
-    raw.gated = false; raw.on = false; raw.ox = raw.oy = raw.gx = raw.gy = 0.f;
-    if (row_begin + t < row_end) mlp_fetch_issue(io, row_begin + t, raw);
-    // a solve launched as a programmatic dependent (NDP_UPDATE_F_FROM_PREVIOUS_KERNEL) may be scheduled as CTAs of this
-    // grid retire; it synchronises on this grid's completion itself before it reads the forces
-    asm volatile("griddepcontrol.launch_dependents;");
     {
         // side parameters: one coalesced 128-bit load per thread from the device copy (staging them from the kernel's
         // constant-bank argument took 9 % of the kernel: every lane of a warp read a different constant address)
@@ -227,6 +205,35 @@ __global__ void __launch_bounds__(MLPT_CTA_THREADS, 1) mlp_tc_kernel(const MlpSm
     // weight images are [W_hi; W_lo] (2R rows) per k-chunk: the lo rows start R / 8 row groups into each chunk
     constexpr uint32_t LO1 = (MLP_H1 / 8) * 128, LO2 = (MLP_H2 / 8) * 128, LO3 = (MLP_H3 / 8) * 128;
     uint32_t phase = 0;
+    // This kernel is launched as a programmatic dependent of whatever precedes it in the stream: everything above (barriers,
+    // weight copy, tensor-memory allocation -- nothing another kernel writes) has run under that kernel's tail; its
+    // results (features, pair lists, the row count) are read from here on.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const long long M = mlp_rows(io);
+    // Rows are dealt to the (CTA, group) pairs in units of 32 (one warp's rows), as evenly as they go: every group gets
+    // floor or ceil of (row-warps / groups) of them as one contiguous range, walked in 128-row tiles.  The last tile of a
+    // range is then partial everywhere (its idle warps skip the CUDA-core phases) instead of a full extra round on a
+    // fraction of the SMs: 86 016 rows on 296 groups are 128 + 128 + 32 (or 64) rows each, not three full tiles on 80
+    // groups and two on the rest.  Group g of CTA c has index g * gridDim.x + c, so the longer ranges land on different SMs.
+    const long long n_w = (M + 31) / 32, n_grp = (long long)gridDim.x * MLPT_GROUPS;
+    const long long gidx = (long long)grp * gridDim.x + blockIdx.x;
+    const long long w_q = n_w / n_grp, w_r = n_w % n_grp;
+    const long long row_begin = (gidx * w_q + (gidx < w_r ? gidx : w_r)) * 32;
+    const long long row_end_raw = row_begin + (w_q + (gidx < w_r ? 1 : 0)) * 32;
+    const long long row_end = row_end_raw < M ? row_end_raw : M;
+    // (device-sized launches: a CTA may find no rows for either of its groups; it still waits for its weight copy and
+    // frees its tensor memory below)
+    const long long n_tiles = row_end > row_begin ? (row_end - row_begin + MLPT_ROWS - 1) / MLPT_ROWS : 0;
+    MlpRaw raw;  // loaded, not yet used: the features are formed one tile later (mlp_fetch_finish)
+#pragma unroll
+    for (int i = 0; i < 6; i++) { raw.o[i] = 0.f; raw.e[i] = 0.f; }
+    raw.gated = false; raw.on = false; raw.ox = raw.oy = raw.gx = raw.gy = 0.f;
+    if (row_begin + t < row_end) mlp_fetch_issue(io, row_begin + t, raw);
+    // a solve launched as a programmatic dependent (NDP_UPDATE_F_FROM_PREVIOUS_KERNEL) may be scheduled as CTAs of this
+    // grid retire; it synchronises on this grid's completion itself before it reads the forces.  Issued only now, after
+    // this grid's own dependency wait: the dependent's prologue reads data (the iterate) that the kernels before this one
+    // may still have been writing.
+    asm volatile("griddepcontrol.launch_dependents;");
 
     MLPT_STAMP(stamp++);  // setup done
     for (long long tile = 0; tile < n_tiles; tile++) {
@@ -407,6 +414,7 @@ __global__ void __launch_bounds__(MLPT_CTA_THREADS, 1) mlp_tc_kernel(const MlpSm
         MLPT_STAMP(stamp++);
     }
     MLPT_STAMP(stamp++);  // this group's tiles done
+    if (threadIdx.x == 0) mbar_wait(wbar, 0);  // the bulk copy into this CTA's shared memory must not outlive it
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     MLPT_STAMP(stamp++);  // both groups done
@@ -457,7 +465,17 @@ inline int mlp_tc_launch(const MlpSmall* sp_dev, const void* wimg, const MlpIo& 
     const long long tiles = (io.M + MLPT_ROWS - 1) / MLPT_ROWS;  // io.M is the row capacity when the count lives on the device
     const long long ctas = (tiles + MLPT_GROUPS - 1) / MLPT_GROUPS;
     const int grd = (int)(ctas < n_sm ? ctas : n_sm);
-    mlp_tc_kernel<<<grd, MLPT_CTA_THREADS, MLPT_SMEM, st>>>(sp_dev, reinterpret_cast<const __half*>(wimg), io);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grd);
+    cfg.blockDim = dim3(MLPT_CTA_THREADS);
+    cfg.dynamicSmemBytes = MLPT_SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // see griddepcontrol.wait in the kernel
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, mlp_tc_kernel, sp_dev, reinterpret_cast<const __half*>(wimg), io);
     return (int)cudaGetLastError();
 }
 
