@@ -332,6 +332,9 @@ static int set_get(ndp_handle* h, int field, int stage, void* dev, int64_t ld, v
     return 0;
 }
 
+#ifdef NDP_RTI_PROF
+namespace ndp { int rti_prof_f32_20_0(unsigned long long* host); }  // diagnostics build (tests/diag/gpu_diag_rti_phases.py)
+#endif
 extern "C" {
 
 const char* ndp_last_error(void) { return g_err.c_str(); }
@@ -750,6 +753,9 @@ int ndp_mlp_destroy(ndp_mlp* m) {
 }
 
 // debug helper (not part of the public header): phase timestamps of the last profiled tensor-core launch
+#ifdef NDP_RTI_PROF
+int ndp_debug_rti_prof(unsigned long long* host) { return ndp::rti_prof_f32_20_0(host); }
+#endif
 int ndp_debug_mlp_prof(long long* host128) {
     return (int)cudaMemcpyFromSymbol(host128, ndp::g_mlpt_prof, sizeof(long long) * 128);
 }

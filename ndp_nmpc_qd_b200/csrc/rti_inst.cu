@@ -41,6 +41,10 @@ void NDP_CAT(rti_launch_, NDP_INST_TAG)(int grid, int threads, size_t smem, cuda
     cudaLaunchKernelEx(&cfg, rti_step_kernel<NDP_INST_T, NDP_INST_N, NDP_INST_LAT>, c, a);
 }
 
+#ifdef NDP_RTI_PROF
+int NDP_CAT(rti_prof_, NDP_INST_TAG)(unsigned long long* host) { return (int)cudaMemcpyFromSymbol(host, g_rti_prof, sizeof(unsigned long long) * 2048 * 8); }
+#endif
+
 const void* NDP_CAT(rti_kernel_, NDP_INST_TAG)() { return (const void*)rti_step_kernel<NDP_INST_T, NDP_INST_N, NDP_INST_LAT>; }
 
 #if !NDP_INST_LAT_IS_TRUE

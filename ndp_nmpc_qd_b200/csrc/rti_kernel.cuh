@@ -1313,6 +1313,14 @@ __device__ __forceinline__ void constrained_qp(const RtiCfg<T>& c, int lane, uns
 }
 
 constexpr int RTI_CTA = 64;  // threads per CTA of both launches (4 problems)
+#ifdef NDP_RTI_PROF
+// diagnostics build: globaltimer stamps of every CTA's first pass (thread 0): entry, record staged, cost records,
+// backward sweep, forward sweep, stores
+static __device__ unsigned long long g_rti_prof[2048 * 8];
+#define RTI_GT(i) do { if (threadIdx.x == 0 && blockIdx.x < 2048 && base == (int)blockIdx.x * ppc) { unsigned long long t_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_)); g_rti_prof[blockIdx.x * 8 + (i)] = t_; } } while (0)
+#else
+#define RTI_GT(i) do { } while (0)
+#endif
 constexpr int QUEUE_SWEPT = 1 << 30;  // queue entry flag: the unconstrained sweep of this solve has run (statistics)
 
 // Stage one problem record in shared memory with asynchronous copies (one wait): iterate, then either the stored
@@ -1441,10 +1449,15 @@ __global__ void __launch_bounds__(RTI_CTA, (sizeof(T) == 4) ? (kLat ? 4 : 8) : 3
         const bool live = base + grp < a.B;
         const int prob = live ? base + grp : a.B - 1;
         const bool more = base + (int)gridDim.x * ppc < a.B;  // this CTA has another pass: the tiles' zero pads are needed again
+        RTI_GT(0);
+#ifdef NDP_RTI_PROF
+        if (threadIdx.x == 0 && blockIdx.x < 2048 && base == (int)blockIdx.x * ppc) { unsigned sm_; asm volatile("mov.u32 %0, %smid;" : "=r"(sm_)); g_rti_prof[blockIdx.x * 8 + 6] = sm_; }
+#endif
         T* gX = a.X + (size_t)prob * (N + 1) * NX;
         T* gU = a.U + (size_t)prob * N * NU;
         const T x0v = isx ? a.x0[(size_t)prob * NX + lane] : T(0);  // requested before the record's copies are waited for
         stage_problem<T>(a, N, L, lane, mask, sm, prob, a.xr != nullptr, live);
+        RTI_GT(1);
         // a set left by the previous solve of this problem (active_set_warm): straight to the constrained kernel
         unsigned long long* g_as = a.as_store + (size_t)prob * (AS_OWNERS * 4);
         unsigned long long as_any = 0ull;
@@ -1460,12 +1473,15 @@ __global__ void __launch_bounds__(RTI_CTA, (sizeof(T) == 4) ? (kLat ? 4 : 8) : 3
             cost_records<T>(N, lane, sm + L.oY, sX, sU, sm + L.oPar);
             __syncwarp(mask);
             const T dx0 = isx ? x0v - sX[lane] : T(0);
+            RTI_GT(2);
             // ---- preparation + unconstrained feedback; the step is accepted on the fly ----
             ok = backward_sweep<T, true, 0, false>(c, N, lane, mask, sm, L, ws, WL, ws, sTriv, nullptr);
+            RTI_GT(3);
             forward_sweep<T, true>(c, N, lane, mask, dx0, sm, L, ws, WL, lo, hi, gX, gU, nullptr, viol, bad, nact_l,
                                    more);
         }
         const int nact = (int)grp_sum<float>((float)nact_l, mask);
+        RTI_GT(4);
         if (!live) {
             // nothing of its own to store
         } else if (warm || (ok && viol && !bad)) {
@@ -1512,6 +1528,7 @@ __global__ void __launch_bounds__(RTI_CTA, (sizeof(T) == 4) ? (kLat ? 4 : 8) : 3
             }
         }
         __syncwarp(mask);
+        RTI_GT(5);
     }
 }
 
