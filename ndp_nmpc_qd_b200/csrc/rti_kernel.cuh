@@ -35,6 +35,8 @@ constexpr int NYS = 14;  // yref stride per stage (global)
 constexpr int SYS = 16;  // shared-memory stride of the per-stage cost record (residuals, see cost_records)
 constexpr int NPS = 8;   // parameter stride per stage
 constexpr int TLD = 12;  // leading dimension of the [A B b] tiles and of the forward-sweep records
+constexpr int PTRI = 56;  // 55 elements of the packed lower triangle of a 10 x 10 symmetric matrix, padded to a multiple of 4
+constexpr int PSAVE = PTRI + 12;  // (P | p) as saved for partial sweeps
 constexpr int RTI_THREADS = 128;
 constexpr int RTI_PPC = RTI_THREADS / GL;  // problems per CTA (upper bound)
 
@@ -98,8 +100,8 @@ struct SmemLayout {
         : oX(0), oU(al4((N + 1) * NX)), oPar(oU + N * NU), oY(oPar + (N + 1) * NPS), oDz(oY + (N + 1) * SYS),
           // QP step [k][lane]; the FW_RING x (14 x TLD) ring of the accepted forward sweep runs from oY over sDz, P+,
           // p+ and the tiles: oY .. oHux must span at least FW_RING * 14 * TLD elements (static_assert below)
-          oP(oY + (((N + 1) * (nominal ? SYS : SYS + 16) > 636) ? (N + 1) * (nominal ? SYS : SYS + 16) : 636)),
-          op(oP + 10 * 12),        // P+ rows, stride 12; then p+
+          oP(oY + (((N + 1) * (nominal ? SYS : SYS + 16) > 700) ? (N + 1) * (nominal ? SYS : SYS + 16) : 700)),
+          op(oP + PTRI),           // P+ as its packed lower triangle (P is symmetric): element (a, b), a >= b, at a (a + 1) / 2 + b; then p+
           oT0(op + 12),            // tile of stage k:   rows r = 0..9 of [A B](:,6..13) | b | pad3, stride TLD
           oT1(oT0 + 10 * TLD),     // tile of stage k-1 (the integrator fills two stages per pass)
           oHux(oT1 + 10 * TLD),    // Hux transposed [i][m]
@@ -118,9 +120,9 @@ struct WsLayout {
           oHrow(oZc + (long long)(N + 1) * 16),  // [k][m][16]: row m of [Hux Guu], [14] = gradient
           oTv(oHrow + (long long)N * 4 * 16),    // [k][a][12]: multiplier row of pinned velocity component a of stage k+1:
                                                  // nu = -(T(a, 0..9) . dx_k + T(a, 10))
-          oPs(oTv + (long long)N * 3 * 12),      // [k][132]: (P_k | p_k) as left in shared memory by backward stage k -- lets an
+          oPs(oTv + (long long)N * 3 * 12),      // [k][PSAVE]: (P_k | p_k) as left in shared memory by backward stage k -- lets an
                                                  // active-set round restart its backward sweep at the highest stage that changed
-          total(oPs + (long long)N * 132) {}
+          total(oPs + (long long)N * PSAVE) {}
 };
 
 template <typename T> struct Vec4;
@@ -152,6 +154,22 @@ template <> __device__ __forceinline__ float trsqrt<float>(float x) {
     return y * (1.5f - 0.5f * x * y * y);
 }
 template <> __device__ __forceinline__ double trsqrt<double>(double x) { return 1.0 / sqrt(x); }
+
+// Packed fp32 pairs (sm_100 FFMA2): (d0, d1) += (a0, a1) * (b0, b1) in ONE issue slot.  The nominal kernel is bound by
+// issue slots (~70 % of them used on every scheduler, FMA pipe under 40 %), so its long dot products run on pairs with
+// two partial sums each; fp64 keeps scalar FMAs.
+template <typename T>
+__device__ __forceinline__ void fma2(T& d0, T& d1, T a0, T a1, T b0, T b1) {
+    d0 += a0 * b0;
+    d1 += a1 * b1;
+}
+template <>
+__device__ __forceinline__ void fma2<float>(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+    asm("{\n\t.reg .b64 ra, rb, rc;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%0, %1};\n\t"
+        "fma.rn.f32x2 rc, ra, rb, rc;\n\tmov.b64 {%0, %1}, rc;\n\t}"
+        : "+f"(d0), "+f"(d1)
+        : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
 
 template <typename T>
 __device__ __forceinline__ T grp_sum(T v, unsigned mask) {
@@ -297,7 +315,7 @@ __device__ __forceinline__ void add_cost(T (&H)[14], const RtiCfg<T>& c, int j, 
 // Terminal stage: P_N = W_e, p_N = gradient (no bounds at the terminal node: acados lbx/ubx
 // apply to intermediate nodes only).
 template <typename T>
-__device__ __forceinline__ void backward_terminal(const RtiCfg<T>& c, int N, int j, unsigned mask, T* sm, const SmemLayout& L) {
+__device__ __forceinline__ void backward_terminal(const RtiCfg<T>& c, int N, int j, unsigned mask, T* sm, const SmemLayout& L, T (&pv)[10]) {
     T H[14];
 #pragma unroll
     for (int i = 0; i < 14; i++) H[i] = T(0);
@@ -305,11 +323,14 @@ __device__ __forceinline__ void backward_terminal(const RtiCfg<T>& c, int N, int
     __syncwarp(mask);
     if (j < 10) {
 #pragma unroll
-        for (int i = 0; i < 10; i++) sm[L.oP + i * 12 + j] = H[i];
+        for (int i = 0; i < 10; i++)
+            if (i >= j) sm[L.oP + i * (i + 1) / 2 + j] = H[i];
     } else if (j == 14) {
 #pragma unroll
         for (int i = 0; i < 10; i++) sm[L.op + i] = H[i];
     }
+#pragma unroll
+    for (int i = 0; i < 10; i++) pv[i] = H[i];
     __syncwarp(mask);
 }
 
@@ -346,7 +367,7 @@ struct ActiveSet {
 template <typename T, int kBar, bool kRows>
 __device__ __forceinline__ bool backward_stage(const RtiCfg<T>& c, int N, int k, int j, unsigned mask, T* sm, const SmemLayout& L, T* ws,
                                                const WsLayout& WL, T* rec, const T* __restrict__ sT, const T* __restrict__ colp,
-                                               const ActiveSet<T>* as) {
+                                               const ActiveSet<T>* as, T (&pv)[10]) {
     const T* sX = sm + L.oX;
     const T* sU = sm + L.oU;
     const T* sPar = sm + L.oPar;
@@ -357,20 +378,33 @@ __device__ __forceinline__ bool backward_stage(const RtiCfg<T>& c, int N, int k,
 #pragma unroll
     for (int r = 0; r < 10; r++) col[r] = colp[r * TLD];
     // W = P+ col (+ p+ on the gradient lane)
+    // p+ lives in the gradient lane's registers between the stages of the nominal sweep (pv: this lane's Pn of the
+    // previous stage, i.e. p+ on lane 14); the constrained sweeps keep it in shared memory, where the partial-sweep
+    // save / restore finds (P | p) contiguous
     T W[10], spv[12];
-    Vec4<T>::ld(sp, spv[0], spv[1], spv[2], spv[3]);
-    Vec4<T>::ld(sp + 4, spv[4], spv[5], spv[6], spv[7]);
-    Vec4<T>::ld(sp + 8, spv[8], spv[9], spv[10], spv[11]);
+    if (kBar != 0) {
+        Vec4<T>::ld(sp, spv[0], spv[1], spv[2], spv[3]);
+        Vec4<T>::ld(sp + 4, spv[4], spv[5], spv[6], spv[7]);
+        Vec4<T>::ld(sp + 8, spv[8], spv[9], spv[10], spv[11]);
+    } else {
 #pragma unroll
-    for (int i = 0; i < 10; i++) {
-        T p0, p1, p2, p3, p4, p5, p6, p7, p8, p9, pa, pb;
-        Vec4<T>::ld(sP + i * 12, p0, p1, p2, p3);
-        Vec4<T>::ld(sP + i * 12 + 4, p4, p5, p6, p7);
-        Vec4<T>::ld(sP + i * 12 + 8, p8, p9, pa, pb);
-        T acc = (j == 14) ? spv[i] : T(0);
-        acc += p0 * col[0]; acc += p1 * col[1]; acc += p2 * col[2]; acc += p3 * col[3]; acc += p4 * col[4];
-        acc += p5 * col[5]; acc += p6 * col[6]; acc += p7 * col[7]; acc += p8 * col[8]; acc += p9 * col[9];
-        W[i] = acc;
+        for (int i = 0; i < 10; i++) spv[i] = pv[i];
+    }
+    // P+ streams in once as its packed lower triangle (14 broadcast 128-bit loads instead of 30 for the full rows --
+    // shared-memory wavefronts are what this kernel runs out of): element (a, b) feeds W[a] and, off the diagonal, W[b]
+    T tri[PTRI];
+#pragma unroll
+    for (int q = 0; q < PTRI / 4; q++) Vec4<T>::ld(sP + 4 * q, tri[4 * q], tri[4 * q + 1], tri[4 * q + 2], tri[4 * q + 3]);
+#pragma unroll
+    for (int i = 0; i < 10; i++) W[i] = (j == 14) ? spv[i] : T(0);
+#pragma unroll
+    for (int a = 0; a < 10; a++) {
+#pragma unroll
+        for (int b = 0; b <= a; b++) {
+            const T pv = tri[a * (a + 1) / 2 + b];
+            W[a] += pv * col[b];
+            if (b != a) W[b] += pv * col[a];
+        }
     }
     // H[:,j] = [A B]' W  (columns 0..5 of [A B] are [I; 0; 0] and [hI; I; 0])
     T H[14];
@@ -385,8 +419,10 @@ __device__ __forceinline__ bool backward_stage(const RtiCfg<T>& c, int N, int k,
         T a0, a1, a2, a3, a4, a5, a6, a7;
         Vec4<T>::ld(sT + r * TLD, a0, a1, a2, a3);
         Vec4<T>::ld(sT + r * TLD + 4, a4, a5, a6, a7);
-        H[6] += a0 * W[r]; H[7] += a1 * W[r]; H[8] += a2 * W[r]; H[9] += a3 * W[r];
-        H[10] += a4 * W[r]; H[11] += a5 * W[r]; H[12] += a6 * W[r]; H[13] += a7 * W[r];
+        fma2<T>(H[6], H[7], a0, a1, W[r], W[r]);
+        fma2<T>(H[8], H[9], a2, a3, W[r], W[r]);
+        fma2<T>(H[10], H[11], a4, a5, W[r], W[r]);
+        fma2<T>(H[12], H[13], a6, a7, W[r], W[r]);
     }
     add_cost<T>(H, c, j, k, false, sX, sm + L.oY, sPar);
     if (kRows) {
@@ -469,6 +505,7 @@ __device__ __forceinline__ bool backward_stage(const RtiCfg<T>& c, int N, int k,
     const T x1 = (y1 - l21 * x2 - l31 * x3) * i11;
     const T x0 = (y0 - l10 * x1 - l20 * x2 - l30 * x3) * i00;
     T K0 = -x0, K1 = -x1, K2 = -x2, K3 = -x3;  // K[:,j] (j < 10) or kappa (j == 14)
+    const T K0u = K0, K1u = K1, K2u = K2, K3u = K3;  // the unconstrained feedback column (K0..K3 may pick up the velocity-pin terms)
     bool ok_v = true;
     bool vpins = false;
     T tv0 = T(0), tv1 = T(0), tv2 = T(0);
@@ -551,7 +588,10 @@ __device__ __forceinline__ bool backward_stage(const RtiCfg<T>& c, int N, int k,
     for (int i = 0; i < 10; i++) {
         T h0, h1, h2, h3;
         Vec4<T>::ld(sHux + i * 4, h0, h1, h2, h3);
-        Pn[i] = H[i] - h0 * x0 - h1 * x1 - h2 * x2 - h3 * x3;  // unconstrained part: H_xx + H_xu K_unc (four dependent FFMAs)
+        T pa = H[i], pb = T(0);  // unconstrained part: H_xx + H_xu K_unc
+        fma2<T>(pa, pb, h0, h1, K0u, K1u);
+        fma2<T>(pa, pb, h2, h3, K2u, K3u);
+        Pn[i] = pa + pb;
     }
     if (kBar == 2 && vpins) {
         const T* sRv = sm + L.oDz;
@@ -559,26 +599,27 @@ __device__ __forceinline__ bool backward_stage(const RtiCfg<T>& c, int N, int k,
         for (int i = 0; i < 10; i++) Pn[i] += sRv[i] * tv0 + sRv[12 + i] * tv1 + sRv[24 + i] * tv2;
     }
     if (j < 10) {
-        // keep P exactly symmetric (lower triangle mirrored): without this the antisymmetric rounding
-        // part is amplified by the recursion (1e-3 relative error at N = 80 in fp32)
+        // only the lower triangle is kept (entry (i, j), i >= j, from lane j): P stays exactly symmetric -- the
+        // antisymmetric rounding part would be amplified by the recursion (1e-3 relative error at N = 80 in fp32)
 #pragma unroll
         for (int i = 0; i < 10; i++) {
-            if (i >= j) sP[i * 12 + j] = Pn[i];
-            if (i > j) sP[j * 12 + i] = Pn[i];
+            if (i >= j) sP[i * (i + 1) / 2 + j] = Pn[i];
         }
-    } else if (j == 14) {
+    } else if (kBar != 0 && j == 14) {
         Vec4<T>::st(sp, Pn[0], Pn[1], Pn[2], Pn[3]);
         Vec4<T>::st(sp + 4, Pn[4], Pn[5], Pn[6], Pn[7]);
         Vec4<T>::st(sp + 8, Pn[8], Pn[9], T(0), T(0));
     }
+#pragma unroll
+    for (int i = 0; i < 10; i++) pv[i] = Pn[i];
     __syncwarp(mask);
     if (kBar == 2) {
-        // keep (P_k | p_k) -- 132 contiguous elements from sP -- for partial sweeps of later rounds
-        T* dst = ws + WL.oPs + (long long)k * 132;
+        // keep (P_k | p_k) -- PSAVE contiguous elements from sP -- for partial sweeps of later rounds
+        T* dst = ws + WL.oPs + (long long)k * PSAVE;
 #pragma unroll
-        for (int q = 0; q < 3; q++) {
+        for (int q = 0; q < 2; q++) {
             const int idx = j + q * GL;
-            if (idx < 33) {
+            if (idx < PSAVE / 4) {
                 T a0, a1, a2, a3;
                 Vec4<T>::ld(sP + idx * 4, a0, a1, a2, a3);
                 Vec4<T>::st(dst + idx * 4, a0, a1, a2, a3);
@@ -614,15 +655,18 @@ __device__ __forceinline__ bool backward_sweep(const RtiCfg<T>& c, int N, int j,
     // k_top (!kLin, kBar == 2): the highest stage whose pins changed since the previous sweep of this problem -- the
     // stages above it are unchanged, so the recursion restarts from the saved (P, p) of stage k_top + 1
     const int k_first = (!kLin && kBar == 2 && k_top < N - 1) ? k_top : N - 1;
+    T pv[10];
+#pragma unroll
+    for (int i = 0; i < 10; i++) pv[i] = T(0);
     if (k_first == N - 1) {
-        backward_terminal<T>(c, N, j, mask, sm, L);
+        backward_terminal<T>(c, N, j, mask, sm, L, pv);
     } else {
-        const T* src = ws + WL.oPs + (long long)(k_first + 1) * 132;
+        const T* src = ws + WL.oPs + (long long)(k_first + 1) * PSAVE;
         T* sP = sm + L.oP;
 #pragma unroll
-        for (int q = 0; q < 3; q++) {
+        for (int q = 0; q < 2; q++) {
             const int idx = j + q * GL;
-            if (idx < 33) {
+            if (idx < PSAVE / 4) {
                 T a0, a1, a2, a3;
                 Vec4<T>::ld(src + idx * 4, a0, a1, a2, a3);
                 Vec4<T>::st(sP + idx * 4, a0, a1, a2, a3);
@@ -662,10 +706,10 @@ __device__ __forceinline__ bool backward_sweep(const RtiCfg<T>& c, int N, int j,
             }
             __syncwarp(mask);
             tile_to_ws<T>(sT0, rec + (long long)k * 14 * TLD, j);
-            ok &= backward_stage<T, kBar, kRows>(c, N, k, j, mask, sm, L, ws, WL, rec, sT0, col0, as);
+            ok &= backward_stage<T, kBar, kRows>(c, N, k, j, mask, sm, L, ws, WL, rec, sT0, col0, as, pv);
             if (k >= 1) {
                 tile_to_ws<T>(sT1, rec + (long long)(k - 1) * 14 * TLD, j);
-                ok &= backward_stage<T, kBar, kRows>(c, N, k - 1, j, mask, sm, L, ws, WL, rec, sT1, col1, as);
+                ok &= backward_stage<T, kBar, kRows>(c, N, k - 1, j, mask, sm, L, ws, WL, rec, sT1, col1, as, pv);
             }
         }
     } else {
@@ -692,7 +736,7 @@ __device__ __forceinline__ bool backward_sweep(const RtiCfg<T>& c, int N, int j,
         int par = 0;
         for (int k = k_first; k >= 0; k--) {
             if (k >= 1) fetch(k - 1);
-            ok &= backward_stage<T, kBar, kRows>(c, N, k, j, mask, sm, L, ws, WL, rec, par ? sT1 : sT0, par ? col1 : col0, as);
+            ok &= backward_stage<T, kBar, kRows>(c, N, k, j, mask, sm, L, ws, WL, rec, par ? sT1 : sT0, par ? col1 : col0, as, pv);
             if (k >= 1) {
                 put(par ? sT0 : sT1);
                 __syncwarp(mask);
@@ -798,14 +842,15 @@ __device__ __forceinline__ void forward_sweep(const RtiCfg<T>& c, int N, int lan
             issue(k + FW_RING, u);
             T dz;
             stage(k, cf, dz);
-            if (lane < 14) {
+            {
+                // branch-free: lanes without a box carry lo / hi = -+1e30 (lane_box), lanes 14 / 15 repeat lane 13's record;
+                // the velocity box starts at stage 1
                 const T v = it_cur + dz;
-                itp[k * its] = v;
+                if (lane < 14) itp[k * its] = v;
                 b_l |= !(fabs(v) <= T(1e30));
-                if (isu || (isv && k >= 1)) {
-                    v_l |= !(v >= lo && v <= hi);
-                    n_l += (v <= lo) + (v >= hi);
-                }
+                const bool chk = !(isv && k == 0);
+                v_l |= chk && !(v >= lo && v <= hi);
+                n_l += (int)(chk && v <= lo) + (int)(chk && v >= hi);
             }
             it_cur = it_nxt;
           }
