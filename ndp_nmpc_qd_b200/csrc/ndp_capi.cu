@@ -333,7 +333,7 @@ static int set_get(ndp_handle* h, int field, int stage, void* dev, int64_t ld, v
 }
 
 #ifdef NDP_RTI_PROF
-namespace ndp { int rti_prof_f32_20_0(unsigned long long* host); }  // diagnostics build (tests/diag/gpu_diag_rti_phases.py)
+namespace ndp { int rti_prof_f32_20_0(unsigned long long* host); int rti_cprof_f32_20_0(unsigned long long* host); }  // diagnostics build (tests/diag/gpu_diag_rti_phases.py)
 #endif
 extern "C" {
 
@@ -358,7 +358,8 @@ void ndp_default_config(ndp_config* c) {
     c->u_max[3] = 9.81 / 0.36;
     c->ipm_max_iter = 50;
     c->polish_max = 24;
-    c->active_set_first = 20;
+    c->active_set_first = 10;  // measured on the stress variant of config 3 (profiles/r2_stress_active_set_rounds.jsonl): the launch is as long as its
+                               // slowest problem, and a problem whose rounds have not settled by then is faster through the interior-point estimate
     c->active_set_warm = 0;
     c->ipm_tol_mu = 0.0;
 }
@@ -755,6 +756,7 @@ int ndp_mlp_destroy(ndp_mlp* m) {
 // debug helper (not part of the public header): phase timestamps of the last profiled tensor-core launch
 #ifdef NDP_RTI_PROF
 int ndp_debug_rti_prof(unsigned long long* host) { return ndp::rti_prof_f32_20_0(host); }
+int ndp_debug_rti_cprof(unsigned long long* host) { return ndp::rti_cprof_f32_20_0(host); }
 #endif
 int ndp_debug_mlp_prof(long long* host128) {
     return (int)cudaMemcpyFromSymbol(host128, ndp::g_mlpt_prof, sizeof(long long) * 128);

@@ -43,6 +43,7 @@ void NDP_CAT(rti_launch_, NDP_INST_TAG)(int grid, int threads, size_t smem, cuda
 
 #ifdef NDP_RTI_PROF
 int NDP_CAT(rti_prof_, NDP_INST_TAG)(unsigned long long* host) { return (int)cudaMemcpyFromSymbol(host, g_rti_prof, sizeof(unsigned long long) * 2048 * 8); }
+int NDP_CAT(rti_cprof_, NDP_INST_TAG)(unsigned long long* host) { return (int)cudaMemcpyFromSymbol(host, g_con_prof, sizeof(unsigned long long) * (2 * 8192 + 2)); }
 #endif
 
 const void* NDP_CAT(rti_kernel_, NDP_INST_TAG)() { return (const void*)rti_step_kernel<NDP_INST_T, NDP_INST_N, NDP_INST_LAT>; }

@@ -1362,6 +1362,7 @@ constexpr int RTI_CTA = 64;  // threads per CTA of both launches (4 problems)
 // diagnostics build: globaltimer stamps of every CTA's first pass (thread 0): entry, record staged, cost records,
 // backward sweep, forward sweep, stores
 static __device__ unsigned long long g_rti_prof[2048 * 8];
+static __device__ unsigned long long g_con_prof[2 * 8192 + 2];  // constrained kernel: [2 p] start / [2 p + 1] end of problem p; [16384] first CTA entry
 #define RTI_GT(i) do { if (threadIdx.x == 0 && blockIdx.x < 2048 && base == (int)blockIdx.x * ppc) { unsigned long long t_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_)); g_rti_prof[blockIdx.x * 8 + (i)] = t_; } } while (0)
 #else
 #define RTI_GT(i) do { } while (0)
@@ -1585,6 +1586,9 @@ __global__ void __launch_bounds__(RTI_CTA, (sizeof(T) == 4) ? 4 : 2) rti_constra
     // launched as a programmatic dependent of the nominal kernel: wait for its queue (a no-op for an ordinary launch)
     asm volatile("griddepcontrol.wait;" ::: "memory");
     const int count = *reinterpret_cast<volatile int*>(a.qctl);
+#ifdef NDP_RTI_PROF
+    if (blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_)); g_con_prof[16384] = t_; }
+#endif
     const int N = (kN > 0) ? kN : c.N;
     const SmemLayout L(N);
     const int lane = threadIdx.x & 15;
@@ -1613,6 +1617,9 @@ __global__ void __launch_bounds__(RTI_CTA, (sizeof(T) == 4) ? 4 : 2) rti_constra
             if (slot >= count) break;
             const int entry = a.queue[slot];
             const int prob = entry & (QUEUE_SWEPT - 1);
+#ifdef NDP_RTI_PROF
+            if (lane == 0 && prob < 8192) { unsigned long long t_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_)); g_con_prof[2 * prob] = t_; }
+#endif
             stage_problem<T>(as_plain, N, L, lane, mask, sm, prob, false);
             cost_records<T>(N, lane, sm + L.oY, sm + L.oX, sm + L.oU, sm + L.oPar);
             __syncwarp(mask);
@@ -1624,6 +1631,9 @@ __global__ void __launch_bounds__(RTI_CTA, (sizeof(T) == 4) ? 4 : 2) rti_constra
                                   a.u0 ? a.u0 + (size_t)prob * NU : nullptr, a.status + prob, a.status2 ? a.status2 + prob : nullptr,
                                   a.stats + (size_t)prob * 4,
                                   a.as_store + (size_t)prob * (AS_OWNERS * 4), a.as_warm != 0, (entry & QUEUE_SWEPT) ? 1 : 0);
+#ifdef NDP_RTI_PROF
+            if (lane == 0 && prob < 8192) { unsigned long long t_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_)); g_con_prof[2 * prob + 1] = t_; }
+#endif
             // the tiles' zero pad columns (the sweeps of this problem may have run the ring over them)
             for (int i = lane; i < 20; i += GL) { T* q = sm + L.oT0 + i * TLD + 9; q[0] = T(0); q[1] = T(0); q[2] = T(0); }
             __syncwarp(mask);
