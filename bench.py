@@ -359,10 +359,22 @@ def run_native(args, rank, local_rank, world):
     traffic = None
     prof = os.path.join(ROOT, "profiles", "ncu_rti_summary_f64.json" if f64 else "ncu_rti_summary.json")
     traffic_src = None
+    co_bounds = None
     if os.path.exists(prof):
         try:
             pj = json.load(open(prof))
             traffic = pj.get("dram_bytes_per_launch")
+            r = pj.get("rti", {})
+            if r.get("smem_wavefronts_per_launch") and r.get("warp_instructions_per_launch"):
+                # what the kernel actually runs out of: shared-memory wavefronts (1 per clock and SM) and issue
+                # slots (1 per clock and scheduler), counted under ncu, over this run's own kernel time
+                clk = peaks["sm_max_mhz"] * 1e6
+                co_bounds = dict(smem_wavefronts_per_launch=r["smem_wavefronts_per_launch"],
+                                 smem_frac_of_peak=r["smem_wavefronts_per_launch"] / (148 * clk * solve_s),
+                                 warp_instructions_per_launch=r["warp_instructions_per_launch"],
+                                 issue_frac_of_peak=r["warp_instructions_per_launch"] / (148 * 4 * clk * solve_s),
+                                 note="the kernel is co-bound by shared-memory wavefronts and issue slots (4096 problems are 3.46 warps per scheduler: "
+                                      "the schedulers holding 4 warps, ~75 % issue-active, set the launch time)")
             traffic_src = f"{os.path.relpath(prof, ROOT)} written by `bench.py --profile` on {pj.get('when', pj.get('source', '?'))}"
         except Exception:
             traffic = None
@@ -383,7 +395,7 @@ def run_native(args, rank, local_rank, world):
         gpu_launches=int(launches),
         roofline=dict(bound="fp64" if f64 else "fp32", kernel="rti_step_kernel<double>" if f64 else "rti_step_kernel<float>", achieved=ach_tf, peak=fp32_peak,
                       unit="TFLOP/s", frac=ach_tf / fp32_peak,
-                      traffic=traffic, traffic_source=traffic_src, flop_per_solve=flop, n_fact_mean=n_fact, kernel_ms=float(solve_ms.mean()),
+                      traffic=traffic, traffic_source=traffic_src, co_bounds=co_bounds, flop_per_solve=flop, n_fact_mean=n_fact, kernel_ms=float(solve_ms.mean()),
                       peak_source=f"148 SM x {lanes} FMA x 2 x {peaks['sm_max_mhz']:.0f} MHz ({peaks['source']} sm_max_mhz)",
                       hbm=dict(achieved=compulsory_bytes_per_solve(N_HORIZON, elt) * B / solve_s / 1e9, peak=peaks["hbm_gbs"], unit="GB/s",
                                frac=compulsory_bytes_per_solve(N_HORIZON, elt) * B / solve_s / 1e9 / peaks["hbm_gbs"],
@@ -626,7 +638,8 @@ def run_profile(args):
     tmp = tempfile.NamedTemporaryFile(suffix=".csv", delete=False).name
     child = [sys.executable, os.path.abspath(__file__), "--steps", "6", "--warmup", "3", "--batch", str(args.batch), "--dtype", args.dtype,
              "--kernels-only"]
-    cmd = ["ncu", "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum", "--clock-control", "none",
+    cmd = ["ncu", "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,l1tex__data_pipe_lsu_wavefronts_mem_shared.sum,"
+           "smsp__inst_executed.sum", "--clock-control", "none",
            "-k", "regex:rti_step_kernel|mlp_tc_kernel", "-c", "80", "--csv", "--log-file", tmp] + child
     rc = subprocess.call(cmd, stdout=subprocess.DEVNULL)
     rows, header = [], None
@@ -655,6 +668,8 @@ def run_profile(args):
         tr = [l.get("dram__bytes_read.sum", 0.0) + l.get("dram__bytes_write.sum", 0.0) for l in ls]
         out[k] = dict(launches=len(ls), dram_bytes_per_launch=float(np.mean(tr)), dram_read=float(np.mean([l.get("dram__bytes_read.sum", 0.0) for l in ls])),
                       dram_write=float(np.mean([l.get("dram__bytes_write.sum", 0.0) for l in ls])),
+                      smem_wavefronts_per_launch=float(np.mean([l.get("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", 0.0) for l in ls])),
+                      warp_instructions_per_launch=float(np.mean([l.get("smsp__inst_executed.sum", 0.0) for l in ls])),
                       kernel_us_under_ncu=float(np.mean([l.get("gpu__time_duration.sum", 0.0) for l in ls])))
     if "rti" in out:
         out["dram_bytes_per_launch"] = out["rti"]["dram_bytes_per_launch"]
