@@ -171,6 +171,20 @@ __device__ __forceinline__ void fma2<float>(float& d0, float& d1, float a0, floa
         : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
 }
 
+// (d0, d1) = (a0, a1) * (b0, b1) + (c0, c1), the accumulator input separate from the result (no copy of c needed)
+template <typename T>
+__device__ __forceinline__ void fma2o(T& d0, T& d1, T a0, T a1, T b0, T b1, T c0, T c1) {
+    d0 = a0 * b0 + c0;
+    d1 = a1 * b1 + c1;
+}
+template <>
+__device__ __forceinline__ void fma2o<float>(float& d0, float& d1, float a0, float a1, float b0, float b1, float c0, float c1) {
+    asm("{\n\t.reg .b64 ra, rb, rc;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+        "fma.rn.f32x2 rc, ra, rb, rc;\n\tmov.b64 {%0, %1}, rc;\n\t}"
+        : "=f"(d0), "=f"(d1)
+        : "f"(a0), "f"(a1), "f"(b0), "f"(b1), "f"(c0), "f"(c1));
+}
+
 template <typename T>
 __device__ __forceinline__ T grp_sum(T v, unsigned mask) {
 #pragma unroll
@@ -201,11 +215,16 @@ __device__ __forceinline__ T grp_min(T v, unsigned mask) {
 // One RK4 step of the state (every lane, redundantly) and of this lane's sensitivity column.
 // x[10], u[4] in shared memory; fm = f / mass.  Column j: initial e_j for j < 10, forcing
 // B_c[:, j-10] for j = 10..13, nothing for j >= 14.
+// The state and its sensitivity column are carried as PAIRS (x_i, s_i): wherever both see the same coefficient -- the
+// stage values x0 + a k, the quaternion rows (linear in (q, s) with the body rates as coefficients) and the weighted sum
+// of the slopes -- one packed FFMA2 does both (the nominal kernel is bound by issue slots: 29 of ~90 instructions per
+// RK stage saved).
 template <typename T>
 __device__ __forceinline__ void rk4_column(const RtiCfg<T>& c, int j, const T* __restrict__ x, const T* __restrict__ u,
                                            T fm0, T fm1, T fm2, T (&xa)[10], T (&sa)[10]) {
     const T h = c.h;
     const T hwx = T(0.5) * u[0], hwy = T(0.5) * u[1], hwz = T(0.5) * u[2], cc = u[3];
+    const T nwx = -hwx, nwy = -hwy, nwz = -hwz;
     const T ew0 = (j == 10) ? T(0.5) : T(0), ew1 = (j == 11) ? T(0.5) : T(0), ew2 = (j == 12) ? T(0.5) : T(0);
     const T ec = (j == 13) ? T(1) : T(0);
     const T c2 = T(2) * cc, c4n = T(-4) * cc, fg2 = fm2 - c.g;
@@ -221,35 +240,46 @@ __device__ __forceinline__ void rk4_column(const RtiCfg<T>& c, int j, const T* _
     }
 #pragma unroll
     for (int st = 0; st < 4; st++) {
-        const T a = (st == 0) ? T(0) : ((st == 3) ? h : h * T(0.5));
-        const T vx = x0[3] + a * kx[3], vy = x0[4] + a * kx[4], vz = x0[5] + a * kx[5];
-        const T qw = x0[6] + a * kx[6], qx = x0[7] + a * kx[7], qy = x0[8] + a * kx[8], qz = x0[9] + a * kx[9];
-        const T s3 = s0[3] + a * ks[3], s4 = s0[4] + a * ks[4], s5 = s0[5] + a * ks[5];
-        const T s6 = s0[6] + a * ks[6], s7 = s0[7] + a * ks[7], s8 = s0[8] + a * ks[8], s9 = s0[9] + a * ks[9];
+        const T a = (st == 3) ? h : h * T(0.5);
+        // stage values of (v, q) and of their sensitivities
+        T zx[10], zs[10];
+#pragma unroll
+        for (int i = 3; i < 10; i++) {
+            if (st == 0) { zx[i] = x0[i]; zs[i] = s0[i]; }
+            else fma2o<T>(zx[i], zs[i], a, a, kx[i], ks[i], x0[i], s0[i]);
+        }
+        const T qw = zx[6], qx = zx[7], qy = zx[8], qz = zx[9];
+        const T s6 = zs[6], s7 = zs[7], s8 = zs[8], s9 = zs[9];
         const T r13 = T(2) * (qx * qz + qw * qy), r23 = T(2) * (qy * qz - qw * qx);
         const T r33 = T(1) - T(2) * qx * qx - T(2) * qy * qy;
-        kx[0] = vx; kx[1] = vy; kx[2] = vz;
+        kx[0] = zx[3]; kx[1] = zx[4]; kx[2] = zx[5];
+        ks[0] = zs[3]; ks[1] = zs[4]; ks[2] = zs[5];
         kx[3] = r13 * cc + fm0;
         kx[4] = r23 * cc + fm1;
         kx[5] = r33 * cc + fg2;
-        kx[6] = -hwx * qx - hwy * qy - hwz * qz;
-        kx[7] = hwx * qw + hwz * qy - hwy * qz;
-        kx[8] = hwy * qw - hwz * qx + hwx * qz;
-        kx[9] = hwz * qw + hwy * qx - hwx * qy;
-        ks[0] = s3; ks[1] = s4; ks[2] = s5;
         ks[3] = c2 * (qy * s6 + qz * s7 + qw * s8 + qx * s9) + ec * r13;
         ks[4] = c2 * (-qx * s6 - qw * s7 + qz * s8 + qy * s9) + ec * r23;
         ks[5] = c4n * (qx * s7 + qy * s8) + ec * r33;
-        ks[6] = (-hwx * s7 - hwy * s8 - hwz * s9) + (-qx * ew0 - qy * ew1 - qz * ew2);
-        ks[7] = (hwx * s6 + hwz * s8 - hwy * s9) + (qw * ew0 - qz * ew1 + qy * ew2);
-        ks[8] = (hwy * s6 - hwz * s7 + hwx * s9) + (qz * ew0 + qw * ew1 - qx * ew2);
-        ks[9] = (hwz * s6 + hwy * s7 - hwx * s8) + (-qy * ew0 + qx * ew1 + qw * ew2);
+        // quaternion rows: (kx, ks) = M(w / 2) (q, s) + (0, M(e / 2) q)
+        const T e6 = -qx * ew0 - qy * ew1 - qz * ew2;
+        const T e7 = qw * ew0 - qz * ew1 + qy * ew2;
+        const T e8 = qz * ew0 + qw * ew1 - qx * ew2;
+        const T e9 = -qy * ew0 + qx * ew1 + qw * ew2;
+        fma2o<T>(kx[6], ks[6], nwx, nwx, qx, s7, T(0), e6);
+        fma2<T>(kx[6], ks[6], nwy, nwy, qy, s8);
+        fma2<T>(kx[6], ks[6], nwz, nwz, qz, s9);
+        fma2o<T>(kx[7], ks[7], hwx, hwx, qw, s6, T(0), e7);
+        fma2<T>(kx[7], ks[7], hwz, hwz, qy, s8);
+        fma2<T>(kx[7], ks[7], nwy, nwy, qz, s9);
+        fma2o<T>(kx[8], ks[8], hwy, hwy, qw, s6, T(0), e8);
+        fma2<T>(kx[8], ks[8], nwz, nwz, qx, s7);
+        fma2<T>(kx[8], ks[8], hwx, hwx, qz, s9);
+        fma2o<T>(kx[9], ks[9], hwz, hwz, qw, s6, T(0), e9);
+        fma2<T>(kx[9], ks[9], hwy, hwy, qx, s7);
+        fma2<T>(kx[9], ks[9], nwx, nwx, qy, s8);
         const T bw = (st == 0 || st == 3) ? h * T(1.0 / 6.0) : h * T(1.0 / 3.0);
 #pragma unroll
-        for (int i = 0; i < 10; i++) {
-            xa[i] += bw * kx[i];
-            sa[i] += bw * ks[i];
-        }
+        for (int i = 0; i < 10; i++) fma2<T>(xa[i], sa[i], bw, bw, kx[i], ks[i]);
     }
 }
 
@@ -1463,8 +1493,11 @@ __device__ __forceinline__ void lane_box(const RtiCfg<T>& c, int lane, T& lo, T&
 // kLat: the latency build (fp32 only) -- same code with half the resident CTAs per SM, i.e. twice the registers,
 // which ptxas spends on instruction-level parallelism.  Chosen when the whole batch is resident at that occupancy
 // (B <= 148 * 4 * 4 problems).
+#ifndef NDP_RTI_CTAS
+#define NDP_RTI_CTAS 8
+#endif
 template <typename T, int kN, bool kLat>
-__global__ void __launch_bounds__(RTI_CTA, (sizeof(T) == 4) ? (kLat ? 4 : 8) : 3) rti_step_kernel(const __grid_constant__ RtiCfg<T> c, const RtiArgs<T> a) {
+__global__ void __launch_bounds__(RTI_CTA, (sizeof(T) == 4) ? (kLat ? 4 : NDP_RTI_CTAS) : 3) rti_step_kernel(const __grid_constant__ RtiCfg<T> c, const RtiArgs<T> a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int N = (kN > 0) ? kN : c.N;
     const SmemLayout L(N, true);
