@@ -150,7 +150,10 @@ template <> struct Vec4<double> {
 // reciprocal square root: MUFU.RSQ + one Newton step (fp32, ~1 ulp) / IEEE (fp64)
 template <typename T> __device__ __forceinline__ T trsqrt(T x);
 template <> __device__ __forceinline__ float trsqrt<float>(float x) {
-    const float y = rsqrtf(x);
+    // the bare MUFU.RSQ: rsqrtf() wraps it in a denormal-range fix-up (two compares / selects / scalings per call) that the
+    // pivots of a Riccati stage (O(1) .. O(1e4), tested for > 0 separately) never need
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y * (1.5f - 0.5f * x * y * y);
 }
 template <> __device__ __forceinline__ double trsqrt<double>(double x) { return 1.0 / sqrt(x); }
