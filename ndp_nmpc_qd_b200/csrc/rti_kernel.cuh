@@ -93,7 +93,7 @@ __host__ __device__ constexpr int al4(int o) { return (o + 3) & ~3; }
 
 // ---- per-problem shared memory layout (elements of T; every region 4-element aligned) ----
 struct SmemLayout {
-    int oX, oU, oPar, oY, oDz, oP, op, oT0, oT1, oHux, total;  // oY and oDz are adjacent: see forward_sweep
+    int oX, oU, oPar, oY, oDz, oP, op, oT0, oT1, oHux, oIpm, total;  // oY and oDz are adjacent: see forward_sweep
     // nominal: the layout of rti_step_kernel, which never forms a QP step array (sDz, (N+1) x 16 elements -- 5 KB of the
     // 19 KB per problem at N = 80): only the constrained kernel's layout carries it
     __host__ __device__ constexpr explicit SmemLayout(int N, bool nominal = false)
@@ -105,8 +105,13 @@ struct SmemLayout {
           oT0(op + 12),            // tile of stage k:   rows r = 0..9 of [A B](:,6..13) | b | pad3, stride TLD
           oT1(oT0 + 10 * TLD),     // tile of stage k-1 (the integrator fills two stages per pass)
           oHux(oT1 + 10 * TLD),    // Hux transposed [i][m]
+          // constrained kernel only: the interior-point vectors TL TU LL LU CL CU, each [k][8] (the seven box-owning lanes),
+          // then the barrier diagonal and gradient of the sweeps, [k <= N][8] each:
+          // their element-wise updates are dependent load - compute - store chains over the stages, ~50 us per
+          // iteration out of the L2-resident workspace, a few us from here
+          oIpm(oHux + 10 * 4),
           // problem stride = 16 (mod 32) words: the two problems of a warp then sit on disjoint bank halves
-          total(((oHux + 10 * 4 + 15) & ~31) + 16) {}
+          total(((oIpm + (nominal ? 0 : 6 * N * 8 + 2 * (N + 1) * 8) + 15) & ~31) + 16) {}
 };
 
 // ---- per-slot global workspace layout (elements of T) ----
@@ -157,6 +162,12 @@ template <> __device__ __forceinline__ float trsqrt<float>(float x) {
     return y * (1.5f - 0.5f * x * y * y);
 }
 template <> __device__ __forceinline__ double trsqrt<double>(double x) { return 1.0 / sqrt(x); }
+
+// Division inside the interior-point vector updates: fp32 takes the two-instruction approximate form (2 ulp; the IEEE
+// sequence is ~10 instructions and these loops are a lone problem's serial tail); the iteration only has to deliver an
+// active-set estimate to the exact rounds.  fp64 divides exactly.
+template <typename T> __device__ __forceinline__ T tdiv(T a, T b) { return a / b; }
+template <> __device__ __forceinline__ float tdiv<float>(float a, float b) { return __fdividef(a, b); }
 
 // Packed fp32 pairs (sm_100 FFMA2): (d0, d1) += (a0, a1) * (b0, b1) in ONE issue slot.  The nominal kernel is bound by
 // issue slots (~70 % of them used on every scheduler, FMA pipe under 40 %), so its long dot products run on pairs with
@@ -482,13 +493,20 @@ __device__ __forceinline__ bool backward_stage(const RtiCfg<T>& c, int N, int k,
             ubeta[m] = __shfl_sync(mask, bnd, 10 + m, GL);
         }
     } else if (kBar == 1) {
+        // barrier diagonal / gradient of the boxed variables (velocities: slots 0..2, inputs: 3..6 of the stage's row)
+        const T* sBD = sm + L.oIpm + 6 * N * 8;
+        const T* sBG = sBD + (N + 1) * 8;
         if (j < 14) {
-            const T d = ws[WL.oBarD + k * 16 + j];
+            const bool boxl = (j >= 3 && j < 6) || j >= 10;
+            const T d = boxl ? sBD[k * 8 + as_owner(j)] : T(0);
 #pragma unroll
             for (int i = 0; i < 14; i++) H[i] += (j == i) ? d : T(0);
         } else if (j == 14) {
-#pragma unroll
-            for (int i = 0; i < 14; i++) H[i] += ws[WL.oBarG + k * 16 + i];
+            T g0, g1, g2, g3, g4, g5, g6, g7;
+            Vec4<T>::ld(sBG + k * 8, g0, g1, g2, g3);
+            Vec4<T>::ld(sBG + k * 8 + 4, g4, g5, g6, g7);
+            H[3] += g0; H[4] += g1; H[5] += g2;
+            H[10] += g3; H[11] += g4; H[12] += g5; H[13] += g6;
         }
     }
     // 4x4 input block G = Huu from lanes 10..13, Cholesky, solve for this lane's column
@@ -529,6 +547,14 @@ __device__ __forceinline__ bool backward_stage(const RtiCfg<T>& c, int N, int k,
     const T e3 = g33 - l30 * l30 - l31 * l31 - l32 * l32;
     const T i33 = trsqrt(e3);
     const bool ok = (g00 > T(0)) && (e1 > T(0)) && (e2 > T(0)) && (e3 > T(0));
+    if (kBar == 1 && j == 15) {
+        // interior-point sweeps keep the factors of G: the corrector of the same iteration changes only the gradient
+        // (same barrier weights), so it re-solves with them instead of factorising again (delta_backward)
+        T* fq = ws + WL.oHrow + (long long)k * 64;
+        Vec4<T>::st(fq, i00, l10, l20, l30);
+        Vec4<T>::st(fq + 4, i11, l21, l31, i22);
+        Vec4<T>::st(fq + 8, l32, i33, T(0), T(0));
+    }
     const T y0 = H[10] * i00;
     const T y1 = (H[11] - l10 * y0) * i11;
     const T y2 = (H[12] - l20 * y0 - l21 * y1) * i22;
@@ -780,6 +806,63 @@ __device__ __forceinline__ bool backward_sweep(const RtiCfg<T>& c, int N, int j,
     return grp_all(mask, ok);
 }
 
+// Gradient-only backward sweep for a CHANGE dG of the stage gradients (dG[k][8]: the boxed variables, as_owner order) under the
+// factorisation left by the last backward_sweep<.., kBar = 1, ..>: the Riccati matrices P_k, the feedback K_k and the
+// factors of G_k do not depend on the gradient, so
+//     dg = [A B]' dp+ + dG_k,   dkappa = -G^-1 dg_u,   dp = dg_x + K' dg_u
+// and the step changes by the forward sweep of (K, dkappa) from dx_0 = 0 with b = 0.  Lane i < 14 carries dg_i, lanes
+// 0..9 dp_i; dkappa replaces kappa in the feedback rows of `rec`.  About a fifth of a factorising sweep: this is the
+// corrector of the Mehrotra iteration (HPIPM re-uses its factorisation in the same way).
+template <typename T>
+__device__ __forceinline__ void delta_backward(const RtiCfg<T>& c, int N, int j, unsigned mask, const T* __restrict__ ws, const WsLayout& WL,
+                                               T* rec, const T* __restrict__ sTriv, const T* __restrict__ dG) {
+    const int jc = (j >= 6 && j < 14) ? j - 6 : 0;
+    const bool tcol = (j >= 6 && j < 14), xl = j < 10, ul = (j >= 10 && j < 14), boxl = (j >= 3 && j < 6) || ul;
+    T triv[10];
+#pragma unroll
+    for (int r = 0; r < 10; r++) triv[r] = (j < 6) ? sTriv[r * TLD + j] : T(0);
+    T col[10], fq[10], kf[4], dg0;
+    auto fetch = [&](int k) {
+        const T* rk = rec + (long long)k * 14 * TLD;
+#pragma unroll
+        for (int r = 0; r < 10; r++) col[r] = tcol ? rk[r * TLD + jc] : triv[r];
+        const T* f = ws + WL.oHrow + (long long)k * 64;
+        Vec4<T>::ld(f, fq[0], fq[1], fq[2], fq[3]);
+        Vec4<T>::ld(f + 4, fq[4], fq[5], fq[6], fq[7]);
+        T d0, d1;
+        Vec4<T>::ld(f + 8, fq[8], fq[9], d0, d1);
+#pragma unroll
+        for (int m = 0; m < 4; m++) kf[m] = xl ? rk[(10 + m) * TLD + j] : T(0);
+        dg0 = boxl ? dG[k * 8 + as_owner(j)] : T(0);
+    };
+    T dp = T(0);
+    fetch(N - 1);
+    for (int k = N - 1; k >= 0; k--) {
+        T g = dg0;
+#pragma unroll
+        for (int r = 0; r < 10; r++) g += col[r] * __shfl_sync(mask, dp, r, GL);
+        const T i00 = fq[0], l10 = fq[1], l20 = fq[2], l30 = fq[3], i11 = fq[4], l21 = fq[5], l31 = fq[6], i22 = fq[7], l32 = fq[8], i33 = fq[9];
+        const T k0 = kf[0], k1 = kf[1], k2 = kf[2], k3 = kf[3];
+        if (k > 0) fetch(k - 1);   // next stage's records travel while this one is solved
+        const T gu0 = __shfl_sync(mask, g, 10, GL), gu1 = __shfl_sync(mask, g, 11, GL);
+        const T gu2 = __shfl_sync(mask, g, 12, GL), gu3 = __shfl_sync(mask, g, 13, GL);
+        const T y0 = gu0 * i00;
+        const T y1 = (gu1 - l10 * y0) * i11;
+        const T y2 = (gu2 - l20 * y0 - l21 * y1) * i22;
+        const T y3 = (gu3 - l30 * y0 - l31 * y1 - l32 * y2) * i33;
+        const T x3 = y3 * i33;
+        const T x2 = (y2 - l32 * x3) * i22;
+        const T x1 = (y1 - l21 * x2 - l31 * x3) * i11;
+        const T x0 = (y0 - l10 * x1 - l20 * x2 - l30 * x3) * i00;
+        if (ul) {
+            const T xm = (j == 10) ? x0 : ((j == 11) ? x1 : ((j == 12) ? x2 : x3));
+            rec[((long long)k * 14 + j) * TLD + 10] = -xm;
+        }
+        dp = xl ? g + k0 * gu0 + k1 * gu1 + k2 * gu2 + k3 * gu3 : T(0);
+    }
+    __syncwarp(mask);
+}
+
 // 4/8/16-byte asynchronous global -> shared copies (LDGSTS): the whole problem record is requested
 // up front and lands while nothing else waits on it
 template <int kBytes>
@@ -810,7 +893,7 @@ static_assert(SmemLayout(1, true).oHux - SmemLayout(1, true).oY >= FW_RING * FW_
 template <typename T, bool kFinal>
 __device__ __forceinline__ void forward_sweep(const RtiCfg<T>& c, int N, int lane, unsigned mask, T dx0, T* sm, const SmemLayout& L,
                                               const T* rec_base, const WsLayout& WL, T lo, T hi, T* gX, T* gU, T* gu0, bool& viol, bool& bad,
-                                              int& nact, bool rezero_pads = true, bool zero_b = false) {
+                                              int& nact, bool rezero_pads = true, bool zero_b = false, bool accum = false) {
     T* sDz = sm + L.oDz;
     const bool isx = lane < 10, isu = (lane >= 10 && lane < 14), isv = (lane >= 3 && lane < 6);
     const T* rec = rec_base + (long long)((lane < 14) ? lane : 13) * TLD;
@@ -921,7 +1004,7 @@ __device__ __forceinline__ void forward_sweep(const RtiCfg<T>& c, int N, int lan
                 if (k < N) {
                     T dz;
                     stage(k, buf[u], dz);
-                    if (lane < 14) sDz[k * 16 + lane] = dz;
+                    if (lane < 14) sDz[k * 16 + lane] = accum ? sDz[k * 16 + lane] + dz : dz;
                     if (k + kPf < N) {
                         const T* r = rec + (long long)(k + kPf) * FW_REC;
                         Vec4<T>::ld(r, buf[u][0], buf[u][1], buf[u][2], buf[u][3]);
@@ -931,11 +1014,25 @@ __device__ __forceinline__ void forward_sweep(const RtiCfg<T>& c, int N, int lan
                 }
             }
         }
-        if (isx) sDz[N * 16 + lane] = z;
+        if (isx) sDz[N * 16 + lane] = accum ? sDz[N * 16 + lane] + z : z;
     }
     __syncwarp(mask);
 }
 
+#ifdef NDP_RTI_PROF
+// diagnostics build: globaltimer stamps of every CTA's first pass (thread 0): entry, record staged, cost records,
+// backward sweep, forward sweep, stores
+static __device__ unsigned long long g_rti_prof[2048 * 8];
+static __device__ unsigned long long g_con_prof[2 * 8192 + 2];  // constrained kernel: [2 p] start / [2 p + 1] end of problem p; [16384] first CTA entry
+#define RTI_GT(i) do { if (threadIdx.x == 0 && blockIdx.x < 2048 && base == (int)blockIdx.x * ppc) { unsigned long long t_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_)); g_rti_prof[blockIdx.x * 8 + (i)] = t_; } } while (0)
+// interior-point phases of the constrained kernel (clock64 sums, lane 0 of the group): g_con_prof[100 + i]
+#define IPM_T0() long long ipm_t0_ = clock64()
+#define IPM_T(i) do { if (lane == 0) { const long long t_ = clock64(); g_con_prof[100 + (i)] += (unsigned long long)(t_ - ipm_t0_); ipm_t0_ = t_; } } while (0)
+#else
+#define IPM_T0() do { } while (0)
+#define IPM_T(i) do { } while (0)
+#define RTI_GT(i) do { } while (0)
+#endif
 enum { IPM_LL = 0, IPM_LU, IPM_TL, IPM_TU, IPM_CL, IPM_CU, IPM_ACT };
 
 constexpr int AS_HIST = 6;  // active-set hashes remembered for the cycle test
@@ -971,11 +1068,12 @@ __device__ __forceinline__ void constrained_qp(const RtiCfg<T>& c, int lane, uns
     int status = 0, n_fact = n_fact0, n_ipm = 0, n_pol = 0;
     bool viol = false, bad = false;
     int nact_l = 0;
-    T* wI = ws + WL.oIpm;
+    T* wI = sm + L.oIpm;  // [field][k][8]: box lane bl = as_owner(lane)
+    const int bl = (isu || isv) ? as_owner(lane) : 7;
     T* wZ = ws + WL.oZc;
-    T* bD = ws + WL.oBarD;
-    T* bG = ws + WL.oBarG;
-    const int FS = N * 16;  // field stride
+    T* bD = sm + L.oIpm + 6 * N * 8;  // [k <= N][8], slot bl
+    T* bG = bD + (N + 1) * 8;
+    const int FS = N * 8;  // field stride of the interior-point vectors
     bool ipm_ok = false, pol_ok = false;
     ActiveSet<T> as;
     as.lo = lo; as.hi = hi;
@@ -1127,9 +1225,9 @@ __device__ __forceinline__ void constrained_qp(const RtiCfg<T>& c, int lane, uns
             as.lo_m = StageMask(); as.hi_m = StageMask();
             for (int k = 0; k < N; k++)
                 if (has_box(k)) {
-                    const int e = k * 16 + lane;
-                    if (wI[IPM_TL * FS + e] < wI[IPM_LL * FS + e]) as.lo_m.set(k);
-                    else if (wI[IPM_TU * FS + e] < wI[IPM_LU * FS + e]) as.hi_m.set(k);
+                    const int e = k * 16 + lane, ei = k * 8 + bl;
+                    if (wI[IPM_TL * FS + ei] < wI[IPM_LL * FS + ei]) as.lo_m.set(k);
+                    else if (wI[IPM_TU * FS + ei] < wI[IPM_LU * FS + ei]) as.hi_m.set(k);
                 }
             __syncwarp(mask);
             return pdas(max_rounds);
@@ -1142,8 +1240,7 @@ __device__ __forceinline__ void constrained_qp(const RtiCfg<T>& c, int lane, uns
             n_fact++;
         }
         for (int k = 0; k <= N; k++) {
-            bD[k * 16 + lane] = T(0);
-            bG[k * 16 + lane] = T(0);
+            if (lane < 8) { bD[k * 8 + lane] = T(0); bG[k * 8 + lane] = T(0); }
             wZ[k * 16 + lane] = (k == 0 && isx) ? dx0 : T(0);
         }
         __syncwarp(mask);
@@ -1153,10 +1250,10 @@ __device__ __forceinline__ void constrained_qp(const RtiCfg<T>& c, int lane, uns
                 const T it_v = iter_at(k);
                 const T lb = lo - it_v, ub = hi - it_v;
                 const T tl = fmax(-lb, c.t_floor), tu = fmax(ub, c.t_floor);
-                wI[IPM_TL * FS + k * 16 + lane] = tl;
-                wI[IPM_TU * FS + k * 16 + lane] = tu;
-                wI[IPM_LL * FS + k * 16 + lane] = c.mu0 / tl;
-                wI[IPM_LU * FS + k * 16 + lane] = c.mu0 / tu;
+                wI[IPM_TL * FS + k * 8 + bl] = tl;
+                wI[IPM_TU * FS + k * 8 + bl] = tu;
+                wI[IPM_LL * FS + k * 8 + bl] = tdiv<T>(c.mu0, tl);
+                wI[IPM_LU * FS + k * 8 + bl] = tdiv<T>(c.mu0, tu);
                 nb_l++;
             }
         const T inv_m = T(1) / (T(2) * grp_sum<T>((T)nb_l, mask));
@@ -1166,23 +1263,28 @@ __device__ __forceinline__ void constrained_qp(const RtiCfg<T>& c, int lane, uns
         // iteration, not the solve: its active-set estimate still goes to the rounds
         bool ipm_broken = false;
         int it = 0;
+        IPM_T0();
         for (it = 0; status == 0 && it <= c.ipm_max_iter; it++) {
             if (it >= 3 && (it % 3) == 0 && res_lin <= T(1e-1) && c.polish_max > 0) {
-                if (rounds_from_ipm(3)) { pol_ok = true; break; }
+                IPM_T(7);
+                const bool r_ok = rounds_from_ipm(3);
+                IPM_T(8);
+                if (r_ok) { pol_ok = true; break; }
             }
             // complementarity, affine barrier terms
+            IPM_T(0);
             T mu_l = T(0);
             for (int k = 0; k < N; k++)
                 if (has_box(k)) {
-                    const int e = k * 16 + lane;
+                    const int e = k * 16 + lane, ei = k * 8 + bl;
                     const T it_v = iter_at(k);
                     const T lb = lo - it_v, ub = hi - it_v;
-                    const T tl = wI[IPM_TL * FS + e], tu = wI[IPM_TU * FS + e];
-                    const T ll = wI[IPM_LL * FS + e], lu = wI[IPM_LU * FS + e];
+                    const T tl = wI[IPM_TL * FS + ei], tu = wI[IPM_TU * FS + ei];
+                    const T ll = wI[IPM_LL * FS + ei], lu = wI[IPM_LU * FS + ei];
                     mu_l += ll * tl + lu * tu;
-                    const T gl = ll / tl, gu = lu / tu;
-                    bD[e] = gl + gu;
-                    bG[e] = (-gu * ub + lu) - (gl * lb + ll);
+                    const T gl = tdiv<T>(ll, tl), gu = tdiv<T>(lu, tu);
+                    bD[ei] = gl + gu;
+                    bG[ei] = (-gu * ub + lu) - (gl * lb + ll);
                 }
             mu = grp_sum<T>(mu_l, mask) * inv_m;
             if (it > 0 && res_lin <= c.tol_res && mu < c.tol_mu) { ipm_ok = true; break; }
@@ -1192,105 +1294,115 @@ __device__ __forceinline__ void constrained_qp(const RtiCfg<T>& c, int lane, uns
             mu_prev = mu;
             __syncwarp(mask);
             // ---- predictor ----
+            IPM_T(1);
             if (!backward_sweep<T, false, 1, false>(c, N, lane, mask, sm, L, ws, WL, rec, sTriv, nullptr)) { ipm_broken = true; break; }
             n_fact++;
+            IPM_T(2);
             forward_sweep<T, false>(c, N, lane, mask, dx0, sm, L, rec, WL, lo, hi, gX, gU, nullptr, viol, bad, nact_l);
+            IPM_T(3);
             T amax = T(1e30);
             for (int k = 0; k < N; k++)
                 if (has_box(k)) {
-                    const int e = k * 16 + lane;
+                    const int e = k * 16 + lane, ei = k * 8 + bl;
                     const T it_v = iter_at(k);
                     const T lb = lo - it_v, ub = hi - it_v;
                     const T zn = sDz[e];
-                    const T tl = wI[IPM_TL * FS + e], tu = wI[IPM_TU * FS + e];
-                    const T ll = wI[IPM_LL * FS + e], lu = wI[IPM_LU * FS + e];
+                    const T tl = wI[IPM_TL * FS + ei], tu = wI[IPM_TU * FS + ei];
+                    const T ll = wI[IPM_LL * FS + ei], lu = wI[IPM_LU * FS + ei];
                     const T dtl = (zn - lb) - tl, dtu = (ub - zn) - tu;
-                    const T dll = -(ll / tl) * dtl - ll, dlu = -(lu / tu) * dtu - lu;
-                    wI[IPM_CL * FS + e] = dll * dtl;
-                    wI[IPM_CU * FS + e] = dlu * dtu;
-                    if (dtl < T(0)) amax = fmin(amax, -tl / dtl);
-                    if (dtu < T(0)) amax = fmin(amax, -tu / dtu);
-                    if (dll < T(0)) amax = fmin(amax, -ll / dll);
-                    if (dlu < T(0)) amax = fmin(amax, -lu / dlu);
+                    const T dll = -tdiv<T>(ll, tl) * dtl - ll, dlu = -tdiv<T>(lu, tu) * dtu - lu;
+                    wI[IPM_CL * FS + ei] = dll * dtl;
+                    wI[IPM_CU * FS + ei] = dlu * dtu;
+                    if (dtl < T(0)) amax = fmin(amax, tdiv<T>(-tl, dtl));
+                    if (dtu < T(0)) amax = fmin(amax, tdiv<T>(-tu, dtu));
+                    if (dll < T(0)) amax = fmin(amax, tdiv<T>(-ll, dll));
+                    if (dlu < T(0)) amax = fmin(amax, tdiv<T>(-lu, dlu));
                 }
             const T a_aff = fmin(grp_min<T>(amax, mask), T(1));
             T mua_l = T(0);
             for (int k = 0; k < N; k++)
                 if (has_box(k)) {
-                    const int e = k * 16 + lane;
+                    const int e = k * 16 + lane, ei = k * 8 + bl;
                     const T it_v = iter_at(k);
                     const T lb = lo - it_v, ub = hi - it_v;
                     const T zn = sDz[e];
-                    const T tl = wI[IPM_TL * FS + e], tu = wI[IPM_TU * FS + e];
-                    const T ll = wI[IPM_LL * FS + e], lu = wI[IPM_LU * FS + e];
+                    const T tl = wI[IPM_TL * FS + ei], tu = wI[IPM_TU * FS + ei];
+                    const T ll = wI[IPM_LL * FS + ei], lu = wI[IPM_LU * FS + ei];
                     const T dtl = (zn - lb) - tl, dtu = (ub - zn) - tu;
-                    const T dll = -(ll / tl) * dtl - ll, dlu = -(lu / tu) * dtu - lu;
+                    const T dll = -tdiv<T>(ll, tl) * dtl - ll, dlu = -tdiv<T>(lu, tu) * dtu - lu;
                     mua_l += (ll + a_aff * dll) * (tl + a_aff * dtl) + (lu + a_aff * dlu) * (tu + a_aff * dtu);
                 }
             const T mu_aff = grp_sum<T>(mua_l, mask) * inv_m;
-            const T sg = mu_aff / mu;
+            const T sg = tdiv<T>(mu_aff, mu);
             const T sigma_mu = sg * sg * sg * mu;
             // ---- corrector ----
             for (int k = 0; k < N; k++)
                 if (has_box(k)) {
-                    const int e = k * 16 + lane;
-                    const T it_v = iter_at(k);
-                    const T lb = lo - it_v, ub = hi - it_v;
-                    const T tl = wI[IPM_TL * FS + e], tu = wI[IPM_TU * FS + e];
-                    const T ll = wI[IPM_LL * FS + e], lu = wI[IPM_LU * FS + e];
-                    const T gl = ll / tl, gu = lu / tu;
-                    const T cl = wI[IPM_CL * FS + e], cu = wI[IPM_CU * FS + e];
-                    bG[e] = ((sigma_mu - cu) / tu - gu * ub + lu) - ((sigma_mu - cl) / tl + gl * lb + ll);
+                    const int e = k * 16 + lane, ei = k * 8 + bl;
+                    const T tl = wI[IPM_TL * FS + ei], tu = wI[IPM_TU * FS + ei];
+                    const T cl = wI[IPM_CL * FS + ei], cu = wI[IPM_CU * FS + ei];
+                    // only the CHANGE of the barrier gradient against the predictor's: the weights bD stay, so the corrector
+                    // re-uses the predictor's factorisation (delta_backward) and adds its step to the affine one
+                    bG[ei] = tdiv<T>(sigma_mu - cu, tu) - tdiv<T>(sigma_mu - cl, tl);
                 }
             __syncwarp(mask);
-            if (!backward_sweep<T, false, 1, false>(c, N, lane, mask, sm, L, ws, WL, rec, sTriv, nullptr)) { ipm_broken = true; break; }
-            n_fact++;
-            forward_sweep<T, false>(c, N, lane, mask, dx0, sm, L, rec, WL, lo, hi, gX, gU, nullptr, viol, bad, nact_l);
+            IPM_T(4);
+            delta_backward<T>(c, N, lane, mask, ws, WL, rec, sTriv, bG);
+            IPM_T(5);
+            forward_sweep<T, false>(c, N, lane, mask, T(0), sm, L, rec, WL, lo, hi, gX, gU, nullptr, viol, bad, nact_l, true, true, true);
+            IPM_T(6);
             amax = T(1e30);
             for (int k = 0; k < N; k++)
                 if (has_box(k)) {
-                    const int e = k * 16 + lane;
+                    const int e = k * 16 + lane, ei = k * 8 + bl;
                     const T it_v = iter_at(k);
                     const T lb = lo - it_v, ub = hi - it_v;
                     const T zn = sDz[e];
-                    const T tl = wI[IPM_TL * FS + e], tu = wI[IPM_TU * FS + e];
-                    const T ll = wI[IPM_LL * FS + e], lu = wI[IPM_LU * FS + e];
-                    const T cl = wI[IPM_CL * FS + e], cu = wI[IPM_CU * FS + e];
+                    const T tl = wI[IPM_TL * FS + ei], tu = wI[IPM_TU * FS + ei];
+                    const T ll = wI[IPM_LL * FS + ei], lu = wI[IPM_LU * FS + ei];
+                    const T cl = wI[IPM_CL * FS + ei], cu = wI[IPM_CU * FS + ei];
                     const T dtl = (zn - lb) - tl, dtu = (ub - zn) - tu;
-                    const T dll = (sigma_mu - cl) / tl - (ll / tl) * dtl - ll;
-                    const T dlu = (sigma_mu - cu) / tu - (lu / tu) * dtu - lu;
-                    if (dtl < T(0)) amax = fmin(amax, -tl / dtl);
-                    if (dtu < T(0)) amax = fmin(amax, -tu / dtu);
-                    if (dll < T(0)) amax = fmin(amax, -ll / dll);
-                    if (dlu < T(0)) amax = fmin(amax, -lu / dlu);
+                    const T dll = tdiv<T>(sigma_mu - cl - ll * dtl, tl) - ll;
+                    const T dlu = tdiv<T>(sigma_mu - cu - lu * dtu, tu) - lu;
+                    if (dtl < T(0)) amax = fmin(amax, tdiv<T>(-tl, dtl));
+                    if (dtu < T(0)) amax = fmin(amax, tdiv<T>(-tu, dtu));
+                    if (dll < T(0)) amax = fmin(amax, tdiv<T>(-ll, dll));
+                    if (dlu < T(0)) amax = fmin(amax, tdiv<T>(-lu, dlu));
                 }
             const T alpha = fmin(T(1), T(0.995) * grp_min<T>(amax, mask));
             for (int k = 0; k < N; k++)
                 if (has_box(k)) {
-                    const int e = k * 16 + lane;
+                    const int e = k * 16 + lane, ei = k * 8 + bl;
                     const T it_v = iter_at(k);
                     const T lb = lo - it_v, ub = hi - it_v;
                     const T zn = sDz[e];
-                    const T tl = wI[IPM_TL * FS + e], tu = wI[IPM_TU * FS + e];
-                    const T ll = wI[IPM_LL * FS + e], lu = wI[IPM_LU * FS + e];
-                    const T cl = wI[IPM_CL * FS + e], cu = wI[IPM_CU * FS + e];
+                    const T tl = wI[IPM_TL * FS + ei], tu = wI[IPM_TU * FS + ei];
+                    const T ll = wI[IPM_LL * FS + ei], lu = wI[IPM_LU * FS + ei];
+                    const T cl = wI[IPM_CL * FS + ei], cu = wI[IPM_CU * FS + ei];
                     const T dtl = (zn - lb) - tl, dtu = (ub - zn) - tu;
-                    const T dll = (sigma_mu - cl) / tl - (ll / tl) * dtl - ll;
-                    const T dlu = (sigma_mu - cu) / tu - (lu / tu) * dtu - lu;
-                    wI[IPM_TL * FS + e] = fmax(tl + alpha * dtl, c.t_min);
-                    wI[IPM_TU * FS + e] = fmax(tu + alpha * dtu, c.t_min);
-                    wI[IPM_LL * FS + e] = fmax(ll + alpha * dll, c.t_min);
-                    wI[IPM_LU * FS + e] = fmax(lu + alpha * dlu, c.t_min);
+                    const T dll = tdiv<T>(sigma_mu - cl - ll * dtl, tl) - ll;
+                    const T dlu = tdiv<T>(sigma_mu - cu - lu * dtu, tu) - lu;
+                    wI[IPM_TL * FS + ei] = fmax(tl + alpha * dtl, c.t_min);
+                    wI[IPM_TU * FS + ei] = fmax(tu + alpha * dtu, c.t_min);
+                    wI[IPM_LL * FS + ei] = fmax(ll + alpha * dll, c.t_min);
+                    wI[IPM_LU * FS + ei] = fmax(lu + alpha * dlu, c.t_min);
                 }
-            if (lane < 14)
-                for (int k = 0; k <= N; k++) {
-                    if (k == N && !isx) break;
-                    const int e = k * 16 + lane;
-                    wZ[e] += alpha * (sDz[e] - wZ[e]);
+            if (lane < 14) {
+                // (the iterate of the interior-point method stays in the workspace: four independent loads per round trip)
+                const int kn = isx ? N + 1 : N;
+                for (int k0 = 0; k0 < kn; k0 += 4) {
+                    T zv[4];
+#pragma unroll
+                    for (int q = 0; q < 4; q++) zv[q] = (k0 + q < kn) ? wZ[(k0 + q) * 16 + lane] : T(0);
+#pragma unroll
+                    for (int q = 0; q < 4; q++)
+                        if (k0 + q < kn) wZ[(k0 + q) * 16 + lane] = zv[q] + alpha * (sDz[(k0 + q) * 16 + lane] - zv[q]);
                 }
+            }
             res_lin *= (T(1) - alpha);
             n_ipm++;
             __syncwarp(mask);
+            IPM_T(7);
         }
         if (!pol_ok && status == 0 && c.polish_max > 0 && n_ipm > 0) pol_ok = rounds_from_ipm(c.polish_max);
         if (ipm_broken && !pol_ok) status = 4;
@@ -1391,15 +1503,6 @@ __device__ __forceinline__ void constrained_qp(const RtiCfg<T>& c, int lane, uns
 }
 
 constexpr int RTI_CTA = 64;  // threads per CTA of both launches (4 problems)
-#ifdef NDP_RTI_PROF
-// diagnostics build: globaltimer stamps of every CTA's first pass (thread 0): entry, record staged, cost records,
-// backward sweep, forward sweep, stores
-static __device__ unsigned long long g_rti_prof[2048 * 8];
-static __device__ unsigned long long g_con_prof[2 * 8192 + 2];  // constrained kernel: [2 p] start / [2 p + 1] end of problem p; [16384] first CTA entry
-#define RTI_GT(i) do { if (threadIdx.x == 0 && blockIdx.x < 2048 && base == (int)blockIdx.x * ppc) { unsigned long long t_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_)); g_rti_prof[blockIdx.x * 8 + (i)] = t_; } } while (0)
-#else
-#define RTI_GT(i) do { } while (0)
-#endif
 constexpr int QUEUE_SWEPT = 1 << 30;  // queue entry flag: the unconstrained sweep of this solve has run (statistics)
 
 // Stage one problem record in shared memory with asynchronous copies (one wait): iterate, then either the stored

@@ -29,3 +29,17 @@ for p in (596, 3722, 1752, 2726):
             ms.append(e0.elapsed_time(e1))
         st = eng.stats().cpu().numpy()[0]
         print("problem %d %s: %.0f us, sweeps %d, ipm iterations %d, rounds %d -> %.1f us per sweep" % (p, kw, np.median(ms) * 1e3, st[0], st[1], st[2], np.median(ms) * 1e3 / st[0]))
+
+# interior-point phase times of the LAST problem's runs (library built with -DNDP_RTI_PROF: clock64 sums since the
+# library was loaded, so the numbers are relative shares)
+import ctypes as C
+from ndp_nmpc_qd_b200 import _lib
+lib = _lib.load()
+if hasattr(lib, "ndp_debug_rti_cprof"):
+    buf = (C.c_ulonglong * (2 * 8192 + 2))()
+    lib.ndp_debug_rti_cprof(buf)
+    v = np.array(buf[100:109], dtype=np.float64)
+    names = ["rounds->loop gap", "barrier terms loop", "predictor backward", "predictor forward", "predictor step loops", "delta backward",
+             "delta forward", "step length + update loops", "rounds from the IPM estimate"]
+    for n, x in zip(names, v):
+        print("%-32s %6.1f %%" % (n, 100 * x / v.sum()))
