@@ -47,7 +47,8 @@ struct alignas(16) MlpSmall {
 // shared memory map (bytes): weights once per CTA, one activation region per 128-thread group
 // (h2 hi/lo alias the front of the h1 region: h1 is dead once the layer-2 MMAs have committed)
 constexpr int MLPT_GROUPS = 2;
-constexpr int MLPT_TMEM_COLS = 256;  // one 128-column fp32 accumulator per group, reused by the three layers
+constexpr int MLPT_TMEM_COLS = 512;  // per group: a 128-column fp32 accumulator (reused by the three layers) + the fp16 activation
+                                     // operand of the next layer, hi | lo, 64 columns each (two K elements per 32-bit column)
 constexpr int MLPT_CTA_THREADS = MLPT_GROUPS * MLPT_THREADS;
 constexpr int MLPT_S_W2H = 0;
 constexpr int MLPT_S_W2L = MLPT_S_W2H + MLPT_W2_ELEMS * 2;
@@ -55,10 +56,8 @@ constexpr int MLPT_S_W3H = MLPT_S_W2L + MLPT_W2_ELEMS * 2;
 constexpr int MLPT_S_W3L = MLPT_S_W3H + MLPT_W3_ELEMS * 2;
 constexpr int MLPT_S_W1H = MLPT_S_W3L + MLPT_W3_ELEMS * 2;   // [W1_hi; W1_lo]: 256 rows x 16
 constexpr int MLPT_S_ACT = MLPT_S_W1H + 2 * MLPT_W1_ELEMS * 2;
-constexpr int MLPT_ACT_BYTES = 2 * MLPT_ROWS * MLP_H1 * 2;       // h1 hi + lo [128 x 128] fp16
-constexpr int MLPT_A1H = 0, MLPT_A1L = MLPT_ROWS * MLP_H1 * 2;   // offsets inside a group's region
-constexpr int MLPT_A2H = 0, MLPT_A2L = MLPT_ROWS * MLP_H2 * 2;
-constexpr int MLPT_A0H = 0, MLPT_A0L = MLPT_ROWS * MLPT_K1 * 2;  // feature tiles [128 x 16] hi / lo (dead once layer 1 has committed)
+constexpr int MLPT_ACT_BYTES = 2 * MLPT_ROWS * MLPT_K1 * 2;      // per group: the feature tiles [128 x 16] fp16, hi + lo
+constexpr int MLPT_A0H = 0, MLPT_A0L = MLPT_ROWS * MLPT_K1 * 2;
 constexpr int MLPT_S_PAR = MLPT_S_ACT + MLPT_GROUPS * MLPT_ACT_BYTES;  // fp32 side parameters (MlpSmall image)
 constexpr int MLPT_S_OUT = MLPT_S_PAR + (int)sizeof(MlpSmall);         // layer-4 partial sums of the upper column half [groups][128][4] fp32
 constexpr int MLPT_S_BAR = MLPT_S_OUT + MLPT_GROUPS * MLPT_ROWS * 16;  // 3 mbarriers (24 B) + tmem base (4 B)
@@ -83,6 +82,59 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
+}
+// same with the A operand in tensor memory (row m of A in lane m, two K elements per 32-bit column): the activations never
+// pass through shared memory, and the tensor core reads only the weights from it
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// 16 columns of this thread's TMEM lane <- 16 registers (32 fp16 values)
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]),
+        "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// packed fp32 pairs (sm_100 add / sub / fma .f32x2): one issue slot for two lanes of arithmetic -- the epilogues of this
+// kernel are bound by issue slots once the activations no longer travel through shared memory
+__device__ __forceinline__ void add2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+    asm("{\n\t.reg .b64 ra, rb;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tadd.rn.f32x2 ra, ra, rb;\n\tmov.b64 {%0, %1}, ra;\n\t}"
+        : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+__device__ __forceinline__ void sub2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+    asm("{\n\t.reg .b64 ra, rb;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tsub.rn.f32x2 ra, ra, rb;\n\tmov.b64 {%0, %1}, ra;\n\t}"
+        : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+__device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+    asm("{\n\t.reg .b64 ra, rb, rc;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%0, %1};\n\t"
+        "fma.rn.f32x2 rc, ra, rb, rc;\n\tmov.b64 {%0, %1}, rc;\n\t}"
+        : "+f"(d0), "+f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+// split 32 fp32 values (after ReLU and an optional bias) into fp16 hi / lo pairs, packed two per register
+__device__ __forceinline__ void split32(const float (&m)[32], int first, const float* bias, uint32_t (&hi)[16], uint32_t (&lo)[16]) {
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        float a = m[2 * i], b = m[2 * i + 1];
+        if (bias) {
+            const float2 bb = *reinterpret_cast<const float2*>(bias + first + 2 * i);
+            add2(a, b, a, b, bb.x, bb.y);
+        }
+        a = fmaxf(a, 0.f); b = fmaxf(b, 0.f);
+        const __half2 h = __floats2half2_rn(a, b);
+        const float2 f = __half22float2(h);
+        float la, lb;
+        sub2(la, lb, a, b, f.x, f.y);
+        const __half2 l = __floats2half2_rn(la, lb);
+        hi[i] = *reinterpret_cast<const uint32_t*>(&h);
+        lo[i] = *reinterpret_cast<const uint32_t*>(&l);
+    }
 }
 // one elected lane of a converged warp (lets ptxas keep the MMA operands on the uniform datapath)
 __device__ __forceinline__ uint32_t elect_one_sync() {
@@ -152,10 +204,6 @@ __global__ void __launch_bounds__(MLPT_CTA_THREADS, 1) mlp_tc_kernel(const MlpSm
     const int grp = threadIdx.x / MLPT_THREADS, tg = threadIdx.x % MLPT_THREADS, t = tg & 127, hf = tg >> 7, warp = tg >> 5;
     float4* sOut = reinterpret_cast<float4*>(smt + MLPT_S_OUT) + grp * MLPT_ROWS;
     unsigned char* act = smt + MLPT_S_ACT + grp * MLPT_ACT_BYTES;
-    __half* sA1h = reinterpret_cast<__half*>(act + MLPT_A1H);
-    __half* sA1l = reinterpret_cast<__half*>(act + MLPT_A1L);
-    __half* sA2h = reinterpret_cast<__half*>(act + MLPT_A2H);
-    __half* sA2l = reinterpret_cast<__half*>(act + MLPT_A2L);
     __half* sA0h = reinterpret_cast<__half*>(act + MLPT_A0H);
     __half* sA0l = reinterpret_cast<__half*>(act + MLPT_A0L);
     const MlpSmall& sq = *reinterpret_cast<const MlpSmall*>(smt + MLPT_S_PAR);
@@ -197,9 +245,9 @@ __global__ void __launch_bounds__(MLPT_CTA_THREADS, 1) mlp_tc_kernel(const MlpSm
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tD = *sTmem + grp * (MLPT_TMEM_COLS / MLPT_GROUPS);  // the accumulator of every layer (each is dead before the next is issued)
+    const uint32_t tAh = tD + 128, tAl = tD + 192;  // the next layer's A operand in tensor memory: fp16 hi | lo, element k in column k / 2
     const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;  // this warp's TMEM lane quarter
     const uint32_t aW2h = smem_u32(smt + MLPT_S_W2H), aW3h = smem_u32(smt + MLPT_S_W3H), aW1h = smem_u32(smt + MLPT_S_W1H);
-    const uint32_t aA1h = smem_u32(sA1h), aA1l = smem_u32(sA1l), aA2h = smem_u32(sA2h), aA2l = smem_u32(sA2l);
     const uint32_t aA0h = smem_u32(sA0h), aA0l = smem_u32(sA0l);
     constexpr uint32_t ID0 = umma_idesc(128, MLP_H1), ID1 = umma_idesc(128, MLP_H2), ID2 = umma_idesc(128, MLP_H3);
     // weight images are [W_hi; W_lo] (2R rows) per k-chunk: the lo rows start R / 8 row groups into each chunk
@@ -282,20 +330,17 @@ __global__ void __launch_bounds__(MLPT_CTA_THREADS, 1) mlp_tc_kernel(const MlpSm
         mbar_wait(bar, phase);
         phase ^= 1;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        // ---- epilogue 0: h1 = relu(D0) -> hi/lo operand tiles ----
+        // ---- epilogue 0: h1 = relu(D0) -> fp16 hi / lo, straight back into tensor memory as layer 2's A operand ----
 #pragma unroll 1
         for (int c0 = hf * 64; live && c0 < hf * 64 + 64; c0 += 32) {
             float m[32];
             tmem_ld32(tD + lane_sel + c0, m);
-#pragma unroll
-            for (int kb = 0; kb < 4; kb++) {
-                float h[8];
-#pragma unroll
-                for (int i = 0; i < 8; i++) h[i] = fmaxf(m[kb * 8 + i], 0.f);
-                const int off = umma_off(t, c0 + kb * 8, MLPT_ROWS);
-                split_store8(h, sA1h + off, sA1l + off);
-            }
+            uint32_t hi[16], lo[16];
+            split32(m, 0, nullptr, hi, lo);
+            tmem_st16(tAh + lane_sel + c0 / 2, hi);
+            tmem_st16(tAl + lane_sel + c0 / 2, lo);
         }
+        tmem_st_wait();
         MLPT_STAMP(stamp++);
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -308,17 +353,15 @@ __global__ void __launch_bounds__(MLPT_CTA_THREADS, 1) mlp_tc_kernel(const MlpSm
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
             for (int ks = 0; ks < MLP_H1 / 16; ks++) {
-                const uint32_t ao = ks * 2 * (MLPT_ROWS / 8) * 128;  // two k-chunks per step
-                const uint32_t bo = ks * 2 * (2 * MLP_H2 / 8) * 128;
-                const uint64_t dAh = umma_desc(aA1h + ao, (MLPT_ROWS / 8) * 128, 128), dAl = umma_desc(aA1l + ao, (MLPT_ROWS / 8) * 128, 128);
+                const uint32_t bo = ks * 2 * (2 * MLP_H2 / 8) * 128;   // two k-chunks of the weight image per step; 8 columns of A
                 const uint64_t dBh = umma_desc(aW2h + bo, (2 * MLP_H2 / 8) * 128, 128), dBl = umma_desc(aW2h + bo + LO2, (2 * MLP_H2 / 8) * 128, 128);
-                umma_f16(tD, dAh, dBl, ID1, ks > 0);   // corrections of every k-step first (see layer 1)
-                umma_f16(tD, dAl, dBh, ID1, 1);
+                umma_f16_ts(tD, tAh + ks * 8, dBl, ID1, ks > 0);   // corrections of every k-step first (see layer 1)
+                umma_f16_ts(tD, tAl + ks * 8, dBh, ID1, 1);
             }
 #pragma unroll
             for (int ks = 0; ks < MLP_H1 / 16; ks++) {
-                const uint32_t ao = ks * 2 * (MLPT_ROWS / 8) * 128, bo = ks * 2 * (2 * MLP_H2 / 8) * 128;
-                umma_f16(tD, umma_desc(aA1h + ao, (MLPT_ROWS / 8) * 128, 128), umma_desc(aW2h + bo, (2 * MLP_H2 / 8) * 128, 128), ID1, 1);
+                const uint32_t bo = ks * 2 * (2 * MLP_H2 / 8) * 128;
+                umma_f16_ts(tD, tAh + ks * 8, umma_desc(aW2h + bo, (2 * MLP_H2 / 8) * 128, 128), ID1, 1);
             }
             umma_commit(bar);
           }
@@ -329,23 +372,17 @@ __global__ void __launch_bounds__(MLPT_CTA_THREADS, 1) mlp_tc_kernel(const MlpSm
         phase ^= 1;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         MLPT_STAMP(stamp++);
-        // ---- epilogue 1: h2 = relu(D1 + b2) -> hi/lo operand tiles (over the dead h1 tiles) ----
+        // ---- epilogue 1: h2 = relu(D1 + b2) -> fp16 hi / lo into tensor memory (over the dead h1 operand) ----
         if (live) {
             const int c0 = hf * 32;
             float m[32];
             tmem_ld32(tD + lane_sel + c0, m);
-#pragma unroll
-            for (int kb = 0; kb < 4; kb++) {
-                float h[8];
-#pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    const int n = c0 + kb * 8 + i;
-                    h[i] = fmaxf(m[kb * 8 + i] + sq.b2[n], 0.f);
-                }
-                const int off = umma_off(t, c0 + kb * 8, MLPT_ROWS);
-                split_store8(h, sA2h + off, sA2l + off);
-            }
+            uint32_t hi[16], lo[16];
+            split32(m, c0, sq.b2, hi, lo);
+            tmem_st16(tAh + lane_sel + c0 / 2, hi);
+            tmem_st16(tAl + lane_sel + c0 / 2, lo);
         }
+        tmem_st_wait();
         MLPT_STAMP(stamp++);
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -357,17 +394,15 @@ __global__ void __launch_bounds__(MLPT_CTA_THREADS, 1) mlp_tc_kernel(const MlpSm
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
             for (int ks = 0; ks < MLP_H2 / 16; ks++) {
-                const uint32_t ao = ks * 2 * (MLPT_ROWS / 8) * 128;
                 const uint32_t bo = ks * 2 * (2 * MLP_H3 / 8) * 128;
-                const uint64_t dAh = umma_desc(aA2h + ao, (MLPT_ROWS / 8) * 128, 128), dAl = umma_desc(aA2l + ao, (MLPT_ROWS / 8) * 128, 128);
                 const uint64_t dBh = umma_desc(aW3h + bo, (2 * MLP_H3 / 8) * 128, 128), dBl = umma_desc(aW3h + bo + LO3, (2 * MLP_H3 / 8) * 128, 128);
-                umma_f16(tD, dAh, dBl, ID2, ks > 0);
-                umma_f16(tD, dAl, dBh, ID2, 1);
+                umma_f16_ts(tD, tAh + ks * 8, dBl, ID2, ks > 0);
+                umma_f16_ts(tD, tAl + ks * 8, dBh, ID2, 1);
             }
 #pragma unroll
             for (int ks = 0; ks < MLP_H2 / 16; ks++) {
-                const uint32_t ao = ks * 2 * (MLPT_ROWS / 8) * 128, bo = ks * 2 * (2 * MLP_H3 / 8) * 128;
-                umma_f16(tD, umma_desc(aA2h + ao, (MLPT_ROWS / 8) * 128, 128), umma_desc(aW3h + bo, (2 * MLP_H3 / 8) * 128, 128), ID2, 1);
+                const uint32_t bo = ks * 2 * (2 * MLP_H3 / 8) * 128;
+                umma_f16_ts(tD, tAh + ks * 8, umma_desc(aW3h + bo, (2 * MLP_H3 / 8) * 128, 128), ID2, 1);
             }
             umma_commit(bar);
           }
@@ -392,14 +427,13 @@ __global__ void __launch_bounds__(MLPT_CTA_THREADS, 1) mlp_tc_kernel(const MlpSm
                 const float4 w0 = *reinterpret_cast<const float4*>(sq.W4 + c0 + 4 * i4);
                 const float4 w1 = *reinterpret_cast<const float4*>(sq.W4 + MLP_H3 + c0 + 4 * i4);
                 const float4 w2 = *reinterpret_cast<const float4*>(sq.W4 + 2 * MLP_H3 + c0 + 4 * i4);
-                const float h0 = fmaxf(m[4 * i4 + 0] + b.x, 0.f);
-                const float h1 = fmaxf(m[4 * i4 + 1] + b.y, 0.f);
-                const float h2 = fmaxf(m[4 * i4 + 2] + b.z, 0.f);
-                const float h3 = fmaxf(m[4 * i4 + 3] + b.w, 0.f);
-                o0 = fmaf(w0.x, h0, o0); o1 = fmaf(w1.x, h0, o1); o2 = fmaf(w2.x, h0, o2);
-                q0 = fmaf(w0.y, h1, q0); q1 = fmaf(w1.y, h1, q1); q2 = fmaf(w2.y, h1, q2);
-                o0 = fmaf(w0.z, h2, o0); o1 = fmaf(w1.z, h2, o1); o2 = fmaf(w2.z, h2, o2);
-                q0 = fmaf(w0.w, h3, q0); q1 = fmaf(w1.w, h3, q1); q2 = fmaf(w2.w, h3, q2);
+                float h0, h1, h2, h3;
+                add2(h0, h1, m[4 * i4 + 0], m[4 * i4 + 1], b.x, b.y);
+                add2(h2, h3, m[4 * i4 + 2], m[4 * i4 + 3], b.z, b.w);
+                h0 = fmaxf(h0, 0.f); h1 = fmaxf(h1, 0.f); h2 = fmaxf(h2, 0.f); h3 = fmaxf(h3, 0.f);
+                // (o, q) = the partial sums over the even / odd columns: one packed FMA per output and column pair
+                ffma2(o0, q0, w0.x, w0.y, h0, h1); ffma2(o1, q1, w1.x, w1.y, h0, h1); ffma2(o2, q2, w2.x, w2.y, h0, h1);
+                ffma2(o0, q0, w0.z, w0.w, h2, h3); ffma2(o1, q1, w1.z, w1.w, h2, h3); ffma2(o2, q2, w2.z, w2.w, h2, h3);
             }
         }
         o0 += q0; o1 += q1; o2 += q2;
