@@ -23,7 +23,7 @@ def _nvcc() -> str:
 RTI_INST = os.path.join(HERE, "csrc", "rti_inst.cu")
 # (tag, element type, horizon template argument (0 = run-time N), latency build)
 RTI_INSTANCES = [("f32_20_0", "float", 20, "false"), ("f32_40_0", "float", 40, "false"), ("f32_80_0", "float", 80, "false"),
-                 ("f32_0_0", "float", 0, "false"), ("f32_20_1", "float", 20, "true"), ("f32_20_2", "float", 20, "sm"),
+                 ("f32_0_0", "float", 0, "false"), ("f32_20_1", "float", 20, "true"),
                  ("f64_20_0", "double", 20, "false"), ("f64_40_0", "double", 40, "false"), ("f64_80_0", "double", 80, "false"),
                  ("f64_0_0", "double", 0, "false")]
 
@@ -56,10 +56,9 @@ def build(force: bool = False, verbose: bool = False, defines=(), out: str = OUT
     rdc = []
     jobs = [(os.path.join(obj_dir, "ndp_capi.o"), [SRC])]
     for tag, typ, n, lat in RTI_INSTANCES:
-        sm_wide = lat == "sm"   # the SM-wide nominal kernel: no constrained kernel of its own either
         jobs.append((os.path.join(obj_dir, f"rti_{tag}.o"),
-                     [RTI_INST, f"-DNDP_INST_T={typ}", f"-DNDP_INST_N={n}", f"-DNDP_INST_LAT={'false' if sm_wide else lat}", f"-DNDP_INST_TAG={tag}",
-                      f"-DNDP_INST_LAT_IS_TRUE={1 if lat in ('true', 'sm') else 0}", f"-DNDP_INST_SM={1 if sm_wide else 0}"] + rdc))
+                     [RTI_INST, f"-DNDP_INST_T={typ}", f"-DNDP_INST_N={n}", f"-DNDP_INST_LAT={lat}", f"-DNDP_INST_TAG={tag}",
+                      f"-DNDP_INST_LAT_IS_TRUE={1 if lat == 'true' else 0}"] + rdc))
 
     def compile_one(job):
         obj, args = job

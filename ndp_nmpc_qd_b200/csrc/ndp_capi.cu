@@ -206,7 +206,7 @@ RtiCfg<T> make_cfg(const ndp_config& g) {
     void rti_claunch_##tag(int, int, size_t, cudaStream_t, const RtiCfg<T>&, const RtiArgs<T>&);               \
     const void* rti_ckernel_##tag();
 NDP_RTI_DECL(f32_20_0, float) NDP_RTI_DECL(f32_40_0, float) NDP_RTI_DECL(f32_80_0, float) NDP_RTI_DECL(f32_0_0, float)
-NDP_RTI_DECL(f32_20_1, float) NDP_RTI_DECL(f32_20_2, float)
+NDP_RTI_DECL(f32_20_1, float)
 NDP_RTI_DECL(f64_20_0, double) NDP_RTI_DECL(f64_40_0, double) NDP_RTI_DECL(f64_80_0, double) NDP_RTI_DECL(f64_0_0, double)
 #undef NDP_RTI_DECL
 
@@ -217,11 +217,10 @@ struct RtiInst {
     void (*claunch)(int, int, size_t, cudaStream_t, const RtiCfg<T>&, const RtiArgs<T>&);  // constrained kernel (shared by the latency build)
     const void* (*ckernel)();
 };
-// lat: 1 the latency build, 2 the SM-wide kernel (fp32, N = 20 only)
-template <typename T> RtiInst<T> rti_inst(int N, int lat);
-template <> RtiInst<float> rti_inst<float>(int N, int lat) {
-    if (lat == 1 && N == 20) return {rti_launch_f32_20_1, rti_kernel_f32_20_1, rti_claunch_f32_20_0, rti_ckernel_f32_20_0};
-    if (lat == 2 && N == 20) return {rti_launch_f32_20_2, rti_kernel_f32_20_2, rti_claunch_f32_20_0, rti_ckernel_f32_20_0};
+// lat: the latency build (fp32, N = 20 only)
+template <typename T> RtiInst<T> rti_inst(int N, bool lat);
+template <> RtiInst<float> rti_inst<float>(int N, bool lat) {
+    if (lat && N == 20) return {rti_launch_f32_20_1, rti_kernel_f32_20_1, rti_claunch_f32_20_0, rti_ckernel_f32_20_0};
     switch (N) {
         case 20: return {rti_launch_f32_20_0, rti_kernel_f32_20_0, rti_claunch_f32_20_0, rti_ckernel_f32_20_0};
         case 40: return {rti_launch_f32_40_0, rti_kernel_f32_40_0, rti_claunch_f32_40_0, rti_ckernel_f32_40_0};
@@ -229,7 +228,7 @@ template <> RtiInst<float> rti_inst<float>(int N, int lat) {
         default: return {rti_launch_f32_0_0, rti_kernel_f32_0_0, rti_claunch_f32_0_0, rti_ckernel_f32_0_0};
     }
 }
-template <> RtiInst<double> rti_inst<double>(int N, int) {
+template <> RtiInst<double> rti_inst<double>(int N, bool) {
     switch (N) {
         case 20: return {rti_launch_f64_20_0, rti_kernel_f64_20_0, rti_claunch_f64_20_0, rti_ckernel_f64_20_0};
         case 40: return {rti_launch_f64_40_0, rti_kernel_f64_40_0, rti_claunch_f64_40_0, rti_ckernel_f64_40_0};
@@ -265,7 +264,7 @@ int launch_solve(ndp_handle* h, const void* x0, void* u0, cudaStream_t st, const
     a.qctl = h->qctl;
     a.B = h->cfg.batch;
     const int thr = h->ppc * GL;
-    const RtiInst<T> inst = rti_inst<T>(h->cfg.N, h->lat);
+    const RtiInst<T> inst = rti_inst<T>(h->cfg.N, h->lat != 0);
     if (h->timing) cudaEventRecord(h->tev[0], st);
     inst.launch(h->grid, thr, h->smem, st, c, a, pdl && xr && f);
     CU(cudaGetLastError());
@@ -288,11 +287,11 @@ int launch_solve(ndp_handle* h, const void* x0, void* u0, cudaStream_t st, const
 
 using namespace ndp;
 
-static const void* rti_kernel_ptr(int elt, int N, int lat) {
-    return elt == 4 ? rti_inst<float>(N, lat).kernel() : rti_inst<double>(N, 0).kernel();
+static const void* rti_kernel_ptr(int elt, int N, bool lat) {
+    return elt == 4 ? rti_inst<float>(N, lat).kernel() : rti_inst<double>(N, false).kernel();
 }
 static const void* rti_ckernel_ptr(int elt, int N) {
-    return elt == 4 ? rti_inst<float>(N, 0).ckernel() : rti_inst<double>(N, 0).ckernel();
+    return elt == 4 ? rti_inst<float>(N, false).ckernel() : rti_inst<double>(N, false).ckernel();
 }
 
 static int field_geom(const ndp_handle* h, int field, void** base, int* n_int, int* sdim, int* dim, int* dim_last, int* n_stages) {
@@ -392,7 +391,7 @@ int ndp_create(const ndp_config* cfg, ndp_handle** out) {
     // (N = 80 fp32: 14 KB per problem -> 3 CTAs of 4, but 7 CTAs of 2)
     {
         int best = -1, best_ppc = 0;
-        const void* k0 = rti_kernel_ptr(h->elt, N, 0);
+        const void* k0 = rti_kernel_ptr(h->elt, N, false);
         for (int ppc = 4; ppc >= 1; ppc >>= 1) {
             const size_t sm = smem_of(L, ppc);
             if (sm > 227 * 1024) continue;
@@ -408,7 +407,7 @@ int ndp_create(const ndp_config* cfg, ndp_handle** out) {
     const int need = (B + h->ppc - 1) / h->ppc;
     // latency build first (fp32): taken when the whole batch is resident at its lower occupancy
     for (int lat = (h->elt == 4 && N == 20) ? 1 : 0; lat >= 0; lat--) {
-        kfn = rti_kernel_ptr(h->elt, N, lat);
+        kfn = rti_kernel_ptr(h->elt, N, lat != 0);
         e = (cudaError_t)raise_dyn_smem(kfn, dev, h->smem);
         if (e != cudaSuccess) { delete h; return cuda_fail(e, "cudaFuncSetAttribute(rti_step_kernel)"); }
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, h->ppc * GL, h->smem);
@@ -419,29 +418,6 @@ int ndp_create(const ndp_config* cfg, ndp_handle** out) {
     const int cap = n_sm * occ;  // persistent: at most one resident wave, grid-stride over problems
     h->grid = need < cap ? need : cap;
     h->slots = h->grid * h->ppc;
-    // SM-wide build (fp32, N = 20): one 14-warp CTA per SM whose 3-warp schedulers take most of the linearisation
-    // (rti_step_kernel_sm).  Taken when the batch does not fit the latency build and fills the SMs to at least 3 warps per
-    // scheduler -- the regime in which the 64-thread CTAs leave the 4 : 3 split of DESIGN.md 4.1; NDP_RTI_SM=0 / 1 overrides.
-    {
-        const char* env = std::getenv("NDP_RTI_SM");
-        const bool want = env ? (env[0] == '1') : (B >= n_sm * 20);
-        if (want && h->lat == 0 && h->elt == 4 && N == 20) {
-            const void* ksm = rti_kernel_ptr(4, 20, 2);
-            const size_t sm_bytes = ((size_t)L.total * SMW_PPC + 10 * TLD) * 4 + sizeof(int) * SMW_PPC * SMW_MAX_PASSES;
-            int osm = 0;
-            if (sm_bytes <= 227 * 1024 && raise_dyn_smem(ksm, dev, sm_bytes) == 0 &&
-                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&osm, ksm, SMW_THREADS, sm_bytes) == cudaSuccess && osm >= 1) {
-                h->lat = 2;
-                h->ppc = SMW_PPC;
-                h->smem = sm_bytes;
-                const int need_sm = (B + SMW_PPC - 1) / SMW_PPC;
-                h->grid = need_sm < n_sm ? need_sm : n_sm;
-                h->slots = (B <= h->grid * SMW_PPC) ? B : h->grid * SMW_PPC;   // one pass: slot = problem index
-            } else {
-                cudaGetLastError();
-            }
-        }
-    }
     h->ws_stride = WL.oBarD;  // the nominal kernel only keeps the stage records of its forward sweep
     {
         const void* cfn = rti_ckernel_ptr(h->elt, N);

@@ -15,14 +15,6 @@
 #ifndef NDP_INST_LAT_IS_TRUE
 #define NDP_INST_LAT_IS_TRUE 0
 #endif
-#ifndef NDP_INST_SM
-#define NDP_INST_SM 0   // 1: the SM-wide nominal kernel (rti_step_kernel_sm) under the same entry points
-#endif
-#if NDP_INST_SM
-#define NDP_NOMINAL_KERNEL rti_step_kernel_sm<NDP_INST_T, NDP_INST_N>
-#else
-#define NDP_NOMINAL_KERNEL rti_step_kernel<NDP_INST_T, NDP_INST_N, NDP_INST_LAT>
-#endif
 #define NDP_CAT2(a, b) a##b
 #define NDP_CAT(a, b) NDP_CAT2(a, b)
 
@@ -33,7 +25,7 @@ namespace ndp {
 void NDP_CAT(rti_launch_, NDP_INST_TAG)(int grid, int threads, size_t smem, cudaStream_t st, const RtiCfg<NDP_INST_T>& c,
                                         const RtiArgs<NDP_INST_T>& a, bool pdl) {
     if (!pdl) {
-        NDP_NOMINAL_KERNEL<<<grid, threads, smem, st>>>(c, a);
+        rti_step_kernel<NDP_INST_T, NDP_INST_N, NDP_INST_LAT><<<grid, threads, smem, st>>>(c, a);
         return;
     }
     cudaLaunchConfig_t cfg = {};
@@ -46,7 +38,7 @@ void NDP_CAT(rti_launch_, NDP_INST_TAG)(int grid, int threads, size_t smem, cuda
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaLaunchKernelEx(&cfg, NDP_NOMINAL_KERNEL, c, a);
+    cudaLaunchKernelEx(&cfg, rti_step_kernel<NDP_INST_T, NDP_INST_N, NDP_INST_LAT>, c, a);
 }
 
 #ifdef NDP_RTI_PROF
@@ -54,7 +46,7 @@ int NDP_CAT(rti_prof_, NDP_INST_TAG)(unsigned long long* host) { return (int)cud
 int NDP_CAT(rti_cprof_, NDP_INST_TAG)(unsigned long long* host) { return (int)cudaMemcpyFromSymbol(host, g_con_prof, sizeof(unsigned long long) * (2 * 8192 + 2)); }
 #endif
 
-const void* NDP_CAT(rti_kernel_, NDP_INST_TAG)() { return (const void*)NDP_NOMINAL_KERNEL; }
+const void* NDP_CAT(rti_kernel_, NDP_INST_TAG)() { return (const void*)rti_step_kernel<NDP_INST_T, NDP_INST_N, NDP_INST_LAT>; }
 
 #if !NDP_INST_LAT_IS_TRUE
 // the constrained kernel of this (precision, horizon): always a programmatic dependent of the nominal launch before it

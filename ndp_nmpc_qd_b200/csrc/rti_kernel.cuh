@@ -870,11 +870,6 @@ __device__ __forceinline__ void cp_async(void* smem_dst, const void* gsrc) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(d), "l"(gsrc), "n"(kBytes) : "memory");
 }
-// 16-byte copy that allocates in L2 only: for records another warp of the CTA has just written (no stale L1 line can answer)
-__device__ __forceinline__ void cp_async_cg16(void* smem_dst, const void* gsrc) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
-}
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
@@ -895,7 +890,7 @@ static_assert(SmemLayout(1, true).oHux - SmemLayout(1, true).oY >= FW_RING * FW_
 // wide stores once the step is accepted -- global memory keeps the old iterate until then, which is what a failed or
 // handed-over problem needs) and the box test / NaN test / active count are fused in (returned through viol / bad / nact).
 // !kFinal (IPM sweeps): records are register-prefetched and the step goes to sDz[k][lane].
-template <typename T, bool kFinal, bool kCg = false>
+template <typename T, bool kFinal>
 __device__ __forceinline__ void forward_sweep(const RtiCfg<T>& c, int N, int lane, unsigned mask, T dx0, T* sm, const SmemLayout& L,
                                               const T* rec_base, const WsLayout& WL, T lo, T hi, T* gX, T* gU, T* gu0, bool& viol, bool& bad,
                                               int& nact, bool rezero_pads = true, bool zero_b = false, bool accum = false) {
@@ -935,10 +930,7 @@ __device__ __forceinline__ void forward_sweep(const RtiCfg<T>& c, int N, int lan
                 T* d = ring + slot * FW_REC;
 #pragma unroll
                 for (int q = 0; q < 3; q++) {
-                    if (kCg) {
-                        if (sizeof(T) == 4) cp_async_cg16(d + 4 * q, r + 4 * q);
-                        else { cp_async_cg16(d + 4 * q, r + 4 * q); cp_async_cg16(d + 4 * q + 2, r + 4 * q + 2); }
-                    } else if (sizeof(T) == 4) cp_async<16>(d + 4 * q, r + 4 * q);
+                    if (sizeof(T) == 4) cp_async<16>(d + 4 * q, r + 4 * q);
                     else { cp_async<16>(d + 4 * q, r + 4 * q); cp_async<16>(d + 4 * q + 2, r + 4 * q + 2); }
                 }
             }
@@ -1722,246 +1714,6 @@ __global__ void __launch_bounds__(RTI_CTA, (sizeof(T) == 4) ? (kLat ? 4 : NDP_RT
         }
         __syncwarp(mask);
         RTI_GT(5);
-    }
-}
-
-// ======================= SM-wide nominal kernel =======================
-// The same step with ONE CTA per SM (14 warps, 28 problems): what changes is who linearises.  With 4096 problems an SM
-// holds 13.8 warps, so two of its four schedulers carry 4 warps and two carry 3, every scheduler issues at the same rate,
-// and the launch lasts as long as the 4-warp schedulers need.  The RK4 / sensitivity work is a quarter of
-// the instructions and independent across stages and problems, so here it is a pool of items (problem, stage pair) that
-// the warps of the 3-warp schedulers take most of -- they write the [A B b] tiles of OTHER groups' problems straight to
-// those problems' workspace records and raise a flag per item; every group then runs the Riccati recursion of its own
-// problem on tiles fetched from the workspace (L2), waiting on the flags.  Arithmetic and results are those of
-// rti_step_kernel, bit for bit.
-constexpr int SMW_WARPS = 14, SMW_PPC = 2 * SMW_WARPS, SMW_THREADS = 32 * SMW_WARPS;
-constexpr int SMW_MAX_PASSES = 64;  // stage pairs per problem the flag table is sized for (N <= 128)
-
-__device__ __forceinline__ void st_release_cta(int* p, int v) {
-    asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory");
-}
-__device__ __forceinline__ int ld_acquire_cta(const int* p) {
-    int v;
-    asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"((unsigned)__cvta_generic_to_shared(p)) : "memory");
-    return v;
-}
-
-// linearise the stage pair (k, k - 1) of the problem staged at `smp` into this group's own tile pair (scratch) and copy
-// the tiles to the problem's workspace records `recp`
-template <typename T>
-__device__ __forceinline__ void linearise_item(const RtiCfg<T>& c, int j, unsigned mask, const SmemLayout& L, T* sm_own, const T* smp, T* recp, int k) {
-    T* sT0 = sm_own + L.oT0;
-    T* sT1 = sm_own + L.oT1;
-    const T* sX = smp + L.oX;
-    const T* sU = smp + L.oU;
-    const T* sPar = smp + L.oPar;
-    const int half = j >> 3, cj = j & 7;
-    const int kk = (k - half >= 0) ? k - half : 0;
-    {
-        T xa[10], sa[10];
-        const T* pr = sPar + kk * NPS;
-        rk4_column<T>(c, 6 + cj, sX + kk * NX, sU + kk * NU, pr[4] * c.inv_mass, pr[5] * c.inv_mass, pr[6] * c.inv_mass, xa, sa);
-        T* t = (half ? sT1 : sT0) + cj;
-#pragma unroll
-        for (int r = 0; r < 10; r++) t[r * TLD] = sa[r];
-        T b0 = xa[0];
-#pragma unroll
-        for (int r = 1; r < 8; r++) b0 = (cj == r) ? xa[r] : b0;
-        const T b1 = (cj == 0) ? xa[8] : xa[9];
-        T* tb = (half ? sT1 : sT0) + 8;
-        const T* xn = sX + (kk + 1) * NX;
-        tb[cj * TLD] = b0 - xn[cj];
-        if (cj < 2) tb[(8 + cj) * TLD] = b1 - xn[8 + cj];
-    }
-    __syncwarp(mask);
-    tile_to_ws<T>(sT0, recp + (long long)k * 14 * TLD, j);
-    if (k >= 1) tile_to_ws<T>(sT1, recp + (long long)(k - 1) * 14 * TLD, j);
-    __syncwarp(mask);
-}
-
-template <typename T, int kN>
-__global__ void __launch_bounds__(SMW_THREADS, 1) rti_step_kernel_sm(const __grid_constant__ RtiCfg<T> c, const RtiArgs<T> a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int N = (kN > 0) ? kN : c.N;
-    const SmemLayout L(N, true);
-    const WsLayout WL(N);
-    const int lane = threadIdx.x & 15;
-    const int grp = threadIdx.x >> 4;
-    const int warp = threadIdx.x >> 5;
-    const unsigned hmask = 0xFFFFu << (threadIdx.x & 16);
-    const unsigned mask = 0xffffffffu;
-    T* sTriv = reinterpret_cast<T*>(smem_raw);
-    T* sm0 = sTriv + 10 * TLD;                    // problem g of the CTA at sm0 + g * L.total
-    T* sm = sm0 + (size_t)grp * L.total;
-    int* flags = reinterpret_cast<int*>(sm0 + (size_t)SMW_PPC * L.total);   // [SMW_PPC][SMW_MAX_PASSES]
-    T* sX = sm + L.oX;
-    T* sU = sm + L.oU;
-    for (int i = threadIdx.x; i < 10 * TLD; i += blockDim.x) {
-        const int r = i / TLD, cc = i - r * TLD;
-        sTriv[i] = (cc < 6 && cc == r) ? T(1) : ((cc >= 3 && cc < 6 && cc - 3 == r) ? c.h : T(0));
-    }
-    for (int i = lane; i < 20 * TLD; i += GL) sm[L.oT0 + i] = T(0);
-    for (int i = threadIdx.x; i < SMW_PPC * SMW_MAX_PASSES; i += blockDim.x) flags[i] = 0;
-    __syncthreads();
-    T lo, hi;
-    lane_box<T>(c, lane, lo, hi);
-    const bool isx = lane < 10, isu = (lane >= 10 && lane < 14), isv = (lane >= 3 && lane < 6);
-    const int n_items = (N + 1) >> 1;   // stage pairs per problem
-    // the warps of the schedulers that hold 3 warps (warp % 4 >= 2) take 5 / 7 of the linearisation items
-#ifndef NDP_SMW_MODE
-#define NDP_SMW_MODE 0
-#endif
-    const bool lifter = (NDP_SMW_MODE == 1) ? ((warp & 3) < 2 && warp < 12) : (warp & 3) >= 2;   // (mode 1: A/B check of the warp -> scheduler map)
-    const int wi = (warp >> 2) * 2 + (warp & 1);      // rank among the warps of its class: 0..5 (lifters), 0..7
-    const int n_cls = lifter ? 6 : 8;
-    const int per_pass = (int)gridDim.x * SMW_PPC;
-    const bool single = a.B <= per_pass;             // one pass: workspace slot = problem index (the constrained kernel finds the tiles there)
-
-    int token = 0;
-    for (int base = 0; base < a.B; base += per_pass) {
-        token++;
-        // this pass's problems, dealt evenly to the CTAs
-        const int cnt = (a.B - base < per_pass) ? a.B - base : per_pass;
-        const int q_c = cnt / (int)gridDim.x, r_c = cnt % (int)gridDim.x, cb = (int)blockIdx.x;
-        const int first = base + cb * q_c + (cb < r_c ? cb : r_c);
-        const int n_c = q_c + (cb < r_c ? 1 : 0);
-        if (n_c == 0) break;   // (uniform over the CTA; later passes are no larger)
-        const bool live = grp < n_c;
-        const int prob = first + (live ? grp : n_c - 1);
-        const bool more = base + per_pass < a.B;
-        auto slot_of = [&](int g) { return single ? (long long)(first + g) : (long long)((int)blockIdx.x * SMW_PPC + g); };
-        T* ws = a.ws + slot_of(live ? grp : n_c - 1) * a.ws_stride;
-        T* gX = a.X + (size_t)prob * (N + 1) * NX;
-        T* gU = a.U + (size_t)prob * N * NU;
-        const T x0v = isx ? a.x0[(size_t)prob * NX + lane] : T(0);
-        stage_problem<T>(a, N, L, lane, mask, sm, prob, a.xr != nullptr, live);
-        unsigned long long* g_as = a.as_store + (size_t)prob * (AS_OWNERS * 4);
-        unsigned long long as_any = 0ull;
-        if (a.as_warm && (isu || isv)) {
-            const ulonglong2 m0 = *reinterpret_cast<const ulonglong2*>(g_as + as_owner(lane) * 4);
-            const ulonglong2 m1 = *reinterpret_cast<const ulonglong2*>(g_as + as_owner(lane) * 4 + 2);
-            as_any = m0.x | m0.y | m1.x | m1.y;
-        }
-        const bool warm = grp_any(mask, as_any != 0ull);
-        cost_records<T>(N, lane, sm + L.oY, sX, sU, sm + L.oPar);
-        __syncthreads();   // every problem of the CTA is staged: any warp may linearise it
-        // ---- linearisation items: row q = stage pair (N - 1 - 2 q, N - 2 - 2 q) of the n_c problems; the first n_l of a
-        //      row go to the lifter warps, the rest to the others, two problems (one per half warp) at a time.  Every warp
-        //      produces its items of row q + 1 between fetching the tiles of row q (L2 latency) and running the two Riccati
-        //      stages of row q on them: the instruction mix of a scheduler stays that of the fused kernel. ----
-        const int n_l = (NDP_SMW_MODE == 2) ? ((n_c * 3 / 7) & ~1) : ((n_c >= 7) ? ((n_c * 5 / 7) & ~1) : 0);   // (mode 2: no skew)
-        const int pl = n_l >> 1, pg = (n_c - n_l + 1) >> 1;      // pairs per row of the two classes
-        const int pn = lifter ? pl : pg, p0 = lifter ? 0 : n_l;
-        auto do_items = [&](int q) {
-            int pr = (wi - (q * pn) % n_cls + n_cls) % n_cls;
-            for (; pr < pn; pr += n_cls) {
-                int p = p0 + 2 * pr + ((threadIdx.x >> 4) & 1);
-                const bool has = p < (lifter ? n_l : n_c);
-                if (!has) p = p0 + 2 * pr;   // the odd half of a class's last pair: repeats its neighbour's item (same values)
-                linearise_item<T>(c, lane, mask, L, sm, sm0 + (size_t)p * L.total, a.ws + slot_of(p) * a.ws_stride, N - 1 - 2 * q);
-                if (lane == 0) st_release_cta(flags + p * SMW_MAX_PASSES + q, token);
-            }
-        };
-        bool ok = true, viol = false, bad = false, stuck = false;
-        int nact_l = 0;
-        const bool sweep = __any_sync(0xffffffffu, !warm);
-        const int* my_flags = flags + (live ? grp : n_c - 1) * SMW_MAX_PASSES;
-        T pv[10];
-#pragma unroll
-        for (int i = 0; i < 10; i++) pv[i] = T(0);
-        T* sT0 = sm + L.oT0;
-        T* sT1 = sm + L.oT1;
-        const int jc = (lane >= 6 && lane < 15) ? lane - 6 : 9;
-        const T* col0 = (lane < 6) ? sTriv + lane : sT0 + jc;
-        const T* col1 = (lane < 6) ? sTriv + lane : sT1 + jc;
-        if (sweep) backward_terminal<T>(c, N, lane, mask, sm, L, pv);
-        do_items(0);
-        for (int q = 0; q < n_items; q++) {
-            const int kA = N - 1 - 2 * q, kB = kA - 1;
-            T pre[4][4];
-            if (sweep) {
-                int spins = 0;
-                for (;;) {
-                    const bool ready = ld_acquire_cta(my_flags + q) == token;
-                    if (__all_sync(0xffffffffu, ready)) break;
-                    if (++spins > (1 << 22)) { stuck = true; break; }   // never in a correct schedule: do not hang the GPU on a bug
-                }
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const int idx = lane + (u & 1) * GL, k = (u < 2) ? kA : kB;
-                    if (idx < 30 && k >= 0) {
-                        const T* src = ws + (long long)k * 14 * TLD + idx * 4;
-                        if (sizeof(T) == 4) {
-                            const float4 v = __ldcg(reinterpret_cast<const float4*>(src));
-                            pre[u][0] = v.x; pre[u][1] = v.y; pre[u][2] = v.z; pre[u][3] = v.w;
-                        } else {
-                            const double2 v = __ldcg(reinterpret_cast<const double2*>(src)), w2 = __ldcg(reinterpret_cast<const double2*>(src) + 1);
-                            pre[u][0] = v.x; pre[u][1] = v.y; pre[u][2] = w2.x; pre[u][3] = w2.y;
-                        }
-                    }
-                }
-            }
-            if (q + 1 < n_items) do_items(q + 1);
-            if (sweep) {
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const int idx = lane + (u & 1) * GL, k = (u < 2) ? kA : kB;
-                    if (idx < 30 && k >= 0) Vec4<T>::st(((u < 2) ? sT0 : sT1) + idx * 4, pre[u][0], pre[u][1], pre[u][2], pre[u][3]);
-                }
-                __syncwarp(mask);
-                ok &= backward_stage<T, 0, false>(c, N, kA, lane, mask, sm, L, ws, WL, ws, sT0, col0, nullptr, pv);
-                if (kB >= 0) ok &= backward_stage<T, 0, false>(c, N, kB, lane, mask, sm, L, ws, WL, ws, sT1, col1, nullptr, pv);
-            }
-        }
-        ok = grp_all(mask, ok);
-        if (sweep) {
-            const T dx0 = isx ? x0v - sX[lane] : T(0);
-            forward_sweep<T, true, true>(c, N, lane, mask, dx0, sm, L, ws, WL, lo, hi, gX, gU, nullptr, viol, bad, nact_l, more);
-        }
-        if (stuck) ok = false;
-        const int nact = (int)grp_sum<float>((float)nact_l, mask);
-        if (!live) {
-            // nothing of its own to store
-        } else if (warm || (ok && viol && !bad)) {
-            if (!warm && (isu || isv)) {
-                StageMask m_lo, m_hi;
-                for (int k = isv ? 1 : 0; k < N; k++) {
-                    const T v = isu ? sU[k * NU + (lane - 10)] : sX[k * NX + lane];
-                    if (v < lo) m_lo.set(k);
-                    else if (v > hi) m_hi.set(k);
-                }
-                unsigned long long* p = g_as + as_owner(lane) * 4;
-                p[0] = m_lo.w0; p[1] = m_lo.w1; p[2] = m_hi.w0; p[3] = m_hi.w1;
-            }
-            __syncwarp(hmask);
-            if (lane == 0) {
-                __threadfence();
-                const int slot = atomicAdd(a.qctl, 1);
-                a.queue[slot] = prob | (warm ? 0 : QUEUE_SWEPT);
-            }
-        } else {
-            int status = 0;
-            if (!ok) status = 4;
-            if (bad) status = 1;
-            if (status == 0) {
-                constexpr int E2 = 8 / (int)sizeof(T);
-                typedef typename std::conditional<sizeof(T) == 4, float2, double>::type V2;
-                for (int i = lane; i < (N + 1) * NX / E2; i += GL) reinterpret_cast<V2*>(gX)[i] = reinterpret_cast<const V2*>(sX)[i];
-                for (int i = lane; i < N * NU / E2; i += GL) reinterpret_cast<V2*>(gU)[i] = reinterpret_cast<const V2*>(sU)[i];
-                if (a.u0 && lane < NU) a.u0[(size_t)prob * NU + lane] = sU[lane];
-            } else if (a.u0 && lane < NU) {
-                a.u0[(size_t)prob * NU + lane] = gU[lane];
-            }
-            if (lane == 0) {
-                a.status[prob] = status;
-                if (a.status2) a.status2[prob] = status;
-                a.stats[prob * 4 + 0] = 1;
-                a.stats[prob * 4 + 1] = 0;
-                a.stats[prob * 4 + 2] = 0;
-                a.stats[prob * 4 + 3] = nact;
-            }
-        }
-        __syncthreads();   // the next pass restages every problem region
     }
 }
 
