@@ -129,7 +129,7 @@ def lattice_swarm(n_all: int, seed: int = 0):
     return off, rng.uniform(0, 20.0, n_all)
 
 
-def time_swarm(n_all: int, modes, steps: int = 50, warmup: int = 100, device=None, N: int = 20) -> dict:
+def time_swarm(n_all: int, modes, steps: int = 50, warmup: int = 100, device=None, N: int = 20, use_graph: bool = True) -> dict:
     """Times the coupled-swarm RTI step (reference generation + exchange + gated all-pairs MLP + local solves) of
     `n_all` quads sharded over the ranks of the initialised process group, for each exchange mode; device time, max over
     ranks.  With more than one mode the forces of the modes are compared bit for bit."""
@@ -155,17 +155,49 @@ def time_swarm(n_all: int, modes, steps: int = 50, warmup: int = 100, device=Non
         x0 = xr[:, 0].contiguous()
         sw.engine.reset(xr, ur)
         u0 = torch.empty((max(e - b, 1), 4), dtype=torch.float32, device=dev)
+        def one_step():
+            t_loc.add_(0.02)
+            rg.horizon(t_loc, None, N, 0.1, off_loc, xr=xr, ur=ur)
+            sw.step(x0, xr, ur, None, u0)
+
         for _ in range(warmup):
             sw.step(x0, xr, ur, None, u0)
         torch.cuda.synchronize(dev)
+        # The step (clock update, reference generation, exchange, pair list + MLP + sum, the two solver kernels) is captured
+        # once into a CUDA graph and replayed, like the closed loop of config 5: ten dependent launches of a few us each
+        # otherwise leave a launch gap apiece.  Only when the pair buffers are sized for the worst case (the pair count then
+        # never leaves the device); every rank takes the same decision.
+        graph, launch_mode = None, "eager"
+        if use_graph and n_all * (n_all - 1) // world <= (2 << 20):
+            ok = torch.ones(1, dtype=torch.int64, device=dev)
+            try:
+                cap = torch.cuda.Stream(device=dev)
+                cap.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(cap):
+                    one_step()
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=cap):
+                        one_step()
+                torch.cuda.current_stream(dev).wait_stream(cap)
+                graph = g
+            except Exception:  # noqa: BLE001
+                ok.zero_()
+            torch.cuda.synchronize(dev)
+            if world > 1:
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok) == 0:
+                graph = None
+            else:
+                launch_mode = "cuda graph replay"
         if world > 1:
             dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
-            t_loc.add_(0.02)
-            rg.horizon(t_loc, None, N, 0.1, off_loc, xr=xr, ur=ur)
-            sw.step(x0, xr, ur, None, u0)
+            if graph is not None:
+                graph.replay()
+            else:
+                one_step()
         e1.record()
         torch.cuda.synchronize(dev)
         ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -176,7 +208,7 @@ def time_swarm(n_all: int, modes, steps: int = 50, warmup: int = 100, device=Non
         stats = sw.engine.stats()[: e - b]
         first = out.get(sw.mode, {}).get("ms_per_step")
         out[sw.mode] = dict(ms_per_step=float(ms) / steps, quad_steps_per_s=n_all * steps / (float(ms) * 1e-3), status_nonzero=int(bad),
-                            riccati_sweeps_max_rank0=int(stats[:, 0].max()) if e > b else 0)
+                            riccati_sweeps_max_rank0=int(stats[:, 0].max()) if e > b else 0, launch_mode=launch_mode)
         if first is not None:
             out[sw.mode]["ms_per_step_first_pass"] = first
         forces[sw.mode] = sw.f[: e - b].clone()
