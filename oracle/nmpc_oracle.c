@@ -26,6 +26,13 @@
 #include <string.h>
 #ifdef _OPENMP
 #include <omp.h>
+
+/* debugging switch read once (getenv scans the environment: not something to do per interior-point iteration of a timed run) */
+static int orc_trace_on(void) {
+    static int on = -1;
+    if (on < 0) on = getenv("ORC_TRACE") ? 1 : 0;
+    return on;
+}
 #endif
 
 #ifndef ORC_REAL
@@ -809,7 +816,7 @@ ipm_again:
         for (int k = 0; k < N; k++)
             for (int m = 0; m < NU; m++) du[k][m] += alpha * (dun[k][m] - du[k][m]);
         res_lin *= (1 - alpha);
-        if (getenv("ORC_TRACE")) fprintf(stderr, "it %d mu %.3e res %.3e alpha %.4f res_lin %.3e sigma_mu %.3e\n", it, (double)mu, (double)res, (double)alpha, (double)res_lin, (double)sigma_mu);
+        if (orc_trace_on()) fprintf(stderr, "it %d mu %.3e res %.3e alpha %.4f res_lin %.3e sigma_mu %.3e\n", it, (double)mu, (double)res, (double)alpha, (double)res_lin, (double)sigma_mu);
     }
 done:;
     int nact = 0;
@@ -840,7 +847,7 @@ done:;
             status = 4;
             goto ipm_again;
         }
-        if (getenv("ORC_TRACE")) fprintf(stderr, "polish: rounds %d status %d nact %d\n", rounds, status, nact);
+        if (orc_trace_on()) fprintf(stderr, "polish: rounds %d status %d nact %d\n", rounds, status, nact);
     }
     /* ---- update: full step ---- */
     int nan = 0;
