@@ -128,6 +128,35 @@ def test_qp_kkt_residuals():
     assert (qp.G @ z - qp.d).max() < 1e-8
 
 
+def test_qp_solution_vs_scipy_slsqp():
+    """Third-party pin of the QP solve: the same linearised QP, condensed onto the null space of the dynamics equalities,
+    handed to scipy's SLSQP (Kraft's active-set SQP; scipy is an independent, published solver present in this image --
+    acados / HPIPM are not).  The QP is strictly convex, so every correct solver, HPIPM included, has ONE answer; SLSQP
+    stops at ~1e-7 of it (its line search runs out of precision first: status 8 on the velocity-box cases).  Covers no
+    active bound, active input bounds and 14-15 active velocity bounds."""
+    so = pytest.importorskip("scipy.optimize")
+    import scipy.linalg as sl
+    vm = np.array(wl.V_BOX)
+    cases = [(wl.independent_problems(2, seed=5), on.OcpParams()), (wl.independent_problems(2, seed=5, scale=15.0), on.OcpParams()),
+             (wl.velocity_box_problems(2, seed=2), on.OcpParams(v_min=-vm, v_max=vm))]
+    n_act = []
+    for w, p in cases:
+        for b in range(2):
+            d = on.rti_step(w["x0"][b], w["xr"][b], w["ur"][b], np.zeros((21, 3)), w["xr"][b].copy(), w["ur"][b].copy(), p, tol=1e-12)
+            qp, z = d["qp"], d["z"]
+            Z = sl.null_space(qp.Aeq)
+            zp = np.linalg.lstsq(qp.Aeq, qp.beq, rcond=None)[0]
+            Hr, gr, Gr, dr = Z.T @ qp.H @ Z, Z.T @ (qp.H @ zp + qp.g), qp.G @ Z, qp.d - qp.G @ zp
+            fin = np.isfinite(dr)  # the default velocity box is +-inf
+            r = so.minimize(lambda y: 0.5 * y @ Hr @ y + gr @ y, np.zeros(Z.shape[1]), jac=lambda y: Hr @ y + gr, method="SLSQP",
+                            constraints=[{"type": "ineq", "fun": lambda y: dr[fin] - Gr[fin] @ y, "jac": lambda y: -Gr[fin]}],
+                            options=dict(ftol=1e-16, maxiter=500))
+            assert r.status in (0, 8), r.message
+            assert np.abs(zp + Z @ r.x - z).max() < 2e-6
+            n_act.append(d["n_active"])
+    assert n_act[0] == 0 and max(n_act[2:4]) >= 1 and min(n_act[4:]) >= 10, n_act
+
+
 def test_rti_is_exact_for_feasible_unconstrained_case(c_oracle):
     """No active bound => the RTI step equals the equality-constrained LQ solution: the IPM path
     and a single Riccati sweep must agree (basis of the CUDA fast path)."""
