@@ -472,8 +472,12 @@ __device__ __forceinline__ bool backward_stage(const RtiCfg<T>& c, int N, int k,
     if (kRows) {
         // rows of the un-penalised [Hux Guu] (by symmetry: column 10+m) and g_u, for the multiplier test
         if (j >= 10 && j < 14) {
-#pragma unroll
-            for (int i = 0; i < 14; i++) ws[WL.oHrow + (k * 4 + (j - 10)) * 16 + i] = H[i];
+            T* hrow = ws + WL.oHrow + (k * 4 + (j - 10)) * 16;
+            Vec4<T>::st(hrow, H[0], H[1], H[2], H[3]);
+            Vec4<T>::st(hrow + 4, H[4], H[5], H[6], H[7]);
+            Vec4<T>::st(hrow + 8, H[8], H[9], H[10], H[11]);
+            hrow[12] = H[12];
+            hrow[13] = H[13];
         } else if (j == 14) {
 #pragma unroll
             for (int m = 0; m < 4; m++) ws[WL.oHrow + (k * 4 + m) * 16 + 14] = H[10 + m];
@@ -876,6 +880,9 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int kPending>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory"); }
 
+ // L1 prefetch of a global line that is read a little later
+__device__ __forceinline__ void pf_l1(const void* g) { asm volatile("prefetch.global.L1 [%0];" ::"l"(__cvta_generic_to_global(g))); }
+
 constexpr int FW_RING = 6;            // stages of forward-sweep records in flight (L2 latency / stage time ~ 4-5)
 constexpr int FW_REC = 14 * TLD;      // one stage: 14 lanes x TLD
 static_assert(SmemLayout(1, true).oHux - SmemLayout(1, true).oY >= FW_RING * FW_REC && SmemLayout(80, true).oHux - SmemLayout(80, true).oY >= FW_RING * FW_REC,
@@ -1028,9 +1035,11 @@ static __device__ unsigned long long g_con_prof[2 * 8192 + 2];  // constrained k
 // interior-point phases of the constrained kernel (clock64 sums, lane 0 of the group): g_con_prof[100 + i]
 #define IPM_T0() long long ipm_t0_ = clock64()
 #define IPM_T(i) do { if (lane == 0) { const long long t_ = clock64(); g_con_prof[100 + (i)] += (unsigned long long)(t_ - ipm_t0_); ipm_t0_ = t_; } } while (0)
+#define IPM_CNT(i, v) do { if (lane == 0) g_con_prof[100 + (i)] += (unsigned long long)(v); } while (0)
 #else
 #define IPM_T0() do { } while (0)
 #define IPM_T(i) do { } while (0)
+#define IPM_CNT(i, v) do { } while (0)
 #define RTI_GT(i) do { } while (0)
 #endif
 enum { IPM_LL = 0, IPM_LU, IPM_TL, IPM_TU, IPM_CL, IPM_CU, IPM_ACT };
@@ -1107,85 +1116,147 @@ __device__ __forceinline__ void constrained_qp(const RtiCfg<T>& c, int lane, uns
                 hist[0] = h;
             }
             bool fact_ok;
+            IPM_T0();
             if (!lin_done) fact_ok = backward_sweep<T, true, 2, true>(c, N, lane, mask, sm, L, ws, WL, rec, sTriv, &as);
             else fact_ok = backward_sweep<T, false, 2, true>(c, N, lane, mask, sm, L, ws, WL, rec, sTriv, &as, false, k_top);
             lin_done = true;
             if (!fact_ok) return false;
             n_fact++;
             n_pol++;
+            IPM_T(10);
+            IPM_CNT(20, 1);
+            IPM_CNT(21, k_top + 1);
             forward_sweep<T, false>(c, N, lane, mask, dx0, sm, L, rec, WL, lo, hi, gX, gU, nullptr, viol, bad, nact_l);
+            IPM_T(11);
             bool changed = false, any_viol = false;
             T worst = T(0);  // most wrong-signed multiplier of this lane's pinned bounds (damped mode releases one)
             int worst_k = -1;
             int top_l = -1;  // highest backward stage whose pins this lane changed (a velocity pin of stage k acts at stage k - 1)
-            for (int k = 0; k < N; k++) {
-                // multipliers of the velocity components of stage k+1 pinned in this sweep
-                const int k1 = k + 1;
-                const bool vp = isv && (k1 < N) && (as.lo_m.test(k1) || as.hi_m.test(k1));
-                T nu = T(0);
-                if (vp) {
-                    const T* tv = ws + WL.oTv + (long long)k * 36 + (lane - 3) * 12;
-                    nu = tv[10];
+            // Multiplier test and set update, spread over ALL 16 lanes.  (It used to run on the seven box-owning lanes, each
+            // walking its N stages with two divergent dot-product paths and a ballot per stage: ~950 cycles per stage,
+            // 10 us of a lone problem's 35 us round.)  The (stage, variable) items are dealt out -- input m = (lane - 10) & 3
+            // at stages (lane >> 2) + 4 t, velocity component a = lane % 3 at stages 1 + lane / 3 + 5 t -- every lane
+            // evaluates its items against a copy of the owner's masks and leaves one action code per item in shared
+            // memory (the interior-point scratch fields are dead while the rounds run); the owners then apply the codes to
+            // their register-held masks.  Same arithmetic per item, same resulting sets.
+            {
+                // (12 N elements over the fields CL | CU, 16 N: scratch of one interior-point iteration, rebuilt by the next)
+                T* sNu = wI + IPM_CL * FS;  // [k][4]: multipliers of the velocity components of stage k + 1 pinned in this sweep
+                T* sAct = sNu + 4 * N;      // [k][8]: per owner slot (as_owner order): 0 keep, 1 pin at lo, 2 pin at hi, 3 release
+                const int um = (lane - 10) & 3, ug = lane >> 2, uo = 10 + um;  // this lane's input items: owner lane uo
+                const int va = lane % 3, vg = lane / 3, vo = 3 + va;           // velocity items (lane 15: none)
+                StageMask u_lo, u_hi, v_lo, v_hi, v_any;
+                u_lo.w0 = __shfl_sync(mask, as.lo_m.w0, uo, GL); u_lo.w1 = __shfl_sync(mask, as.lo_m.w1, uo, GL);
+                u_hi.w0 = __shfl_sync(mask, as.hi_m.w0, uo, GL); u_hi.w1 = __shfl_sync(mask, as.hi_m.w1, uo, GL);
+                v_lo.w0 = __shfl_sync(mask, as.lo_m.w0, vo, GL); v_lo.w1 = __shfl_sync(mask, as.lo_m.w1, vo, GL);
+                v_hi.w0 = __shfl_sync(mask, as.hi_m.w0, vo, GL); v_hi.w1 = __shfl_sync(mask, as.hi_m.w1, vo, GL);
+                {
+                    const unsigned long long p0 = isv ? (as.lo_m.w0 | as.hi_m.w0) : 0ull, p1 = isv ? (as.lo_m.w1 | as.hi_m.w1) : 0ull;
+                    v_any.w0 = __shfl_sync(mask, p0, 3, GL) | __shfl_sync(mask, p0, 4, GL) | __shfl_sync(mask, p0, 5, GL);
+                    v_any.w1 = __shfl_sync(mask, p1, 3, GL) | __shfl_sync(mask, p1, 4, GL) | __shfl_sync(mask, p1, 5, GL);
+                }
+                const T ulo = __shfl_sync(mask, lo, uo, GL), uhi = __shfl_sync(mask, hi, uo, GL);
+                const T vlo = __shfl_sync(mask, lo, vo, GL), vhi = __shfl_sync(mask, hi, vo, GL);
+                const T ueps = __shfl_sync(mask, feas_eps, uo, GL), veps = __shfl_sync(mask, feas_eps, vo, GL);
+                int worst_key = 0x7fffffff;  // (owner lane << 8 | stage) of this lane's most wrong-signed multiplier
+                // rows of the pinned items: requested now, read below (they were written through L2 by the backward sweep)
+                for (int k1 = 1 + vg; k1 < N && lane < 15; k1 += 5)
+                    if (v_lo.test(k1) || v_hi.test(k1))
+                        pf_l1(ws + WL.oTv + (long long)(k1 - 1) * 36 + va * 12);
+                for (int k = ug; k < N; k += 4)
+                    if (u_lo.test(k) || u_hi.test(k)) {
+                        const T* hr = ws + WL.oHrow + (k * 4 + um) * 16;
+                        pf_l1(hr);
+                        if (sizeof(T) == 8) pf_l1(hr + 8);
+                        if (k + 1 < N && v_any.test(k + 1)) pf_l1(rec + ((long long)k * 14 + 3) * TLD + 4);
+                    }
+                // velocity items
+                for (int k1 = 1 + vg; k1 < N && lane < 15; k1 += 5) {
+                    const int k = k1 - 1;
+                    const bool at_lo = v_lo.test(k1), at_hi = v_hi.test(k1);
+                    T act = T(0), nu = T(0);
+                    if (at_lo || at_hi) {
+                        const T* tv = ws + WL.oTv + (long long)k * 36 + va * 12;
+                        nu = tv[10];
 #pragma unroll
-                    for (int i = 0; i < 10; i++) nu += tv[i] * sDz[k * 16 + i];
-                    nu = -nu;
+                        for (int i = 0; i < 10; i++) nu += tv[i] * sDz[k * 16 + i];
+                        nu = -nu;
+                        const T lam = at_hi ? nu : -nu;  // >= 0 at a KKT point
+                        if (lam < T(0)) {
+                            if (!damped) act = T(3);
+                            else if (lam < worst || (lam == worst && ((vo << 8) | k1) < worst_key)) { worst = lam; worst_key = (vo << 8) | k1; }
+                        }
+                    } else {
+                        const T it_v = sX[k1 * NX + 3 + va], zn = sDz[k1 * 16 + 3 + va];
+                        if (zn > vhi - it_v + veps) act = T(2);
+                        else if (zn < vlo - it_v - veps) act = T(1);
+                    }
+                    sNu[k * 4 + va] = nu;
+                    sAct[k1 * 8 + va] = act;
                 }
-                const unsigned vb = (__ballot_sync(mask, vp) >> (((mask & 1u) ? 0 : 16) + 3)) & 7u;
-                T nu0 = T(0), nu1 = T(0), nu2 = T(0);
-                if (vb) {
-                    nu0 = __shfl_sync(mask, nu, 3, GL);
-                    nu1 = __shfl_sync(mask, nu, 4, GL);
-                    nu2 = __shfl_sync(mask, nu, 5, GL);
-                }
-                if (isu) {
-                    const T it_v = sU[k * NU + (lane - 10)];
-                    const bool at_lo = as.lo_m.test(k), at_hi = as.hi_m.test(k);
+                __syncwarp(mask);
+                // input items
+                for (int k = ug; k < N; k += 4) {
+                    const bool at_lo = u_lo.test(k), at_hi = u_hi.test(k);
+                    T act = T(0);
                     if (at_lo || at_hi) {
                         // multiplier of the pinned input from the un-penalised row of [Hux Guu | g_u] (+ the pinned
                         // velocity rows of this stage's mixed constraint)
-                        const T* hr = ws + WL.oHrow + (k * 4 + (lane - 10)) * 16;
+                        const T* hr = ws + WL.oHrow + (k * 4 + um) * 16;
                         T gq = hr[14];
 #pragma unroll
                         for (int i = 0; i < 14; i++) gq += hr[i] * sDz[k * 16 + i];
-                        if (vb) {
-                            const T* eb = rec + ((long long)k * 14 + 3) * TLD + 4 + (lane - 10);  // (E B)(a, m)
-                            gq += eb[0] * nu0 + eb[TLD] * nu1 + eb[2 * TLD] * nu2;
+                        if (k + 1 < N && v_any.test(k + 1)) {
+                            const T* eb = rec + ((long long)k * 14 + 3) * TLD + 4 + um;  // (E B)(a, m)
+                            gq += eb[0] * sNu[k * 4] + eb[TLD] * sNu[k * 4 + 1] + eb[2 * TLD] * sNu[k * 4 + 2];
                         }
                         const T lam = at_hi ? -gq : gq;  // >= 0 at a KKT point
                         if (lam < T(0)) {
-                            if (!damped) { as.lo_m.clear(k); as.hi_m.clear(k); changed = true; top_l = k; }
-                            else if (lam < worst) { worst = lam; worst_k = k; }
+                            if (!damped) act = T(3);
+                            else if (lam < worst || (lam == worst && ((uo << 8) | k) < worst_key)) { worst = lam; worst_key = (uo << 8) | k; }
                         }
                     } else {
-                        const T zn = sDz[k * 16 + lane];
-                        if (zn > hi - it_v + feas_eps) { as.hi_m.set(k); changed = true; any_viol = true; top_l = k; }
-                        else if (zn < lo - it_v - feas_eps) { as.lo_m.set(k); changed = true; any_viol = true; top_l = k; }
+                        const T it_v = sU[k * NU + um], zn = sDz[k * 16 + 10 + um];
+                        if (zn > uhi - it_v + ueps) act = T(2);
+                        else if (zn < ulo - it_v - ueps) act = T(1);
                     }
+                    sAct[k * 8 + 3 + um] = act;
                 }
-                if (isv && k1 < N) {
-                    if (vp) {
-                        const T lam = as.hi_m.test(k1) ? nu : -nu;
-                        if (lam < T(0)) {
-                            if (!damped) { as.lo_m.clear(k1); as.hi_m.clear(k1); changed = true; top_l = k; }
-                            else if (lam < worst) { worst = lam; worst_k = k1; }
+                __syncwarp(mask);
+                // the owners apply the codes of their variable (a velocity pin of stage k acts at backward stage k - 1)
+                if (isu || isv) {
+                    const int slot = as_owner(lane);
+#pragma unroll 4
+                    for (int k = isv ? 1 : 0; k < N; k++) {
+                        const T act = sAct[k * 8 + slot];
+                        if (act != T(0)) {
+                            if (act == T(1)) { as.lo_m.set(k); any_viol = true; }
+                            else if (act == T(2)) { as.hi_m.set(k); any_viol = true; }
+                            else { as.lo_m.clear(k); as.hi_m.clear(k); }
+                            changed = true;
+                            top_l = isv ? k - 1 : k;
                         }
-                    } else {
-                        const T it_v = sX[k1 * NX + lane], zn = sDz[k1 * 16 + lane];
-                        if (zn > hi - it_v + feas_eps) { as.hi_m.set(k1); changed = true; any_viol = true; top_l = k; }
-                        else if (zn < lo - it_v - feas_eps) { as.lo_m.set(k1); changed = true; any_viol = true; top_l = k; }
                     }
                 }
+                if (damped) {
+                    // the problem's single worst multiplier: its owner releases it below, once nothing is violated
+                    const T w_all = grp_min<T>(worst, mask);
+                    int key = (worst == w_all && w_all < T(0)) ? worst_key : 0x7fffffff;
+#pragma unroll
+                    for (int o = 8; o >= 1; o >>= 1) {
+                        const int other = __shfl_xor_sync(mask, key, o, GL);
+                        key = other < key ? other : key;
+                    }
+                    worst = w_all;
+                    worst_k = (key != 0x7fffffff && (key >> 8) == lane) ? (key & 255) : -1;
+                }
+                __syncwarp(mask);
             }
             any_viol = __any_sync(mask, any_viol);
-            if (damped && !any_viol) {
-                // release the single worst multiplier of the problem
-                const T w_all = grp_min<T>(worst, mask);
-                const bool cand = (worst_k >= 0) && (worst == w_all) && (w_all < T(0));
-                const unsigned cb = (__ballot_sync(mask, cand) >> ((mask & 1u) ? 0 : 16)) & 0xFFFFu;
-                if (cand && (cb & ((1u << lane) - 1u)) == 0u) {
-                    as.lo_m.clear(worst_k); as.hi_m.clear(worst_k); changed = true;
-                    top_l = isv ? worst_k - 1 : worst_k;
-                }
+            if (damped && !any_viol && worst_k >= 0) {
+                // release the single worst multiplier of the problem (this lane owns it)
+                as.lo_m.clear(worst_k); as.hi_m.clear(worst_k); changed = true;
+                top_l = isv ? worst_k - 1 : worst_k;
             }
             changed = __any_sync(mask, changed);
 #pragma unroll
@@ -1195,6 +1266,7 @@ __device__ __forceinline__ void constrained_qp(const RtiCfg<T>& c, int lane, uns
             }
             k_top = top_l;
             __syncwarp(mask);
+            IPM_T(12);
             if (!changed) {
                 // pinned variables sit exactly on their bound
                 if (isu || isv)
@@ -1263,6 +1335,15 @@ __device__ __forceinline__ void constrained_qp(const RtiCfg<T>& c, int lane, uns
         // iteration, not the solve: its active-set estimate still goes to the rounds
         bool ipm_broken = false;
         int it = 0;
+        // element-wise passes over this lane's boxed variables: stages 0 (inputs) / 1 (velocities) .. N - 1.  Branch-free
+        // bodies, unrolled, so that the loads and reciprocals of four stages overlap (these serial loops were ~30 % of a
+        // lone problem's interior-point iteration)
+        auto box_loop = [&](auto&& body) {
+            if (isu || isv) {
+#pragma unroll 4
+                for (int k = isv ? 1 : 0; k < N; k++) body(k);
+            }
+        };
         IPM_T0();
         for (it = 0; status == 0 && it <= c.ipm_max_iter; it++) {
             if (it >= 3 && (it % 3) == 0 && res_lin <= T(1e-1) && c.polish_max > 0) {
@@ -1274,18 +1355,17 @@ __device__ __forceinline__ void constrained_qp(const RtiCfg<T>& c, int lane, uns
             // complementarity, affine barrier terms
             IPM_T(0);
             T mu_l = T(0);
-            for (int k = 0; k < N; k++)
-                if (has_box(k)) {
-                    const int e = k * 16 + lane, ei = k * 8 + bl;
-                    const T it_v = iter_at(k);
-                    const T lb = lo - it_v, ub = hi - it_v;
-                    const T tl = wI[IPM_TL * FS + ei], tu = wI[IPM_TU * FS + ei];
-                    const T ll = wI[IPM_LL * FS + ei], lu = wI[IPM_LU * FS + ei];
-                    mu_l += ll * tl + lu * tu;
-                    const T gl = tdiv<T>(ll, tl), gu = tdiv<T>(lu, tu);
-                    bD[ei] = gl + gu;
-                    bG[ei] = (-gu * ub + lu) - (gl * lb + ll);
-                }
+            box_loop([&](int k) {
+                const int e = k * 16 + lane, ei = k * 8 + bl;
+                const T it_v = iter_at(k);
+                const T lb = lo - it_v, ub = hi - it_v;
+                const T tl = wI[IPM_TL * FS + ei], tu = wI[IPM_TU * FS + ei];
+                const T ll = wI[IPM_LL * FS + ei], lu = wI[IPM_LU * FS + ei];
+                mu_l += ll * tl + lu * tu;
+                const T gl = tdiv<T>(ll, tl), gu = tdiv<T>(lu, tu);
+                bD[ei] = gl + gu;
+                bG[ei] = (-gu * ub + lu) - (gl * lb + ll);
+            });
             mu = grp_sum<T>(mu_l, mask) * inv_m;
             if (it > 0 && res_lin <= c.tol_res && mu < c.tol_mu) { ipm_ok = true; break; }
             if (it > 3 && res_lin <= c.tol_res && mu > T(0.9) * mu_prev && mu < T(1e-2)) { ipm_ok = true; break; }
@@ -1301,50 +1381,47 @@ __device__ __forceinline__ void constrained_qp(const RtiCfg<T>& c, int lane, uns
             forward_sweep<T, false>(c, N, lane, mask, dx0, sm, L, rec, WL, lo, hi, gX, gU, nullptr, viol, bad, nact_l);
             IPM_T(3);
             T amax = T(1e30);
-            for (int k = 0; k < N; k++)
-                if (has_box(k)) {
-                    const int e = k * 16 + lane, ei = k * 8 + bl;
-                    const T it_v = iter_at(k);
-                    const T lb = lo - it_v, ub = hi - it_v;
-                    const T zn = sDz[e];
-                    const T tl = wI[IPM_TL * FS + ei], tu = wI[IPM_TU * FS + ei];
-                    const T ll = wI[IPM_LL * FS + ei], lu = wI[IPM_LU * FS + ei];
-                    const T dtl = (zn - lb) - tl, dtu = (ub - zn) - tu;
-                    const T dll = -tdiv<T>(ll, tl) * dtl - ll, dlu = -tdiv<T>(lu, tu) * dtu - lu;
-                    wI[IPM_CL * FS + ei] = dll * dtl;
-                    wI[IPM_CU * FS + ei] = dlu * dtu;
-                    if (dtl < T(0)) amax = fmin(amax, tdiv<T>(-tl, dtl));
-                    if (dtu < T(0)) amax = fmin(amax, tdiv<T>(-tu, dtu));
-                    if (dll < T(0)) amax = fmin(amax, tdiv<T>(-ll, dll));
-                    if (dlu < T(0)) amax = fmin(amax, tdiv<T>(-lu, dlu));
-                }
+            box_loop([&](int k) {
+                const int e = k * 16 + lane, ei = k * 8 + bl;
+                const T it_v = iter_at(k);
+                const T lb = lo - it_v, ub = hi - it_v;
+                const T zn = sDz[e];
+                const T tl = wI[IPM_TL * FS + ei], tu = wI[IPM_TU * FS + ei];
+                const T ll = wI[IPM_LL * FS + ei], lu = wI[IPM_LU * FS + ei];
+                const T dtl = (zn - lb) - tl, dtu = (ub - zn) - tu;
+                const T dll = -tdiv<T>(ll, tl) * dtl - ll, dlu = -tdiv<T>(lu, tu) * dtu - lu;
+                wI[IPM_CL * FS + ei] = dll * dtl;
+                wI[IPM_CU * FS + ei] = dlu * dtu;
+                if (dtl < T(0)) amax = fmin(amax, tdiv<T>(-tl, dtl));
+                if (dtu < T(0)) amax = fmin(amax, tdiv<T>(-tu, dtu));
+                if (dll < T(0)) amax = fmin(amax, tdiv<T>(-ll, dll));
+                if (dlu < T(0)) amax = fmin(amax, tdiv<T>(-lu, dlu));
+            });
             const T a_aff = fmin(grp_min<T>(amax, mask), T(1));
             T mua_l = T(0);
-            for (int k = 0; k < N; k++)
-                if (has_box(k)) {
-                    const int e = k * 16 + lane, ei = k * 8 + bl;
-                    const T it_v = iter_at(k);
-                    const T lb = lo - it_v, ub = hi - it_v;
-                    const T zn = sDz[e];
-                    const T tl = wI[IPM_TL * FS + ei], tu = wI[IPM_TU * FS + ei];
-                    const T ll = wI[IPM_LL * FS + ei], lu = wI[IPM_LU * FS + ei];
-                    const T dtl = (zn - lb) - tl, dtu = (ub - zn) - tu;
-                    const T dll = -tdiv<T>(ll, tl) * dtl - ll, dlu = -tdiv<T>(lu, tu) * dtu - lu;
-                    mua_l += (ll + a_aff * dll) * (tl + a_aff * dtl) + (lu + a_aff * dlu) * (tu + a_aff * dtu);
-                }
+            box_loop([&](int k) {
+                const int e = k * 16 + lane, ei = k * 8 + bl;
+                const T it_v = iter_at(k);
+                const T lb = lo - it_v, ub = hi - it_v;
+                const T zn = sDz[e];
+                const T tl = wI[IPM_TL * FS + ei], tu = wI[IPM_TU * FS + ei];
+                const T ll = wI[IPM_LL * FS + ei], lu = wI[IPM_LU * FS + ei];
+                const T dtl = (zn - lb) - tl, dtu = (ub - zn) - tu;
+                const T dll = -tdiv<T>(ll, tl) * dtl - ll, dlu = -tdiv<T>(lu, tu) * dtu - lu;
+                mua_l += (ll + a_aff * dll) * (tl + a_aff * dtl) + (lu + a_aff * dlu) * (tu + a_aff * dtu);
+            });
             const T mu_aff = grp_sum<T>(mua_l, mask) * inv_m;
             const T sg = tdiv<T>(mu_aff, mu);
             const T sigma_mu = sg * sg * sg * mu;
             // ---- corrector ----
-            for (int k = 0; k < N; k++)
-                if (has_box(k)) {
-                    const int e = k * 16 + lane, ei = k * 8 + bl;
-                    const T tl = wI[IPM_TL * FS + ei], tu = wI[IPM_TU * FS + ei];
-                    const T cl = wI[IPM_CL * FS + ei], cu = wI[IPM_CU * FS + ei];
-                    // only the CHANGE of the barrier gradient against the predictor's: the weights bD stay, so the corrector
-                    // re-uses the predictor's factorisation (delta_backward) and adds its step to the affine one
-                    bG[ei] = tdiv<T>(sigma_mu - cu, tu) - tdiv<T>(sigma_mu - cl, tl);
-                }
+            box_loop([&](int k) {
+                const int e = k * 16 + lane, ei = k * 8 + bl;
+                const T tl = wI[IPM_TL * FS + ei], tu = wI[IPM_TU * FS + ei];
+                const T cl = wI[IPM_CL * FS + ei], cu = wI[IPM_CU * FS + ei];
+                // only the CHANGE of the barrier gradient against the predictor's: the weights bD stay, so the corrector
+                // re-uses the predictor's factorisation (delta_backward) and adds its step to the affine one
+                bG[ei] = tdiv<T>(sigma_mu - cu, tu) - tdiv<T>(sigma_mu - cl, tl);
+            });
             __syncwarp(mask);
             IPM_T(4);
             delta_backward<T>(c, N, lane, mask, ws, WL, rec, sTriv, bG);
@@ -1352,41 +1429,39 @@ __device__ __forceinline__ void constrained_qp(const RtiCfg<T>& c, int lane, uns
             forward_sweep<T, false>(c, N, lane, mask, T(0), sm, L, rec, WL, lo, hi, gX, gU, nullptr, viol, bad, nact_l, true, true, true);
             IPM_T(6);
             amax = T(1e30);
-            for (int k = 0; k < N; k++)
-                if (has_box(k)) {
-                    const int e = k * 16 + lane, ei = k * 8 + bl;
-                    const T it_v = iter_at(k);
-                    const T lb = lo - it_v, ub = hi - it_v;
-                    const T zn = sDz[e];
-                    const T tl = wI[IPM_TL * FS + ei], tu = wI[IPM_TU * FS + ei];
-                    const T ll = wI[IPM_LL * FS + ei], lu = wI[IPM_LU * FS + ei];
-                    const T cl = wI[IPM_CL * FS + ei], cu = wI[IPM_CU * FS + ei];
-                    const T dtl = (zn - lb) - tl, dtu = (ub - zn) - tu;
-                    const T dll = tdiv<T>(sigma_mu - cl - ll * dtl, tl) - ll;
-                    const T dlu = tdiv<T>(sigma_mu - cu - lu * dtu, tu) - lu;
-                    if (dtl < T(0)) amax = fmin(amax, tdiv<T>(-tl, dtl));
-                    if (dtu < T(0)) amax = fmin(amax, tdiv<T>(-tu, dtu));
-                    if (dll < T(0)) amax = fmin(amax, tdiv<T>(-ll, dll));
-                    if (dlu < T(0)) amax = fmin(amax, tdiv<T>(-lu, dlu));
-                }
+            box_loop([&](int k) {
+                const int e = k * 16 + lane, ei = k * 8 + bl;
+                const T it_v = iter_at(k);
+                const T lb = lo - it_v, ub = hi - it_v;
+                const T zn = sDz[e];
+                const T tl = wI[IPM_TL * FS + ei], tu = wI[IPM_TU * FS + ei];
+                const T ll = wI[IPM_LL * FS + ei], lu = wI[IPM_LU * FS + ei];
+                const T cl = wI[IPM_CL * FS + ei], cu = wI[IPM_CU * FS + ei];
+                const T dtl = (zn - lb) - tl, dtu = (ub - zn) - tu;
+                const T dll = tdiv<T>(sigma_mu - cl - ll * dtl, tl) - ll;
+                const T dlu = tdiv<T>(sigma_mu - cu - lu * dtu, tu) - lu;
+                if (dtl < T(0)) amax = fmin(amax, tdiv<T>(-tl, dtl));
+                if (dtu < T(0)) amax = fmin(amax, tdiv<T>(-tu, dtu));
+                if (dll < T(0)) amax = fmin(amax, tdiv<T>(-ll, dll));
+                if (dlu < T(0)) amax = fmin(amax, tdiv<T>(-lu, dlu));
+            });
             const T alpha = fmin(T(1), T(0.995) * grp_min<T>(amax, mask));
-            for (int k = 0; k < N; k++)
-                if (has_box(k)) {
-                    const int e = k * 16 + lane, ei = k * 8 + bl;
-                    const T it_v = iter_at(k);
-                    const T lb = lo - it_v, ub = hi - it_v;
-                    const T zn = sDz[e];
-                    const T tl = wI[IPM_TL * FS + ei], tu = wI[IPM_TU * FS + ei];
-                    const T ll = wI[IPM_LL * FS + ei], lu = wI[IPM_LU * FS + ei];
-                    const T cl = wI[IPM_CL * FS + ei], cu = wI[IPM_CU * FS + ei];
-                    const T dtl = (zn - lb) - tl, dtu = (ub - zn) - tu;
-                    const T dll = tdiv<T>(sigma_mu - cl - ll * dtl, tl) - ll;
-                    const T dlu = tdiv<T>(sigma_mu - cu - lu * dtu, tu) - lu;
-                    wI[IPM_TL * FS + ei] = fmax(tl + alpha * dtl, c.t_min);
-                    wI[IPM_TU * FS + ei] = fmax(tu + alpha * dtu, c.t_min);
-                    wI[IPM_LL * FS + ei] = fmax(ll + alpha * dll, c.t_min);
-                    wI[IPM_LU * FS + ei] = fmax(lu + alpha * dlu, c.t_min);
-                }
+            box_loop([&](int k) {
+                const int e = k * 16 + lane, ei = k * 8 + bl;
+                const T it_v = iter_at(k);
+                const T lb = lo - it_v, ub = hi - it_v;
+                const T zn = sDz[e];
+                const T tl = wI[IPM_TL * FS + ei], tu = wI[IPM_TU * FS + ei];
+                const T ll = wI[IPM_LL * FS + ei], lu = wI[IPM_LU * FS + ei];
+                const T cl = wI[IPM_CL * FS + ei], cu = wI[IPM_CU * FS + ei];
+                const T dtl = (zn - lb) - tl, dtu = (ub - zn) - tu;
+                const T dll = tdiv<T>(sigma_mu - cl - ll * dtl, tl) - ll;
+                const T dlu = tdiv<T>(sigma_mu - cu - lu * dtu, tu) - lu;
+                wI[IPM_TL * FS + ei] = fmax(tl + alpha * dtl, c.t_min);
+                wI[IPM_TU * FS + ei] = fmax(tu + alpha * dtu, c.t_min);
+                wI[IPM_LL * FS + ei] = fmax(ll + alpha * dll, c.t_min);
+                wI[IPM_LU * FS + ei] = fmax(lu + alpha * dlu, c.t_min);
+            });
             if (lane < 14) {
                 // (the iterate of the interior-point method stays in the workspace: four independent loads per round trip)
                 const int kn = isx ? N + 1 : N;

@@ -43,3 +43,7 @@ if hasattr(lib, "ndp_debug_rti_cprof"):
              "delta forward", "step length + update loops", "rounds from the IPM estimate"]
     for n, x in zip(names, v):
         print("%-32s %6.1f %%" % (n, 100 * x / v.sum()))
+    r = np.array(buf[110:113], dtype=np.float64)
+    for n, x in zip(["round: backward sweep", "round: forward sweep", "round: multipliers + set update"], r):
+        print("%-32s %6.1f %%   %8.0f cycles per round" % (n, 100 * x / r.sum(), x / max(buf[120], 1)))
+    print("rounds %d, backward stages per round %.1f" % (buf[120], buf[121] / max(buf[120], 1)))
