@@ -84,7 +84,7 @@ struct ndp_handle {
     long long ws_c_stride;
     int slots_c, grid_c;
     int* queue;                    // [B] problems handed from the nominal to the constrained kernel
-    int* qctl;                     // {count, head, done, pad}
+    int* qctl;                     // {count (back part), head, done, count (front part)}
     int timing;                    // ndp_kernel_timing: record events around the two kernels of every solve
     cudaEvent_t tev[3];
     size_t smem;
@@ -359,7 +359,7 @@ void ndp_default_config(ndp_config* c) {
     c->u_max[3] = 9.81 / 0.36;
     c->ipm_max_iter = 50;
     c->polish_max = 24;
-    c->active_set_first = 10;  // measured on the stress variant of config 3 (profiles/r2_stress_active_set_rounds.jsonl): the launch is as long as its
+    c->active_set_first = 8;   // measured on the stress variant of config 3 (profiles/r2_stress_active_set_rounds.jsonl): the launch is as long as its
                                // slowest problem, and a problem whose rounds have not settled by then is faster through the interior-point estimate
     c->active_set_warm = 0;
     c->ipm_tol_mu = 0.0;
