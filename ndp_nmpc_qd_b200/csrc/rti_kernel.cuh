@@ -488,15 +488,13 @@ __device__ __forceinline__ bool backward_stage(const RtiCfg<T>& c, int N, int k,
     // every lane; the elimination itself happens on the gathered 4x4 block below
     bool upin[4] = {false, false, false, false};
     T ubeta[4] = {T(0), T(0), T(0), T(0)};
+    bool pin = false, mine = false;  // kBar == 2: this lane's input is pinned at stage k / its velocity component at stage k + 1
+    T bnd = T(0);
     if (kBar == 2) {
         const bool at_lo = as->lo_m.test(k), at_hi = as->hi_m.test(k);
-        const bool pin = (j >= 10 && j < 14) && (at_lo || at_hi);
-        const T bnd = (at_lo ? as->lo : as->hi) - sU[k * NU + ((j - 10) & 3)];
-#pragma unroll
-        for (int m = 0; m < 4; m++) {
-            upin[m] = __shfl_sync(mask, (int)pin, 10 + m, GL) != 0;
-            ubeta[m] = __shfl_sync(mask, bnd, 10 + m, GL);
-        }
+        pin = (j >= 10 && j < 14) && (at_lo || at_hi);
+        bnd = (at_lo ? as->lo : as->hi) - sU[k * NU + ((j - 10) & 3)];
+        mine = (j >= 3 && j < 6) && (k + 1 < N) && (as->lo_m.test(k + 1) || as->hi_m.test(k + 1));
     } else if (kBar == 1) {
         // barrier diagonal / gradient of the boxed variables (velocities: slots 0..2, inputs: 3..6 of the stage's row)
         const T* sBD = sm + L.oIpm + 6 * N * 8;
@@ -515,11 +513,40 @@ __device__ __forceinline__ bool backward_stage(const RtiCfg<T>& c, int N, int k,
         }
     }
     // 4x4 input block G = Huu from lanes 10..13, Cholesky, solve for this lane's column
-    T g00 = __shfl_sync(mask, H[10], 10, GL), g10 = __shfl_sync(mask, H[11], 10, GL);
-    T g20 = __shfl_sync(mask, H[12], 10, GL), g30 = __shfl_sync(mask, H[13], 10, GL);
-    T g11 = __shfl_sync(mask, H[11], 11, GL), g21 = __shfl_sync(mask, H[12], 11, GL);
-    T g31 = __shfl_sync(mask, H[13], 11, GL), g22 = __shfl_sync(mask, H[12], 12, GL);
-    T g32 = __shfl_sync(mask, H[13], 12, GL), g33 = __shfl_sync(mask, H[13], 13, GL);
+    T g00, g10, g20, g30, g11, g21, g31, g22, g32, g33;
+    unsigned vpin_bits = 0u;  // kBar == 2: velocity components of stage k + 1 pinned (bit a)
+    if (kBar == 0) {
+        // nominal kernel: whole-warp lockstep under a compile-time mask -- bare shuffles
+        g00 = __shfl_sync(mask, H[10], 10, GL); g10 = __shfl_sync(mask, H[11], 10, GL);
+        g20 = __shfl_sync(mask, H[12], 10, GL); g30 = __shfl_sync(mask, H[13], 10, GL);
+        g11 = __shfl_sync(mask, H[11], 11, GL); g21 = __shfl_sync(mask, H[12], 11, GL);
+        g31 = __shfl_sync(mask, H[13], 11, GL); g22 = __shfl_sync(mask, H[12], 12, GL);
+        g32 = __shfl_sync(mask, H[13], 12, GL); g33 = __shfl_sync(mask, H[13], 13, GL);
+    } else {
+        // constrained kernel: the two halves of a warp diverge, so every shuffle on the run-time half mask is wrapped in a
+        // WARPSYNC ... ENDCOLLECTIVE pair (18 shuffles + a ballot per stage).  One exchange through shared memory instead:
+        // the Hux region is dead until this stage's rows are stored below.
+        T* sx = sHux;
+        if (j >= 10 && j < 14) {
+            Vec4<T>::st(sx + (j - 10) * 4, H[10], H[11], H[12], H[13]);
+            if (kBar == 2) { sx[16 + (j - 10)] = pin ? T(1) : T(0); sx[20 + (j - 10)] = bnd; }
+        }
+        if (kBar == 2 && j >= 3 && j < 6) sx[24 + (j - 3)] = mine ? T(1) : T(0);
+        __syncwarp(mask);
+        T t0, t1, t2, t3;
+        Vec4<T>::ld(sx, g00, g10, g20, g30);
+        Vec4<T>::ld(sx + 4, t0, g11, g21, g31);
+        Vec4<T>::ld(sx + 8, t0, t1, g22, g32);
+        Vec4<T>::ld(sx + 12, t0, t1, t2, g33);
+        if (kBar == 2) {
+            Vec4<T>::ld(sx + 16, t0, t1, t2, t3);
+            upin[0] = t0 != T(0); upin[1] = t1 != T(0); upin[2] = t2 != T(0); upin[3] = t3 != T(0);
+            Vec4<T>::ld(sx + 20, ubeta[0], ubeta[1], ubeta[2], ubeta[3]);
+            Vec4<T>::ld(sx + 24, t0, t1, t2, t3);
+            vpin_bits = (t0 != T(0) ? 1u : 0u) | (t1 != T(0) ? 2u : 0u) | (t2 != T(0) ? 4u : 0u);
+        }
+        __syncwarp(mask);
+    }
     const T hu0 = H[10], hu1 = H[11], hu2 = H[12], hu3 = H[13];  // un-eliminated rows of this column (what sHux keeps)
     if (kBar == 2) {
         // EXACT elimination of the pinned inputs: du_m = beta_m.  Their rows / columns leave the 4x4 block (identity
@@ -575,8 +602,7 @@ __device__ __forceinline__ bool backward_stage(const RtiCfg<T>& c, int N, int k,
     T tv0 = T(0), tv1 = T(0), tv2 = T(0);
     if (kBar == 2) {
         const int k1 = k + 1;
-        const bool mine = (j >= 3 && j < 6) && (k1 < N) && (as->lo_m.test(k1) || as->hi_m.test(k1));
-        const unsigned pins = (__ballot_sync(mask, mine) >> (((mask & 1u) ? 0 : 16) + 3)) & 7u;
+        const unsigned pins = vpin_bits;
         if (pins) {  // uniform over the group
             vpins = true;
             const T beta_own = mine ? ((as->lo_m.test(k1) ? as->lo : as->hi) - sX[k1 * NX + j]) : T(0);
