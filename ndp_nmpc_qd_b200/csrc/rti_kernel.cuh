@@ -929,7 +929,7 @@ __device__ __forceinline__ void forward_sweep(const RtiCfg<T>& c, int N, int lan
                                               const T* rec_base, const WsLayout& WL, T lo, T hi, T* gX, T* gU, T* gu0, bool& viol, bool& bad,
                                               int& nact, bool rezero_pads = true, bool zero_b = false, bool accum = false) {
     T* sDz = sm + L.oDz;
-    const bool isx = lane < 10, isu = (lane >= 10 && lane < 14), isv = (lane >= 3 && lane < 6);
+    const bool isx = lane < 10, isv = (lane >= 3 && lane < 6);
     const T* rec = rec_base + (long long)((lane < 14) ? lane : 13) * TLD;
     T z = isx ? dx0 : T(0);
     // one stage: consumes this lane's record cf, the iterate value it_cur (kFinal)
@@ -1324,7 +1324,7 @@ __device__ __forceinline__ void constrained_qp(const RtiCfg<T>& c, int lane, uns
             as.lo_m = StageMask(); as.hi_m = StageMask();
             for (int k = 0; k < N; k++)
                 if (has_box(k)) {
-                    const int e = k * 16 + lane, ei = k * 8 + bl;
+                    const int ei = k * 8 + bl;
                     if (wI[IPM_TL * FS + ei] < wI[IPM_LL * FS + ei]) as.lo_m.set(k);
                     else if (wI[IPM_TU * FS + ei] < wI[IPM_LU * FS + ei]) as.hi_m.set(k);
                 }
@@ -1383,7 +1383,7 @@ __device__ __forceinline__ void constrained_qp(const RtiCfg<T>& c, int lane, uns
             IPM_T(0);
             T mu_l = T(0);
             box_loop([&](int k) {
-                const int e = k * 16 + lane, ei = k * 8 + bl;
+                const int ei = k * 8 + bl;
                 const T it_v = iter_at(k);
                 const T lb = lo - it_v, ub = hi - it_v;
                 const T tl = wI[IPM_TL * FS + ei], tu = wI[IPM_TU * FS + ei];
@@ -1442,7 +1442,7 @@ __device__ __forceinline__ void constrained_qp(const RtiCfg<T>& c, int lane, uns
             const T sigma_mu = sg * sg * sg * mu;
             // ---- corrector ----
             box_loop([&](int k) {
-                const int e = k * 16 + lane, ei = k * 8 + bl;
+                const int ei = k * 8 + bl;
                 const T tl = wI[IPM_TL * FS + ei], tu = wI[IPM_TU * FS + ei];
                 const T cl = wI[IPM_CL * FS + ei], cu = wI[IPM_CU * FS + ei];
                 // only the CHANGE of the barrier gradient against the predictor's: the weights bD stay, so the corrector
