@@ -74,7 +74,7 @@ typedef struct ndp_config {
     int32_t polish_max;   /* active-set refinement rounds after the IPM  */
     double ipm_tol_mu;    /* IPM complementarity target (<=0: precision default) */
     int32_t active_set_first; /* active-set rounds tried from the unconstrained step's violated bounds before
-                               * the IPM (0: IPM first); both routes end at the same QP solution */
+                               * the IPM (0: IPM first; default 8); both routes end at the same QP solution */
     int32_t active_set_warm;  /* 1: a solve that ends with active input bounds leaves them as the first guess of the
                                * problem's next solve (skips the unconstrained sweep; fewer sweeps on average in
                                * saturated closed loops, but a stale guess can cost the slowest problem more rounds,
